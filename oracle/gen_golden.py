@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Usage:  python -m oracle.gen_golden
+
+Protocol: build `TreasurehuntWorld` + `TreasurehuntEnv` from /root/reference,
+swap each agent's IQN for the reference's own `RandomModel` (models/base_model.py:107-111) so only
+env + observation + buffer are exercised, call `set_seed(seed)` (utils/helpers.py:22-32)
+immediately before `env.reset()`, then run `take_turn()` and dump everything the engine must
+reproduce: per-turn kind-id grids, per-agent buffer arrays, rewards, positions, draw counts.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import shim  # noqa: E402
+
+shim.install()
+
+from sorrel.buffers import Buffer  # noqa: E402
+from sorrel.examples.treasurehunt.entities import EmptyEntity  # noqa: E402
+from sorrel.examples.treasurehunt.env import TreasurehuntEnv  # noqa: E402
+from sorrel.examples.treasurehunt.world import TreasurehuntWorld  # noqa: E402
+from sorrel.models.base_model import RandomModel  # noqa: E402
+from sorrel.utils.helpers import set_seed  # noqa: E402
+
+from oracle.recorder import DrawLog, record  # noqa: E402
+
+CLASS_IDS = {"EmptyEntity": 0, "Wall": 1, "Gem": 2, "Bone": 3, "Food": 4, "TreasurehuntAgent": 5, "Sand": 6}
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def grid_ids(world) -> np.ndarray:
+    H, W, L = world.map.shape
+    g = np.zeros((H, W, L), dtype=np.uint8)
+    for idx, e in np.ndenumerate(world.map):
+        g[idx] = CLASS_IDS[type(e).__name__]
+    return g
+
+
+def build(H, W, A, v, p, T):
+    config = {
+        "experiment": {"epochs": 1, "max_turns": T, "record_period": 50},
+        "model": {"agent_vision_radius": v, "epsilon_decay": 0.0005, "observation_spec": "onehot",
+                  "num_agents": A},
+        "world": {"height": H, "width": W, "gem_value": 10, "food_value": 5, "bone_value": -10,
+                  "spawn_prob": p},
+    }
+    world = TreasurehuntWorld(config=config, default_entity=EmptyEntity())
+    env = TreasurehuntEnv(world, config)
+    return world, env
+
+
+def run_case(name, seed, H, W, A, v, p, T, epochs=1, capacity=None, n_frames=1, sample_batch=0,
+             per_turn_grids=True):
+    world, env = build(H, W, A, v, p, T)
+    cap = capacity or T * epochs
+    for ag in env.agents:
+        m = RandomModel(ag.observation_spec.input_size, 4, cap)
+        # same construction the example uses for IQN's memory (env.py:100-102) + frame stacking
+        m.memory = Buffer(capacity=cap, obs_shape=tuple(ag.observation_spec.input_size), n_frames=n_frames)
+        m.memory.extra_data["positions"] = np.zeros((cap, 2), dtype=np.int64)
+        ag.model = m
+    log = DrawLog()
+    grids, starts, totals, cur_states, n_draws = [], [], [], [], []
+    samples = {}
+    with record(log):
+        set_seed(seed)
+        for ep in range(epochs):
+            env.reset()
+            starts.append([ag.location[:2] for ag in env.agents])
+            if n_frames > 1:
+                for ag in env.agents:  # iRainbowModel.start_epoch_action iqn.py:426-436
+                    ag.model.memory.add_empty()
+            for t in range(T):
+                env.take_turn()
+                if per_turn_grids:
+                    grids.append(grid_ids(world))
+                n_draws.append(len(log))
+                if n_frames > 1:
+                    cur_states.append(np.stack([ag.model.memory.current_state() for ag in env.agents]))
+            world.is_done = True  # environment.py:171
+            totals.append(world.total_reward)
+            if not per_turn_grids:
+                grids.append(grid_ids(world))
+        if sample_batch:
+            outs = [ag.model.memory.sample(sample_batch) for ag in env.agents]
+            sample_idx = [c[2] for c in log.calls if c[0] == "choice" and c[1][1] == sample_batch]
+            samples = {
+                "sample_idx": np.stack(sample_idx[-len(env.agents):]).astype(np.int64),
+                "sample_states": np.stack([o[0] for o in outs]),
+                "sample_actions": np.stack([o[1] for o in outs]),
+                "sample_rewards": np.stack([o[2] for o in outs]),
+                "sample_next_states": np.stack([o[3] for o in outs]),
+                "sample_dones": np.stack([o[4] for o in outs]),
+                "sample_valid": np.stack([o[5] for o in outs]),
+            }
+    mems = [ag.model.memory for ag in env.agents]
+    h = hashlib.sha256()
+    for b in mems:
+        for arr in (b.states, b.actions, b.rewards, b.dones, b.extra_data["positions"]):
+            h.update(arr.tobytes())
+    data = dict(
+        seed=seed, H=H, W=W, A=A, v=v, p=p, T=T, epochs=epochs, capacity=cap, n_frames=n_frames,
+        starts=np.array(starts, dtype=np.int64),
+        grids=np.array(grids, dtype=np.uint8),
+        total_reward=np.array(totals, dtype=np.float64),
+        states=np.stack([b.states for b in mems]),
+        actions=np.stack([b.actions for b in mems]),
+        rewards=np.stack([b.rewards for b in mems]),
+        dones=np.stack([b.dones for b in mems]),
+        positions=np.stack([b.extra_data["positions"] for b in mems]),
+        buf_idx=np.array([b.idx for b in mems]), buf_size=np.array([b.size for b in mems]),
+        n_draws=np.array(n_draws, dtype=np.int64),
+        n_uniform=np.int64(sum(1 for c in log.calls if c[0] == "random")),
+        n_spawn=np.int64(sum(1 for c in log.calls if c[0] == "choice_obj")),
+        buf_sha=h.hexdigest()[:16],
+        grid_sha=hashlib.sha256(grids[-1][:, :, 1].tobytes()).hexdigest()[:16],
+        **samples,
+    )
+    if cur_states:
+        data["current_states"] = np.array(cur_states, dtype=np.float32)
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **data)
+    print(f"{name}: total_reward={totals} buf_sha={data['buf_sha']} grid_sha={data['grid_sha']} "
+          f"draws={len(log)} -> {os.path.getsize(path)} B")
+
+
+def observe_cases():
+    """Direct OneHotObservationSpec.observe probes on random multi-layer worlds."""
+    from sorrel.entities import Entity
+    from sorrel.observation.observation_spec import OneHotObservationSpec
+    from sorrel.worlds import Gridworld
+
+    names = ["EmptyEntity", "Wall", "Gem", "Bone"]
+
+    def mk(kind):
+        e = Entity()
+        e.kind = kind
+        return e
+
+    rng = np.random.RandomState(1234)
+    cases = []
+    for _ in range(60):
+        H, W, L = rng.randint(5, 12), rng.randint(5, 12), rng.randint(1, 4)
+        v = rng.randint(1, min((H - 1) // 2, (W - 1) // 2) + 1)
+        world = Gridworld(H, W, L, mk("EmptyEntity"))
+        kinds = rng.randint(0, 4, size=(H, W, L)).astype(np.uint8)
+        for idx in np.ndindex(H, W, L):
+            world.add(idx, mk(names[kinds[idx]]))
+        spec = OneHotObservationSpec(names, full_view=False, vision_radius=int(v))
+        for _ in range(5):
+            y, x = rng.randint(0, H), rng.randint(0, W)
+            obs = spec.observe(world, (y, x, 0))
+            cases.append((kinds, int(v), int(y), int(x), obs))
+    np.savez_compressed(
+        os.path.join(OUT, "observe_cases.npz"),
+        n=len(cases),
+        **{f"kinds_{i}": c[0] for i, c in enumerate(cases)},
+        **{f"meta_{i}": np.array(c[1:4]) for i, c in enumerate(cases)},
+        **{f"obs_{i}": c[4] for i, c in enumerate(cases)},
+    )
+    print(f"observe_cases: {len(cases)} cases")
+
+
+def main():
+    run_case("kat1_s0_a1_21", 0, 21, 21, 1, 2, 0.005, 100)
+    run_case("kat2_s0_a8_21", 0, 21, 21, 8, 2, 0.005, 100)
+    run_case("kat3_s7_a2_11", 7, 11, 11, 2, 2, 0.05, 50)
+    for s in range(1, 7):
+        run_case(f"c1_s{s}_a1_21", s, 21, 21, 1, 2, 0.005, 100)
+    run_case("dense_s3_a3_7", 3, 7, 7, 3, 3, 0.2, 40)  # v = (H-1)//2: heavy out-of-bounds fill
+    run_case("crowd_s5_a12_8", 5, 8, 8, 12, 1, 0.1, 60)  # 12 agents on 36 cells: many conflicts
+    run_case("mid_s2_a8_32", 2, 32, 32, 8, 4, 0.005, 30)
+    run_case("rect_s9_a4_9x15", 9, 9, 15, 4, 3, 0.03, 50)
+    # ring wrap + add_empty + current_state + sample: 3 epochs, capacity 64 < 3*(40+4), F=5
+    run_case("ring_s11_a2_11", 11, 11, 11, 2, 2, 0.05, 40, epochs=3, capacity=64, n_frames=5,
+             sample_batch=16)
+    run_case("ring_s12_a1_21", 12, 21, 21, 1, 2, 0.005, 100, epochs=2, capacity=256, n_frames=5,
+             sample_batch=64)
+    run_case("large_s4_a64_128", 4, 128, 128, 64, 4, 0.005, 2, per_turn_grids=False)
+    observe_cases()
+
+
+if __name__ == "__main__":
+    main()
