@@ -1,0 +1,242 @@
+/*
+ * sorrel_b200.h -- C ABI of the B200-native batched gridworld engine.
+ *
+ * One shared library (libsorrel_b200.so, sm_100a only) implements the environment-step /
+ * one-hot observation / replay-buffer hot path of social-ai-uoft/sorrel v1.4.0 for N
+ * independent world instances per call.  The reference has no FFI: its boundary is a set of
+ * Python methods.  Each entry point below names the reference method(s) it replaces
+ * (file:line relative to the reference root); INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - plain C types, pointers and sizes only; no C++/torch types.
+ *  - every pointer named `d_*` or living in a struct documented "device" is a DEVICE pointer on
+ *    the current CUDA device, owned by the caller (PyTorch); the library allocates nothing
+ *    persistent, keeps no global state and never frees caller memory.
+ *  - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*).
+ *  - return value: 0 (SB_OK) or a negative SbStatus; never throws, never exits.
+ *  - kernel-side invariant violations (an agent stepping off the grid, a replay tape that does
+ *    not line up with the cells that drew) set bits in the caller-provided device error word.
+ */
+#ifndef SORREL_B200_H
+#define SORREL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1
+
+#define SB_MAX_KINDS 32    /* entity classes per world (kind ids are uint8 < SB_MAX_KINDS) */
+#define SB_MAX_CHANNELS 32 /* observation channels C = len(entity_list) */
+#define SB_MAX_LAYERS 8
+#define SB_MAX_CHOICES 8 /* kinds a spawn rule can choose from */
+#define SB_MAX_ACTIONS 8
+#define SB_MAX_AGENTS 64 /* agents per world instance */
+#define SB_PAD_KIND 0xFF /* value of the padding bytes after each H*W plane */
+
+typedef enum SbStatus {
+  SB_OK = 0,
+  SB_EINVAL = -1,       /* NULL / negative / inconsistent argument            -> ValueError  */
+  SB_EUNSUPPORTED = -2, /* shape outside what the kernels implement            -> ValueError  */
+  SB_EALIGN = -3,       /* pointer not 16-byte aligned                         -> ValueError  */
+  SB_ECUDA = -4,        /* CUDA runtime / launch error (sb_last_cuda_error)    -> RuntimeError */
+  SB_ENODEVICE = -5,    /* no sm_100 device visible                            -> RuntimeError */
+  SB_EVISION = -6       /* vision radius > (H-1)/2 or (W-1)/2: the reference silently returns a
+                           wrong-shaped crop there (visual_field.py:78-87)     -> ValueError  */
+} SbStatus;
+
+/* bits of the device error word */
+#define SB_ERR_OFFGRID 1u   /* agent moved outside [0,H)x[0,W): numpy index wrap / IndexError in
+                               the reference (gridworld.py:95-122 with a negative index) */
+#define SB_ERR_TAPE_ALIGN 2u /* replay: a cell drew a uniform where the tape holds NaN */
+#define SB_ERR_BAD_ACTION 4u /* action outside [0, num_actions) */
+#define SB_ERR_BAD_KIND 8u   /* grid byte >= num_kinds */
+
+/* transition rules (per kind) */
+#define SB_RULE_NONE 0
+#define SB_RULE_SPAWN 1 /* Bernoulli(spawn_prob) -> uniform choice among spawn_choice_kinds;
+                           EmptyEntity.transition, examples/treasurehunt/entities.py:69-85 */
+
+/* sources of randomness / actions for sb_step */
+#define SB_RNG_TAPE 0   /* replay recorded numpy draws: bit-exact to the reference */
+#define SB_RNG_PHILOX 1 /* counter-based Philox4x32-10 keyed by (seed, global env id, tick) */
+#define SB_POLICY_TAPE 0    /* actions supplied by the caller */
+#define SB_POLICY_UNIFORM 1 /* in-kernel uniform policy == RandomModel, models/base_model.py:107 */
+
+/* Philox counter word 3 ("domain"); word0 = global env id, word1 = tick, word2 = index */
+#define SB_DOM_SWEEP 0x53570000u  /* index = cell >> 4 : 16 cells per call, one byte each */
+#define SB_DOM_CELL 0x43450000u   /* index = cell      : 45 refinement bits + 64 choice bits */
+#define SB_DOM_ACTION 0x41430000u /* index = agent     : 64 action bits */
+#define SB_DOM_RESET 0x52530000u  /* index = try       : 64 placement bits */
+
+/*
+ * World family description (host memory, copied by value at every call).
+ *
+ * Replaces the per-object state of Gridworld / Entity (sorrel/worlds/gridworld.py:36-65,
+ * sorrel/entities/entity.py:9-68): a *kind* is an entity class; its `value`, `passable`,
+ * transition rule and appearance row live in tables indexed by a uint8 kind id.
+ *
+ * Grid memory: uint8 d_grid[num_envs][num_dyn_layers][plane_stride], plane_stride =
+ * sb_plane_stride(H, W) = H*W rounded up to 16, padding bytes = SB_PAD_KIND.  Only layers that
+ * can change are stored per instance ("dynamic"); static layers are read from d_template.
+ */
+typedef struct SbWorldDesc {
+  int32_t abi_version; /* SB_ABI_VERSION */
+  int32_t num_envs;    /* N: world instances owned by this rank */
+  int32_t num_agents;  /* A per instance (Environment.agents, environment.py:31-54) */
+  int32_t height, width, num_layers; /* Gridworld(height,width,layers,...) gridworld.py:36 */
+  int32_t num_dyn_layers;
+  int32_t dyn_layers[SB_MAX_LAYERS]; /* layer index of each dynamic plane, ascending */
+  int32_t agent_layer;               /* layer the agents live on (must be dynamic) */
+  int32_t num_kinds;
+  int32_t num_channels;              /* C */
+  int32_t vision;                    /* v; S = 2v+1 (ObservationSpec.vision_radius) */
+  int32_t fill_kind;                 /* ObservationSpec.fill_entity_kind ("Wall") */
+  int32_t agent_kind;
+  int32_t default_kind;              /* Gridworld.default_entity: what a vacated cell becomes */
+  int32_t num_actions;               /* ActionSpec.n_actions, action/action_spec.py:4-47 */
+  int8_t action_dy[SB_MAX_ACTIONS];  /* MovingAgent.movement agents/agent.py:187-213 */
+  int8_t action_dx[SB_MAX_ACTIONS];
+  int32_t num_spawn_choices;
+  uint8_t spawn_choice_kinds[SB_MAX_CHOICES]; /* order of the choice array, entities.py:77-81 */
+  double spawn_prob;                 /* world.spawn_prob, treasurehunt/world.py:29 */
+  uint64_t env_id_base;              /* global id of instance 0 (rank offset; shard invariance) */
+  float kind_value[SB_MAX_KINDS];    /* Entity.value */
+  uint8_t kind_passable[SB_MAX_KINDS];
+  uint8_t kind_rule[SB_MAX_KINDS];
+  const double* d_appearance; /* device [num_kinds][C]: ObservationSpec.entity_map rows */
+  const double* h_appearance; /* HOST copy of the same table (lets the library pick the one-hot
+                                 fast path without a device read) */
+  const uint8_t* d_template;  /* device [num_layers][plane_stride]: world after
+                                 populate_environment, before agents are placed */
+  int32_t static_layers_invisible; /* 1 when every kind on a static layer has an all-zero
+                                      appearance row (treasurehunt Sand, entities.py:23-31) */
+  int32_t reserved0;
+} SbWorldDesc;
+
+/*
+ * Batched replay ring: one reference `Buffer` (sorrel/buffers.py:11-44) per agent row,
+ * rows = num_envs * num_agents, row r = env * A + agent.  `idx`/`size` are host scalars shared
+ * by all rows (every agent adds exactly one experience per turn).
+ *   states    float  [rows][capacity][obs_size]  (row-major per agent: frame stacks contiguous)
+ *   actions   int64  [capacity][rows]
+ *   rewards   float  [capacity][rows]
+ *   dones     float  [capacity][rows]
+ *   positions int64  [capacity][rows][2]         (extra_data["positions"], treasurehunt/env.py:100)
+ */
+typedef struct SbBufferDesc {
+  int32_t capacity;
+  int32_t obs_size; /* C*S*S floats */
+  int32_t n_frames;
+  int32_t reserved;
+  int64_t rows;
+  float* d_states;
+  int64_t* d_actions;
+  float* d_rewards;
+  float* d_dones;
+  int64_t* d_positions; /* may be NULL */
+} SbBufferDesc;
+
+/* sb_step modes */
+#define SB_MODE_FUSED 0 /* per turn: sweep; for each agent in list order: observe, act, record */
+#define SB_MODE_SPLIT 1 /* one launch = [sweep] -> [act agent act_agent] -> [observe agent obs_agent];
+                           lets a live policy run between observe(k) and act(k) */
+
+typedef struct SbStepArgs {
+  int32_t mode;      /* SB_MODE_* */
+  int32_t num_turns; /* T >= 1 turns per launch (FUSED); must be 1 for SPLIT */
+  uint32_t tick0;    /* global turn counter of the first turn (Philox counter word 1) */
+  int32_t slot0;     /* ring slot (Buffer.idx) the first turn writes */
+  int32_t rng;       /* SB_RNG_* */
+  int32_t policy;    /* SB_POLICY_* */
+  uint64_t seed;     /* Philox key */
+  int32_t do_sweep;  /* SPLIT: run the entity sweep in this launch */
+  int32_t act_agent; /* SPLIT: agent index to act, or -1 */
+  int32_t obs_agent; /* SPLIT: agent index to observe, or -1 */
+  int32_t reserved;
+  const int32_t* d_actions;  /* [T][N][A]   (policy TAPE / SPLIT act) */
+  const double* d_spawn_u;   /* [T][N][Ldyn*H*W] f64, NaN where the reference drew nothing */
+  const uint8_t* d_spawn_c;  /* [T][N][Ldyn*H*W] index into spawn_choice_kinds, 255 = none */
+  float* d_obs_out;          /* optional [T][N][A][obs_size] (when no ring is attached) */
+  float* d_reward_out;       /* optional [T][N][A] */
+  int32_t* d_action_out;     /* optional [T][N][A] actions actually taken */
+  uint8_t* d_drew_out;       /* optional [T][N][Ldyn*H*W] 1 where a cell consumed a uniform */
+  uint32_t* d_error;         /* device error word (OR of SB_ERR_*) */
+} SbStepArgs;
+
+/* -- library / geometry ------------------------------------------------------------------ */
+int sb_abi_version(void);
+const char* sb_strerror(int status);
+/* text of the last CUDA error seen by the calling thread (for SB_ECUDA) */
+const char* sb_last_cuda_error(void);
+/* number of CUDA kernels this library has launched in the calling process (bench "gpu_launches") */
+uint64_t sb_launch_count(void);
+int32_t sb_plane_stride(int32_t height, int32_t width);
+/* bytes of d_grid for a descriptor */
+size_t sb_grid_bytes(const SbWorldDesc* desc);
+/* validate a descriptor without touching the device (shape limits, vision rule) */
+int sb_validate(const SbWorldDesc* desc);
+
+/* -- Environment.reset + populate_environment -------------------------------------------- *
+ * environment.py:72-79 -> examples/treasurehunt/env.py:114-147: copy the template into every
+ * instance, place the A agents on distinct cells of the spawnable list, zero total_reward.
+ *   d_spawnable  int32 [n_spawnable]  plane cell index (y*W+x) on the agent layer, reference order
+ *   d_placement  int32 [N][A] indices into the spawnable list (replayed np.random.choice), or
+ *                NULL to draw them in-kernel from Philox (seed, env id, tick, SB_DOM_RESET)
+ */
+int sb_reset(const SbWorldDesc* desc, uint8_t* d_grid, int32_t* d_agent_pos, double* d_total_reward,
+             const int32_t* d_spawnable, int32_t n_spawnable, const int32_t* d_placement,
+             uint64_t seed, uint32_t tick, void* stream);
+
+/* -- Environment.take_turn ---------------------------------------------------------------- *
+ * environment.py:81-93 (entity sweep -> EmptyEntity.transition treasurehunt/entities.py:69-85;
+ * then Agent.transition agents/agent.py:155-173 = pov/observe -> action -> act/move -> reward ->
+ * Buffer.add) for all N instances, `num_turns` turns per launch.
+ *   d_agent_pos    int32 [N][A] plane cell index of every agent
+ *   d_total_reward f64   [N]    world.total_reward
+ *   buf            ring the observations/experiences are written into, or NULL
+ */
+int sb_step(const SbWorldDesc* desc, const SbStepArgs* args, uint8_t* d_grid, int32_t* d_agent_pos,
+            double* d_total_reward, const SbBufferDesc* buf, void* stream);
+
+/* -- ObservationSpec.observe -------------------------------------------------------------- *
+ * observation/observation_spec.py:175-205 -> visual_field.py:9-101 for every (instance, agent):
+ * d_obs_out float [N][A][C][S][S].  Pure function of the grid; does not modify state.
+ */
+int sb_observe(const SbWorldDesc* desc, const uint8_t* d_grid, const int32_t* d_agent_pos,
+               float* d_obs_out, void* stream);
+
+/* -- Buffer.add (buffers.py:46-63) for all rows at ring slot `slot` ------------------------ */
+int sb_buffer_add(const SbBufferDesc* buf, int32_t slot, const float* d_obs, const int64_t* d_actions,
+                  const float* d_rewards, const float* d_dones, const int64_t* d_positions,
+                  void* stream);
+
+/* -- Buffer.sample gather (buffers.py:112-124) --------------------------------------------- *
+ * sample b reads frames [start_b, start_b + n_frames] of row row_b.  Index draws
+ * (buffers.py:109-111) are the caller's.  Outputs: states/next_states float [B][F*obs],
+ * actions int64 [B], rewards/dones float [B], valid double [B].
+ */
+int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts,
+                     int32_t batch, float* d_states, int64_t* d_actions, float* d_rewards,
+                     float* d_next_states, float* d_dones, double* d_valid, void* stream);
+
+/* -- Buffer.current_state (buffers.py:143-154): rows [idx-(F-1), idx) with ring wrap --------- *
+ * d_out float [rows][F-1][obs_size]
+ */
+int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, void* stream);
+
+/* -- per-episode reward statistics (feeds Logger.record_turn, utils/logging.py:48-72) ------- *
+ * d_out double[5] = {sum, sum of squares, min, max, count} over d_total_reward[0..n); the only
+ * quantity that is all-reduced across ranks (NCCL, by the caller).  d_scratch: >= sb_stats_scratch_bytes().
+ */
+size_t sb_stats_scratch_bytes(void);
+int sb_reward_stats(const double* d_total_reward, int64_t n, double* d_out, void* d_scratch,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SORREL_B200_H */

@@ -1,0 +1,222 @@
+"""Device-resident batched replay buffer with the reference `Buffer` API.
+
+Mirrors `sorrel.buffers.Buffer` (sorrel/buffers.py:11-201): same constructor arguments, attribute
+names, dtypes (states f32, actions i64, rewards/dones f32, extra_data i64), the same `idx`/`size`
+bookkeeping including the quirks (`add_empty` advances by n_frames-1 without zeroing, buffers.py:65-69;
+`sample` ignores the write head, buffers.py:109-111), but holds ONE ring per agent row for
+`rows = num_envs * num_agents` agents that all advance in lock-step:
+
+    states    float32 [rows, capacity, *obs_shape]   one reference Buffer.states per row
+    actions   int64   [capacity, rows]               actions[:, r] is row r's Buffer.actions
+    rewards   float32 [capacity, rows]
+    dones     float32 [capacity, rows]
+    extra_data["positions"] int64 [capacity, rows, 2]
+
+`rows=1` reproduces a single reference buffer.  All data movement is done by the CUDA kernels
+behind `sb_buffer_add / sb_buffer_sample / sb_buffer_current_state`; the environment step writes
+observations straight into `states` (no separate observation tensor, no copy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import SbBufferDesc, check, lib
+
+
+class Buffer:
+    def __init__(self, capacity: int, obs_shape: Sequence[int], n_frames: int = 1, rows: int = 1,
+                 device: torch.device | str = "cuda", **kwargs):
+        self.lib = lib()
+        self.capacity = int(capacity)
+        self.obs_shape = tuple(int(x) for x in obs_shape)
+        self.obs_size = int(np.prod(self.obs_shape))
+        self.n_frames = int(n_frames)
+        self.rows = int(rows)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _abi.SorrelB200Error("sorrel_b200.Buffer lives on a CUDA device (no CPU fallback)")
+        self.extra_data: dict[str, torch.Tensor] = {}
+        self._alloc()
+        for key, value in kwargs.items():  # buffers.py:38-44
+            shape = (self.capacity, self.rows, *value) if isinstance(value, tuple) else (self.capacity, self.rows)
+            self.extra_data[key] = torch.zeros(shape, dtype=torch.int64, device=self.device)
+        self.idx = 0
+        self.size = 0
+        self._desc = None
+
+    def _alloc(self):
+        dev = self.device
+        self.states = torch.zeros((self.rows, self.capacity, *self.obs_shape), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((self.capacity, self.rows), dtype=torch.int64, device=dev)
+        self.rewards = torch.zeros((self.capacity, self.rows), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((self.capacity, self.rows), dtype=torch.float32, device=dev)
+        self._desc = None
+
+    # -- C ABI view ---------------------------------------------------------------------------
+    def desc(self) -> SbBufferDesc:
+        if self._desc is None:
+            d = SbBufferDesc()
+            d.capacity, d.obs_size, d.n_frames, d.rows = self.capacity, self.obs_size, self.n_frames, self.rows
+            d.d_states = self.states.data_ptr()
+            d.d_actions = self.actions.data_ptr()
+            d.d_rewards = self.rewards.data_ptr()
+            d.d_dones = self.dones.data_ptr()
+            pos = self.extra_data.get("positions")
+            d.d_positions = pos.data_ptr() if pos is not None else None
+            self._desc = d
+        return self._desc
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def advance(self, turns: int) -> None:
+        """idx/size bookkeeping of `turns` consecutive add()s (buffers.py:62-63)."""
+        self.idx = (self.idx + turns) % self.capacity
+        self.size = min(self.size + turns, self.capacity)
+
+    # -- reference API -------------------------------------------------------------------------
+    def add(self, obs, action, reward, done, **kwargs) -> None:
+        """Buffer.add (buffers.py:46-63) for every row at once.
+
+        obs [rows, *obs_shape] f32, action [rows] i64, reward [rows] f32, done [rows] f32 (device
+        tensors; scalars/arrays are converted), positions=[rows, 2] i64."""
+        dev = self.device
+
+        def t(x, dtype, shape):
+            x = torch.as_tensor(x, dtype=dtype, device=dev)
+            return x.expand(shape).contiguous() if x.shape != shape else x.contiguous()
+
+        obs = t(obs, torch.float32, (self.rows, self.obs_size)) if torch.as_tensor(obs).dim() <= 2 else \
+            torch.as_tensor(obs, dtype=torch.float32, device=dev).reshape(self.rows, self.obs_size).contiguous()
+        action = t(action, torch.int64, (self.rows,))
+        reward = t(reward, torch.float32, (self.rows,))
+        done = t(done, torch.float32, (self.rows,))
+        pos = kwargs.get("positions")
+        if pos is not None and "positions" in self.extra_data:
+            pos = t(pos, torch.int64, (self.rows, 2))
+        else:
+            pos = None
+        self._desc = None if self._desc is None else self._desc
+        check(self.lib.sb_buffer_add(C.byref(self.desc()), self.idx, obs.data_ptr(), action.data_ptr(),
+                                     reward.data_ptr(), done.data_ptr(),
+                                     pos.data_ptr() if pos is not None else None, self._stream()),
+              "sb_buffer_add")
+        for key, value in kwargs.items():  # other extra_data keys: plain slot write
+            if key != "positions" and key in self.extra_data:
+                self.extra_data[key][self.idx] = torch.as_tensor(value, dtype=torch.int64, device=dev)
+        self.advance(1)
+
+    def add_empty(self) -> None:
+        """buffers.py:65-69: advance the head by n_frames-1, rows are NOT zeroed."""
+        self.idx = (self.idx + self.n_frames - 1) % self.capacity
+        self.size = min(self.size + 1, self.capacity)
+
+    def sample_indices(self, batch_size: int, rows: torch.Tensor | np.ndarray | None = None):
+        """The index draw of Buffer.sample (buffers.py:109-111), batched.
+
+        Start slots come from `np.random.choice(max(1, size - n_frames - 1), batch_size,
+        replace=False)` -- the very call (and numpy global stream) the reference uses, so a
+        single-row buffer seeded like the reference samples the same transitions.  Rows are
+        uniform over agents unless given."""
+        starts = np.random.choice(max(1, self.size - self.n_frames - 1), batch_size, replace=False)
+        if rows is None:
+            rows = np.zeros(batch_size, dtype=np.int64) if self.rows == 1 else \
+                np.random.randint(0, self.rows, size=batch_size)
+        return np.asarray(rows, dtype=np.int64), starts.astype(np.int64)
+
+    def gather(self, rows, starts):
+        """Buffer.sample's gather (buffers.py:112-124) for (row, start) pairs; device tensors in
+        the reference's shapes/dtypes: states (B, F*obs) f32, actions (B,1) i64, rewards (B,1) f32,
+        next_states (B, F*obs) f32, dones (B,1) f32, valid (B,1) f64."""
+        dev = self.device
+        rows = torch.as_tensor(rows, dtype=torch.int64, device=dev).contiguous()
+        starts = torch.as_tensor(starts, dtype=torch.int64, device=dev).contiguous()
+        B = int(rows.numel())
+        F = self.n_frames
+        states = torch.empty((B, F * self.obs_size), dtype=torch.float32, device=dev)
+        next_states = torch.empty((B, F * self.obs_size), dtype=torch.float32, device=dev)
+        actions = torch.empty((B, 1), dtype=torch.int64, device=dev)
+        rewards = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        dones = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        valid = torch.empty((B, 1), dtype=torch.float64, device=dev)
+        check(self.lib.sb_buffer_sample(C.byref(self.desc()), rows.data_ptr(), starts.data_ptr(), B,
+                                        states.data_ptr(), actions.data_ptr(), rewards.data_ptr(),
+                                        next_states.data_ptr(), dones.data_ptr(), valid.data_ptr(),
+                                        self._stream()), "sb_buffer_sample")
+        return states, actions, rewards, next_states, dones, valid
+
+    def sample(self, batch_size: int):
+        """Buffer.sample (buffers.py:98-124).  Raises ValueError when batch_size exceeds the
+        population, like np.random.choice(replace=False) does in the reference."""
+        rows, starts = self.sample_indices(batch_size)
+        return self.gather(rows, starts)
+
+    def clear(self) -> None:
+        """buffers.py:126-133 (extra_data is left untouched, as in the reference)."""
+        self._alloc()
+        self.idx = 0
+        self.size = 0
+
+    def getidx(self) -> int:
+        return self.idx
+
+    def current_state(self) -> torch.Tensor:
+        """buffers.py:143-154: the last n_frames-1 observations before the write head, per row:
+        float32 [rows, n_frames-1, *obs_shape].  A zero-copy view unless the window wraps."""
+        F1 = self.n_frames - 1
+        if self.idx >= F1:
+            return self.states[:, self.idx - F1: self.idx]
+        out = torch.empty((self.rows, F1, *self.obs_shape), dtype=torch.float32, device=self.device)
+        check(self.lib.sb_buffer_current_state(C.byref(self.desc()), self.idx, out.data_ptr(), self._stream()),
+              "sb_buffer_current_state")
+        return out
+
+    def __repr__(self):
+        return f"Buffer(capacity={self.capacity}, obs_shape={self.obs_shape}, rows={self.rows})"
+
+    __str__ = __repr__
+
+    def __len__(self):
+        return self.size
+
+    def __getitem__(self, idx):
+        return (self.states[:, idx], self.actions[idx], self.rewards[idx], self.dones[idx])
+
+    def row(self, r: int) -> dict[str, np.ndarray]:
+        """Row r as host arrays laid out exactly like one reference Buffer."""
+        out = {
+            "states": self.states[r].cpu().numpy(),
+            "actions": self.actions[:, r].cpu().numpy(),
+            "rewards": self.rewards[:, r].cpu().numpy(),
+            "dones": self.dones[:, r].cpu().numpy(),
+        }
+        for k, v in self.extra_data.items():
+            out[k] = v[:, r].cpu().numpy()
+        return out
+
+    def save(self, output_file: str | Path, row: int = 0) -> None:
+        """Buffer.save (buffers.py:168-178): same .npz keys, one row."""
+        r = self.row(row)
+        np.savez_compressed(Path(output_file), states=r["states"], actions=r["actions"], rewards=r["rewards"],
+                            dones=r["dones"], n_frames=self.n_frames, idx=self.idx)
+
+    @classmethod
+    def load(cls, input_file: str | Path, device: torch.device | str = "cuda") -> "Buffer":
+        """Buffer.load (buffers.py:180-201) into a single-row device buffer."""
+        with np.load(Path(input_file)) as data:
+            states, actions = data["states"], data["actions"]
+            out = cls(capacity=len(actions), obs_shape=states.shape[1:], n_frames=int(data["n_frames"]),
+                      rows=1, device=device)
+            out.states[0].copy_(torch.from_numpy(states))
+            out.actions[:, 0].copy_(torch.from_numpy(actions))
+            out.rewards[:, 0].copy_(torch.from_numpy(data["rewards"]))
+            out.dones[:, 0].copy_(torch.from_numpy(data["dones"]))
+            out.idx = int(data["idx"])
+            out.size = len(states)
+        return out

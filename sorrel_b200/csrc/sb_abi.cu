@@ -1,0 +1,521 @@
+// sb_abi.cu -- extern "C" entry points of libsorrel_b200.so (see include/sorrel_b200.h):
+// argument validation, derivation of the device-side world view, and the small kernels that do
+// not live in sb_step.cu (reset, replay-ring add / sample / current_state, reward statistics).
+#include <atomic>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sb_internal.h"
+
+namespace sb {
+
+static thread_local char g_cuda_err[256] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int note_cuda_error() {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaPeekAtLastError();
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", cudaGetErrorString(e));
+  return SB_ECUDA;
+}
+static int note_cuda_error(cudaError_t e) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", cudaGetErrorString(e));
+  return SB_ECUDA;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ceil(p * 2^53): `u < p` for u = k / 2^53 (numpy random_sample) <=> k < threshold
+static uint64_t spawn_threshold(double p) {
+  if (!(p > 0.0)) return 0;
+  if (p >= 1.0) return 1ull << 53;
+  return (uint64_t)ceil(ldexp(p, 53));
+}
+
+int make_dev(const SbWorldDesc* w, SbDev* out) {
+  if (!w || !out) return SB_EINVAL;
+  if (w->abi_version != SB_ABI_VERSION) return SB_EINVAL;
+  if (w->num_envs <= 0 || w->num_agents <= 0 || w->height <= 0 || w->width <= 0) return SB_EINVAL;
+  if (w->num_layers <= 0 || w->num_layers > SB_MAX_LAYERS) return SB_EUNSUPPORTED;
+  if (w->num_dyn_layers <= 0 || w->num_dyn_layers > w->num_layers) return SB_EINVAL;
+  if (w->num_agents > SB_MAX_AGENTS) return SB_EUNSUPPORTED;
+  if (w->num_kinds <= 0 || w->num_kinds > SB_MAX_KINDS) return SB_EUNSUPPORTED;
+  if (w->num_channels <= 0 || w->num_channels > SB_MAX_CHANNELS) return SB_EUNSUPPORTED;
+  if (w->height > 4096 || w->width > 4096) return SB_EUNSUPPORTED;
+  if (w->vision < 0) return SB_EINVAL;
+  // visual_field.py:78-87 returns a wrong-shaped crop beyond this
+  if (w->vision > (w->height - 1) / 2 || w->vision > (w->width - 1) / 2) return SB_EVISION;
+  if (w->vision > 10) return SB_EUNSUPPORTED;  // window index is 9 bits in the kernel LUT
+  if (w->num_actions <= 0 || w->num_actions > SB_MAX_ACTIONS) return SB_EUNSUPPORTED;
+  if (w->num_spawn_choices < 0 || w->num_spawn_choices > SB_MAX_CHOICES) return SB_EUNSUPPORTED;
+  auto kind_ok = [&](int k) { return k >= 0 && k < w->num_kinds; };
+  if (!kind_ok(w->fill_kind) || !kind_ok(w->agent_kind) || !kind_ok(w->default_kind)) return SB_EINVAL;
+  if (!(w->spawn_prob >= 0.0) || w->spawn_prob > 1.0) return SB_EINVAL;
+  if (!w->d_appearance || !w->h_appearance || !w->d_template) return SB_EINVAL;
+  if (w->env_id_base + (uint64_t)w->num_envs > 0xFFFFFFFFull) return SB_EUNSUPPORTED;
+
+  SbDev d;
+  memset(&d, 0, sizeof(d));
+  d.N = w->num_envs;
+  d.A = w->num_agents;
+  d.H = w->height;
+  d.W = w->width;
+  d.HW = d.H * d.W;
+  d.plane_stride = sb_plane_stride(d.H, d.W);
+  d.n_planes = w->num_dyn_layers;
+  d.env_stride = d.n_planes * d.plane_stride;
+  if (d.env_stride >= (1 << 20)) return SB_EUNSUPPORTED;  // cell id is 20 bits in the spawn queue
+  d.n_chunks = d.env_stride / 16;
+  d.L = w->num_layers;
+  for (int z = 0; z < SB_MAX_LAYERS; ++z) d.plane_of_layer[z] = -1;
+  d.agent_plane = -1;
+  int prev = -1;
+  for (int pl = 0; pl < d.n_planes; ++pl) {
+    int z = w->dyn_layers[pl];
+    if (z <= prev || z >= d.L) return SB_EINVAL;
+    prev = z;
+    d.plane_of_layer[z] = pl;
+    if (z == w->agent_layer) d.agent_plane = pl;
+  }
+  if (d.agent_plane < 0) return SB_EINVAL;
+  d.K = w->num_kinds;
+  d.C = w->num_channels;
+  d.v = w->vision;
+  d.S = 2 * d.v + 1;
+  d.SS = d.S * d.S;
+  d.obs_size = d.C * d.SS;
+  d.fill_kind = w->fill_kind;
+  d.agent_kind = w->agent_kind;
+  d.default_kind = w->default_kind;
+  d.n_actions = w->num_actions;
+  d.n_choices = w->num_spawn_choices;
+  d.env_id_base = w->env_id_base;
+  d.p = w->spawn_prob;
+  const uint64_t thr = spawn_threshold(d.p);
+  d.hi8 = (uint32_t)(thr >> 45);
+  d.lo45 = thr & ((1ull << 45) - 1);
+  int n_spawn_kinds = 0;
+  d.single_spawn_kind = -1;
+  for (int k = 0; k < d.K; ++k) {
+    d.value[k] = w->kind_value[k];
+    if (w->kind_passable[k]) d.passable_mask |= 1u << k;
+    if (w->kind_rule[k] == SB_RULE_SPAWN) {
+      d.spawn_mask |= 1u << k;
+      d.single_spawn_kind = k;
+      ++n_spawn_kinds;
+    } else if (w->kind_rule[k] != SB_RULE_NONE) {
+      return SB_EUNSUPPORTED;
+    }
+  }
+  if (n_spawn_kinds != 1) d.single_spawn_kind = -1;
+  if (n_spawn_kinds > 0 && d.n_choices == 0 && d.p > 0.0) return SB_EINVAL;
+  for (int i = 0; i < d.n_choices; ++i) {
+    if (!kind_ok(w->spawn_choice_kinds[i])) return SB_EINVAL;
+    d.choices_packed |= (uint64_t)w->spawn_choice_kinds[i] << (8 * i);
+  }
+  for (int i = 0; i < d.n_actions; ++i) {
+    d.dy_packed |= (uint64_t)(uint8_t)w->action_dy[i] << (8 * i);
+    d.dx_packed |= (uint64_t)(uint8_t)w->action_dx[i] << (8 * i);
+  }
+  d.simd_sweep = (d.single_spawn_kind >= 0 && d.hi8 + 1u <= 128u) ? 1 : 0;
+  // one-hot fast path: every appearance row is all-zero or exactly one 1.0
+  d.fast_obs = w->static_layers_invisible || d.n_planes == d.L ? 1 : 0;
+  for (int k = 0; k < d.K; ++k) {
+    int ch = 255, ones = 0;
+    for (int c = 0; c < d.C; ++c) {
+      double v = w->h_appearance[k * d.C + c];
+      if (v == 1.0) {
+        ch = c;
+        ++ones;
+      } else if (v != 0.0) {
+        d.fast_obs = 0;
+      }
+    }
+    if (ones > 1) d.fast_obs = 0;
+    d.channel[k] = (uint8_t)ch;
+  }
+  for (int k = d.K; k < SB_MAX_KINDS; ++k) d.channel[k] = 255;
+  d.fill_channel = d.channel[d.fill_kind];
+  d.app = w->d_appearance;
+  d.tmpl = w->d_template;
+  *out = d;
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset: Environment.reset + populate_environment (environment.py:72-79, treasurehunt/env.py:114-147)
+// ------------------------------------------------------------------------------------------------
+constexpr int RESET_LPE = 4;
+__global__ void __launch_bounds__(SB_THREADS)
+    reset_kernel(const __grid_constant__ SbDev d, uint8_t* __restrict__ grid, int32_t* __restrict__ agent_pos,
+                 double* __restrict__ total_reward, const int32_t* __restrict__ spawnable, int n_spawnable,
+                 const int32_t* __restrict__ placement, uint64_t seed, uint32_t tick) {
+  const int tid = threadIdx.x, lane = tid & (RESET_LPE - 1);
+  const long long env = (long long)blockIdx.x * (SB_THREADS / RESET_LPE) + tid / RESET_LPE;
+  const bool active = env < d.N;
+  if (active) {
+    uint4* dst = reinterpret_cast<uint4*>(grid + (size_t)env * d.env_stride);
+    const int cpp = d.plane_stride / 16;
+    for (int c = lane; c < d.n_chunks; c += RESET_LPE) {
+      int pl = c / cpp, off = c - pl * cpp;
+      int z = 0;
+      for (int zz = 0; zz < d.L; ++zz)
+        if (d.plane_of_layer[zz] == pl) z = zz;
+      dst[c] = __ldg(reinterpret_cast<const uint4*>(d.tmpl + (size_t)z * d.plane_stride) + off);
+    }
+  }
+  __syncwarp();  // orders the template copy before lane 0's placement writes
+  if (active && lane == 0) {
+    uint8_t* plane = grid + (size_t)env * d.env_stride + (size_t)d.agent_plane * d.plane_stride;
+    const uint32_t envid = (uint32_t)(d.env_id_base + (uint64_t)env);
+    uint32_t j = 0;
+    for (int a = 0; a < d.A; ++a) {
+      int cell;
+      if (placement) {
+        cell = spawnable[placement[(size_t)env * d.A + a]];
+      } else {
+        // sequential rejection: uniform over the spawnable cells not taken yet
+        for (;;) {
+          SbU4 w = sb_philox(envid, tick, j++, SB_DOM_RESET, (uint32_t)seed, (uint32_t)(seed >> 32));
+          cell = spawnable[sb_bounded(w.x, w.y, (uint32_t)n_spawnable)];
+          if (plane[cell] != (uint8_t)d.agent_kind) break;
+        }
+      }
+      plane[cell] = (uint8_t)d.agent_kind;  // world.add(loc, agent) overwrites, gridworld.py:67-76
+      agent_pos[(size_t)env * d.A + a] = cell;
+    }
+    total_reward[env] = 0.0;  // create_world, gridworld.py:65
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// replay ring
+// ------------------------------------------------------------------------------------------------
+__global__ void buffer_add_kernel(SbBufferDesc b, int slot, const float* __restrict__ obs,
+                                  const int64_t* __restrict__ actions, const float* __restrict__ rewards,
+                                  const float* __restrict__ dones, const int64_t* __restrict__ positions) {
+  // one warp per row: states[row][slot][:] = obs[row][:]  (Buffer.add, buffers.py:56-62)
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= b.rows) return;
+  const float* src = obs + (size_t)row * b.obs_size;
+  float* dst = b.d_states + ((size_t)row * b.capacity + slot) * b.obs_size;
+  for (int e = lane; e < b.obs_size; e += 32) dst[e] = src[e];
+  if (lane == 0) {
+    const size_t at = (size_t)slot * b.rows + row;
+    b.d_actions[at] = actions[row];
+    b.d_rewards[at] = rewards[row];
+    b.d_dones[at] = dones[row];
+    if (b.d_positions && positions) {
+      b.d_positions[2 * at] = positions[2 * row];
+      b.d_positions[2 * at + 1] = positions[2 * row + 1];
+    }
+  }
+}
+
+__global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__ rows_idx,
+                                     const int64_t* __restrict__ starts, int batch, float* __restrict__ states,
+                                     int64_t* __restrict__ actions, float* __restrict__ rewards,
+                                     float* __restrict__ next_states, float* __restrict__ dones,
+                                     double* __restrict__ valid) {
+  // one warp per sample (Buffer.sample, buffers.py:112-124): the F stacked frames of a row are
+  // contiguous in the ring, so states / next_states are two overlapping linear copies.
+  const int sample = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (sample >= batch) return;
+  const int64_t row = rows_idx[sample], s0 = starts[sample];
+  const int F = b.n_frames;
+  const size_t n = (size_t)F * b.obs_size;
+  const float* src = b.d_states + ((size_t)row * b.capacity + s0) * b.obs_size;
+  float* ds = states + (size_t)sample * n;
+  float* dn = next_states + (size_t)sample * n;
+  // 8-byte path when everything is 8-byte aligned (obs_size even), else scalar
+  if ((b.obs_size & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ds) |
+                                 reinterpret_cast<uintptr_t>(dn)) & 7u) == 0) {
+    const float2* s2 = reinterpret_cast<const float2*>(src);
+    float2* ds2 = reinterpret_cast<float2*>(ds);
+    float2* dn2 = reinterpret_cast<float2*>(dn);
+    const size_t n2 = n / 2, o2 = b.obs_size / 2;
+    for (size_t e = lane; e < n2 + o2; e += 32) {
+      float2 v = s2[e];
+      if (e < n2) ds2[e] = v;
+      if (e >= o2) dn2[e - o2] = v;
+    }
+  } else {
+    for (size_t e = lane; e < n + b.obs_size; e += 32) {
+      float v = src[e];
+      if (e < n) ds[e] = v;
+      if (e >= (size_t)b.obs_size) dn[e - b.obs_size] = v;
+    }
+  }
+  if (lane == 0) {
+    const size_t last = (size_t)(s0 + F - 1) * b.rows + row;  // indices[:, -1]
+    actions[sample] = b.d_actions[last];
+    rewards[sample] = b.d_rewards[last];
+    dones[sample] = b.d_dones[last];
+    bool any = false;  // valid = 1 - any(dones[indices[:, :-1]]), buffers.py:120-122
+    for (int f = 0; f < F - 1; ++f) any = any || (b.d_dones[(size_t)(s0 + f) * b.rows + row] != 0.0f);
+    valid[sample] = any ? 0.0 : 1.0;
+  }
+}
+
+__global__ void buffer_current_state_kernel(SbBufferDesc b, int idx, float* __restrict__ out) {
+  // rows [idx-(F-1), idx) with ring wrap (Buffer.current_state, buffers.py:143-154)
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= b.rows) return;
+  const int F1 = b.n_frames - 1;
+  for (int f = 0; f < F1; ++f) {
+    int slot = idx - F1 + f;
+    if (slot < 0) slot += b.capacity;
+    const float* src = b.d_states + ((size_t)row * b.capacity + slot) * b.obs_size;
+    float* dst = out + ((size_t)row * F1 + f) * b.obs_size;
+    for (int e = lane; e < b.obs_size; e += 32) dst[e] = src[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reward statistics: deterministic two-level reduction (fixed block order)
+// ------------------------------------------------------------------------------------------------
+constexpr int STATS_BLOCKS = 296, STATS_THREADS = 256;
+struct StatsScratch {
+  double part[STATS_BLOCKS][4];
+  unsigned int ticket;
+};
+
+__device__ inline void stats_merge(double& s, double& ss, double& mn, double& mx, double s2, double ss2,
+                                   double mn2, double mx2) {
+  s += s2;
+  ss += ss2;
+  mn = fmin(mn, mn2);
+  mx = fmax(mx, mx2);
+}
+
+__global__ void __launch_bounds__(STATS_THREADS)
+    reward_stats_kernel(const double* __restrict__ x, long long n, double* __restrict__ out, StatsScratch* sc) {
+  __shared__ double sh[STATS_THREADS / 32][4];
+  __shared__ bool last;
+  double s = 0, ss = 0, mn = INFINITY, mx = -INFINITY;
+  for (long long i = (long long)blockIdx.x * STATS_THREADS + threadIdx.x; i < n;
+       i += (long long)gridDim.x * STATS_THREADS) {
+    double v = x[i];
+    s += v;
+    ss += v * v;
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+  }
+  auto warp_reduce = [&]() {
+    for (int o = 16; o > 0; o >>= 1)
+      stats_merge(s, ss, mn, mx, __shfl_down_sync(~0u, s, o), __shfl_down_sync(~0u, ss, o),
+                  __shfl_down_sync(~0u, mn, o), __shfl_down_sync(~0u, mx, o));
+  };
+  warp_reduce();
+  if ((threadIdx.x & 31) == 0) {
+    double* r = sh[threadIdx.x >> 5];
+    r[0] = s, r[1] = ss, r[2] = mn, r[3] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < STATS_THREADS / 32; ++w) stats_merge(s, ss, mn, mx, sh[w][0], sh[w][1], sh[w][2], sh[w][3]);
+    double* r = sc->part[blockIdx.x];
+    r[0] = s, r[1] = ss, r[2] = mn, r[3] = mx;
+    __threadfence();
+    last = atomicAdd(&sc->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    s = 0, ss = 0, mn = INFINITY, mx = -INFINITY;
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+      volatile double* r = sc->part[b];
+      stats_merge(s, ss, mn, mx, r[0], r[1], r[2], r[3]);
+    }
+    out[0] = s, out[1] = ss, out[2] = mn, out[3] = mx, out[4] = (double)n;
+    sc->ticket = 0;
+  }
+}
+
+static int check_buf(const SbBufferDesc* b) {
+  if (!b) return SB_EINVAL;
+  if (b->capacity <= 0 || b->obs_size <= 0 || b->n_frames <= 0 || b->rows <= 0) return SB_EINVAL;
+  if (!b->d_states || !b->d_actions || !b->d_rewards || !b->d_dones) return SB_EINVAL;
+  return SB_OK;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sb_abi_version(void) { return SB_ABI_VERSION; }
+
+const char* sb_strerror(int status) {
+  switch (status) {
+    case SB_OK: return "ok";
+    case SB_EINVAL: return "invalid argument";
+    case SB_EUNSUPPORTED: return "shape not supported by the sm_100a kernels";
+    case SB_EALIGN: return "pointer is not 16-byte aligned";
+    case SB_ECUDA: return "CUDA error (see sb_last_cuda_error)";
+    case SB_ENODEVICE: return "no CUDA device with compute capability 10.x";
+    case SB_EVISION: return "vision radius exceeds (H-1)/2 or (W-1)/2";
+    default: return "unknown status";
+  }
+}
+
+const char* sb_last_cuda_error(void) { return g_cuda_err; }
+uint64_t sb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int32_t sb_plane_stride(int32_t height, int32_t width) { return (height * width + 15) / 16 * 16; }
+
+size_t sb_grid_bytes(const SbWorldDesc* w) {
+  if (!w) return 0;
+  return (size_t)w->num_envs * (size_t)w->num_dyn_layers * (size_t)sb_plane_stride(w->height, w->width);
+}
+
+int sb_validate(const SbWorldDesc* w) {
+  SbDev d;
+  return make_dev(w, &d);
+}
+
+int sb_reset(const SbWorldDesc* w, uint8_t* d_grid, int32_t* d_agent_pos, double* d_total_reward,
+             const int32_t* d_spawnable, int32_t n_spawnable, const int32_t* d_placement, uint64_t seed,
+             uint32_t tick, void* stream) {
+  SbDev d;
+  int rc = make_dev(w, &d);
+  if (rc) return rc;
+  if (!d_grid || !d_agent_pos || !d_total_reward || !d_spawnable) return SB_EINVAL;
+  if (n_spawnable < d.A) return SB_EINVAL;  // np.random.choice(replace=False) raises ValueError
+  if (!aligned16(d_grid) || !aligned16(d.tmpl)) return SB_EALIGN;
+  const int epb = SB_THREADS / RESET_LPE;
+  const unsigned blocks = (unsigned)(((long long)d.N + epb - 1) / epb);
+  reset_kernel<<<blocks, SB_THREADS, 0, (cudaStream_t)stream>>>(d, d_grid, d_agent_pos, d_total_reward,
+                                                                d_spawnable, n_spawnable, d_placement, seed,
+                                                                tick);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
+}
+
+int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t* d_agent_pos,
+            double* d_total_reward, const SbBufferDesc* buf, void* stream) {
+  SbDev d;
+  int rc = make_dev(w, &d);
+  if (rc) return rc;
+  if (!a || !d_grid || !d_agent_pos || !d_total_reward) return SB_EINVAL;
+  if (!aligned16(d_grid)) return SB_EALIGN;
+  if (a->num_turns < 1) return SB_EINVAL;
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  p.a = *a;
+  if (a->mode == SB_MODE_SPLIT) {
+    if (a->num_turns != 1) return SB_EINVAL;
+    if (a->act_agent >= d.A || a->obs_agent >= d.A) return SB_EINVAL;
+    if (a->act_agent < 0) p.a.act_agent = -1;
+    if (a->obs_agent < 0 && a->obs_agent != SB_OBS_ALL) p.a.obs_agent = -1;
+    if (a->act_agent >= 0 && a->policy == SB_POLICY_TAPE && !a->d_actions) return SB_EINVAL;
+  } else if (a->mode == SB_MODE_FUSED) {
+    if (a->policy == SB_POLICY_TAPE && !a->d_actions) return SB_EINVAL;
+  } else {
+    return SB_EINVAL;
+  }
+  const bool sweeps = a->mode == SB_MODE_FUSED || a->do_sweep;
+  if (sweeps && a->rng == SB_RNG_TAPE && (!a->d_spawn_u || !a->d_spawn_c)) return SB_EINVAL;
+  if (a->rng != SB_RNG_TAPE && a->rng != SB_RNG_PHILOX) return SB_EINVAL;
+  if (a->policy != SB_POLICY_TAPE && a->policy != SB_POLICY_UNIFORM) return SB_EINVAL;
+  if (buf) {
+    rc = check_buf(buf);
+    if (rc) return rc;
+    if (buf->obs_size != d.obs_size || buf->rows != (int64_t)d.N * d.A) return SB_EINVAL;
+    if (a->slot0 < 0 || a->slot0 >= buf->capacity) return SB_EINVAL;
+    p.buf = *buf;
+    p.has_buf = 1;
+  }
+  p.write_back = 1;
+  p.grid = d_grid;
+  p.agent_pos = d_agent_pos;
+  p.total_reward = d_total_reward;
+  return launch_step(d, p, (cudaStream_t)stream);
+}
+
+int sb_observe(const SbWorldDesc* w, const uint8_t* d_grid, const int32_t* d_agent_pos, float* d_obs_out,
+               void* stream) {
+  SbDev d;
+  int rc = make_dev(w, &d);
+  if (rc) return rc;
+  if (!d_grid || !d_agent_pos || !d_obs_out) return SB_EINVAL;
+  if (!aligned16(d_grid)) return SB_EALIGN;
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  p.a.mode = SB_MODE_SPLIT;
+  p.a.num_turns = 1;
+  p.a.rng = SB_RNG_PHILOX;
+  p.a.policy = SB_POLICY_TAPE;
+  p.a.act_agent = -1;
+  p.a.obs_agent = SB_OBS_ALL;
+  p.a.d_obs_out = d_obs_out;
+  p.write_back = 0;
+  p.grid = const_cast<uint8_t*>(d_grid);
+  p.agent_pos = const_cast<int32_t*>(d_agent_pos);
+  p.total_reward = nullptr;
+  return launch_step(d, p, (cudaStream_t)stream);
+}
+
+int sb_buffer_add(const SbBufferDesc* buf, int32_t slot, const float* d_obs, const int64_t* d_actions,
+                  const float* d_rewards, const float* d_dones, const int64_t* d_positions, void* stream) {
+  int rc = check_buf(buf);
+  if (rc) return rc;
+  if (slot < 0 || slot >= buf->capacity || !d_obs || !d_actions || !d_rewards || !d_dones) return SB_EINVAL;
+  const long long threads = buf->rows * 32;
+  buffer_add_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *buf, slot, d_obs, d_actions, d_rewards, d_dones, d_positions);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
+}
+
+int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts, int32_t batch,
+                     float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states,
+                     float* d_dones, double* d_valid, void* stream) {
+  int rc = check_buf(buf);
+  if (rc) return rc;
+  if (batch <= 0 || !d_rows || !d_starts || !d_states || !d_actions || !d_rewards || !d_next_states ||
+      !d_dones || !d_valid)
+    return SB_EINVAL;
+  const long long threads = (long long)batch * 32;
+  buffer_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *buf, d_rows, d_starts, batch, d_states, d_actions, d_rewards, d_next_states, d_dones, d_valid);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
+}
+
+int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, void* stream) {
+  int rc = check_buf(buf);
+  if (rc) return rc;
+  if (idx < 0 || idx >= buf->capacity || !d_out) return SB_EINVAL;
+  if (buf->n_frames < 2) return SB_OK;  // zero rows, like states[idx:idx]
+  const long long threads = buf->rows * 32;
+  buffer_current_state_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*buf, idx,
+                                                                                                   d_out);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
+}
+
+size_t sb_stats_scratch_bytes(void) { return sizeof(StatsScratch); }
+
+int sb_reward_stats(const double* d_total_reward, int64_t n, double* d_out, void* d_scratch, void* stream) {
+  if (!d_total_reward || n <= 0 || !d_out || !d_scratch) return SB_EINVAL;
+  long long want = (n + STATS_THREADS - 1) / STATS_THREADS;
+  unsigned blocks = (unsigned)(want < STATS_BLOCKS ? want : STATS_BLOCKS);
+  reward_stats_kernel<<<blocks, STATS_THREADS, 0, (cudaStream_t)stream>>>(d_total_reward, n, d_out,
+                                                                         (StatsScratch*)d_scratch);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// sb_core.cuh -- per-lane building blocks of the step / observation kernels.
+//
+// Everything here is a pure function of its arguments (plus the shared-memory image of one world
+// instance), marked SB_HD so that tests/hostcheck can compile the very same source with g++ and
+// unit-test it against the oracle without a GPU.  The kernels in sb_step.cu only add the tiling,
+// the synchronisation and the global-memory traffic around these functions.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/sorrel_b200.h"
+
+#if defined(__CUDACC__)
+#define SB_HD __host__ __device__ __forceinline__
+#else
+#define SB_HD static inline
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Device-side view of SbWorldDesc: everything the kernels need, precomputed once per call on the
+// host (sb_abi.cu: make_dev) and passed by value as a __grid_constant__ kernel parameter.
+// ------------------------------------------------------------------------------------------------
+struct SbDev {
+  int32_t N, A, H, W, HW;
+  int32_t plane_stride;  // bytes per stored plane (H*W rounded up to 16)
+  int32_t n_planes;      // dynamic layers stored per instance
+  int32_t env_stride;    // n_planes * plane_stride
+  int32_t n_chunks;      // env_stride / 16
+  int32_t agent_plane;   // plane index of the agent layer
+  int32_t L;             // all layers (static ones live in tmpl)
+  int32_t plane_of_layer[SB_MAX_LAYERS];  // -1 for static layers
+  int32_t K, C, v, S, SS, obs_size;
+  int32_t fill_kind, agent_kind, default_kind, n_actions, n_choices;
+  int32_t fast_obs;           // appearance rows are zero / one-hot and static layers invisible
+  int32_t fill_channel;       // fast path: channel of the fill kind (or 255 = none)
+  int32_t single_spawn_kind;  // >= 0 when exactly one kind carries SB_RULE_SPAWN
+  int32_t simd_sweep;         // byte-SIMD candidate test usable (single spawn kind, hi8 < 128)
+  uint32_t passable_mask, spawn_mask;  // bit k: kind k passable / has SB_RULE_SPAWN
+  uint32_t hi8;                        // top 8 bits of the 53-bit spawn threshold
+  uint64_t lo45;                       // low 45 bits
+  uint64_t choices_packed;             // spawn_choice_kinds, one byte each
+  uint64_t dy_packed, dx_packed;       // action deltas, one signed byte each
+  uint64_t env_id_base;
+  double p;
+  float value[SB_MAX_KINDS];
+  uint8_t channel[SB_MAX_KINDS];  // fast path: one-hot channel of the kind, 255 = all-zero row
+  const double* app;              // device [K][C]
+  const uint8_t* tmpl;            // device [L][plane_stride]
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11)
+// ------------------------------------------------------------------------------------------------
+struct SbU4 {
+  uint32_t x, y, z, w;
+};
+
+SB_HD void sb_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+  lo = a * b;
+  hi = __umulhi(a, b);
+#else
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  lo = (uint32_t)p;
+  hi = (uint32_t)(p >> 32);
+#endif
+}
+
+SB_HD SbU4 sb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    sb_mulhilo(M0, c0, hi0, lo0);
+    sb_mulhilo(M1, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += W0;
+    k1 += W1;
+  }
+  SbU4 o;
+  o.x = c0;
+  o.y = c1;
+  o.z = c2;
+  o.w = c3;
+  return o;
+}
+
+SB_HD uint64_t sb_mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+
+// uniform integer in [0, n) from 64 random bits (multiply-shift; bias <= n / 2^64)
+SB_HD uint32_t sb_bounded(uint32_t hi, uint32_t lo, uint32_t n) {
+  return (uint32_t)sb_mulhi64(((uint64_t)hi << 32) | lo, (uint64_t)n);
+}
+
+SB_HD uint32_t sb_byte_of(const SbU4& r, int b) {
+  uint32_t w = (b & 8) ? ((b & 4) ? r.w : r.z) : ((b & 4) ? r.y : r.x);
+  return (w >> (8 * (b & 3))) & 0xFFu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Counter-based spawn rule (DESIGN.md "Counter-based RNG").  Cell `cell` (= plane * plane_stride +
+// y*W + x) of instance `env` at tick `tick` spawns iff U < ceil(p * 2^53) where the 53-bit uniform
+// U = r8 : refine45 is evaluated lazily: r8 is byte (cell & 15) of Philox(env, tick, cell >> 4,
+// SWEEP); only when r8 == hi8 are the low 45 bits (from Philox(env, tick, cell, CELL)) needed.
+// ------------------------------------------------------------------------------------------------
+
+// Second level: called for cells whose r8 <= hi8.  Returns the kind to spawn, or -1.
+SB_HD int sb_resolve_spawn(const SbDev& d, uint32_t env, uint32_t tick, uint32_t cell, bool r8_equal,
+                           uint32_t k0, uint32_t k1) {
+  SbU4 w = sb_philox(env, tick, cell, SB_DOM_CELL, k0, k1);
+  if (r8_equal) {
+    uint64_t refine = (((uint64_t)w.x << 13) | (uint64_t)(w.y >> 19)) & ((1ull << 45) - 1);
+    if (!(refine < d.lo45)) return -1;
+  }
+  uint32_t ci = sb_bounded(w.z, w.w, (uint32_t)d.n_choices);
+  return (int)((d.choices_packed >> (8 * ci)) & 0xFFu);
+}
+
+// Byte-SIMD first level for one 16-cell chunk: bit (8*b+7) of the returned words' union is
+// condensed into a 16-bit mask: bit b set iff kinds[b] == single_spawn_kind and r8[b] <= hi8.
+// Requires d.simd_sweep (hi8 + 1 <= 128).
+SB_HD uint32_t sb_simd_cand_word(uint32_t kinds, uint32_t rnd, uint32_t spawn4, uint32_t n4c) {
+  // zero-byte detect on kinds ^ spawn4 (exact per byte)
+  uint32_t x = kinds ^ spawn4;
+  uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  uint32_t eq = ~(t | x | 0x7F7F7F7Fu);  // 0x80 where byte == 0
+  // per-byte rnd < n  (n <= 128):  s = (rnd & 0x7F) + (128 - n): bit7 set iff low7 >= n
+  uint32_t s = (rnd & 0x7F7F7F7Fu) + n4c;  // n4c = (128 - n) replicated
+  uint32_t lt = ~(s | rnd) & 0x80808080u;
+  return eq & lt;
+}
+
+SB_HD uint32_t sb_pack_mask(uint32_t m) {
+  // gather bits 7,15,23,31 -> bits 0..3
+  m >>= 7;
+  return (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Agent move: MovingAgent.act agents/agent.py:215-225 + Gridworld.move gridworld.py:95-122.
+// `genv` is the (shared-memory) image of the instance.  Returns the reward; updates *yx (packed
+// y<<16|x) and, when `writer`, the two grid cells.  `err` collects SB_ERR_* bits.
+// ------------------------------------------------------------------------------------------------
+SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action, bool writer,
+                         uint32_t& err) {
+  int y = (int)(*yx >> 16), x = (int)(*yx & 0xFFFFu);
+  int dy = 0, dx = 0;
+  if ((unsigned)action < (unsigned)d.n_actions) {
+    dy = (int)(int8_t)((d.dy_packed >> (8 * action)) & 0xFF);
+    dx = (int)(int8_t)((d.dx_packed >> (8 * action)) & 0xFF);
+  } else {
+    err |= SB_ERR_BAD_ACTION;
+  }
+  int ny = y + dy, nx = x + dx;
+  if ((unsigned)ny >= (unsigned)d.H || (unsigned)nx >= (unsigned)d.W) {
+    err |= SB_ERR_OFFGRID;
+    return 0.0f;
+  }
+  uint8_t* plane = genv + d.agent_plane * d.plane_stride;
+  uint32_t tk = plane[ny * d.W + nx];
+  if (tk >= (uint32_t)d.K) {
+    err |= SB_ERR_BAD_KIND;
+    return 0.0f;
+  }
+  float reward = d.value[tk];  // reward = value of the entity at the target cell (agent.py:219-220)
+  if ((d.passable_mask >> tk) & 1u) {
+    if (writer) {
+      plane[ny * d.W + nx] = (uint8_t)d.agent_kind;  // target entity discarded, agent placed
+      plane[y * d.W + x] = (uint8_t)d.default_kind;  // vacated cell <- default entity
+    }
+    *yx = ((uint32_t)ny << 16) | (uint32_t)nx;
+  }
+  return reward;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Observation, general path: closed form of visual_field (observation/visual_field.py:9-101):
+// element (c, i, j) of the crop centred on (y, x).  float64 sum over layers in z order, like
+// np.sum(axis=-1) on a short axis; the caller rounds to float32 (Buffer.states, buffers.py:31,56).
+// ------------------------------------------------------------------------------------------------
+SB_HD double sb_obs_general(const SbDev& d, const uint8_t* genv, const uint8_t* tmpl, const double* app,
+                            int y, int x, int c, int i, int j) {
+  int yy = y - d.v + i, xx = x - d.v + j;
+  if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) return app[d.fill_kind * d.C + c];
+  int cell = yy * d.W + xx;
+  double s = 0.0;
+  for (int z = 0; z < d.L; ++z) {
+    int pl = d.plane_of_layer[z];
+    uint32_t kind = pl >= 0 ? genv[pl * d.plane_stride + cell] : tmpl[z * d.plane_stride + cell];
+    s += app[kind * d.C + c];
+  }
+  return s;
+}
+
+// Fast path, phase A: channel code of window cell (i, j) on plane `pl` (255 = contributes nothing).
+SB_HD uint32_t sb_window_code(const SbDev& d, const uint8_t* genv, int y, int x, int i, int j, int pl) {
+  int yy = y - d.v + i, xx = x - d.v + j;
+  if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W)
+    return pl == 0 ? (uint32_t)d.fill_channel : 255u;  // out of bounds: the fill kind, once
+  uint32_t kind = genv[pl * d.plane_stride + yy * d.W + xx];
+  return kind < (uint32_t)SB_MAX_KINDS ? d.channel[kind] : 255u;
+}

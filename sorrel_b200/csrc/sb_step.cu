@@ -1,0 +1,397 @@
+// sb_step.cu -- the environment-step kernel (entity sweep + sequential agents + observation +
+// replay-ring write), sm_100a.
+//
+// Replaces Environment.take_turn (sorrel/environment.py:81-93) for N independent instances:
+//   sweep   : EmptyEntity.transition           examples/treasurehunt/entities.py:69-85
+//   observe : OneHotObservationSpec.observe    observation/observation_spec.py:175-205
+//             -> visual_field                  observation/visual_field.py:9-101
+//   act     : MovingAgent.act / Gridworld.move agents/agent.py:215-225, worlds/gridworld.py:95-122
+//   record  : Agent.add_memory -> Buffer.add   agents/agent.py:113-136, buffers.py:46-63
+//
+// Tiling: a *group* of LPE lanes (4..32, a power of two) owns one world instance whose dynamic
+// planes are staged in shared memory for the whole launch (all `num_turns` turns), so the grid is
+// read and written once per launch while every turn streams one observation row per agent straight
+// into its replay-ring slot with 128-bit stores.  Groups never talk to each other; the only
+// intra-warp cooperation is the per-warp spawn-candidate queue (see sweep_philox_simd).
+#include <cuda_runtime.h>
+
+#include "sb_core.cuh"
+#include "sb_internal.h"
+
+namespace sb {
+
+template <int LPE>
+struct Smem {
+  uint16_t* lut_e;   // [obs_size]  (channel << 9) | window index
+  uint16_t* lut_ij;  // [SS]        (i << 8) | j
+  uint32_t* q;       // [warps][SB_QCAP] spawn candidates of the warp's instances
+  uint32_t* qn;      // [warps]
+  uint8_t* envs;     // [EPB][env_smem]
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// bytes of shared memory per instance: planes + agent yx + agent actions + window codes
+__host__ __device__ inline int env_smem_bytes(const SbDev& d) {
+  return round_up(d.env_stride + 8 * d.A + d.SS * d.n_planes, 16);
+}
+
+__host__ __device__ inline int block_smem_bytes(const SbDev& d, int threads, int lpe) {
+  int lut = round_up(2 * d.obs_size + 2 * d.SS, 16);
+  int q = round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
+  return lut + q + (threads / lpe) * env_smem_bytes(d);
+}
+
+__device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float e) {
+  // streaming 128-bit store: observation rows are written once and not re-read by this kernel
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(e)
+               : "memory");
+}
+
+template <int LPE, int RNG>
+__global__ void __launch_bounds__(SB_THREADS)
+    step_kernel(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int EPB = SB_THREADS / LPE;
+  constexpr int GPW = 32 / LPE;  // groups per warp
+  const int tid = threadIdx.x;
+  const int lane = tid & (LPE - 1);
+  const int grp = tid / LPE;
+  const int wlane = tid & 31;
+  const int warp = tid >> 5;
+
+  // ---- carve shared memory --------------------------------------------------------------
+  uint16_t* lut_e = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* lut_ij = lut_e + d.obs_size;
+  const int lut_bytes = round_up(2 * d.obs_size + 2 * d.SS, 16);
+  uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + lut_bytes);
+  uint32_t* q = qbase + warp * (SB_QCAP + 1);
+  uint32_t* qn = q + SB_QCAP;
+  const int q_bytes = round_up((SB_THREADS / 32) * (SB_QCAP + 1) * 4, 16);
+  const int esz = env_smem_bytes(d);
+  uint8_t* envs = smem_raw + lut_bytes + q_bytes;
+  uint8_t* genv = envs + grp * esz;
+  uint32_t* spos = reinterpret_cast<uint32_t*>(genv + d.env_stride);
+  int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
+  uint8_t* swin = reinterpret_cast<uint8_t*>(sact + d.A);
+
+  for (int e = tid; e < d.obs_size; e += SB_THREADS) {
+    int c = e / d.SS;
+    lut_e[e] = (uint16_t)((c << 9) | (e - c * d.SS));
+  }
+  for (int ij = tid; ij < d.SS; ij += SB_THREADS) {
+    int i = ij / d.S;
+    lut_ij[ij] = (uint16_t)((i << 8) | (ij - i * d.S));
+  }
+  if (wlane == 0) *qn = 0;
+  __syncthreads();
+
+  const long long env0 = (long long)blockIdx.x * EPB;
+  if (env0 + (long long)warp * GPW >= d.N) return;  // whole warp idle (only warp-level syncs below)
+  const long long env = env0 + grp;
+  const bool active = env < d.N;
+  const uint32_t envid = (uint32_t)(d.env_id_base + (uint64_t)env);
+  const uint32_t k0 = (uint32_t)p.a.seed, k1 = (uint32_t)(p.a.seed >> 32);
+
+  // ---- stage the instance ------------------------------------------------------------------
+  uint4* genv4 = reinterpret_cast<uint4*>(genv);
+  if (active) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.grid + (size_t)env * d.env_stride);
+    for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = __ldg(src + c);
+    for (int a = lane; a < d.A; a += LPE) {
+      int pos = p.agent_pos[(size_t)env * d.A + a];
+      int y = pos / d.W;
+      spos[a] = ((uint32_t)y << 16) | (uint32_t)(pos - y * d.W);
+    }
+  } else {
+    for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int a = lane; a < d.A; a += LPE) spos[a] = 0;
+  }
+  double total = (active && lane == 0 && p.write_back) ? p.total_reward[env] : 0.0;
+  uint32_t err = 0;
+  __syncwarp();
+
+  const int T = p.a.num_turns;
+  const size_t rows = (size_t)d.N * d.A;
+  const size_t tape_stride = (size_t)d.env_stride;  // tape entries per instance per turn
+
+  for (int t = 0; t < T; ++t) {
+    const uint32_t tick = p.a.tick0 + (uint32_t)t;
+    int slot = 0;
+    if (p.has_buf) {
+      slot = p.a.slot0 + t;
+      slot -= (slot / p.buf.capacity) * p.buf.capacity;
+    }
+    const bool fused = p.a.mode == SB_MODE_FUSED;
+
+    // ---- actions of this turn (parallel over agents; hides the tape-load latency) ------------
+    if (fused || p.a.act_agent >= 0) {
+      for (int a = lane; a < d.A; a += LPE) {
+        int act = 0;
+        if (p.a.policy == SB_POLICY_UNIFORM) {
+          SbU4 w = sb_philox(envid, tick, (uint32_t)a, SB_DOM_ACTION, k0, k1);
+          act = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
+        } else if (active && p.a.d_actions) {
+          act = p.a.d_actions[((size_t)t * d.N + env) * d.A + a];
+        }
+        sact[a] = act;
+      }
+    }
+
+    // ---- entity sweep ----------------------------------------------------------------------
+    if (fused || p.a.do_sweep) {
+      if (RNG == SB_K_TAPE) {
+        const double* tu = p.a.d_spawn_u + ((size_t)t * d.N + (active ? env : 0)) * tape_stride;
+        const uint8_t* tc = p.a.d_spawn_c + ((size_t)t * d.N + (active ? env : 0)) * tape_stride;
+        uint8_t* drew = p.a.d_drew_out ? p.a.d_drew_out + ((size_t)t * d.N + (active ? env : 0)) * tape_stride
+                                       : nullptr;
+        if (active) {
+          for (int cell = lane; cell < d.env_stride; cell += LPE) {
+            uint32_t kind = genv[cell];
+            double u = tu[cell];
+            bool has_rule = kind < (uint32_t)SB_MAX_KINDS && ((d.spawn_mask >> kind) & 1u);
+            if (drew) drew[cell] = has_rule ? 1 : 0;
+            if (has_rule) {
+              if (u != u) {
+                err |= SB_ERR_TAPE_ALIGN;  // the reference drew here, the tape did not
+              } else if (u < d.p) {        // np.random.random() < world.spawn_prob, entities.py:72-74
+                uint32_t ci = tc[cell];
+                if (ci < (uint32_t)d.n_choices) genv[cell] = (uint8_t)((d.choices_packed >> (8 * ci)) & 0xFF);
+                else err |= SB_ERR_TAPE_ALIGN;
+              }
+            } else if (u == u) {
+              err |= SB_ERR_TAPE_ALIGN;  // tape holds a draw for a cell that has no rule
+            }
+          }
+        }
+      } else if (RNG == SB_K_PHILOX_SIMD) {
+        // First level, byte-SIMD: one Philox call covers the 16 cells of a chunk; cells whose
+        // random byte is <= hi8 AND that carry the spawn rule are rare (about 2 per instance-turn
+        // at p = 0.005), so they are pushed to a per-warp queue and resolved by all 32 lanes at
+        // once instead of diverging inside the chunk loop.
+        const uint32_t spawn4 = (uint32_t)d.single_spawn_kind * 0x01010101u;
+        const uint32_t n4c = (128u - (d.hi8 + 1u)) * 0x01010101u;
+        const int iters = (d.n_chunks + LPE - 1) / LPE;
+        for (int it = 0; it < iters; ++it) {
+          const int c = it * LPE + lane;
+          uint32_t m = 0;
+          SbU4 r;
+          r.x = r.y = r.z = r.w = 0;
+          if (c < d.n_chunks) {
+            uint4 k = genv4[c];
+            r = sb_philox(envid, tick, (uint32_t)c, SB_DOM_SWEEP, k0, k1);
+            m = sb_pack_mask(sb_simd_cand_word(k.x, r.x, spawn4, n4c)) |
+                (sb_pack_mask(sb_simd_cand_word(k.y, r.y, spawn4, n4c)) << 4) |
+                (sb_pack_mask(sb_simd_cand_word(k.z, r.z, spawn4, n4c)) << 8) |
+                (sb_pack_mask(sb_simd_cand_word(k.w, r.w, spawn4, n4c)) << 12);
+          }
+          if (__ballot_sync(0xFFFFFFFFu, m != 0)) {
+            while (m) {
+              int b = __ffs(m) - 1;
+              m &= m - 1;
+              uint32_t r8 = sb_byte_of(r, b);
+              uint32_t cell = (uint32_t)(c * 16 + b);
+              uint32_t entry = ((r8 == d.hi8) ? 0x80000000u : 0u) | ((uint32_t)grp << 20) | cell;
+              uint32_t at = atomicAdd(qn, 1u);
+              if (at < SB_QCAP) {
+                q[at] = entry;
+              } else {  // queue full (dense spawning): resolve in place
+                int kind = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, k0, k1);
+                if (kind >= 0) genv[cell] = (uint8_t)kind;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        const uint32_t nq = min(*qn, (uint32_t)SB_QCAP);
+        for (uint32_t i = wlane; i < nq; i += 32) {
+          uint32_t entry = q[i];
+          uint32_t g = (entry >> 20) & 0x7FFu, cell = entry & 0xFFFFFu;
+          uint32_t eid = (uint32_t)(d.env_id_base + (uint64_t)(env0 + g));
+          int kind = sb_resolve_spawn(d, eid, tick, cell, (entry >> 31) != 0, k0, k1);
+          if (kind >= 0) envs[g * esz + cell] = (uint8_t)kind;
+        }
+        __syncwarp();
+        if (wlane == 0) *qn = 0;
+      } else {  // SB_K_PHILOX_GENERIC: several spawning kinds or a large probability
+        for (int c = lane; c < d.n_chunks; c += LPE) {
+          SbU4 r = sb_philox(envid, tick, (uint32_t)c, SB_DOM_SWEEP, k0, k1);
+          for (int b = 0; b < 16; ++b) {
+            uint32_t cell = (uint32_t)(c * 16 + b);
+            uint32_t kind = genv[cell];
+            if (kind >= (uint32_t)SB_MAX_KINDS || !((d.spawn_mask >> kind) & 1u)) continue;
+            uint32_t r8 = sb_byte_of(r, b);
+            if (r8 > d.hi8) continue;
+            int nk = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, k0, k1);
+            if (nk >= 0) genv[cell] = (uint8_t)nk;
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- agents, sequentially in list order (environment.py:92) -------------------------------
+    auto observe = [&](int a) {
+      const uint32_t yx = spos[a];
+      const int y = (int)(yx >> 16), x = (int)(yx & 0xFFFFu);
+      float* dst0 = (p.has_buf && active)
+                        ? p.buf.d_states + (((size_t)env * d.A + a) * p.buf.capacity + slot) * d.obs_size
+                        : nullptr;
+      float* dst1 = (p.a.d_obs_out && active)
+                        ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size
+                        : nullptr;
+      if (d.fast_obs) {
+        // phase A: channel code of every window cell on every stored plane
+        for (int pl = 0; pl < d.n_planes; ++pl)
+          for (int ij = lane; ij < d.SS; ij += LPE) {
+            uint32_t l = lut_ij[ij];
+            swin[pl * d.SS + ij] = (uint8_t)sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), pl);
+          }
+        __syncwarp();
+        // phase B: obs[c][i][j] = number of planes whose code == c, as the linear float stream
+        auto val = [&](int e) -> float {
+          uint32_t l = lut_e[e];
+          uint32_t c = l >> 9, ij = l & 511u;
+          int cnt = 0;
+          for (int pl = 0; pl < d.n_planes; ++pl) cnt += (swin[pl * d.SS + ij] == c) ? 1 : 0;
+          return (float)cnt;
+        };
+        for (int k = 0; k < 2; ++k) {
+          float* dst = k ? dst1 : dst0;
+          if (!dst) continue;
+          int head = (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3;
+          if (head > d.obs_size) head = d.obs_size;
+          if (lane < head) dst[lane] = val(lane);
+          const int nvec = (d.obs_size - head) >> 2;
+          for (int qv = lane; qv < nvec; qv += LPE) {
+            int e0 = head + 4 * qv;
+            st_f4(dst + e0, val(e0), val(e0 + 1), val(e0 + 2), val(e0 + 3));
+          }
+          int e = head + 4 * nvec + lane;
+          if (e < d.obs_size) dst[e] = val(e);
+        }
+      } else {
+        for (int e = lane; e < d.obs_size; e += LPE) {
+          uint32_t l = lut_e[e];
+          uint32_t li = lut_ij[l & 511u];
+          float vf = (float)sb_obs_general(d, genv, d.tmpl, d.app, y, x, (int)(l >> 9), (int)(li >> 8),
+                                           (int)(li & 255u));
+          if (dst0) dst0[e] = vf;
+          if (dst1) dst1[e] = vf;
+        }
+      }
+    };
+
+    auto act = [&](int a) {
+      if (lane == 0) {
+        uint32_t yx = spos[a];
+        const int action = sact[a];
+        float reward = sb_agent_act(d, genv, &yx, action, true, err);
+        spos[a] = yx;
+        total += (double)reward;  // world.total_reward += reward, agent.py:172
+        if (active) {
+          const size_t row = (size_t)env * d.A + a;
+          if (p.has_buf) {
+            const size_t at = (size_t)slot * rows + row;
+            p.buf.d_actions[at] = (int64_t)action;
+            p.buf.d_rewards[at] = reward;
+            p.buf.d_dones[at] = 0.0f;  // world.is_done is False for the whole episode
+            if (p.buf.d_positions) {   // location AFTER the move (agent.py:131-134)
+              p.buf.d_positions[2 * at] = (int64_t)(yx >> 16);
+              p.buf.d_positions[2 * at + 1] = (int64_t)(yx & 0xFFFFu);
+            }
+          }
+          const size_t o = ((size_t)t * d.N + env) * d.A + a;
+          if (p.a.d_reward_out) p.a.d_reward_out[o] = reward;
+          if (p.a.d_action_out) p.a.d_action_out[o] = action;
+        }
+      }
+      __syncwarp();
+    };
+
+    if (fused) {
+      for (int a = 0; a < d.A; ++a) {
+        observe(a);
+        act(a);
+      }
+    } else {
+      if (p.a.act_agent >= 0) act(p.a.act_agent);
+      if (p.a.obs_agent >= 0) {
+        observe(p.a.obs_agent);
+      } else if (p.a.obs_agent == SB_OBS_ALL) {
+        for (int a = 0; a < d.A; ++a) {
+          observe(a);
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- write the instance back ---------------------------------------------------------------
+  if (active && p.write_back) {
+    uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * d.env_stride);
+    for (int c = lane; c < d.n_chunks; c += LPE) dst[c] = genv4[c];
+    for (int a = lane; a < d.A; a += LPE) {
+      uint32_t yx = spos[a];
+      p.agent_pos[(size_t)env * d.A + a] = (int32_t)((yx >> 16) * d.W + (yx & 0xFFFFu));
+    }
+    if (lane == 0) p.total_reward[env] = total;
+  }
+  if (active && err && p.a.d_error) atomicOr(p.a.d_error, err);
+}
+
+// ----------------------------------------------------------------------------------------------
+// launch
+// ----------------------------------------------------------------------------------------------
+template <int LPE, int RNG>
+static int launch_one(const SbDev& d, const StepParams& p, cudaStream_t s) {
+  const int smem = block_smem_bytes(d, SB_THREADS, LPE);
+  if (smem > 227 * 1024) return SB_EUNSUPPORTED;
+  auto kern = step_kernel<LPE, RNG>;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return note_cuda_error();
+  }
+  const int epb = SB_THREADS / LPE;
+  const long long blocks = ((long long)d.N + epb - 1) / epb;
+  kern<<<(unsigned)blocks, SB_THREADS, smem, s>>>(d, p);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
+}
+
+template <int LPE>
+static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t s) {
+  switch (kr) {
+    case SB_K_TAPE: return launch_one<LPE, SB_K_TAPE>(d, p, s);
+    case SB_K_PHILOX_SIMD: return launch_one<LPE, SB_K_PHILOX_SIMD>(d, p, s);
+    default: return launch_one<LPE, SB_K_PHILOX_GENERIC>(d, p, s);
+  }
+}
+
+int pick_lpe(const SbDev& d) {
+  if (const char* e = getenv("SB_LPE")) {
+    int v = atoi(e);
+    if (v == 4 || v == 8 || v == 16 || v == 32) return v;
+  }
+  int lpe = 4;
+  while (lpe < 32 && d.n_chunks / lpe > 8) lpe *= 2;
+  // shared memory must fit
+  while (lpe < 32 && block_smem_bytes(d, SB_THREADS, lpe) > 200 * 1024) lpe *= 2;
+  return lpe;
+}
+
+int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s) {
+  int kr;
+  if (p.a.rng == SB_RNG_TAPE) kr = SB_K_TAPE;
+  else kr = d.simd_sweep ? SB_K_PHILOX_SIMD : SB_K_PHILOX_GENERIC;
+  switch (pick_lpe(d)) {
+    case 4: return launch_rng<4>(d, p, kr, s);
+    case 8: return launch_rng<8>(d, p, kr, s);
+    case 16: return launch_rng<16>(d, p, kr, s);
+    default: return launch_rng<32>(d, p, kr, s);
+  }
+}
+
+}  // namespace sb

@@ -1,0 +1,273 @@
+"""Low-level driver of the CUDA kernels: device-resident state of N world instances.
+
+This is the layer directly above the C ABI.  It owns the PyTorch tensors (device memory is
+PyTorch's job, see include/sorrel_b200.h "Conventions"), fills `SbWorldDesc` from a `WorldSpec`
+and exposes one method per entry point.  The reference-shaped classes (`Gridworld`,
+`Environment`, `Buffer`, ...) in the sibling modules are thin layers over this one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import SbStepArgs, SbWorldDesc, check, lib
+
+# MovingAgent decode (sorrel/agents/agent.py:187-213): ["up","down","left","right"] -> (dy, dx)
+MOVE_DELTAS = {"up": (-1, 0), "down": (1, 0), "left": (0, -1), "right": (0, 1)}
+
+
+@dataclass
+class WorldSpec:
+    """A world family: kind table (one row per entity class), template and agent setup.
+
+    `template[H, W, L]` is the map right after `populate_environment()` without the agents;
+    `spawnable` lists the (y, x) cells on `agent_layer` an agent may be placed on, in the order
+    the reference enumerates them (np.ndindex, examples/treasurehunt/env.py:122-137).
+    """
+
+    height: int
+    width: int
+    layers: int
+    kind_names: list[str]
+    kind_value: list[float]
+    kind_passable: list[bool]
+    kind_rule: list[int]
+    appearance: np.ndarray  # [K, C] float64
+    template: np.ndarray  # [H, W, L] uint8
+    spawnable: np.ndarray  # [n, 2] (y, x)
+    agent_kind: int
+    agent_layer: int
+    default_kind: int
+    fill_kind: int
+    vision: int
+    num_agents: int
+    spawn_prob: float = 0.0
+    spawn_choices: list[int] = field(default_factory=list)
+    action_deltas: list[tuple[int, int]] = field(
+        default_factory=lambda: [MOVE_DELTAS[a] for a in ("up", "down", "left", "right")])
+    dynamic_layers: list[int] | None = None  # default: every layer holding a non-static kind
+
+    @property
+    def channels(self) -> int:
+        return int(self.appearance.shape[1])
+
+    @property
+    def obs_side(self) -> int:
+        return 2 * self.vision + 1
+
+    @property
+    def obs_size(self) -> int:
+        return self.channels * self.obs_side ** 2
+
+    def resolved_dynamic_layers(self) -> list[int]:
+        if self.dynamic_layers is not None:
+            return sorted(self.dynamic_layers)
+        dyn = {self.agent_layer}
+        for z in range(self.layers):
+            kinds = np.unique(self.template[:, :, z])
+            if any(self.kind_rule[k] != _abi.SB_RULE_NONE for k in kinds):
+                dyn.add(z)
+        return sorted(dyn)
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """N instances of one `WorldSpec` on one CUDA device (one rank's shard)."""
+
+    def __init__(self, spec: WorldSpec, num_envs: int, device: torch.device | str = "cuda",
+                 env_id_base: int = 0, seed: int = 0):
+        self.lib = lib()  # raises if the CUDA library is missing
+        self.spec = spec
+        self.N = int(num_envs)
+        self.A = int(spec.num_agents)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _abi.SorrelB200Error("sorrel_b200 runs on CUDA devices only (no CPU fallback)")
+        self.seed = int(seed)
+        self.tick = 0  # global turn counter (Philox counter word 1); first turn is tick 1
+        self.dyn_layers = spec.resolved_dynamic_layers()
+        self.plane_stride = int(self.lib.sb_plane_stride(spec.height, spec.width))
+        self.n_planes = len(self.dyn_layers)
+        self.env_stride = self.n_planes * self.plane_stride
+        H, W, L = spec.height, spec.width, spec.layers
+
+        # ---- shared tables ------------------------------------------------------------------
+        self.h_appearance = np.ascontiguousarray(spec.appearance, dtype=np.float64)
+        self.d_appearance = torch.from_numpy(self.h_appearance).to(self.device)
+        tmpl = np.full((L, self.plane_stride), _abi.SB_PAD_KIND, dtype=np.uint8)
+        tmpl[:, : H * W] = np.moveaxis(spec.template, 2, 0).reshape(L, H * W)
+        self.d_template = torch.from_numpy(tmpl).to(self.device)
+        spawn_cells = (np.asarray(spec.spawnable)[:, 0] * W + np.asarray(spec.spawnable)[:, 1]).astype(np.int32)
+        self.n_spawnable = int(spawn_cells.size)
+        self.d_spawnable = torch.from_numpy(spawn_cells).to(self.device)
+        static_kinds = {int(k) for z in range(L) if z not in self.dyn_layers
+                        for k in np.unique(spec.template[:, :, z])}
+        invisible = all(not self.h_appearance[k].any() for k in static_kinds)
+
+        # ---- per-instance state ---------------------------------------------------------------
+        self.grid = torch.empty((self.N, self.n_planes, self.plane_stride), dtype=torch.uint8, device=self.device)
+        self.agent_pos = torch.zeros((self.N, self.A), dtype=torch.int32, device=self.device)
+        self.total_reward = torch.zeros(self.N, dtype=torch.float64, device=self.device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+        d = SbWorldDesc()
+        d.abi_version = _abi.SB_ABI_VERSION
+        d.num_envs, d.num_agents = self.N, self.A
+        d.height, d.width, d.num_layers = H, W, L
+        d.num_dyn_layers = self.n_planes
+        for i, z in enumerate(self.dyn_layers):
+            d.dyn_layers[i] = z
+        d.agent_layer = spec.agent_layer
+        d.num_kinds = len(spec.kind_names)
+        d.num_channels = spec.channels
+        d.vision = spec.vision
+        d.fill_kind, d.agent_kind, d.default_kind = spec.fill_kind, spec.agent_kind, spec.default_kind
+        d.num_actions = len(spec.action_deltas)
+        for i, (dy, dx) in enumerate(spec.action_deltas[: _abi.SB_MAX_ACTIONS]):
+            d.action_dy[i], d.action_dx[i] = dy, dx
+        d.num_spawn_choices = len(spec.spawn_choices)
+        for i, k in enumerate(spec.spawn_choices[: _abi.SB_MAX_CHOICES]):
+            d.spawn_choice_kinds[i] = k
+        d.spawn_prob = float(spec.spawn_prob)
+        d.env_id_base = int(env_id_base)
+        for k in range(min(len(spec.kind_names), _abi.SB_MAX_KINDS)):
+            d.kind_value[k] = float(spec.kind_value[k])
+            d.kind_passable[k] = 1 if spec.kind_passable[k] else 0
+            d.kind_rule[k] = int(spec.kind_rule[k])
+        d.d_appearance = self.d_appearance.data_ptr()
+        d.h_appearance = self.h_appearance.ctypes.data
+        d.d_template = self.d_template.data_ptr()
+        d.static_layers_invisible = 1 if invisible else 0
+        self.desc = d
+        check(self.lib.sb_validate(C.byref(d)), "world description")
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, placement: torch.Tensor | None = None) -> None:
+        """Environment.reset (environment.py:72-79): template copy + agent placement.
+
+        placement: int32 [N, A] indices into the spawnable list (a replayed
+        `np.random.choice(len(valid), size=A, replace=False)`), or None to draw in-kernel."""
+        if placement is not None:
+            placement = placement.to(device=self.device, dtype=torch.int32).contiguous()
+            assert placement.shape == (self.N, self.A)
+        check(self.lib.sb_reset(C.byref(self.desc), self.grid.data_ptr(), self.agent_pos.data_ptr(),
+                                self.total_reward.data_ptr(), self.d_spawnable.data_ptr(), self.n_spawnable,
+                                _ptr(placement), self.seed, self.tick + 1, self._stream()), "sb_reset")
+
+    def step(self, num_turns: int = 1, *, buffer=None, actions: torch.Tensor | None = None,
+             spawn_u: torch.Tensor | None = None, spawn_c: torch.Tensor | None = None,
+             obs_out: torch.Tensor | None = None, reward_out: torch.Tensor | None = None,
+             action_out: torch.Tensor | None = None, drew_out: torch.Tensor | None = None) -> None:
+        """`num_turns` fused Environment.take_turn()s (environment.py:81-93) for every instance.
+
+        actions given -> replayed / host policy; None -> in-kernel uniform policy (RandomModel).
+        spawn_u/spawn_c given -> replayed numpy draws; None -> Philox.
+        With a `buffer` (buffers.Buffer) every agent-turn is recorded into its ring."""
+        T = int(num_turns)
+        a = SbStepArgs()
+        a.mode = _abi.SB_MODE_FUSED
+        a.num_turns = T
+        a.tick0 = self.tick + 1
+        a.seed = self.seed
+        a.rng = _abi.SB_RNG_TAPE if spawn_u is not None else _abi.SB_RNG_PHILOX
+        a.policy = _abi.SB_POLICY_TAPE if actions is not None else _abi.SB_POLICY_UNIFORM
+        a.act_agent = a.obs_agent = -1
+        self._fill_ptrs(a, T, actions, spawn_u, spawn_c, obs_out, reward_out, action_out, drew_out)
+        bdesc = None
+        if buffer is not None:
+            a.slot0 = buffer.idx
+            bdesc = C.byref(buffer.desc())
+        check(self.lib.sb_step(C.byref(self.desc), C.byref(a), self.grid.data_ptr(), self.agent_pos.data_ptr(),
+                               self.total_reward.data_ptr(), bdesc, self._stream()), "sb_step")
+        self.tick += T
+        if buffer is not None:
+            buffer.advance(T)
+
+    def phase(self, *, sweep: bool = False, act_agent: int = -1, obs_agent: int = -1, buffer=None,
+              actions: torch.Tensor | None = None, spawn_u=None, spawn_c=None, obs_out=None, reward_out=None,
+              new_turn: bool = False) -> None:
+        """One split-phase launch: [sweep] -> [act agent k] -> [observe agent j] (SB_MODE_SPLIT).
+
+        Lets a live policy run between `pov()` and `act()` of each agent exactly like
+        Agent.transition (agents/agent.py:155-173).  `new_turn` advances the tick first."""
+        if new_turn:
+            self.tick += 1
+        a = SbStepArgs()
+        a.mode = _abi.SB_MODE_SPLIT
+        a.num_turns = 1
+        a.tick0 = self.tick
+        a.seed = self.seed
+        a.rng = _abi.SB_RNG_TAPE if spawn_u is not None else _abi.SB_RNG_PHILOX
+        a.policy = _abi.SB_POLICY_TAPE if actions is not None else _abi.SB_POLICY_UNIFORM
+        a.do_sweep = 1 if sweep else 0
+        a.act_agent, a.obs_agent = act_agent, obs_agent
+        self._fill_ptrs(a, 1, actions, spawn_u, spawn_c, obs_out, reward_out, None, None)
+        bdesc = None
+        if buffer is not None:
+            a.slot0 = buffer.idx
+            bdesc = C.byref(buffer.desc())
+        check(self.lib.sb_step(C.byref(self.desc), C.byref(a), self.grid.data_ptr(), self.agent_pos.data_ptr(),
+                               self.total_reward.data_ptr(), bdesc, self._stream()), "sb_step(split)")
+
+    def _fill_ptrs(self, a, T, actions, spawn_u, spawn_c, obs_out, reward_out, action_out, drew_out):
+        N, A, ES = self.N, self.A, self.env_stride
+
+        def chk(t, shape, dtype, name):
+            if t is None:
+                return None
+            if t.device != self.grid.device or t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError(f"{name}: expected contiguous {dtype} {shape} on {self.grid.device}, "
+                                 f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+            return t.data_ptr()
+
+        a.d_actions = chk(actions, (T, N, A), torch.int32, "actions")
+        a.d_spawn_u = chk(spawn_u, (T, N, ES), torch.float64, "spawn_u")
+        a.d_spawn_c = chk(spawn_c, (T, N, ES), torch.uint8, "spawn_c")
+        a.d_obs_out = chk(obs_out, (T, N, A, self.spec.obs_size), torch.float32, "obs_out")
+        a.d_reward_out = chk(reward_out, (T, N, A), torch.float32, "reward_out")
+        a.d_action_out = chk(action_out, (T, N, A), torch.int32, "action_out")
+        a.d_drew_out = chk(drew_out, (T, N, ES), torch.uint8, "drew_out")
+        a.d_error = self.error.data_ptr()
+
+    def observe(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """ObservationSpec.observe for every (instance, agent): float32 [N, A, C, S, S]."""
+        s = self.spec
+        if out is None:
+            out = torch.empty((self.N, self.A, s.channels, s.obs_side, s.obs_side), dtype=torch.float32,
+                              device=self.device)
+        check(self.lib.sb_observe(C.byref(self.desc), self.grid.data_ptr(), self.agent_pos.data_ptr(),
+                                  out.data_ptr(), self._stream()), "sb_observe")
+        return out
+
+    def check_errors(self) -> None:
+        """Synchronising read of the device error word; raises the reference's exception type."""
+        bits = int(self.error.item())
+        if bits:
+            self.error.zero_()
+            raise _abi.error_bits_to_exception(bits)
+
+    # ------------------------------------------------------------------------------------------
+    def grid_numpy(self) -> np.ndarray:
+        """Read back all layers as uint8 [N, H, W, L] (static layers filled from the template)."""
+        s = self.spec
+        H, W, L = s.height, s.width, s.layers
+        out = np.broadcast_to(s.template[None], (self.N, H, W, L)).copy()
+        g = self.grid.cpu().numpy()
+        for pl, z in enumerate(self.dyn_layers):
+            out[:, :, :, z] = g[:, pl, : H * W].reshape(self.N, H, W)
+        return out
+
+    def agent_yx(self) -> np.ndarray:
+        """int64 [N, A, 2] agent locations (y, x)."""
+        p = self.agent_pos.cpu().numpy().astype(np.int64)
+        return np.stack([p // self.spec.width, p % self.spec.width], axis=-1)
