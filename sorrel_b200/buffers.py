@@ -90,10 +90,9 @@ class Buffer:
 
         def t(x, dtype, shape):
             x = torch.as_tensor(x, dtype=dtype, device=dev)
-            return x.expand(shape).contiguous() if x.shape != shape else x.contiguous()
+            return x.expand(shape).contiguous() if tuple(x.shape) != shape else x.contiguous()
 
-        obs = t(obs, torch.float32, (self.rows, self.obs_size)) if torch.as_tensor(obs).dim() <= 2 else \
-            torch.as_tensor(obs, dtype=torch.float32, device=dev).reshape(self.rows, self.obs_size).contiguous()
+        obs = torch.as_tensor(obs, dtype=torch.float32, device=dev).reshape(self.rows, self.obs_size).contiguous()
         action = t(action, torch.int64, (self.rows,))
         reward = t(reward, torch.float32, (self.rows,))
         done = t(done, torch.float32, (self.rows,))
@@ -102,7 +101,6 @@ class Buffer:
             pos = t(pos, torch.int64, (self.rows, 2))
         else:
             pos = None
-        self._desc = None if self._desc is None else self._desc
         check(self.lib.sb_buffer_add(C.byref(self.desc()), self.idx, obs.data_ptr(), action.data_ptr(),
                                      reward.data_ptr(), done.data_ptr(),
                                      pos.data_ptr() if pos is not None else None, self._stream()),
