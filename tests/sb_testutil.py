@@ -1,0 +1,76 @@
+"""Shared helpers for the test-suite: golden fixtures, oracle runs, oracle-spec -> engine-spec."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from oracle import restatement as R
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases(max_cells: int = 64 * 64, with_large: bool = False):
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
+        name = os.path.basename(f)[:-4]
+        if name == "observe_cases":
+            continue
+        if name.startswith("large") and not with_large:
+            continue
+        out.append(name)
+    return out
+
+
+def load_golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def spec_from_golden(g) -> R.WorldSpec:
+    return R.treasurehunt_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), float(g["p"]))
+
+
+def engine_spec(o: R.WorldSpec):
+    """oracle WorldSpec -> sorrel_b200.engine.WorldSpec (field-for-field)."""
+    from sorrel_b200.engine import WorldSpec
+
+    return WorldSpec(
+        height=o.height, width=o.width, layers=o.layers, kind_names=list(o.kind_names),
+        kind_value=list(o.kind_value), kind_passable=list(o.kind_passable), kind_rule=list(o.kind_rule),
+        appearance=np.array(o.appearance, dtype=np.float64), template=o.template.copy(),
+        spawnable=np.asarray(o.spawnable)[:, :2].copy(), agent_kind=o.agent_kind, agent_layer=o.agent_layer,
+        default_kind=o.default_kind, fill_kind=o.fill_kind, vision=o.vision, num_agents=o.num_agents,
+        spawn_prob=o.spawn_prob, spawn_choices=list(o.spawn_choices),
+        dynamic_layers=list(o.dynamic_layers) if o.dynamic_layers else None,
+    )
+
+
+def plane_stride(h: int, w: int) -> int:
+    return (h * w + 15) // 16 * 16
+
+
+def run_oracle_episode(spec: R.WorldSpec, draws, T: int, env_id: int = 0, capacity: int | None = None,
+                       n_frames: int = 1, tick0: int = 0):
+    """reset + T turns; returns the env (with tapes recorded) and per-turn grids."""
+    env = R.OracleEnv(spec, draws, env_id=env_id, capacity=capacity or T, n_frames=n_frames, record_tapes=True)
+    env.tick = tick0
+    env.reset()
+    grids = []
+    for _ in range(T):
+        env.take_turn()
+        grids.append(env.grid.copy())
+    return env, np.array(grids)
+
+
+def pad_tapes(spec: R.WorldSpec, tapes: dict):
+    """dense [T, Ldyn*H*W] tapes -> the kernel layout [T, Ldyn*plane_stride] (NaN / 255 padding)."""
+    HW = spec.height * spec.width
+    ps = plane_stride(spec.height, spec.width)
+    nd = len(spec.dynamic_layers)
+    T = tapes["actions"].shape[0]
+    u = np.full((T, nd, ps), np.nan, dtype=np.float64)
+    c = np.full((T, nd, ps), 255, dtype=np.uint8)
+    u[:, :, :HW] = tapes["spawn_u"].reshape(T, nd, HW)
+    c[:, :, :HW] = tapes["spawn_c"].reshape(T, nd, HW)
+    return u.reshape(T, nd * ps), c.reshape(T, nd * ps)

@@ -1,0 +1,461 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bit-exact everywhere (integer / byte / index work; observations are small integers held in f32).
+Nothing here reads /root/reference: golden results were generated from it ahead of time
+(oracle/gen_golden.py) and the oracle restatement regenerates the numpy draw tapes from seeds.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+import sb_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+SMALL_CASES = util.golden_cases()
+
+
+def _engine(spec, n, device, **kw):
+    from sorrel_b200.engine import Engine
+
+    return Engine(util.engine_spec(spec), n, device=device, **kw)
+
+
+def _buffer(spec, n, capacity, device, n_frames=1):
+    from sorrel_b200.buffers import Buffer
+
+    return Buffer(capacity, (spec.obs_size,), n_frames=n_frames, rows=n * spec.num_agents, device=device,
+                  positions=(2,))
+
+
+def _tapes_to_device(spec, env_tapes, device):
+    """list (per env) of oracle tapes -> stacked device tensors [T, N, ...]."""
+    us, cs = zip(*(util.pad_tapes(spec, t) for t in env_tapes))
+    spawn_u = torch.from_numpy(np.stack(us, axis=1)).to(device)
+    spawn_c = torch.from_numpy(np.stack(cs, axis=1)).to(device)
+    actions = torch.from_numpy(np.stack([t["actions"] for t in env_tapes], axis=1)).to(device)
+    placement = torch.from_numpy(np.stack([t["placement"] for t in env_tapes]).astype(np.int32)).to(device)
+    return spawn_u, spawn_c, actions, placement
+
+
+def _compare_buffers(buf, oracle_envs, A):
+    for n, env in enumerate(oracle_envs):
+        for a in range(A):
+            row = buf.row(n * A + a)
+            ob = env.buffers[a]
+            assert row["states"].dtype == np.float32 and row["actions"].dtype == np.int64
+            np.testing.assert_array_equal(row["states"], ob.states, err_msg=f"states env {n} agent {a}")
+            np.testing.assert_array_equal(row["actions"], ob.actions)
+            np.testing.assert_array_equal(row["rewards"], ob.rewards)
+            np.testing.assert_array_equal(row["dones"], ob.dones)
+            np.testing.assert_array_equal(row["positions"], ob.positions)
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. replayed numpy draws: golden fixtures (generated from the unmodified reference)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_golden_replay_per_turn(name, cuda_device):
+    """One launch per turn; every turn's grid, and all buffer arrays, equal the reference's."""
+    g = util.load_golden(name)
+    if int(g["epochs"]) != 1:
+        pytest.skip("multi-epoch fixture: covered by test_golden_ring")
+    spec = util.spec_from_golden(g)
+    T, A = int(g["T"]), int(g["A"])
+    env, grids = util.run_oracle_episode(spec, R.NumpyDraws(int(g["seed"])), T)
+    np.testing.assert_array_equal(grids, g["grids"])  # oracle == reference (also a CPU test)
+    spawn_u, spawn_c, actions, placement = _tapes_to_device(spec, [env.dense_tapes()], cuda_device)
+    eng = _engine(spec, 1, cuda_device)
+    buf = _buffer(spec, 1, T, cuda_device)
+    eng.reset(placement)
+    np.testing.assert_array_equal(eng.agent_yx()[0], g["starts"][0])
+    drew = torch.zeros((1, 1, eng.env_stride), dtype=torch.uint8, device=cuda_device)
+    for t in range(T):
+        eng.step(1, buffer=buf, actions=actions[t:t + 1].contiguous(), spawn_u=spawn_u[t:t + 1].contiguous(),
+                 spawn_c=spawn_c[t:t + 1].contiguous(), drew_out=drew)
+        np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][t], err_msg=f"turn {t}")
+        np.testing.assert_array_equal(drew.cpu().numpy()[0, 0] == 1, ~np.isnan(spawn_u[t, 0].cpu().numpy()))
+    eng.check_errors()
+    assert float(eng.total_reward[0]) == float(g["total_reward"][0])
+    for a in range(A):
+        row = buf.row(a)
+        for key in ("states", "actions", "rewards", "dones", "positions"):
+            assert row[key].dtype == g[key].dtype
+            np.testing.assert_array_equal(row[key], g[key][a], err_msg=key)
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_golden_replay_fused(name, cuda_device):
+    """All T turns in ONE launch (grid resident in shared memory): same final state and buffers."""
+    g = util.load_golden(name)
+    if int(g["epochs"]) != 1:
+        pytest.skip("multi-epoch fixture: covered by test_golden_ring")
+    spec = util.spec_from_golden(g)
+    T, A = int(g["T"]), int(g["A"])
+    env, _ = util.run_oracle_episode(spec, R.NumpyDraws(int(g["seed"])), T)
+    spawn_u, spawn_c, actions, placement = _tapes_to_device(spec, [env.dense_tapes()], cuda_device)
+    eng = _engine(spec, 1, cuda_device)
+    buf = _buffer(spec, 1, T, cuda_device)
+    eng.reset(placement)
+    rew = torch.zeros((T, 1, A), dtype=torch.float32, device=cuda_device)
+    eng.step(T, buffer=buf, actions=actions, spawn_u=spawn_u, spawn_c=spawn_c, reward_out=rew)
+    eng.check_errors()
+    np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][-1])
+    assert float(eng.total_reward[0]) == float(g["total_reward"][0])
+    for a in range(A):
+        row = buf.row(a)
+        for key in ("states", "actions", "rewards", "dones", "positions"):
+            np.testing.assert_array_equal(row[key], g[key][a], err_msg=key)
+        np.testing.assert_array_equal(rew[:, 0, a].cpu().numpy(), g["rewards"][a])
+
+
+def test_golden_large_map(cuda_device):
+    """128x128, 64 agents, 9x9 window (config 4 shape) against the reference's own two turns."""
+    g = util.load_golden("large_s4_a64_128")
+    spec = util.spec_from_golden(g)
+    T, A = int(g["T"]), int(g["A"])
+    env, _ = util.run_oracle_episode(spec, R.NumpyDraws(int(g["seed"])), T)
+    spawn_u, spawn_c, actions, placement = _tapes_to_device(spec, [env.dense_tapes()], cuda_device)
+    eng = _engine(spec, 1, cuda_device)
+    buf = _buffer(spec, 1, T, cuda_device)
+    eng.reset(placement)
+    eng.step(T, buffer=buf, actions=actions, spawn_u=spawn_u, spawn_c=spawn_c)
+    eng.check_errors()
+    np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][-1])
+    for a in range(A):
+        row = buf.row(a)
+        for key in ("states", "actions", "rewards", "dones", "positions"):
+            np.testing.assert_array_equal(row[key], g[key][a], err_msg=f"{key} agent {a}")
+
+
+@pytest.mark.parametrize("name", ["ring_s11_a2_11", "ring_s12_a1_21"])
+def test_golden_ring(name, cuda_device):
+    """Multi-epoch fixture: ring wrap, add_empty, current_state and sample against the reference."""
+    g = util.load_golden(name)
+    spec = util.spec_from_golden(g)
+    T, A, E, F, cap = int(g["T"]), int(g["A"]), int(g["epochs"]), int(g["n_frames"]), int(g["capacity"])
+    draws = R.NumpyDraws(int(g["seed"]))
+    oenv = R.OracleEnv(spec, draws, capacity=cap, n_frames=F, record_tapes=True)
+    eng = _engine(spec, 1, cuda_device)
+    buf = _buffer(spec, 1, cap, cuda_device, n_frames=F)
+    ci = 0
+    for ep in range(E):
+        oenv.tapes = {"spawn_u": [], "spawn_c": [], "actions": [], "placement": None}
+        oenv.reset()
+        for b in oenv.buffers:
+            b.add_empty()
+        for _ in range(T):
+            oenv.take_turn()
+        spawn_u, spawn_c, actions, placement = _tapes_to_device(spec, [oenv.dense_tapes()], cuda_device)
+        eng.reset(placement)
+        buf.add_empty()
+        # split the episode into launches of uneven length to exercise slot wrap inside a launch
+        t = 0
+        for chunk in (1, 7, T - 8):
+            sl = slice(t, t + chunk)
+            eng.step(chunk, buffer=buf, actions=actions[sl].contiguous(), spawn_u=spawn_u[sl].contiguous(),
+                     spawn_c=spawn_c[sl].contiguous())
+            t += chunk
+            cs = buf.current_state().cpu().numpy()  # [rows, F-1, obs]
+            np.testing.assert_array_equal(cs, g["current_states"][ci + t - 1])
+        ci += T
+        assert float(eng.total_reward[0]) == float(g["total_reward"][ep])
+    eng.check_errors()
+    assert buf.idx == int(g["buf_idx"][0]) and buf.size == int(g["buf_size"][0])
+    for a in range(A):
+        row = buf.row(a)
+        for key in ("states", "actions", "rewards", "dones", "positions"):
+            np.testing.assert_array_equal(row[key], g[key][a], err_msg=key)
+        # Buffer.sample gather on the reference's own drawn indices
+        idx = g["sample_idx"][a]
+        out = buf.gather(np.full(len(idx), a, dtype=np.int64), idx)
+        for o, key in zip(out, ("sample_states", "sample_actions", "sample_rewards", "sample_next_states",
+                                "sample_dones", "sample_valid")):
+            ref = g[key][a]
+            got = o.cpu().numpy()
+            assert got.dtype == ref.dtype and got.shape == ref.shape, key
+            np.testing.assert_array_equal(got, ref, err_msg=key)
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. many instances at once, replayed numpy streams (seed = instance id)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("A,H,v,p,T,N", [(1, 21, 2, 0.005, 100, 96), (8, 21, 2, 0.005, 40, 40),
+                                         (3, 9, 3, 0.15, 30, 33)])
+def test_batched_replay(A, H, v, p, T, N, cuda_device):
+    spec = R.treasurehunt_spec(H, H, A, v, p)
+    envs, tapes, finals = [], [], []
+    for n in range(N):
+        env, grids = util.run_oracle_episode(spec, R.NumpyDraws(1000 + n), T, env_id=n)
+        envs.append(env)
+        tapes.append(env.dense_tapes())
+        finals.append(grids[-1])
+    spawn_u, spawn_c, actions, placement = _tapes_to_device(spec, tapes, cuda_device)
+    eng = _engine(spec, N, cuda_device)
+    buf = _buffer(spec, N, T, cuda_device)
+    eng.reset(placement)
+    # two launches: T1 + T2 turns
+    T1 = T // 3
+    eng.step(T1, buffer=buf, actions=actions[:T1].contiguous(), spawn_u=spawn_u[:T1].contiguous(),
+             spawn_c=spawn_c[:T1].contiguous())
+    eng.step(T - T1, buffer=buf, actions=actions[T1:].contiguous(), spawn_u=spawn_u[T1:].contiguous(),
+             spawn_c=spawn_c[T1:].contiguous())
+    eng.check_errors()
+    np.testing.assert_array_equal(eng.grid_numpy(), np.stack(finals))
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), np.array([e.total_reward for e in envs]))
+    np.testing.assert_array_equal(eng.agent_yx(), np.stack([e.pos for e in envs]))
+    _compare_buffers(buf, envs, A)
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. counter-based mode (what the benchmark runs): kernels vs oracle with the same Philox stream
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("A,H,W,v,p,T,N,lpe", [
+    (1, 21, 21, 2, 0.005, 60, 70, None), (8, 21, 21, 2, 0.005, 25, 37, None), (2, 11, 14, 3, 0.3, 20, 19, None),
+    (4, 12, 12, 1, 0.9, 6, 9, None), (1, 21, 21, 2, 0.005, 30, 20, 8), (1, 21, 21, 2, 0.005, 30, 20, 32),
+    (3, 40, 40, 4, 0.01, 10, 6, None)])
+def test_philox_mode(A, H, W, v, p, T, N, lpe, cuda_device, monkeypatch):
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
+    seed, base = 0x1234ABCD5678, 5
+    spec = R.treasurehunt_spec(H, W, A, v, p)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    buf = _buffer(spec, N, T, cuda_device)
+    eng.reset()
+    eng.step(T, buffer=buf)
+    eng.check_errors()
+    envs = []
+    for n in range(N):
+        env, _ = util.run_oracle_episode(spec, R.PhiloxDraws(seed), T, env_id=base + n)
+        envs.append(env)
+    np.testing.assert_array_equal(eng.grid_numpy(), np.stack([e.grid for e in envs]))
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), np.array([e.total_reward for e in envs]))
+    _compare_buffers(buf, envs, A)
+
+
+def test_shard_invariance(cuda_device):
+    """N instances on one engine == the concatenation of two shards (rank offset env_id_base)."""
+    spec = R.treasurehunt_spec(21, 21, 2, 2, 0.01)
+    N, T = 64, 30
+    full = _engine(spec, N, cuda_device, seed=7)
+    fb = _buffer(spec, N, T, cuda_device)
+    full.reset()
+    full.step(T, buffer=fb)
+    parts = []
+    for r in range(2):
+        e = _engine(spec, N // 2, cuda_device, seed=7, env_id_base=r * N // 2)
+        b = _buffer(spec, N // 2, T, cuda_device)
+        e.reset()
+        e.step(T, buffer=b)
+        parts.append((e, b))
+    np.testing.assert_array_equal(full.grid_numpy(), np.concatenate([e.grid_numpy() for e, _ in parts]))
+    assert torch.equal(fb.states, torch.cat([b.states for _, b in parts]))
+    assert torch.equal(fb.rewards, torch.cat([b.rewards for _, b in parts], dim=1))
+
+
+def test_split_phase_equals_fused(cuda_device):
+    """Live-policy path: sweep+observe / act per agent (SB_MODE_SPLIT) == the fused launch."""
+    spec = R.treasurehunt_spec(21, 21, 3, 2, 0.02)
+    N, T, A = 50, 12, 3
+    fused = _engine(spec, N, cuda_device, seed=3)
+    fb = _buffer(spec, N, T, cuda_device)
+    fused.reset()
+    acts = torch.zeros((T, N, A), dtype=torch.int32, device=cuda_device)
+    fused.step(T, buffer=fb, action_out=acts)
+    split = _engine(spec, N, cuda_device, seed=3)
+    sb = _buffer(spec, N, T, cuda_device)
+    split.reset()
+    for t in range(T):
+        split.phase(sweep=True, obs_agent=0, buffer=sb, new_turn=True)
+        for a in range(A):
+            nxt = a + 1 if a + 1 < A else -1
+            split.phase(act_agent=a, obs_agent=nxt, buffer=sb, actions=acts[t:t + 1].contiguous())
+        sb.advance(1)
+    split.check_errors()
+    np.testing.assert_array_equal(split.grid_numpy(), fused.grid_numpy())
+    assert torch.equal(sb.states, fb.states) and torch.equal(sb.rewards, fb.rewards)
+    assert torch.equal(sb.actions, fb.actions) and torch.equal(sb.extra_data["positions"], fb.extra_data["positions"])
+    assert torch.equal(split.total_reward, fused.total_reward)
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. observation kernel alone
+# ------------------------------------------------------------------------------------------------
+def test_observe_golden_cases(cuda_device):
+    """sb_observe against OneHotObservationSpec.observe outputs captured from the reference on
+    random 1-3 layer worlds (every layer dynamic, sums over layers, heavy out-of-bounds fill)."""
+    from sorrel_b200.engine import Engine, WorldSpec
+
+    g = util.load_golden("observe_cases")
+    app = np.zeros((4, 4))
+    for k in range(1, 4):
+        app[k, k] = 1.0
+    for i in range(int(g["n"])):
+        kinds = g[f"kinds_{i}"]
+        v, y, x = (int(t) for t in g[f"meta_{i}"])
+        H, W, L = kinds.shape
+        spec = WorldSpec(height=H, width=W, layers=L, kind_names=["EmptyEntity", "Wall", "Gem", "Bone"],
+                         kind_value=[0, 0, 0, 0], kind_passable=[True] * 4, kind_rule=[0] * 4, appearance=app,
+                         template=kinds, spawnable=np.array([[0, 0]]), agent_kind=3, agent_layer=0,
+                         default_kind=0, fill_kind=1, vision=v, num_agents=1, dynamic_layers=list(range(L)))
+        eng = Engine(spec, 1, device=cuda_device)
+        eng.grid.copy_(eng.d_template[None])
+        eng.agent_pos[0, 0] = y * W + x
+        obs = eng.observe().cpu().numpy()[0, 0]
+        np.testing.assert_array_equal(obs.astype(np.float64), g[f"obs_{i}"], err_msg=f"case {i}")
+
+
+@pytest.mark.parametrize("general", [False, True])
+def test_observe_random(general, cuda_device):
+    """Fast one-hot path and the general table path (non one-hot appearance: f64 sum over layers,
+    static layer visible) against the oracle's closed form."""
+    rng = np.random.RandomState(5)
+    spec = R.treasurehunt_spec(13, 17, 5, 3, 0.0)
+    if general:
+        spec.appearance = rng.randint(0, 256, size=spec.appearance.shape).astype(np.float64)
+    N = 24
+    eng = _engine(spec, N, cuda_device)
+    eng.reset()
+    # scatter random items on the dynamic layer (not over walls / agents)
+    g = eng.grid.cpu().numpy()
+    mask = (g[:, 0, : 13 * 17] == 0) & (rng.rand(N, 13 * 17) < 0.4)
+    g[:, 0, : 13 * 17][mask] = rng.randint(2, 5, size=int(mask.sum()))
+    eng.grid.copy_(torch.from_numpy(g))
+    obs = eng.observe().cpu().numpy()
+    full = eng.grid_numpy()
+    yx = eng.agent_yx()
+    for n in range(N):
+        for a in range(5):
+            ref = R.observe(spec, full[n], int(yx[n, a, 0]), int(yx[n, a, 1])).astype(np.float32)
+            np.testing.assert_array_equal(obs[n, a], ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. replay ring primitives, reward statistics, reset
+# ------------------------------------------------------------------------------------------------
+def test_buffer_add_matches_reference_semantics(cuda_device):
+    from sorrel_b200.buffers import Buffer
+
+    rows, cap, obs, F = 6, 10, 14, 4
+    rng = np.random.RandomState(0)
+    buf = Buffer(cap, (obs,), n_frames=F, rows=rows, device=cuda_device, positions=(2,))
+    refs = [R.OracleBuffer(cap, obs, F) for _ in range(rows)]
+    for step in range(27):
+        if step % 9 == 0:
+            buf.add_empty()
+            for r in refs:
+                r.add_empty()
+        o = rng.rand(rows, obs).astype(np.float32)
+        a = rng.randint(0, 4, rows)
+        rw = rng.randn(rows).astype(np.float32)
+        dn = (rng.rand(rows) < 0.3).astype(np.float32)
+        pos = rng.randint(0, 21, (rows, 2))
+        buf.add(torch.from_numpy(o).to(cuda_device), a, rw, dn, positions=pos)
+        for r in range(rows):
+            refs[r].add(o[r], a[r], rw[r], dn[r], tuple(pos[r]))
+        cs = buf.current_state().cpu().numpy()
+        for r in range(rows):
+            np.testing.assert_array_equal(cs[r], refs[r].current_state())
+    assert buf.idx == refs[0].idx and len(buf) == refs[0].size
+    for r in range(rows):
+        row = buf.row(r)
+        np.testing.assert_array_equal(row["states"], refs[r].states)
+        np.testing.assert_array_equal(row["positions"], refs[r].positions)
+    # gather with dones present -> `valid` path
+    starts = np.array([0, 1, 2, 3, 4], dtype=np.int64)
+    for r in range(rows):
+        got = buf.gather(np.full(5, r), starts)
+        ref = refs[r].gather(starts)
+        for o_, r_ in zip(got, ref):
+            np.testing.assert_array_equal(o_.cpu().numpy(), r_)
+    with pytest.raises(ValueError):  # np.random.choice(replace=False) over-sampling, buffers.py:109
+        buf.sample(10_000)
+
+
+def test_reward_stats(cuda_device):
+    import ctypes as C
+
+    from sorrel_b200._abi import check, lib
+
+    L = lib()
+    for n in (1, 31, 4097, 300_001):
+        x = torch.from_numpy(np.random.RandomState(n).randint(-50, 80, n).astype(np.float64)).to(cuda_device)
+        out = torch.zeros(5, dtype=torch.float64, device=cuda_device)
+        scratch = torch.zeros(L.sb_stats_scratch_bytes(), dtype=torch.uint8, device=cuda_device)
+        for _ in range(2):  # the ticket must re-arm itself
+            check(L.sb_reward_stats(x.data_ptr(), n, out.data_ptr(), scratch.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream))
+            xs = x.cpu().numpy()
+            np.testing.assert_array_equal(out.cpu().numpy(),
+                                          np.array([xs.sum(), (xs * xs).sum(), xs.min(), xs.max(), n]))
+
+
+def test_reset_philox_placement(cuda_device):
+    spec = R.treasurehunt_spec(9, 9, 12, 2, 0.0)
+    N, seed = 40, 99
+    eng = _engine(spec, N, cuda_device, seed=seed, env_id_base=3)
+    for episode_tick in (0, 17):
+        eng.tick = episode_tick
+        eng.reset()
+        yx = eng.agent_yx()
+        for n in range(N):
+            picks = R.PhiloxDraws(seed).placement(len(spec.spawnable), 12, 3 + n, episode_tick + 1)
+            np.testing.assert_array_equal(yx[n], spec.spawnable[picks][:, :2])
+        g = eng.grid_numpy()
+        assert ((g[:, :, :, 1] == spec.agent_kind).sum(axis=(1, 2)) == 12).all()
+        assert (eng.total_reward == 0).all()
+
+
+def test_errors_and_validation(cuda_device):
+    spec = R.treasurehunt_spec(7, 7, 1, 2, 0.0)
+    spec.vision = 4  # > (H-1)//2: the reference silently returns a wrong-shaped crop
+    with pytest.raises(ValueError):
+        _engine(spec, 1, cuda_device)
+    # an unwalled world lets the agent step off the grid -> IndexError like the reference
+    spec = R.treasurehunt_spec(7, 7, 1, 2, 0.0)
+    spec.template[:, :, 1] = 0
+    spec.spawnable = np.array([[0, 0, 1]])
+    eng = _engine(spec, 1, cuda_device)
+    eng.reset(torch.zeros((1, 1), dtype=torch.int32))
+    acts = torch.zeros((1, 1, 1), dtype=torch.int32, device=cuda_device)  # "up" from row 0
+    eng.step(1, actions=acts)
+    with pytest.raises(IndexError):
+        eng.check_errors()
+    acts[:] = 7  # not an action
+    eng.step(1, actions=acts)
+    with pytest.raises(KeyError):
+        eng.check_errors()
+
+
+# ------------------------------------------------------------------------------------------------
+# 6. full-size property tests (sizes the oracle cannot replay in seconds)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_invariants(cuda_device):
+    """Config-2/5 shape at 262144 instances: size-independent invariants of the rule set."""
+    spec = R.treasurehunt_spec(21, 21, 1, 2, 0.005)
+    N, T, cap = 1 << 18, 50, 8
+    eng = _engine(spec, N, cuda_device, seed=11)
+    buf = _buffer(spec, N, cap, cuda_device)
+    eng.reset()
+    rew = torch.zeros((T, N, 1), dtype=torch.float32, device=cuda_device)
+    eng.step(T, buffer=buf, reward_out=rew)
+    eng.check_errors()
+    g = eng.grid[:, 0, : 21 * 21].view(N, 21, 21)
+    border = torch.ones((21, 21), dtype=torch.bool, device=cuda_device)
+    border[1:-1, 1:-1] = False
+    assert (g[:, border] == 1).all() and (g[:, ~border] != 1).all()  # walls never move or appear
+    assert ((g == 5).sum(dim=(1, 2)) == 1).all()  # exactly one agent per instance
+    pos = eng.agent_pos[:, 0].long()
+    assert (g.reshape(N, -1).gather(1, pos[:, None]) == 5).all()  # ... at its recorded position
+    assert torch.equal(eng.total_reward, rew.double().sum(dim=(0, 2)))  # reward bookkeeping
+    # spawn rate: items only appear through Bernoulli(p) on empty cells
+    items = ((g >= 2) & (g <= 4)).sum().item()
+    expect = N * T * 0.005 * 330  # ~330 empty cells on average over the episode start
+    assert 0.8 * expect < items < 1.2 * expect
+    # every observation row is a valid one-hot crop: 25 cells, each channel-sum <= 1, centre = agent
+    st = buf.states.view(N, cap, 6, 5, 5)
+    assert (st[:, :, 0] == 0).all() and (st.sum(dim=2) <= 1).all()
+    assert (st[:, :, 5, 2, 2] == 1).all()
