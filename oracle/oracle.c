@@ -1,0 +1,493 @@
+/*
+ * oracle.c -- plain C restatement of the reference step / observation / replay-buffer path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): used by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs as the CHECKER and the CPU baseline.  The product
+ * (sorrel_b200/) never links, loads or calls it.
+ *
+ * Follows (file:line relative to the reference root, social-ai-uoft/sorrel v1.4.0):
+ *   Environment.reset / take_turn        sorrel/environment.py:72-93
+ *   populate_environment                 sorrel/examples/treasurehunt/env.py:114-147
+ *   EmptyEntity.transition               sorrel/examples/treasurehunt/entities.py:69-85
+ *   Agent.transition / MovingAgent.act   sorrel/agents/agent.py:155-173, 187-225
+ *   Gridworld.observe / move             sorrel/worlds/gridworld.py:95-133
+ *   visual_field (closed form)           sorrel/observation/visual_field.py:9-101
+ *   Buffer.add                           sorrel/buffers.py:46-63
+ *
+ * Randomness (three interchangeable sources, same step code):
+ *   OR_RNG_NUMPY  -- own MT19937 + the numpy *legacy* RandomState draw algorithms (numpy is a
+ *                    third-party dependency of the reference, pinned ^2.5.0 in pyproject.toml:33,
+ *                    2.3.5 installed; its legacy stream is frozen by NEP 19): init_genrand seeding,
+ *                    random_sample = (a>>5, b>>6) 53-bit doubles, randint/choice = masked rejection on
+ *                    32-bit outputs, permutation = Fisher-Yates from the top with masked rejection.
+ *                    Validated against numpy itself in tests/test_coracle.py.
+ *   OR_RNG_PHILOX -- the engine's counter-based stream (Philox4x32-10).
+ *   tapes         -- OR_RNG_NUMPY can record the dense replay tapes the CUDA kernels consume.
+ *
+ * Parity status: pinned against tests/golden/ (generated from the unmodified reference).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#define OR_MAX_KINDS 32
+#define OR_MAX_LAYERS 8
+#define OR_RNG_NUMPY 0
+#define OR_RNG_PHILOX 1
+#define OR_RULE_SPAWN 1
+
+#define DOM_SWEEP 0x53570000u
+#define DOM_CELL 0x43450000u
+#define DOM_ACTION 0x41430000u
+#define DOM_RESET 0x52530000u
+
+/* ---------------------------------------------------------------------------------------------
+ * MT19937 + numpy legacy draws
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t key[624];
+  int pos;
+} mt_t;
+
+static void mt_seed(mt_t* s, uint32_t seed) { /* numpy mt19937_seed == init_genrand */
+  for (int i = 0; i < 624; ++i) {
+    s->key[i] = seed;
+    seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)i + 1u;
+  }
+  s->pos = 624;
+}
+
+static void mt_gen(mt_t* s) {
+  const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, A = 0x9908b0dfu;
+  uint32_t* k = s->key;
+  int i;
+  for (i = 0; i < 624 - 397; ++i) {
+    uint32_t y = (k[i] & UP) | (k[i + 1] & LO);
+    k[i] = k[i + 397] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+  }
+  for (; i < 623; ++i) {
+    uint32_t y = (k[i] & UP) | (k[i + 1] & LO);
+    k[i] = k[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+  }
+  uint32_t y = (k[623] & UP) | (k[0] & LO);
+  k[623] = k[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+  s->pos = 0;
+}
+
+static inline uint32_t mt_next32(mt_t* s) {
+  if (s->pos == 624) mt_gen(s);
+  uint32_t y = s->key[s->pos++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+/* RandomState.random_sample(): mt19937_next_double */
+static inline double np_random_sample(mt_t* s) {
+  uint32_t a = mt_next32(s) >> 5, b = mt_next32(s) >> 6;
+  return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+
+static inline uint32_t mask_ge(uint32_t m) {
+  m |= m >> 1;
+  m |= m >> 2;
+  m |= m >> 4;
+  m |= m >> 8;
+  m |= m >> 16;
+  return m;
+}
+
+/* RandomState.randint(0, n) / choice(n): masked rejection on 32-bit draws (n-1 < 2^32-1) */
+static inline uint32_t np_randint(mt_t* s, uint32_t n) {
+  uint32_t rng = n - 1;
+  if (rng == 0) return 0;
+  uint32_t mask = mask_ge(rng), v;
+  while ((v = (mt_next32(s) & mask)) > rng) {
+  }
+  return v;
+}
+
+/* RandomState.permutation(n)[:k]: arange + legacy shuffle (i = n-1..1, j = random_interval(i)) */
+static void np_permutation_head(mt_t* s, int n, int k, int32_t* out, int32_t* scratch) {
+  for (int i = 0; i < n; ++i) scratch[i] = i;
+  for (int i = n - 1; i >= 1; --i) {
+    uint32_t mask = mask_ge((uint32_t)i), j;
+    while ((j = (mt_next32(s) & mask)) > (uint32_t)i) {
+    }
+    int32_t t = scratch[i];
+    scratch[i] = scratch[j];
+    scratch[j] = t;
+  }
+  for (int i = 0; i < k; ++i) out[i] = scratch[i];
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Philox4x32-10 (Salmon et al., SC'11)
+ * ------------------------------------------------------------------------------------------- */
+static inline void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+
+static inline uint32_t bounded64(uint32_t hi, uint32_t lo, uint32_t n) {
+  return (uint32_t)(((unsigned __int128)(((uint64_t)hi << 32) | lo) * n) >> 64);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * world description / state
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t H, W, L, A, K, C, v;
+  int32_t n_dyn, dyn_layers[OR_MAX_LAYERS];
+  int32_t agent_layer, fill_kind, agent_kind, default_kind;
+  int32_t n_actions, dy[8], dx[8];
+  int32_t n_choices, choices[8];
+  int32_t n_spawnable;
+  double p;
+  float value[OR_MAX_KINDS];
+  uint8_t passable[OR_MAX_KINDS], rule[OR_MAX_KINDS];
+  const double* appearance; /* [K][C] */
+  const uint8_t* tmpl;      /* [H][W][L] (reference index order y, x, z) */
+  const int32_t* spawnable; /* [n_spawnable] y*W+x on the agent layer, reference order */
+} or_world_t;
+
+typedef struct {
+  or_world_t w;
+  int64_t N;
+  int rng_mode, threads, capacity, n_frames, obs_size, plane_stride, record;
+  uint64_t seed, env_id_base;
+  uint32_t tick; /* global turn counter */
+  int idx, size;
+  /* state */
+  uint8_t* grid; /* [N][H][W][L] */
+  int32_t* pos;  /* [N][A] cell index */
+  double* total; /* [N] */
+  mt_t* mt;      /* [N] numpy streams (seed = seed + n) */
+  /* ring, engine layout */
+  float* states;      /* [N*A][cap][obs] */
+  int64_t* actions;   /* [cap][N*A] */
+  float* rewards;     /* [cap][N*A] */
+  float* dones;       /* [cap][N*A] */
+  int64_t* positions; /* [cap][N*A][2] */
+  /* optional tapes of the last or_step call (kernel layout: padded planes) */
+  double* tape_u;   /* [T][N][n_dyn*plane_stride] */
+  uint8_t* tape_c;  /* same */
+  int32_t* tape_a;  /* [T][N][A] */
+  int32_t* tape_pl; /* [N][A] placement of the last reset */
+  int tape_T;
+  uint32_t hi8;
+  uint64_t lo45;
+} or_env_t;
+
+static int zd_of_layer(const or_world_t* w, int z) {
+  for (int i = 0; i < w->n_dyn; ++i)
+    if (w->dyn_layers[i] == z) return i;
+  return -1;
+}
+
+or_env_t* or_create(const or_world_t* w, int64_t N, int capacity, int n_frames, int rng_mode, uint64_t seed,
+                    uint64_t env_id_base, int threads, int record) {
+  or_env_t* e = (or_env_t*)calloc(1, sizeof(or_env_t));
+  e->w = *w;
+  e->N = N;
+  e->rng_mode = rng_mode;
+  e->seed = seed;
+  e->env_id_base = env_id_base;
+  e->threads = threads > 0 ? threads : 1;
+  e->capacity = capacity;
+  e->n_frames = n_frames;
+  e->record = record;
+  int S = 2 * w->v + 1;
+  e->obs_size = w->C * S * S;
+  e->plane_stride = (w->H * w->W + 15) / 16 * 16;
+  size_t cells = (size_t)w->H * w->W * w->L, rows = (size_t)N * w->A;
+  e->grid = (uint8_t*)malloc(N * cells);
+  e->pos = (int32_t*)calloc(rows, sizeof(int32_t));
+  e->total = (double*)calloc(N, sizeof(double));
+  if (rng_mode == OR_RNG_NUMPY) {
+    e->mt = (mt_t*)malloc(N * sizeof(mt_t));
+    for (int64_t n = 0; n < N; ++n) mt_seed(&e->mt[n], (uint32_t)(seed + (uint64_t)n));
+  }
+  if (capacity > 0) {
+    e->states = (float*)calloc(rows * capacity * e->obs_size, sizeof(float));
+    e->actions = (int64_t*)calloc(rows * capacity, sizeof(int64_t));
+    e->rewards = (float*)calloc(rows * capacity, sizeof(float));
+    e->dones = (float*)calloc(rows * capacity, sizeof(float));
+    e->positions = (int64_t*)calloc(rows * capacity * 2, sizeof(int64_t));
+  }
+  e->tape_pl = (int32_t*)calloc(rows, sizeof(int32_t));
+  double p = w->p;
+  uint64_t thr = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(p, 53)));
+  e->hi8 = (uint32_t)(thr >> 45);
+  e->lo45 = thr & ((1ull << 45) - 1);
+  return e;
+}
+
+void or_destroy(or_env_t* e) {
+  if (!e) return;
+  free(e->grid), free(e->pos), free(e->total), free(e->mt), free(e->states), free(e->actions);
+  free(e->rewards), free(e->dones), free(e->positions), free(e->tape_u), free(e->tape_c), free(e->tape_a);
+  free(e->tape_pl);
+  free(e);
+}
+
+/* Environment.reset (environment.py:72-79) + populate_environment (treasurehunt/env.py:114-147) */
+static void reset_range(or_env_t* e, int64_t n0, int64_t n1) {
+  const or_world_t* w = &e->w;
+  const size_t cells = (size_t)w->H * w->W * w->L;
+  int32_t* scratch = (int32_t*)malloc(sizeof(int32_t) * (w->n_spawnable > 0 ? w->n_spawnable : 1));
+  int32_t picks[64];
+  for (int64_t n = n0; n < n1; ++n) {
+    uint8_t* g = e->grid + n * cells;
+    memcpy(g, w->tmpl, cells);
+    e->total[n] = 0.0; /* create_world, gridworld.py:65 */
+    if (e->rng_mode == OR_RNG_NUMPY) {
+      /* np.random.choice(len(valid), size=A, replace=False) == permutation(len)[:A], env.py:141 */
+      np_permutation_head(&e->mt[n], w->n_spawnable, w->A, picks, scratch);
+    } else {
+      uint32_t env = (uint32_t)(e->env_id_base + (uint64_t)n), j = 0, r[4];
+      for (int a = 0; a < w->A; ++a) {
+        for (;;) {
+          philox(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
+          int32_t cand = (int32_t)bounded64(r[0], r[1], (uint32_t)w->n_spawnable);
+          int dup = 0;
+          for (int b = 0; b < a; ++b) dup |= picks[b] == cand;
+          if (!dup) {
+            picks[a] = cand;
+            break;
+          }
+        }
+      }
+    }
+    for (int a = 0; a < w->A; ++a) {
+      int cell = w->spawnable[picks[a]];
+      g[(size_t)cell * w->L + w->agent_layer] = (uint8_t)w->agent_kind; /* world.add, gridworld.py:67-76 */
+      e->pos[n * w->A + a] = cell;
+      e->tape_pl[n * w->A + a] = picks[a];
+    }
+  }
+  free(scratch);
+}
+
+/* closed form of visual_field (visual_field.py:9-101): float64 sum over layers in z order,
+ * stored as float32 (Buffer.states, buffers.py:31,56) */
+static void observe(const or_world_t* w, const uint8_t* g, int y, int x, float* out) {
+  const int S = 2 * w->v + 1, C = w->C;
+  for (int i = 0; i < S; ++i)
+    for (int j = 0; j < S; ++j) {
+      int yy = y - w->v + i, xx = x - w->v + j;
+      if (yy >= 0 && yy < w->H && xx >= 0 && xx < w->W) {
+        const uint8_t* cell = g + ((size_t)yy * w->W + xx) * w->L;
+        for (int c = 0; c < C; ++c) {
+          double s = 0.0;
+          for (int z = 0; z < w->L; ++z) s += w->appearance[cell[z] * C + c];
+          out[(c * S + i) * S + j] = (float)s;
+        }
+      } else {
+        for (int c = 0; c < C; ++c) out[(c * S + i) * S + j] = (float)w->appearance[w->fill_kind * C + c];
+      }
+    }
+}
+
+static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
+  const or_world_t* w = &e->w;
+  const size_t cells = (size_t)w->H * w->W * w->L, rows = (size_t)e->N * w->A;
+  uint8_t* g = e->grid + n * cells;
+  mt_t* mt = e->mt ? &e->mt[n] : 0;
+  const uint32_t env = (uint32_t)(e->env_id_base + (uint64_t)n);
+  const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
+  const size_t tape_stride = (size_t)w->n_dyn * e->plane_stride;
+  float obs_local[32 * 21 * 21];
+  for (int t = 0; t < T; ++t) {
+    const uint32_t tick = e->tick + 1 + (uint32_t)t;
+    double* tu = e->record ? e->tape_u + ((size_t)(t_base + t) * e->N + n) * tape_stride : 0;
+    uint8_t* tc = e->record ? e->tape_c + ((size_t)(t_base + t) * e->N + n) * tape_stride : 0;
+    /* entity sweep in C order (y, x, z) over the live map, environment.py:88-91 */
+    for (int y = 0; y < w->H; ++y)
+      for (int x = 0; x < w->W; ++x)
+        for (int z = 0; z < w->L; ++z) {
+          uint8_t* cellp = g + ((size_t)y * w->W + x) * w->L + z;
+          if (w->rule[*cellp] != OR_RULE_SPAWN) continue;
+          int zd = zd_of_layer(w, z);
+          uint32_t pcell = (uint32_t)(zd * e->plane_stride + y * w->W + x);
+          if (e->rng_mode == OR_RNG_NUMPY) {
+            double u = np_random_sample(mt); /* entities.py:73 */
+            if (tu) tu[pcell] = u;
+            if (u < w->p) {
+              uint32_t ci = np_randint(mt, (uint32_t)w->n_choices); /* np.random.choice, entities.py:75 */
+              if (tc) tc[pcell] = (uint8_t)ci;
+              *cellp = (uint8_t)w->choices[ci];
+            }
+          } else {
+            uint32_t r[4];
+            philox(env, tick, pcell >> 4, DOM_SWEEP, k0, k1, r);
+            uint32_t b = pcell & 15, r8 = (r[b >> 2] >> (8 * (b & 3))) & 0xFF;
+            if (r8 > e->hi8) continue;
+            philox(env, tick, pcell, DOM_CELL, k0, k1, r);
+            if (r8 == e->hi8) {
+              uint64_t refine = (((uint64_t)r[0] << 13) | (r[1] >> 19)) & ((1ull << 45) - 1);
+              if (!(refine < e->lo45)) continue;
+            }
+            *cellp = (uint8_t)w->choices[bounded64(r[2], r[3], (uint32_t)w->n_choices)];
+          }
+        }
+    /* agents in list order, agents/agent.py:155-173 */
+    for (int a = 0; a < w->A; ++a) {
+      const size_t row = (size_t)n * w->A + a;
+      int cell = e->pos[row], y = cell / w->W, x = cell % w->W;
+      int slot = e->capacity > 0 ? (e->idx + t) % e->capacity : 0;
+      float* obs = e->capacity > 0 ? e->states + (row * e->capacity + slot) * e->obs_size : obs_local;
+      observe(w, g, y, x, obs); /* pov(): state BEFORE the move */
+      int action;
+      if (e->rng_mode == OR_RNG_NUMPY) {
+        action = (int)np_randint(mt, (uint32_t)w->n_actions); /* RandomModel, base_model.py:111 */
+      } else {
+        uint32_t r[4];
+        philox(env, tick, (uint32_t)a, DOM_ACTION, k0, k1, r);
+        action = (int)bounded64(r[0], r[1], (uint32_t)w->n_actions);
+      }
+      if (e->record) e->tape_a[((size_t)(t_base + t) * e->N + n) * w->A + a] = action;
+      int ny = y + w->dy[action], nx = x + w->dx[action];
+      float reward = 0.0f;
+      if (ny >= 0 && ny < w->H && nx >= 0 && nx < w->W) {
+        uint8_t* tp = g + ((size_t)ny * w->W + nx) * w->L + w->agent_layer;
+        reward = w->value[*tp]; /* reward = target.value, agent.py:219-220 */
+        if (w->passable[*tp]) { /* Gridworld.move, gridworld.py:95-122 */
+          *tp = (uint8_t)w->agent_kind;
+          g[((size_t)y * w->W + x) * w->L + w->agent_layer] = (uint8_t)w->default_kind;
+          e->pos[row] = ny * w->W + nx;
+          y = ny, x = nx;
+        }
+      }
+      e->total[n] += (double)reward; /* agent.py:172 */
+      if (e->capacity > 0) {          /* Buffer.add, buffers.py:46-63; position AFTER the move */
+        size_t at = (size_t)slot * rows + row;
+        e->actions[at] = action;
+        e->rewards[at] = reward;
+        e->dones[at] = 0.0f; /* world.is_done is False during the episode */
+        e->positions[2 * at] = y;
+        e->positions[2 * at + 1] = x;
+      }
+    }
+  }
+}
+
+/* contiguous ranges of instances on plain pthreads (instances are independent) */
+typedef struct {
+  or_env_t* e;
+  int64_t n0, n1;
+  int T, do_reset;
+} job_t;
+
+static void* job_main(void* arg) {
+  job_t* j = (job_t*)arg;
+  if (j->do_reset) reset_range(j->e, j->n0, j->n1);
+  else
+    for (int64_t n = j->n0; n < j->n1; ++n) step_env(j->e, n, j->T, 0);
+  return 0;
+}
+
+static void run_parallel(or_env_t* e, int T, int do_reset) {
+  int nt = e->threads;
+  if (nt > e->N) nt = (int)e->N;
+  if (nt <= 1) {
+    job_t j = {e, 0, e->N, T, do_reset};
+    job_main(&j);
+    return;
+  }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nt);
+  job_t* jobs = (job_t*)malloc(sizeof(job_t) * nt);
+  for (int i = 0; i < nt; ++i) {
+    jobs[i].e = e;
+    jobs[i].n0 = e->N * i / nt;
+    jobs[i].n1 = e->N * (i + 1) / nt;
+    jobs[i].T = T;
+    jobs[i].do_reset = do_reset;
+    pthread_create(&th[i], 0, job_main, &jobs[i]);
+  }
+  for (int i = 0; i < nt; ++i) pthread_join(th[i], 0);
+  free(th), free(jobs);
+}
+
+void or_reset(or_env_t* e) { run_parallel(e, 0, 1); }
+
+/* T x Environment.take_turn for every instance (instance-major: one world stays in cache) */
+void or_step(or_env_t* e, int T) {
+  const or_world_t* w = &e->w;
+  if (e->record) {
+    const size_t tape_stride = (size_t)w->n_dyn * e->plane_stride;
+    free(e->tape_u), free(e->tape_c), free(e->tape_a);
+    size_t cnt = (size_t)T * e->N * tape_stride;
+    e->tape_u = (double*)malloc(cnt * sizeof(double));
+    e->tape_c = (uint8_t*)malloc(cnt);
+    e->tape_a = (int32_t*)malloc((size_t)T * e->N * w->A * sizeof(int32_t));
+    for (size_t i = 0; i < cnt; ++i) e->tape_u[i] = NAN;
+    memset(e->tape_c, 255, cnt);
+    e->tape_T = T;
+  }
+  run_parallel(e, T, 0);
+  e->tick += (uint32_t)T;
+  if (e->capacity > 0) {
+    e->idx = (e->idx + T) % e->capacity;
+    e->size = e->size + T < e->capacity ? e->size + T : e->capacity;
+  }
+}
+
+void or_add_empty(or_env_t* e) { /* buffers.py:65-69 */
+  e->idx = (e->idx + e->n_frames - 1) % e->capacity;
+  e->size = e->size + 1 < e->capacity ? e->size + 1 : e->capacity;
+}
+
+/* accessors for the ctypes wrapper */
+uint8_t* or_grid(or_env_t* e) { return e->grid; }
+int32_t* or_pos(or_env_t* e) { return e->pos; }
+double* or_total(or_env_t* e) { return e->total; }
+float* or_states(or_env_t* e) { return e->states; }
+int64_t* or_actions(or_env_t* e) { return e->actions; }
+float* or_rewards(or_env_t* e) { return e->rewards; }
+float* or_dones(or_env_t* e) { return e->dones; }
+int64_t* or_positions(or_env_t* e) { return e->positions; }
+double* or_tape_u(or_env_t* e) { return e->tape_u; }
+uint8_t* or_tape_c(or_env_t* e) { return e->tape_c; }
+int32_t* or_tape_a(or_env_t* e) { return e->tape_a; }
+int32_t* or_tape_placement(or_env_t* e) { return e->tape_pl; }
+int or_idx(or_env_t* e) { return e->idx; }
+int or_size(or_env_t* e) { return e->size; }
+void or_set_tick(or_env_t* e, uint32_t tick) { e->tick = tick; }
+int or_max_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+
+/* numpy-legacy stream probes (validated against numpy in tests/test_coracle.py) */
+void or_np_probe(uint32_t seed, int n_uniform, double* u_out, int n_randint, uint32_t bound, uint32_t* r_out,
+                 int perm_n, int perm_k, int32_t* p_out) {
+  mt_t s;
+  mt_seed(&s, seed);
+  for (int i = 0; i < n_uniform; ++i) u_out[i] = np_random_sample(&s);
+  for (int i = 0; i < n_randint; ++i) r_out[i] = np_randint(&s, bound);
+  if (perm_n > 0) {
+    int32_t* scratch = (int32_t*)malloc(sizeof(int32_t) * perm_n);
+    np_permutation_head(&s, perm_n, perm_k, p_out, scratch);
+    free(scratch);
+  }
+}
+
+void or_philox_probe(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}

@@ -1,0 +1,109 @@
+"""CPU: the C restatement (oracle/oracle.c) against numpy's legacy stream, the golden fixtures and
+the Python restatement."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import sb_testutil as util
+from oracle import coracle
+from oracle import restatement as R
+
+
+def test_numpy_legacy_stream_reimplementation():
+    """MT19937 seeding, random_sample, randint (masked rejection) and permutation vs numpy itself."""
+    L = coracle.lib()
+    for seed in list(range(40)) + [2**31 - 1, 2**32 - 1, 123456789]:
+        for bound, perm_n in ((3, 361), (4, 15876), (7, 49), (1, 2), (200, 1000)):
+            u = np.zeros(500)
+            r = np.zeros(300, dtype=np.uint32)
+            k = min(perm_n, 64)
+            p = np.zeros(k, dtype=np.int32)
+            L.or_np_probe(seed, 500, u.ctypes.data, 300, bound, r.ctypes.data, perm_n, k, p.ctypes.data)
+            rs = np.random.RandomState(seed)
+            np.testing.assert_array_equal(u, [rs.random_sample() for _ in range(500)])
+            np.testing.assert_array_equal(r, [rs.randint(0, bound) for _ in range(300)])
+            np.testing.assert_array_equal(p, rs.permutation(perm_n)[:k])
+
+
+def test_philox_matches_python():
+    L = coracle.lib()
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        ctr = rng.randint(0, 2**32, 4, dtype=np.uint64).astype(np.uint32)
+        key = rng.randint(0, 2**32, 2, dtype=np.uint64).astype(np.uint32)
+        out = np.zeros(4, dtype=np.uint32)
+        L.or_philox_probe(ctr.ctypes.data, key.ctypes.data, out.ctypes.data)
+        assert tuple(int(x) for x in out) == R.philox4x32_10(ctr, key)
+
+
+@pytest.mark.parametrize("name", util.golden_cases(with_large=True))
+def test_c_oracle_reproduces_reference(name):
+    g = util.load_golden(name)
+    spec = util.spec_from_golden(g)
+    T, E, F, A = int(g["T"]), int(g["epochs"]), int(g["n_frames"]), int(g["A"])
+    co = coracle.COracle(spec, 1, capacity=int(g["capacity"]), n_frames=F, rng=coracle.RNG_NUMPY,
+                         seed=int(g["seed"]))
+    per_turn = g["grids"].shape[0] == T * E
+    gi = 0
+    for ep in range(E):
+        co.reset()
+        yx = np.stack([co.pos[0] // spec.width, co.pos[0] % spec.width], axis=-1)
+        np.testing.assert_array_equal(yx, g["starts"][ep])
+        if F > 1:
+            co.add_empty()
+        if per_turn:
+            for t in range(T):
+                co.step(1)
+                np.testing.assert_array_equal(co.grid[0], g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+                gi += 1
+        else:
+            co.step(T)
+            np.testing.assert_array_equal(co.grid[0], g["grids"][ep])
+        assert co.total_reward[0] == float(g["total_reward"][ep])
+    ring = co.ring()
+    for a in range(A):
+        np.testing.assert_array_equal(ring["states"][a], g["states"][a])
+        np.testing.assert_array_equal(ring["actions"][:, a], g["actions"][a])
+        np.testing.assert_array_equal(ring["rewards"][:, a], g["rewards"][a])
+        np.testing.assert_array_equal(ring["dones"][:, a], g["dones"][a])
+        np.testing.assert_array_equal(ring["positions"][:, a], g["positions"][a])
+    assert co.idx == int(g["buf_idx"][0]) and co.size == int(g["buf_size"][0])
+
+
+@pytest.mark.parametrize("A,H,W,v,p,T,N", [(1, 21, 21, 2, 0.005, 40, 12), (5, 9, 12, 2, 0.3, 15, 7),
+                                           (2, 8, 8, 1, 1.0, 5, 3)])
+def test_c_oracle_philox_equals_python(A, H, W, v, p, T, N):
+    """Counter-based mode: C (multi-threaded) == Python restatement, including the tapes layout."""
+    spec = R.treasurehunt_spec(H, W, A, v, p)
+    seed, base = 0xDEADBEEF1234, 11
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
+    co.reset()
+    co.step(T // 2)
+    co.step(T - T // 2)
+    ring = co.ring()
+    for n in range(N):
+        env, _ = util.run_oracle_episode(spec, R.PhiloxDraws(seed), T, env_id=base + n)
+        np.testing.assert_array_equal(co.grid[n], env.grid)
+        assert co.total_reward[n] == env.total_reward
+        for a in range(A):
+            np.testing.assert_array_equal(ring["states"][n * A + a], env.buffers[a].states)
+            np.testing.assert_array_equal(ring["positions"][:, n * A + a], env.buffers[a].positions)
+
+
+def test_c_oracle_tapes_equal_python_tapes():
+    spec = R.treasurehunt_spec(11, 13, 3, 2, 0.05)
+    T, N = 20, 5
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_NUMPY, seed=500, record=True, threads=2)
+    co.reset()
+    co.step(T)
+    ct = co.tapes()
+    for n in range(N):
+        env, _ = util.run_oracle_episode(spec, R.NumpyDraws(500 + n), T)
+        u, c = util.pad_tapes(spec, env.dense_tapes())
+        np.testing.assert_array_equal(ct["spawn_u"][:, n], u)
+        np.testing.assert_array_equal(ct["spawn_c"][:, n], c)
+        np.testing.assert_array_equal(ct["actions"][:, n], env.dense_tapes()["actions"])
+        np.testing.assert_array_equal(ct["placement"][n], env.dense_tapes()["placement"])
