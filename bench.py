@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- agent-env-steps/s (including observations) of the batched gridworld engine.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on host cores
+
+Workload (BASELINE.json configs[4], the one the metric "at 1/2/4/8 B200" is quoted on):
+2^20 treasurehunt worlds in total (21x21x2, 1 agent, 5x5 one-hot view, C=6, spawn_prob 0.005,
+episodes of 100 turns), sharded over the ranks with no collective on the step path.  One *step* =
+one launch of `--turns` fused turns for every instance of the rank (entity sweep, observation written
+straight into the replay ring, move, reward, Buffer.add) followed by one Buffer.sample gather of
+turns*N/64 transitions (5 stacked frames); every 100 turns the worlds are reset (and `add_empty`
+advances the ring) exactly like Environment.run_experiment, and the per-episode reward statistics are
+all-reduced (the only collective).  `value` times that with everything resident in HBM; `e2e` drives the
+same launch from pinned HOST action buffers and reads the rewards back to the host every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "agent_env_steps_per_sec_incl_obs"
+UNIT = "agent-env-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-total", type=int, default=1 << 20, help="world instances over all ranks")
+    ap.add_argument("--turns", type=int, default=25, help="fused turns per launch (one step)")
+    ap.add_argument("--agents", type=int, default=1)
+    ap.add_argument("--size", type=int, default=21)
+    ap.add_argument("--vision", type=int, default=2)
+    ap.add_argument("--spawn-prob", type=float, default=0.005)
+    ap.add_argument("--capacity", type=int, default=32, help="replay ring rows per agent")
+    ap.add_argument("--n-frames", type=int, default=5)
+    ap.add_argument("--max-turns", type=int, default=100)
+    ap.add_argument("--sample-div", type=int, default=64, help="sample 1 transition per this many agent-steps; 0 = off")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"treasurehunt {a.size}x{a.size}x2, {a.agents} agent(s)/env, v={a.vision} one-hot C=6, "
+            f"{a.envs_total} envs total, {a.turns} turns/launch, ring cap {a.capacity}, F={a.n_frames}, "
+            f"sample 1/{a.sample_div}")
+
+
+def alg_bytes_per_env_step(a) -> int:
+    """2*H*W*L_dyn + A*(C*S^2*4 + 36) + 8."""
+    S = 2 * a.vision + 1
+    return 2 * a.size * a.size * 1 + a.agents * (6 * S * S * 4 + 36) + 8
+
+
+def oracle_spec(a):
+    from oracle import restatement as R
+
+    return R.treasurehunt_spec(a.size, a.size, a.agents, a.vision, a.spawn_prob)
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C port (the reference is pure Python and cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------------
+def cpu_port_throughput(a, seconds: float, threads: int | None = None):
+    from oracle import coracle
+
+    threads = threads or coracle.max_threads()
+    spec = oracle_spec(a)
+    n = max(threads * 64, 1024)
+    co = coracle.COracle(spec, n, capacity=a.capacity, n_frames=a.n_frames, rng=coracle.RNG_NUMPY, seed=a.seed,
+                         threads=threads)
+    co.reset()
+    co.add_empty()
+    co.step(a.turns)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    turns_in_episode = a.turns
+    while True:
+        if turns_in_episode >= a.max_turns:
+            co.reset()
+            co.add_empty()
+            turns_in_episode = 0
+        co.step(a.turns)
+        turns_in_episode += a.turns
+        done += n * a.agents * a.turns
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} envs x {done // (n * a.agents)} turns of the same workload (C oracle port, "
+                      f"numpy-legacy MT19937 draws, {threads} pthreads), {dt:.1f} s"}
+
+
+def python_port_throughput(a, seconds: float = 3.0):
+    """The Python restatement (same loop structure as the reference's Python) on one core."""
+    from oracle import restatement as R
+
+    env = R.OracleEnv(oracle_spec(a), R.NumpyDraws(a.seed), capacity=a.capacity, n_frames=a.n_frames)
+    env.reset()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        env.take_turn()
+        n += a.agents
+    return n / (time.perf_counter() - t0)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    per_step = max(1.0, a.cpu_seconds / max(1, a.steps + a.warmup))
+    vals = []
+    for i in range(a.warmup + a.steps):
+        r = cpu_port_throughput(a, per_step)
+        if i >= a.warmup:
+            vals.append(r["value"])
+    value = sum(vals) / len(vals)
+    r["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "CPU arm: oracle C port on host cores, bounded sample"},
+        "cpu_baseline": r,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[6]) for r in rows if len(r) > 6 and r[6].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from sorrel_b200.buffers import Buffer
+    from sorrel_b200.engine import Engine
+    from sorrel_b200.stats import RewardStats
+    import sb_testutil as util
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert a.envs_total % world == 0
+    N = a.envs_total // world
+    T, A = a.turns, a.agents
+    spec = util.engine_spec(oracle_spec(a))
+    eng = Engine(spec, N, device=dev, env_id_base=rank * N, seed=a.seed)
+    buf = Buffer(a.capacity, (spec.obs_size,), n_frames=a.n_frames, rows=N * A, device=dev, positions=(2,))
+    stats = RewardStats(dev)
+    lib = eng.lib
+    B = (T * N * A) // a.sample_div if a.sample_div else 0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+
+    turns_in_episode = [a.max_turns]  # forces a reset at the first step
+    episode_stats = []
+
+    def one_step(ev0=None, ev1=None, actions=None, reward_out=None):
+        if turns_in_episode[0] >= a.max_turns:  # Environment.run_experiment epoch boundary
+            if eng.tick > 0:
+                episode_stats.append(stats.all_reduce(eng.total_reward))  # NCCL, <= 40 bytes
+            eng.reset()
+            buf.add_empty()
+            turns_in_episode[0] = 0
+        if ev0 is not None:
+            ev0.record()
+        eng.step(T, buffer=buf, actions=actions, reward_out=reward_out)
+        if ev1 is not None:
+            ev1.record()
+        turns_in_episode[0] += T
+        if B:
+            hi = max(1, buf.size - buf.n_frames - 1)
+            rows = torch.randint(0, N * A, (B,), device=dev, generator=gen)
+            starts = torch.randint(0, hi, (B,), device=dev, generator=gen)
+            return buf.gather(rows, starts)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value") ----------------
+    for _ in range(a.warmup):
+        one_step()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = lib.sb_launch_count()
+    t_wall0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(a.steps):
+        one_step(*evs[i])
+    g1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = lib.sb_launch_count() - l0
+    ms_total = g0.elapsed_time(g1)
+    eng.check_errors()
+    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
+    steps_total = a.envs_total * A * T * a.steps
+    value = steps_total / (ms_total * 1e-3)
+
+    # ---------------- end-to-end with host buffers ----------------
+    e2e = None
+    if not a.no_e2e:
+        from sorrel_b200.hostio import HostStepPipeline
+
+        pipe = HostStepPipeline(eng, buf, T)
+        h_actions = [torch.randint(0, 4, (T, N, A), dtype=torch.int32).pin_memory() for _ in range(2)]
+        for i in range(max(2, a.warmup // 2)):
+            if turns_in_episode[0] >= a.max_turns:
+                eng.reset()
+                buf.add_empty()
+                turns_in_episode[0] = 0
+            pipe.submit(h_actions[i % 2])
+            turns_in_episode[0] += T
+        pipe.drain()
+        barrier()
+        t0 = time.perf_counter()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(a.steps):
+            if turns_in_episode[0] >= a.max_turns:
+                eng.reset()
+                buf.add_empty()
+                turns_in_episode[0] = 0
+            pipe.submit(h_actions[i % 2])
+            turns_in_episode[0] += T
+        results = pipe.drain()
+        c1.record()
+        barrier()
+        e2e_ms = max(c0.elapsed_time(c1), 1e3 * (time.perf_counter() - t0))
+        te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item())
+        e2e = {"value": steps_total / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
+               "ms_per_step": e2e_ms / a.steps, "reward_checksum": float(results)}
+        eng.check_errors()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_per_launch = alg_bytes_per_env_step(a) * N * T
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("step_kernel_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "sb::step_kernel", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                "step_kernel_share_of_step": k_ms * a.steps / (ms_total if world == 1 else ms_total)}
+
+    cpu = None
+    if not a.no_cpu:
+        cpu = cpu_port_throughput(a, a.cpu_seconds)
+        cpu["python_port_1core"] = python_port_throughput(a, 2.0)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a), "envs_per_gpu": N, "parallelism": f"env-shard x{world}",
+                   "l2": "inputs larger than L2 (grid + ring slots touched per step >> 126 MB)",
+                   "policy": "in-kernel uniform (RandomModel)", "rng": "philox4x32-10"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
+        "episodes_reduced": len(episode_stats),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

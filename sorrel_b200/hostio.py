@@ -1,0 +1,57 @@
+"""Host-facing stepping: actions arrive in pinned HOST memory, rewards go back to the host.
+
+`HostStepPipeline.submit(host_actions)` is the end-to-end form of `Environment.take_turn` for a
+caller whose policy lives on the host: H2D copy of the step's actions, the fused step launch
+(observations stay in HBM, written straight into the replay ring), D2H copy of the step's rewards.
+The three stages run on three CUDA streams with `depth` buffers in flight, so the copies of step
+i+1 / i-1 overlap the kernel of step i.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class HostStepPipeline:
+    def __init__(self, engine, buffer, turns: int, depth: int = 2):
+        self.eng, self.buf, self.T, self.depth = engine, buffer, int(turns), depth
+        dev, N, A = engine.device, engine.N, engine.A
+        shape = (self.T, N, A)
+        self.d_actions = [torch.empty(shape, dtype=torch.int32, device=dev) for _ in range(depth)]
+        self.d_rewards = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.h_rewards = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.s_h2d, self.s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        mk = lambda: [torch.cuda.Event() for _ in range(depth)]  # noqa: E731
+        self.ev_h2d, self.ev_compute, self.ev_d2h = mk(), mk(), mk()
+        self.i = 0
+        self.h2d_bytes = self.d_actions[0].numel() * 4
+        self.d2h_bytes = self.d_rewards[0].numel() * 4
+
+    def submit(self, h_actions: torch.Tensor) -> torch.Tensor:
+        """Enqueue one step driven by `h_actions` (pinned int32 [T, N, A]).  Returns the pinned host
+        reward buffer this step will fill (valid after `wait(slot)` / `drain()`)."""
+        k = self.i % self.depth
+        cur = torch.cuda.current_stream(self.eng.device)
+        if self.i >= self.depth:
+            self.ev_d2h[k].synchronize()  # the host buffer of slot k is about to be reused
+        with torch.cuda.stream(self.s_h2d):
+            self.s_h2d.wait_event(self.ev_compute[k])  # kernel that read d_actions[k] is done
+            self.d_actions[k].copy_(h_actions, non_blocking=True)
+            self.ev_h2d[k].record(self.s_h2d)
+        cur.wait_event(self.ev_h2d[k])
+        cur.wait_event(self.ev_d2h[k])  # previous read-back of d_rewards[k] is done
+        self.eng.step(self.T, buffer=self.buf, actions=self.d_actions[k], reward_out=self.d_rewards[k])
+        self.ev_compute[k].record(cur)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_compute[k])
+            self.h_rewards[k].copy_(self.d_rewards[k], non_blocking=True)
+            self.ev_d2h[k].record(self.s_d2h)
+        self.i += 1
+        return self.h_rewards[k]
+
+    def drain(self) -> float:
+        """Wait for everything in flight; returns a checksum of the last step's host rewards."""
+        self.s_h2d.synchronize()
+        self.s_d2h.synchronize()
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        last = (self.i - 1) % self.depth if self.i else 0
+        return float(self.h_rewards[last].sum())
