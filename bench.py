@@ -19,7 +19,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -53,6 +52,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks")
     return ap.parse_args()
 
 
@@ -148,37 +148,57 @@ def run_reference(a):
 # clocks sampler
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+    """Samples SM clock / throttle reasons DURING the timed region through NVML in a thread
+    (in-process and cheap, so that sampling does not perturb the launches it observes)."""
 
-    def __init__(self, index: int):
-        self.rows, self.proc = [], None
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int, period: float = 0.05):
+        self.rows, self.ok, self.period, self._stop = [], False, period, threading.Event()
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as exc:  # noqa: BLE001
+            self.err = repr(exc)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.perf_counter(), sm, reasons, power))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
-        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
-        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        pw = [float(r[6]) for r in rows if len(r) > 6 and r[6].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"]}
+        self._stop.set()
+        self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": [n for b, n in self.REASONS.items() if bits & b], "samples": len(rows),
+                "power_w_max": max((r[3] for r in rows), default=None)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -215,26 +235,40 @@ def run_ours(a):
 
     turns_in_episode = [a.max_turns]  # forces a reset at the first step
     episode_stats = []
+    seg = {"boundary": [], "step": [], "sample": []}  # (event, event) pairs per segment, timed steps only
 
-    def one_step(ev0=None, ev1=None, actions=None, reward_out=None):
+    def mark(name, record):
+        if not record:
+            return None
+        e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        seg[name].append(e)
+        e[0].record()
+        return e
+
+    def one_step(record=False, actions=None, reward_out=None):
         if turns_in_episode[0] >= a.max_turns:  # Environment.run_experiment epoch boundary
-            if eng.tick > 0:
-                episode_stats.append(stats.all_reduce(eng.total_reward))  # NCCL, <= 40 bytes
+            e = mark("boundary", record)
+            episode_stats.append(stats.all_reduce(eng.total_reward))  # NCCL all_gather, 40 bytes per rank
             eng.reset()
             buf.add_empty()
             turns_in_episode[0] = 0
-        if ev0 is not None:
-            ev0.record()
+            if e:
+                e[1].record()
+        e = mark("step", record)
         eng.step(T, buffer=buf, actions=actions, reward_out=reward_out)
-        if ev1 is not None:
-            ev1.record()
+        if e:
+            e[1].record()
         turns_in_episode[0] += T
+        out = None
         if B:
+            e = mark("sample", record)
             hi = max(1, buf.size - buf.n_frames - 1)
             rows = torch.randint(0, N * A, (B,), device=dev, generator=gen)
             starts = torch.randint(0, hi, (B,), device=dev, generator=gen)
-            return buf.gather(rows, starts)
-        return None
+            out = buf.gather(rows, starts)
+            if e:
+                e[1].record()
+        return out
 
     def barrier():
         if world > 1:
@@ -242,24 +276,26 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ("value") ----------------
-    for _ in range(a.warmup):
+    # warm-up: at least W steps AND one full episode boundary (stats + reset kernels get loaded)
+    warm = max(a.warmup, a.max_turns // T + 1)
+    for _ in range(warm):
         one_step()
     barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    clocks = ClockSampler(local) if rank == 0 else None
+    clocks = ClockSampler(local) if (rank == 0 and not a.no_clocks) else None
     l0 = lib.sb_launch_count()
     t_wall0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for i in range(a.steps):
-        one_step(*evs[i])
+        one_step(record=True)
     g1.record()
     barrier()
     t_wall1 = time.perf_counter()
     launches = lib.sb_launch_count() - l0
     ms_total = g0.elapsed_time(g1)
     eng.check_errors()
-    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in seg["step"]]
+    breakdown = {k: sum(e0.elapsed_time(e1) for e0, e1 in v) / a.steps for k, v in seg.items()}
     tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -328,7 +364,7 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "sb::step_kernel", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                "step_kernel_share_of_step": k_ms * a.steps / (ms_total if world == 1 else ms_total)}
+                "step_kernel_share_of_step": k_ms * a.steps / ms_total, "breakdown_ms_per_step": breakdown}
 
     cpu = None
     if not a.no_cpu:

@@ -120,6 +120,11 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     d.dx_packed |= (uint64_t)(uint8_t)w->action_dx[i] << (8 * i);
   }
   d.simd_sweep = (d.single_spawn_kind >= 0 && d.hi8 + 1u <= 128u) ? 1 : 0;
+  {
+    uint32_t n2 = 1;
+    while (n2 < d.hi8 + 1u) n2 <<= 1;
+    d.hmask4 = ((~(n2 - 1u)) & 0xFFu) * 0x01010101u;
+  }
   // one-hot fast path: every appearance row is all-zero or exactly one 1.0
   d.fast_obs = w->static_layers_invisible || d.n_planes == d.L ? 1 : 0;
   for (int k = 0; k < d.K; ++k) {

@@ -33,7 +33,8 @@ struct SbDev {
   int32_t fast_obs;           // appearance rows are zero / one-hot and static layers invisible
   int32_t fill_channel;       // fast path: channel of the fill kind (or 255 = none)
   int32_t single_spawn_kind;  // >= 0 when exactly one kind carries SB_RULE_SPAWN
-  int32_t simd_sweep;         // byte-SIMD candidate test usable (single spawn kind, hi8 < 128)
+  int32_t simd_sweep;         // byte-SIMD candidate filter usable (single spawn kind, hi8 < 128)
+  uint32_t hmask4;            // ~(n2 - 1) replicated in 4 bytes, n2 = smallest power of two > hi8
   uint32_t passable_mask, spawn_mask;  // bit k: kind k passable / has SB_RULE_SPAWN
   uint32_t hi8;                        // top 8 bits of the 53-bit spawn threshold
   uint64_t lo45;                       // low 45 bits
@@ -125,24 +126,21 @@ SB_HD int sb_resolve_spawn(const SbDev& d, uint32_t env, uint32_t tick, uint32_t
   return (int)((d.choices_packed >> (8 * ci)) & 0xFFu);
 }
 
-// Byte-SIMD first level for one 16-cell chunk: bit (8*b+7) of the returned words' union is
-// condensed into a 16-bit mask: bit b set iff kinds[b] == single_spawn_kind and r8[b] <= hi8.
-// Requires d.simd_sweep (hi8 + 1 <= 128).
-SB_HD uint32_t sb_simd_cand_word(uint32_t kinds, uint32_t rnd, uint32_t spawn4, uint32_t n4c) {
-  // zero-byte detect on kinds ^ spawn4 (exact per byte)
-  uint32_t x = kinds ^ spawn4;
+// Byte-SIMD first-level FILTER for 4 cells (one 32-bit word of kinds / random bytes): returns 0x80 in
+// every byte whose kind == single_spawn_kind and whose random byte r8 < n2, n2 = 2^k >= hi8 + 1
+// (`hmask4` = ~(n2-1) replicated).  A superset of {r8 <= hi8}: the exact comparison happens when the
+// candidate is resolved.  One zero-byte detection on (kinds ^ spawn4) | (rnd & hmask4).
+SB_HD uint32_t sb_simd_cand_word(uint32_t kinds, uint32_t rnd, uint32_t spawn4, uint32_t hmask4) {
+  uint32_t x = (kinds ^ spawn4) | (rnd & hmask4);
   uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-  uint32_t eq = ~(t | x | 0x7F7F7F7Fu);  // 0x80 where byte == 0
-  // per-byte rnd < n  (n <= 128):  s = (rnd & 0x7F) + (128 - n): bit7 set iff low7 >= n
-  uint32_t s = (rnd & 0x7F7F7F7Fu) + n4c;  // n4c = (128 - n) replicated
-  uint32_t lt = ~(s | rnd) & 0x80808080u;
-  return eq & lt;
+  return ~(t | x | 0x7F7F7F7Fu);  // 0x80 where the byte of x is zero (exact, no cross-byte carries)
 }
 
-SB_HD uint32_t sb_pack_mask(uint32_t m) {
-  // gather bits 7,15,23,31 -> bits 0..3
-  m >>= 7;
-  return (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+// Candidate mask of a 16-cell chunk: bit (8*b + w) set <=> byte b of word w is a candidate.
+SB_HD uint32_t sb_simd_cand_chunk(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t r0, uint32_t r1,
+                                  uint32_t r2, uint32_t r3, uint32_t spawn4, uint32_t hmask4) {
+  return (sb_simd_cand_word(k0, r0, spawn4, hmask4) >> 7) | (sb_simd_cand_word(k1, r1, spawn4, hmask4) >> 6) |
+         (sb_simd_cand_word(k2, r2, spawn4, hmask4) >> 5) | (sb_simd_cand_word(k3, r3, spawn4, hmask4) >> 4);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -26,6 +26,8 @@ struct StepParams {
   uint8_t* grid;
   int32_t* agent_pos;
   double* total_reward;
+  // shared-memory layout, computed once on the host (sb_step.cu: launch_one)
+  int32_t lut_bytes, q_bytes, env_smem, stage_off;
 };
 
 int note_cuda_error();  // records cudaGetLastError() text for sb_last_cuda_error, returns SB_ECUDA

@@ -12,7 +12,7 @@
 // planes are staged in shared memory for the whole launch (all `num_turns` turns), so the grid is
 // read and written once per launch while every turn streams one observation row per agent straight
 // into its replay-ring slot with 128-bit stores.  Groups never talk to each other; the only
-// intra-warp cooperation is the per-warp spawn-candidate queue (see sweep_philox_simd).
+// intra-warp cooperation is the per-warp spawn-candidate queue of the Philox sweep.
 #include <cuda_runtime.h>
 
 #include "sb_core.cuh"
@@ -20,24 +20,22 @@
 
 namespace sb {
 
-template <int LPE>
-struct Smem {
-  uint16_t* lut_e;   // [obs_size]  (channel << 9) | window index
-  uint16_t* lut_ij;  // [SS]        (i << 8) | j
-  uint32_t* q;       // [warps][SB_QCAP] spawn candidates of the warp's instances
-  uint32_t* qn;      // [warps]
-  uint8_t* envs;     // [EPB][env_smem]
-};
-
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// bytes of shared memory per instance: planes + agent yx + agent actions + window codes
+// Shared memory per instance: dynamic planes | agent yx[A] | agent actions[A] | staging row.
+// The staging row holds ONE observation (obs_size floats + 4 of alignment slack); it is all-zero
+// between observations.  The per-instance size is padded to 64 (mod 128) bytes so that the two
+// groups served by one quarter-warp of a 128-bit shared-memory access hit disjoint banks.
+__host__ __device__ inline int stage_offset_bytes(const SbDev& d) { return round_up(d.env_stride + 8 * d.A, 16); }
+
 __host__ __device__ inline int env_smem_bytes(const SbDev& d) {
-  return round_up(d.env_stride + 8 * d.A + d.SS * d.n_planes, 16);
+  int b = round_up(stage_offset_bytes(d) + 4 * (d.obs_size + 4), 16);
+  while ((b & 127) != 64) b += 16;
+  return b;
 }
 
 __host__ __device__ inline int block_smem_bytes(const SbDev& d, int threads, int lpe) {
-  int lut = round_up(2 * d.obs_size + 2 * d.SS, 16);
+  int lut = round_up(2 * d.SS, 16);
   int q = round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
   return lut + q + (threads / lpe) * env_smem_bytes(d);
 }
@@ -48,7 +46,8 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
                : "memory");
 }
 
-template <int LPE, int RNG>
+// LPE  lanes per instance; RNG  SB_K_* sweep variant; NP1  one stored plane + one-hot fast path
+template <int LPE, int RNG, bool NP1>
 __global__ void __launch_bounds__(SB_THREADS)
     step_kernel(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -61,28 +60,22 @@ __global__ void __launch_bounds__(SB_THREADS)
   const int warp = tid >> 5;
 
   // ---- carve shared memory --------------------------------------------------------------
-  uint16_t* lut_e = reinterpret_cast<uint16_t*>(smem_raw);
-  uint16_t* lut_ij = lut_e + d.obs_size;
-  const int lut_bytes = round_up(2 * d.obs_size + 2 * d.SS, 16);
-  uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + lut_bytes);
-  uint32_t* q = qbase + warp * (SB_QCAP + 1);
+  uint16_t* lut_ij = reinterpret_cast<uint16_t*>(smem_raw);  // [SS] (i << 8) | j of window cell ij
+  uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + p.lut_bytes);
+  uint32_t* q = qbase + warp * (SB_QCAP + 1);  // spawn candidates of this warp's instances
   uint32_t* qn = q + SB_QCAP;
-  const int q_bytes = round_up((SB_THREADS / 32) * (SB_QCAP + 1) * 4, 16);
-  const int esz = env_smem_bytes(d);
-  uint8_t* envs = smem_raw + lut_bytes + q_bytes;
+  const int esz = p.env_smem;
+  uint8_t* envs = smem_raw + p.lut_bytes + p.q_bytes;
   uint8_t* genv = envs + grp * esz;
   uint32_t* spos = reinterpret_cast<uint32_t*>(genv + d.env_stride);
   int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
-  uint8_t* swin = reinterpret_cast<uint8_t*>(sact + d.A);
+  float* stage = reinterpret_cast<float*>(genv + p.stage_off);
 
-  for (int e = tid; e < d.obs_size; e += SB_THREADS) {
-    int c = e / d.SS;
-    lut_e[e] = (uint16_t)((c << 9) | (e - c * d.SS));
-  }
   for (int ij = tid; ij < d.SS; ij += SB_THREADS) {
     int i = ij / d.S;
     lut_ij[ij] = (uint16_t)((i << 8) | (ij - i * d.S));
   }
+  for (int e = lane; e < d.obs_size + 4; e += LPE) stage[e] = 0.0f;
   if (wlane == 0) *qn = 0;
   __syncthreads();
 
@@ -114,15 +107,13 @@ __global__ void __launch_bounds__(SB_THREADS)
   const int T = p.a.num_turns;
   const size_t rows = (size_t)d.N * d.A;
   const size_t tape_stride = (size_t)d.env_stride;  // tape entries per instance per turn
+  const bool fused = p.a.mode == SB_MODE_FUSED;
+  const size_t row0 = (size_t)(active ? env : 0) * d.A;  // first ring row of this instance
+  float* const ring0 = p.has_buf ? p.buf.d_states + row0 * p.buf.capacity * d.obs_size : nullptr;
+  int slot = p.has_buf ? p.a.slot0 : 0;
 
-  for (int t = 0; t < T; ++t) {
+  for (int t = 0; t < T; ++t, slot = (p.has_buf && slot + 1 < p.buf.capacity) ? slot + 1 : 0) {
     const uint32_t tick = p.a.tick0 + (uint32_t)t;
-    int slot = 0;
-    if (p.has_buf) {
-      slot = p.a.slot0 + t;
-      slot -= (slot / p.buf.capacity) * p.buf.capacity;
-    }
-    const bool fused = p.a.mode == SB_MODE_FUSED;
 
     // ---- actions of this turn (parallel over agents; hides the tape-load latency) ------------
     if (fused || p.a.act_agent >= 0) {
@@ -170,7 +161,6 @@ __global__ void __launch_bounds__(SB_THREADS)
         // at p = 0.005), so they are pushed to a per-warp queue and resolved by all 32 lanes at
         // once instead of diverging inside the chunk loop.
         const uint32_t spawn4 = (uint32_t)d.single_spawn_kind * 0x01010101u;
-        const uint32_t n4c = (128u - (d.hi8 + 1u)) * 0x01010101u;
         const int iters = (d.n_chunks + LPE - 1) / LPE;
         for (int it = 0; it < iters; ++it) {
           const int c = it * LPE + lane;
@@ -178,21 +168,21 @@ __global__ void __launch_bounds__(SB_THREADS)
           SbU4 r;
           r.x = r.y = r.z = r.w = 0;
           if (c < d.n_chunks) {
-            uint4 k = genv4[c];
+            const uint4 k = genv4[c];
             r = sb_philox(envid, tick, (uint32_t)c, SB_DOM_SWEEP, k0, k1);
-            m = sb_pack_mask(sb_simd_cand_word(k.x, r.x, spawn4, n4c)) |
-                (sb_pack_mask(sb_simd_cand_word(k.y, r.y, spawn4, n4c)) << 4) |
-                (sb_pack_mask(sb_simd_cand_word(k.z, r.z, spawn4, n4c)) << 8) |
-                (sb_pack_mask(sb_simd_cand_word(k.w, r.w, spawn4, n4c)) << 12);
+            m = sb_simd_cand_chunk(k.x, k.y, k.z, k.w, r.x, r.y, r.z, r.w, spawn4, d.hmask4);
           }
           if (__ballot_sync(0xFFFFFFFFu, m != 0)) {
             while (m) {
-              int b = __ffs(m) - 1;
+              const int pos = __ffs(m) - 1;  // bit 8*b + w: byte b of word w
               m &= m - 1;
-              uint32_t r8 = sb_byte_of(r, b);
-              uint32_t cell = (uint32_t)(c * 16 + b);
-              uint32_t entry = ((r8 == d.hi8) ? 0x80000000u : 0u) | ((uint32_t)grp << 20) | cell;
-              uint32_t at = atomicAdd(qn, 1u);
+              const int w = pos & 7, b = pos >> 3;
+              const uint32_t rw = (w & 2) ? ((w & 1) ? r.w : r.z) : ((w & 1) ? r.y : r.x);
+              const uint32_t r8 = (rw >> (8 * b)) & 0xFFu;
+              if (r8 > d.hi8) continue;  // the filter is a superset (power-of-two bound)
+              const uint32_t cell = (uint32_t)(c * 16 + 4 * w + b);
+              const uint32_t entry = ((r8 == d.hi8) ? 0x80000000u : 0u) | ((uint32_t)grp << 20) | cell;
+              const uint32_t at = atomicAdd(qn, 1u);
               if (at < SB_QCAP) {
                 q[at] = entry;
               } else {  // queue full (dense spawning): resolve in place
@@ -234,50 +224,65 @@ __global__ void __launch_bounds__(SB_THREADS)
     auto observe = [&](int a) {
       const uint32_t yx = spos[a];
       const int y = (int)(yx >> 16), x = (int)(yx & 0xFFFFu);
-      float* dst0 = (p.has_buf && active)
-                        ? p.buf.d_states + (((size_t)env * d.A + a) * p.buf.capacity + slot) * d.obs_size
-                        : nullptr;
-      float* dst1 = (p.a.d_obs_out && active)
-                        ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size
-                        : nullptr;
-      if (d.fast_obs) {
-        // phase A: channel code of every window cell on every stored plane
-        for (int pl = 0; pl < d.n_planes; ++pl)
-          for (int ij = lane; ij < d.SS; ij += LPE) {
-            uint32_t l = lut_ij[ij];
-            swin[pl * d.SS + ij] = (uint8_t)sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), pl);
-          }
-        __syncwarp();
-        // phase B: obs[c][i][j] = number of planes whose code == c, as the linear float stream
-        auto val = [&](int e) -> float {
-          uint32_t l = lut_e[e];
-          uint32_t c = l >> 9, ij = l & 511u;
-          int cnt = 0;
-          for (int pl = 0; pl < d.n_planes; ++pl) cnt += (swin[pl * d.SS + ij] == c) ? 1 : 0;
-          return (float)cnt;
-        };
+      float* dsts[2];
+      dsts[0] = (p.has_buf && active) ? ring0 + ((size_t)a * p.buf.capacity + slot) * d.obs_size : nullptr;
+      dsts[1] = (p.a.d_obs_out && active)
+                    ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size
+                    : nullptr;
+      if (NP1 || d.fast_obs) {
+        // The row is all zeros except one entry per (window cell, stored plane): scatter those into
+        // the zeroed staging row, then stream the row out with 128-bit shared loads / global stores,
+        // zeroing it again on the way.  `off` shifts the row inside the staging buffer so that the
+        // first 16-byte aligned global address lines up with a 16-byte aligned shared address.
+#pragma unroll
         for (int k = 0; k < 2; ++k) {
-          float* dst = k ? dst1 : dst0;
-          if (!dst) continue;
-          int head = (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3;
-          if (head > d.obs_size) head = d.obs_size;
-          if (lane < head) dst[lane] = val(lane);
-          const int nvec = (d.obs_size - head) >> 2;
-          for (int qv = lane; qv < nvec; qv += LPE) {
-            int e0 = head + 4 * qv;
-            st_f4(dst + e0, val(e0), val(e0 + 1), val(e0 + 2), val(e0 + 3));
+          float* dst = dsts[k];
+          if (k == 1 && !p.a.d_obs_out) break;  // uniform: no second destination in this launch
+          const int head = dst ? (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3 : 0;
+          const int off = (4 - head) & 3;
+          if (dst) {
+            for (int ij = lane; ij < d.SS; ij += LPE) {
+              const uint32_t l = lut_ij[ij];
+              if (NP1) {  // one stored plane: every window cell contributes at most one 1.0
+                const uint32_t code = sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), 0);
+                if (code != 255u) stage[off + code * d.SS + ij] = 1.0f;
+              } else {
+                for (int pl = 0; pl < d.n_planes; ++pl) {
+                  const uint32_t code = sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), pl);
+                  if (code != 255u) stage[off + code * d.SS + ij] += 1.0f;  // planes are summed
+                }
+              }
+            }
           }
-          int e = head + 4 * nvec + lane;
-          if (e < d.obs_size) dst[e] = val(e);
+          __syncwarp();
+          if (dst) {
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < head && lane < d.obs_size) {
+              dst[lane] = stage[off + lane];
+              stage[off + lane] = 0.0f;
+            }
+            const int nvec = d.obs_size > head ? (d.obs_size - head) >> 2 : 0;
+            float4* s4 = reinterpret_cast<float4*>(stage + off + head);
+            for (int qv = lane; qv < nvec; qv += LPE) {
+              const float4 v = s4[qv];
+              s4[qv] = zero4;
+              st_f4(dst + head + 4 * qv, v.x, v.y, v.z, v.w);
+            }
+            const int e = head + 4 * nvec + lane;
+            if (e < d.obs_size) {
+              dst[e] = stage[off + e];
+              stage[off + e] = 0.0f;
+            }
+          }
+          __syncwarp();
         }
       } else {
         for (int e = lane; e < d.obs_size; e += LPE) {
-          uint32_t l = lut_e[e];
-          uint32_t li = lut_ij[l & 511u];
-          float vf = (float)sb_obs_general(d, genv, d.tmpl, d.app, y, x, (int)(l >> 9), (int)(li >> 8),
-                                           (int)(li & 255u));
-          if (dst0) dst0[e] = vf;
-          if (dst1) dst1[e] = vf;
+          const int c = e / d.SS;
+          const uint32_t li = lut_ij[e - c * d.SS];
+          float vf = (float)sb_obs_general(d, genv, d.tmpl, d.app, y, x, c, (int)(li >> 8), (int)(li & 255u));
+          if (dsts[0]) dsts[0][e] = vf;
+          if (dsts[1]) dsts[1][e] = vf;
         }
       }
     };
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(SB_THREADS)
         spos[a] = yx;
         total += (double)reward;  // world.total_reward += reward, agent.py:172
         if (active) {
-          const size_t row = (size_t)env * d.A + a;
+          const size_t row = row0 + a;
           if (p.has_buf) {
             const size_t at = (size_t)slot * rows + row;
             p.buf.d_actions[at] = (int64_t)action;
@@ -344,11 +349,15 @@ __global__ void __launch_bounds__(SB_THREADS)
 // ----------------------------------------------------------------------------------------------
 // launch
 // ----------------------------------------------------------------------------------------------
-template <int LPE, int RNG>
-static int launch_one(const SbDev& d, const StepParams& p, cudaStream_t s) {
+template <int LPE, int RNG, bool NP1>
+static int launch_one(const SbDev& d, StepParams p, cudaStream_t s) {
+  p.lut_bytes = round_up(2 * d.SS, 16);
+  p.q_bytes = round_up((SB_THREADS / 32) * (SB_QCAP + 1) * 4, 16);
+  p.env_smem = env_smem_bytes(d);
+  p.stage_off = stage_offset_bytes(d);
   const int smem = block_smem_bytes(d, SB_THREADS, LPE);
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
-  auto kern = step_kernel<LPE, RNG>;
+  auto kern = step_kernel<LPE, RNG, NP1>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return note_cuda_error();
@@ -363,10 +372,12 @@ static int launch_one(const SbDev& d, const StepParams& p, cudaStream_t s) {
 
 template <int LPE>
 static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t s) {
+  const bool np1 = d.fast_obs && d.n_planes == 1;
   switch (kr) {
-    case SB_K_TAPE: return launch_one<LPE, SB_K_TAPE>(d, p, s);
-    case SB_K_PHILOX_SIMD: return launch_one<LPE, SB_K_PHILOX_SIMD>(d, p, s);
-    default: return launch_one<LPE, SB_K_PHILOX_GENERIC>(d, p, s);
+    case SB_K_TAPE: return launch_one<LPE, SB_K_TAPE, false>(d, p, s);  // replay: speed is irrelevant
+    case SB_K_PHILOX_SIMD:
+      return np1 ? launch_one<LPE, SB_K_PHILOX_SIMD, true>(d, p, s) : launch_one<LPE, SB_K_PHILOX_SIMD, false>(d, p, s);
+    default: return launch_one<LPE, SB_K_PHILOX_GENERIC, false>(d, p, s);
   }
 }
 

@@ -1,0 +1,197 @@
+"""`Environment` with the reference's interface (sorrel/environment.py:18-300), batched.
+
+Subclass it exactly like the reference: implement `setup_agents()` (assign `self.agents`) and
+`populate_environment()` (edit `self.world.map` through `world.add`, then hand the valid spawn
+cells to `self.place_agents(...)` instead of drawing one placement with numpy).  `reset()` and
+`take_turn()` then advance ALL `world.num_envs` instances on the GPU:
+
+* every agent uses an in-kernel policy (`RandomModel`)  -> one fused launch per `take_turn()`
+  (`take_turns(T)` fuses T turns per launch);
+* otherwise -> the split-phase path: `Agent.transition` runs pov / get_action / act per agent
+  slot with the policy on the host side of the launch boundary, in the reference's order.
+"""
+from __future__ import annotations
+
+import os
+from abc import abstractmethod
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import config as _config
+from .agents import Agent
+from .buffers import Buffer
+from .models import AgentMemory
+from .stats import RewardStats, summarize
+from .worlds import Gridworld
+
+
+class Environment:
+    world: Gridworld
+    agents: list[Agent]
+    stop_if_done: bool
+
+    def __init__(self, world: Gridworld, config, stop_if_done: bool = False) -> None:
+        if isinstance(config, (list, tuple)):
+            self.config = _config.from_dotlist(config)  # environment.py:44-46
+        else:
+            self.config = _config.wrap(config)
+        self.world = world
+        self.turn = 0
+        self.world.create_world()
+        self.stop_if_done = stop_if_done
+        self._spawnable = None
+        self.setup_agents()
+        self.populate_environment()
+        self._compile()
+        self.reset()
+
+    # -- to be provided by the subclass (environment.py:56-70) -----------------------------------
+    @abstractmethod
+    def setup_agents(self) -> None:
+        """Create the agent slots and assign them to self.agents."""
+
+    @abstractmethod
+    def populate_environment(self) -> None:
+        """Fill self.world.map (walls, floor, ...) and call self.place_agents(valid_locations)."""
+
+    def place_agents(self, valid_spawn_locations) -> None:
+        """Batched stand-in for `np.random.choice(len(valid), size=A, replace=False)` + `world.add(loc,
+        agent)` (examples/treasurehunt/env.py:141-147): every instance draws its own placement on
+        the device at each reset."""
+        self._spawnable = np.asarray([tuple(loc) for loc in valid_spawn_locations], dtype=np.int64).reshape(-1, 3)
+
+    # -- engine wiring ---------------------------------------------------------------------------
+    def _compile(self) -> None:
+        if self._spawnable is None:
+            raise RuntimeError("populate_environment() must call self.place_agents(valid_spawn_locations)")
+        a0 = self.agents[0]
+        for k, ag in enumerate(self.agents):
+            ag.index, ag.env = k, self
+            if type(ag) is not type(a0) or ag.kind_key() != a0.kind_key():
+                raise ValueError("all agent slots must be of one Agent class (one kind-table row)")
+        A = len(self.agents)
+        eng = self.world.compile(a0, a0.observation_spec, a0.action_spec, A, self._spawnable)
+        model = a0.model
+        cap = int(getattr(model, "memory_size", 0) or self.config.get("engine", {}).get("buffer_capacity", 1024))
+        n_frames = int(getattr(model, "n_frames", 1))
+        self.buffer = Buffer(cap, (eng.spec.obs_size,), n_frames=n_frames, rows=eng.N * A, device=eng.device,
+                             positions=(2,))
+        for k, ag in enumerate(self.agents):
+            ag.model.memory = AgentMemory(self.buffer, k, A)
+        self.stats = RewardStats(eng.device)
+        self._fusable = all(getattr(ag.model, "in_kernel_policy", False) for ag in self.agents)
+        self._reward_slot = torch.zeros((1, eng.N, A), dtype=torch.float32, device=eng.device)
+        self._action_slot = torch.zeros((1, eng.N, A), dtype=torch.int32, device=eng.device)
+        self._turn_open = False
+
+    @property
+    def engine(self):
+        return self.world.engine
+
+    # -- reference API ---------------------------------------------------------------------------
+    def reset(self) -> None:
+        """environment.py:72-79"""
+        self.turn = 0
+        self.world.is_done = False
+        self.engine.reset()
+        for agent in self.agents:
+            agent.reset()
+
+    def add_empty(self) -> None:
+        """What every IQN model does at epoch start through `memory.add_empty()` (iqn.py:426-436),
+        once for the shared ring."""
+        self.buffer.add_empty()
+
+    def take_turn(self) -> None:
+        """environment.py:81-93 for every instance."""
+        if self._fusable:
+            self.take_turns(1)
+            return
+        self.turn += 1
+        self._turn_open = False
+        for agent in self.agents:  # entity sweep happens in agent 0's pov launch
+            agent.transition(self.world)
+        self.buffer.advance(1)
+
+    def take_turns(self, num_turns: int) -> None:
+        """`num_turns` x take_turn() in ONE launch (in-kernel policies only)."""
+        if not self._fusable:
+            raise RuntimeError("take_turns() needs in-kernel policies; use take_turn() with a host policy")
+        self.engine.step(num_turns, buffer=self.buffer)
+        self.turn += num_turns
+
+    # -- split-phase plumbing used by Agent.pov / Agent.act ----------------------------------------
+    def _observe_slot(self, k: int) -> torch.Tensor:
+        eng = self.engine
+        if k == 0 and not self._turn_open:
+            eng.phase(sweep=True, obs_agent=0, buffer=self.buffer, new_turn=True)
+            self._turn_open = True
+        elif k > 0 and self._pending_obs != k:
+            eng.phase(obs_agent=k, buffer=self.buffer)
+        self._pending_obs = None
+        A = len(self.agents)
+        return self.buffer.states[k::A, self.buffer.idx].reshape(eng.N, -1)
+
+    _pending_obs = None
+
+    def _act_slot(self, k: int, action) -> torch.Tensor:
+        eng = self.engine
+        A = len(self.agents)
+        act = torch.as_tensor(action, device=eng.device).to(torch.int32).reshape(-1)
+        if act.numel() == 1:
+            act = act.expand(eng.N)
+        self._action_slot[0, :, k] = act
+        nxt = k + 1 if k + 1 < A else -1
+        # act agent k and, in the same launch, observe agent k+1 (it must see k's move)
+        eng.phase(act_agent=k, obs_agent=nxt, buffer=self.buffer, actions=self._action_slot,
+                  reward_out=self._reward_slot)
+        self._pending_obs = nxt if nxt >= 0 else None
+        return self._reward_slot[0, :, k]
+
+    # -- experiment loop ---------------------------------------------------------------------------
+    def reward_summary(self) -> dict:
+        """mean/std/min/max of world.total_reward over every instance of every rank (one tiny
+        all_gather; see stats.py)."""
+        return summarize(self.stats.all_reduce(self.engine.total_reward))
+
+    def run_experiment(self, animate: bool = False, logging: bool = True, logger=None,
+                       output_dir: Path | None = None) -> list[dict]:
+        """environment.py:108-211 without the host-only extras (GIF rendering, checkpoints):
+        epochs x (reset, start_epoch_action, max_turns turns, end_epoch_action, train_step, log,
+        epsilon decay).  Returns the per-epoch reward summaries."""
+        exp = self.config.experiment
+        history = []
+        fuse = int(self.config.get("engine", {}).get("turns_per_launch", 25))
+        for epoch in range(exp.epochs + 1):
+            self.reset()
+            self.add_empty()
+            for agent in self.agents:
+                agent.model.start_epoch_action(epoch=epoch)
+            while not self.turn >= exp.max_turns:
+                if self._fusable:
+                    self.take_turns(min(fuse, exp.max_turns - self.turn))
+                else:
+                    self.take_turn()
+                if self.world.is_done and self.stop_if_done:
+                    break
+            self.world.is_done = True
+            total_loss = 0
+            for agent in self.agents:
+                agent.model.end_epoch_action(epoch=epoch)
+                total_loss = agent.model.train_step()
+            summary = self.reward_summary()
+            summary["epoch"], summary["loss"] = epoch, float(np.asarray(total_loss))
+            history.append(summary)
+            if logging:
+                if logger is not None:
+                    logger.record_turn(epoch, total_loss, summary["mean"], self.agents[0].model.epsilon)
+                elif int(os.environ.get("RANK", "0")) == 0:
+                    print(f"epoch {epoch:4d}  reward mean {summary['mean']:8.3f}  std {summary['std']:7.3f}  "
+                          f"min {summary['min']:6.1f}  max {summary['max']:6.1f}  envs {summary['count']}")
+            for agent in self.agents:
+                if hasattr(self.config.model, "epsilon_decay"):
+                    agent.model.epsilon_decay(self.config.model.epsilon_decay)
+        self.engine.check_errors()
+        return history

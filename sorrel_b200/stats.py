@@ -29,9 +29,9 @@ def all_reduce_partial(partial: torch.Tensor, group=None) -> torch.Tensor:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return combine_partials(partial[None])
     world = dist.get_world_size(group)
-    parts = torch.empty((world, 5), dtype=partial.dtype, device=partial.device)
-    dist.all_gather_into_tensor(parts, partial.contiguous(), group=group)
-    return combine_partials(parts)
+    parts = [torch.empty(5, dtype=partial.dtype, device=partial.device) for _ in range(world)]
+    dist.all_gather(parts, partial.contiguous(), group=group)
+    return combine_partials(torch.stack(parts))
 
 
 def summarize(stats5: torch.Tensor) -> dict:

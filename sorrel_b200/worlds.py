@@ -1,0 +1,219 @@
+"""`Gridworld` with the reference's interface (sorrel/worlds/gridworld.py:10-196), batched.
+
+The reference world is one `numpy.ndarray(dtype=object)` of `Entity` instances.  Here the object
+array `map` is only the *template* the user edits with `add()/remove()/move()` while the world is
+being described (`Environment.populate_environment`); `compile()` turns it into a kind table plus a
+uint8 template and creates `num_envs` device-resident instances stepped by the CUDA kernels.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+import torch
+
+from . import _abi
+from .engine import MOVE_DELTAS, Engine, WorldSpec
+from .entities import Entity
+from .rules import BernoulliSpawn
+
+
+class Gridworld:
+    def __init__(self, height: int, width: int, layers: int, default_entity: Entity, num_envs: int = 1,
+                 device: torch.device | str = "cuda", seed: int = 0, env_id_base: int = 0):
+        self.height = height
+        self.width = width
+        self.layers = layers
+        self.default_entity = default_entity
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        self.engine: Engine | None = None
+        self.spec: WorldSpec | None = None
+        self._kinds: list[Entity] = []
+        self.create_world()
+        self.turn = 0
+        self.max_turns = 0
+        self.is_done = False
+
+    # ------------------------------------------------------------------------------------------
+    # template editing (same calls as the reference)
+    # ------------------------------------------------------------------------------------------
+    def create_world(self) -> None:
+        """gridworld.py:47-65.  The template shares ONE default-entity prototype per cell kind
+        instead of H*W*L deep copies (the copies only exist to give every Python object its own
+        location, which kind ids do not need)."""
+        self.map = np.full((self.height, self.width, self.layers), self.default_entity, dtype=object)
+        self._template_total_reward = 0.0
+
+    def add(self, target_location: tuple[int, ...], entity: Entity) -> None:
+        """gridworld.py:67-76"""
+        entity.location = target_location
+        self.map[target_location] = entity
+
+    def remove(self, target_location: tuple[int, ...]) -> Entity:
+        """gridworld.py:78-93"""
+        entity = self.map[target_location]
+        self.map[target_location] = self.default_entity
+        return entity
+
+    def move(self, entity: Entity, new_location: tuple[int, ...]) -> bool:
+        """gridworld.py:95-122 on the template."""
+        if self.map[new_location].passable:
+            previous_location = entity.location
+            entity.location = new_location
+            self.map[new_location] = entity
+            self.map[previous_location] = self.default_entity
+            return True
+        return False
+
+    def observe(self, target_location: tuple[int, ...], env: int | None = None) -> Entity:
+        """gridworld.py:124-133.  With `env`, reads the cell of that device instance back and
+        returns the prototype entity of its kind."""
+        if env is None or self.engine is None:
+            return self.map[target_location]
+        y, x, z = target_location
+        kinds = self.engine.grid_numpy()[env]
+        return self._kinds[int(kinds[y, x, z])]
+
+    def observe_all_layers(self, target_location: tuple[int, ...], env: int | None = None) -> list[Entity]:
+        """gridworld.py:135-147"""
+        return [self.observe((*target_location[:-1], i), env) for i in range(self.layers)]
+
+    def valid_location(self, index: tuple[int, ...]) -> bool:
+        """gridworld.py:153-179"""
+        if hasattr(index, "to_tuple"):
+            index = index.to_tuple()
+        shape = self.map.shape
+        if len(index) != len(shape):
+            raise IndexError(f"Index {index} and world shape {shape} must be the same length.")
+        if min(index) < 0:
+            return False
+        return all(y < x for x, y in zip(shape, index))
+
+    def get_entities_of_kind(self, kind: str) -> list[Entity]:
+        """gridworld.py:181-196 (template)."""
+        return [x for _, x in np.ndenumerate(self.map) if x.kind == kind]
+
+    # ------------------------------------------------------------------------------------------
+    # compilation: object template -> kind table + uint8 template -> device instances
+    # ------------------------------------------------------------------------------------------
+    def build_spec(self, agent_proto: Entity, observation_spec, action_spec, num_agents: int,
+                   spawnable) -> WorldSpec:
+        """Pure host logic (no CUDA): derive the kind table from the entity prototypes."""
+        entity_list = list(getattr(observation_spec, "entity_list", []))
+        protos: dict[tuple, Entity] = {}
+
+        def note(e: Entity):
+            protos.setdefault(e.kind_key(), e)
+
+        note(self.default_entity)
+        for _, e in np.ndenumerate(self.map):
+            note(e)
+        note(agent_proto)
+        rules = {}
+        for key, e in list(protos.items()):
+            rule = e.transition_rule(self)
+            if rule is not None:
+                if not isinstance(rule, BernoulliSpawn):
+                    raise ValueError(f"{e.kind}: unsupported transition rule {rule!r}")
+                rules[key] = rule
+                for c in rule.choices:
+                    note(c)
+        distinct = {(r.prob, tuple(c.kind_key() for c in r.choices)) for r in rules.values()}
+        if len(distinct) > 1:
+            raise ValueError("only one distinct BernoulliSpawn rule per world is supported")
+
+        def order(item):
+            name = item[0][0]
+            return (entity_list.index(name) if name in entity_list else len(entity_list), name)
+
+        keys = [k for k, _ in sorted(protos.items(), key=order)]
+        if len(keys) > _abi.SB_MAX_KINDS:
+            raise ValueError(f"{len(keys)} entity kinds exceed the engine limit of {_abi.SB_MAX_KINDS}")
+        kid = {k: i for i, k in enumerate(keys)}
+        self._kinds = [protos[k] for k in keys]
+        C = observation_spec.num_channels
+        appearance = np.zeros((len(keys), C), dtype=np.float64)
+        for k, i in kid.items():
+            appearance[i] = observation_spec.appearance_row(protos[k].kind)  # KeyError like visual_field.py:49
+        template = np.zeros((self.height, self.width, self.layers), dtype=np.uint8)
+        for idx, e in np.ndenumerate(self.map):
+            template[idx] = kid[e.kind_key()]
+        fill = [i for k, i in kid.items() if protos[k].kind == observation_spec.fill_entity_kind]
+        if not fill:
+            # the fill kind only matters through its appearance row: add a table-only kind
+            raise KeyError(observation_spec.fill_entity_kind)
+        spawnable = np.asarray(spawnable, dtype=np.int64).reshape(-1, 3)
+        agent_layers = set(spawnable[:, 2].tolist())
+        if len(agent_layers) != 1:
+            raise ValueError("all spawn locations must be on one layer")
+        deltas = []
+        for i in range(action_spec.n_actions):
+            name = action_spec.actions[i]
+            if name not in MOVE_DELTAS:
+                raise ValueError(f"action {name!r} has no movement decode in the B200 engine")
+            deltas.append(MOVE_DELTAS[name])
+        rule = next(iter(rules.values()), None)
+        spec = WorldSpec(
+            height=self.height, width=self.width, layers=self.layers,
+            kind_names=[protos[k].__class__.__name__ for k in keys],
+            kind_value=[float(protos[k].value) for k in keys],
+            kind_passable=[bool(protos[k].passable) for k in keys],
+            kind_rule=[_abi.SB_RULE_SPAWN if k in rules else _abi.SB_RULE_NONE for k in keys],
+            appearance=appearance, template=template, spawnable=spawnable[:, :2].copy(),
+            agent_kind=kid[agent_proto.kind_key()], agent_layer=int(spawnable[0, 2]),
+            default_kind=kid[self.default_entity.kind_key()], fill_kind=fill[0],
+            vision=int(observation_spec.vision_radius), num_agents=int(num_agents),
+            spawn_prob=float(rule.prob) if rule else 0.0,
+            spawn_choices=[kid[c.kind_key()] for c in rule.choices] if rule else [],
+            action_deltas=deltas,
+        )
+        return spec
+
+    def compile(self, agent_proto: Entity, observation_spec, action_spec, num_agents: int, spawnable) -> Engine:
+        self.spec = self.build_spec(agent_proto, observation_spec, action_spec, num_agents, spawnable)
+        self.engine = Engine(self.spec, self.num_envs, device=self.device, env_id_base=self.env_id_base,
+                             seed=self.seed)
+        return self.engine
+
+    # ------------------------------------------------------------------------------------------
+    # device-side views
+    # ------------------------------------------------------------------------------------------
+    @property
+    def total_reward(self):
+        """float64 device tensor [num_envs] once compiled (world.total_reward of every instance)."""
+        return self.engine.total_reward if self.engine is not None else self._template_total_reward
+
+    @total_reward.setter
+    def total_reward(self, value):
+        if self.engine is not None and not isinstance(value, torch.Tensor):
+            self.engine.total_reward.fill_(float(value))
+        elif self.engine is None:
+            self._template_total_reward = value
+
+    def observe_from(self, location) -> torch.Tensor:
+        """One-hot crop centred on `location` in every instance: float32 [N, C, S, S]."""
+        eng = self.engine
+        if isinstance(location, torch.Tensor):
+            cells = (location[:, 0] * self.width + location[:, 1]).to(torch.int32)
+        else:
+            cells = torch.full((eng.N,), int(location[0]) * self.width + int(location[1]), dtype=torch.int32)
+        saved = eng.agent_pos
+        probe = saved.clone()
+        probe[:, 0] = cells.to(eng.device)
+        eng.agent_pos = probe
+        try:
+            out = eng.observe()[:, 0].clone()
+        finally:
+            eng.agent_pos = saved
+        return out
+
+    def instance_map(self, env: int = 0) -> np.ndarray:
+        """Object array [H, W, L] of prototype entities for one device instance (debug / rendering)."""
+        kinds = self.engine.grid_numpy()[env]
+        out = np.empty(kinds.shape, dtype=object)
+        for idx, k in np.ndenumerate(kinds):
+            out[idx] = self._kinds[int(k)]
+        return out

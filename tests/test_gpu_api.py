@@ -1,0 +1,136 @@
+"""GPU: the reference-shaped API (Environment / Gridworld / Agent / ObservationSpec / Buffer) on the
+treasurehunt example, against the oracle."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import sb_testutil as util
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+
+CONFIG = {
+    "experiment": {"epochs": 1, "max_turns": 30, "record_period": 50},
+    "model": {"agent_vision_radius": 2, "epsilon_decay": 0.0005, "observation_spec": "onehot", "num_agents": 3,
+              "memory_size": 64, "n_frames": 3},
+    "world": {"height": 11, "width": 13, "gem_value": 10, "food_value": 5, "bone_value": -10, "spawn_prob": 0.03},
+}
+
+
+def _make(num_envs, seed, model_factory=None, **over):
+    from sorrel_b200.examples.treasurehunt.entities import EmptyEntity
+    from sorrel_b200.examples.treasurehunt.env import TreasurehuntEnv
+    from sorrel_b200.examples.treasurehunt.world import TreasurehuntWorld
+
+    cfg = {k: dict(v) for k, v in CONFIG.items()}
+    for k, v in over.items():
+        cfg["model"][k] = v
+    world = TreasurehuntWorld(cfg, EmptyEntity(), num_envs=num_envs, device="cuda:0", seed=seed)
+    return TreasurehuntEnv(world, cfg, model_factory=model_factory), cfg
+
+
+def _oracle_spec():
+    w, m = CONFIG["world"], CONFIG["model"]
+    return R.treasurehunt_spec(w["height"], w["width"], m["num_agents"], m["agent_vision_radius"], w["spawn_prob"])
+
+
+def test_example_env_fused_matches_oracle(cuda_device):
+    """treasurehunt with RandomModel agents: take_turn()/take_turns() == oracle with the same stream."""
+    N, seed, T = 24, 77, 20
+    env, _ = _make(N, seed)
+    env.add_empty()
+    env.take_turn()
+    env.take_turns(T - 1)
+    env.engine.check_errors()
+    spec = _oracle_spec()
+    grids = env.engine.grid_numpy()
+    for n in range(N):
+        o = R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=n, capacity=64, n_frames=3)
+        o.reset()
+        for b in o.buffers:
+            b.add_empty()
+        for _ in range(T):
+            o.take_turn()
+        np.testing.assert_array_equal(grids[n], o.grid)
+        for a in range(3):
+            mem = env.agents[a].model.memory
+            np.testing.assert_array_equal(mem.states[n].cpu().numpy(), o.buffers[a].states)
+            np.testing.assert_array_equal(mem.rewards[:, n].cpu().numpy(), o.buffers[a].rewards)
+            np.testing.assert_array_equal(mem.current_state()[n].cpu().numpy(), o.buffers[a].current_state())
+        assert float(env.world.total_reward[n]) == o.total_reward
+    # world.observe(env=...) reads a device instance back as entity prototypes
+    yx = env.engine.agent_yx()[0, 0]
+    assert env.world.observe((int(yx[0]), int(yx[1]), 1), env=0).kind == "TreasurehuntAgent"
+    s = env.reward_summary()
+    assert s["count"] == N and abs(s["mean"] - float(env.world.total_reward.mean())) < 1e-9
+
+
+def test_split_phase_host_policy_matches_oracle(cuda_device):
+    """A policy that runs on the host side of the launch boundary (here: a deterministic function of
+    the observation) goes through Agent.transition = pov -> get_action -> act per agent slot, and
+    reproduces the oracle stepping with the same observation-dependent actions."""
+    from sorrel_b200.models import BaseModel
+
+    class ObsPolicy(BaseModel):
+        """action = (number of non-zero entries in the stacked frames) mod 4"""
+
+        def take_action(self, state):
+            return (state != 0).sum(dim=1).to(torch.int32) % 4
+
+    N, seed, T = 10, 5, 12
+    env, _ = _make(N, seed, model_factory=lambda inp, na: ObsPolicy(inp, na, memory_size=64, n_frames=3))
+    assert not env._fusable
+    env.add_empty()
+    for _ in range(T):
+        env.take_turn()
+    env.engine.check_errors()
+    spec = _oracle_spec()
+    grids = env.engine.grid_numpy()
+
+    class Draws(R.PhiloxDraws):
+        def action(self, n_actions, env_id, tick, agent):
+            buf = self.env.buffers[agent]
+            obs = R.observe(self.env.spec, self.env.grid, *self.env.pos[agent]).reshape(-1).astype(np.float32)
+            stacked = np.concatenate((buf.current_state().reshape(-1), obs))
+            return int((stacked != 0).sum() % 4)
+
+    for n in range(N):
+        d = Draws(seed)
+        o = R.OracleEnv(spec, d, env_id=n, capacity=64, n_frames=3)
+        d.env = o
+        o.reset()
+        for b in o.buffers:
+            b.add_empty()
+        for _ in range(T):
+            o.take_turn()
+        np.testing.assert_array_equal(grids[n], o.grid, err_msg=f"instance {n}")
+        for a in range(3):
+            mem = env.agents[a].model.memory
+            np.testing.assert_array_equal(mem.states[n].cpu().numpy(), o.buffers[a].states)
+            np.testing.assert_array_equal(mem.actions[:, n].cpu().numpy(), o.buffers[a].actions)
+            np.testing.assert_array_equal(mem.rewards[:, n].cpu().numpy(), o.buffers[a].rewards)
+            np.testing.assert_array_equal(env.buffer.extra_data["positions"][:, n * 3 + a].cpu().numpy(),
+                                          o.buffers[a].positions)
+        assert float(env.world.total_reward[n]) == o.total_reward
+
+
+def test_run_experiment_and_observe_from(cuda_device):
+    env, cfg = _make(16, 3)
+    hist = env.run_experiment(logging=False)
+    assert len(hist) == cfg["experiment"]["epochs"] + 1 and hist[0]["count"] == 16
+    # ObservationSpec.observe(world, location): the crop from an arbitrary cell in every instance
+    spec = env.agents[0].observation_spec
+    obs = spec.observe(env.world, (1, 1, 1)).cpu().numpy()
+    full = env.engine.grid_numpy()
+    for n in range(16):
+        ref = R.observe(_oracle_spec(), full[n], 1, 1).astype(np.float32)
+        np.testing.assert_array_equal(obs[n], ref)
+    allobs = spec.observe(env.world)
+    assert tuple(allobs.shape) == (16, 3, 6, 5, 5)
+    # sample() through an agent's memory view: shapes/dtypes of Buffer.sample (buffers.py:98-124)
+    out = env.agents[1].model.memory.sample(8)
+    assert [tuple(o.shape) for o in out] == [(8, 450), (8, 1), (8, 1), (8, 450), (8, 1), (8, 1)]
+    assert [o.dtype for o in out] == [torch.float32, torch.int64, torch.float32, torch.float32, torch.float32,
+                                      torch.float64]

@@ -1,0 +1,117 @@
+"""CPU: host-side logic of the reference-shaped API (no CUDA calls): kind-table compilation from
+entity classes, observation-spec maps, config wrapper, reward-stat combination, error mapping."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import sb_testutil as util
+from oracle import restatement as R
+
+
+def _th_world(H=21, W=21, num_agents=1, v=2, p=0.005):
+    from sorrel_b200.action import ActionSpec
+    from sorrel_b200.examples.treasurehunt.agents import TreasurehuntAgent
+    from sorrel_b200.examples.treasurehunt.entities import EmptyEntity, Sand, Wall
+    from sorrel_b200.examples.treasurehunt.world import TreasurehuntWorld
+    from sorrel_b200.models import RandomModel
+    from sorrel_b200.observation import OneHotObservationSpec
+
+    config = {"world": {"height": H, "width": W, "gem_value": 10, "food_value": 5, "bone_value": -10,
+                        "spawn_prob": p}}
+    world = TreasurehuntWorld(config, EmptyEntity(), num_envs=4, device="cuda")  # no CUDA call until compile()
+    spawn = []
+    for index in np.ndindex(world.map.shape):
+        y, x, z = index
+        if (y in [0, H - 1] or x in [0, W - 1]) and z == 1:
+            world.add(index, Wall())
+        elif z == 0:
+            world.add(index, Sand())
+        else:
+            spawn.append(index)
+    spec = OneHotObservationSpec(["EmptyEntity", "Wall", "Gem", "Bone", "Food", "TreasurehuntAgent"],
+                                 full_view=False, vision_radius=v)
+    aspec = ActionSpec(["up", "down", "left", "right"])
+    agent = TreasurehuntAgent(spec, aspec, RandomModel((150,), 4, 16))
+    return world, agent, spec, aspec, spawn
+
+
+@pytest.mark.parametrize("H,W,A,v,p", [(21, 21, 1, 2, 0.005), (9, 15, 4, 3, 0.03)])
+def test_kind_table_from_entity_classes_equals_oracle_spec(H, W, A, v, p):
+    """The table compiled from the example's Entity classes is the oracle's hand-written spec."""
+    world, agent, spec, aspec, spawn = _th_world(H, W, A, v, p)
+    got = world.build_spec(agent, spec, aspec, A, spawn)
+    ref = util.engine_spec(R.treasurehunt_spec(H, W, A, v, p))
+    assert got.kind_names == ref.kind_names
+    assert got.kind_value == [float(x) for x in ref.kind_value]
+    assert got.kind_passable == ref.kind_passable and got.kind_rule == ref.kind_rule
+    np.testing.assert_array_equal(got.appearance, ref.appearance)
+    np.testing.assert_array_equal(got.template, ref.template)
+    np.testing.assert_array_equal(got.spawnable, ref.spawnable)
+    assert (got.agent_kind, got.agent_layer, got.default_kind, got.fill_kind) == \
+           (ref.agent_kind, ref.agent_layer, ref.default_kind, ref.fill_kind)
+    assert got.spawn_prob == ref.spawn_prob and got.spawn_choices == ref.spawn_choices
+    assert got.action_deltas == ref.action_deltas and got.resolved_dynamic_layers() == [1]
+
+
+def test_observation_spec_matches_reference_semantics():
+    from sorrel_b200.observation import OneHotObservationSpec
+
+    s = OneHotObservationSpec(["EmptyEntity", "Wall", "Gem"], full_view=False, vision_radius=3)
+    assert s.input_size == (3, 7, 7)
+    np.testing.assert_array_equal(s.entity_map["EmptyEntity"], np.zeros(3))  # observation_spec.py:169-170
+    np.testing.assert_array_equal(s.entity_map["Gem"], [0, 0, 1])
+    with pytest.raises(TypeError):
+        OneHotObservationSpec(["a"], full_view=False)  # observation_spec.py:51-52
+    with pytest.raises(TypeError):
+        OneHotObservationSpec(["a"], full_view=True)  # observation_spec.py:49-50
+    s.override_input_size((147,))
+    assert s.input_size == (147,)
+    with pytest.raises(KeyError):
+        s.appearance_row("Unknown")  # visual_field.py:49
+
+
+def test_gridworld_template_api():
+    world, agent, *_ = _th_world(7, 7)
+    assert world.valid_location((0, 0, 0)) and not world.valid_location((7, 0, 0)) and not world.valid_location((-1, 0, 0))
+    with pytest.raises(IndexError):
+        world.valid_location((0, 0))  # gridworld.py:168-171
+    assert world.observe((0, 0, 1)).kind == "Wall" and world.observe((3, 3, 1)).kind == "EmptyEntity"
+    assert [e.kind for e in world.observe_all_layers((3, 3, 1))] == ["EmptyEntity", "EmptyEntity"]
+    assert len(world.get_entities_of_kind("Wall")) == 24
+    from sorrel_b200.entities import Entity
+
+    e = Entity()
+    with pytest.raises(AttributeError):
+        _ = e.location  # entity.py:51-52
+
+
+def test_config_wrapper():
+    from sorrel_b200 import config
+
+    c = config.wrap({"model": {"num_agents": 3}, "world": {"height": 5}})
+    assert c.model.num_agents == 3 and c.model.get("missing", 2) == 2 and not hasattr(c.model, "epsilon_decay")
+    d = config.from_dotlist(["a.b=1", "a.c=x"])
+    assert d.a.b == "1" and d.a.c == "x"
+
+
+def test_reward_stats_combination():
+    from sorrel_b200.stats import combine_partials, summarize
+
+    x = [np.arange(10.0), np.arange(5.0) - 7]
+    parts = torch.tensor([[v.sum(), (v * v).sum(), v.min(), v.max(), len(v)] for v in x], dtype=torch.float64)
+    allv = np.concatenate(x)
+    s = summarize(combine_partials(parts))
+    assert s["count"] == 15 and s["min"] == allv.min() and s["max"] == allv.max()
+    assert abs(s["mean"] - allv.mean()) < 1e-12 and abs(s["std"] - allv.std()) < 1e-12
+
+
+def test_error_mapping():
+    from sorrel_b200 import _abi
+
+    assert isinstance(_abi.error_bits_to_exception(_abi.SB_ERR_OFFGRID), IndexError)
+    assert isinstance(_abi.error_bits_to_exception(_abi.SB_ERR_BAD_ACTION), KeyError)
+    assert _abi.error_bits_to_exception(0) is None
+    with pytest.raises(ValueError):
+        _abi.check(_abi.SB_EVISION)
