@@ -142,6 +142,7 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     d.channel[k] = (uint8_t)ch;
   }
   for (int k = d.K; k < SB_MAX_KINDS; ++k) d.channel[k] = 255;
+  for (int k = 0; k < 8; ++k) d.channel8 |= (uint64_t)d.channel[k] << (8 * k);
   d.fill_channel = d.channel[d.fill_kind];
   d.app = w->d_appearance;
   d.tmpl = w->d_template;

@@ -39,6 +39,7 @@ struct SbDev {
   uint32_t hi8;                        // top 8 bits of the 53-bit spawn threshold
   uint64_t lo45;                       // low 45 bits
   uint64_t choices_packed;             // spawn_choice_kinds, one byte each
+  uint64_t channel8;                   // channel[0..7] packed (used when K <= 8)
   uint64_t dy_packed, dx_packed;       // action deltas, one signed byte each
   uint64_t env_id_base;
   double p;
@@ -56,14 +57,9 @@ struct SbU4 {
 };
 
 SB_HD void sb_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#if defined(__CUDA_ARCH__)
-  lo = a * b;
-  hi = __umulhi(a, b);
-#else
-  uint64_t p = (uint64_t)a * (uint64_t)b;
+  const uint64_t p = (uint64_t)a * (uint64_t)b;  // mul.wide.u32 -> one IMAD.WIDE.U32
   lo = (uint32_t)p;
   hi = (uint32_t)(p >> 32);
-#endif
 }
 
 SB_HD SbU4 sb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
@@ -80,6 +76,37 @@ SB_HD SbU4 sb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_
     c3 = lo0;
     k0 += W0;
     k1 += W1;
+  }
+  SbU4 o;
+  o.x = c0;
+  o.y = c1;
+  o.z = c2;
+  o.w = c3;
+  return o;
+}
+
+// Same function with the 10 round keys (k + r*W) precomputed: rk[2r], rk[2r+1].  The kernels pass a
+// pointer into their __grid_constant__ parameters, so every key is a constant-bank operand of the
+// XOR and the key schedule costs no instructions.
+SB_HD void sb_philox_round_keys(uint32_t k0, uint32_t k1, uint32_t rk[20]) {
+  for (int r = 0; r < 10; ++r) {
+    rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+    rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+  }
+}
+
+SB_HD SbU4 sb_philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* __restrict__ rk) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    sb_mulhilo(M0, c0, hi0, lo0);
+    sb_mulhilo(M1, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
   }
   SbU4 o;
   o.x = c0;
@@ -116,14 +143,24 @@ SB_HD uint32_t sb_byte_of(const SbU4& r, int b) {
 
 // Second level: called for cells whose r8 <= hi8.  Returns the kind to spawn, or -1.
 SB_HD int sb_resolve_spawn(const SbDev& d, uint32_t env, uint32_t tick, uint32_t cell, bool r8_equal,
-                           uint32_t k0, uint32_t k1) {
-  SbU4 w = sb_philox(env, tick, cell, SB_DOM_CELL, k0, k1);
+                           const uint32_t* __restrict__ rk) {
+  SbU4 w = sb_philox_rk(env, tick, cell, SB_DOM_CELL, rk);
   if (r8_equal) {
     uint64_t refine = (((uint64_t)w.x << 13) | (uint64_t)(w.y >> 19)) & ((1ull << 45) - 1);
     if (!(refine < d.lo45)) return -1;
   }
   uint32_t ci = sb_bounded(w.z, w.w, (uint32_t)d.n_choices);
   return (int)((d.choices_packed >> (8 * ci)) & 0xFFu);
+}
+
+// Resolve a cell that passed the byte-SIMD filter: recompute its first-level byte (the filter keeps
+// no per-cell state), apply the exact comparison and, if it spawns, draw the kind.  -1 = no spawn.
+SB_HD int sb_resolve_candidate(const SbDev& d, uint32_t env, uint32_t tick, uint32_t cell,
+                               const uint32_t* __restrict__ rk) {
+  const SbU4 r = sb_philox_rk(env, tick, cell >> 4, SB_DOM_SWEEP, rk);
+  const uint32_t r8 = sb_byte_of(r, (int)(cell & 15u));
+  if (r8 > d.hi8) return -1;  // the filter bound is a power of two >= hi8 + 1
+  return sb_resolve_spawn(d, env, tick, cell, r8 == d.hi8, rk);
 }
 
 // Byte-SIMD first-level FILTER for 4 cells (one 32-bit word of kinds / random bytes): returns 0x80 in
@@ -205,5 +242,12 @@ SB_HD uint32_t sb_window_code(const SbDev& d, const uint8_t* genv, int y, int x,
   if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W)
     return pl == 0 ? (uint32_t)d.fill_channel : 255u;  // out of bounds: the fill kind, once
   uint32_t kind = genv[pl * d.plane_stride + yy * d.W + xx];
+  if (d.K <= 8) {  // 8-entry table in a register pair, one byte-permute
+#if defined(__CUDA_ARCH__)
+    return __byte_perm((uint32_t)d.channel8, (uint32_t)(d.channel8 >> 32), kind & 7u) & 0xFFu;
+#else
+    return (uint32_t)(d.channel8 >> (8 * (kind & 7u))) & 0xFFu;
+#endif
+  }
   return kind < (uint32_t)SB_MAX_KINDS ? d.channel[kind] : 255u;
 }

@@ -26,8 +26,12 @@ struct StepParams {
   uint8_t* grid;
   int32_t* agent_pos;
   double* total_reward;
-  // shared-memory layout, computed once on the host (sb_step.cu: launch_one)
-  int32_t lut_bytes, q_bytes, env_smem, stage_off;
+  // shared-memory layout (struct-of-arrays over the block's instances), computed on the host in
+  // sb_step.cu: launch_one.  Per-instance strides are padded to 64 (mod 128) bytes so the two groups
+  // served by one quarter-warp of a 128-bit shared access hit disjoint banks.
+  int32_t q_off, planes_off, pos_off, stage_off;  // block-level byte offsets
+  int32_t plane_env, stage_env;                   // per-instance strides of planes / staging rows
+  uint32_t rk[20];                                // Philox round keys of a.seed (constant-bank operands)
 };
 
 int note_cuda_error();  // records cudaGetLastError() text for sb_last_cuda_error, returns SB_ECUDA

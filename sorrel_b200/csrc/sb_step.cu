@@ -22,22 +22,31 @@ namespace sb {
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// Shared memory per instance: dynamic planes | agent yx[A] | agent actions[A] | staging row.
-// The staging row holds ONE observation (obs_size floats + 4 of alignment slack); it is all-zero
-// between observations.  The per-instance size is padded to 64 (mod 128) bytes so that the two
-// groups served by one quarter-warp of a 128-bit shared-memory access hit disjoint banks.
-__host__ __device__ inline int stage_offset_bytes(const SbDev& d) { return round_up(d.env_stride + 8 * d.A, 16); }
-
-__host__ __device__ inline int env_smem_bytes(const SbDev& d) {
-  int b = round_up(stage_offset_bytes(d) + 4 * (d.obs_size + 4), 16);
+__host__ __device__ inline int pad64mod128(int b) {
+  b = round_up(b, 16);
   while ((b & 127) != 64) b += 16;
   return b;
 }
 
-__host__ __device__ inline int block_smem_bytes(const SbDev& d, int threads, int lpe) {
-  int lut = round_up(2 * d.SS, 16);
-  int q = round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
-  return lut + q + (threads / lpe) * env_smem_bytes(d);
+// Shared-memory layout of a block (see StepParams).  The staging row of an instance holds ONE
+// observation (+4 elements of alignment slack) and is all-zero between observations; it is bf16 when a
+// single stored plane is observed (entries are 0 or 1: the float is the bf16 shifted left by 16) and
+// f32 otherwise (entries are sums over planes).
+struct SmemLayout {
+  int q_off, planes_off, pos_off, stage_off, plane_env, stage_env, total;
+};
+
+__host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, bool np1) {
+  SmemLayout L;
+  const int epb = threads / lpe;
+  L.q_off = round_up(2 * d.SS, 16);
+  L.planes_off = L.q_off + round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
+  L.plane_env = pad64mod128(d.env_stride);
+  L.pos_off = L.planes_off + epb * L.plane_env;
+  L.stage_off = L.pos_off + round_up(epb * 8 * d.A, 16);
+  L.stage_env = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
+  L.total = L.stage_off + epb * L.stage_env;
+  return L;
 }
 
 __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float e) {
@@ -48,7 +57,7 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
 
 // LPE  lanes per instance; RNG  SB_K_* sweep variant; NP1  one stored plane + one-hot fast path
 template <int LPE, int RNG, bool NP1>
-__global__ void __launch_bounds__(SB_THREADS)
+__global__ void __launch_bounds__(SB_THREADS, 8)
     step_kernel(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int EPB = SB_THREADS / LPE;
@@ -61,21 +70,23 @@ __global__ void __launch_bounds__(SB_THREADS)
 
   // ---- carve shared memory --------------------------------------------------------------
   uint16_t* lut_ij = reinterpret_cast<uint16_t*>(smem_raw);  // [SS] (i << 8) | j of window cell ij
-  uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + p.lut_bytes);
+  uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + p.q_off);
   uint32_t* q = qbase + warp * (SB_QCAP + 1);  // spawn candidates of this warp's instances
   uint32_t* qn = q + SB_QCAP;
-  const int esz = p.env_smem;
-  uint8_t* envs = smem_raw + p.lut_bytes + p.q_bytes;
+  const int esz = p.plane_env;
+  uint8_t* envs = smem_raw + p.planes_off;
   uint8_t* genv = envs + grp * esz;
-  uint32_t* spos = reinterpret_cast<uint32_t*>(genv + d.env_stride);
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * 2 * d.A;
   int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
-  float* stage = reinterpret_cast<float*>(genv + p.stage_off);
+  uint8_t* stage_raw = smem_raw + p.stage_off + grp * p.stage_env;
+  float* stage = reinterpret_cast<float*>(stage_raw);          // !NP1
+  uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_raw);  // NP1: bf16
 
   for (int ij = tid; ij < d.SS; ij += SB_THREADS) {
     int i = ij / d.S;
     lut_ij[ij] = (uint16_t)((i << 8) | (ij - i * d.S));
   }
-  for (int e = lane; e < d.obs_size + 4; e += LPE) stage[e] = 0.0f;
+  for (int e = lane; e < p.stage_env / 4; e += LPE) reinterpret_cast<uint32_t*>(stage_raw)[e] = 0u;
   if (wlane == 0) *qn = 0;
   __syncthreads();
 
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(SB_THREADS)
   const long long env = env0 + grp;
   const bool active = env < d.N;
   const uint32_t envid = (uint32_t)(d.env_id_base + (uint64_t)env);
-  const uint32_t k0 = (uint32_t)p.a.seed, k1 = (uint32_t)(p.a.seed >> 32);
+  const uint32_t* __restrict__ rk = p.rk;
 
   // ---- stage the instance ------------------------------------------------------------------
   uint4* genv4 = reinterpret_cast<uint4*>(genv);
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(SB_THREADS)
       for (int a = lane; a < d.A; a += LPE) {
         int act = 0;
         if (p.a.policy == SB_POLICY_UNIFORM) {
-          SbU4 w = sb_philox(envid, tick, (uint32_t)a, SB_DOM_ACTION, k0, k1);
+          SbU4 w = sb_philox_rk(envid, tick, (uint32_t)a, SB_DOM_ACTION, rk);
           act = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
         } else if (active && p.a.d_actions) {
           act = p.a.d_actions[((size_t)t * d.N + env) * d.A + a];
@@ -162,31 +173,27 @@ __global__ void __launch_bounds__(SB_THREADS)
         // once instead of diverging inside the chunk loop.
         const uint32_t spawn4 = (uint32_t)d.single_spawn_kind * 0x01010101u;
         const int iters = (d.n_chunks + LPE - 1) / LPE;
+        // The loop stays rolled (one Philox body in the instruction cache); a lane that finds
+        // candidates only appends their cell ids to the warp queue.
+#pragma unroll 1
         for (int it = 0; it < iters; ++it) {
           const int c = it * LPE + lane;
           uint32_t m = 0;
-          SbU4 r;
-          r.x = r.y = r.z = r.w = 0;
           if (c < d.n_chunks) {
             const uint4 k = genv4[c];
-            r = sb_philox(envid, tick, (uint32_t)c, SB_DOM_SWEEP, k0, k1);
+            const SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
             m = sb_simd_cand_chunk(k.x, k.y, k.z, k.w, r.x, r.y, r.z, r.w, spawn4, d.hmask4);
           }
           if (__ballot_sync(0xFFFFFFFFu, m != 0)) {
             while (m) {
-              const int pos = __ffs(m) - 1;  // bit 8*b + w: byte b of word w
+              const int pos = __ffs(m) - 1;  // bit 8*b + w: byte b of word w of the chunk
               m &= m - 1;
-              const int w = pos & 7, b = pos >> 3;
-              const uint32_t rw = (w & 2) ? ((w & 1) ? r.w : r.z) : ((w & 1) ? r.y : r.x);
-              const uint32_t r8 = (rw >> (8 * b)) & 0xFFu;
-              if (r8 > d.hi8) continue;  // the filter is a superset (power-of-two bound)
-              const uint32_t cell = (uint32_t)(c * 16 + 4 * w + b);
-              const uint32_t entry = ((r8 == d.hi8) ? 0x80000000u : 0u) | ((uint32_t)grp << 20) | cell;
+              const uint32_t cell = (uint32_t)(c * 16 + 4 * (pos & 7) + (pos >> 3));
               const uint32_t at = atomicAdd(qn, 1u);
               if (at < SB_QCAP) {
-                q[at] = entry;
+                q[at] = ((uint32_t)grp << 20) | cell;
               } else {  // queue full (dense spawning): resolve in place
-                int kind = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, k0, k1);
+                const int kind = sb_resolve_candidate(d, envid, tick, cell, rk);
                 if (kind >= 0) genv[cell] = (uint8_t)kind;
               }
             }
@@ -195,24 +202,24 @@ __global__ void __launch_bounds__(SB_THREADS)
         __syncwarp();
         const uint32_t nq = min(*qn, (uint32_t)SB_QCAP);
         for (uint32_t i = wlane; i < nq; i += 32) {
-          uint32_t entry = q[i];
-          uint32_t g = (entry >> 20) & 0x7FFu, cell = entry & 0xFFFFFu;
-          uint32_t eid = (uint32_t)(d.env_id_base + (uint64_t)(env0 + g));
-          int kind = sb_resolve_spawn(d, eid, tick, cell, (entry >> 31) != 0, k0, k1);
+          const uint32_t entry = q[i];
+          const uint32_t g = entry >> 20, cell = entry & 0xFFFFFu;
+          const uint32_t eid = (uint32_t)(d.env_id_base + (uint64_t)(env0 + g));
+          const int kind = sb_resolve_candidate(d, eid, tick, cell, rk);
           if (kind >= 0) envs[g * esz + cell] = (uint8_t)kind;
         }
         __syncwarp();
         if (wlane == 0) *qn = 0;
       } else {  // SB_K_PHILOX_GENERIC: several spawning kinds or a large probability
         for (int c = lane; c < d.n_chunks; c += LPE) {
-          SbU4 r = sb_philox(envid, tick, (uint32_t)c, SB_DOM_SWEEP, k0, k1);
+          SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
           for (int b = 0; b < 16; ++b) {
             uint32_t cell = (uint32_t)(c * 16 + b);
             uint32_t kind = genv[cell];
             if (kind >= (uint32_t)SB_MAX_KINDS || !((d.spawn_mask >> kind) & 1u)) continue;
             uint32_t r8 = sb_byte_of(r, b);
             if (r8 > d.hi8) continue;
-            int nk = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, k0, k1);
+            int nk = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, rk);
             if (nk >= 0) genv[cell] = (uint8_t)nk;
           }
         }
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(SB_THREADS)
               const uint32_t l = lut_ij[ij];
               if (NP1) {  // one stored plane: every window cell contributes at most one 1.0
                 const uint32_t code = sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), 0);
-                if (code != 255u) stage[off + code * d.SS + ij] = 1.0f;
+                if (code != 255u) stage16[off + code * d.SS + ij] = 0x3F80;  // bf16(1.0)
               } else {
                 for (int pl = 0; pl < d.n_planes; ++pl) {
                   const uint32_t code = sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), pl);
@@ -256,22 +263,40 @@ __global__ void __launch_bounds__(SB_THREADS)
           }
           __syncwarp();
           if (dst) {
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < head && lane < d.obs_size) {
-              dst[lane] = stage[off + lane];
-              stage[off + lane] = 0.0f;
-            }
             const int nvec = d.obs_size > head ? (d.obs_size - head) >> 2 : 0;
-            float4* s4 = reinterpret_cast<float4*>(stage + off + head);
-            for (int qv = lane; qv < nvec; qv += LPE) {
-              const float4 v = s4[qv];
-              s4[qv] = zero4;
-              st_f4(dst + head + 4 * qv, v.x, v.y, v.z, v.w);
-            }
-            const int e = head + 4 * nvec + lane;
-            if (e < d.obs_size) {
-              dst[e] = stage[off + e];
-              stage[off + e] = 0.0f;
+            const int etail = head + 4 * nvec + lane;
+            if (NP1) {
+              if (lane < head && lane < d.obs_size) {
+                dst[lane] = __uint_as_float((uint32_t)stage16[off + lane] << 16);
+                stage16[off + lane] = 0;
+              }
+              uint2* s2 = reinterpret_cast<uint2*>(stage16 + off + head);  // 4 bf16 per 8-byte load
+              for (int qv = lane; qv < nvec; qv += LPE) {
+                const uint2 w = s2[qv];
+                s2[qv] = make_uint2(0u, 0u);
+                st_f4(dst + head + 4 * qv, __uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
+                      __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+              }
+              if (etail < d.obs_size) {
+                dst[etail] = __uint_as_float((uint32_t)stage16[off + etail] << 16);
+                stage16[off + etail] = 0;
+              }
+            } else {
+              const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (lane < head && lane < d.obs_size) {
+                dst[lane] = stage[off + lane];
+                stage[off + lane] = 0.0f;
+              }
+              float4* s4 = reinterpret_cast<float4*>(stage + off + head);
+              for (int qv = lane; qv < nvec; qv += LPE) {
+                const float4 v = s4[qv];
+                s4[qv] = zero4;
+                st_f4(dst + head + 4 * qv, v.x, v.y, v.z, v.w);
+              }
+              if (etail < d.obs_size) {
+                dst[etail] = stage[off + etail];
+                stage[off + etail] = 0.0f;
+              }
             }
           }
           __syncwarp();
@@ -351,11 +376,11 @@ __global__ void __launch_bounds__(SB_THREADS)
 // ----------------------------------------------------------------------------------------------
 template <int LPE, int RNG, bool NP1>
 static int launch_one(const SbDev& d, StepParams p, cudaStream_t s) {
-  p.lut_bytes = round_up(2 * d.SS, 16);
-  p.q_bytes = round_up((SB_THREADS / 32) * (SB_QCAP + 1) * 4, 16);
-  p.env_smem = env_smem_bytes(d);
-  p.stage_off = stage_offset_bytes(d);
-  const int smem = block_smem_bytes(d, SB_THREADS, LPE);
+  const SmemLayout L = smem_layout(d, SB_THREADS, LPE, NP1);
+  sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
+  p.q_off = L.q_off, p.planes_off = L.planes_off, p.pos_off = L.pos_off, p.stage_off = L.stage_off;
+  p.plane_env = L.plane_env, p.stage_env = L.stage_env;
+  const int smem = L.total;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
   auto kern = step_kernel<LPE, RNG, NP1>;
   if (smem > 48 * 1024) {
@@ -388,8 +413,11 @@ int pick_lpe(const SbDev& d) {
   }
   int lpe = 4;
   while (lpe < 32 && d.n_chunks / lpe > 8) lpe *= 2;
+  // small batches: widen the group until ~16 warps per SM are in flight (148 SMs), trading lane
+  // efficiency for latency (config 2: 4096 instances would otherwise occupy 128 blocks)
+  while (lpe < 32 && (long long)d.N * lpe < 148LL * 16 * 32) lpe *= 2;
   // shared memory must fit
-  while (lpe < 32 && block_smem_bytes(d, SB_THREADS, lpe) > 200 * 1024) lpe *= 2;
+  while (lpe < 32 && smem_layout(d, SB_THREADS, lpe, false).total > 200 * 1024) lpe *= 2;
   return lpe;
 }
 
