@@ -359,8 +359,10 @@ def run_ours(a):
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("step_kernel_dram_bytes_per_launch")
+    if os.path.exists(tp):  # ncu-measured DRAM bytes of one launch; only valid for the shape it was taken on
+        tj = json.load(open(tp))
+        if (tj.get("envs_per_gpu"), tj.get("turns"), tj.get("agents"), tj.get("size")) == (N, T, A, a.size):
+            traffic = tj.get("step_kernel_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "sb::step_kernel", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
