@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks")
+    ap.add_argument("--obs-study", action="store_true",
+                    help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
     return ap.parse_args()
 
 
@@ -388,9 +390,61 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_obs_study(a):
+    """BASELINE configs[3]: large map, many agents, one-hot crop written at HBM speed (sb_observe alone)."""
+    import torch
+
+    from sorrel_b200.engine import Engine
+    import sb_testutil as util
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    spec = util.engine_spec(oracle_spec(a))
+    N, A = a.envs_total, a.agents
+    eng = Engine(spec, N, device=dev, seed=a.seed)
+    eng.reset()
+    # ~35 % of the interior pre-seeded with items (steady-state density of the reference, SURVEY 8d)
+    g = eng.grid[:, 0, : a.size * a.size]
+    items = torch.randint(2, 5, g.shape, device=dev, dtype=torch.uint8)
+    mask = (g == 0) & (torch.rand(g.shape, device=dev) < 0.35)
+    g[mask] = items[mask]
+    S = 2 * a.vision + 1
+    obs = spec.channels * S * S
+    # rotate over several output tensors so that consecutive launches do not hit lines still in L2
+    n_out = max(2, int(200e6 // (N * A * obs * 4)) + 1)
+    outs = [torch.empty((N, A, spec.channels, S, S), dtype=torch.float32, device=dev) for _ in range(n_out)]
+    for i in range(a.warmup):
+        eng.observe(outs[i % n_out])
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for i in range(a.steps):
+        evs[i][0].record()
+        eng.observe(outs[i % n_out])
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    ms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    k_ms = sum(ms) / len(ms)
+    alg = N * A * obs * 4 + N * a.size * a.size + N * A * 4
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    ach = alg / (k_ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "observations_per_sec", "value": N * A / (k_ms * 1e-3), "unit": "obs/s", "n_gpus": 1,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": k_ms, "higher_is_better": True, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"obs-kernel study: {N} envs x {A} agents, {a.size}x{a.size} map, {S}x{S} one-hot "
+                               f"window, C={spec.channels}, {obs * 4} B per observation, {n_out} rotating outputs"},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "kernel": "sb::observe_kernel", "kernel_ms": k_ms, "kernel_ms_min": ms[0],
+                     "algorithmic_bytes_per_launch": alg},
+    }), flush=True)
+
+
 def main():
     a = parse_args()
-    if a.impl == "reference":
+    if a.obs_study:
+        run_obs_study(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

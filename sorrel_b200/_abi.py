@@ -24,7 +24,8 @@ SB_RNG_TAPE, SB_RNG_PHILOX = 0, 1
 SB_POLICY_TAPE, SB_POLICY_UNIFORM = 0, 1
 SB_MODE_FUSED, SB_MODE_SPLIT = 0, 1
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsorrel_b200.so")
+LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                         "libsorrel_b200.so")
 
 
 class SbWorldDesc(C.Structure):

@@ -86,6 +86,7 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   d.S = 2 * d.v + 1;
   d.SS = d.S * d.S;
   d.obs_size = d.C * d.SS;
+  d.inv_S = (65536u + (uint32_t)d.S - 1u) / (uint32_t)d.S;
   d.fill_kind = w->fill_kind;
   d.agent_kind = w->agent_kind;
   d.default_kind = w->default_kind;
@@ -453,20 +454,7 @@ int sb_observe(const SbWorldDesc* w, const uint8_t* d_grid, const int32_t* d_age
   if (rc) return rc;
   if (!d_grid || !d_agent_pos || !d_obs_out) return SB_EINVAL;
   if (!aligned16(d_grid)) return SB_EALIGN;
-  StepParams p;
-  memset(&p, 0, sizeof(p));
-  p.a.mode = SB_MODE_SPLIT;
-  p.a.num_turns = 1;
-  p.a.rng = SB_RNG_PHILOX;
-  p.a.policy = SB_POLICY_TAPE;
-  p.a.act_agent = -1;
-  p.a.obs_agent = SB_OBS_ALL;
-  p.a.d_obs_out = d_obs_out;
-  p.write_back = 0;
-  p.grid = const_cast<uint8_t*>(d_grid);
-  p.agent_pos = const_cast<int32_t*>(d_agent_pos);
-  p.total_reward = nullptr;
-  return launch_step(d, p, (cudaStream_t)stream);
+  return launch_observe(d, d_grid, d_agent_pos, d_obs_out, (cudaStream_t)stream);
 }
 
 int sb_buffer_add(const SbBufferDesc* buf, int32_t slot, const float* d_obs, const int64_t* d_actions,

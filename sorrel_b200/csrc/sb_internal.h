@@ -40,5 +40,6 @@ void count_launch();
 int make_dev(const SbWorldDesc* desc, SbDev* out);  // validates + derives the device view
 int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s);
 int pick_lpe(const SbDev& d);
+int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos, float* out, cudaStream_t s);
 
 }  // namespace sb

@@ -18,6 +18,16 @@
 #include "sb_core.cuh"
 #include "sb_internal.h"
 
+// tuning knobs (compile-time; the defaults are the measured best, see profiles/README.md)
+#ifndef SB_SCATTER_UNROLL
+#define SB_SCATTER_UNROLL 1
+#endif
+#ifndef SB_COPY_UNROLL
+#define SB_COPY_UNROLL 1
+#endif
+#define SB_PRAGMA_(x) _Pragma(#x)
+#define SB_UNROLL(n) SB_PRAGMA_(unroll n)
+
 namespace sb {
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -55,6 +65,173 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
                : "memory");
 }
 
+// One observation row through the one-hot fast path, by the LANES lanes that own the instance (all
+// of them must call; `dst == nullptr` only takes part in the synchronisation; the caller issues the
+// trailing __syncwarp, which lets it overlap the agent's move with the stream-out).  The row is all zeros
+// except one entry per (window cell, stored plane): the lanes scatter those into the zeroed staging
+// row, then stream the row out with wide shared loads / 128-bit global stores, zeroing it again on the
+// way.  `off` shifts the row inside the staging buffer so that the first 16-byte aligned global
+// address lines up with an aligned shared address (ring rows are only 8-byte aligned: 600 B, 1944 B).
+// `genv` may point to shared or global memory.
+template <int LANES, bool NP1>
+__device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint16_t* lut_ij,
+                                                uint8_t* stage_raw, int y, int x, float* dst, int lane) {
+  float* stage = reinterpret_cast<float*>(stage_raw);          // !NP1: f32 sums over planes
+  uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_raw);  // NP1: bf16 (0 or 1.0)
+  const int head = dst ? (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3 : 0;
+  const int off = (4 - head) & 3;
+  if (dst) {
+    // window cell ij -> (i, j) = (ij / S, ij % S) by multiply-shift (exact for ij < 512, S <= 21); the
+    // loop is unrolled so the dependent shared-memory reads of several cells are in flight together
+    const uint32_t inv_s = d.inv_S;
+SB_UNROLL(SB_SCATTER_UNROLL)
+    for (int ij = lane; ij < d.SS; ij += LANES) {
+#ifdef SB_IJ_LUT
+      const uint32_t l_ = lut_ij[ij];
+      const int i = (int)(l_ >> 8), j = (int)(l_ & 255u);
+#else
+      const int i = (int)(((uint32_t)ij * inv_s) >> 16), j = ij - i * d.S;
+#endif
+      if (NP1) {  // one stored plane: every window cell contributes at most one 1.0
+        const uint32_t code = sb_window_code(d, genv, y, x, i, j, 0);
+        if (code != 255u) stage16[off + code * d.SS + ij] = 0x3F80;  // bf16(1.0)
+      } else {
+        for (int pl = 0; pl < d.n_planes; ++pl) {
+          const uint32_t code = sb_window_code(d, genv, y, x, i, j, pl);
+          if (code != 255u) stage[off + code * d.SS + ij] += 1.0f;  // planes are summed
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (dst) {
+    const int nvec = d.obs_size > head ? (d.obs_size - head) >> 2 : 0;
+    const int etail = head + 4 * nvec + lane;
+    if (NP1) {
+      if (lane < head && lane < d.obs_size) {
+        dst[lane] = __uint_as_float((uint32_t)stage16[off + lane] << 16);
+        stage16[off + lane] = 0;
+      }
+      uint2* s2 = reinterpret_cast<uint2*>(stage16 + off + head);  // 4 bf16 per 8-byte load
+SB_UNROLL(SB_COPY_UNROLL)
+      for (int qv = lane; qv < nvec; qv += LANES) {
+        const uint2 w = s2[qv];
+        s2[qv] = make_uint2(0u, 0u);
+        st_f4(dst + head + 4 * qv, __uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
+              __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+      }
+      if (etail < d.obs_size) {
+        dst[etail] = __uint_as_float((uint32_t)stage16[off + etail] << 16);
+        stage16[off + etail] = 0;
+      }
+    } else {
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < head && lane < d.obs_size) {
+        dst[lane] = stage[off + lane];
+        stage[off + lane] = 0.0f;
+      }
+      float4* s4 = reinterpret_cast<float4*>(stage + off + head);
+SB_UNROLL(SB_COPY_UNROLL)
+      for (int qv = lane; qv < nvec; qv += LANES) {
+        const float4 v = s4[qv];
+        s4[qv] = zero4;
+        st_f4(dst + head + 4 * qv, v.x, v.y, v.z, v.w);
+      }
+      if (etail < d.obs_size) {
+        dst[etail] = stage[off + etail];
+        stage[off + etail] = 0.0f;
+      }
+    }
+  }
+  // NOTE: the caller must __syncwarp() before the staging row is scattered into again.
+}
+
+// ----------------------------------------------------------------------------------------------
+// Standalone observation kernel (sb_observe): a pure function of grid + positions, so every
+// (instance, agent) pair is independent: one warp per pair, window cells read straight from global
+// memory (the instance's planes are shared by its agents through L1/L2), rows streamed out with
+// 128-bit stores.  Config 4 (128x128, 64 agents, 9x9 window): 1944 B written per pair.
+// ----------------------------------------------------------------------------------------------
+constexpr int OBS_THREADS = 256;
+
+// LANES lanes (16 or 32) serve one (instance, agent) pair; every group walks a CONTIGUOUS range of
+// pairs so that (env, agent) advance incrementally (no divisions in the loop), the agents of one
+// instance are served back to back (its planes stay in L1) and consecutive rows land in the same DRAM
+// pages.
+template <bool NP1, int LANES>
+__global__ void __launch_bounds__(OBS_THREADS)
+    observe_kernel(const __grid_constant__ SbDev d, const uint8_t* __restrict__ grid,
+                   const int32_t* __restrict__ agent_pos, float* __restrict__ out, int stage_bytes, int fast,
+                   unsigned pairs_per_group) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int GROUPS = OBS_THREADS / LANES;
+  uint16_t* lut_ij = reinterpret_cast<uint16_t*>(smem_raw);
+  const int lut_bytes = round_up(2 * d.SS, 16);
+  const int grp = threadIdx.x / LANES, lane = threadIdx.x & (LANES - 1);
+  uint8_t* stage_raw = smem_raw + lut_bytes + grp * stage_bytes;
+  for (int ij = threadIdx.x; ij < d.SS; ij += OBS_THREADS) {
+    int i = ij / d.S;
+    lut_ij[ij] = (uint16_t)((i << 8) | (ij - i * d.S));
+  }
+  for (int e = lane; e < stage_bytes / 4; e += LANES) reinterpret_cast<uint32_t*>(stage_raw)[e] = 0u;
+  __syncthreads();
+  const unsigned long long pairs = (unsigned long long)d.N * d.A;
+  const unsigned long long first = ((unsigned long long)blockIdx.x * GROUPS + grp) * pairs_per_group;
+  unsigned long long env = first / (unsigned)d.A;
+  int a = (int)(first - env * (unsigned)d.A);
+  for (unsigned k = 0; k < pairs_per_group; ++k) {  // uniform trip count: both halves of a warp stay in step
+    const unsigned long long pair = first + k;
+    const bool valid = pair < pairs;
+    int y = 0, x = 0;
+    if (valid) {
+      const int pos = agent_pos[pair];
+      y = pos / d.W;
+      x = pos - y * d.W;
+    }
+    const uint8_t* genv = grid + (size_t)(valid ? env : 0) * d.env_stride;
+    float* dst = valid ? out + (size_t)pair * d.obs_size : nullptr;
+    if (fast) {
+      emit_onehot_row<LANES, NP1>(d, genv, lut_ij, stage_raw, y, x, dst, lane);
+      __syncwarp();
+    } else if (valid) {
+      for (int e = lane; e < d.obs_size; e += LANES) {
+        const int c = e / d.SS;
+        const uint32_t li = lut_ij[e - c * d.SS];
+        dst[e] = (float)sb_obs_general(d, genv, d.tmpl, d.app, y, x, c, (int)(li >> 8), (int)(li & 255u));
+      }
+    }
+    if (++a == d.A) {
+      a = 0;
+      ++env;
+    }
+  }
+}
+
+int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos, float* out, cudaStream_t s) {
+  const bool np1 = d.fast_obs && d.n_planes == 1;
+  const int lanes = d.obs_size <= 256 ? 16 : 32;  // small rows: two pairs per warp
+  const int groups = OBS_THREADS / lanes;
+  const int stage_bytes = round_up((d.obs_size + 4) * (np1 ? 2 : 4), 16);
+  const int smem = round_up(2 * d.SS, 16) + groups * stage_bytes;
+  if (smem > 227 * 1024) return SB_EUNSUPPORTED;
+  const unsigned long long pairs = (unsigned long long)d.N * d.A;
+  // persistent grid: up to 8 blocks (64 warps) per SM; each group takes a contiguous run of pairs
+  unsigned long long blocks = (pairs + groups - 1) / groups;
+  if (blocks > 148ull * 8) blocks = 148ull * 8;
+  const unsigned long long ppg = (pairs + blocks * groups - 1) / (blocks * groups);
+  if (ppg > 0xFFFFFFFFull) return SB_EUNSUPPORTED;
+  auto launch = [&](auto kern) -> int {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return note_cuda_error();
+    kern<<<(unsigned)blocks, OBS_THREADS, smem, s>>>(d, grid, agent_pos, out, stage_bytes, d.fast_obs, (unsigned)ppg);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : note_cuda_error();
+  };
+  if (lanes == 16) return np1 ? launch(observe_kernel<true, 16>) : launch(observe_kernel<false, 16>);
+  return np1 ? launch(observe_kernel<true, 32>) : launch(observe_kernel<false, 32>);
+}
+
 // LPE  lanes per instance; RNG  SB_K_* sweep variant; NP1  one stored plane + one-hot fast path
 template <int LPE, int RNG, bool NP1>
 __global__ void __launch_bounds__(SB_THREADS, 8)
@@ -79,8 +256,6 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * 2 * d.A;
   int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
   uint8_t* stage_raw = smem_raw + p.stage_off + grp * p.stage_env;
-  float* stage = reinterpret_cast<float*>(stage_raw);          // !NP1
-  uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_raw);  // NP1: bf16
 
   for (int ij = tid; ij < d.SS; ij += SB_THREADS) {
     int i = ij / d.S;
@@ -237,69 +412,10 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
                     ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size
                     : nullptr;
       if (NP1 || d.fast_obs) {
-        // The row is all zeros except one entry per (window cell, stored plane): scatter those into
-        // the zeroed staging row, then stream the row out with 128-bit shared loads / global stores,
-        // zeroing it again on the way.  `off` shifts the row inside the staging buffer so that the
-        // first 16-byte aligned global address lines up with a 16-byte aligned shared address.
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          float* dst = dsts[k];
-          if (k == 1 && !p.a.d_obs_out) break;  // uniform: no second destination in this launch
-          const int head = dst ? (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3 : 0;
-          const int off = (4 - head) & 3;
-          if (dst) {
-            for (int ij = lane; ij < d.SS; ij += LPE) {
-              const uint32_t l = lut_ij[ij];
-              if (NP1) {  // one stored plane: every window cell contributes at most one 1.0
-                const uint32_t code = sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), 0);
-                if (code != 255u) stage16[off + code * d.SS + ij] = 0x3F80;  // bf16(1.0)
-              } else {
-                for (int pl = 0; pl < d.n_planes; ++pl) {
-                  const uint32_t code = sb_window_code(d, genv, y, x, (int)(l >> 8), (int)(l & 255u), pl);
-                  if (code != 255u) stage[off + code * d.SS + ij] += 1.0f;  // planes are summed
-                }
-              }
-            }
-          }
+        emit_onehot_row<LPE, NP1>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
+        if (p.a.d_obs_out) {
           __syncwarp();
-          if (dst) {
-            const int nvec = d.obs_size > head ? (d.obs_size - head) >> 2 : 0;
-            const int etail = head + 4 * nvec + lane;
-            if (NP1) {
-              if (lane < head && lane < d.obs_size) {
-                dst[lane] = __uint_as_float((uint32_t)stage16[off + lane] << 16);
-                stage16[off + lane] = 0;
-              }
-              uint2* s2 = reinterpret_cast<uint2*>(stage16 + off + head);  // 4 bf16 per 8-byte load
-              for (int qv = lane; qv < nvec; qv += LPE) {
-                const uint2 w = s2[qv];
-                s2[qv] = make_uint2(0u, 0u);
-                st_f4(dst + head + 4 * qv, __uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
-                      __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
-              }
-              if (etail < d.obs_size) {
-                dst[etail] = __uint_as_float((uint32_t)stage16[off + etail] << 16);
-                stage16[off + etail] = 0;
-              }
-            } else {
-              const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (lane < head && lane < d.obs_size) {
-                dst[lane] = stage[off + lane];
-                stage[off + lane] = 0.0f;
-              }
-              float4* s4 = reinterpret_cast<float4*>(stage + off + head);
-              for (int qv = lane; qv < nvec; qv += LPE) {
-                const float4 v = s4[qv];
-                s4[qv] = zero4;
-                st_f4(dst + head + 4 * qv, v.x, v.y, v.z, v.w);
-              }
-              if (etail < d.obs_size) {
-                dst[etail] = stage[off + etail];
-                stage[off + etail] = 0.0f;
-              }
-            }
-          }
-          __syncwarp();
+          emit_onehot_row<LPE, NP1>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
         }
       } else {
         for (int e = lane; e < d.obs_size; e += LPE) {
@@ -342,6 +458,9 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
     if (fused) {
       for (int a = 0; a < d.A; ++a) {
         observe(a);
+#ifdef SB_SPLIT_SYNC
+        __syncwarp();
+#endif
         act(a);
       }
     } else {
@@ -413,6 +532,7 @@ int pick_lpe(const SbDev& d) {
   }
   int lpe = 4;
   while (lpe < 32 && d.n_chunks / lpe > 8) lpe *= 2;
+  if (d.A >= 4 && lpe < 8) lpe = 8;  // agent phases dominate: halve their latency (measured, profiles/README.md)
   // small batches: widen the group until ~16 warps per SM are in flight (148 SMs), trading lane
   // efficiency for latency (config 2: 4096 instances would otherwise occupy 128 blocks)
   while (lpe < 32 && (long long)d.N * lpe < 148LL * 16 * 32) lpe *= 2;

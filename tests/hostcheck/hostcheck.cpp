@@ -1,0 +1,101 @@
+// hostcheck.cpp -- compiles the kernels' per-lane device functions (sorrel_b200/csrc/sb_core.cuh) for the
+// HOST so that the CPU test-suite can unit-test them against the oracle without a GPU.
+// TEST-ONLY: nothing in the product loads this library; it is not a CPU fallback (no kernel, no tiling,
+// no entry point of include/sorrel_b200.h is implemented here).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../sorrel_b200/csrc/sb_core.cuh"
+
+extern "C" {
+
+void hc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, uint32_t* out_rk) {
+  SbU4 r = sb_philox(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
+  uint32_t rk[20];
+  sb_philox_round_keys(key[0], key[1], rk);
+  SbU4 q = sb_philox_rk(ctr[0], ctr[1], ctr[2], ctr[3], rk);
+  out_rk[0] = q.x, out_rk[1] = q.y, out_rk[2] = q.z, out_rk[3] = q.w;
+}
+
+static void set_prob(SbDev* d, double p, int n_choices) {
+  uint64_t thr = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(p, 53)));
+  d->p = p;
+  d->hi8 = (uint32_t)(thr >> 45);
+  d->lo45 = thr & ((1ull << 45) - 1);
+  d->n_choices = n_choices;
+  d->choices_packed = 0x0706050403020100ull;
+  uint32_t n2 = 1;
+  while (n2 < d->hi8 + 1u) n2 <<= 1;
+  d->hmask4 = ((~(n2 - 1u)) & 0xFFu) * 0x01010101u;
+}
+
+// first-level filter of one chunk: returns the 16-bit mask (bit = byte index in the chunk) of candidates
+uint32_t hc_filter_chunk(const uint8_t* kinds16, const uint8_t* rnd16, int spawn_kind, double p) {
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  set_prob(&d, p, 3);
+  uint32_t k[4], r[4];
+  memcpy(k, kinds16, 16);
+  memcpy(r, rnd16, 16);
+  uint32_t m = sb_simd_cand_chunk(k[0], k[1], k[2], k[3], r[0], r[1], r[2], r[3], (uint32_t)spawn_kind * 0x01010101u,
+                                  d.hmask4);
+  uint32_t out = 0;
+  for (int pos = 0; pos < 32; ++pos)
+    if (m & (1u << pos)) out |= 1u << (4 * (pos & 7) + (pos >> 3));
+  return out;
+}
+
+uint32_t hc_filter_bound(double p) {  // n2: the filter passes bytes < n2
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  set_prob(&d, p, 3);
+  return ((~d.hmask4) & 0xFFu) + 1u;
+}
+
+int hc_resolve_candidate(double p, int n_choices, uint32_t env, uint32_t tick, uint32_t cell, uint64_t seed) {
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  set_prob(&d, p, n_choices);
+  uint32_t rk[20];
+  sb_philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), rk);
+  return sb_resolve_candidate(d, env, tick, cell, rk);
+}
+
+uint32_t hc_action(uint32_t env, uint32_t tick, uint32_t agent, uint32_t n_actions, uint64_t seed) {
+  SbU4 w = sb_philox(env, tick, agent, SB_DOM_ACTION, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return sb_bounded(w.x, w.y, n_actions);
+}
+
+// one agent move on a single-plane world; returns reward, updates grid / yx / err
+float hc_agent_act(uint8_t* grid, int H, int W, int K, const float* value, uint32_t passable_mask, int agent_kind,
+                   int default_kind, uint32_t* yx, int action, uint32_t* err) {
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  d.H = H, d.W = W, d.K = K, d.plane_stride = (H * W + 15) / 16 * 16, d.agent_plane = 0;
+  d.n_actions = 4;
+  const int8_t dy[4] = {-1, 1, 0, 0}, dx[4] = {0, 0, -1, 1};
+  for (int i = 0; i < 4; ++i) {
+    d.dy_packed |= (uint64_t)(uint8_t)dy[i] << (8 * i);
+    d.dx_packed |= (uint64_t)(uint8_t)dx[i] << (8 * i);
+  }
+  for (int k = 0; k < K; ++k) d.value[k] = value[k];
+  d.passable_mask = passable_mask, d.agent_kind = agent_kind, d.default_kind = default_kind;
+  uint32_t e = 0;
+  float r = sb_agent_act(d, grid, yx, action, true, e);
+  *err = e;
+  return r;
+}
+
+// general-path observation of one element
+double hc_obs_general(const uint8_t* planes, const uint8_t* tmpl, const double* app, int H, int W, int L,
+                      const int* plane_of_layer, int K, int C, int v, int fill_kind, int y, int x, int c, int i, int j) {
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  d.H = H, d.W = W, d.L = L, d.K = K, d.C = C, d.v = v, d.fill_kind = fill_kind;
+  d.plane_stride = (H * W + 15) / 16 * 16;
+  for (int z = 0; z < L; ++z) d.plane_of_layer[z] = plane_of_layer[z];
+  return sb_obs_general(d, planes, tmpl, app, y, x, c, i, j);
+}
+}

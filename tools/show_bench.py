@@ -2,6 +2,6 @@ import json,sys,glob
 for f in sorted(glob.glob(sys.argv[1])):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1]); r=d['roofline']
-        print(f"{f.split('/')[-1]:28s} value={d['value']:.3e} ms/step={d['ms_per_step']:.3f} kernel_ms={r['kernel_ms']:.3f} frac={r['frac']:.3f} share={r['step_kernel_share_of_step']:.2f}")
+        print(f"{f.split('/')[-1]:28s} value={d['value']:.3e} ms/step={d['ms_per_step']:.3f} kernel_ms={r['kernel_ms']:.3f} frac={r['frac']:.3f} share={r.get('step_kernel_share_of_step',0):.2f}")
         if d.get('e2e'): print('    e2e %.3e'%d['e2e']['value'])
     except Exception as e: print(f,'ERR',e)
