@@ -53,6 +53,10 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks")
+    ap.add_argument("--rng", default="philox", choices=["philox", "sparse"],
+                    help="counter-based spawn sampling: philox = one random byte per cell per turn (dense, like the "
+                         "reference's draw-per-cell loop); sparse = Binomial count + distinct cells (same law)")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra sparse-sampler timing")
     ap.add_argument("--obs-study", action="store_true",
                     help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
     return ap.parse_args()
@@ -257,7 +261,7 @@ def run_ours(a):
             if e:
                 e[1].record()
         e = mark("step", record)
-        eng.step(T, buffer=buf, actions=actions, reward_out=reward_out)
+        eng.step(T, buffer=buf, actions=actions, reward_out=reward_out, rng=a.rng)
         if e:
             e[1].record()
         turns_in_episode[0] += T
@@ -297,6 +301,7 @@ def run_ours(a):
     ms_total = g0.elapsed_time(g1)
     eng.check_errors()
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in seg["step"]]
+    seg_main = seg
     breakdown = {k: sum(e0.elapsed_time(e1) for e0, e1 in v) / a.steps for k, v in seg.items()}
     tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -306,12 +311,36 @@ def run_ours(a):
     steps_total = a.envs_total * A * T * a.steps
     value = steps_total / (ms_total * 1e-3)
 
+    # ---------------- the same workload with the sparse spawn sampler (reported beside `value`) ----------------
+    alt = None
+    if a.rng == "philox" and eng.sparse_available and not a.no_alt:
+        a.rng = "sparse"
+        seg = {"boundary": [], "step": [], "sample": []}
+        for _ in range(3):
+            one_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(a.steps):
+            one_step(record=True)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sk = [e0.elapsed_time(e1) for e0, e1 in seg["step"]]
+        alt = {"rng": "sparse (Binomial count + distinct cells; same law as one draw per cell)",
+               "value": steps_total / (float(ts.item()) * 1e-3), "unit": UNIT,
+               "ms_per_step": float(ts.item()) / a.steps, "kernel_ms": sum(sk) / len(sk)}
+        a.rng = "philox"
+        eng.check_errors()
+
     # ---------------- end-to-end with host buffers ----------------
     e2e = None
     if not a.no_e2e:
         from sorrel_b200.hostio import HostStepPipeline
 
-        pipe = HostStepPipeline(eng, buf, T)
+        pipe = HostStepPipeline(eng, buf, T, rng=a.rng)
         h_actions = [torch.randint(0, 4, (T, N, A), dtype=torch.int32).pin_memory() for _ in range(2)]
         for i in range(max(2, a.warmup // 2)):
             if turns_in_episode[0] >= a.max_turns:
@@ -381,8 +410,11 @@ def run_ours(a):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(a), "envs_per_gpu": N, "parallelism": f"env-shard x{world}",
                    "l2": "inputs larger than L2 (grid + ring slots touched per step >> 126 MB)",
-                   "policy": "in-kernel uniform (RandomModel)", "rng": "philox4x32-10"},
+                   "policy": "in-kernel uniform (RandomModel)",
+                   "rng": "philox4x32-10, " + ("one byte per cell per turn" if a.rng == "philox" else
+                                               "sparse (Binomial count + distinct cells)")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
+        "sparse_rng": alt,
         "episodes_reduced": len(episode_stats),
     }
     print(json.dumps(line), flush=True)

@@ -62,7 +62,12 @@ typedef enum SbStatus {
 
 /* sources of randomness / actions for sb_step */
 #define SB_RNG_TAPE 0   /* replay recorded numpy draws: bit-exact to the reference */
-#define SB_RNG_PHILOX 1 /* counter-based Philox4x32-10 keyed by (seed, global env id, tick) */
+#define SB_RNG_PHILOX 1 /* counter-based Philox4x32-10 keyed by (seed, global env id, tick): one random
+                           byte per cell per turn (dense; mirrors the reference's draw-per-cell loop) */
+#define SB_RNG_SPARSE 2 /* same generator, sparse sampling of the same Bernoulli field: the number of
+                           spawning cells K ~ Binomial(cells, p) is drawn first (inverse CDF on
+                           SbWorldDesc.spawn_cdf), then K distinct uniform cells.  Identical in
+                           distribution to per-cell draws; needs spawn_cdf_len > 0 */
 #define SB_POLICY_TAPE 0    /* actions supplied by the caller */
 #define SB_POLICY_UNIFORM 1 /* in-kernel uniform policy == RandomModel, models/base_model.py:107 */
 
@@ -71,6 +76,8 @@ typedef enum SbStatus {
 #define SB_DOM_CELL 0x43450000u   /* index = cell      : 45 refinement bits + 64 choice bits */
 #define SB_DOM_ACTION 0x41430000u /* index = agent     : 64 action bits */
 #define SB_DOM_RESET 0x52530000u  /* index = try       : 64 placement bits */
+#define SB_DOM_SPARSE 0x53500000u /* index 0: 64 bits -> K;  index j >= 1: 64 position bits + 64 choice bits */
+#define SB_SPARSE_KMAX 64         /* entries of the Binomial CDF table */
 
 /*
  * World family description (host memory, copied by value at every call).
@@ -114,7 +121,11 @@ typedef struct SbWorldDesc {
                                  populate_environment, before agents are placed */
   int32_t static_layers_invisible; /* 1 when every kind on a static layer has an all-zero
                                       appearance row (treasurehunt Sand, entities.py:23-31) */
-  int32_t reserved0;
+  int32_t spawn_cdf_len;           /* 0, or SB_SPARSE_KMAX when spawn_cdf is filled (SB_RNG_SPARSE) */
+  /* spawn_cdf[k] = floor(2^64 * P(X <= k)), X ~ Binomial(num_dyn_layers * plane_stride, P/2^53),
+     P = ceil(spawn_prob * 2^53), saturated at 2^64-1; computed exactly (rational arithmetic) by the
+     caller, see sorrel_b200/engine.py: binomial_cdf_u64.  K = #{k : u64 >= spawn_cdf[k]}. */
+  uint64_t spawn_cdf[SB_SPARSE_KMAX];
 } SbWorldDesc;
 
 /*

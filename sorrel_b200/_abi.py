@@ -20,7 +20,8 @@ SB_PAD_KIND = 0xFF
 SB_OK, SB_EINVAL, SB_EUNSUPPORTED, SB_EALIGN, SB_ECUDA, SB_ENODEVICE, SB_EVISION = 0, -1, -2, -3, -4, -5, -6
 SB_ERR_OFFGRID, SB_ERR_TAPE_ALIGN, SB_ERR_BAD_ACTION, SB_ERR_BAD_KIND = 1, 2, 4, 8
 SB_RULE_NONE, SB_RULE_SPAWN = 0, 1
-SB_RNG_TAPE, SB_RNG_PHILOX = 0, 1
+SB_RNG_TAPE, SB_RNG_PHILOX, SB_RNG_SPARSE = 0, 1, 2
+SB_SPARSE_KMAX = 64
 SB_POLICY_TAPE, SB_POLICY_UNIFORM = 0, 1
 SB_MODE_FUSED, SB_MODE_SPLIT = 0, 1
 
@@ -59,7 +60,8 @@ class SbWorldDesc(C.Structure):
         ("h_appearance", C.c_void_p),
         ("d_template", C.c_void_p),
         ("static_layers_invisible", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("spawn_cdf_len", C.c_int32),
+        ("spawn_cdf", C.c_uint64 * 64),
     ]
 
 

@@ -145,6 +145,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   for (int k = d.K; k < SB_MAX_KINDS; ++k) d.channel[k] = 255;
   for (int k = 0; k < 8; ++k) d.channel8 |= (uint64_t)d.channel[k] << (8 * k);
   d.fill_channel = d.channel[d.fill_kind];
+  d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536) ? 1 : 0;
+  if (d.sparse_ok) memcpy(d.cdf, w->spawn_cdf, sizeof(d.cdf));
   d.app = w->d_appearance;
   d.tmpl = w->d_template;
   *out = d;
@@ -430,7 +432,8 @@ int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t*
   }
   const bool sweeps = a->mode == SB_MODE_FUSED || a->do_sweep;
   if (sweeps && a->rng == SB_RNG_TAPE && (!a->d_spawn_u || !a->d_spawn_c)) return SB_EINVAL;
-  if (a->rng != SB_RNG_TAPE && a->rng != SB_RNG_PHILOX) return SB_EINVAL;
+  if (a->rng != SB_RNG_TAPE && a->rng != SB_RNG_PHILOX && a->rng != SB_RNG_SPARSE) return SB_EINVAL;
+  if (a->rng == SB_RNG_SPARSE && !d.sparse_ok) return SB_EINVAL;
   if (a->policy != SB_POLICY_TAPE && a->policy != SB_POLICY_UNIFORM) return SB_EINVAL;
   if (buf) {
     rc = check_buf(buf);

@@ -46,6 +46,8 @@ struct SbDev {
   double p;
   float value[SB_MAX_KINDS];
   uint8_t channel[SB_MAX_KINDS];  // fast path: one-hot channel of the kind, 255 = all-zero row
+  int32_t sparse_ok;              // spawn_cdf is valid (SB_RNG_SPARSE available)
+  uint64_t cdf[SB_SPARSE_KMAX];   // Binomial(env_stride, p) CDF in 0.64 fixed point
   const double* app;              // device [K][C]
   const uint8_t* tmpl;            // device [L][plane_stride]
 };
@@ -162,6 +164,13 @@ SB_HD int sb_resolve_candidate(const SbDev& d, uint32_t env, uint32_t tick, uint
   const uint32_t r8 = sb_byte_of(r, (int)(cell & 15u));
   if (r8 > d.hi8) return -1;  // the filter bound is a power of two >= hi8 + 1
   return sb_resolve_spawn(d, env, tick, cell, r8 == d.hi8, rk);
+}
+
+// Sparse sampling of the spawn field (SB_RNG_SPARSE).  K = number of table entries <= u.
+SB_HD int sb_sparse_count(const SbDev& d, uint64_t u) {
+  int k = 0;
+  while (k < SB_SPARSE_KMAX && u >= d.cdf[k]) ++k;
+  return k;
 }
 
 // Byte-SIMD first-level FILTER for 4 cells (one 32-bit word of kinds / random bytes): returns 0x80 in

@@ -43,7 +43,7 @@ __host__ __device__ inline int pad64mod128(int b) {
 // single stored plane is observed (entries are 0 or 1: the float is the bf16 shifted left by 16) and
 // f32 otherwise (entries are sums over planes).
 struct SmemLayout {
-  int q_off, planes_off, pos_off, stage_off, plane_env, stage_env, total;
+  int q_off, planes_off, pos_off, stage_off, hits_off, plane_env, stage_env, total;
 };
 
 __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, bool np1) {
@@ -55,7 +55,8 @@ __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, boo
   L.pos_off = L.planes_off + epb * L.plane_env;
   L.stage_off = L.pos_off + round_up(epb * 8 * d.A, 16);
   L.stage_env = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
-  L.total = L.stage_off + epb * L.stage_env;
+  L.hits_off = L.stage_off + epb * L.stage_env;  // SB_RNG_SPARSE: accepted cells of the turn, u16[KMAX]
+  L.total = L.hits_off + epb * SB_SPARSE_KMAX * 2;
   return L;
 }
 
@@ -385,6 +386,37 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         }
         __syncwarp();
         if (wlane == 0) *qn = 0;
+      } else if (RNG == SB_K_SPARSE) {
+        // Sparse sampling of the same Bernoulli field: K ~ Binomial(cells, p) by inverse CDF, then K
+        // distinct uniform cells (sequential rejection over the draw stream j = 1, 2, ...).  The lanes of
+        // the group draw LPE stream entries at a time; lane 0 accepts them in stream order.
+        uint16_t* hits = reinterpret_cast<uint16_t*>(smem_raw + p.hits_off) + grp * SB_SPARSE_KMAX;
+        const SbU4 r0 = sb_philox_rk(envid, tick, 0u, SB_DOM_SPARSE, rk);
+        const int K = sb_sparse_count(d, ((uint64_t)r0.x << 32) | r0.y);
+        int accepted = 0;
+        uint32_t base = 1;
+        while (__any_sync(0xFFFFFFFFu, accepted < K)) {
+          const SbU4 r = sb_philox_rk(envid, tick, base + (uint32_t)lane, SB_DOM_SPARSE, rk);
+          const uint32_t pos = (uint32_t)sb_mulhi64(((uint64_t)r.x << 32) | r.y, (uint64_t)d.env_stride);
+          const uint32_t ci = sb_bounded(r.z, r.w, (uint32_t)d.n_choices);
+#pragma unroll
+          for (int l = 0; l < LPE; ++l) {
+            const uint32_t pl = __shfl_sync(0xFFFFFFFFu, pos, l, LPE);
+            const uint32_t cl = __shfl_sync(0xFFFFFFFFu, ci, l, LPE);
+            if (lane == 0 && accepted < K) {
+              bool dup = false;
+              for (int h = 0; h < accepted; ++h) dup |= hits[h] == (uint16_t)pl;
+              if (!dup) {
+                hits[accepted++] = (uint16_t)pl;
+                const uint32_t kind = genv[pl];
+                if (kind < (uint32_t)SB_MAX_KINDS && ((d.spawn_mask >> kind) & 1u))
+                  genv[pl] = (uint8_t)((d.choices_packed >> (8 * cl)) & 0xFFu);
+              }
+            }
+          }
+          accepted = __shfl_sync(0xFFFFFFFFu, accepted, 0, LPE);
+          base += LPE;
+        }
       } else {  // SB_K_PHILOX_GENERIC: several spawning kinds or a large probability
         for (int c = lane; c < d.n_chunks; c += LPE) {
           SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
@@ -498,7 +530,7 @@ static int launch_one(const SbDev& d, StepParams p, cudaStream_t s) {
   const SmemLayout L = smem_layout(d, SB_THREADS, LPE, NP1);
   sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
   p.q_off = L.q_off, p.planes_off = L.planes_off, p.pos_off = L.pos_off, p.stage_off = L.stage_off;
-  p.plane_env = L.plane_env, p.stage_env = L.stage_env;
+  p.plane_env = L.plane_env, p.stage_env = L.stage_env, p.hits_off = L.hits_off;
   const int smem = L.total;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
   auto kern = step_kernel<LPE, RNG, NP1>;
@@ -521,6 +553,8 @@ static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t 
     case SB_K_TAPE: return launch_one<LPE, SB_K_TAPE, false>(d, p, s);  // replay: speed is irrelevant
     case SB_K_PHILOX_SIMD:
       return np1 ? launch_one<LPE, SB_K_PHILOX_SIMD, true>(d, p, s) : launch_one<LPE, SB_K_PHILOX_SIMD, false>(d, p, s);
+    case SB_K_SPARSE:
+      return np1 ? launch_one<LPE, SB_K_SPARSE, true>(d, p, s) : launch_one<LPE, SB_K_SPARSE, false>(d, p, s);
     default: return launch_one<LPE, SB_K_PHILOX_GENERIC, false>(d, p, s);
   }
 }
@@ -544,6 +578,7 @@ int pick_lpe(const SbDev& d) {
 int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s) {
   int kr;
   if (p.a.rng == SB_RNG_TAPE) kr = SB_K_TAPE;
+  else if (p.a.rng == SB_RNG_SPARSE) kr = SB_K_SPARSE;
   else kr = d.simd_sweep ? SB_K_PHILOX_SIMD : SB_K_PHILOX_GENERIC;
   switch (pick_lpe(d)) {
     case 4: return launch_rng<4>(d, p, kr, s);

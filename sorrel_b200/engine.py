@@ -74,6 +74,39 @@ class WorldSpec:
         return sorted(dyn)
 
 
+def spawn_threshold_53(p: float) -> int:
+    """ceil(p * 2^53): numpy's `random_sample() < p` is `k < this` for the 53-bit integer k."""
+    import math
+
+    if not p > 0.0:
+        return 0
+    if p >= 1.0:
+        return 1 << 53
+    return int(math.ceil(math.ldexp(p, 53)))
+
+
+def binomial_cdf_u64(n_cells: int, p: float, kmax: int = _abi.SB_SPARSE_KMAX) -> list[int] | None:
+    """SbWorldDesc.spawn_cdf: floor(2^64 * P(X <= k)), X ~ Binomial(n_cells, P/2^53), exact rational
+    arithmetic.  None when the table cannot hold (almost) all of the mass (dense spawning) -- then
+    only the per-cell mode SB_RNG_PHILOX is available."""
+    from fractions import Fraction
+
+    P = spawn_threshold_53(p)
+    if P == 0 or P >= 1 << 53:
+        return None
+    q = Fraction(P, 1 << 53)
+    if n_cells * q > 16:
+        return None
+    out, acc, term = [], Fraction(0), (1 - q) ** n_cells
+    for k in range(kmax):
+        acc += term
+        out.append(min((acc.numerator << 64) // acc.denominator, (1 << 64) - 1))
+        term = term * (n_cells - k) / (k + 1) * q / (1 - q)
+    if (1 << 64) - out[-1] > 1 << 8:  # tail beyond kmax must be negligible (< 2^-56)
+        return None
+    return out
+
+
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -145,6 +178,12 @@ class Engine:
         d.h_appearance = self.h_appearance.ctypes.data
         d.d_template = self.d_template.data_ptr()
         d.static_layers_invisible = 1 if invisible else 0
+        cdf = binomial_cdf_u64(self.env_stride, spec.spawn_prob) if self.env_stride < 65536 else None
+        self.sparse_available = cdf is not None
+        if cdf is not None:
+            d.spawn_cdf_len = len(cdf)
+            for i, v in enumerate(cdf):
+                d.spawn_cdf[i] = v
         self.desc = d
         check(self.lib.sb_validate(C.byref(d)), "world description")
 
@@ -167,11 +206,13 @@ class Engine:
     def step(self, num_turns: int = 1, *, buffer=None, actions: torch.Tensor | None = None,
              spawn_u: torch.Tensor | None = None, spawn_c: torch.Tensor | None = None,
              obs_out: torch.Tensor | None = None, reward_out: torch.Tensor | None = None,
-             action_out: torch.Tensor | None = None, drew_out: torch.Tensor | None = None) -> None:
+             action_out: torch.Tensor | None = None, drew_out: torch.Tensor | None = None,
+             rng: str = "philox") -> None:
         """`num_turns` fused Environment.take_turn()s (environment.py:81-93) for every instance.
 
         actions given -> replayed / host policy; None -> in-kernel uniform policy (RandomModel).
-        spawn_u/spawn_c given -> replayed numpy draws; None -> Philox.
+        spawn_u/spawn_c given -> replayed numpy draws; None -> Philox: rng="philox" draws one byte
+        per cell (dense), rng="sparse" samples the same Bernoulli field sparsely (SB_RNG_SPARSE).
         With a `buffer` (buffers.Buffer) every agent-turn is recorded into its ring."""
         T = int(num_turns)
         a = SbStepArgs()
@@ -179,7 +220,8 @@ class Engine:
         a.num_turns = T
         a.tick0 = self.tick + 1
         a.seed = self.seed
-        a.rng = _abi.SB_RNG_TAPE if spawn_u is not None else _abi.SB_RNG_PHILOX
+        a.rng = _abi.SB_RNG_TAPE if spawn_u is not None else \
+            (_abi.SB_RNG_SPARSE if rng == "sparse" else _abi.SB_RNG_PHILOX)
         a.policy = _abi.SB_POLICY_TAPE if actions is not None else _abi.SB_POLICY_UNIFORM
         a.act_agent = a.obs_agent = -1
         self._fill_ptrs(a, T, actions, spawn_u, spawn_c, obs_out, reward_out, action_out, drew_out)
@@ -195,7 +237,7 @@ class Engine:
 
     def phase(self, *, sweep: bool = False, act_agent: int = -1, obs_agent: int = -1, buffer=None,
               actions: torch.Tensor | None = None, spawn_u=None, spawn_c=None, obs_out=None, reward_out=None,
-              new_turn: bool = False) -> None:
+              new_turn: bool = False, rng: str = "philox") -> None:
         """One split-phase launch: [sweep] -> [act agent k] -> [observe agent j] (SB_MODE_SPLIT).
 
         Lets a live policy run between `pov()` and `act()` of each agent exactly like
@@ -207,7 +249,8 @@ class Engine:
         a.num_turns = 1
         a.tick0 = self.tick
         a.seed = self.seed
-        a.rng = _abi.SB_RNG_TAPE if spawn_u is not None else _abi.SB_RNG_PHILOX
+        a.rng = _abi.SB_RNG_TAPE if spawn_u is not None else \
+            (_abi.SB_RNG_SPARSE if rng == "sparse" else _abi.SB_RNG_PHILOX)
         a.policy = _abi.SB_POLICY_TAPE if actions is not None else _abi.SB_POLICY_UNIFORM
         a.do_sweep = 1 if sweep else 0
         a.act_agent, a.obs_agent = act_agent, obs_agent

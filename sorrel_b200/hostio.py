@@ -12,8 +12,8 @@ import torch
 
 
 class HostStepPipeline:
-    def __init__(self, engine, buffer, turns: int, depth: int = 2):
-        self.eng, self.buf, self.T, self.depth = engine, buffer, int(turns), depth
+    def __init__(self, engine, buffer, turns: int, depth: int = 2, rng: str = "philox"):
+        self.eng, self.buf, self.T, self.depth, self.rng = engine, buffer, int(turns), depth, rng
         dev, N, A = engine.device, engine.N, engine.A
         shape = (self.T, N, A)
         self.d_actions = [torch.empty(shape, dtype=torch.int32, device=dev) for _ in range(depth)]
@@ -39,7 +39,7 @@ class HostStepPipeline:
             self.ev_h2d[k].record(self.s_h2d)
         cur.wait_event(self.ev_h2d[k])
         cur.wait_event(self.ev_d2h[k])  # previous read-back of d_rewards[k] is done
-        self.eng.step(self.T, buffer=self.buf, actions=self.d_actions[k], reward_out=self.d_rewards[k])
+        self.eng.step(self.T, buffer=self.buf, actions=self.d_actions[k], reward_out=self.d_rewards[k], rng=self.rng)
         self.ev_compute[k].record(cur)
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(self.ev_compute[k])

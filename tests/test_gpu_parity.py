@@ -236,6 +236,53 @@ def test_philox_mode(A, H, W, v, p, T, N, lpe, cuda_device, monkeypatch):
     _compare_buffers(buf, envs, A)
 
 
+@pytest.mark.parametrize("A,H,W,v,p,T,N,lpe", [
+    (1, 21, 21, 2, 0.005, 60, 70, None), (8, 21, 21, 2, 0.005, 25, 37, None), (2, 11, 14, 3, 0.03, 30, 19, None),
+    (1, 21, 21, 2, 0.005, 30, 20, 8), (1, 21, 21, 2, 0.02, 30, 12, 32), (3, 40, 40, 4, 0.002, 10, 6, None)])
+def test_sparse_mode(A, H, W, v, p, T, N, lpe, cuda_device, monkeypatch):
+    """SB_RNG_SPARSE (Binomial count + distinct uniform cells): kernels == oracle with the same stream."""
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
+    seed, base = 0xFEEDC0DE77, 9
+    spec = R.treasurehunt_spec(H, W, A, v, p)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    assert eng.sparse_available
+    buf = _buffer(spec, N, T, cuda_device)
+    eng.reset()
+    eng.step(T // 2, buffer=buf, rng="sparse")
+    eng.step(T - T // 2, buffer=buf, rng="sparse")
+    eng.check_errors()
+    envs = []
+    for n in range(N):
+        env, _ = util.run_oracle_episode(spec, R.SparseDraws(seed), T, env_id=base + n)
+        envs.append(env)
+    np.testing.assert_array_equal(eng.grid_numpy(), np.stack([e.grid for e in envs]))
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), np.array([e.total_reward for e in envs]))
+    _compare_buffers(buf, envs, A)
+
+
+def test_sparse_and_dense_modes_have_the_same_statistics(cuda_device):
+    """Both counter-based modes sample iid Bernoulli(p) per empty cell + uniform kind choice: compare
+    spawn counts per kind over 2^16 instances x 1 turn from identical start states."""
+    spec = R.treasurehunt_spec(21, 21, 1, 2, 0.005)
+    N = 1 << 16
+    counts = {}
+    for mode in ("philox", "sparse"):
+        eng = _engine(spec, N, cuda_device, seed=2025)
+        eng.reset()
+        eng.step(1, rng=mode)
+        g = eng.grid[:, 0, : 441]
+        counts[mode] = np.array([int((g == k).sum()) for k in (2, 3, 4)], dtype=np.float64)
+    expect = N * 360 * spec.spawn_prob / 3  # 361 interior cells minus the agent, three kinds
+    for mode, c in counts.items():
+        assert np.all(np.abs(c - expect) < 5 * np.sqrt(expect)), (mode, c, expect)
+    with pytest.raises(ValueError):  # dense spawning has no sparse table
+        e2 = _engine(R.treasurehunt_spec(9, 9, 1, 2, 0.4), 4, cuda_device)
+        assert not e2.sparse_available
+        e2.reset()
+        e2.step(1, rng="sparse")
+
+
 def test_shard_invariance(cuda_device):
     """N instances on one engine == the concatenation of two shards (rank offset env_id_base)."""
     spec = R.treasurehunt_spec(21, 21, 2, 2, 0.01)

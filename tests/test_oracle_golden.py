@@ -118,3 +118,26 @@ def test_spawn_threshold_is_exact():
     for p in (0.005, 0.05, 0.5, 1 / 3, 1e-9, 0.999999):
         thr = R.spawn_threshold(p)
         assert (thr - 1) / 2**53 < p <= thr / 2**53 or thr / 2**53 == p
+
+
+def test_sparse_sampler_matches_dense_law():
+    """SparseDraws and PhiloxDraws sample the same law: spawn counts per turn ~ Binomial(#empty, p)."""
+    spec = R.treasurehunt_spec(21, 21, 1, 2, 0.005)
+    n_env = 150  # the dense Python sampler evaluates Philox per cell: keep it small (the GPU test uses 2^16)
+    tot = {"dense": 0, "sparse": 0}
+    for name, cls in (("dense", R.PhiloxDraws), ("sparse", R.SparseDraws)):
+        for e in range(n_env):
+            env = R.OracleEnv(spec, cls(99), env_id=e)
+            env.reset()
+            before = int(((env.grid[:, :, 1] >= 2) & (env.grid[:, :, 1] <= 4)).sum())
+            env.take_turn()
+            tot[name] += int(((env.grid[:, :, 1] >= 2) & (env.grid[:, :, 1] <= 4)).sum()) - before
+    expect = n_env * 360 * 0.005
+    for v in tot.values():
+        assert abs(v - expect) < 4 * expect ** 0.5 + 1, tot
+    cdf = R.binomial_cdf_u64(448, 0.005)
+    assert cdf == sorted(cdf) and cdf[-1] == (1 << 64) - 1
+    # P(K = 0) = (1 - q)^448 exactly
+    from fractions import Fraction
+    q = Fraction(R.spawn_threshold(0.005), 1 << 53)
+    assert cdf[0] == int((1 - q) ** 448 * (1 << 64))
