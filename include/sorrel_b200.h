@@ -55,6 +55,10 @@ typedef enum SbStatus {
 #define SB_ERR_BAD_ACTION 4u /* action outside [0, num_actions) */
 #define SB_ERR_BAD_KIND 8u   /* grid byte >= num_kinds */
 
+/* observation transforms */
+#define SB_OBS_SUM 0 /* OneHotObservationSpec / raw table sums (observation_spec.py:175-205) */
+#define SB_OBS_RGB 1 /* RGBObservationSpec: clip(sum, 0, 255) / 255 in f64 (observation_spec.py:386-483) */
+
 /* transition rules (per kind) */
 #define SB_RULE_NONE 0
 #define SB_RULE_SPAWN 1 /* Bernoulli(spawn_prob) -> uniform choice among spawn_choice_kinds;
@@ -126,6 +130,8 @@ typedef struct SbWorldDesc {
      P = ceil(spawn_prob * 2^53), saturated at 2^64-1; computed exactly (rational arithmetic) by the
      caller, see sorrel_b200/engine.py: binomial_cdf_u64.  K = #{k : u64 >= spawn_cdf[k]}. */
   uint64_t spawn_cdf[SB_SPARSE_KMAX];
+  int32_t obs_transform; /* SB_OBS_*: applied to the per-cell sum over layers before the f32 store */
+  int32_t reserved1;
 } SbWorldDesc;
 
 /*

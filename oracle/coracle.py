@@ -23,7 +23,7 @@ class OrWorld(C.Structure):
         ("default_kind", C.c_int32),
         ("n_actions", C.c_int32), ("dy", C.c_int32 * 8), ("dx", C.c_int32 * 8),
         ("n_choices", C.c_int32), ("choices", C.c_int32 * 8),
-        ("n_spawnable", C.c_int32),
+        ("n_spawnable", C.c_int32), ("obs_transform", C.c_int32),
         ("p", C.c_double),
         ("value", C.c_float * 32), ("passable", C.c_uint8 * 32), ("rule", C.c_uint8 * 32),
         ("appearance", C.c_void_p), ("tmpl", C.c_void_p), ("spawnable", C.c_void_p),
@@ -92,6 +92,7 @@ class COracle:
         for i, k in enumerate(spec.spawn_choices):
             w.choices[i] = k
         w.p = spec.spawn_prob
+        w.obs_transform = int(getattr(spec, "obs_transform", 0))
         for k in range(w.K):
             w.value[k] = float(spec.kind_value[k])
             w.passable[k] = 1 if spec.kind_passable[k] else 0

@@ -42,10 +42,10 @@ def grid_ids(world) -> np.ndarray:
     return g
 
 
-def build(H, W, A, v, p, T):
+def build(H, W, A, v, p, T, obs="onehot"):
     config = {
         "experiment": {"epochs": 1, "max_turns": T, "record_period": 50},
-        "model": {"agent_vision_radius": v, "epsilon_decay": 0.0005, "observation_spec": "onehot",
+        "model": {"agent_vision_radius": v, "epsilon_decay": 0.0005, "observation_spec": obs,
                   "num_agents": A},
         "world": {"height": H, "width": W, "gem_value": 10, "food_value": 5, "bone_value": -10,
                   "spawn_prob": p},
@@ -56,8 +56,8 @@ def build(H, W, A, v, p, T):
 
 
 def run_case(name, seed, H, W, A, v, p, T, epochs=1, capacity=None, n_frames=1, sample_batch=0,
-             per_turn_grids=True):
-    world, env = build(H, W, A, v, p, T)
+             per_turn_grids=True, obs="onehot"):
+    world, env = build(H, W, A, v, p, T, obs)
     cap = capacity or T * epochs
     for ag in env.agents:
         m = RandomModel(ag.observation_spec.input_size, 4, cap)
@@ -118,6 +118,7 @@ def run_case(name, seed, H, W, A, v, p, T, epochs=1, capacity=None, n_frames=1, 
         n_draws=np.array(n_draws, dtype=np.int64),
         n_uniform=np.int64(sum(1 for c in log.calls if c[0] == "random")),
         n_spawn=np.int64(sum(1 for c in log.calls if c[0] == "choice_obj")),
+        obs_spec=obs,
         buf_sha=h.hexdigest()[:16],
         grid_sha=hashlib.sha256(grids[-1][:, :, 1].tobytes()).hexdigest()[:16],
         **samples,
@@ -131,7 +132,7 @@ def run_case(name, seed, H, W, A, v, p, T, epochs=1, capacity=None, n_frames=1, 
           f"draws={len(log)} -> {os.path.getsize(path)} B")
 
 
-def observe_cases():
+def observe_cases(rgb_only=False):
     """Direct OneHotObservationSpec.observe probes on random multi-layer worlds."""
     from sorrel.entities import Entity
     from sorrel.observation.observation_spec import OneHotObservationSpec
@@ -146,7 +147,7 @@ def observe_cases():
 
     rng = np.random.RandomState(1234)
     cases = []
-    for _ in range(60):
+    for _ in range(0 if rgb_only else 60):
         H, W, L = rng.randint(5, 12), rng.randint(5, 12), rng.randint(1, 4)
         v = rng.randint(1, min((H - 1) // 2, (W - 1) // 2) + 1)
         world = Gridworld(H, W, L, mk("EmptyEntity"))
@@ -158,6 +159,33 @@ def observe_cases():
             y, x = rng.randint(0, H), rng.randint(0, W)
             obs = spec.observe(world, (y, x, 0))
             cases.append((kinds, int(v), int(y), int(x), obs))
+    # RGBObservationSpec on the same kind of worlds (clip(sum, 0, 255) / 255, observation_spec.py:483)
+    from sorrel.observation.observation_spec import RGBObservationSpec
+
+    rgb_cases = []
+    rng = np.random.RandomState(4321)  # own stream: independent of the one-hot probes above
+    for _ in range(30):
+        H, W, L = rng.randint(5, 12), rng.randint(5, 12), rng.randint(1, 4)
+        v = rng.randint(1, min((H - 1) // 2, (W - 1) // 2) + 1)
+        world = Gridworld(H, W, L, mk("EmptyEntity"))
+        kinds = rng.randint(0, 4, size=(H, W, L)).astype(np.uint8)
+        for idx in np.ndindex(H, W, L):
+            world.add(idx, mk(names[kinds[idx]]))
+        spec = RGBObservationSpec(names, full_view=False, vision_radius=int(v))
+        table = np.stack([spec.entity_map[n] for n in names]).astype(np.float64)
+        for _ in range(4):
+            y, x = rng.randint(0, H), rng.randint(0, W)
+            rgb_cases.append((kinds, int(v), int(y), int(x), spec.observe(world, (y, x, 0)), table))
+    np.savez_compressed(
+        os.path.join(OUT, "observe_rgb_cases.npz"), n=len(rgb_cases),
+        **{f"kinds_{i}": c[0] for i, c in enumerate(rgb_cases)},
+        **{f"meta_{i}": np.array(c[1:4]) for i, c in enumerate(rgb_cases)},
+        **{f"obs_{i}": c[4] for i, c in enumerate(rgb_cases)},
+        **{f"table_{i}": c[5] for i, c in enumerate(rgb_cases)},
+    )
+    print(f"observe_rgb_cases: {len(rgb_cases)} cases")
+    if rgb_only:
+        return
     np.savez_compressed(
         os.path.join(OUT, "observe_cases.npz"),
         n=len(cases),
@@ -169,6 +197,10 @@ def observe_cases():
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "rgb":  # only the fixtures added after the first generation
+        run_case("rgb_s13_a2_11", 13, 11, 11, 2, 2, 0.05, 40, obs="rgb")
+        observe_cases(rgb_only=True)
+        return
     run_case("kat1_s0_a1_21", 0, 21, 21, 1, 2, 0.005, 100)
     run_case("kat2_s0_a8_21", 0, 21, 21, 8, 2, 0.005, 100)
     run_case("kat3_s7_a2_11", 7, 11, 11, 2, 2, 0.05, 50)
@@ -184,6 +216,8 @@ def main():
     run_case("ring_s12_a1_21", 12, 21, 21, 1, 2, 0.005, 100, epochs=2, capacity=256, n_frames=5,
              sample_batch=64)
     run_case("large_s4_a64_128", 4, 128, 128, 64, 4, 0.005, 2, per_turn_grids=False)
+    # the example's DEFAULT observation spec (examples/treasurehunt/main.py:24)
+    run_case("rgb_s13_a2_11", 13, 11, 11, 2, 2, 0.05, 40, obs="rgb")
     observe_cases()
 
 

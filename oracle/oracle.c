@@ -158,6 +158,7 @@ typedef struct {
   int32_t n_actions, dy[8], dx[8];
   int32_t n_choices, choices[8];
   int32_t n_spawnable;
+  int32_t obs_transform; /* 0 none, 1 RGB: clip(sum, 0, 255) / 255 (observation_spec.py:483) */
   double p;
   float value[OR_MAX_KINDS];
   uint8_t passable[OR_MAX_KINDS], rule[OR_MAX_KINDS];
@@ -296,10 +297,15 @@ static void observe(const or_world_t* w, const uint8_t* g, int y, int x, float* 
         for (int c = 0; c < C; ++c) {
           double s = 0.0;
           for (int z = 0; z < w->L; ++z) s += w->appearance[cell[z] * C + c];
+          if (w->obs_transform == 1) s = (s < 0.0 ? 0.0 : (s > 255.0 ? 255.0 : s)) / 255.0;
           out[(c * S + i) * S + j] = (float)s;
         }
       } else {
-        for (int c = 0; c < C; ++c) out[(c * S + i) * S + j] = (float)w->appearance[w->fill_kind * C + c];
+        for (int c = 0; c < C; ++c) {
+          double s = w->appearance[w->fill_kind * C + c];
+          if (w->obs_transform == 1) s = (s < 0.0 ? 0.0 : (s > 255.0 ? 255.0 : s)) / 255.0;
+          out[(c * S + i) * S + j] = (float)s;
+        }
       }
     }
 }

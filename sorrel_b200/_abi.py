@@ -24,6 +24,7 @@ SB_RNG_TAPE, SB_RNG_PHILOX, SB_RNG_SPARSE = 0, 1, 2
 SB_SPARSE_KMAX = 64
 SB_POLICY_TAPE, SB_POLICY_UNIFORM = 0, 1
 SB_MODE_FUSED, SB_MODE_SPLIT = 0, 1
+SB_OBS_SUM, SB_OBS_RGB = 0, 1
 
 LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                          "libsorrel_b200.so")
@@ -62,6 +63,8 @@ class SbWorldDesc(C.Structure):
         ("static_layers_invisible", C.c_int32),
         ("spawn_cdf_len", C.c_int32),
         ("spawn_cdf", C.c_uint64 * 64),
+        ("obs_transform", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 

@@ -47,6 +47,7 @@ struct SbDev {
   float value[SB_MAX_KINDS];
   uint8_t channel[SB_MAX_KINDS];  // fast path: one-hot channel of the kind, 255 = all-zero row
   int32_t sparse_ok;              // spawn_cdf is valid (SB_RNG_SPARSE available)
+  int32_t obs_transform;          // SB_OBS_*
   uint64_t cdf[SB_SPARSE_KMAX];   // Binomial(env_stride, p) CDF in 0.64 fixed point
   const double* app;              // device [K][C]
   const uint8_t* tmpl;            // device [L][plane_stride]
@@ -235,14 +236,18 @@ SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action
 SB_HD double sb_obs_general(const SbDev& d, const uint8_t* genv, const uint8_t* tmpl, const double* app,
                             int y, int x, int c, int i, int j) {
   int yy = y - d.v + i, xx = x - d.v + j;
-  if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) return app[d.fill_kind * d.C + c];
-  int cell = yy * d.W + xx;
   double s = 0.0;
-  for (int z = 0; z < d.L; ++z) {
-    int pl = d.plane_of_layer[z];
-    uint32_t kind = pl >= 0 ? genv[pl * d.plane_stride + cell] : tmpl[z * d.plane_stride + cell];
-    s += app[kind * d.C + c];
+  if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) {
+    s = app[d.fill_kind * d.C + c];
+  } else {
+    int cell = yy * d.W + xx;
+    for (int z = 0; z < d.L; ++z) {
+      int pl = d.plane_of_layer[z];
+      uint32_t kind = pl >= 0 ? genv[pl * d.plane_stride + cell] : tmpl[z * d.plane_stride + cell];
+      s += app[kind * d.C + c];
+    }
   }
+  if (d.obs_transform == SB_OBS_RGB) s = (s < 0.0 ? 0.0 : (s > 255.0 ? 255.0 : s)) / 255.0;  // np.clip(..)/255
   return s;
 }
 

@@ -50,6 +50,7 @@ class WorldSpec:
     action_deltas: list[tuple[int, int]] = field(
         default_factory=lambda: [MOVE_DELTAS[a] for a in ("up", "down", "left", "right")])
     dynamic_layers: list[int] | None = None  # default: every layer holding a non-static kind
+    obs_transform: int = 0  # _abi.SB_OBS_SUM (one-hot / raw sums) or _abi.SB_OBS_RGB
 
     @property
     def channels(self) -> int:
@@ -178,6 +179,7 @@ class Engine:
         d.h_appearance = self.h_appearance.ctypes.data
         d.d_template = self.d_template.data_ptr()
         d.static_layers_invisible = 1 if invisible else 0
+        d.obs_transform = int(spec.obs_transform)
         cdf = binomial_cdf_u64(self.env_stride, spec.spawn_prob) if self.env_stride < 65536 else None
         self.sparse_available = cdf is not None
         if cdf is not None:

@@ -6,7 +6,7 @@ from sorrel_b200.environment import Environment
 from sorrel_b200.examples.treasurehunt.agents import TreasurehuntAgent
 from sorrel_b200.examples.treasurehunt.entities import Sand, Wall
 from sorrel_b200.models import RandomModel
-from sorrel_b200.observation import OneHotObservationSpec
+from sorrel_b200.observation import OneHotObservationSpec, RGBObservationSpec
 
 
 class TreasurehuntEnv(Environment):
@@ -20,10 +20,14 @@ class TreasurehuntEnv(Environment):
         for _ in range(agent_num):
             entity_list = ["EmptyEntity", "Wall", "Gem", "Bone", "Food", "TreasurehuntAgent"]
             obs_spec_type = self.config.model.get("observation_spec", "onehot")
-            if obs_spec_type != "onehot":
-                raise ValueError(f"observation spec {obs_spec_type!r} is not implemented by the B200 engine")
-            observation_spec = OneHotObservationSpec(
-                entity_list, full_view=False, vision_radius=self.config.model.agent_vision_radius)
+            if obs_spec_type == "onehot":
+                observation_spec = OneHotObservationSpec(
+                    entity_list, full_view=False, vision_radius=self.config.model.agent_vision_radius)
+            elif obs_spec_type == "rgb":
+                observation_spec = RGBObservationSpec(
+                    entity_list, full_view=False, vision_radius=self.config.model.agent_vision_radius)
+            else:
+                raise ValueError(f"Unknown observation spec type: {obs_spec_type}")
             observation_spec.override_input_size((int(np.prod(observation_spec.input_size)),))
             action_spec = ActionSpec(["up", "down", "left", "right"])
             if self.model_factory is not None:

@@ -20,6 +20,8 @@ def one_hot_encode(value: int, num_classes: int) -> np.ndarray:
 
 
 class ObservationSpec:
+    #: transform the kernels apply to the per-cell sum over layers (_abi.SB_OBS_*)
+    obs_transform = 0
     entity_map: dict
     vision_radius: int
     full_view: bool
@@ -83,6 +85,43 @@ class OneHotObservationSpec(ObservationSpec):
         location None  -> float32 device tensor [N, A, C, S, S]: the view of every agent.
         location given -> (y, x[, z]) tuple or an int tensor [N, 2]: the view from that cell in
                           every instance, float32 [N, C, S, S]."""
+        if location is None:
+            return world.engine.observe()
+        return world.observe_from(location)
+
+
+class RGBObservationSpec(ObservationSpec):
+    """observation_spec.py:386-483: RGB appearance per kind (EmptyEntity black, the others spread over
+    the hue circle), layers summed in 0..255 space, `clip(sum, 0, 255) / 255` (kernel transform SB_OBS_RGB)."""
+
+    obs_transform = 1
+
+    def __init__(self, entity_list: list[str], full_view: bool, vision_radius: int | None = None,
+                 env_dims: Sequence[int] | None = None, fill_entity_kind: str = "Wall"):
+        super().__init__(entity_list, full_view, vision_radius, env_dims, fill_entity_kind)
+        if self.full_view:
+            raise NotImplementedError(
+                "full_view observations are not implemented by the B200 engine yet (egocentric crops only)")
+        self.input_size = (3, 2 * self.vision_radius + 1, 2 * self.vision_radius + 1)
+
+    def generate_map(self, entity_list: list[str]) -> dict[str, np.ndarray]:
+        """observation_spec.py:420-448"""
+        import colorsys
+
+        entity_map: dict[str, np.ndarray] = {}
+        num_colors = len([e for e in entity_list if e != "EmptyEntity"])
+        color_idx = 0
+        for x in entity_list:
+            if x == "EmptyEntity":
+                entity_map[x] = np.zeros(3, dtype=np.uint8)
+            else:
+                rgb = colorsys.hsv_to_rgb(color_idx / max(1, num_colors), 1.0, 1.0)
+                entity_map[x] = np.array([int(c * 255) for c in rgb], dtype=np.uint8)
+                color_idx += 1
+        return entity_map
+
+    def observe(self, world, location=None):
+        """observation_spec.py:450-483 for every instance (see OneHotObservationSpec.observe)."""
         if location is None:
             return world.engine.observe()
         return world.observe_from(location)

@@ -168,7 +168,7 @@ class Gridworld:
             vision=int(observation_spec.vision_radius), num_agents=int(num_agents),
             spawn_prob=float(rule.prob) if rule else 0.0,
             spawn_choices=[kid[c.kind_key()] for c in rule.choices] if rule else [],
-            action_deltas=deltas,
+            action_deltas=deltas, obs_transform=int(getattr(observation_spec, "obs_transform", 0)),
         )
         return spec
 

@@ -15,7 +15,7 @@ def golden_cases(max_cells: int = 64 * 64, with_large: bool = False):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name == "observe_cases":
+        if name.startswith("observe_"):
             continue
         if name.startswith("large") and not with_large:
             continue
@@ -28,7 +28,8 @@ def load_golden(name: str):
 
 
 def spec_from_golden(g) -> R.WorldSpec:
-    return R.treasurehunt_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), float(g["p"]))
+    obs = str(g["obs_spec"]) if "obs_spec" in g else "onehot"
+    return R.treasurehunt_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), float(g["p"]), obs=obs)
 
 
 def engine_spec(o: R.WorldSpec):
@@ -43,6 +44,7 @@ def engine_spec(o: R.WorldSpec):
         default_kind=o.default_kind, fill_kind=o.fill_kind, vision=o.vision, num_agents=o.num_agents,
         spawn_prob=o.spawn_prob, spawn_choices=list(o.spawn_choices),
         dynamic_layers=list(o.dynamic_layers) if o.dynamic_layers else None,
+        obs_transform=int(getattr(o, "obs_transform", 0)),
     )
 
 

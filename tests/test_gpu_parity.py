@@ -355,6 +355,28 @@ def test_observe_golden_cases(cuda_device):
         np.testing.assert_array_equal(obs.astype(np.float64), g[f"obs_{i}"], err_msg=f"case {i}")
 
 
+def test_observe_rgb_golden_cases(cuda_device):
+    """sb_observe with the RGB transform against RGBObservationSpec.observe outputs from the reference
+    (float32 of the reference's float64, i.e. what Buffer.states would hold)."""
+    from sorrel_b200.engine import Engine, WorldSpec
+
+    g = util.load_golden("observe_rgb_cases")
+    for i in range(int(g["n"])):
+        kinds = g[f"kinds_{i}"]
+        v, y, x = (int(t) for t in g[f"meta_{i}"])
+        H, W, L = kinds.shape
+        spec = WorldSpec(height=H, width=W, layers=L, kind_names=["EmptyEntity", "Wall", "Gem", "Bone"],
+                         kind_value=[0, 0, 0, 0], kind_passable=[True] * 4, kind_rule=[0] * 4,
+                         appearance=g[f"table_{i}"], template=kinds, spawnable=np.array([[0, 0]]), agent_kind=3,
+                         agent_layer=0, default_kind=0, fill_kind=1, vision=v, num_agents=1,
+                         dynamic_layers=list(range(L)), obs_transform=1)
+        eng = Engine(spec, 1, device=cuda_device)
+        eng.grid.copy_(eng.d_template[None])
+        eng.agent_pos[0, 0] = y * W + x
+        obs = eng.observe().cpu().numpy()[0, 0]
+        np.testing.assert_array_equal(obs, g[f"obs_{i}"].astype(np.float32), err_msg=f"case {i}")
+
+
 @pytest.mark.parametrize("general", [False, True])
 def test_observe_random(general, cuda_device):
     """Fast one-hot path and the general table path (non one-hot appearance: f64 sum over layers,

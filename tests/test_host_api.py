@@ -115,3 +115,24 @@ def test_error_mapping():
     assert _abi.error_bits_to_exception(0) is None
     with pytest.raises(ValueError):
         _abi.check(_abi.SB_EVISION)
+
+
+def test_rgb_observation_spec_matches_reference_map():
+    """RGBObservationSpec.generate_map (observation_spec.py:420-448): 4 kinds -> black, red, green, blue."""
+    from sorrel_b200.observation import RGBObservationSpec
+
+    s = RGBObservationSpec(["EmptyEntity", "Wall", "Gem", "Bone"], full_view=False, vision_radius=2)
+    assert s.input_size == (3, 5, 5) and s.obs_transform == 1
+    assert [s.entity_map[k].tolist() for k in ("EmptyEntity", "Wall", "Gem", "Bone")] == \
+           [[0, 0, 0], [255, 0, 0], [0, 255, 0], [0, 0, 255]]
+    g = util.load_golden("observe_rgb_cases")
+    np.testing.assert_array_equal(np.stack([s.appearance_row(k) for k in ("EmptyEntity", "Wall", "Gem", "Bone")]),
+                                  g["table_0"])
+    # the example's kind table with the RGB spec == the oracle's
+    world, agent, _, aspec, spawn = _th_world(11, 11, 2, 2, 0.05)
+    rgb = RGBObservationSpec(["EmptyEntity", "Wall", "Gem", "Bone", "Food", "TreasurehuntAgent"], full_view=False,
+                             vision_radius=2)
+    got = world.build_spec(agent, rgb, aspec, 2, spawn)
+    ref = R.treasurehunt_spec(11, 11, 2, 2, 0.05, obs="rgb")
+    np.testing.assert_array_equal(got.appearance, ref.appearance)
+    assert got.obs_transform == 1

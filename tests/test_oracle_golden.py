@@ -141,3 +141,16 @@ def test_sparse_sampler_matches_dense_law():
     from fractions import Fraction
     q = Fraction(R.spawn_threshold(0.005), 1 << 53)
     assert cdf[0] == int((1 - q) ** 448 * (1 << 64))
+
+
+def test_rgb_observe_against_reference_outputs():
+    """RGBObservationSpec.observe outputs captured from the reference (sum over layers, clip, /255)."""
+    g = util.load_golden("observe_rgb_cases")
+    for i in range(int(g["n"])):
+        kinds = g[f"kinds_{i}"]
+        v, y, x = (int(t) for t in g[f"meta_{i}"])
+        H, W, L = kinds.shape
+        spec = R.WorldSpec(H, W, L, ["E", "W", "G", "B"], [0] * 4, [True] * 4, [0] * 4, g[f"table_{i}"], kinds,
+                           np.zeros((0, 3)), 3, 0, 0, 1, v, 0, 0.0, [], obs_transform=1)
+        o = R.observe(spec, kinds, y, x)
+        np.testing.assert_array_equal(o, g[f"obs_{i}"])
