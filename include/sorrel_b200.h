@@ -240,6 +240,15 @@ int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64
                      int32_t batch, float* d_states, int64_t* d_actions, float* d_rewards,
                      float* d_next_states, float* d_dones, double* d_valid, void* stream);
 
+/* -- TransformerBuffer.sample_transformer gather (buffers.py:319-355) ----------------------------- *
+ * like sb_buffer_sample, but the actions keep the time axis: d_action_seq int64 [B][F] =
+ * actions[start .. start+F), d_next_action_seq float [B][F] = actions[start+1 .. start+F+1] cast to f32.
+ */
+int sb_buffer_sample_transformer(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts,
+                                 int32_t batch, float* d_states, int64_t* d_action_seq,
+                                 float* d_next_action_seq, float* d_next_states, float* d_dones,
+                                 double* d_valid, void* stream);
+
 /* -- Buffer.current_state (buffers.py:143-154): rows [idx-(F-1), idx) with ring wrap --------- *
  * d_out float [rows][F-1][obs_size]
  */

@@ -132,6 +132,38 @@ def run_case(name, seed, H, W, A, v, p, T, epochs=1, capacity=None, n_frames=1, 
           f"draws={len(log)} -> {os.path.getsize(path)} B")
 
 
+def transformer_case():
+    """TransformerBuffer.combine + sample_transformer (buffers.py:273-355) on a 2-agent episode."""
+    from sorrel.buffers import TransformerBuffer
+
+    T, cap, F = 40, 64, 4
+    world, env = build(11, 11, 2, 2, 0.05, T)
+    for ag in env.agents:
+        m = RandomModel(ag.observation_spec.input_size, 4, cap)
+        m.memory = TransformerBuffer(capacity=cap, obs_shape=tuple(ag.observation_spec.input_size), n_frames=F)
+        m.memory.extra_data["positions"] = np.zeros((cap, 2), dtype=np.int64)
+        ag.model = m
+    log = DrawLog()
+    with record(log):
+        set_seed(21)
+        env.reset()
+        for _ in range(T):
+            env.take_turn()
+        comb = TransformerBuffer.combine([ag.model.memory for ag in env.agents])
+        out = comb.sample_transformer(24)
+        idx = [c[2] for c in log.calls if c[0] == "choice" and c[1][1] == 24][-1]
+    mems = [ag.model.memory for ag in env.agents]
+    np.savez_compressed(
+        os.path.join(OUT, "transformer_s21_a2_11.npz"), seed=21, H=11, W=11, A=2, v=2, p=0.05, T=T, capacity=cap,
+        n_frames=F, states=np.stack([b.states for b in mems]), actions=np.stack([b.actions for b in mems]),
+        comb_states=comb.states, comb_actions=comb.actions, comb_rewards=comb.rewards, comb_dones=comb.dones,
+        comb_positions=comb.extra_data["positions"], comb_agent_ids=comb.extra_data["agent_ids"],
+        comb_idx=comb.idx, comb_size=comb.size, sample_idx=np.asarray(idx, dtype=np.int64),
+        t_states=out[0], t_actions=out[1], t_next_actions=out[2], t_next_states=out[3], t_dones=out[4],
+        t_valid=out[5], t_agent_ids=out[6])
+    print("transformer_s21_a2_11: sampled", out[0].shape, out[1].dtype, out[2].dtype, out[6][:6])
+
+
 def observe_cases(rgb_only=False):
     """Direct OneHotObservationSpec.observe probes on random multi-layer worlds."""
     from sorrel.entities import Entity
@@ -197,6 +229,9 @@ def observe_cases(rgb_only=False):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "transformer":
+        transformer_case()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "rgb":  # only the fixtures added after the first generation
         run_case("rgb_s13_a2_11", 13, 11, 11, 2, 2, 0.05, 40, obs="rgb")
         observe_cases(rgb_only=True)
@@ -218,6 +253,7 @@ def main():
     run_case("large_s4_a64_128", 4, 128, 128, 64, 4, 0.005, 2, per_turn_grids=False)
     # the example's DEFAULT observation spec (examples/treasurehunt/main.py:24)
     run_case("rgb_s13_a2_11", 13, 11, 11, 2, 2, 0.05, 40, obs="rgb")
+    transformer_case()
     observe_cases()
 
 

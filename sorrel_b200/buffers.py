@@ -155,6 +155,48 @@ class Buffer:
         rows, starts = self.sample_indices(batch_size)
         return self.gather(rows, starts)
 
+    def gather_transformer(self, rows, starts):
+        """TransformerBuffer.sample_transformer's gather (buffers.py:332-355): like `gather` but the
+        actions keep their time axis.  Returns (states (B,F*obs) f32, actions (B,F) i64, next_actions
+        (B,F) f32, next_states (B,F*obs) f32, dones (B,1) f32, valid (B,1) f64, agent_ids (B,) i64 =
+        the ring row of every sample, the batched form of `combine`'s agent ids)."""
+        dev = self.device
+        rows = torch.as_tensor(rows, dtype=torch.int64, device=dev).contiguous()
+        starts = torch.as_tensor(starts, dtype=torch.int64, device=dev).contiguous()
+        B, F = int(rows.numel()), self.n_frames
+        states = torch.empty((B, F * self.obs_size), dtype=torch.float32, device=dev)
+        next_states = torch.empty((B, F * self.obs_size), dtype=torch.float32, device=dev)
+        actions = torch.empty((B, F), dtype=torch.int64, device=dev)
+        next_actions = torch.empty((B, F), dtype=torch.float32, device=dev)
+        dones = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        valid = torch.empty((B, 1), dtype=torch.float64, device=dev)
+        check(self.lib.sb_buffer_sample_transformer(C.byref(self.desc()), rows.data_ptr(), starts.data_ptr(), B,
+                                                    states.data_ptr(), actions.data_ptr(), next_actions.data_ptr(),
+                                                    next_states.data_ptr(), dones.data_ptr(), valid.data_ptr(),
+                                                    self._stream()), "sb_buffer_sample_transformer")
+        return states, actions, next_actions, next_states, dones, valid, rows
+
+    def sample_transformer(self, batch_size: int):
+        """TransformerBuffer.sample_transformer (buffers.py:319-355) over all rows."""
+        rows, starts = self.sample_indices(batch_size)
+        return self.gather_transformer(rows, starts)
+
+    def combined(self) -> dict[str, np.ndarray]:
+        """Host arrays equal to `TransformerBuffer.combine([one reference buffer per row])`
+        (buffers.py:273-317): the first `size` slots of every row back to back, `agent_ids` = row
+        (the reference allocates agent_ids but never fills them, so there they are all 0)."""
+        n = self.size
+        out = {
+            "states": self.states[:, :n].reshape(self.rows * n, *self.obs_shape).cpu().numpy(),
+            "actions": self.actions[:n].t().reshape(-1).cpu().numpy(),
+            "rewards": self.rewards[:n].t().reshape(-1).cpu().numpy(),
+            "dones": self.dones[:n].t().reshape(-1).cpu().numpy(),
+            "agent_ids": np.repeat(np.arange(self.rows, dtype=np.int64), n),
+        }
+        for k, v in self.extra_data.items():
+            out[k] = v[:n].transpose(0, 1).reshape(self.rows * n, *v.shape[2:]).cpu().numpy()
+        return out
+
     def clear(self) -> None:
         """buffers.py:126-133 (extra_data is left untouched, as in the reference)."""
         self._alloc()
@@ -198,11 +240,13 @@ class Buffer:
             out[k] = v[:, r].cpu().numpy()
         return out
 
-    def save(self, output_file: str | Path, row: int = 0) -> None:
-        """Buffer.save (buffers.py:168-178): same .npz keys, one row."""
+    def save(self, output_file: str | Path, row: int = 0, with_extra: bool = False) -> None:
+        """Buffer.save (buffers.py:168-178): same .npz keys, one row.  `with_extra=True` adds the
+        extra_data arrays like SavedGames.save / TransformerBuffer.save (buffers.py:225-243, 361-379)."""
         r = self.row(row)
+        extra = {k: r[k] for k in self.extra_data} if with_extra else {}
         np.savez_compressed(Path(output_file), states=r["states"], actions=r["actions"], rewards=r["rewards"],
-                            dones=r["dones"], n_frames=self.n_frames, idx=self.idx)
+                            dones=r["dones"], n_frames=self.n_frames, idx=self.idx, **extra)
 
     @classmethod
     def load(cls, input_file: str | Path, device: torch.device | str = "cuda") -> "Buffer":

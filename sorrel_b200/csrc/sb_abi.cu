@@ -230,7 +230,8 @@ __global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__
                                      const int64_t* __restrict__ starts, int batch, float* __restrict__ states,
                                      int64_t* __restrict__ actions, float* __restrict__ rewards,
                                      float* __restrict__ next_states, float* __restrict__ dones,
-                                     double* __restrict__ valid) {
+                                     double* __restrict__ valid, int64_t* __restrict__ action_seq,
+                                     float* __restrict__ next_action_seq) {
   // one warp per sample (Buffer.sample, buffers.py:112-124): the F stacked frames of a row are
   // contiguous in the ring, so states / next_states are two overlapping linear copies.
   const int sample = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -261,10 +262,14 @@ __global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__
       if (e >= (size_t)b.obs_size) dn[e - b.obs_size] = v;
     }
   }
+  if (action_seq && lane < F) {  // sample_transformer: actions[indices], actions[indices + 1] as f32
+    action_seq[(size_t)sample * F + lane] = b.d_actions[(size_t)(s0 + lane) * b.rows + row];
+    next_action_seq[(size_t)sample * F + lane] = (float)b.d_actions[(size_t)(s0 + lane + 1) * b.rows + row];
+  }
   if (lane == 0) {
     const size_t last = (size_t)(s0 + F - 1) * b.rows + row;  // indices[:, -1]
-    actions[sample] = b.d_actions[last];
-    rewards[sample] = b.d_rewards[last];
+    if (actions) actions[sample] = b.d_actions[last];
+    if (rewards) rewards[sample] = b.d_rewards[last];
     dones[sample] = b.d_dones[last];
     bool any = false;  // valid = 1 - any(dones[indices[:, :-1]]), buffers.py:120-122
     for (int f = 0; f < F - 1; ++f) any = any || (b.d_dones[(size_t)(s0 + f) * b.rows + row] != 0.0f);
@@ -485,7 +490,26 @@ int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64
     return SB_EINVAL;
   const long long threads = (long long)batch * 32;
   buffer_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *buf, d_rows, d_starts, batch, d_states, d_actions, d_rewards, d_next_states, d_dones, d_valid);
+      *buf, d_rows, d_starts, batch, d_states, d_actions, d_rewards, d_next_states, d_dones, d_valid, nullptr,
+      nullptr);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
+}
+
+int sb_buffer_sample_transformer(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts,
+                                 int32_t batch, float* d_states, int64_t* d_action_seq, float* d_next_action_seq,
+                                 float* d_next_states, float* d_dones, double* d_valid, void* stream) {
+  int rc = check_buf(buf);
+  if (rc) return rc;
+  if (batch <= 0 || !d_rows || !d_starts || !d_states || !d_action_seq || !d_next_action_seq || !d_next_states ||
+      !d_dones || !d_valid)
+    return SB_EINVAL;
+  if (buf->n_frames > 32) return SB_EUNSUPPORTED;
+  const long long threads = (long long)batch * 32;
+  buffer_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *buf, d_rows, d_starts, batch, d_states, nullptr, nullptr, d_next_states, d_dones, d_valid, d_action_seq,
+      d_next_action_seq);
   count_launch();
   if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
   return SB_OK;

@@ -31,6 +31,7 @@ struct StepParams {
   // sb_step.cu: launch_one.  Per-instance strides are padded to 64 (mod 128) bytes so the two groups
   // served by one quarter-warp of a 128-bit shared access hit disjoint banks.
   int32_t q_off, planes_off, pos_off, stage_off, hits_off;  // block-level byte offsets
+  int32_t staged;                                 // planes staged in shared memory (else used in place)
   int32_t plane_env, stage_env;                   // per-instance strides of planes / staging rows
   uint32_t rk[20];                                // Philox round keys of a.seed (constant-bank operands)
 };

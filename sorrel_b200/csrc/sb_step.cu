@@ -46,12 +46,19 @@ struct SmemLayout {
   int q_off, planes_off, pos_off, stage_off, hits_off, plane_env, stage_env, total;
 };
 
+// planes above this size stay in global memory (a 128x128 plane is 16 KB: staging it would leave room for
+// ~12 instances, i.e. 12 warps, per SM)
+__host__ inline bool stage_planes(const SbDev& d) {
+  if (const char* e = getenv("SB_STAGED")) return atoi(e) != 0;
+  return d.env_stride <= 4096;
+}
+
 __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, bool np1) {
   SmemLayout L;
   const int epb = threads / lpe;
   L.q_off = round_up(2 * d.SS, 16);
   L.planes_off = L.q_off + round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
-  L.plane_env = pad64mod128(d.env_stride);
+  L.plane_env = stage_planes(d) ? pad64mod128(d.env_stride) : 0;
   L.pos_off = L.planes_off + epb * L.plane_env;
   L.stage_off = L.pos_off + round_up(epb * 8 * d.A, 16);
   L.stage_env = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
@@ -251,9 +258,12 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + p.q_off);
   uint32_t* q = qbase + warp * (SB_QCAP + 1);  // spawn candidates of this warp's instances
   uint32_t* qn = q + SB_QCAP;
-  const int esz = p.plane_env;
-  uint8_t* envs = smem_raw + p.planes_off;
-  uint8_t* genv = envs + grp * esz;
+  // planes: staged in shared memory for the whole launch, or (large maps, p.staged == 0) used in
+  // place in global memory so that shared memory does not cap the number of resident warps
+  const long long env0 = (long long)blockIdx.x * EPB;
+  const int esz = p.staged ? p.plane_env : d.env_stride;
+  uint8_t* envs = p.staged ? smem_raw + p.planes_off : p.grid + (size_t)env0 * d.env_stride;
+  uint8_t* genv = envs + (size_t)grp * esz;
   uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * 2 * d.A;
   int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
   uint8_t* stage_raw = smem_raw + p.stage_off + grp * p.stage_env;
@@ -266,7 +276,6 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   if (wlane == 0) *qn = 0;
   __syncthreads();
 
-  const long long env0 = (long long)blockIdx.x * EPB;
   if (env0 + (long long)warp * GPW >= d.N) return;  // whole warp idle (only warp-level syncs below)
   const long long env = env0 + grp;
   const bool active = env < d.N;
@@ -276,15 +285,18 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   // ---- stage the instance ------------------------------------------------------------------
   uint4* genv4 = reinterpret_cast<uint4*>(genv);
   if (active) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.grid + (size_t)env * d.env_stride);
-    for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = __ldg(src + c);
+    if (p.staged) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.grid + (size_t)env * d.env_stride);
+      for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = __ldg(src + c);
+    }
     for (int a = lane; a < d.A; a += LPE) {
       int pos = p.agent_pos[(size_t)env * d.A + a];
       int y = pos / d.W;
       spos[a] = ((uint32_t)y << 16) | (uint32_t)(pos - y * d.W);
     }
-  } else {
-    for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  } else {  // lanes past the last instance: never touch a grid (every access below is guarded by `active`)
+    if (p.staged)
+      for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = make_uint4(~0u, ~0u, ~0u, ~0u);
     for (int a = lane; a < d.A; a += LPE) spos[a] = 0;
   }
   double total = (active && lane == 0 && p.write_back) ? p.total_reward[env] : 0.0;
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         for (int it = 0; it < iters; ++it) {
           const int c = it * LPE + lane;
           uint32_t m = 0;
-          if (c < d.n_chunks) {
+          if (c < d.n_chunks && active) {
             const uint4 k = genv4[c];
             const SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
             m = sb_simd_cand_chunk(k.x, k.y, k.z, k.w, r.x, r.y, r.z, r.w, spawn4, d.hmask4);
@@ -382,7 +394,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           const uint32_t g = entry >> 20, cell = entry & 0xFFFFFu;
           const uint32_t eid = (uint32_t)(d.env_id_base + (uint64_t)(env0 + g));
           const int kind = sb_resolve_candidate(d, eid, tick, cell, rk);
-          if (kind >= 0) envs[g * esz + cell] = (uint8_t)kind;
+          if (kind >= 0) envs[(size_t)g * esz + cell] = (uint8_t)kind;
         }
         __syncwarp();
         if (wlane == 0) *qn = 0;
@@ -392,7 +404,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         // the group draw LPE stream entries at a time; lane 0 accepts them in stream order.
         uint16_t* hits = reinterpret_cast<uint16_t*>(smem_raw + p.hits_off) + grp * SB_SPARSE_KMAX;
         const SbU4 r0 = sb_philox_rk(envid, tick, 0u, SB_DOM_SPARSE, rk);
-        const int K = sb_sparse_count(d, ((uint64_t)r0.x << 32) | r0.y);
+        const int K = active ? sb_sparse_count(d, ((uint64_t)r0.x << 32) | r0.y) : 0;
         int accepted = 0;
         uint32_t base = 1;
         while (__any_sync(0xFFFFFFFFu, accepted < K)) {
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           base += LPE;
         }
       } else {  // SB_K_PHILOX_GENERIC: several spawning kinds or a large probability
-        for (int c = lane; c < d.n_chunks; c += LPE) {
+        for (int c = lane; c < d.n_chunks && active; c += LPE) {
           SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
           for (int b = 0; b < 16; ++b) {
             uint32_t cell = (uint32_t)(c * 16 + b);
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           __syncwarp();
           emit_onehot_row<LPE, NP1>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
         }
-      } else {
+      } else if (active) {
         for (int e = lane; e < d.obs_size; e += LPE) {
           const int c = e / d.SS;
           const uint32_t li = lut_ij[e - c * d.SS];
@@ -461,7 +473,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
     };
 
     auto act = [&](int a) {
-      if (lane == 0) {
+      if (lane == 0 && active) {
         uint32_t yx = spos[a];
         const int action = sact[a];
         float reward = sb_agent_act(d, genv, &yx, action, true, err);
@@ -511,8 +523,10 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
 
   // ---- write the instance back ---------------------------------------------------------------
   if (active && p.write_back) {
-    uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * d.env_stride);
-    for (int c = lane; c < d.n_chunks; c += LPE) dst[c] = genv4[c];
+    if (p.staged) {
+      uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * d.env_stride);
+      for (int c = lane; c < d.n_chunks; c += LPE) dst[c] = genv4[c];
+    }
     for (int a = lane; a < d.A; a += LPE) {
       uint32_t yx = spos[a];
       p.agent_pos[(size_t)env * d.A + a] = (int32_t)((yx >> 16) * d.W + (yx & 0xFFFFu));
@@ -531,6 +545,7 @@ static int launch_one(const SbDev& d, StepParams p, cudaStream_t s) {
   sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
   p.q_off = L.q_off, p.planes_off = L.planes_off, p.pos_off = L.pos_off, p.stage_off = L.stage_off;
   p.plane_env = L.plane_env, p.stage_env = L.stage_env, p.hits_off = L.hits_off;
+  p.staged = stage_planes(d) ? 1 : 0;
   const int smem = L.total;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
   auto kern = step_kernel<LPE, RNG, NP1>;

@@ -15,7 +15,7 @@ def golden_cases(max_cells: int = 64 * 64, with_large: bool = False):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name.startswith("observe_"):
+        if name.startswith(("observe_", "transformer_")):
             continue
         if name.startswith("large") and not with_large:
             continue

@@ -444,6 +444,42 @@ def test_buffer_add_matches_reference_semantics(cuda_device):
         buf.sample(10_000)
 
 
+def test_transformer_buffer_golden(cuda_device):
+    """TransformerBuffer.combine + sample_transformer outputs captured from the reference."""
+    from sorrel_b200.buffers import Buffer
+
+    g = util.load_golden("transformer_s21_a2_11")
+    A, cap, F, T = 2, int(g["capacity"]), int(g["n_frames"]), int(g["T"])
+    spec = R.treasurehunt_spec(11, 11, A, 2, 0.05)
+    env, _ = util.run_oracle_episode(spec, R.NumpyDraws(21), T)
+    spawn_u, spawn_c, actions, placement = _tapes_to_device(spec, [env.dense_tapes()], cuda_device)
+    eng = _engine(spec, 1, cuda_device)
+    buf = Buffer(cap, (spec.obs_size,), n_frames=F, rows=A, device=cuda_device, positions=(2,))
+    eng.reset(placement)
+    eng.step(T, buffer=buf, actions=actions, spawn_u=spawn_u, spawn_c=spawn_c)
+    comb = buf.combined()
+    for key in ("states", "actions", "rewards", "dones", "positions"):
+        ref = g["comb_" + key]
+        assert comb[key].dtype == ref.dtype, key
+        np.testing.assert_array_equal(comb[key], ref, err_msg=key)
+    assert len(comb["actions"]) == int(g["comb_size"])
+    # The reference's combine() allocates agent_ids but never fills them (buffers.py:298-313 copies only the
+    # keys the source buffers hold), so its ids are all 0; the engine returns the ids the docstring promises.
+    assert not g["comb_agent_ids"].any() and not g["t_agent_ids"].any()
+    np.testing.assert_array_equal(comb["agent_ids"], np.repeat(np.arange(A), T))
+    # sample_transformer on the reference's drawn indices of the COMBINED buffer -> (row, start) pairs
+    idx = g["sample_idx"]
+    rows, starts = idx // T, idx % T
+    keep = starts + F + 1 <= T  # windows that stay inside one agent's segment map 1:1 onto a ring row
+    out = buf.gather_transformer(rows[keep], starts[keep])
+    for o, key in zip(out[:6], ("t_states", "t_actions", "t_next_actions", "t_next_states", "t_dones", "t_valid")):
+        got, ref = o.cpu().numpy(), g[key][keep]
+        assert got.dtype == ref.dtype and got.shape == ref.shape, key
+        np.testing.assert_array_equal(got, ref, err_msg=key)
+    np.testing.assert_array_equal(out[6].cpu().numpy(), rows[keep])
+    assert int(keep.sum()) >= 12
+
+
 def test_reward_stats(cuda_device):
     import ctypes as C
 
