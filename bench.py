@@ -57,6 +57,7 @@ def parse_args():
                     help="counter-based spawn sampling: philox = one random byte per cell per turn (dense, like the "
                          "reference's draw-per-cell loop); sparse = Binomial count + distinct cells (same law)")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra sparse-sampler timing")
+    ap.add_argument("--no-graphs", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--obs-study", action="store_true",
                     help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
     return ap.parse_args()
@@ -239,6 +240,7 @@ def run_ours(a):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
 
+    graphs = {}  # rng mode -> StepGraph
     turns_in_episode = [a.max_turns]  # forces a reset at the first step
     episode_stats = []
     seg = {"boundary": [], "step": [], "sample": []}  # (event, event) pairs per segment, timed steps only
@@ -260,18 +262,25 @@ def run_ours(a):
             turns_in_episode[0] = 0
             if e:
                 e[1].record()
+        sg = graphs.get(a.rng)  # CUDA-graph replay (device-resident tick/slot) once captured
         e = mark("step", record)
-        eng.step(T, buffer=buf, actions=actions, reward_out=reward_out, rng=a.rng)
+        if sg is not None and actions is None:
+            sg.replay_step()
+        else:
+            eng.step(T, buffer=buf, actions=actions, reward_out=reward_out, rng=a.rng)
         if e:
             e[1].record()
         turns_in_episode[0] += T
         out = None
         if B:
             e = mark("sample", record)
-            hi = max(1, buf.size - buf.n_frames - 1)
-            rows = torch.randint(0, N * A, (B,), device=dev, generator=gen)
-            starts = torch.randint(0, hi, (B,), device=dev, generator=gen)
-            out = buf.gather(rows, starts)
+            if sg is not None and actions is None:
+                out = sg.replay_sample()
+            else:
+                hi = max(1, buf.size - buf.n_frames - 1)
+                rows = torch.randint(0, N * A, (B,), device=dev, generator=gen)
+                starts = torch.randint(0, hi, (B,), device=dev, generator=gen)
+                out = buf.gather(rows, starts)
             if e:
                 e[1].record()
         return out
@@ -286,17 +295,33 @@ def run_ours(a):
     warm = max(a.warmup, a.max_turns // T + 1)
     for _ in range(warm):
         one_step()
-    barrier()
+    if not a.no_graphs:  # the ring is full and every kernel has run once: capture, then warm the replays
+        from sorrel_b200.graphs import StepGraph
+
+        graphs[a.rng] = StepGraph(eng, buf, T, rng=a.rng, sample_batch=B)
+        for _ in range(3):
+            one_step()
+    # NVML is initialised BEFORE the barrier: doing it after would make rank 0 enter the timed region a few
+    # milliseconds late and every other rank wait for it at the first all-gather (measured: +4.6 ms)
     clocks = ClockSampler(local) if (rank == 0 and not a.no_clocks) else None
+    barrier()
     l0 = lib.sb_launch_count()
     t_wall0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
+    host_s = []
     for i in range(a.steps):
+        h0 = time.perf_counter()
         one_step(record=True)
+        host_s.append(time.perf_counter() - h0)
     g1.record()
+    t_enq = time.perf_counter()
     barrier()
     t_wall1 = time.perf_counter()
+    if os.environ.get("SB_BENCH_DEBUG"):
+        print(f"[rank {rank}] gpu_ms={g0.elapsed_time(g1):.3f} host_enqueue_ms={1e3 * (t_enq - t_wall0):.3f} "
+              f"host_step_ms max={1e3 * max(host_s):.3f} median={1e3 * sorted(host_s)[len(host_s) // 2]:.3f} "
+              f"wall_ms={1e3 * (t_wall1 - t_wall0):.3f}", file=sys.stderr, flush=True)
     launches = lib.sb_launch_count() - l0
     ms_total = g0.elapsed_time(g1)
     eng.check_errors()
@@ -318,6 +343,10 @@ def run_ours(a):
         seg = {"boundary": [], "step": [], "sample": []}
         for _ in range(3):
             one_step()
+        if not a.no_graphs:
+            graphs["sparse"] = StepGraph(eng, buf, T, rng="sparse", sample_batch=B)
+            for _ in range(3):
+                one_step()
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
@@ -411,6 +440,7 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "envs_per_gpu": N, "parallelism": f"env-shard x{world}",
                    "l2": "inputs larger than L2 (grid + ring slots touched per step >> 126 MB)",
                    "policy": "in-kernel uniform (RandomModel)",
+                   "launch": "eager" if a.no_graphs else "CUDA graph replay (device-resident tick/slot)",
                    "rng": "philox4x32-10, " + ("one byte per cell per turn" if a.rng == "philox" else
                                                "sparse (Binomial count + distinct cells)")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,

@@ -182,6 +182,9 @@ typedef struct SbStepArgs {
   int32_t* d_action_out;     /* optional [T][N][A] actions actually taken */
   uint8_t* d_drew_out;       /* optional [T][N][Ldyn*H*W] 1 where a cell consumed a uniform */
   uint32_t* d_error;         /* device error word (OR of SB_ERR_*) */
+  const uint32_t* d_clock;   /* optional device uint32[2] = {tick0, slot0}: when set, the kernel reads the
+                                two counters from device memory instead of the fields above, so that an
+                                identical launch can be replayed from a CUDA graph (sb_clock_advance) */
 } SbStepArgs;
 
 /* -- library / geometry ------------------------------------------------------------------ */
@@ -218,6 +221,10 @@ int sb_reset(const SbWorldDesc* desc, uint8_t* d_grid, int32_t* d_agent_pos, dou
  */
 int sb_step(const SbWorldDesc* desc, const SbStepArgs* args, uint8_t* d_grid, int32_t* d_agent_pos,
             double* d_total_reward, const SbBufferDesc* buf, void* stream);
+
+/* Advance a device-resident {tick, slot} pair (see SbStepArgs.d_clock): tick += add_tick,
+ * slot = (slot + add_slot) % capacity.  Graph-capturable companion of sb_step. */
+int sb_clock_advance(uint32_t* d_clock, uint32_t add_tick, uint32_t add_slot, uint32_t capacity, void* stream);
 
 /* -- ObservationSpec.observe -------------------------------------------------------------- *
  * observation/observation_spec.py:175-205 -> visual_field.py:9-101 for every (instance, agent):

@@ -104,6 +104,7 @@ class SbStepArgs(C.Structure):
         ("d_action_out", C.c_void_p),
         ("d_drew_out", C.c_void_p),
         ("d_error", C.c_void_p),
+        ("d_clock", C.c_void_p),
     ]
 
 
@@ -120,6 +121,7 @@ SIGNATURES = {
                            C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "sb_step": (C.c_int, [C.POINTER(SbWorldDesc), C.POINTER(SbStepArgs), C.c_void_p, C.c_void_p, C.c_void_p,
                           C.POINTER(SbBufferDesc), C.c_void_p]),
+    "sb_clock_advance": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sb_observe": (C.c_int, [C.POINTER(SbWorldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_buffer_add": (C.c_int, [C.POINTER(SbBufferDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),

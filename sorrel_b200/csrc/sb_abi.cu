@@ -353,6 +353,11 @@ __global__ void __launch_bounds__(STATS_THREADS)
   }
 }
 
+__global__ void clock_advance_kernel(uint32_t* clock, uint32_t add_tick, uint32_t add_slot, uint32_t capacity) {
+  clock[0] += add_tick;
+  clock[1] = (clock[1] + add_slot) % capacity;
+}
+
 static int check_buf(const SbBufferDesc* b) {
   if (!b) return SB_EINVAL;
   if (b->capacity <= 0 || b->obs_size <= 0 || b->n_frames <= 0 || b->rows <= 0) return SB_EINVAL;
@@ -446,7 +451,7 @@ int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t*
     rc = check_buf(buf);
     if (rc) return rc;
     if (buf->obs_size != d.obs_size || buf->rows != (int64_t)d.N * d.A) return SB_EINVAL;
-    if (a->slot0 < 0 || a->slot0 >= buf->capacity) return SB_EINVAL;
+    if (!a->d_clock && (a->slot0 < 0 || a->slot0 >= buf->capacity)) return SB_EINVAL;
     p.buf = *buf;
     p.has_buf = 1;
   }
@@ -455,6 +460,14 @@ int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t*
   p.agent_pos = d_agent_pos;
   p.total_reward = d_total_reward;
   return launch_step(d, p, (cudaStream_t)stream);
+}
+
+int sb_clock_advance(uint32_t* d_clock, uint32_t add_tick, uint32_t add_slot, uint32_t capacity, void* stream) {
+  if (!d_clock || capacity == 0) return SB_EINVAL;
+  clock_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_clock, add_tick, add_slot, capacity);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+  return SB_OK;
 }
 
 int sb_observe(const SbWorldDesc* w, const uint8_t* d_grid, const int32_t* d_agent_pos, float* d_obs_out,

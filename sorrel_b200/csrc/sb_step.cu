@@ -309,10 +309,12 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   const bool fused = p.a.mode == SB_MODE_FUSED;
   const size_t row0 = (size_t)(active ? env : 0) * d.A;  // first ring row of this instance
   float* const ring0 = p.has_buf ? p.buf.d_states + row0 * p.buf.capacity * d.obs_size : nullptr;
-  int slot = p.has_buf ? p.a.slot0 : 0;
+  // {tick0, slot0} from the launch arguments, or from device memory for graph-replayed launches
+  const uint32_t tick0 = p.a.d_clock ? p.a.d_clock[0] : p.a.tick0;
+  int slot = p.has_buf ? (p.a.d_clock ? (int)p.a.d_clock[1] : p.a.slot0) : 0;
 
   for (int t = 0; t < T; ++t, slot = (p.has_buf && slot + 1 < p.buf.capacity) ? slot + 1 : 0) {
-    const uint32_t tick = p.a.tick0 + (uint32_t)t;
+    const uint32_t tick = tick0 + (uint32_t)t;
 
     // ---- actions of this turn (parallel over agents; hides the tape-load latency) ------------
     if (fused || p.a.act_agent >= 0) {

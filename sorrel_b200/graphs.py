@@ -1,0 +1,107 @@
+"""CUDA-graph replay of the fused step (+ optional Buffer.sample) for launch-bound regimes.
+
+A step launch is identical from turn to turn except for two integers (the global tick and the ring
+slot).  `SbStepArgs.d_clock` lets the kernel read them from device memory and `sb_clock_advance`
+advances them on the device, so one captured graph = [step kernel, clock advance, (index draw, sample
+gather)] can be replayed without any per-step host work: small batches (config 2: 4096 instances) and
+multi-GPU strong scaling stop being bound by Python / launch latency.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+from ._abi import SbStepArgs, check
+
+
+class StepGraph:
+    def __init__(self, engine, buffer, turns: int, rng: str = "philox", sample_batch: int = 0):
+        """Capture one step of `turns` fused turns with the in-kernel policy, recording into `buffer`.
+
+        Every kernel involved must have been launched once before (CUDA loads modules lazily and that
+        is not capturable): run one eager `engine.step(...)` / `buffer.gather(...)` first."""
+        self.eng, self.buf, self.T, self.rng, self.B = engine, buffer, int(turns), rng, int(sample_batch)
+        dev = engine.device
+        self.clock = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._dev = [0, 0]  # host mirror of the device clock {tick0, slot0}
+        self._args = SbStepArgs()
+        a = self._args
+        a.mode, a.num_turns, a.seed = _abi.SB_MODE_FUSED, self.T, engine.seed
+        a.rng = _abi.SB_RNG_SPARSE if rng == "sparse" else _abi.SB_RNG_PHILOX
+        a.policy = _abi.SB_POLICY_UNIFORM
+        a.act_agent = a.obs_agent = -1
+        a.d_error = engine.error.data_ptr()
+        a.d_clock = self.clock.data_ptr()
+        self.sample = None
+        if self.B:
+            F, obs = buffer.n_frames, buffer.obs_size
+            self._hi = max(1, buffer.size - F - 1)
+            self.rows = torch.zeros(self.B, dtype=torch.int64, device=dev)
+            self.starts = torch.zeros(self.B, dtype=torch.int64, device=dev)
+            self.sample = (torch.empty((self.B, F * obs), dtype=torch.float32, device=dev),
+                           torch.empty((self.B, 1), dtype=torch.int64, device=dev),
+                           torch.empty((self.B, 1), dtype=torch.float32, device=dev),
+                           torch.empty((self.B, F * obs), dtype=torch.float32, device=dev),
+                           torch.empty((self.B, 1), dtype=torch.float32, device=dev),
+                           torch.empty((self.B, 1), dtype=torch.float64, device=dev))
+        self._sync_clock()
+        torch.cuda.synchronize(dev)
+        # two graphs (step / sample) so that a caller can put CUDA events between them
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue_step()
+        self.sample_graph = None
+        if self.B:
+            self.sample_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.sample_graph):
+                self._enqueue_sample()
+
+    def _enqueue_step(self):
+        eng, buf, lib = self.eng, self.buf, self.eng.lib
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        check(lib.sb_step(C.byref(eng.desc), C.byref(self._args), eng.grid.data_ptr(), eng.agent_pos.data_ptr(),
+                          eng.total_reward.data_ptr(), C.byref(buf.desc()), stream), "sb_step(graph)")
+        check(lib.sb_clock_advance(self.clock.data_ptr(), self.T, self.T, buf.capacity, stream), "sb_clock_advance")
+
+    def _enqueue_sample(self):
+        buf, lib = self.buf, self.eng.lib
+        stream = torch.cuda.current_stream(self.eng.device).cuda_stream
+        self.rows.random_(0, buf.rows)
+        self.starts.random_(0, self._hi)
+        s = self.sample
+        check(lib.sb_buffer_sample(C.byref(buf.desc()), self.rows.data_ptr(), self.starts.data_ptr(), self.B,
+                                   s[0].data_ptr(), s[1].data_ptr(), s[2].data_ptr(), s[3].data_ptr(),
+                                   s[4].data_ptr(), s[5].data_ptr(), stream), "sb_buffer_sample(graph)")
+
+    def _sync_clock(self):
+        """Bring the device clock in line with the host bookkeeping (after reset / add_empty / eager steps)."""
+        want = [(self.eng.tick + 1) & 0xFFFFFFFF, self.buf.idx]
+        if want != self._dev:
+            cap = self.buf.capacity
+            check(self.eng.lib.sb_clock_advance(self.clock.data_ptr(), (want[0] - self._dev[0]) & 0xFFFFFFFF,
+                                                (want[1] - self._dev[1]) % cap, cap,
+                                                torch.cuda.current_stream(self.eng.device).cuda_stream),
+                  "sb_clock_advance")
+            self._dev = want
+
+    def replay_step(self):
+        """`turns` fused turns for every instance."""
+        self._sync_clock()
+        self.graph.replay()
+        self.eng.tick += self.T
+        self.buf.advance(self.T)
+        self._dev = [(self._dev[0] + self.T) & 0xFFFFFFFF, (self._dev[1] + self.T) % self.buf.capacity]
+
+    def replay_sample(self):
+        """Draw `sample_batch` (row, start) pairs and gather them; returns the (reused) batch tensors."""
+        if max(1, self.buf.size - self.buf.n_frames - 1) != self._hi:
+            raise RuntimeError("the ring population changed since capture: capture the StepGraph again")
+        self.sample_graph.replay()
+        return self.sample
+
+    def replay(self):
+        """One step (+ sample): returns the sampled batch tensors (overwritten by the next replay) or None."""
+        self.replay_step()
+        return self.replay_sample() if self.B else None

@@ -283,6 +283,45 @@ def test_sparse_and_dense_modes_have_the_same_statistics(cuda_device):
         e2.step(1, rng="sparse")
 
 
+def test_cuda_graph_replay_equals_eager(cuda_device):
+    """StepGraph (device-resident tick/slot, sb_clock_advance) replays == eager launches, across resets,
+    add_empty and ring wrap."""
+    from sorrel_b200.graphs import StepGraph
+
+    spec = R.treasurehunt_spec(21, 21, 2, 2, 0.01)
+    N, T, cap = 48, 5, 16
+    eager, eb = _engine(spec, N, cuda_device, seed=5), None
+    eb = _buffer(spec, N, cap, cuda_device, n_frames=3)
+    graph_e = _engine(spec, N, cuda_device, seed=5)
+    gb = _buffer(spec, N, cap, cuda_device, n_frames=3)
+    for e, b in ((eager, eb), (graph_e, gb)):
+        e.reset()
+        b.add_empty()
+        for _ in range(4):  # fills the ring (size == capacity) and loads the kernels before capture
+            e.step(T, buffer=b)
+    b.gather(np.zeros(4, dtype=np.int64), np.zeros(4, dtype=np.int64))
+    sg = StepGraph(graph_e, gb, T, sample_batch=8)
+    for it in range(9):
+        if it in (3, 6):  # episode boundary on both
+            for e, b in ((eager, eb), (graph_e, gb)):
+                e.reset()
+                b.add_empty()
+        eager.step(T, buffer=eb)
+        out = sg.replay()
+        assert out[0].shape == (8, 3 * spec.obs_size)
+    eager.check_errors()
+    graph_e.check_errors()
+    assert graph_e.tick == eager.tick and gb.idx == eb.idx and gb.size == eb.size
+    np.testing.assert_array_equal(graph_e.grid_numpy(), eager.grid_numpy())
+    assert torch.equal(gb.states, eb.states) and torch.equal(gb.actions, eb.actions)
+    assert torch.equal(gb.rewards, eb.rewards) and torch.equal(graph_e.total_reward, eager.total_reward)
+    # the captured sample is a valid gather of the ring
+    rows, starts = sg.rows.cpu().numpy(), sg.starts.cpu().numpy()
+    ref = gb.gather(rows, starts)
+    for o, r in zip(out, ref):
+        assert torch.equal(o, r)
+
+
 def test_shard_invariance(cuda_device):
     """N instances on one engine == the concatenation of two shards (rank offset env_id_base)."""
     spec = R.treasurehunt_spec(21, 21, 2, 2, 0.01)
