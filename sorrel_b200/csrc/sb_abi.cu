@@ -19,10 +19,6 @@ int note_cuda_error() {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", cudaGetErrorString(e));
   return SB_ECUDA;
 }
-static int note_cuda_error(cudaError_t e) {
-  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", cudaGetErrorString(e));
-  return SB_ECUDA;
-}
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
