@@ -371,25 +371,31 @@ def run_ours(a):
 
         pipe = HostStepPipeline(eng, buf, T, rng=a.rng)
         h_actions = [torch.randint(0, 4, (T, N, A), dtype=torch.int32).pin_memory() for _ in range(2)]
-        for i in range(max(2, a.warmup // 2)):
+        def e2e_step(i):
+            """The same step as `one_step` (boundary stats + reset, fused turns, Buffer.sample), with the
+            step's actions coming from pinned host memory and its rewards read back to the host."""
             if turns_in_episode[0] >= a.max_turns:
+                episode_stats.append(stats.all_reduce(eng.total_reward))
                 eng.reset()
                 buf.add_empty()
                 turns_in_episode[0] = 0
             pipe.submit(h_actions[i % 2])
             turns_in_episode[0] += T
+            if B:
+                hi = max(1, buf.size - buf.n_frames - 1)
+                rows = torch.randint(0, N * A, (B,), device=dev, generator=gen)
+                starts = torch.randint(0, hi, (B,), device=dev, generator=gen)
+                buf.gather(rows, starts)
+
+        for i in range(max(3, a.warmup)):
+            e2e_step(i)
         pipe.drain()
         barrier()
         t0 = time.perf_counter()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for i in range(a.steps):
-            if turns_in_episode[0] >= a.max_turns:
-                eng.reset()
-                buf.add_empty()
-                turns_in_episode[0] = 0
-            pipe.submit(h_actions[i % 2])
-            turns_in_episode[0] += T
+            e2e_step(i)
         results = pipe.drain()
         c1.record()
         barrier()
