@@ -228,9 +228,102 @@ def observe_cases(rgb_only=False):
     print(f"observe_cases: {len(cases)} cases")
 
 
+CLEANUP_IDS = {"EmptyEntity": 0, "Wall": 1, "River": 2, "Pollution": 3, "AppleTree": 4, "Apple": 5, "CleanBeam": 6,
+               "ZapBeam": 7, "CleanupAgent": 8, "Sand": 9}
+
+
+def cleanup_grid_ids(world) -> np.ndarray:
+    """Kind ids of a CleanupWorld; a beam whose turn_counter is 1 (swept once) gets id 10 / 11."""
+    H, W, L = world.map.shape
+    g = np.zeros((H, W, L), dtype=np.uint8)
+    for idx, e in np.ndenumerate(world.map):
+        k = CLEANUP_IDS[type(e).__name__]
+        if k in (6, 7) and e.turn_counter >= 1:
+            k += 4
+        g[idx] = k
+    return g
+
+
+def run_cleanup_case(name, seed, H, W, A, v, T, epochs=1, initial_apples=20, apple_p=0.002, pollution_p=0.009,
+                     beam_radius=3, n_frames=1):
+    """examples/cleanup with the reference's RandomModel (6 actions) instead of IQN; everything else unmodified."""
+    from omegaconf import OmegaConf
+    from sorrel.examples.cleanup.entities import EmptyEntity as CEmpty
+    from sorrel.examples.cleanup.env import CleanupEnv
+    from sorrel.examples.cleanup.world import CleanupWorld
+
+    cfg = OmegaConf.create({
+        "experiment": {"name": "cleanup", "epochs": epochs, "max_turns": T, "epsilon_decay": 0.0001,
+                       "record_period": 50},
+        "env": {"height": H, "width": W, "layers": 3, "default_object": "EmptyEntity", "full_mdp": False,
+                "pollution_threshold": 0.5, "initial_apples": initial_apples, "apple_spawn_chance": apple_p,
+                "pollution_spawn_chance": pollution_p, "mode": "DEFAULT"},
+        "model": {"iqn": {"type": "iRainbowModel", "parameters": {
+            "layer_size": 16, "n_step": 3, "batch_size": 8, "memory_size": 64, "LR": 0.00025, "TAU": .001,
+            "GAMMA": 0.99, "n_quantiles": 4, "sync_freq": 200, "model_update_freq": 4, "epsilon": 0.8,
+            "device": "cpu"}}, "epsilon_decay": 0.0001},
+        "agent": {"agent": {"num": A, "model": "iqn", "beam_radius": beam_radius, "rotation": False,
+                            "obs": {"channels": 8, "vision": v, "n_frames": n_frames, "embeddings": 3}}},
+        "root": "x", "log": False})
+    world = CleanupWorld(config=cfg, default_entity=CEmpty())
+    env = CleanupEnv(world, cfg)
+    cap = T * epochs + (n_frames - 1) * epochs
+    for ag in env.agents:
+        m = RandomModel(ag.observation_spec.input_size, 6, cap)
+        m.memory = Buffer(capacity=cap, obs_shape=(ag.observation_spec.input_size[1],), n_frames=n_frames)
+        m.memory.extra_data["positions"] = np.zeros((cap, 2), dtype=np.int64)
+        ag.model = m
+    log = DrawLog()
+    grids, starts, totals, facings = [], [], [], []
+    with record(log):
+        set_seed(seed)
+        for ep in range(epochs):
+            env.reset()
+            starts.append([ag.location[:2] for ag in env.agents])
+            if n_frames > 1:
+                for ag in env.agents:
+                    ag.model.memory.add_empty()
+            grids.append(cleanup_grid_ids(world))  # state right after reset (apples + agents placed)
+            for t in range(T):
+                env.take_turn()
+                grids.append(cleanup_grid_ids(world))
+                facings.append([ag.direction for ag in env.agents])
+            world.is_done = True
+            totals.append(world.total_reward)
+    mems = [ag.model.memory for ag in env.agents]
+    data = dict(
+        world="cleanup", seed=seed, H=H, W=W, A=A, v=v, T=T, epochs=epochs, capacity=cap, n_frames=n_frames,
+        initial_apples=initial_apples, apple_p=apple_p, pollution_p=pollution_p, beam_radius=beam_radius,
+        starts=np.array(starts, dtype=np.int64), grids=np.array(grids, dtype=np.uint8),
+        facings=np.array(facings, dtype=np.int64), total_reward=np.array(totals, dtype=np.float64),
+        states=np.stack([b.states for b in mems]), actions=np.stack([b.actions for b in mems]),
+        rewards=np.stack([b.rewards for b in mems]), dones=np.stack([b.dones for b in mems]),
+        positions=np.stack([b.extra_data["positions"] for b in mems]),
+        buf_idx=np.array([b.idx for b in mems]), buf_size=np.array([b.size for b in mems]),
+        n_uniform=np.int64(sum(1 for c in log.calls if c[0] == "random")),
+    )
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **data)
+    acts = np.stack([b.actions for b in mems])
+    print(f"{name}: total_reward={totals} uniforms={int(data['n_uniform'])} beams={(acts >= 4).sum()} "
+          f"rewards!=0: {(np.stack([b.rewards for b in mems]) != 0).sum()} -> {os.path.getsize(path)} B")
+
+
+def cleanup_cases():
+    run_cleanup_case("cleanup_s3_a10_21x31", 3, 21, 31, 10, 5, 60)  # the example's own shape (configs/config.yaml)
+    run_cleanup_case("cleanup_s5_a4_15x16", 5, 15, 16, 4, 3, 80, initial_apples=8, apple_p=0.05, pollution_p=0.1,
+                     beam_radius=2)  # dense dynamics: many spawns, cleaned pollution, eaten apples
+    run_cleanup_case("cleanup_s8_a6_12x19", 8, 12, 19, 6, 2, 40, epochs=2, initial_apples=5, apple_p=0.02,
+                     pollution_p=0.05, n_frames=3)  # two episodes: facings persist across reset, ring add_empty
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "transformer":
         transformer_case()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "cleanup":
+        cleanup_cases()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "rgb":  # only the fixtures added after the first generation
         run_case("rgb_s13_a2_11", 13, 11, 11, 2, 2, 0.05, 40, obs="rgb")
@@ -255,6 +348,7 @@ def main():
     run_case("rgb_s13_a2_11", 13, 11, 11, 2, 2, 0.05, 40, obs="rgb")
     transformer_case()
     observe_cases()
+    cleanup_cases()
 
 
 if __name__ == "__main__":

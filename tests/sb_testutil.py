@@ -15,7 +15,7 @@ def golden_cases(max_cells: int = 64 * 64, with_large: bool = False):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name.startswith(("observe_", "transformer_")):
+        if name.startswith(("observe_", "transformer_", "cleanup_")):
             continue
         if name.startswith("large") and not with_large:
             continue
@@ -25,6 +25,15 @@ def golden_cases(max_cells: int = 64 * 64, with_large: bool = False):
 
 def load_golden(name: str):
     return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def cleanup_cases():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "cleanup_*.npz")))
+
+
+def cleanup_spec_from_golden(g) -> R.WorldSpec:
+    return R.cleanup_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), int(g["initial_apples"]),
+                          float(g["apple_p"]), float(g["pollution_p"]), int(g["beam_radius"]))
 
 
 def spec_from_golden(g) -> R.WorldSpec:

@@ -154,3 +154,35 @@ def test_rgb_observe_against_reference_outputs():
                            np.zeros((0, 3)), 3, 0, 0, 1, v, 0, 0.0, [], obs_transform=1)
         o = R.observe(spec, kinds, y, x)
         np.testing.assert_array_equal(o, g[f"obs_{i}"])
+
+
+@pytest.mark.parametrize("name", util.cleanup_cases())
+def test_restatement_reproduces_reference_cleanup(name):
+    """examples/cleanup: column rules (River/Pollution/AppleTree/Apple), beams with a
+    one-turn lifetime, facings, all-layer rewards, one-hot crop + positional code -- every turn's grid
+    (beam ages included), facings, total reward and all buffer arrays equal the reference's."""
+    g = util.load_golden(name)
+    spec = util.cleanup_spec_from_golden(g)
+    T, E, F = int(g["T"]), int(g["epochs"]), int(g["n_frames"])
+    env = R.OracleEnv(spec, R.NumpyDraws(int(g["seed"])), capacity=int(g["capacity"]), n_frames=F)
+    gi = 0
+    for ep in range(E):
+        env.reset()
+        if F > 1:
+            for b in env.buffers:
+                b.add_empty()
+        np.testing.assert_array_equal(env.pos, g["starts"][ep])
+        np.testing.assert_array_equal(env.grid, g["grids"][gi], err_msg=f"epoch {ep} after reset")
+        gi += 1
+        for t in range(T):
+            env.take_turn()
+            np.testing.assert_array_equal(env.grid, g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+            np.testing.assert_array_equal(env.facing, g["facings"][ep * T + t])
+            gi += 1
+        assert env.total_reward == float(g["total_reward"][ep])
+    for a, b in enumerate(env.buffers):
+        for key, arr in (("states", b.states), ("actions", b.actions), ("rewards", b.rewards),
+                         ("dones", b.dones), ("positions", b.positions)):
+            assert arr.dtype == g[key].dtype, key
+            np.testing.assert_array_equal(arr, g[key][a], err_msg=key)
+        assert b.idx == int(g["buf_idx"][a]) and b.size == int(g["buf_size"][a])
