@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 1
+#define SB_ABI_VERSION 2
 
 #define SB_MAX_KINDS 32    /* entity classes per world (kind ids are uint8 < SB_MAX_KINDS) */
 #define SB_MAX_CHANNELS 32 /* observation channels C = len(entity_list) */
@@ -36,6 +36,9 @@ extern "C" {
 #define SB_MAX_ACTIONS 8
 #define SB_MAX_AGENTS 64 /* agents per world instance */
 #define SB_PAD_KIND 0xFF /* value of the padding bytes after each H*W plane */
+#define SB_NO_KIND 0xFF  /* "no kind" in kind-valued tables (action_beam_kind) */
+#define SB_MAX_BEAM_CELLS 16 /* cells one beam covers (cleanup: 3 * beam_radius = 9) */
+#define SB_MAX_ITEM_GROUPS 4 /* item groups placed by sb_reset_ex before the agents */
 
 typedef enum SbStatus {
   SB_OK = 0,
@@ -63,6 +66,17 @@ typedef enum SbStatus {
 #define SB_RULE_NONE 0
 #define SB_RULE_SPAWN 1 /* Bernoulli(spawn_prob) -> uniform choice among spawn_choice_kinds;
                            EmptyEntity.transition, examples/treasurehunt/entities.py:69-85 */
+/* "column rules": a transition may read the other layers of its own (y, x) column, which is all the
+   reference's shipped rule sets do.  The sweep visits the planes in ascending layer order, so a rule
+   sees lower layers after, higher layers before their own transition of the turn -- exactly the
+   C-order np.ndenumerate sweep of Environment.take_turn (environment.py:88-91). */
+#define SB_RULE_SPAWN_TO 2  /* Bernoulli(kind_rule_prob[k]) -> kind_rule_to[k], no choice draw:
+                               River -> Pollution, AppleTree -> Apple (examples/cleanup/entities.py:43-54,74-90) */
+#define SB_RULE_BECOME_IF 3 /* the cell of the same column on layer kind_rule_layer[k] holds a kind of
+                               kind_rule_mask[k] -> kind_rule_to[k]: Pollution under a CleanBeam -> River,
+                               Apple under an agent -> AppleTree (cleanup/entities.py:57-71,93-105) */
+#define SB_RULE_BECOME 4    /* unconditionally -> kind_rule_to[k]: Beam.transition (cleanup/agents.py:199-204)
+                               with the per-entity turn_counter folded into the kind id */
 
 /* sources of randomness / actions for sb_step */
 #define SB_RNG_TAPE 0   /* replay recorded numpy draws: bit-exact to the reference */
@@ -132,7 +146,40 @@ typedef struct SbWorldDesc {
   uint64_t spawn_cdf[SB_SPARSE_KMAX];
   int32_t obs_transform; /* SB_OBS_*: applied to the per-cell sum over layers before the f32 store */
   int32_t reserved1;
+  /* ---- ABI v2: column rules, facings + beams, all-layer rewards, positional code (examples/cleanup) ---- */
+  double kind_rule_prob[SB_MAX_KINDS];   /* SB_RULE_SPAWN_TO */
+  uint8_t kind_rule_to[SB_MAX_KINDS];    /* SB_RULE_SPAWN_TO / BECOME_IF / BECOME */
+  int8_t kind_rule_layer[SB_MAX_KINDS];  /* SB_RULE_BECOME_IF: a dynamic layer */
+  uint32_t kind_rule_mask[SB_MAX_KINDS]; /* SB_RULE_BECOME_IF: bit j set <=> kind j satisfies the test */
+  int8_t action_facing[SB_MAX_ACTIONS];  /* facing (0 N, 1 E, 2 S, 3 W) the agent takes with the action, -1 =
+                                            unchanged (MovingAgent.movement, agents/agent.py:199-211) */
+  uint8_t action_beam_kind[SB_MAX_ACTIONS]; /* kind the action's beam places, SB_NO_KIND = no beam
+                                               (CleanupAgent.spawn_beam, cleanup/agents.py:93-145) */
+  int32_t uses_facing;    /* 1: action_facing / action_beam_kind are meaningful and SbStepArgs.d_agent_facing
+                             must be set; 0: plain MovingAgent (treasurehunt) */
+  int32_t beam_layer;     /* dynamic layer the beams live on */
+  int32_t num_beam_cells; /* <= SB_MAX_BEAM_CELLS */
+  int8_t beam_dy[4][SB_MAX_BEAM_CELLS]; /* beam cells relative to the agent, per facing */
+  int8_t beam_dx[4][SB_MAX_BEAM_CELLS];
+  uint32_t beam_block_mask;  /* kinds on the beam layer a beam does not replace (Wall) */
+  int32_t reward_all_layers; /* reward = sum of Entity.value over all layers of the target column
+                                (world.observe_all_layers, cleanup/agents.py:160-170) instead of the agent layer's */
+  int32_t reward_count;      /* times the reward is added to world.total_reward per agent turn: 1, or 2 for
+                                cleanup (cleanup/agents.py:172 and agents/agent.py:172); 0 means 1 */
+  int32_t obs_extra;         /* floats appended to every observation after the C*S*S crop */
+  const float* d_obs_extra;  /* device [H*W][obs_extra], row of the agent's cell: positional code
+                                (CleanupObservation.observe cleanup/agents.py:52-62, observation/embedding.py:8-44),
+                                computed by the caller (numpy, f64 -> f32 like Buffer.states) */
 } SbWorldDesc;
+
+/* One group of items placed on distinct cells at reset, before the agents (cleanup/env.py:126-132:
+ * `initial_apples` Apples on the orchard cells). */
+typedef struct SbItemGroup {
+  int32_t kind, layer, count, n_cells;
+  const int32_t* d_cells;     /* device int32 [n_cells] plane cell index (y*W+x), reference order */
+  const int32_t* d_placement; /* device int32 [N][count] indices into d_cells (replayed np.random.choice),
+                                 or NULL to draw in-kernel: Philox(seed, env id, tick, ((g+1)<<24) + try, SB_DOM_RESET) */
+} SbItemGroup;
 
 /*
  * Batched replay ring: one reference `Buffer` (sorrel/buffers.py:11-44) per agent row,
@@ -146,7 +193,7 @@ typedef struct SbWorldDesc {
  */
 typedef struct SbBufferDesc {
   int32_t capacity;
-  int32_t obs_size; /* C*S*S floats */
+  int32_t obs_size; /* C*S*S + obs_extra floats */
   int32_t n_frames;
   int32_t reserved;
   int64_t rows;
@@ -185,6 +232,7 @@ typedef struct SbStepArgs {
   const uint32_t* d_clock;   /* optional device uint32[2] = {tick0, slot0}: when set, the kernel reads the
                                 two counters from device memory instead of the fields above, so that an
                                 identical launch can be replayed from a CUDA graph (sb_clock_advance) */
+  int32_t* d_agent_facing;   /* [N][A] MovingAgent.direction, read and written; required iff desc.uses_facing */
 } SbStepArgs;
 
 /* -- library / geometry ------------------------------------------------------------------ */
@@ -211,6 +259,12 @@ int sb_reset(const SbWorldDesc* desc, uint8_t* d_grid, int32_t* d_agent_pos, dou
              const int32_t* d_spawnable, int32_t n_spawnable, const int32_t* d_placement,
              uint64_t seed, uint32_t tick, void* stream);
 
+/* Same with item groups placed first (examples/cleanup/env.py:85-140): groups[g] host array, n_groups <=
+ * SB_MAX_ITEM_GROUPS.  sb_reset(...) == sb_reset_ex(..., NULL, 0, ...). */
+int sb_reset_ex(const SbWorldDesc* desc, uint8_t* d_grid, int32_t* d_agent_pos, double* d_total_reward,
+                const int32_t* d_spawnable, int32_t n_spawnable, const int32_t* d_placement,
+                const SbItemGroup* groups, int32_t n_groups, uint64_t seed, uint32_t tick, void* stream);
+
 /* -- Environment.take_turn ---------------------------------------------------------------- *
  * environment.py:81-93 (entity sweep -> EmptyEntity.transition treasurehunt/entities.py:69-85;
  * then Agent.transition agents/agent.py:155-173 = pov/observe -> action -> act/move -> reward ->
@@ -228,7 +282,7 @@ int sb_clock_advance(uint32_t* d_clock, uint32_t add_tick, uint32_t add_slot, ui
 
 /* -- ObservationSpec.observe -------------------------------------------------------------- *
  * observation/observation_spec.py:175-205 -> visual_field.py:9-101 for every (instance, agent):
- * d_obs_out float [N][A][C][S][S].  Pure function of the grid; does not modify state.
+ * d_obs_out float [N][A][C*S*S + obs_extra].  Pure function of the grid; does not modify state.
  */
 int sb_observe(const SbWorldDesc* desc, const uint8_t* d_grid, const int32_t* d_agent_pos,
                float* d_obs_out, void* stream);

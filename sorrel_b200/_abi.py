@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-SB_ABI_VERSION = 1
+SB_ABI_VERSION = 2
 SB_MAX_KINDS = 32
 SB_MAX_CHANNELS = 32
 SB_MAX_LAYERS = 8
@@ -16,10 +16,13 @@ SB_MAX_CHOICES = 8
 SB_MAX_ACTIONS = 8
 SB_MAX_AGENTS = 64
 SB_PAD_KIND = 0xFF
+SB_NO_KIND = 0xFF
+SB_MAX_BEAM_CELLS = 16
+SB_MAX_ITEM_GROUPS = 4
 
 SB_OK, SB_EINVAL, SB_EUNSUPPORTED, SB_EALIGN, SB_ECUDA, SB_ENODEVICE, SB_EVISION = 0, -1, -2, -3, -4, -5, -6
 SB_ERR_OFFGRID, SB_ERR_TAPE_ALIGN, SB_ERR_BAD_ACTION, SB_ERR_BAD_KIND = 1, 2, 4, 8
-SB_RULE_NONE, SB_RULE_SPAWN = 0, 1
+SB_RULE_NONE, SB_RULE_SPAWN, SB_RULE_SPAWN_TO, SB_RULE_BECOME_IF, SB_RULE_BECOME = 0, 1, 2, 3, 4
 SB_RNG_TAPE, SB_RNG_PHILOX, SB_RNG_SPARSE = 0, 1, 2
 SB_SPARSE_KMAX = 64
 SB_POLICY_TAPE, SB_POLICY_UNIFORM = 0, 1
@@ -65,6 +68,34 @@ class SbWorldDesc(C.Structure):
         ("spawn_cdf", C.c_uint64 * 64),
         ("obs_transform", C.c_int32),
         ("reserved1", C.c_int32),
+        # ---- ABI v2 ----
+        ("kind_rule_prob", C.c_double * SB_MAX_KINDS),
+        ("kind_rule_to", C.c_uint8 * SB_MAX_KINDS),
+        ("kind_rule_layer", C.c_int8 * SB_MAX_KINDS),
+        ("kind_rule_mask", C.c_uint32 * SB_MAX_KINDS),
+        ("action_facing", C.c_int8 * SB_MAX_ACTIONS),
+        ("action_beam_kind", C.c_uint8 * SB_MAX_ACTIONS),
+        ("uses_facing", C.c_int32),
+        ("beam_layer", C.c_int32),
+        ("num_beam_cells", C.c_int32),
+        ("beam_dy", (C.c_int8 * SB_MAX_BEAM_CELLS) * 4),
+        ("beam_dx", (C.c_int8 * SB_MAX_BEAM_CELLS) * 4),
+        ("beam_block_mask", C.c_uint32),
+        ("reward_all_layers", C.c_int32),
+        ("reward_count", C.c_int32),
+        ("obs_extra", C.c_int32),
+        ("d_obs_extra", C.c_void_p),
+    ]
+
+
+class SbItemGroup(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("layer", C.c_int32),
+        ("count", C.c_int32),
+        ("n_cells", C.c_int32),
+        ("d_cells", C.c_void_p),
+        ("d_placement", C.c_void_p),
     ]
 
 
@@ -105,6 +136,7 @@ class SbStepArgs(C.Structure):
         ("d_drew_out", C.c_void_p),
         ("d_error", C.c_void_p),
         ("d_clock", C.c_void_p),
+        ("d_agent_facing", C.c_void_p),
     ]
 
 
@@ -119,6 +151,8 @@ SIGNATURES = {
     "sb_validate": (C.c_int, [C.POINTER(SbWorldDesc)]),
     "sb_reset": (C.c_int, [C.POINTER(SbWorldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                            C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "sb_reset_ex": (C.c_int, [C.POINTER(SbWorldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                              C.c_void_p, C.POINTER(SbItemGroup), C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "sb_step": (C.c_int, [C.POINTER(SbWorldDesc), C.POINTER(SbStepArgs), C.c_void_p, C.c_void_p, C.c_void_p,
                           C.POINTER(SbBufferDesc), C.c_void_p]),
     "sb_clock_advance": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),

@@ -81,7 +81,11 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   d.v = w->vision;
   d.S = 2 * d.v + 1;
   d.SS = d.S * d.S;
-  d.obs_size = d.C * d.SS;
+  d.oh_size = d.C * d.SS;
+  if (w->obs_extra < 0 || w->obs_extra > 256 || (w->obs_extra > 0 && !w->d_obs_extra)) return SB_EINVAL;
+  d.obs_extra = w->obs_extra;
+  d.extra_tbl = w->d_obs_extra;
+  d.obs_size = d.oh_size + d.obs_extra;
   d.inv_S = (65536u + (uint32_t)d.S - 1u) / (uint32_t)d.S;
   d.fill_kind = w->fill_kind;
   d.agent_kind = w->agent_kind;
@@ -98,15 +102,66 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   for (int k = 0; k < d.K; ++k) {
     d.value[k] = w->kind_value[k];
     if (w->kind_passable[k]) d.passable_mask |= 1u << k;
-    if (w->kind_rule[k] == SB_RULE_SPAWN) {
+    const int rule = w->kind_rule[k];
+    d.rule[k] = (uint8_t)rule;
+    d.rule_to[k] = w->kind_rule_to[k];
+    if (rule == SB_RULE_SPAWN) {
       d.spawn_mask |= 1u << k;
+      d.draw_mask |= 1u << k;
       d.single_spawn_kind = k;
+      d.prob[k] = w->spawn_prob;
+      d.thr53[k] = thr;
       ++n_spawn_kinds;
-    } else if (w->kind_rule[k] != SB_RULE_NONE) {
+    } else if (rule == SB_RULE_SPAWN_TO) {
+      if (!(w->kind_rule_prob[k] >= 0.0) || w->kind_rule_prob[k] > 1.0 || !kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
+      d.draw_mask |= 1u << k;
+      d.prob[k] = w->kind_rule_prob[k];
+      d.thr53[k] = spawn_threshold(d.prob[k]);
+      d.ext_rules = 1;
+    } else if (rule == SB_RULE_BECOME_IF) {
+      const int z = w->kind_rule_layer[k];
+      if (z < 0 || z >= d.L || d.plane_of_layer[z] < 0 || !kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
+      d.rule_plane_off[k] = d.plane_of_layer[z] * d.plane_stride;
+      d.rule_mask[k] = w->kind_rule_mask[k];
+      d.ext_rules = 1;
+    } else if (rule == SB_RULE_BECOME) {
+      if (!kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
+      d.ext_rules = 1;
+    } else if (rule != SB_RULE_NONE) {
       return SB_EUNSUPPORTED;
     }
   }
-  if (n_spawn_kinds != 1) d.single_spawn_kind = -1;
+  if (n_spawn_kinds != 1 || d.ext_rules) d.single_spawn_kind = -1;
+  // facings / beams / all-layer rewards (MovingAgent.movement, CleanupAgent.spawn_beam / act)
+  d.reward_all = w->reward_all_layers ? 1 : 0;
+  d.reward_count = w->reward_count > 0 ? w->reward_count : 1;
+  d.beam_plane = -1;
+  for (int i = 0; i < SB_MAX_ACTIONS; ++i) {
+    d.act_facing[i] = -1;
+    d.act_beam[i] = SB_NO_KIND;
+  }
+  if (w->uses_facing) {
+    bool any_beam = false;
+    for (int i = 0; i < w->num_actions; ++i) {
+      if (w->action_facing[i] > 3) return SB_EINVAL;
+      d.act_facing[i] = w->action_facing[i] < 0 ? -1 : w->action_facing[i];
+      d.act_beam[i] = w->action_beam_kind[i];
+      if (d.act_beam[i] != SB_NO_KIND) {
+        if (!kind_ok(d.act_beam[i])) return SB_EINVAL;
+        any_beam = true;
+      }
+    }
+    if (any_beam) {
+      if (w->beam_layer < 0 || w->beam_layer >= d.L || d.plane_of_layer[w->beam_layer] < 0) return SB_EINVAL;
+      if (w->num_beam_cells < 0 || w->num_beam_cells > SB_MAX_BEAM_CELLS) return SB_EUNSUPPORTED;
+      d.beam_plane = d.plane_of_layer[w->beam_layer];
+      d.n_beam = w->num_beam_cells;
+      memcpy(d.beam_dy, w->beam_dy, sizeof(d.beam_dy));
+      memcpy(d.beam_dx, w->beam_dx, sizeof(d.beam_dx));
+      d.beam_block_mask = w->beam_block_mask;
+    }
+  }
+  d.ext_act = (w->uses_facing || d.reward_all || d.reward_count != 1) ? 1 : 0;
   if (n_spawn_kinds > 0 && d.n_choices == 0 && d.p > 0.0) return SB_EINVAL;
   for (int i = 0; i < d.n_choices; ++i) {
     if (!kind_ok(w->spawn_choice_kinds[i])) return SB_EINVAL;
@@ -116,7 +171,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     d.dy_packed |= (uint64_t)(uint8_t)w->action_dy[i] << (8 * i);
     d.dx_packed |= (uint64_t)(uint8_t)w->action_dx[i] << (8 * i);
   }
-  d.simd_sweep = (d.single_spawn_kind >= 0 && d.hi8 + 1u <= 128u) ? 1 : 0;
+  const bool ext = d.ext_rules || d.ext_act || d.obs_extra > 0;  // only the generic / replay variants implement these
+  d.simd_sweep = (d.single_spawn_kind >= 0 && d.hi8 + 1u <= 128u && !ext) ? 1 : 0;
   {
     uint32_t n2 = 1;
     while (n2 < d.hi8 + 1u) n2 <<= 1;
@@ -143,7 +199,7 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   for (int k = d.K; k < SB_MAX_KINDS; ++k) d.channel[k] = 255;
   for (int k = 0; k < 8; ++k) d.channel8 |= (uint64_t)d.channel[k] << (8 * k);
   d.fill_channel = d.channel[d.fill_kind];
-  d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536) ? 1 : 0;
+  d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536 && !ext) ? 1 : 0;
   if (d.sparse_ok) memcpy(d.cdf, w->spawn_cdf, sizeof(d.cdf));
   d.app = w->d_appearance;
   d.tmpl = w->d_template;
@@ -155,10 +211,18 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
 // reset: Environment.reset + populate_environment (environment.py:72-79, treasurehunt/env.py:114-147)
 // ------------------------------------------------------------------------------------------------
 constexpr int RESET_LPE = 4;
+struct ResetGroups {
+  int32_t n;
+  int32_t kind[SB_MAX_ITEM_GROUPS], plane[SB_MAX_ITEM_GROUPS], count[SB_MAX_ITEM_GROUPS], n_cells[SB_MAX_ITEM_GROUPS];
+  const int32_t* cells[SB_MAX_ITEM_GROUPS];
+  const int32_t* placement[SB_MAX_ITEM_GROUPS];
+};
+
 __global__ void __launch_bounds__(SB_THREADS)
     reset_kernel(const __grid_constant__ SbDev d, uint8_t* __restrict__ grid, int32_t* __restrict__ agent_pos,
                  double* __restrict__ total_reward, const int32_t* __restrict__ spawnable, int n_spawnable,
-                 const int32_t* __restrict__ placement, uint64_t seed, uint32_t tick) {
+                 const int32_t* __restrict__ placement, const __grid_constant__ ResetGroups groups, uint64_t seed,
+                 uint32_t tick) {
   const int tid = threadIdx.x, lane = tid & (RESET_LPE - 1);
   const long long env = (long long)blockIdx.x * (SB_THREADS / RESET_LPE) + tid / RESET_LPE;
   const bool active = env < d.N;
@@ -177,6 +241,24 @@ __global__ void __launch_bounds__(SB_THREADS)
   if (active && lane == 0) {
     uint8_t* plane = grid + (size_t)env * d.env_stride + (size_t)d.agent_plane * d.plane_stride;
     const uint32_t envid = (uint32_t)(d.env_id_base + (uint64_t)env);
+    // item groups first, in order (cleanup/env.py:126-132: apples before agents)
+    for (int g = 0; g < groups.n; ++g) {
+      uint8_t* gp = grid + (size_t)env * d.env_stride + (size_t)groups.plane[g] * d.plane_stride;
+      uint32_t jg = (uint32_t)(g + 1) << 24;
+      for (int i = 0; i < groups.count[g]; ++i) {
+        int cell;
+        if (groups.placement[g]) {
+          cell = groups.cells[g][groups.placement[g][(size_t)env * groups.count[g] + i]];
+        } else {
+          for (;;) {
+            SbU4 w = sb_philox(envid, tick, jg++, SB_DOM_RESET, (uint32_t)seed, (uint32_t)(seed >> 32));
+            cell = groups.cells[g][sb_bounded(w.x, w.y, (uint32_t)groups.n_cells[g])];
+            if (gp[cell] != (uint8_t)groups.kind[g]) break;
+          }
+        }
+        gp[cell] = (uint8_t)groups.kind[g];
+      }
+    }
     uint32_t j = 0;
     for (int a = 0; a < d.A; ++a) {
       int cell;
@@ -400,17 +482,40 @@ int sb_validate(const SbWorldDesc* w) {
 int sb_reset(const SbWorldDesc* w, uint8_t* d_grid, int32_t* d_agent_pos, double* d_total_reward,
              const int32_t* d_spawnable, int32_t n_spawnable, const int32_t* d_placement, uint64_t seed,
              uint32_t tick, void* stream) {
+  return sb_reset_ex(w, d_grid, d_agent_pos, d_total_reward, d_spawnable, n_spawnable, d_placement, nullptr, 0,
+                     seed, tick, stream);
+}
+
+int sb_reset_ex(const SbWorldDesc* w, uint8_t* d_grid, int32_t* d_agent_pos, double* d_total_reward,
+                const int32_t* d_spawnable, int32_t n_spawnable, const int32_t* d_placement,
+                const SbItemGroup* item_groups, int32_t n_groups, uint64_t seed, uint32_t tick, void* stream) {
   SbDev d;
   int rc = make_dev(w, &d);
   if (rc) return rc;
   if (!d_grid || !d_agent_pos || !d_total_reward || !d_spawnable) return SB_EINVAL;
   if (n_spawnable < d.A) return SB_EINVAL;  // np.random.choice(replace=False) raises ValueError
   if (!aligned16(d_grid) || !aligned16(d.tmpl)) return SB_EALIGN;
+  if (n_groups < 0 || n_groups > SB_MAX_ITEM_GROUPS || (n_groups > 0 && !item_groups)) return SB_EINVAL;
+  ResetGroups groups;
+  memset(&groups, 0, sizeof(groups));
+  groups.n = n_groups;
+  for (int g = 0; g < n_groups; ++g) {
+    const SbItemGroup& ig = item_groups[g];
+    if (ig.kind < 0 || ig.kind >= d.K || ig.layer < 0 || ig.layer >= d.L || d.plane_of_layer[ig.layer] < 0)
+      return SB_EINVAL;
+    if (ig.count < 0 || ig.n_cells < ig.count || !ig.d_cells) return SB_EINVAL;  // choice(replace=False)
+    groups.kind[g] = ig.kind;
+    groups.plane[g] = d.plane_of_layer[ig.layer];
+    groups.count[g] = ig.count;
+    groups.n_cells[g] = ig.n_cells;
+    groups.cells[g] = ig.d_cells;
+    groups.placement[g] = ig.d_placement;
+  }
   const int epb = SB_THREADS / RESET_LPE;
   const unsigned blocks = (unsigned)(((long long)d.N + epb - 1) / epb);
   reset_kernel<<<blocks, SB_THREADS, 0, (cudaStream_t)stream>>>(d, d_grid, d_agent_pos, d_total_reward,
-                                                                d_spawnable, n_spawnable, d_placement, seed,
-                                                                tick);
+                                                                d_spawnable, n_spawnable, d_placement, groups,
+                                                                seed, tick);
   count_launch();
   if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
   return SB_OK;
@@ -442,6 +547,7 @@ int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t*
   if (sweeps && a->rng == SB_RNG_TAPE && (!a->d_spawn_u || !a->d_spawn_c)) return SB_EINVAL;
   if (a->rng != SB_RNG_TAPE && a->rng != SB_RNG_PHILOX && a->rng != SB_RNG_SPARSE) return SB_EINVAL;
   if (a->rng == SB_RNG_SPARSE && !d.sparse_ok) return SB_EINVAL;
+  if (w->uses_facing && !a->d_agent_facing) return SB_EINVAL;
   if (a->policy != SB_POLICY_TAPE && a->policy != SB_POLICY_UNIFORM) return SB_EINVAL;
   if (buf) {
     rc = check_buf(buf);

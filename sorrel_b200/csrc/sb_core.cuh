@@ -51,6 +51,24 @@ struct SbDev {
   uint64_t cdf[SB_SPARSE_KMAX];   // Binomial(env_stride, p) CDF in 0.64 fixed point
   const double* app;              // device [K][C]
   const uint8_t* tmpl;            // device [L][plane_stride]
+  // ---- column rules / facings / beams / positional code (ABI v2; examples/cleanup) ----
+  int32_t oh_size;    // C*S*S: the crop part of an observation row; obs_size = oh_size + obs_extra
+  int32_t obs_extra;  // floats appended from extra_tbl[cell]
+  const float* extra_tbl;
+  int32_t ext_rules;  // some kind carries a rule other than SB_RULE_SPAWN
+  int32_t ext_act;    // facings / beams / all-layer rewards / reward_count != 1
+  uint32_t draw_mask; // kinds whose rule consumes a uniform (SPAWN, SPAWN_TO)
+  uint8_t rule[SB_MAX_KINDS], rule_to[SB_MAX_KINDS];
+  int32_t rule_plane_off[SB_MAX_KINDS];  // BECOME_IF: byte offset of the tested plane
+  uint32_t rule_mask[SB_MAX_KINDS];
+  uint64_t thr53[SB_MAX_KINDS];  // ceil(prob * 2^53) per drawing kind
+  double prob[SB_MAX_KINDS];     // replay compares the recorded f64 uniform with this
+  int8_t act_facing[SB_MAX_ACTIONS];
+  uint8_t act_beam[SB_MAX_ACTIONS];
+  int32_t beam_plane, n_beam;
+  int8_t beam_dy[4][SB_MAX_BEAM_CELLS], beam_dx[4][SB_MAX_BEAM_CELLS];
+  uint32_t beam_block_mask;
+  int32_t reward_all, reward_count;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -167,6 +185,29 @@ SB_HD int sb_resolve_candidate(const SbDev& d, uint32_t env, uint32_t tick, uint
   return sb_resolve_spawn(d, env, tick, cell, r8 == d.hi8, rk);
 }
 
+// SB_RULE_SPAWN_TO under the counter-based stream: the same lazily evaluated 53-bit uniform, no choice draw.
+// `r8` is the cell's first-level byte; true = the cell spawns.
+SB_HD bool sb_bernoulli_hit(uint64_t thr53, uint32_t r8, uint32_t env, uint32_t tick, uint32_t cell,
+                            const uint32_t* __restrict__ rk) {
+  const uint32_t hi8 = (uint32_t)(thr53 >> 45);
+  if (r8 > hi8) return false;
+  if (r8 < hi8) return true;
+  const SbU4 w = sb_philox_rk(env, tick, cell, SB_DOM_CELL, rk);
+  const uint64_t refine = (((uint64_t)w.x << 13) | (uint64_t)(w.y >> 19)) & ((1ull << 45) - 1);
+  return refine < (thr53 & ((1ull << 45) - 1));
+}
+
+// Deterministic column rules (SB_RULE_BECOME_IF / SB_RULE_BECOME) for the cell at byte offset `cell` = plane
+// base + `off` of the instance image `genv`.  Returns the new kind, or -1 when the cell keeps its kind.
+SB_HD int sb_column_rule(const SbDev& d, const uint8_t* genv, uint32_t kind, uint32_t rule, int off) {
+  if (rule == SB_RULE_BECOME) return (int)d.rule_to[kind];
+  if (rule == SB_RULE_BECOME_IF) {
+    const uint32_t other = genv[d.rule_plane_off[kind] + off];
+    if (other < (uint32_t)SB_MAX_KINDS && ((d.rule_mask[kind] >> other) & 1u)) return (int)d.rule_to[kind];
+  }
+  return -1;
+}
+
 // Sparse sampling of the spawn field (SB_RNG_SPARSE).  K = number of table entries <= u.
 SB_HD int sb_sparse_count(const SbDev& d, uint64_t u) {
   int k = 0;
@@ -197,7 +238,7 @@ SB_HD uint32_t sb_simd_cand_chunk(uint32_t k0, uint32_t k1, uint32_t k2, uint32_
 // y<<16|x) and, when `writer`, the two grid cells.  `err` collects SB_ERR_* bits.
 // ------------------------------------------------------------------------------------------------
 SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action, bool writer,
-                         uint32_t& err) {
+                         uint32_t& err, bool all_layers = false) {
   int y = (int)(*yx >> 16), x = (int)(*yx & 0xFFFFu);
   int dy = 0, dx = 0;
   if ((unsigned)action < (unsigned)d.n_actions) {
@@ -218,6 +259,15 @@ SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action
     return 0.0f;
   }
   float reward = d.value[tk];  // reward = value of the entity at the target cell (agent.py:219-220)
+  if (all_layers) {  // sum over every layer of the target column (observe_all_layers, cleanup/agents.py:160-170)
+    reward = 0.0f;
+    for (int z = 0; z < d.L; ++z) {
+      const int pl = d.plane_of_layer[z];
+      const uint32_t k = pl >= 0 ? genv[pl * d.plane_stride + ny * d.W + nx] : d.tmpl[z * d.plane_stride + ny * d.W + nx];
+      if (k < (uint32_t)d.K) reward += d.value[k];
+      else err |= SB_ERR_BAD_KIND;
+    }
+  }
   if ((d.passable_mask >> tk) & 1u) {
     if (writer) {
       plane[ny * d.W + nx] = (uint8_t)d.agent_kind;  // target entity discarded, agent placed

@@ -60,7 +60,7 @@ __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, boo
   L.planes_off = L.q_off + round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
   L.plane_env = stage_planes(d) ? pad64mod128(d.env_stride) : 0;
   L.pos_off = L.planes_off + epb * L.plane_env;
-  L.stage_off = L.pos_off + round_up(epb * 8 * d.A, 16);
+  L.stage_off = L.pos_off + round_up(epb * 12 * d.A, 16);  // packed yx, action, facing per agent
   L.stage_env = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
   L.hits_off = L.stage_off + epb * L.stage_env;  // SB_RNG_SPARSE: accepted cells of the turn, u16[KMAX]
   L.total = L.hits_off + epb * SB_SPARSE_KMAX * 2;
@@ -113,10 +113,10 @@ SB_UNROLL(SB_SCATTER_UNROLL)
   }
   __syncwarp();
   if (dst) {
-    const int nvec = d.obs_size > head ? (d.obs_size - head) >> 2 : 0;
+    const int nvec = d.oh_size > head ? (d.oh_size - head) >> 2 : 0;
     const int etail = head + 4 * nvec + lane;
     if (NP1) {
-      if (lane < head && lane < d.obs_size) {
+      if (lane < head && lane < d.oh_size) {
         dst[lane] = __uint_as_float((uint32_t)stage16[off + lane] << 16);
         stage16[off + lane] = 0;
       }
@@ -128,13 +128,13 @@ SB_UNROLL(SB_COPY_UNROLL)
         st_f4(dst + head + 4 * qv, __uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
               __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
       }
-      if (etail < d.obs_size) {
+      if (etail < d.oh_size) {
         dst[etail] = __uint_as_float((uint32_t)stage16[off + etail] << 16);
         stage16[off + etail] = 0;
       }
     } else {
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane < head && lane < d.obs_size) {
+      if (lane < head && lane < d.oh_size) {
         dst[lane] = stage[off + lane];
         stage[off + lane] = 0.0f;
       }
@@ -145,7 +145,7 @@ SB_UNROLL(SB_COPY_UNROLL)
         s4[qv] = zero4;
         st_f4(dst + head + 4 * qv, v.x, v.y, v.z, v.w);
       }
-      if (etail < d.obs_size) {
+      if (etail < d.oh_size) {
         dst[etail] = stage[off + etail];
         stage[off + etail] = 0.0f;
       }
@@ -202,11 +202,15 @@ __global__ void __launch_bounds__(OBS_THREADS)
       emit_onehot_row<LANES, NP1>(d, genv, lut_ij, stage_raw, y, x, dst, lane);
       __syncwarp();
     } else if (valid) {
-      for (int e = lane; e < d.obs_size; e += LANES) {
+      for (int e = lane; e < d.oh_size; e += LANES) {
         const int c = e / d.SS;
         const uint32_t li = lut_ij[e - c * d.SS];
         dst[e] = (float)sb_obs_general(d, genv, d.tmpl, d.app, y, x, c, (int)(li >> 8), (int)(li & 255u));
       }
+    }
+    if (d.obs_extra && valid) {  // positional code of the agent's cell (CleanupObservation.observe)
+      const float* src = d.extra_tbl + (size_t)(y * d.W + x) * d.obs_extra;
+      for (int e = lane; e < d.obs_extra; e += LANES) dst[d.oh_size + e] = __ldg(src + e);
     }
     if (++a == d.A) {
       a = 0;
@@ -247,6 +251,9 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int EPB = SB_THREADS / LPE;
   constexpr int GPW = 32 / LPE;  // groups per warp
+  // facings / beams / positional code are compiled only into the replay and generic variants: a world that
+  // uses them never takes the byte-SIMD or sparse fast paths (make_dev clears simd_sweep / sparse_ok)
+  constexpr bool EXT = RNG == SB_K_TAPE || RNG == SB_K_PHILOX_GENERIC;
   const int tid = threadIdx.x;
   const int lane = tid & (LPE - 1);
   const int grp = tid / LPE;
@@ -264,8 +271,9 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   const int esz = p.staged ? p.plane_env : d.env_stride;
   uint8_t* envs = p.staged ? smem_raw + p.planes_off : p.grid + (size_t)env0 * d.env_stride;
   uint8_t* genv = envs + (size_t)grp * esz;
-  uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * 2 * d.A;
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * 3 * d.A;
   int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
+  int32_t* sfacing = sact + d.A;  // MovingAgent.direction (only read when d.ext_act)
   uint8_t* stage_raw = smem_raw + p.stage_off + grp * p.stage_env;
 
   for (int ij = tid; ij < d.SS; ij += SB_THREADS) {
@@ -293,11 +301,12 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       int pos = p.agent_pos[(size_t)env * d.A + a];
       int y = pos / d.W;
       spos[a] = ((uint32_t)y << 16) | (uint32_t)(pos - y * d.W);
+      if (EXT) sfacing[a] = p.a.d_agent_facing ? p.a.d_agent_facing[(size_t)env * d.A + a] : 2;
     }
   } else {  // lanes past the last instance: never touch a grid (every access below is guarded by `active`)
     if (p.staged)
       for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    for (int a = lane; a < d.A; a += LPE) spos[a] = 0;
+    for (int a = lane; a < d.A; a += LPE) spos[a] = 0, sfacing[a] = 0;
   }
   double total = (active && lane == 0 && p.write_back) ? p.total_reward[env] : 0.0;
   uint32_t err = 0;
@@ -333,28 +342,43 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
     // ---- entity sweep ----------------------------------------------------------------------
     if (fused || p.a.do_sweep) {
       if (RNG == SB_K_TAPE) {
+        // Replay, all rule types.  Planes in ascending layer order with a warp barrier in between: a column
+        // rule then sees lower layers after and higher layers before their own transition of this turn,
+        // like the C-order sweep of environment.py:88-91 (rules only read their own column).
         const double* tu = p.a.d_spawn_u + ((size_t)t * d.N + (active ? env : 0)) * tape_stride;
         const uint8_t* tc = p.a.d_spawn_c + ((size_t)t * d.N + (active ? env : 0)) * tape_stride;
         uint8_t* drew = p.a.d_drew_out ? p.a.d_drew_out + ((size_t)t * d.N + (active ? env : 0)) * tape_stride
                                        : nullptr;
-        if (active) {
-          for (int cell = lane; cell < d.env_stride; cell += LPE) {
-            uint32_t kind = genv[cell];
-            double u = tu[cell];
-            bool has_rule = kind < (uint32_t)SB_MAX_KINDS && ((d.spawn_mask >> kind) & 1u);
-            if (drew) drew[cell] = has_rule ? 1 : 0;
-            if (has_rule) {
+        for (int pl = 0; pl < d.n_planes; ++pl) {
+          const int base = pl * d.plane_stride;
+          for (int off = lane; off < d.plane_stride && active; off += LPE) {
+            const int cell = base + off;
+            const uint32_t kind = genv[cell];
+            const uint32_t rule = kind < (uint32_t)SB_MAX_KINDS ? d.rule[kind] : (uint32_t)SB_RULE_NONE;
+            const bool draws = rule == SB_RULE_SPAWN || rule == SB_RULE_SPAWN_TO;
+            const double u = tu[cell];
+            if (drew) drew[cell] = draws ? 1 : 0;
+            if (draws) {
               if (u != u) {
                 err |= SB_ERR_TAPE_ALIGN;  // the reference drew here, the tape did not
-              } else if (u < d.p) {        // np.random.random() < world.spawn_prob, entities.py:72-74
-                uint32_t ci = tc[cell];
-                if (ci < (uint32_t)d.n_choices) genv[cell] = (uint8_t)((d.choices_packed >> (8 * ci)) & 0xFF);
-                else err |= SB_ERR_TAPE_ALIGN;
+              } else if (u < d.prob[kind]) {  // np.random.random() < prob (entities.py:72-74, cleanup/entities.py:52,86)
+                if (rule == SB_RULE_SPAWN) {
+                  const uint32_t ci = tc[cell];
+                  if (ci < (uint32_t)d.n_choices) genv[cell] = (uint8_t)((d.choices_packed >> (8 * ci)) & 0xFF);
+                  else err |= SB_ERR_TAPE_ALIGN;
+                } else {
+                  genv[cell] = d.rule_to[kind];
+                }
               }
-            } else if (u == u) {
-              err |= SB_ERR_TAPE_ALIGN;  // tape holds a draw for a cell that has no rule
+            } else {
+              if (u == u) err |= SB_ERR_TAPE_ALIGN;  // tape holds a draw for a cell that has no drawing rule
+              if (rule != SB_RULE_NONE) {
+                const int nk = sb_column_rule(d, genv, kind, rule, off);
+                if (nk >= 0) genv[cell] = (uint8_t)nk;
+              }
             }
           }
+          __syncwarp();
         }
       } else if (RNG == SB_K_PHILOX_SIMD) {
         // First level, byte-SIMD: one Philox call covers the 16 cells of a chunk; cells whose
@@ -431,18 +455,39 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           accepted = __shfl_sync(0xFFFFFFFFu, accepted, 0, LPE);
           base += LPE;
         }
-      } else {  // SB_K_PHILOX_GENERIC: several spawning kinds or a large probability
-        for (int c = lane; c < d.n_chunks && active; c += LPE) {
-          SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
-          for (int b = 0; b < 16; ++b) {
-            uint32_t cell = (uint32_t)(c * 16 + b);
-            uint32_t kind = genv[cell];
-            if (kind >= (uint32_t)SB_MAX_KINDS || !((d.spawn_mask >> kind) & 1u)) continue;
-            uint32_t r8 = sb_byte_of(r, b);
-            if (r8 > d.hi8) continue;
-            int nk = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, rk);
-            if (nk >= 0) genv[cell] = (uint8_t)nk;
+      } else {  // SB_K_PHILOX_GENERIC: several spawning kinds, a large probability, or column rules
+        const int cpp = d.plane_stride / 16;
+        for (int pl = 0; pl < d.n_planes; ++pl) {
+          for (int cc = lane; cc < cpp && active; cc += LPE) {
+            const int c = pl * cpp + cc;
+            bool have_r = false;
+            SbU4 r;
+            for (int b = 0; b < 16; ++b) {
+              const uint32_t cell = (uint32_t)(c * 16 + b);
+              const uint32_t kind = genv[cell];
+              if (kind >= (uint32_t)SB_MAX_KINDS) continue;
+              const uint32_t rule = d.rule[kind];
+              if (rule == SB_RULE_NONE) continue;
+              if (rule == SB_RULE_SPAWN || rule == SB_RULE_SPAWN_TO) {
+                if (!have_r) {
+                  r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
+                  have_r = true;
+                }
+                const uint32_t r8 = sb_byte_of(r, b);
+                if (rule == SB_RULE_SPAWN) {
+                  if (r8 > d.hi8) continue;
+                  const int nk = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, rk);
+                  if (nk >= 0) genv[cell] = (uint8_t)nk;
+                } else if (sb_bernoulli_hit(d.thr53[kind], r8, envid, tick, cell, rk)) {
+                  genv[cell] = d.rule_to[kind];
+                }
+              } else {
+                const int nk = sb_column_rule(d, genv, kind, rule, cc * 16 + b);
+                if (nk >= 0) genv[cell] = (uint8_t)nk;
+              }
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -464,7 +509,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           emit_onehot_row<LPE, NP1>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
         }
       } else if (active) {
-        for (int e = lane; e < d.obs_size; e += LPE) {
+        for (int e = lane; e < d.oh_size; e += LPE) {
           const int c = e / d.SS;
           const uint32_t li = lut_ij[e - c * d.SS];
           float vf = (float)sb_obs_general(d, genv, d.tmpl, d.app, y, x, c, (int)(li >> 8), (int)(li & 255u));
@@ -472,15 +517,48 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           if (dsts[1]) dsts[1][e] = vf;
         }
       }
+      if (EXT && d.obs_extra && active) {  // positional code of the agent's cell (CleanupObservation.observe)
+        const float* src = d.extra_tbl + (size_t)(y * d.W + x) * d.obs_extra;
+        for (int e = lane; e < d.obs_extra; e += LPE) {
+          const float vf = __ldg(src + e);
+          if (dsts[0]) dsts[0][d.oh_size + e] = vf;
+          if (dsts[1]) dsts[1][d.oh_size + e] = vf;
+        }
+      }
     };
 
     auto act = [&](int a) {
+      if (EXT && d.ext_act) {
+        // MovingAgent.movement sets the facing (agents/agent.py:199-211); beam actions then replace every
+        // in-map, non-blocked cell of the beam pattern on the beam layer (CleanupAgent.spawn_beam,
+        // cleanup/agents.py:93-145) BEFORE the reward is read (agents.py:158-170).  Lanes share the cells.
+        const int action = sact[a];
+        const bool ok = (unsigned)action < (unsigned)d.n_actions;
+        int facing = sfacing[a] & 3;
+        if (ok && d.act_facing[action] >= 0) facing = d.act_facing[action];
+        const uint32_t bk = ok ? (uint32_t)d.act_beam[action] : (uint32_t)SB_NO_KIND;
+        if (active && bk != (uint32_t)SB_NO_KIND) {
+          const uint32_t yx0 = spos[a];
+          const int y0 = (int)(yx0 >> 16), x0 = (int)(yx0 & 0xFFFFu);
+          uint8_t* bp = genv + d.beam_plane * d.plane_stride;
+          for (int b = lane; b < d.n_beam; b += LPE) {
+            const int yy = y0 + d.beam_dy[facing][b], xx = x0 + d.beam_dx[facing][b];
+            if ((unsigned)yy < (unsigned)d.H && (unsigned)xx < (unsigned)d.W) {  // world.valid_location
+              const uint32_t k = bp[yy * d.W + xx];
+              if (!(k < (uint32_t)SB_MAX_KINDS && ((d.beam_block_mask >> k) & 1u))) bp[yy * d.W + xx] = (uint8_t)bk;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) sfacing[a] = facing;
+      }
       if (lane == 0 && active) {
         uint32_t yx = spos[a];
         const int action = sact[a];
-        float reward = sb_agent_act(d, genv, &yx, action, true, err);
+        float reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all);
         spos[a] = yx;
-        total += (double)reward;  // world.total_reward += reward, agent.py:172
+        // world.total_reward += reward (agent.py:172; cleanup adds it twice: cleanup/agents.py:172)
+        total += (double)(EXT ? reward * (float)d.reward_count : reward);
         if (active) {
           const size_t row = row0 + a;
           if (p.has_buf) {
@@ -533,6 +611,8 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       uint32_t yx = spos[a];
       p.agent_pos[(size_t)env * d.A + a] = (int32_t)((yx >> 16) * d.W + (yx & 0xFFFFu));
     }
+    if (EXT && p.a.d_agent_facing)
+      for (int a = lane; a < d.A; a += LPE) p.a.d_agent_facing[(size_t)env * d.A + a] = sfacing[a];
     if (lane == 0) p.total_reward[env] = total;
   }
   if (active && err && p.a.d_error) atomicOr(p.a.d_error, err);

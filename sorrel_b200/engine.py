@@ -51,6 +51,21 @@ class WorldSpec:
         default_factory=lambda: [MOVE_DELTAS[a] for a in ("up", "down", "left", "right")])
     dynamic_layers: list[int] | None = None  # default: every layer holding a non-static kind
     obs_transform: int = 0  # _abi.SB_OBS_SUM (one-hot / raw sums) or _abi.SB_OBS_RGB
+    # ---- column rules, facings + beams, all-layer rewards, positional code (examples/cleanup) ----
+    kind_rule_prob: list[float] | None = None  # SB_RULE_SPAWN_TO probability per kind
+    kind_rule_to: list[int] | None = None  # resulting kind of SPAWN_TO / BECOME_IF / BECOME
+    kind_rule_layer: list[int] | None = None  # BECOME_IF: layer of the same column that is tested
+    kind_rule_mask: list[int] | None = None  # BECOME_IF: bit j set <=> kind j satisfies the test
+    action_facing: list[int] | None = None  # facing 0 N, 1 E, 2 S, 3 W an action sets; -1 unchanged
+    action_beam_kind: list[int] | None = None  # kind an action's beam places; SB_NO_KIND = none
+    beam_layer: int = -1
+    beam_offsets: np.ndarray | None = None  # [4, n, 2] (dy, dx) per facing
+    beam_block_mask: int = 0
+    reward_all_layers: bool = False
+    reward_count: int = 1
+    initial_facing: int = 2  # MovingAgent.direction default (agents/agent.py:185)
+    obs_extra: np.ndarray | None = None  # [H, W, E] appended to the flattened crop (positional code)
+    item_groups: list = field(default_factory=list)  # (kind, layer, count, cells[n, 2]) placed at reset, in order
 
     @property
     def channels(self) -> int:
@@ -61,13 +76,23 @@ class WorldSpec:
         return 2 * self.vision + 1
 
     @property
-    def obs_size(self) -> int:
+    def onehot_size(self) -> int:
         return self.channels * self.obs_side ** 2
+
+    @property
+    def obs_size(self) -> int:
+        return self.onehot_size + (0 if self.obs_extra is None else int(self.obs_extra.shape[2]))
+
+    @property
+    def uses_facing(self) -> bool:
+        return self.action_facing is not None or self.action_beam_kind is not None
 
     def resolved_dynamic_layers(self) -> list[int]:
         if self.dynamic_layers is not None:
             return sorted(self.dynamic_layers)
         dyn = {self.agent_layer}
+        if self.beam_layer >= 0:
+            dyn.add(self.beam_layer)
         for z in range(self.layers):
             kinds = np.unique(self.template[:, :, z])
             if any(self.kind_rule[k] != _abi.SB_RULE_NONE for k in kinds):
@@ -150,6 +175,18 @@ class Engine:
         self.agent_pos = torch.zeros((self.N, self.A), dtype=torch.int32, device=self.device)
         self.total_reward = torch.zeros(self.N, dtype=torch.float64, device=self.device)
         self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # MovingAgent.direction of every agent: set at construction, NOT reset by Environment.reset
+        self.agent_facing = torch.full((self.N, self.A), int(spec.initial_facing), dtype=torch.int32,
+                                       device=self.device) if spec.uses_facing else None
+        self.d_obs_extra = None
+        if spec.obs_extra is not None:  # f64 -> f32 exactly like `Buffer.states[idx] = obs` (buffers.py:56)
+            ex = np.ascontiguousarray(spec.obs_extra, dtype=np.float64).reshape(H * W, -1).astype(np.float32)
+            self.d_obs_extra = torch.from_numpy(ex).to(self.device)
+        self.item_groups = []  # (kind, layer, count, device cells)
+        for kind, layer, count, cells in spec.item_groups:
+            cells = np.asarray(cells)
+            flat = (cells[:, 0] * W + cells[:, 1]).astype(np.int32)
+            self.item_groups.append((int(kind), int(layer), int(count), torch.from_numpy(flat).to(self.device)))
 
         d = SbWorldDesc()
         d.abi_version = _abi.SB_ABI_VERSION
@@ -180,6 +217,32 @@ class Engine:
         d.d_template = self.d_template.data_ptr()
         d.static_layers_invisible = 1 if invisible else 0
         d.obs_transform = int(spec.obs_transform)
+        K = min(len(spec.kind_names), _abi.SB_MAX_KINDS)
+        for k in range(K):
+            d.kind_rule_prob[k] = float(spec.kind_rule_prob[k]) if spec.kind_rule_prob else 0.0
+            d.kind_rule_to[k] = int(spec.kind_rule_to[k]) if spec.kind_rule_to else _abi.SB_NO_KIND
+            d.kind_rule_layer[k] = int(spec.kind_rule_layer[k]) if spec.kind_rule_layer else -1
+            d.kind_rule_mask[k] = int(spec.kind_rule_mask[k]) if spec.kind_rule_mask else 0
+        d.uses_facing = 1 if spec.uses_facing else 0
+        for i in range(_abi.SB_MAX_ACTIONS):
+            d.action_facing[i] = int(spec.action_facing[i]) if spec.action_facing and i < len(spec.action_facing) else -1
+            d.action_beam_kind[i] = int(spec.action_beam_kind[i]) \
+                if spec.action_beam_kind and i < len(spec.action_beam_kind) else _abi.SB_NO_KIND
+        d.beam_layer = int(spec.beam_layer)
+        if spec.beam_offsets is not None:
+            bo = np.asarray(spec.beam_offsets)
+            if bo.shape[0] != 4 or bo.shape[1] > _abi.SB_MAX_BEAM_CELLS:
+                raise ValueError("beam_offsets must be [4, n <= SB_MAX_BEAM_CELLS, 2]")
+            d.num_beam_cells = int(bo.shape[1])
+            for f in range(4):
+                for b in range(bo.shape[1]):
+                    d.beam_dy[f][b], d.beam_dx[f][b] = int(bo[f, b, 0]), int(bo[f, b, 1])
+        d.beam_block_mask = int(spec.beam_block_mask)
+        d.reward_all_layers = 1 if spec.reward_all_layers else 0
+        d.reward_count = int(spec.reward_count)
+        if self.d_obs_extra is not None:
+            d.obs_extra = int(self.d_obs_extra.shape[1])
+            d.d_obs_extra = self.d_obs_extra.data_ptr()
         cdf = binomial_cdf_u64(self.env_stride, spec.spawn_prob) if self.env_stride < 65536 else None
         self.sparse_available = cdf is not None
         if cdf is not None:
@@ -193,17 +256,30 @@ class Engine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def reset(self, placement: torch.Tensor | None = None) -> None:
-        """Environment.reset (environment.py:72-79): template copy + agent placement.
+    def reset(self, placement: torch.Tensor | None = None, item_placement=None) -> None:
+        """Environment.reset (environment.py:72-79): template copy, item groups, agent placement.
 
         placement: int32 [N, A] indices into the spawnable list (a replayed
-        `np.random.choice(len(valid), size=A, replace=False)`), or None to draw in-kernel."""
+        `np.random.choice(len(valid), size=A, replace=False)`), or None to draw in-kernel.
+        item_placement: one int32 [N, count] tensor per item group (replayed), or None."""
         if placement is not None:
             placement = placement.to(device=self.device, dtype=torch.int32).contiguous()
             assert placement.shape == (self.N, self.A)
-        check(self.lib.sb_reset(C.byref(self.desc), self.grid.data_ptr(), self.agent_pos.data_ptr(),
-                                self.total_reward.data_ptr(), self.d_spawnable.data_ptr(), self.n_spawnable,
-                                _ptr(placement), self.seed, self.tick + 1, self._stream()), "sb_reset")
+        groups = (_abi.SbItemGroup * max(1, len(self.item_groups)))()
+        keep = []
+        for g, (kind, layer, count, cells) in enumerate(self.item_groups):
+            groups[g].kind, groups[g].layer, groups[g].count, groups[g].n_cells = kind, layer, count, int(cells.numel())
+            groups[g].d_cells = cells.data_ptr()
+            if item_placement is not None:
+                ip = item_placement[g].to(device=self.device, dtype=torch.int32).contiguous()
+                assert ip.shape == (self.N, count)
+                keep.append(ip)
+                groups[g].d_placement = ip.data_ptr()
+        check(self.lib.sb_reset_ex(C.byref(self.desc), self.grid.data_ptr(), self.agent_pos.data_ptr(),
+                                   self.total_reward.data_ptr(), self.d_spawnable.data_ptr(), self.n_spawnable,
+                                   _ptr(placement), groups, len(self.item_groups), self.seed, self.tick + 1,
+                                   self._stream()), "sb_reset")
+        self._keep = (placement, keep)  # the launch is asynchronous: keep the tapes alive until the next call
 
     def step(self, num_turns: int = 1, *, buffer=None, actions: torch.Tensor | None = None,
              spawn_u: torch.Tensor | None = None, spawn_c: torch.Tensor | None = None,
@@ -283,13 +359,15 @@ class Engine:
         a.d_action_out = chk(action_out, (T, N, A), torch.int32, "action_out")
         a.d_drew_out = chk(drew_out, (T, N, ES), torch.uint8, "drew_out")
         a.d_error = self.error.data_ptr()
+        a.d_agent_facing = _ptr(self.agent_facing)
 
     def observe(self, out: torch.Tensor | None = None) -> torch.Tensor:
         """ObservationSpec.observe for every (instance, agent): float32 [N, A, C, S, S]."""
         s = self.spec
         if out is None:
-            out = torch.empty((self.N, self.A, s.channels, s.obs_side, s.obs_side), dtype=torch.float32,
-                              device=self.device)
+            shape = (self.N, self.A, s.channels, s.obs_side, s.obs_side) if s.obs_extra is None \
+                else (self.N, self.A, s.obs_size)  # crop flattened + positional code
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
         check(self.lib.sb_observe(C.byref(self.desc), self.grid.data_ptr(), self.agent_pos.data_ptr(),
                                   out.data_ptr(), self._stream()), "sb_observe")
         return out

@@ -34,6 +34,7 @@ class StepGraph:
         a.act_agent = a.obs_agent = -1
         a.d_error = engine.error.data_ptr()
         a.d_clock = self.clock.data_ptr()
+        a.d_agent_facing = None if engine.agent_facing is None else engine.agent_facing.data_ptr()
         self.sample = None
         if self.B:
             F, obs = buffer.n_frames, buffer.obs_size

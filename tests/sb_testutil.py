@@ -54,6 +54,12 @@ def engine_spec(o: R.WorldSpec):
         spawn_prob=o.spawn_prob, spawn_choices=list(o.spawn_choices),
         dynamic_layers=list(o.dynamic_layers) if o.dynamic_layers else None,
         obs_transform=int(getattr(o, "obs_transform", 0)),
+        action_deltas=[tuple(d) for d in o.action_deltas],
+        kind_rule_prob=o.kind_rule_prob, kind_rule_to=o.kind_rule_to, kind_rule_layer=o.kind_rule_layer,
+        kind_rule_mask=o.kind_rule_mask, action_facing=o.action_facing, action_beam_kind=o.action_beam_kind,
+        beam_layer=o.beam_layer, beam_offsets=o.beam_offsets, beam_block_mask=o.beam_block_mask,
+        reward_all_layers=o.reward_all_layers, reward_count=o.reward_count, initial_facing=o.initial_facing,
+        obs_extra=o.obs_extra, item_groups=list(o.item_groups),
     )
 
 

@@ -1,0 +1,141 @@
+"""GPU parity for the cleanup rule set: column rules, beams with a one-turn lifetime,
+facings, all-layer rewards and the one-hot crop + positional code, through the C ABI.
+
+Replay mode is compared with fixtures generated from the unmodified reference (oracle/gen_golden.py
+cleanup); the counter-based mode with the oracle restatement running the same Philox stream."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+import sb_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(spec, n, device, **kw):
+    from sorrel_b200.engine import Engine
+
+    return Engine(util.engine_spec(spec), n, device=device, **kw)
+
+
+def _buffer(spec, n, capacity, device, n_frames=1):
+    from sorrel_b200.buffers import Buffer
+
+    return Buffer(capacity, (spec.obs_size,), n_frames=n_frames, rows=n * spec.num_agents, device=device,
+                  positions=(2,))
+
+
+def _episode_tapes(spec, tapes, device):
+    u, c = util.pad_tapes(spec, tapes)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(device)  # noqa: E731
+    return (dev(u[:, None]), dev(c[:, None]), dev(tapes["actions"][:, None]),
+            dev(tapes["placement"].astype(np.int32)[None]),
+            [dev(ip.astype(np.int32)[None]) for ip in tapes["item_placement"]])
+
+
+@pytest.mark.parametrize("name", util.cleanup_cases())
+@pytest.mark.parametrize("fused", [False, True])
+def test_cleanup_golden_replay(name, fused, cuda_device):
+    """Replayed numpy draws: every turn's grid (beam ages included), facings, total reward and all buffer
+    arrays equal the reference's, one launch per turn and with the whole episode fused into one launch."""
+    g = util.load_golden(name)
+    spec = util.cleanup_spec_from_golden(g)
+    T, E, A, F = int(g["T"]), int(g["epochs"]), int(g["A"]), int(g["n_frames"])
+    oenv = R.OracleEnv(spec, R.NumpyDraws(int(g["seed"])), capacity=int(g["capacity"]), n_frames=F, record_tapes=True)
+    eng = _engine(spec, 1, cuda_device)
+    buf = _buffer(spec, 1, int(g["capacity"]), cuda_device, n_frames=F)
+    gi = 0
+    for ep in range(E):
+        oenv.tapes.update({"spawn_u": [], "spawn_c": [], "actions": []})
+        oenv.reset()
+        for _ in range(T):
+            oenv.take_turn()
+        spawn_u, spawn_c, actions, placement, item_pl = _episode_tapes(spec, oenv.dense_tapes(), cuda_device)
+        eng.reset(placement, item_placement=item_pl)
+        if F > 1:
+            buf.add_empty()
+        np.testing.assert_array_equal(eng.agent_yx()[0], g["starts"][ep])
+        np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi], err_msg="after reset")
+        gi += 1
+        if fused:
+            eng.step(T, buffer=buf, actions=actions, spawn_u=spawn_u, spawn_c=spawn_c)
+            gi += T
+            np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi - 1])
+        else:
+            drew = torch.zeros((1, 1, eng.env_stride), dtype=torch.uint8, device=cuda_device)
+            for t in range(T):
+                eng.step(1, buffer=buf, actions=actions[t:t + 1].contiguous(), spawn_u=spawn_u[t:t + 1].contiguous(),
+                         spawn_c=spawn_c[t:t + 1].contiguous(), drew_out=drew)
+                np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+                np.testing.assert_array_equal(eng.agent_facing.cpu().numpy()[0], g["facings"][ep * T + t])
+                np.testing.assert_array_equal(drew.cpu().numpy()[0, 0] == 1, ~np.isnan(spawn_u[t, 0].cpu().numpy()))
+                gi += 1
+        eng.check_errors()
+        assert float(eng.total_reward[0]) == float(g["total_reward"][ep])
+        np.testing.assert_array_equal(eng.agent_facing.cpu().numpy()[0], g["facings"][(ep + 1) * T - 1])
+    for a in range(A):
+        row = buf.row(a)
+        for key in ("states", "actions", "rewards", "dones", "positions"):
+            assert row[key].dtype == g[key].dtype
+            np.testing.assert_array_equal(row[key], g[key][a], err_msg=f"{key} agent {a}")
+
+
+def test_cleanup_philox_batch(cuda_device):
+    """Counter-based mode (in-kernel item / agent placement, Bernoulli draws, uniform policy): many instances
+    against the oracle restatement on the same stream, including a second episode (facings persist)."""
+    spec = R.cleanup_spec(13, 17, 5, 3, initial_apples=6, apple_spawn_chance=0.03, pollution_spawn_chance=0.06,
+                          beam_radius=2)
+    N, T, seed, base = 40, 24, 99, 1000
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    buf = _buffer(spec, N, 2 * T, cuda_device)
+    oenvs = [R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=base + n, capacity=2 * T) for n in range(0, N, 9)]
+    for ep in range(2):
+        eng.reset()
+        for o in oenvs:
+            o.reset()
+        if ep == 0:
+            grids = eng.grid_numpy()
+            for i, n in enumerate(range(0, N, 9)):
+                np.testing.assert_array_equal(grids[n], oenvs[i].grid, err_msg=f"reset, instance {n}")
+        eng.step(T // 2, buffer=buf)  # two launches per episode: state carried through global memory
+        eng.step(T - T // 2, buffer=buf)
+        for o in oenvs:
+            for _ in range(T):
+                o.take_turn()
+        eng.check_errors()
+        grids, tot = eng.grid_numpy(), eng.total_reward.cpu().numpy()
+        for i, n in enumerate(range(0, N, 9)):
+            np.testing.assert_array_equal(grids[n], oenvs[i].grid, err_msg=f"episode {ep}, instance {n}")
+            assert tot[n] == oenvs[i].total_reward
+            np.testing.assert_array_equal(eng.agent_facing.cpu().numpy()[n], oenvs[i].facing)
+    for i, n in enumerate(range(0, N, 9)):
+        for a in range(spec.num_agents):
+            row, ob = buf.row(n * spec.num_agents + a), oenvs[i].buffers[a]
+            np.testing.assert_array_equal(row["states"], ob.states)
+            np.testing.assert_array_equal(row["actions"], ob.actions)
+            np.testing.assert_array_equal(row["rewards"], ob.rewards)
+            np.testing.assert_array_equal(row["positions"], ob.positions)
+
+
+def test_cleanup_observe_standalone(cuda_device):
+    """sb_observe on a cleanup world == the rows the fused step wrote (crop + positional code)."""
+    spec = R.cleanup_spec(21, 31, 10, 5)
+    N = 6
+    eng = _engine(spec, N, cuda_device, seed=5)
+    buf = _buffer(spec, N, 4, cuda_device)
+    eng.reset()
+    eng.step(3, buffer=buf)
+    obs = eng.observe()  # state after 3 turns
+    assert tuple(obs.shape) == (N, spec.num_agents, spec.obs_size)
+    oenv = R.OracleEnv(spec, R.PhiloxDraws(5), env_id=2, capacity=4)
+    oenv.reset()
+    for _ in range(3):
+        oenv.take_turn()
+    for a in range(spec.num_agents):
+        y, x = oenv.pos[a]
+        want = np.concatenate((R.observe(spec, oenv.grid, y, x).reshape(-1), spec.obs_extra[y, x])).astype(np.float32)
+        np.testing.assert_array_equal(obs[2, a].cpu().numpy(), want)
+    eng.check_errors()
