@@ -63,4 +63,17 @@ class Agent(Entity):
 
 
 class MovingAgent(Agent):
-    """agent.py:176-225: up/down/left/right decode lives in the kernel (ActionSpec order)."""
+    """agent.py:176-225: up/down/left/right decode lives in the kernel (ActionSpec order).
+
+    `direction` (agent.py:185) is the facing every instance's agent starts with; the kernels update the
+    per-instance facings when a movement action is taken (`Engine.agent_facing`)."""
+
+    direction = 2  # default: facing down
+    #: reward = sum of Entity.value over all layers of the target column (cleanup/agents.py:160-170)
+    reward_all_layers = False
+    #: times the reward is added to world.total_reward per agent turn (agent.py:172; cleanup adds it twice)
+    reward_count = 1
+
+    def action_effects(self, world) -> dict:
+        """Non-movement actions: action name -> effect from sorrel_b200.rules (e.g. SpawnBeam)."""
+        return {}

@@ -42,6 +42,7 @@ class Environment:
         self.world.create_world()
         self.stop_if_done = stop_if_done
         self._spawnable = None
+        self._item_groups = []
         self.setup_agents()
         self.populate_environment()
         self._compile()
@@ -62,6 +63,12 @@ class Environment:
         the device at each reset."""
         self._spawnable = np.asarray([tuple(loc) for loc in valid_spawn_locations], dtype=np.int64).reshape(-1, 3)
 
+    def place_items(self, entity, valid_locations, count: int) -> None:
+        """Batched stand-in for `np.random.choice(len(points), size=count, replace=False)` + `world.add(loc,
+        entity)` (examples/cleanup/env.py:126-132): every instance draws its own `count` distinct cells at
+        each reset, before the agents are placed.  Call in the order the reference places the groups."""
+        self._item_groups.append((entity, [tuple(loc) for loc in valid_locations], int(count)))
+
     # -- engine wiring ---------------------------------------------------------------------------
     def _compile(self) -> None:
         if self._spawnable is None:
@@ -72,7 +79,7 @@ class Environment:
             if type(ag) is not type(a0) or ag.kind_key() != a0.kind_key():
                 raise ValueError("all agent slots must be of one Agent class (one kind-table row)")
         A = len(self.agents)
-        eng = self.world.compile(a0, a0.observation_spec, a0.action_spec, A, self._spawnable)
+        eng = self.world.compile(a0, a0.observation_spec, a0.action_spec, A, self._spawnable, self._item_groups)
         model = a0.model
         cap = int(getattr(model, "memory_size", 0) or self.config.get("engine", {}).get("buffer_capacity", 1024))
         n_frames = int(getattr(model, "n_frames", 1))

@@ -125,3 +125,20 @@ class RGBObservationSpec(ObservationSpec):
         if location is None:
             return world.engine.observe()
         return world.observe_from(location)
+
+
+def positional_embedding(location, world, scale: tuple[int, int]) -> np.ndarray:
+    """sorrel/observation/embedding.py:8-44: sin/cos code of a (row, column) location at `scale[0]` octaves
+    per axis (the reference uses scale[0] for both loops).  float64, like the reference."""
+    x, y = location[0:2]
+    grid_size = (world.height, world.width)
+    embedding = []
+    for i in range(scale[0]):
+        freq_x = 2 * np.pi * (2**i) / grid_size[0]
+        embedding.append(np.sin(freq_x * x))
+        embedding.append(np.cos(freq_x * x))
+    for j in range(scale[0]):
+        freq_y = 2 * np.pi * (2**j) / grid_size[1]
+        embedding.append(np.sin(freq_y * y))
+        embedding.append(np.cos(freq_y * y))
+    return np.array(embedding)

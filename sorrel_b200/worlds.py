@@ -15,7 +15,8 @@ import torch
 from . import _abi
 from .engine import MOVE_DELTAS, Engine, WorldSpec
 from .entities import Entity
-from .rules import BernoulliSpawn
+from .rules import (MOVE_FACING, BecomeIfLayer, BernoulliBecome, BernoulliSpawn, ExpireAfter, SpawnBeam,
+                    beam_pattern)
 
 
 class Gridworld:
@@ -100,39 +101,69 @@ class Gridworld:
     # compilation: object template -> kind table + uint8 template -> device instances
     # ------------------------------------------------------------------------------------------
     def build_spec(self, agent_proto: Entity, observation_spec, action_spec, num_agents: int,
-                   spawnable) -> WorldSpec:
-        """Pure host logic (no CUDA): derive the kind table from the entity prototypes."""
+                   spawnable, item_groups=()) -> WorldSpec:
+        """Pure host logic (no CUDA): derive the kind table from the entity prototypes.
+
+        A kind-table row is (class, value, passable, age); `age` > 0 only for classes whose rule is
+        `ExpireAfter` (the per-entity turn counter of the reference becomes part of the kind id)."""
         entity_list = list(getattr(observation_spec, "entity_list", []))
         protos: dict[tuple, Entity] = {}
+        pending: list[Entity] = []
 
         def note(e: Entity):
-            protos.setdefault(e.kind_key(), e)
+            key = e.kind_key() + (0,)
+            if key not in protos:
+                protos[key] = e
+                pending.append(e)
+            return key
 
         note(self.default_entity)
         for _, e in np.ndenumerate(self.map):
             note(e)
         note(agent_proto)
-        rules = {}
-        for key, e in list(protos.items()):
+        for ent, _, _ in item_groups:
+            note(ent)
+        effects = dict(agent_proto.action_effects(self)) if hasattr(agent_proto, "action_effects") else {}
+        for eff in effects.values():
+            if not isinstance(eff, SpawnBeam):
+                raise ValueError(f"unsupported action effect {eff!r}")
+            note(eff.entity)
+        # transitive closure over everything a rule can produce
+        rules: dict[tuple, object] = {}
+        while pending:
+            e = pending.pop()
+            if e is agent_proto:
+                continue  # `not isinstance(x, Agent)`: agents are not swept (environment.py:90)
             rule = e.transition_rule(self)
-            if rule is not None:
-                if not isinstance(rule, BernoulliSpawn):
-                    raise ValueError(f"{e.kind}: unsupported transition rule {rule!r}")
-                rules[key] = rule
+            if rule is None:
+                continue
+            key = e.kind_key() + (0,)
+            rules[key] = rule
+            if isinstance(rule, BernoulliSpawn):
                 for c in rule.choices:
                     note(c)
-        distinct = {(r.prob, tuple(c.kind_key() for c in r.choices)) for r in rules.values()}
-        if len(distinct) > 1:
+            elif isinstance(rule, (BernoulliBecome, BecomeIfLayer, ExpireAfter)):
+                note(rule.to)
+            else:
+                raise ValueError(f"{e.kind}: unsupported transition rule {rule!r}")
+        spawn_rules = {(r.prob, tuple(c.kind_key() for c in r.choices)) for r in rules.values()
+                       if isinstance(r, BernoulliSpawn)}
+        if len(spawn_rules) > 1:
             raise ValueError("only one distinct BernoulliSpawn rule per world is supported")
+        for key, r in list(rules.items()):  # aged copies of expiring entities
+            if isinstance(r, ExpireAfter):
+                for age in range(1, r.sweeps + 1):
+                    protos[key[:-1] + (age,)] = protos[key]
 
         def order(item):
-            name = item[0][0]
-            return (entity_list.index(name) if name in entity_list else len(entity_list), name)
+            (name, _, _, age) = item[0]
+            return (age > 0, entity_list.index(name) if name in entity_list else len(entity_list), name, age)
 
         keys = [k for k, _ in sorted(protos.items(), key=order)]
         if len(keys) > _abi.SB_MAX_KINDS:
             raise ValueError(f"{len(keys)} entity kinds exceed the engine limit of {_abi.SB_MAX_KINDS}")
         kid = {k: i for i, k in enumerate(keys)}
+        kind_of = lambda e, age=0: kid[e.kind_key() + (age,)]  # noqa: E731
         self._kinds = [protos[k] for k in keys]
         C = observation_spec.num_channels
         appearance = np.zeros((len(keys), C), dtype=np.float64)
@@ -140,7 +171,7 @@ class Gridworld:
             appearance[i] = observation_spec.appearance_row(protos[k].kind)  # KeyError like visual_field.py:49
         template = np.zeros((self.height, self.width, self.layers), dtype=np.uint8)
         for idx, e in np.ndenumerate(self.map):
-            template[idx] = kid[e.kind_key()]
+            template[idx] = kind_of(e)
         fill = [i for k, i in kid.items() if protos[k].kind == observation_spec.fill_entity_kind]
         if not fill:
             # the fill kind only matters through its appearance row: add a table-only kind
@@ -149,31 +180,87 @@ class Gridworld:
         agent_layers = set(spawnable[:, 2].tolist())
         if len(agent_layers) != 1:
             raise ValueError("all spawn locations must be on one layer")
-        deltas = []
+        agent_layer = int(spawnable[0, 2])
+
+        # ---- rule columns of the kind table ----
+        K = len(keys)
+        kind_rule = [_abi.SB_RULE_NONE] * K
+        prob, to, layer, mask = [0.0] * K, [_abi.SB_NO_KIND] * K, [-1] * K, [0] * K
+        spawn_rule = None
+        for key, r in rules.items():
+            i = kid[key]
+            if isinstance(r, BernoulliSpawn):
+                kind_rule[i], spawn_rule = _abi.SB_RULE_SPAWN, r
+            elif isinstance(r, BernoulliBecome):
+                kind_rule[i], prob[i], to[i] = _abi.SB_RULE_SPAWN_TO, float(r.prob), kind_of(r.to)
+            elif isinstance(r, BecomeIfLayer):
+                kind_rule[i], layer[i], to[i] = _abi.SB_RULE_BECOME_IF, int(r.layer), kind_of(r.to)
+                mask[i] = sum(1 << j for k2, j in kid.items() if protos[k2].kind in r.kinds)
+            elif isinstance(r, ExpireAfter):
+                for age in range(r.sweeps + 1):
+                    j = kid[key[:-1] + (age,)]
+                    kind_rule[j] = _abi.SB_RULE_BECOME
+                    to[j] = kid[key[:-1] + (age + 1,)] if age < r.sweeps else kind_of(r.to)
+        extended = any(kr not in (_abi.SB_RULE_NONE, _abi.SB_RULE_SPAWN) for kr in kind_rule)
+
+        # ---- actions: movement decode, facings, beams ----
+        deltas, facing, beam_kind = [], [], []
+        beam = None
         for i in range(action_spec.n_actions):
             name = action_spec.actions[i]
-            if name not in MOVE_DELTAS:
-                raise ValueError(f"action {name!r} has no movement decode in the B200 engine")
-            deltas.append(MOVE_DELTAS[name])
-        rule = next(iter(rules.values()), None)
+            if name in MOVE_DELTAS:
+                deltas.append(MOVE_DELTAS[name])
+                facing.append(MOVE_FACING[name])
+                beam_kind.append(_abi.SB_NO_KIND)
+            elif name in effects:
+                eff = effects[name]
+                if beam is not None and (eff.radius, eff.blocked_by) != (beam.radius, beam.blocked_by):
+                    raise ValueError("all beam actions of a world must share radius and blocked_by")
+                beam = eff
+                deltas.append((0, 0))
+                facing.append(-1)
+                beam_kind.append(kind_of(eff.entity))
+            else:
+                raise ValueError(f"action {name!r} has no movement decode or effect in the B200 engine")
+        reward_all = bool(getattr(agent_proto, "reward_all_layers", False))
+        reward_count = int(getattr(agent_proto, "reward_count", 1))
+        extra = observation_spec.extras(self) if hasattr(observation_spec, "extras") else None
+        groups = []
+        for ent, locs, count in item_groups:
+            locs = np.asarray([tuple(l) for l in locs], dtype=np.int64).reshape(-1, 3)
+            if len(set(locs[:, 2].tolist())) != 1:
+                raise ValueError("all locations of an item group must be on one layer")
+            groups.append((kind_of(ent), int(locs[0, 2]), int(count), locs[:, :2].copy()))
         spec = WorldSpec(
             height=self.height, width=self.width, layers=self.layers,
-            kind_names=[protos[k].__class__.__name__ for k in keys],
+            kind_names=[protos[k].__class__.__name__ + (f"#{k[3]}" if k[3] else "") for k in keys],
             kind_value=[float(protos[k].value) for k in keys],
             kind_passable=[bool(protos[k].passable) for k in keys],
-            kind_rule=[_abi.SB_RULE_SPAWN if k in rules else _abi.SB_RULE_NONE for k in keys],
+            kind_rule=kind_rule,
             appearance=appearance, template=template, spawnable=spawnable[:, :2].copy(),
-            agent_kind=kid[agent_proto.kind_key()], agent_layer=int(spawnable[0, 2]),
-            default_kind=kid[self.default_entity.kind_key()], fill_kind=fill[0],
+            agent_kind=kind_of(agent_proto), agent_layer=agent_layer,
+            default_kind=kind_of(self.default_entity), fill_kind=fill[0],
             vision=int(observation_spec.vision_radius), num_agents=int(num_agents),
-            spawn_prob=float(rule.prob) if rule else 0.0,
-            spawn_choices=[kid[c.kind_key()] for c in rule.choices] if rule else [],
+            spawn_prob=float(spawn_rule.prob) if spawn_rule else 0.0,
+            spawn_choices=[kind_of(c) for c in spawn_rule.choices] if spawn_rule else [],
             action_deltas=deltas, obs_transform=int(getattr(observation_spec, "obs_transform", 0)),
+            kind_rule_prob=prob if extended else None, kind_rule_to=to if extended else None,
+            kind_rule_layer=layer if extended else None, kind_rule_mask=mask if extended else None,
+            action_facing=facing if beam is not None else None,
+            action_beam_kind=beam_kind if beam is not None else None,
+            beam_layer=agent_layer + 1 if beam is not None else -1,  # `tile_above`, cleanup/agents.py:107-109
+            beam_offsets=np.array(beam_pattern(beam.radius), dtype=np.int64) if beam is not None else None,
+            beam_block_mask=sum(1 << j for k2, j in kid.items() if protos[k2].kind in beam.blocked_by)
+            if beam is not None else 0,
+            reward_all_layers=reward_all, reward_count=reward_count,
+            initial_facing=int(getattr(agent_proto, "direction", 2)),
+            obs_extra=extra, item_groups=groups,
         )
         return spec
 
-    def compile(self, agent_proto: Entity, observation_spec, action_spec, num_agents: int, spawnable) -> Engine:
-        self.spec = self.build_spec(agent_proto, observation_spec, action_spec, num_agents, spawnable)
+    def compile(self, agent_proto: Entity, observation_spec, action_spec, num_agents: int, spawnable,
+                item_groups=()) -> Engine:
+        self.spec = self.build_spec(agent_proto, observation_spec, action_spec, num_agents, spawnable, item_groups)
         self.engine = Engine(self.spec, self.num_envs, device=self.device, env_id_base=self.env_id_base,
                              seed=self.seed)
         return self.engine

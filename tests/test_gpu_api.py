@@ -134,3 +134,112 @@ def test_run_experiment_and_observe_from(cuda_device):
     assert [tuple(o.shape) for o in out] == [(8, 450), (8, 1), (8, 1), (8, 450), (8, 1), (8, 1)]
     assert [o.dtype for o in out] == [torch.float32, torch.int64, torch.float32, torch.float32, torch.float32,
                                       torch.float64]
+
+
+# ------------------------------------------------------------------------------------------------
+# examples/cleanup through the reference-shaped API
+# ------------------------------------------------------------------------------------------------
+CLEANUP_CONFIG = {
+    "experiment": {"name": "cleanup", "epochs": 1, "max_turns": 24, "epsilon_decay": 0.0001},
+    "env": {"height": 13, "width": 17, "layers": 3, "default_object": "EmptyEntity", "full_mdp": False,
+            "pollution_threshold": 0.5, "initial_apples": 6, "apple_spawn_chance": 0.03,
+            "pollution_spawn_chance": 0.06, "mode": "DEFAULT"},
+    "model": {"iqn": {"parameters": {"memory_size": 32}}, "epsilon_decay": 0.0001},
+    "agent": {"agent": {"num": 4, "beam_radius": 2, "obs": {"channels": 8, "vision": 3, "n_frames": 2,
+                                                             "embeddings": 3}}},
+}
+
+
+def _make_cleanup(num_envs, seed, model_factory=None):
+    from sorrel_b200.examples.cleanup.entities import EmptyEntity
+    from sorrel_b200.examples.cleanup.env import CleanupEnv
+    from sorrel_b200.examples.cleanup.world import CleanupWorld
+
+    world = CleanupWorld(CLEANUP_CONFIG, EmptyEntity(), num_envs=num_envs, device="cuda:0", seed=seed)
+    return CleanupEnv(world, CLEANUP_CONFIG, model_factory=model_factory)
+
+
+def _cleanup_oracle_spec():
+    e, a = CLEANUP_CONFIG["env"], CLEANUP_CONFIG["agent"]["agent"]
+    return R.cleanup_spec(e["height"], e["width"], a["num"], a["obs"]["vision"], e["initial_apples"],
+                          e["apple_spawn_chance"], e["pollution_spawn_chance"], a["beam_radius"])
+
+
+def _check_cleanup_against(env, oracles, A, check_actions=False):
+    grids = env.engine.grid_numpy()
+    for n, o in oracles.items():
+        np.testing.assert_array_equal(grids[n], o.grid, err_msg=f"instance {n}")
+        np.testing.assert_array_equal(env.engine.agent_facing.cpu().numpy()[n], o.facing)
+        for a in range(A):
+            mem = env.agents[a].model.memory
+            np.testing.assert_array_equal(mem.states[n].cpu().numpy(), o.buffers[a].states)
+            np.testing.assert_array_equal(mem.rewards[:, n].cpu().numpy(), o.buffers[a].rewards)
+            if check_actions:
+                np.testing.assert_array_equal(mem.actions[:, n].cpu().numpy(), o.buffers[a].actions)
+        assert float(env.world.total_reward[n]) == o.total_reward
+
+
+def test_cleanup_example_env_fused_matches_oracle(cuda_device):
+    """CleanupEnv with RandomModel agents (in-kernel policy): the rule table compiled from the example's
+    entity classes, stepped fused on the device, equals the oracle on the same counter-based stream."""
+    N, seed, T, A = 12, 31, 24, 4
+    env = _make_cleanup(N, seed)
+    assert env._fusable
+    env.add_empty()
+    env.take_turn()
+    env.take_turns(T - 1)
+    env.engine.check_errors()
+    spec = _cleanup_oracle_spec()
+    oracles = {}
+    for n in range(0, N, 5):
+        o = R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=n, capacity=32, n_frames=2)
+        o.reset()
+        for b in o.buffers:
+            b.add_empty()
+        for _ in range(T):
+            o.take_turn()
+        oracles[n] = o
+    _check_cleanup_against(env, oracles, A, check_actions=True)
+    assert 0.0 <= env.world.measure_pollution(0) <= 1.0
+    obs = env.agents[0].observation_spec.observe(env.world)
+    assert tuple(obs.shape) == (N, A, spec.obs_size)
+
+
+def test_cleanup_split_phase_host_policy_matches_oracle(cuda_device):
+    """Host-side policy through Agent.transition (pov -> get_action -> act) on the cleanup rule set: beams,
+    facings and all-layer rewards in split-phase launches equal the oracle with the same policy."""
+    from sorrel_b200.models import BaseModel
+
+    class ObsPolicy(BaseModel):
+        def take_action(self, state):
+            return (state != 0).sum(dim=1).to(torch.int32) % 6
+
+    N, seed, T, A = 6, 8, 14, 4
+    env = _make_cleanup(N, seed, model_factory=lambda inp, na: ObsPolicy(inp, na, memory_size=32, n_frames=2))
+    assert not env._fusable
+    env.add_empty()
+    for _ in range(T):
+        env.take_turn()
+    env.engine.check_errors()
+    spec = _cleanup_oracle_spec()
+
+    class Draws(R.PhiloxDraws):
+        def action(self, n_actions, env_id, tick, agent):
+            o, buf = self.env, self.env.buffers[agent]
+            y, x = o.pos[agent]
+            obs = np.concatenate((R.observe(o.spec, o.grid, y, x).reshape(-1), o.spec.obs_extra[y, x]))
+            stacked = np.concatenate((buf.current_state().reshape(-1), obs.astype(np.float32)))
+            return int((stacked != 0).sum() % 6)
+
+    oracles = {}
+    for n in range(N):
+        d = Draws(seed)
+        o = R.OracleEnv(spec, d, env_id=n, capacity=32, n_frames=2)
+        d.env = o
+        o.reset()
+        for b in o.buffers:
+            b.add_empty()
+        for _ in range(T):
+            o.take_turn()
+        oracles[n] = o
+    _check_cleanup_against(env, oracles, A, check_actions=True)

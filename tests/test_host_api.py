@@ -136,3 +136,52 @@ def test_rgb_observation_spec_matches_reference_map():
     ref = R.treasurehunt_spec(11, 11, 2, 2, 0.05, obs="rgb")
     np.testing.assert_array_equal(got.appearance, ref.appearance)
     assert got.obs_transform == 1
+
+
+def _cleanup_config(H=21, W=31, A=10, v=5, apples=20, apple_p=0.002, poll_p=0.009, radius=3):
+    return {
+        "experiment": {"name": "cleanup", "epochs": 1, "max_turns": 50},
+        "env": {"height": H, "width": W, "layers": 3, "default_object": "EmptyEntity", "full_mdp": False,
+                "pollution_threshold": 0.5, "initial_apples": apples, "apple_spawn_chance": apple_p,
+                "pollution_spawn_chance": poll_p, "mode": "DEFAULT"},
+        "model": {"iqn": {"parameters": {"memory_size": 16}}},
+        "agent": {"agent": {"num": A, "beam_radius": radius,
+                            "obs": {"channels": 8, "vision": v, "n_frames": 2, "embeddings": 3}}},
+    }
+
+
+@pytest.mark.parametrize("shape", [(21, 31, 10, 5, 20, 3), (15, 16, 4, 3, 8, 2)])
+def test_cleanup_kind_table_from_entity_classes_equals_oracle_spec(shape):
+    """examples/cleanup declared through Entity.transition_rule / Agent.action_effects compiles to the very
+    tables the oracle's hand-written cleanup spec holds (which is pinned to the reference's fixtures)."""
+    from sorrel_b200 import config as _config
+    from sorrel_b200.examples.cleanup.entities import EmptyEntity
+    from sorrel_b200.examples.cleanup.env import CleanupEnv
+    from sorrel_b200.examples.cleanup.world import CleanupWorld
+
+    H, W, A, v, apples, radius = shape
+    cfg = _cleanup_config(H, W, A, v, apples, radius=radius)
+    world = CleanupWorld(cfg, EmptyEntity(), num_envs=2)
+    env = CleanupEnv.__new__(CleanupEnv)  # host-only: run the subclass hooks without compiling / CUDA
+    env.config, env.world, env.model_factory = _config.wrap(cfg), world, None
+    env._spawnable, env._item_groups = None, []
+    env.setup_agents()
+    env.populate_environment()
+    a0 = env.agents[0]
+    got = world.build_spec(a0, a0.observation_spec, a0.action_spec, A, env._spawnable, env._item_groups)
+    ref = util.engine_spec(R.cleanup_spec(H, W, A, v, apples, 0.002, 0.009, radius))
+    assert got.kind_names == ref.kind_names
+    assert got.kind_value == [float(x) for x in ref.kind_value]
+    assert got.kind_passable == ref.kind_passable and got.kind_rule == ref.kind_rule
+    for f in ("kind_rule_prob", "kind_rule_to", "kind_rule_layer", "kind_rule_mask", "action_facing",
+              "action_beam_kind", "beam_layer", "beam_block_mask", "reward_all_layers", "reward_count",
+              "initial_facing", "agent_kind", "agent_layer", "default_kind", "fill_kind", "vision", "spawn_prob",
+              "spawn_choices"):
+        assert getattr(got, f) == getattr(ref, f), f
+    assert [tuple(d) for d in got.action_deltas] == [tuple(d) for d in ref.action_deltas]
+    for f in ("appearance", "template", "spawnable", "beam_offsets", "obs_extra"):
+        np.testing.assert_array_equal(getattr(got, f), getattr(ref, f), err_msg=f)
+    assert len(got.item_groups) == 1 and got.item_groups[0][:3] == ref.item_groups[0][:3]
+    np.testing.assert_array_equal(got.item_groups[0][3], ref.item_groups[0][3])
+    assert got.resolved_dynamic_layers() == [0, 1, 2] and got.obs_size == ref.obs_size
+    assert a0.observation_spec.input_size == (1, ref.obs_size)
