@@ -58,12 +58,19 @@ def parse_args():
                          "reference's draw-per-cell loop); sparse = Binomial count + distinct cells (same law)")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra sparse-sampler timing")
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--world", default="treasurehunt", choices=["treasurehunt", "cleanup"],
+                    help="rule set: treasurehunt (BASELINE configs) or the reference's cleanup example (SURVEY 8f rank 3: "
+                         "21x31x3, 10 agents, 11x11 one-hot view + positional code, beams, column rules)")
     ap.add_argument("--obs-study", action="store_true",
                     help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
     return ap.parse_args()
 
 
 def workload_name(a):
+    if a.world == "cleanup":
+        return (f"cleanup 21x31x3, {a.agents} agent(s)/env, v={a.vision} one-hot C=9 + 12 positional floats, "
+                f"{a.envs_total} envs total, {a.turns} turns/launch, ring cap {a.capacity}, F={a.n_frames}, "
+                f"sample 1/{a.sample_div}")
     return (f"treasurehunt {a.size}x{a.size}x2, {a.agents} agent(s)/env, v={a.vision} one-hot C=6, "
             f"{a.envs_total} envs total, {a.turns} turns/launch, ring cap {a.capacity}, F={a.n_frames}, "
             f"sample 1/{a.sample_div}")
@@ -72,12 +79,16 @@ def workload_name(a):
 def alg_bytes_per_env_step(a) -> int:
     """2*H*W*L_dyn + A*(C*S^2*4 + 36) + 8."""
     S = 2 * a.vision + 1
+    if a.world == "cleanup":  # 3 dynamic planes of 21x31, rows of 9*S*S + 12 floats, + 8 B facing r/w per agent
+        return 2 * 21 * 31 * 3 + a.agents * ((9 * S * S + 12) * 4 + 36 + 8) + 8
     return 2 * a.size * a.size * 1 + a.agents * (6 * S * S * 4 + 36) + 8
 
 
 def oracle_spec(a):
     from oracle import restatement as R
 
+    if a.world == "cleanup":
+        return R.cleanup_spec(21, 31, a.agents, a.vision)
     return R.treasurehunt_spec(a.size, a.size, a.agents, a.vision, a.spawn_prob)
 
 
@@ -435,7 +446,11 @@ def run_ours(a):
                 "step_kernel_share_of_step": k_ms * a.steps / ms_total, "breakdown_ms_per_step": breakdown}
 
     cpu = None
-    if not a.no_cpu:
+    if not a.no_cpu and a.world == "cleanup":  # the C port covers treasurehunt; cleanup has the Python restatement
+        v = python_port_throughput(a, a.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"one world, Python restatement (oracle/restatement.py), {a.cpu_seconds:.0f} s"}
+    elif not a.no_cpu:
         cpu = cpu_port_throughput(a, a.cpu_seconds)
         cpu["python_port_1core"] = python_port_throughput(a, 2.0)
 
@@ -447,6 +462,7 @@ def run_ours(a):
                    "l2": "inputs larger than L2 (grid + ring slots touched per step >> 126 MB)",
                    "policy": "in-kernel uniform (RandomModel)",
                    "launch": "eager" if a.no_graphs else "CUDA graph replay (device-resident tick/slot)",
+                   "world": a.world,
                    "rng": "philox4x32-10, " + ("one byte per cell per turn" if a.rng == "philox" else
                                                "sparse (Binomial count + distinct cells)")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,

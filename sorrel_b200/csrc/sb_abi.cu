@@ -123,9 +123,11 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
       if (z < 0 || z >= d.L || d.plane_of_layer[z] < 0 || !kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
       d.rule_plane_off[k] = d.plane_of_layer[z] * d.plane_stride;
       d.rule_mask[k] = w->kind_rule_mask[k];
+      d.det_mask |= 1u << k;
       d.ext_rules = 1;
     } else if (rule == SB_RULE_BECOME) {
       if (!kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
+      d.det_mask |= 1u << k;
       d.ext_rules = 1;
     } else if (rule != SB_RULE_NONE) {
       return SB_EUNSUPPORTED;

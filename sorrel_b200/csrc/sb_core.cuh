@@ -58,6 +58,7 @@ struct SbDev {
   int32_t ext_rules;  // some kind carries a rule other than SB_RULE_SPAWN
   int32_t ext_act;    // facings / beams / all-layer rewards / reward_count != 1
   uint32_t draw_mask; // kinds whose rule consumes a uniform (SPAWN, SPAWN_TO)
+  uint32_t det_mask;  // kinds with a deterministic rule (BECOME_IF, BECOME)
   uint8_t rule[SB_MAX_KINDS], rule_to[SB_MAX_KINDS];
   int32_t rule_plane_off[SB_MAX_KINDS];  // BECOME_IF: byte offset of the tested plane
   uint32_t rule_mask[SB_MAX_KINDS];
@@ -299,6 +300,18 @@ SB_HD double sb_obs_general(const SbDev& d, const uint8_t* genv, const uint8_t* 
   }
   if (d.obs_transform == SB_OBS_RGB) s = (s < 0.0 ? 0.0 : (s > 255.0 ? 255.0 : s)) / 255.0;  // np.clip(..)/255
   return s;
+}
+
+// One-hot channel of a kind (255 = all-zero appearance row / padding byte).
+SB_HD uint32_t sb_kind_channel(const SbDev& d, uint32_t kind) {
+  if (d.K <= 8) {  // 8-entry table in a register pair, one byte-permute
+#if defined(__CUDA_ARCH__)
+    return __byte_perm((uint32_t)d.channel8, (uint32_t)(d.channel8 >> 32), kind & 7u) & 0xFFu;
+#else
+    return (uint32_t)(d.channel8 >> (8 * (kind & 7u))) & 0xFFu;
+#endif
+  }
+  return kind < (uint32_t)SB_MAX_KINDS ? d.channel[kind] : 255u;
 }
 
 // Fast path, phase A: channel code of window cell (i, j) on plane `pl` (255 = contributes nothing).
