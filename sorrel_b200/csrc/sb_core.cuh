@@ -319,13 +319,5 @@ SB_HD uint32_t sb_window_code(const SbDev& d, const uint8_t* genv, int y, int x,
   int yy = y - d.v + i, xx = x - d.v + j;
   if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W)
     return pl == 0 ? (uint32_t)d.fill_channel : 255u;  // out of bounds: the fill kind, once
-  uint32_t kind = genv[pl * d.plane_stride + yy * d.W + xx];
-  if (d.K <= 8) {  // 8-entry table in a register pair, one byte-permute
-#if defined(__CUDA_ARCH__)
-    return __byte_perm((uint32_t)d.channel8, (uint32_t)(d.channel8 >> 32), kind & 7u) & 0xFFu;
-#else
-    return (uint32_t)(d.channel8 >> (8 * (kind & 7u))) & 0xFFu;
-#endif
-  }
-  return kind < (uint32_t)SB_MAX_KINDS ? d.channel[kind] : 255u;
+  return sb_kind_channel(d, genv[pl * d.plane_stride + yy * d.W + xx]);
 }
