@@ -1,6 +1,7 @@
 """Turn the ncu artefacts in gpurun_out/ into the tracked summaries under profiles/.
 
     python tools/summarize_profiles.py r01
+    python tools/summarize_profiles.py r01 --only cleanup_step_kernel c3_step_kernel   # extra captures only
 """
 import collections
 import csv
@@ -97,6 +98,12 @@ def lines(name, top=40):
             f.write(f"{100*v/tot:.2f},{100*smp[k]/ts:.2f},{k[0]},\"{k[1].replace(chr(34), chr(39))}\"\n")
     return tot, dst
 
+
+if "--only" in sys.argv:
+    for extra in sys.argv[sys.argv.index("--only") + 1:]:
+        print(raw(extra)[1])
+        print(lines(extra))
+    sys.exit(0)
 
 print(launches())
 d, p = raw("step_kernel")
