@@ -363,7 +363,7 @@ def run_ours(a):
         s0.record()
         for i in range(a.steps):
             one_step(record=True)
-        s1.record()
+            s1.record()
         barrier()
         ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -407,7 +407,7 @@ def run_ours(a):
         c0.record()
         for i in range(a.steps):
             e2e_step(i)
-        results = pipe.drain()
+            results = pipe.drain()
         c1.record()
         barrier()
         e2e_ms = max(c0.elapsed_time(c1), 1e3 * (time.perf_counter() - t0))

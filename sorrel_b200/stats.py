@@ -34,6 +34,37 @@ def all_reduce_partial(partial: torch.Tensor, group=None) -> torch.Tensor:
     return combine_partials(torch.stack(parts))
 
 
+class PendingStats:
+    """Handle of an all_gather in flight on the collective's own stream (`all_reduce_partial_async`);
+    `result()` joins it and combines the partials (device tensor [5]).
+
+    Measured on 2 x B200 (131 072 instances per GPU, boundary every 4 steps): leaving the NCCL gather un-joined
+    costs ~10 ms per boundary (3.6 ms per step instead of 1.2 ms with the stream-ordered `all_reduce_partial`),
+    so bench.py and Environment use the synchronous form; this one is kept for callers that want the statistics
+    off the step stream and can afford the latency (e.g. gloo on CPU ranks)."""
+
+    def __init__(self, parts, work):
+        self._parts, self._work, self._out = parts, work, None
+
+    def result(self) -> torch.Tensor:
+        if self._out is None:
+            if self._work is not None:
+                self._work.wait()  # stream-level wait (NCCL) / host wait (gloo)
+            self._out = combine_partials(torch.stack(self._parts) if isinstance(self._parts, list) else self._parts)
+        return self._out
+
+
+def all_reduce_partial_async(partial: torch.Tensor, group=None) -> PendingStats:
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return PendingStats(partial[None], None)
+    world = dist.get_world_size(group)
+    parts = [torch.empty(5, dtype=partial.dtype, device=partial.device) for _ in range(world)]
+    work = dist.all_gather(parts, partial.contiguous(), group=group, async_op=True)
+    return PendingStats(parts, work)
+
+
 def summarize(stats5: torch.Tensor) -> dict:
     """{sum, sum_sq, min, max, count} -> the numbers a Logger wants (synchronises)."""
     s, ss, mn, mx, n = (float(x) for x in stats5.tolist())
@@ -58,3 +89,9 @@ class RewardStats:
     def all_reduce(self, total_reward: torch.Tensor, group=None) -> torch.Tensor:
         """Global {sum, sum_sq, min, max, count} as a device tensor (no host sync)."""
         return all_reduce_partial(self.local(total_reward), group)
+
+    def all_reduce_async(self, total_reward: torch.Tensor, group=None) -> PendingStats:
+        """Same, without making the calling stream wait for the other ranks: the shard is reduced on the
+        current stream (so a following `reset` may zero `total_reward`), the all_gather runs on the
+        collective's stream and is joined by `PendingStats.result()`."""
+        return all_reduce_partial_async(self.local(total_reward), group)

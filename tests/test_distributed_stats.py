@@ -20,7 +20,7 @@ def _free_port():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from sorrel_b200.stats import all_reduce_partial, summarize
+    from sorrel_b200.stats import all_reduce_partial, all_reduce_partial_async, summarize
 
     total = 1000
     n = total // world
@@ -31,6 +31,10 @@ def _worker(rank, world, port, out):
     s = summarize(all_reduce_partial(part))
     ok = (s["count"] == total and s["min"] == allv.min() and s["max"] == allv.max()
           and abs(s["mean"] - allv.mean()) < 1e-12 and abs(s["std"] - allv.std()) < 1e-9)
+    # the overlapped form (collective left in flight, joined later) gives the same numbers; several may be pending
+    pend = [all_reduce_partial_async(part * k) for k in (1.0, 2.0)]
+    s2 = summarize(pend[1].result())
+    ok = ok and summarize(pend[0].result()) == s and s2["count"] == 2 * total and s2["max"] == 2 * allv.max()
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
