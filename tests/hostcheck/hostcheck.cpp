@@ -98,4 +98,49 @@ double hc_obs_general(const uint8_t* planes, const uint8_t* tmpl, const double* 
   for (int z = 0; z < L; ++z) d.plane_of_layer[z] = plane_of_layer[z];
   return sb_obs_general(d, planes, tmpl, app, y, x, c, i, j);
 }
+
+// SB_RULE_SPAWN_TO under the counter-based stream: 1 = the cell spawns (first-level byte recomputed here the
+// way the generic sweep does: byte (cell & 15) of Philox(env, tick, cell >> 4, SWEEP))
+int hc_bernoulli_hit(double p, uint32_t env, uint32_t tick, uint32_t cell, uint64_t seed) {
+  const uint64_t thr = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(p, 53)));
+  uint32_t rk[20];
+  sb_philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), rk);
+  const SbU4 r = sb_philox_rk(env, tick, cell >> 4, SB_DOM_SWEEP, rk);
+  return sb_bernoulli_hit(thr, sb_byte_of(r, (int)(cell & 15u)), env, tick, cell, rk) ? 1 : 0;
+}
+
+// deterministic column rules on a 2-plane image: planes[2][stride]; the rule of `kind` tests plane `other_plane`
+int hc_column_rule(const uint8_t* planes, int stride, int off, int rule, int to, int other_plane, uint32_t mask) {
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  const uint32_t kind = planes[off];
+  d.rule_to[kind] = (uint8_t)to;
+  d.rule_plane_off[kind] = other_plane * stride;
+  d.rule_mask[kind] = mask;
+  return sb_column_rule(d, planes, kind, (uint32_t)rule, off);
+}
+
+// all-layer reward (observe_all_layers) through sb_agent_act on an L-plane image
+float hc_agent_act_all_layers(uint8_t* planes, int H, int W, int L, int K, const float* value, uint32_t passable,
+                              int agent_plane, int agent_kind, int default_kind, uint32_t* yx, int action,
+                              uint32_t* err) {
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  d.H = H, d.W = W, d.K = K, d.L = L, d.n_planes = L;
+  d.plane_stride = (H * W + 15) / 16 * 16;
+  for (int z = 0; z < L; ++z) d.plane_of_layer[z] = z;
+  d.agent_plane = agent_plane;
+  d.agent_kind = agent_kind, d.default_kind = default_kind, d.n_actions = 6;
+  d.passable_mask = passable;
+  const int8_t dy[6] = {-1, 1, 0, 0, 0, 0}, dx[6] = {0, 0, -1, 1, 0, 0};
+  for (int i = 0; i < 6; ++i) {
+    d.dy_packed |= (uint64_t)(uint8_t)dy[i] << (8 * i);
+    d.dx_packed |= (uint64_t)(uint8_t)dx[i] << (8 * i);
+  }
+  for (int k = 0; k < K; ++k) d.value[k] = value[k];
+  uint32_t e = 0;
+  float r = sb_agent_act(d, planes, yx, action, true, e, true);
+  *err = e;
+  return r;
+}
 }

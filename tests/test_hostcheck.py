@@ -155,3 +155,73 @@ def test_general_observation_sum_matches_oracle(hc):
                     got = hc.hc_obs_general(planes.ctypes.data, tmpl.ctypes.data, app.ctypes.data, H, W, L,
                                             pol.ctypes.data, K, Cn, v, 1, y, x, c, i, j)
                     assert got == ref[c, i, j]
+
+
+def test_bernoulli_become_matches_oracle(hc):
+    """SB_RULE_SPAWN_TO (River -> Pollution, AppleTree -> Apple): sb_bernoulli_hit == PhiloxDraws.bernoulli."""
+    hc.hc_bernoulli_hit.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
+    rng = np.random.RandomState(11)
+    hits = 0
+    for _ in range(6000):
+        p = float(rng.choice([0.002, 0.009, 0.05, 0.5, 1.0, 0.0, 1 / 256, 2 / 256, 255 / 256]))
+        env, tick, cell = int(rng.randint(0, 2**20)), int(rng.randint(1, 2**16)), int(rng.randint(0, 4096))
+        seed = int(rng.randint(0, 2**62))
+        got = hc.hc_bernoulli_hit(p, env, tick, cell, seed)
+        _, want = R.PhiloxDraws(seed).bernoulli(p, env, tick, cell, cell)
+        assert bool(got) == bool(want)
+        hits += got
+    assert 1000 < hits < 3000  # both outcomes are exercised
+
+
+def test_column_rules(hc):
+    """SB_RULE_BECOME_IF reads the same column on another plane; SB_RULE_BECOME is unconditional."""
+    hc.hc_column_rule.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
+    rng = np.random.RandomState(5)
+    stride = 32
+    for _ in range(500):
+        planes = rng.randint(0, 12, size=2 * stride).astype(np.uint8)
+        off = int(rng.randint(0, stride))
+        mask = int(rng.randint(0, 1 << 12))
+        to = int(rng.randint(0, 12))
+        other = int(planes[stride + off])
+        got = hc.hc_column_rule(planes.ctypes.data, stride, off, R.RULE_BECOME_IF, to, 1, mask)
+        assert got == (to if (mask >> other) & 1 else -1)
+        assert hc.hc_column_rule(planes.ctypes.data, stride, off, R.RULE_BECOME, to, 1, mask) == to
+        assert hc.hc_column_rule(planes.ctypes.data, stride, off, R.RULE_NONE, to, 1, mask) == -1
+
+
+def test_agent_act_all_layer_reward(hc):
+    """cleanup/agents.py:158-176: reward = sum of values over all layers at the target, whether or not the move
+    succeeds; non-movement actions read the agent's own column."""
+    hc.hc_agent_act_all_layers.restype = C.c_float
+    hc.hc_agent_act_all_layers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
+                                           C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    H, W, L, K = 5, 7, 3, 6
+    value = np.array([0, 0, 1, -1, 3, 0], dtype=np.float32)  # kinds: 0 empty, 1 wall, 2 apple, 3 zap, 4 gem, 5 agent
+    passable = 0b000001
+    stride = (H * W + 15) // 16 * 16
+    rng = np.random.RandomState(2)
+    for _ in range(400):
+        planes = np.full(L * stride, 0xFF, dtype=np.uint8)
+        img = rng.choice([0, 1, 2, 3, 4], size=(L, H, W), p=[0.5, 0.1, 0.15, 0.15, 0.1]).astype(np.uint8)
+        img[1] = rng.choice([0, 1, 5], size=(H, W), p=[0.7, 0.15, 0.15])  # agent layer: empty / wall / other agents
+        y, x = int(rng.randint(1, H - 1)), int(rng.randint(1, W - 1))
+        img[1, y, x] = 5
+        for z in range(L):
+            planes[z * stride: z * stride + H * W] = img[z].reshape(-1)
+        action = int(rng.randint(0, 6))
+        dy, dx = ((-1, 0), (1, 0), (0, -1), (0, 1), (0, 0), (0, 0))[action]
+        ny, nx = y + dy, x + dx
+        want = float(sum(value[img[z, ny, nx]] for z in range(L)))
+        moved = img[1, ny, nx] == 0
+        yx = np.array([(y << 16) | x], dtype=np.uint32)
+        err = np.zeros(1, dtype=np.uint32)
+        r = hc.hc_agent_act_all_layers(planes.ctypes.data, H, W, L, K, value.ctypes.data, passable, 1, 5, 0,
+                                       yx.ctypes.data, action, err.ctypes.data)
+        assert r == want and err[0] == 0
+        assert (int(yx[0]) >> 16, int(yx[0]) & 0xFFFF) == ((ny, nx) if moved else (y, x))
+        after = planes[stride: stride + H * W].reshape(H, W)
+        if moved:
+            assert after[ny, nx] == 5 and after[y, x] == 0
+        else:
+            assert after[y, x] == 5
