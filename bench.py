@@ -446,11 +446,7 @@ def run_ours(a):
                 "step_kernel_share_of_step": k_ms * a.steps / ms_total, "breakdown_ms_per_step": breakdown}
 
     cpu = None
-    if not a.no_cpu and a.world == "cleanup":  # the C port covers treasurehunt; cleanup has the Python restatement
-        v = python_port_throughput(a, a.cpu_seconds)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"one world, Python restatement (oracle/restatement.py), {a.cpu_seconds:.0f} s"}
-    elif not a.no_cpu:
+    if not a.no_cpu:
         cpu = cpu_port_throughput(a, a.cpu_seconds)
         cpu["python_port_1core"] = python_port_throughput(a, 2.0)
 

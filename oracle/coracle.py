@@ -27,6 +27,17 @@ class OrWorld(C.Structure):
         ("p", C.c_double),
         ("value", C.c_float * 32), ("passable", C.c_uint8 * 32), ("rule", C.c_uint8 * 32),
         ("appearance", C.c_void_p), ("tmpl", C.c_void_p), ("spawnable", C.c_void_p),
+        ("rule_prob", C.c_double * 32), ("rule_to", C.c_uint8 * 32), ("rule_layer", C.c_int8 * 32),
+        ("rule_mask", C.c_uint32 * 32),
+        ("uses_facing", C.c_int32), ("initial_facing", C.c_int32),
+        ("action_facing", C.c_int8 * 8), ("action_beam_kind", C.c_uint8 * 8),
+        ("beam_layer", C.c_int32), ("n_beam", C.c_int32),
+        ("beam_dy", (C.c_int8 * 16) * 4), ("beam_dx", (C.c_int8 * 16) * 4),
+        ("beam_block_mask", C.c_uint32),
+        ("reward_all_layers", C.c_int32), ("reward_count", C.c_int32),
+        ("obs_extra", C.c_int32), ("extra", C.c_void_p),
+        ("n_groups", C.c_int32), ("group_kind", C.c_int32 * 4), ("group_layer", C.c_int32 * 4),
+        ("group_count", C.c_int32 * 4), ("group_n_cells", C.c_int32 * 4), ("group_cells", C.c_void_p * 4),
     ]
 
 
@@ -48,7 +59,7 @@ def lib():
         L.or_step.argtypes = [C.c_void_p, C.c_int]
         L.or_step.restype = None
         L.or_set_tick.argtypes = [C.c_void_p, C.c_uint32]
-        for name in ("or_grid", "or_pos", "or_total", "or_states", "or_actions", "or_rewards", "or_dones",
+        for name in ("or_grid", "or_pos", "or_facing", "or_total", "or_states", "or_actions", "or_rewards", "or_dones",
                      "or_positions", "or_tape_u", "or_tape_c", "or_tape_a", "or_tape_placement"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_void_p
@@ -86,7 +97,7 @@ class COracle:
         w.agent_layer, w.fill_kind = spec.agent_layer, spec.fill_kind
         w.agent_kind, w.default_kind = spec.agent_kind, spec.default_kind
         w.n_actions = spec.num_actions
-        for i, (dy, dx) in enumerate(R.ACTION_DELTAS[: spec.num_actions]):
+        for i, (dy, dx) in enumerate(spec.action_deltas[: spec.num_actions]):
             w.dy[i], w.dx[i] = dy, dx
         w.n_choices = len(spec.spawn_choices)
         for i, k in enumerate(spec.spawn_choices):
@@ -103,6 +114,38 @@ class COracle:
         self._spawn = np.ascontiguousarray(sp[:, 0] * spec.width + sp[:, 1], dtype=np.int32)
         w.n_spawnable = len(self._spawn)
         w.appearance, w.tmpl, w.spawnable = self._app.ctypes.data, self._tmpl.ctypes.data, self._spawn.ctypes.data
+        # ---- column rules / facings / beams / positional code / item groups (examples/cleanup) ----
+        for k in range(w.K):
+            w.rule_prob[k] = float(spec.kind_rule_prob[k]) if spec.kind_rule_prob else 0.0
+            w.rule_to[k] = int(spec.kind_rule_to[k]) if spec.kind_rule_to else R.NO_KIND
+            w.rule_layer[k] = int(spec.kind_rule_layer[k]) if spec.kind_rule_layer else -1
+            w.rule_mask[k] = int(spec.kind_rule_mask[k]) if spec.kind_rule_mask else 0
+        w.uses_facing = 1 if (spec.action_facing is not None or spec.action_beam_kind is not None) else 0
+        w.initial_facing = int(spec.initial_facing)
+        for i in range(8):
+            w.action_facing[i] = int(spec.action_facing[i]) if spec.action_facing and i < len(spec.action_facing) else -1
+            w.action_beam_kind[i] = int(spec.action_beam_kind[i]) \
+                if spec.action_beam_kind and i < len(spec.action_beam_kind) else R.NO_KIND
+        w.beam_layer = int(spec.beam_layer)
+        if spec.beam_offsets is not None:
+            w.n_beam = int(spec.beam_offsets.shape[1])
+            for f in range(4):
+                for b in range(w.n_beam):
+                    w.beam_dy[f][b], w.beam_dx[f][b] = int(spec.beam_offsets[f, b, 0]), int(spec.beam_offsets[f, b, 1])
+        w.beam_block_mask = int(spec.beam_block_mask)
+        w.reward_all_layers = 1 if spec.reward_all_layers else 0
+        w.reward_count = int(spec.reward_count)
+        self._extra = None
+        if spec.obs_extra is not None:
+            self._extra = np.ascontiguousarray(spec.obs_extra, dtype=np.float64).reshape(spec.height * spec.width, -1)
+            w.obs_extra, w.extra = int(self._extra.shape[1]), self._extra.ctypes.data
+        self._groups = []
+        w.n_groups = len(spec.item_groups)
+        for gi, (kind, layer, count, cells) in enumerate(spec.item_groups):
+            flat = np.ascontiguousarray(np.asarray(cells)[:, 0] * spec.width + np.asarray(cells)[:, 1], dtype=np.int32)
+            self._groups.append(flat)
+            w.group_kind[gi], w.group_layer[gi], w.group_count[gi] = int(kind), int(layer), int(count)
+            w.group_n_cells[gi], w.group_cells[gi] = len(flat), flat.ctypes.data
         self._w = w
         self.threads = threads
         self.h = self.L.or_create(C.byref(w), self.N, self.capacity, n_frames, rng, seed, env_id_base, threads,
@@ -137,6 +180,10 @@ class COracle:
     @property
     def pos(self):
         return _view(self.L.or_pos(self.h), (self.N, self.spec.num_agents), np.int32)
+
+    @property
+    def facing(self):
+        return _view(self.L.or_facing(self.h), (self.N, self.spec.num_agents), np.int32)
 
     @property
     def total_reward(self):

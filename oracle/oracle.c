@@ -13,6 +13,10 @@
  *   Gridworld.observe / move             sorrel/worlds/gridworld.py:95-133
  *   visual_field (closed form)           sorrel/observation/visual_field.py:9-101
  *   Buffer.add                           sorrel/buffers.py:46-63
+ *   cleanup rule set: River/Pollution/AppleTree/Apple.transition  sorrel/examples/cleanup/entities.py:43-105,
+ *                     Beam.transition, CleanupAgent.spawn_beam / act, CleanupObservation.observe
+ *                                                                  sorrel/examples/cleanup/agents.py:21-216,
+ *                     populate_environment                         sorrel/examples/cleanup/env.py:85-140
  *
  * Randomness (three interchangeable sources, same step code):
  *   OR_RNG_NUMPY  -- own MT19937 + the numpy *legacy* RandomState draw algorithms (numpy is a
@@ -38,6 +42,12 @@
 #define OR_RNG_NUMPY 0
 #define OR_RNG_PHILOX 1
 #define OR_RULE_SPAWN 1
+#define OR_RULE_SPAWN_TO 2  /* Bernoulli(rule_prob[k]) -> rule_to[k], one uniform, no choice draw */
+#define OR_RULE_BECOME_IF 3 /* same column on rule_layer[k] holds a kind of rule_mask[k] -> rule_to[k] */
+#define OR_RULE_BECOME 4    /* -> rule_to[k] (beam ageing: turn_counter folded into the kind id) */
+#define OR_NO_KIND 255
+#define OR_MAX_BEAM 16
+#define OR_MAX_GROUPS 4
 
 #define DOM_SWEEP 0x53570000u
 #define DOM_CELL 0x43450000u
@@ -165,6 +175,23 @@ typedef struct {
   const double* appearance; /* [K][C] */
   const uint8_t* tmpl;      /* [H][W][L] (reference index order y, x, z) */
   const int32_t* spawnable; /* [n_spawnable] y*W+x on the agent layer, reference order */
+  /* ---- column rules, facings + beams, all-layer rewards, positional code, item groups (examples/cleanup) ---- */
+  double rule_prob[OR_MAX_KINDS];
+  uint8_t rule_to[OR_MAX_KINDS];
+  int8_t rule_layer[OR_MAX_KINDS];
+  uint32_t rule_mask[OR_MAX_KINDS];
+  int32_t uses_facing, initial_facing;
+  int8_t action_facing[8];
+  uint8_t action_beam_kind[8];
+  int32_t beam_layer, n_beam;
+  int8_t beam_dy[4][OR_MAX_BEAM], beam_dx[4][OR_MAX_BEAM];
+  uint32_t beam_block_mask;
+  int32_t reward_all_layers, reward_count;
+  int32_t obs_extra;
+  const double* extra; /* [H*W][obs_extra] float64 (rounded to f32 when stored, like Buffer.states) */
+  int32_t n_groups, group_kind[OR_MAX_GROUPS], group_layer[OR_MAX_GROUPS], group_count[OR_MAX_GROUPS],
+      group_n_cells[OR_MAX_GROUPS];
+  const int32_t* group_cells[OR_MAX_GROUPS]; /* y*W+x, reference order */
 } or_world_t;
 
 typedef struct {
@@ -177,6 +204,7 @@ typedef struct {
   /* state */
   uint8_t* grid; /* [N][H][W][L] */
   int32_t* pos;  /* [N][A] cell index */
+  int32_t* facing; /* [N][A] MovingAgent.direction: survives reset */
   double* total; /* [N] */
   mt_t* mt;      /* [N] numpy streams (seed = seed + n) */
   /* ring, engine layout */
@@ -214,11 +242,13 @@ or_env_t* or_create(const or_world_t* w, int64_t N, int capacity, int n_frames, 
   e->n_frames = n_frames;
   e->record = record;
   int S = 2 * w->v + 1;
-  e->obs_size = w->C * S * S;
+  e->obs_size = w->C * S * S + w->obs_extra;
   e->plane_stride = (w->H * w->W + 15) / 16 * 16;
   size_t cells = (size_t)w->H * w->W * w->L, rows = (size_t)N * w->A;
   e->grid = (uint8_t*)malloc(N * cells);
   e->pos = (int32_t*)calloc(rows, sizeof(int32_t));
+  e->facing = (int32_t*)calloc(rows, sizeof(int32_t));
+  for (size_t r = 0; r < rows; ++r) e->facing[r] = w->initial_facing;
   e->total = (double*)calloc(N, sizeof(double));
   if (rng_mode == OR_RNG_NUMPY) {
     e->mt = (mt_t*)malloc(N * sizeof(mt_t));
@@ -241,6 +271,7 @@ or_env_t* or_create(const or_world_t* w, int64_t N, int capacity, int n_frames, 
 
 void or_destroy(or_env_t* e) {
   if (!e) return;
+  free(e->facing);
   free(e->grid), free(e->pos), free(e->total), free(e->mt), free(e->states), free(e->actions);
   free(e->rewards), free(e->dones), free(e->positions), free(e->tape_u), free(e->tape_c), free(e->tape_a);
   free(e->tape_pl);
@@ -257,6 +288,32 @@ static void reset_range(or_env_t* e, int64_t n0, int64_t n1) {
     uint8_t* g = e->grid + n * cells;
     memcpy(g, w->tmpl, cells);
     e->total[n] = 0.0; /* create_world, gridworld.py:65 */
+    /* item groups first, in order (cleanup/env.py:126-132: apples before agents) */
+    for (int gi = 0; gi < w->n_groups; ++gi) {
+      int32_t gp[256];
+      const int cnt = w->group_count[gi], nc = w->group_n_cells[gi];
+      if (e->rng_mode == OR_RNG_NUMPY) {
+        int32_t* sc = (int32_t*)malloc(sizeof(int32_t) * (nc > 0 ? nc : 1));
+        np_permutation_head(&e->mt[n], nc, cnt, gp, sc);
+        free(sc);
+      } else {
+        uint32_t env = (uint32_t)(e->env_id_base + (uint64_t)n), j = (uint32_t)(gi + 1) << 24, r[4];
+        for (int a = 0; a < cnt; ++a) {
+          for (;;) {
+            philox(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
+            int32_t cand = (int32_t)bounded64(r[0], r[1], (uint32_t)nc);
+            int dup = 0;
+            for (int b = 0; b < a; ++b) dup |= gp[b] == cand;
+            if (!dup) {
+              gp[a] = cand;
+              break;
+            }
+          }
+        }
+      }
+      for (int a = 0; a < cnt; ++a)
+        g[(size_t)w->group_cells[gi][gp[a]] * w->L + w->group_layer[gi]] = (uint8_t)w->group_kind[gi];
+    }
     if (e->rng_mode == OR_RNG_NUMPY) {
       /* np.random.choice(len(valid), size=A, replace=False) == permutation(len)[:A], env.py:141 */
       np_permutation_head(&e->mt[n], w->n_spawnable, w->A, picks, scratch);
@@ -308,6 +365,9 @@ static void observe(const or_world_t* w, const uint8_t* g, int y, int x, float* 
         }
       }
     }
+  /* CleanupObservation.observe (cleanup/agents.py:52-62): positional code of the agent's cell appended */
+  for (int k = 0; k < w->obs_extra; ++k)
+    out[C * S * S + k] = (float)w->extra[(size_t)(y * w->W + x) * w->obs_extra + k];
 }
 
 static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
@@ -318,7 +378,7 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
   const uint32_t env = (uint32_t)(e->env_id_base + (uint64_t)n);
   const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
   const size_t tape_stride = (size_t)w->n_dyn * e->plane_stride;
-  float obs_local[32 * 21 * 21];
+  float obs_local[32 * 21 * 21 + 256];
   for (int t = 0; t < T; ++t) {
     const uint32_t tick = e->tick + 1 + (uint32_t)t;
     double* tu = e->record ? e->tape_u + ((size_t)(t_base + t) * e->N + n) * tape_stride : 0;
@@ -328,28 +388,47 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
       for (int x = 0; x < w->W; ++x)
         for (int z = 0; z < w->L; ++z) {
           uint8_t* cellp = g + ((size_t)y * w->W + x) * w->L + z;
-          if (w->rule[*cellp] != OR_RULE_SPAWN) continue;
+          const int kind = *cellp, rule = w->rule[kind];
+          if (rule == 0 || kind == w->agent_kind) continue; /* `not isinstance(x, Agent)`, environment.py:90 */
+          if (rule == OR_RULE_BECOME) { /* Beam.transition, cleanup/agents.py:199-204 */
+            *cellp = w->rule_to[kind];
+            continue;
+          }
+          if (rule == OR_RULE_BECOME_IF) { /* Pollution / Apple, cleanup/entities.py:64-71,100-105 */
+            const int other = g[((size_t)y * w->W + x) * w->L + w->rule_layer[kind]];
+            if ((w->rule_mask[kind] >> other) & 1u) *cellp = w->rule_to[kind];
+            continue;
+          }
           int zd = zd_of_layer(w, z);
           uint32_t pcell = (uint32_t)(zd * e->plane_stride + y * w->W + x);
+          const double prob = rule == OR_RULE_SPAWN ? w->p : w->rule_prob[kind];
           if (e->rng_mode == OR_RNG_NUMPY) {
-            double u = np_random_sample(mt); /* entities.py:73 */
+            double u = np_random_sample(mt); /* entities.py:73; cleanup/entities.py:52,86 */
             if (tu) tu[pcell] = u;
-            if (u < w->p) {
-              uint32_t ci = np_randint(mt, (uint32_t)w->n_choices); /* np.random.choice, entities.py:75 */
-              if (tc) tc[pcell] = (uint8_t)ci;
-              *cellp = (uint8_t)w->choices[ci];
+            if (u < prob) {
+              if (rule == OR_RULE_SPAWN) {
+                uint32_t ci = np_randint(mt, (uint32_t)w->n_choices); /* np.random.choice, entities.py:75 */
+                if (tc) tc[pcell] = (uint8_t)ci;
+                *cellp = (uint8_t)w->choices[ci];
+              } else {
+                *cellp = w->rule_to[kind];
+              }
             }
           } else {
             uint32_t r[4];
+            const uint64_t thr = !(prob > 0.0) ? 0 : (prob >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(prob, 53)));
+            const uint32_t hi8 = (uint32_t)(thr >> 45);
+            const uint64_t lo45 = thr & ((1ull << 45) - 1);
             philox(env, tick, pcell >> 4, DOM_SWEEP, k0, k1, r);
             uint32_t b = pcell & 15, r8 = (r[b >> 2] >> (8 * (b & 3))) & 0xFF;
-            if (r8 > e->hi8) continue;
-            philox(env, tick, pcell, DOM_CELL, k0, k1, r);
-            if (r8 == e->hi8) {
+            if (r8 > hi8) continue;
+            if (rule == OR_RULE_SPAWN || r8 == hi8) philox(env, tick, pcell, DOM_CELL, k0, k1, r);
+            if (r8 == hi8) {
               uint64_t refine = (((uint64_t)r[0] << 13) | (r[1] >> 19)) & ((1ull << 45) - 1);
-              if (!(refine < e->lo45)) continue;
+              if (!(refine < lo45)) continue;
             }
-            *cellp = (uint8_t)w->choices[bounded64(r[2], r[3], (uint32_t)w->n_choices)];
+            if (rule == OR_RULE_SPAWN) *cellp = (uint8_t)w->choices[bounded64(r[2], r[3], (uint32_t)w->n_choices)];
+            else *cellp = w->rule_to[kind];
           }
         }
     /* agents in list order, agents/agent.py:155-173 */
@@ -368,11 +447,26 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
         action = (int)bounded64(r[0], r[1], (uint32_t)w->n_actions);
       }
       if (e->record) e->tape_a[((size_t)(t_base + t) * e->N + n) * w->A + a] = action;
+      if (w->uses_facing) {
+        if (w->action_facing[action] >= 0) e->facing[row] = w->action_facing[action]; /* agents/agent.py:199-211 */
+        const int bk = w->action_beam_kind[action], f = e->facing[row] & 3;
+        if (bk != OR_NO_KIND) /* CleanupAgent.spawn_beam, cleanup/agents.py:93-145 */
+          for (int b = 0; b < w->n_beam; ++b) {
+            int by = y + w->beam_dy[f][b], bx = x + w->beam_dx[f][b];
+            if (by < 0 || by >= w->H || bx < 0 || bx >= w->W) continue;
+            uint8_t* bp = g + ((size_t)by * w->W + bx) * w->L + w->beam_layer;
+            if (!((w->beam_block_mask >> *bp) & 1u)) *bp = (uint8_t)bk;
+          }
+      }
       int ny = y + w->dy[action], nx = x + w->dx[action];
       float reward = 0.0f;
       if (ny >= 0 && ny < w->H && nx >= 0 && nx < w->W) {
         uint8_t* tp = g + ((size_t)ny * w->W + nx) * w->L + w->agent_layer;
-        reward = w->value[*tp]; /* reward = target.value, agent.py:219-220 */
+        if (w->reward_all_layers) { /* observe_all_layers, cleanup/agents.py:160-170 */
+          for (int z = 0; z < w->L; ++z) reward += w->value[g[((size_t)ny * w->W + nx) * w->L + z]];
+        } else {
+          reward = w->value[*tp]; /* reward = target.value, agent.py:219-220 */
+        }
         if (w->passable[*tp]) { /* Gridworld.move, gridworld.py:95-122 */
           *tp = (uint8_t)w->agent_kind;
           g[((size_t)y * w->W + x) * w->L + w->agent_layer] = (uint8_t)w->default_kind;
@@ -380,7 +474,8 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
           y = ny, x = nx;
         }
       }
-      e->total[n] += (double)reward; /* agent.py:172 */
+      /* agent.py:172 (cleanup adds the reward a second time in act(): cleanup/agents.py:172) */
+      e->total[n] += (double)reward * (double)(w->reward_count > 0 ? w->reward_count : 1);
       if (e->capacity > 0) {          /* Buffer.add, buffers.py:46-63; position AFTER the move */
         size_t at = (size_t)slot * rows + row;
         e->actions[at] = action;
@@ -462,6 +557,7 @@ void or_add_empty(or_env_t* e) { /* buffers.py:65-69 */
 /* accessors for the ctypes wrapper */
 uint8_t* or_grid(or_env_t* e) { return e->grid; }
 int32_t* or_pos(or_env_t* e) { return e->pos; }
+int32_t* or_facing(or_env_t* e) { return e->facing; }
 double* or_total(or_env_t* e) { return e->total; }
 float* or_states(or_env_t* e) { return e->states; }
 int64_t* or_actions(or_env_t* e) { return e->actions; }

@@ -107,3 +107,61 @@ def test_c_oracle_tapes_equal_python_tapes():
         np.testing.assert_array_equal(ct["spawn_c"][:, n], c)
         np.testing.assert_array_equal(ct["actions"][:, n], env.dense_tapes()["actions"])
         np.testing.assert_array_equal(ct["placement"][n], env.dense_tapes()["placement"])
+
+
+@pytest.mark.parametrize("name", util.cleanup_cases())
+def test_c_oracle_reproduces_reference_cleanup(name):
+    """The C restatement on the cleanup rule set (column rules, beams, facings, all-layer rewards, positional
+    code, apples placed before agents) against the fixtures of the unmodified reference."""
+    g = util.load_golden(name)
+    spec = util.cleanup_spec_from_golden(g)
+    T, E, F, A = int(g["T"]), int(g["epochs"]), int(g["n_frames"]), int(g["A"])
+    co = coracle.COracle(spec, 1, capacity=int(g["capacity"]), n_frames=F, rng=coracle.RNG_NUMPY,
+                         seed=int(g["seed"]))
+    gi = 0
+    for ep in range(E):
+        co.reset()
+        if F > 1:
+            co.add_empty()
+        yx = np.stack([co.pos[0] // spec.width, co.pos[0] % spec.width], axis=-1)
+        np.testing.assert_array_equal(yx, g["starts"][ep])
+        np.testing.assert_array_equal(co.grid[0], g["grids"][gi], err_msg="after reset")
+        gi += 1
+        for t in range(T):
+            co.step(1)
+            np.testing.assert_array_equal(co.grid[0], g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+            np.testing.assert_array_equal(co.facing[0], g["facings"][ep * T + t])
+            gi += 1
+        assert co.total_reward[0] == float(g["total_reward"][ep])
+    ring = co.ring()
+    for a in range(A):
+        np.testing.assert_array_equal(ring["states"][a], g["states"][a])
+        np.testing.assert_array_equal(ring["actions"][:, a], g["actions"][a])
+        np.testing.assert_array_equal(ring["rewards"][:, a], g["rewards"][a])
+        np.testing.assert_array_equal(ring["positions"][:, a], g["positions"][a])
+
+
+def test_c_oracle_philox_equals_python_cleanup():
+    """Counter-based mode on the cleanup rule set: C (multi-threaded) == Python restatement."""
+    spec = R.cleanup_spec(13, 17, 5, 3, initial_apples=6, apple_spawn_chance=0.03, pollution_spawn_chance=0.06,
+                          beam_radius=2)
+    N, T, seed, base = 9, 16, 77, 500
+    co = coracle.COracle(spec, N, capacity=2 * T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=3)
+    pys = [R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=base + n, capacity=2 * T) for n in range(N)]
+    for ep in range(2):
+        co.reset()
+        co.step(T)
+        for n, o in enumerate(pys):
+            o.reset()
+            for _ in range(T):
+                o.take_turn()
+            np.testing.assert_array_equal(co.grid[n], o.grid, err_msg=f"episode {ep} instance {n}")
+            np.testing.assert_array_equal(co.facing[n], o.facing)
+            assert co.total_reward[n] == o.total_reward
+    ring = co.ring()
+    for n, o in enumerate(pys):
+        for a in range(spec.num_agents):
+            row = n * spec.num_agents + a
+            np.testing.assert_array_equal(ring["states"][row], o.buffers[a].states)
+            np.testing.assert_array_equal(ring["rewards"][:, row], o.buffers[a].rewards)
+            np.testing.assert_array_equal(ring["actions"][:, row], o.buffers[a].actions)
