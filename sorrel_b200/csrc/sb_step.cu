@@ -81,7 +81,7 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
 // way.  `off` shifts the row inside the staging buffer so that the first 16-byte aligned global
 // address lines up with an aligned shared address (ring rows are only 8-byte aligned: 600 B, 1944 B).
 // `genv` may point to shared or global memory.
-template <int LANES, bool NP1>
+template <int LANES, bool NP1, int NB = 1>
 __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint16_t* lut_ij,
                                                 uint8_t* stage_raw, int y, int x, float* dst, int lane) {
   float* stage = reinterpret_cast<float*>(stage_raw);          // !NP1: f32 sums over planes
@@ -100,7 +100,29 @@ SB_UNROLL(SB_SCATTER_UNROLL)
 #else
       const int i = (int)(((uint32_t)ij * inv_s) >> 16), j = ij - i * d.S;
 #endif
-      if (NP1) {  // one stored plane: every window cell contributes at most one 1.0
+      if (NP1 && NB > 1) {
+        // planes in GLOBAL memory (standalone observation kernel, unstaged large maps): issue the NB window
+        // loads of this lane back to back, then the dependent scatters (the compiler cannot hoist a generic
+        // load over a shared store by itself)
+        uint32_t kinds[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int q = ij + u * LANES;
+          const int qi = (int)(((uint32_t)q * inv_s) >> 16), qj = q - qi * d.S;
+          const int yy = y - d.v + qi, xx = x - d.v + qj;
+          kinds[u] = 0x100u;  // beyond the window
+          if (q < d.SS)
+            kinds[u] = ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) ? 0x200u  // out of bounds
+                                                                                      : genv[yy * d.W + xx];
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const uint32_t code = kinds[u] < 0x100u ? sb_kind_channel(d, kinds[u])
+                                                  : (kinds[u] == 0x200u ? (uint32_t)d.fill_channel : 255u);
+          if (code != 255u) stage16[off + code * d.SS + ij + u * LANES] = 0x3F80;
+        }
+        ij += (NB - 1) * LANES;
+      } else if (NP1) {  // one stored plane: every window cell contributes at most one 1.0
         const uint32_t code = sb_window_code(d, genv, y, x, i, j, 0);
         if (code != 255u) stage16[off + code * d.SS + ij] = 0x3F80;  // bf16(1.0)
       } else {
@@ -178,13 +200,16 @@ SB_UNROLL(SB_COPY_UNROLL)
 // 128-bit stores.  Config 4 (128x128, 64 agents, 9x9 window): 1944 B written per pair.
 // ----------------------------------------------------------------------------------------------
 constexpr int OBS_THREADS = 256;
+#ifndef SB_OBS_MINB
+#define SB_OBS_MINB 6  // resident blocks per SM the register allocation is sized for (40 registers)
+#endif
 
 // LANES lanes (16 or 32) serve one (instance, agent) pair; every group walks a CONTIGUOUS range of
 // pairs so that (env, agent) advance incrementally (no divisions in the loop), the agents of one
 // instance are served back to back (its planes stay in L1) and consecutive rows land in the same DRAM
 // pages.
 template <bool NP1, int LANES>
-__global__ void __launch_bounds__(OBS_THREADS)
+__global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
     observe_kernel(const __grid_constant__ SbDev d, const uint8_t* __restrict__ grid,
                    const int32_t* __restrict__ agent_pos, float* __restrict__ out, int stage_bytes, int fast,
                    unsigned pairs_per_group) {
@@ -216,7 +241,8 @@ __global__ void __launch_bounds__(OBS_THREADS)
     const uint8_t* genv = grid + (size_t)(valid ? env : 0) * d.env_stride;
     float* dst = valid ? out + (size_t)pair * d.obs_size : nullptr;
     if (fast) {
-      emit_onehot_row<LANES, NP1>(d, genv, lut_ij, stage_raw, y, x, dst, lane);
+      // window loads batched: 2 per lane cover a 5x5 window with 16 lanes, 4 per lane a 9x9 / 11x11 one with 32
+      emit_onehot_row<LANES, NP1, (LANES == 16 ? 2 : 4)>(d, genv, lut_ij, stage_raw, y, x, dst, lane);
       __syncwarp();
     } else if (valid) {
       for (int e = lane; e < d.oh_size; e += LANES) {
@@ -244,15 +270,22 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
   const int smem = round_up(2 * d.SS, 16) + groups * stage_bytes;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
   const unsigned long long pairs = (unsigned long long)d.N * d.A;
-  // persistent grid: up to 8 blocks (64 warps) per SM; each group takes a contiguous run of pairs
-  unsigned long long blocks = (pairs + groups - 1) / groups;
-  if (blocks > 148ull * 8) blocks = 148ull * 8;
-  const unsigned long long ppg = (pairs + blocks * groups - 1) / (blocks * groups);
-  if (ppg > 0xFFFFFFFFull) return SB_EUNSUPPORTED;
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return note_cuda_error();
+    // persistent grid of exactly ONE wave: (SMs) x (blocks that are resident together, from the occupancy
+    // calculator: registers cap it at 6, not 8); each group takes a contiguous run of pairs.  A fixed 148 x 8
+    // grid ran 1.33 waves, i.e. a second, one-third-full wave (ncu: launch__waves_per_multiprocessor).
+    int dev = 0, sms = 148, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OBS_THREADS, smem) != cudaSuccess || per_sm < 1)
+      per_sm = 4;
+    unsigned long long blocks = (pairs + groups - 1) / groups;
+    if (blocks > (unsigned long long)sms * per_sm) blocks = (unsigned long long)sms * per_sm;
+    const unsigned long long ppg = (pairs + blocks * groups - 1) / (blocks * groups);
+    if (ppg > 0xFFFFFFFFull) return SB_EUNSUPPORTED;
     kern<<<(unsigned)blocks, OBS_THREADS, smem, s>>>(d, grid, agent_pos, out, stage_bytes, d.fast_obs, (unsigned)ppg);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : note_cuda_error();
