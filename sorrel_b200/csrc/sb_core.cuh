@@ -238,8 +238,19 @@ SB_HD uint32_t sb_simd_cand_chunk(uint32_t k0, uint32_t k1, uint32_t k2, uint32_
 // `genv` is the (shared-memory) image of the instance.  Returns the reward; updates *yx (packed
 // y<<16|x) and, when `writer`, the two grid cells.  `err` collects SB_ERR_* bits.
 // ------------------------------------------------------------------------------------------------
+// Cell index the action of an agent at packed position `yx` targets on the agent plane, or -1 (bad action /
+// off the grid).  Lets a caller start the load of the target kind early (planes in global memory).
+SB_HD int sb_target_cell(const SbDev& d, uint32_t yx, int action) {
+  if ((unsigned)action >= (unsigned)d.n_actions) return -1;
+  const int ny = (int)(yx >> 16) + (int)(int8_t)((d.dy_packed >> (8 * action)) & 0xFF);
+  const int nx = (int)(yx & 0xFFFFu) + (int)(int8_t)((d.dx_packed >> (8 * action)) & 0xFF);
+  if ((unsigned)ny >= (unsigned)d.H || (unsigned)nx >= (unsigned)d.W) return -1;
+  return ny * d.W + nx;
+}
+
+// `pre_tk` >= 0: kind of the target cell already loaded by the caller (same cell, same state).
 SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action, bool writer,
-                         uint32_t& err, bool all_layers = false) {
+                         uint32_t& err, bool all_layers = false, int pre_tk = -1) {
   int y = (int)(*yx >> 16), x = (int)(*yx & 0xFFFFu);
   int dy = 0, dx = 0;
   if ((unsigned)action < (unsigned)d.n_actions) {
@@ -254,7 +265,7 @@ SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action
     return 0.0f;
   }
   uint8_t* plane = genv + d.agent_plane * d.plane_stride;
-  uint32_t tk = plane[ny * d.W + nx];
+  uint32_t tk = pre_tk >= 0 ? (uint32_t)pre_tk : plane[ny * d.W + nx];
   if (tk >= (uint32_t)d.K) {
     err |= SB_ERR_BAD_KIND;
     return 0.0f;

@@ -9,6 +9,7 @@
 
 #define SB_THREADS 128
 #define SB_QCAP 96       // per-warp spawn-candidate queue entries
+#define SB_PAR 4          // agents of one instance observed / moved at once by a warp (when independent)
 #define SB_OBS_ALL (-2)  // SbStepArgs.obs_agent: observe every agent (sb_observe)
 
 // kernel RNG variants (template parameter)
@@ -33,6 +34,7 @@ struct StepParams {
   int32_t q_off, planes_off, pos_off, stage_off, hits_off;  // block-level byte offsets
   int32_t staged;                                 // planes staged in shared memory (else used in place)
   int32_t plane_env, stage_env;                   // per-instance strides of planes / staging rows
+  int32_t stage_row, par;                         // one staging row; agent-parallel path enabled
   uint32_t rk[20];                                // Philox round keys of a.seed (constant-bank operands)
 };
 

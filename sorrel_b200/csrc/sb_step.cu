@@ -43,7 +43,7 @@ __host__ __device__ inline int pad64mod128(int b) {
 // single stored plane is observed (entries are 0 or 1: the float is the bf16 shifted left by 16) and
 // f32 otherwise (entries are sums over planes).
 struct SmemLayout {
-  int q_off, planes_off, pos_off, stage_off, hits_off, plane_env, stage_env, total;
+  int q_off, planes_off, pos_off, stage_off, hits_off, plane_env, stage_env, stage_row, total;
 };
 
 // planes above this size stay in global memory (a 128x128 plane is 16 KB: staging it would leave room for
@@ -61,7 +61,9 @@ __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, boo
   L.plane_env = stage_planes(d) ? pad64mod128(d.env_stride) : 0;
   L.pos_off = L.planes_off + epb * L.plane_env;
   L.stage_off = L.pos_off + round_up(epb * 12 * d.A, 16);  // packed yx, action, facing per agent
-  L.stage_env = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
+  L.stage_row = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
+  // warp-per-instance worlds with several agents observe up to SB_PAR independent agents at once
+  L.stage_env = (np1 && lpe == 32 && d.A >= SB_PAR) ? SB_PAR * L.stage_row : L.stage_row;
   L.hits_off = L.stage_off + epb * L.stage_env;  // SB_RNG_SPARSE: accepted cells of the turn, u16[KMAX]
   L.total = L.hits_off + epb * SB_SPARSE_KMAX * 2;
   return L;
@@ -564,7 +566,14 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       dsts[1] = (p.a.d_obs_out && active)
                     ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size
                     : nullptr;
-      if (NP1 || d.fast_obs) {
+      if (NP1 && LPE == 32 && !p.staged) {
+        // large maps used in place in global memory: batch the window loads (one L2 round trip per row, not 3)
+        emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
+        if (p.a.d_obs_out) {
+          __syncwarp();
+          emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
+        }
+      } else if (NP1 || d.fast_obs) {
         emit_onehot_row<LPE, NP1>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
         if (p.a.d_obs_out) {
           __syncwarp();
@@ -589,7 +598,30 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       }
     };
 
-    auto act = [&](int a) {
+    // one agent's move by ONE lane: MovingAgent.act + Gridworld.move + the scalar part of Buffer.add
+    auto move_and_record = [&](int a, int pre_tk) -> float {
+      uint32_t yx = spos[a];
+      const int action = sact[a];
+      const float reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all, pre_tk);
+      spos[a] = yx;
+      const size_t row = row0 + a;
+      if (p.has_buf) {
+        const size_t at = (size_t)slot * rows + row;
+        p.buf.d_actions[at] = (int64_t)action;
+        p.buf.d_rewards[at] = reward;
+        p.buf.d_dones[at] = 0.0f;  // world.is_done is False for the whole episode
+        if (p.buf.d_positions) {   // location AFTER the move (agent.py:131-134)
+          p.buf.d_positions[2 * at] = (int64_t)(yx >> 16);
+          p.buf.d_positions[2 * at + 1] = (int64_t)(yx & 0xFFFFu);
+        }
+      }
+      const size_t o = ((size_t)t * d.N + env) * d.A + a;
+      if (p.a.d_reward_out) p.a.d_reward_out[o] = reward;
+      if (p.a.d_action_out) p.a.d_action_out[o] = action;
+      return reward;
+    };
+
+    auto act = [&](int a, int pre_tk) {
       if (EXT && d.ext_act) {
         // MovingAgent.movement sets the facing (agents/agent.py:199-211); beam actions then replace every
         // in-map, non-blocked cell of the beam pattern on the beam layer (CleanupAgent.spawn_beam,
@@ -615,42 +647,86 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         if (lane == 0) sfacing[a] = facing;
       }
       if (lane == 0 && active) {
-        uint32_t yx = spos[a];
-        const int action = sact[a];
-        float reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all);
-        spos[a] = yx;
         // world.total_reward += reward (agent.py:172; cleanup adds it twice: cleanup/agents.py:172)
+        const float reward = move_and_record(a, pre_tk);
         total += (double)(EXT ? reward * (float)d.reward_count : reward);
-        if (active) {
-          const size_t row = row0 + a;
-          if (p.has_buf) {
-            const size_t at = (size_t)slot * rows + row;
-            p.buf.d_actions[at] = (int64_t)action;
-            p.buf.d_rewards[at] = reward;
-            p.buf.d_dones[at] = 0.0f;  // world.is_done is False for the whole episode
-            if (p.buf.d_positions) {   // location AFTER the move (agent.py:131-134)
-              p.buf.d_positions[2 * at] = (int64_t)(yx >> 16);
-              p.buf.d_positions[2 * at + 1] = (int64_t)(yx & 0xFFFFu);
-            }
-          }
-          const size_t o = ((size_t)t * d.N + env) * d.A + a;
-          if (p.a.d_reward_out) p.a.d_reward_out[o] = reward;
-          if (p.a.d_action_out) p.a.d_action_out[o] = action;
-        }
       }
       __syncwarp();
     };
 
-    if (fused) {
+    if (fused && LPE == 32 && NP1 && p.par) {
+      // Warp-per-instance worlds (large maps, many agents): SB_PAR consecutive agents whose positions are
+      // pairwise more than v + 1 apart (Chebyshev) cannot see or touch each other's moves this turn -- an
+      // agent's move changes cells within 1 of its position, a window reaches v -- so their observations and
+      // moves commute with the list order of environment.py:92 and are done AT ONCE, 8 lanes per agent.  Groups
+      // that fail the test (or the tail) take the sequential path.  Rewards are added in list order.
+      constexpr int SL = 32 / SB_PAR;
+      for (int a0 = 0; a0 < d.A; a0 += SB_PAR) {
+        bool par = a0 + SB_PAR <= d.A;
+        if (par) {
+          bool conflict = false;
+          if (lane < SB_PAR * (SB_PAR - 1) / 2) {
+            int i = 0, j = lane + 1;  // lane -> pair (i, j), i < j, row-major over the upper triangle
+            while (j >= SB_PAR) {
+              ++i;
+              j = j - SB_PAR + i + 1;
+            }
+            const uint32_t pi = spos[a0 + i], pj = spos[a0 + j];
+            const int dy = (int)(pi >> 16) - (int)(pj >> 16), dx = (int)(pi & 0xFFFFu) - (int)(pj & 0xFFFFu);
+            conflict = max(abs(dy), abs(dx)) <= d.v + 1;
+          }
+          par = !__any_sync(0xFFFFFFFFu, conflict);
+        }
+        if (par) {
+          const int sub = lane / SL, sl = lane % SL, a = a0 + sub;
+          const uint32_t yx = spos[a];
+          const int y = (int)(yx >> 16), x = (int)(yx & 0xFFFFu);
+          int pre_tk = -1;
+          if (sl == 0 && active) {  // start the load of the cell this agent will step on
+            const int tc = sb_target_cell(d, yx, sact[a]);
+            if (tc >= 0) pre_tk = genv[d.agent_plane * d.plane_stride + tc];
+          }
+          uint8_t* srow = stage_raw + sub * p.stage_row;
+          float* dst0 = (p.has_buf && active) ? ring0 + ((size_t)a * p.buf.capacity + slot) * d.obs_size : nullptr;
+          emit_onehot_row<SL, NP1, 4>(d, genv, lut_ij, srow, y, x, dst0, sl);
+          if (p.a.d_obs_out) {
+            float* dst1 = active ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size : nullptr;
+            __syncwarp();
+            emit_onehot_row<SL, NP1, 4>(d, genv, lut_ij, srow, y, x, dst1, sl);
+          }
+          // every window has been read (the barrier inside emit_onehot_row follows the scatter): move
+          float reward = 0.0f;
+          if (sl == 0 && active) reward = move_and_record(a, pre_tk);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < SB_PAR; ++k) {
+            const float rk_ = __shfl_sync(0xFFFFFFFFu, reward, k * SL);
+            if (lane == 0) total += (double)rk_;  // agent.py:172, in list order
+          }
+        } else {
+          for (int a = a0; a < min(a0 + SB_PAR, d.A); ++a) {
+            observe(a);
+            act(a, -1);
+          }
+        }
+      }
+    } else if (fused) {
       for (int a = 0; a < d.A; ++a) {
+        // planes in global memory: start the load of the cell agent a will step on NOW (its position, its
+        // action and every earlier agent's move are final), so the L2 round trip overlaps the observation
+        int pre_tk = -1;
+        if (!p.staged && lane == 0 && active && !(EXT && d.ext_act)) {
+          const int tc = sb_target_cell(d, spos[a], sact[a]);
+          if (tc >= 0) pre_tk = genv[d.agent_plane * d.plane_stride + tc];
+        }
         observe(a);
 #ifdef SB_SPLIT_SYNC
         __syncwarp();
 #endif
-        act(a);
+        act(a, pre_tk);
       }
     } else {
-      if (p.a.act_agent >= 0) act(p.a.act_agent);
+      if (p.a.act_agent >= 0) act(p.a.act_agent, -1);
       if (p.a.obs_agent >= 0) {
         observe(p.a.obs_agent);
       } else if (p.a.obs_agent == SB_OBS_ALL) {
@@ -689,6 +765,8 @@ static int launch_one(const SbDev& d, StepParams p, cudaStream_t s) {
   sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
   p.q_off = L.q_off, p.planes_off = L.planes_off, p.pos_off = L.pos_off, p.stage_off = L.stage_off;
   p.plane_env = L.plane_env, p.stage_env = L.stage_env, p.hits_off = L.hits_off;
+  p.stage_row = L.stage_row;
+  p.par = (NP1 && LPE == 32 && d.A >= SB_PAR && !d.ext_act && !d.obs_extra && !getenv("SB_NO_PAR")) ? 1 : 0;
   p.staged = stage_planes(d) ? 1 : 0;
   const int smem = L.total;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
@@ -709,7 +787,8 @@ template <int LPE>
 static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t s) {
   const bool np1 = d.fast_obs && d.n_planes == 1;
   switch (kr) {
-    case SB_K_TAPE: return launch_one<LPE, SB_K_TAPE, false>(d, p, s);  // replay: speed is irrelevant
+    case SB_K_TAPE:  // replay: speed is irrelevant, but it shares the observation / agent code under test
+      return np1 ? launch_one<LPE, SB_K_TAPE, true>(d, p, s) : launch_one<LPE, SB_K_TAPE, false>(d, p, s);
     case SB_K_PHILOX_SIMD:
       return np1 ? launch_one<LPE, SB_K_PHILOX_SIMD, true>(d, p, s) : launch_one<LPE, SB_K_PHILOX_SIMD, false>(d, p, s);
     case SB_K_SPARSE:

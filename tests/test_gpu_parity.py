@@ -603,3 +603,46 @@ def test_full_size_invariants(cuda_device):
     st = buf.states.view(N, cap, 6, 5, 5)
     assert (st[:, :, 0] == 0).all() and (st.sum(dim=2) <= 1).all()
     assert (st[:, :, 5, 2, 2] == 1).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# agent-parallel path of the warp-per-instance variant (large maps, many agents)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("A,H,W,v,p,T,N,staged", [
+    (16, 64, 64, 3, 0.01, 30, 6, None),   # staged planes, ~10 % of the 4-agent groups conflict -> both paths
+    (24, 40, 40, 2, 0.02, 25, 5, None),   # crowded: many fall-backs to the sequential path
+    (10, 48, 48, 4, 0.01, 20, 4, None),   # A % 4 != 0: sequential tail
+    (64, 128, 128, 4, 0.005, 12, 3, None),  # BASELINE config 4 shape (planes used in place in global memory)
+    (16, 64, 64, 3, 0.01, 20, 4, 0),      # the same world with unstaged planes
+])
+def test_agent_parallel_path_matches_oracle(A, H, W, v, p, T, N, staged, cuda_device, monkeypatch):
+    """Groups of 4 consecutive agents that are pairwise more than v+1 apart are observed and moved at once
+    (8 lanes each); anything else takes the sequential path.  Both must reproduce the strictly sequential
+    oracle (environment.py:92) bit for bit: grids, positions, every buffer array, total reward."""
+    from oracle import coracle
+
+    monkeypatch.setenv("SB_LPE", "32")
+    if staged is not None:
+        monkeypatch.setenv("SB_STAGED", str(staged))
+    seed, base = 0xC0FFEE1234, 17
+    spec = R.treasurehunt_spec(H, W, A, v, p)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    buf = _buffer(spec, N, T, cuda_device)
+    obs_out = torch.zeros((T - T // 2, N, A, spec.obs_size), dtype=torch.float32, device=cuda_device)
+    eng.reset()
+    eng.step(T // 2, buffer=buf)
+    eng.step(T - T // 2, buffer=buf, obs_out=obs_out)  # second destination of the rows as well
+    eng.check_errors()
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
+    co.reset()
+    co.step(T)
+    np.testing.assert_array_equal(eng.grid_numpy(), co.grid)
+    np.testing.assert_array_equal(eng.agent_pos.cpu().numpy(), co.pos)
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), co.total_reward)
+    ring = co.ring()
+    np.testing.assert_array_equal(buf.states.cpu().numpy(), ring["states"])
+    np.testing.assert_array_equal(buf.actions.cpu().numpy(), ring["actions"])
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
+    np.testing.assert_array_equal(buf.extra_data["positions"].cpu().numpy(), ring["positions"])
+    got = obs_out.cpu().numpy().reshape(T - T // 2, N * A, -1)
+    np.testing.assert_array_equal(got, np.moveaxis(ring["states"][:, T // 2:], 0, 1))
