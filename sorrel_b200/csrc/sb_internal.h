@@ -9,7 +9,9 @@
 
 #define SB_THREADS 128
 #define SB_QCAP 96       // per-warp spawn-candidate queue entries
-#define SB_PAR 4          // agents of one instance observed / moved at once by a warp (when independent)
+#ifndef SB_PAR
+#define SB_PAR 4  // agents of one instance observed / moved at once by a warp (when independent)
+#endif
 #define SB_OBS_ALL (-2)  // SbStepArgs.obs_agent: observe every agent (sb_observe)
 
 // kernel RNG variants (template parameter)
