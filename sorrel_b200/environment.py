@@ -163,6 +163,65 @@ class Environment:
         all_gather; see stats.py)."""
         return summarize(self.stats.all_reduce(self.engine.total_reward))
 
+    def generate_memories(self, num_games: int = 1000, animate: bool = False,
+                          output_dir: Path | None = None) -> list[Path]:
+        """environment.py:213-300: play `num_games` games with the existing models and write one
+        `memories/agent{i}.npz` per agent slot in the `SavedGames` format (buffers.py:358-379: states, actions,
+        rewards, dones, n_frames, idx + extra_data such as positions), games back to back.
+
+        Every device instance plays one game per episode, so ceil(num_games / num_envs) episodes are run and the
+        first `num_games` instance-episodes are kept (instance-major within an episode).  The ring must hold one
+        episode (`capacity >= max_turns`).  `animate` is accepted for signature compatibility (rendering is
+        host-side tooling outside the engine)."""
+        exp = self.config.experiment
+        T, N, A = int(exp.max_turns), self.engine.N, len(self.agents)
+        if self.buffer.capacity < T:
+            raise ValueError(f"replay ring capacity {self.buffer.capacity} cannot hold an episode of {T} turns")
+        if output_dir is None:
+            output_dir = Path(exp.output_dir) if hasattr(exp, "output_dir") else Path("./data/")
+        output_dir = Path(output_dir)
+        os.makedirs(output_dir / "memories", exist_ok=True)
+        fuse = int(self.config.get("engine", {}).get("turns_per_launch", 25))
+        keys = ("states", "actions", "rewards", "dones", *self.buffer.extra_data.keys())
+        chunks = {k: [[] for _ in range(A)] for k in keys}
+        done_games, game = 0, 0
+        while done_games < num_games:
+            self.reset()
+            self.buffer.clear()
+            for agent in self.agents:
+                agent.model.start_epoch_action(epoch=game)
+            while not self.turn >= T:
+                if self._fusable:
+                    self.take_turns(min(fuse, T - self.turn))
+                else:
+                    self.take_turn()
+            self.world.is_done = True
+            take = min(N, num_games - done_games)
+            host = {"states": self.buffer.states[:, :T].cpu().numpy(),            # [rows, T, obs]
+                    "actions": self.buffer.actions[:T].cpu().numpy(),              # [T, rows]
+                    "rewards": self.buffer.rewards[:T].cpu().numpy(),
+                    "dones": self.buffer.dones[:T].cpu().numpy()}
+            for k, v in self.buffer.extra_data.items():
+                host[k] = v[:T].cpu().numpy()                                      # [T, rows, ...]
+            for i, agent in enumerate(self.agents):
+                agent.model.end_epoch_action(epoch=game)
+                rows = np.arange(take) * A + i  # this slot's row in every kept instance
+                chunks["states"][i].append(host["states"][rows].reshape(take * T, -1))
+                for k in keys[1:]:
+                    arr = np.moveaxis(host[k][:, rows], 0, 1)  # [take, T, ...]
+                    chunks[k][i].append(arr.reshape(take * T, *arr.shape[2:]))
+            done_games += take
+            game += 1
+        paths = []
+        for i, agent in enumerate(self.agents):
+            data = {k: np.concatenate(chunks[k][i]) for k in keys}
+            path = output_dir / "memories" / f"agent{i}.npz"
+            np.savez_compressed(path, n_frames=int(getattr(agent.model, "n_frames", 1)),
+                                idx=len(data["actions"]) % max(1, num_games * T), **data)
+            paths.append(path)
+        self.engine.check_errors()
+        return paths
+
     def run_experiment(self, animate: bool = False, logging: bool = True, logger=None,
                        output_dir: Path | None = None) -> list[dict]:
         """environment.py:108-211 without the host-only extras (GIF rendering, checkpoints):

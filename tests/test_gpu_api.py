@@ -243,3 +243,35 @@ def test_cleanup_split_phase_host_policy_matches_oracle(cuda_device):
             o.take_turn()
         oracles[n] = o
     _check_cleanup_against(env, oracles, A, check_actions=True)
+
+
+def test_generate_memories_saved_games_format(cuda_device, tmp_path):
+    """Environment.generate_memories (environment.py:213-300): agent{i}.npz in the SavedGames layout, games back to
+    back; game g of agent i is instance g's episode (checked against the oracle on the same stream)."""
+    N, seed, games = 8, 123, 11  # 11 games from 8 instances: 2 episodes, the second one partly kept
+    env, cfg = _make(N, seed)
+    T = cfg["experiment"]["max_turns"]
+    paths = env.generate_memories(num_games=games, output_dir=tmp_path)
+    assert [p.name for p in paths] == ["agent0.npz", "agent1.npz", "agent2.npz"]
+    spec = _oracle_spec()
+    oracles = []
+    for n in (0, 5):
+        o = R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=n, capacity=T)
+        # the constructor of Environment resets once (environment.py:52-54), generate_memories resets again
+        o.reset()
+        o.reset()
+        for _ in range(T):
+            o.take_turn()
+        oracles.append((n, o))
+    for a, path in enumerate(paths):
+        with np.load(path) as d:
+            assert d["states"].shape == (games * T, 150) and d["states"].dtype == np.float32
+            assert d["actions"].shape == (games * T,) and d["actions"].dtype == np.int64
+            assert d["rewards"].dtype == np.float32 and d["dones"].dtype == np.float32
+            assert d["positions"].shape == (games * T, 2) and int(d["n_frames"]) == 3
+            for n, o in oracles:
+                sl = slice(n * T, (n + 1) * T)
+                np.testing.assert_array_equal(d["states"][sl], o.buffers[a].states)
+                np.testing.assert_array_equal(d["actions"][sl], o.buffers[a].actions)
+                np.testing.assert_array_equal(d["rewards"][sl], o.buffers[a].rewards)
+                np.testing.assert_array_equal(d["positions"][sl], o.buffers[a].positions)
