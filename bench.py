@@ -363,7 +363,7 @@ def run_ours(a):
         s0.record()
         for i in range(a.steps):
             one_step(record=True)
-            s1.record()
+        s1.record()
         barrier()
         ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -380,7 +380,7 @@ def run_ours(a):
     if not a.no_e2e:
         from sorrel_b200.hostio import HostStepPipeline
 
-        pipe = HostStepPipeline(eng, buf, T, rng=a.rng)
+        pipe = HostStepPipeline(eng, buf, T, rng=a.rng, timing=True)
         h_actions = [torch.randint(0, 4, (T, N, A), dtype=torch.int32).pin_memory() for _ in range(2)]
         def e2e_step(i):
             """The same step as `one_step` (boundary stats + reset, fused turns, Buffer.sample), with the
@@ -407,7 +407,7 @@ def run_ours(a):
         c0.record()
         for i in range(a.steps):
             e2e_step(i)
-            results = pipe.drain()
+        results = pipe.drain()
         c1.record()
         barrier()
         e2e_ms = max(c0.elapsed_time(c1), 1e3 * (time.perf_counter() - t0))
@@ -417,7 +417,8 @@ def run_ours(a):
         e2e_ms = float(te.item())
         e2e = {"value": steps_total / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
-               "ms_per_step": e2e_ms / a.steps, "reward_checksum": float(results)}
+               "ms_per_step": e2e_ms / a.steps, "reward_checksum": float(results),
+               "step_kernel_ms": sum(e0.elapsed_time(e1) for e0, e1 in pipe.kernel_events[-a.steps:]) / a.steps}
         eng.check_errors()
 
     if rank != 0:

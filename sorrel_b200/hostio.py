@@ -12,8 +12,9 @@ import torch
 
 
 class HostStepPipeline:
-    def __init__(self, engine, buffer, turns: int, depth: int = 2, rng: str = "philox"):
+    def __init__(self, engine, buffer, turns: int, depth: int = 2, rng: str = "philox", timing: bool = False):
         self.eng, self.buf, self.T, self.depth, self.rng = engine, buffer, int(turns), depth, rng
+        self.timing, self.kernel_events = timing, []  # (start, end) CUDA events around every step launch
         dev, N, A = engine.device, engine.N, engine.A
         shape = (self.T, N, A)
         self.d_actions = [torch.empty(shape, dtype=torch.int32, device=dev) for _ in range(depth)]
@@ -39,7 +40,13 @@ class HostStepPipeline:
             self.ev_h2d[k].record(self.s_h2d)
         cur.wait_event(self.ev_h2d[k])
         cur.wait_event(self.ev_d2h[k])  # previous read-back of d_rewards[k] is done
+        if self.timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
         self.eng.step(self.T, buffer=self.buf, actions=self.d_actions[k], reward_out=self.d_rewards[k], rng=self.rng)
+        if self.timing:
+            e1.record(cur)
+            self.kernel_events.append((e0, e1))
         self.ev_compute[k].record(cur)
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(self.ev_compute[k])
