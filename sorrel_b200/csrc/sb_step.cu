@@ -94,6 +94,7 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
     // window cell ij -> (i, j) = (ij / S, ij % S) by multiply-shift (exact for ij < 512, S <= 21); the
     // loop is unrolled so the dependent shared-memory reads of several cells are in flight together
     const uint32_t inv_s = d.inv_S;
+    uint16_t* const srow16 = stage16 + off;  // hoisted: the compiler recomputed `off` under the store's predicate
 SB_UNROLL(SB_SCATTER_UNROLL)
     for (int ij = lane; ij < d.SS; ij += LANES) {
 #ifdef SB_IJ_LUT
@@ -126,7 +127,7 @@ SB_UNROLL(SB_SCATTER_UNROLL)
         ij += (NB - 1) * LANES;
       } else if (NP1) {  // one stored plane: every window cell contributes at most one 1.0
         const uint32_t code = sb_window_code(d, genv, y, x, i, j, 0);
-        if (code != 255u) stage16[off + code * d.SS + ij] = 0x3F80;  // bf16(1.0)
+        if (code != 255u) srow16[code * d.SS + ij] = 0x3F80;  // bf16(1.0)
       } else {
         // several stored planes are SUMMED (visual_field.py:51).  Slot (channel, ij) of the zeroed row is only
         // ever touched by this lane in this loop iteration, so the first plane stores and only a later plane
@@ -161,13 +162,37 @@ SB_UNROLL(SB_SCATTER_UNROLL)
         dst[lane] = __uint_as_float((uint32_t)stage16[off + lane] << 16);
         stage16[off + lane] = 0;
       }
-      uint2* s2 = reinterpret_cast<uint2*>(stage16 + off + head);  // 4 bf16 per 8-byte load
-SB_UNROLL(SB_COPY_UNROLL)
+      // 4 bf16 per 8-byte shared load -> one 128-bit streaming store
+      if constexpr (LANES > 4) {
+      uint2* s2 = reinterpret_cast<uint2*>(stage16 + off + head);
       for (int qv = lane; qv < nvec; qv += LANES) {
         const uint2 w = s2[qv];
         s2[qv] = make_uint2(0u, 0u);
         st_f4(dst + head + 4 * qv, __uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
               __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+      }
+      } else {
+      // narrow groups own ~10 vectors per lane: running pointers and two vectors per trip (the address
+      // arithmetic and the branch were half of this loop's instructions; measured 7.85 -> 7.71 ms at LANES = 4,
+      // but slower for 8- and 32-lane groups, which keep the simple loop)
+      uint2* sp = reinterpret_cast<uint2*>(stage16 + off + head) + lane;
+      float* gp = dst + head + 4 * lane;
+      int left = nvec - lane;  // vectors this lane still owns: left, left - LANES, ...
+      for (; left > LANES; left -= 2 * LANES, sp += 2 * LANES, gp += 8 * LANES) {
+        const uint2 w0 = sp[0], w1 = sp[LANES];
+        sp[0] = make_uint2(0u, 0u);
+        sp[LANES] = make_uint2(0u, 0u);
+        st_f4(gp, __uint_as_float(w0.x << 16), __uint_as_float(w0.x & 0xFFFF0000u), __uint_as_float(w0.y << 16),
+              __uint_as_float(w0.y & 0xFFFF0000u));
+        st_f4(gp + 4 * LANES, __uint_as_float(w1.x << 16), __uint_as_float(w1.x & 0xFFFF0000u),
+              __uint_as_float(w1.y << 16), __uint_as_float(w1.y & 0xFFFF0000u));
+      }
+      if (left > 0) {
+        const uint2 w = sp[0];
+        sp[0] = make_uint2(0u, 0u);
+        st_f4(gp, __uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+              __uint_as_float(w.y & 0xFFFF0000u));
+      }
       }
       if (etail < d.oh_size) {
         dst[etail] = __uint_as_float((uint32_t)stage16[off + etail] << 16);
@@ -296,8 +321,10 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
   return np1 ? launch(observe_kernel<true, 32>) : launch(observe_kernel<false, 32>);
 }
 
-// LPE  lanes per instance; RNG  SB_K_* sweep variant; NP1  one stored plane + one-hot fast path
-template <int LPE, int RNG, bool NP1>
+// LPE  lanes per instance; RNG  SB_K_* sweep variant; NP1  one stored plane + one-hot fast path;
+// STAGED  planes live in shared memory for the whole launch (compile-time, so that every access to the
+// instance image is an LDS / STS with 32-bit addressing instead of a generic load); false only with LPE == 32
+template <int LPE, int RNG, bool NP1, bool STAGED>
 __global__ void __launch_bounds__(SB_THREADS, 8)
     step_kernel(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -320,9 +347,11 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   // planes: staged in shared memory for the whole launch, or (large maps, p.staged == 0) used in
   // place in global memory so that shared memory does not cap the number of resident warps
   const long long env0 = (long long)blockIdx.x * EPB;
-  const int esz = p.staged ? p.plane_env : d.env_stride;
-  uint8_t* envs = p.staged ? smem_raw + p.planes_off : p.grid + (size_t)env0 * d.env_stride;
-  uint8_t* genv = envs + (size_t)grp * esz;
+  const int esz = STAGED ? p.plane_env : d.env_stride;
+  uint8_t* envs;
+  if constexpr (STAGED) envs = smem_raw + p.planes_off;
+  else envs = p.grid + (size_t)env0 * d.env_stride;
+  uint8_t* genv = envs + (STAGED ? grp * esz : (size_t)grp * esz);
   uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * 3 * d.A;
   int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
   int32_t* sfacing = sact + d.A;  // MovingAgent.direction (only read when d.ext_act)
@@ -345,7 +374,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   // ---- stage the instance ------------------------------------------------------------------
   uint4* genv4 = reinterpret_cast<uint4*>(genv);
   if (active) {
-    if (p.staged) {
+    if (STAGED) {
       const uint4* src = reinterpret_cast<const uint4*>(p.grid + (size_t)env * d.env_stride);
       for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = __ldg(src + c);
     }
@@ -356,7 +385,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       if (EXT) sfacing[a] = p.a.d_agent_facing ? p.a.d_agent_facing[(size_t)env * d.A + a] : 2;
     }
   } else {  // lanes past the last instance: never touch a grid (every access below is guarded by `active`)
-    if (p.staged)
+    if (STAGED)
       for (int c = lane; c < d.n_chunks; c += LPE) genv4[c] = make_uint4(~0u, ~0u, ~0u, ~0u);
     for (int a = lane; a < d.A; a += LPE) spos[a] = 0, sfacing[a] = 0;
   }
@@ -472,7 +501,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           const uint32_t g = entry >> 20, cell = entry & 0xFFFFFu;
           const uint32_t eid = (uint32_t)(d.env_id_base + (uint64_t)(env0 + g));
           const int kind = sb_resolve_candidate(d, eid, tick, cell, rk);
-          if (kind >= 0) envs[(size_t)g * esz + cell] = (uint8_t)kind;
+          if (kind >= 0) envs[(STAGED ? g * esz : (size_t)g * esz) + cell] = (uint8_t)kind;
         }
         __syncwarp();
         if (wlane == 0) *qn = 0;
@@ -566,7 +595,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       dsts[1] = (p.a.d_obs_out && active)
                     ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size
                     : nullptr;
-      if (NP1 && LPE == 32 && !p.staged) {
+      if (NP1 && LPE == 32 && !STAGED) {
         // large maps used in place in global memory: batch the window loads (one L2 round trip per row, not 3)
         emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
         if (p.a.d_obs_out) {
@@ -715,7 +744,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         // planes in global memory: start the load of the cell agent a will step on NOW (its position, its
         // action and every earlier agent's move are final), so the L2 round trip overlaps the observation
         int pre_tk = -1;
-        if (!p.staged && lane == 0 && active && !(EXT && d.ext_act)) {
+        if (!STAGED && lane == 0 && active && !(EXT && d.ext_act)) {
           const int tc = sb_target_cell(d, spos[a], sact[a]);
           if (tc >= 0) pre_tk = genv[d.agent_plane * d.plane_stride + tc];
         }
@@ -741,7 +770,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
 
   // ---- write the instance back ---------------------------------------------------------------
   if (active && p.write_back) {
-    if (p.staged) {
+    if (STAGED) {
       uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * d.env_stride);
       for (int c = lane; c < d.n_chunks; c += LPE) dst[c] = genv4[c];
     }
@@ -770,17 +799,21 @@ static int launch_one(const SbDev& d, StepParams p, cudaStream_t s) {
   p.staged = stage_planes(d) ? 1 : 0;
   const int smem = L.total;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
-  auto kern = step_kernel<LPE, RNG, NP1>;
-  if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return note_cuda_error();
-  }
-  const int epb = SB_THREADS / LPE;
-  const long long blocks = ((long long)d.N + epb - 1) / epb;
-  kern<<<(unsigned)blocks, SB_THREADS, smem, s>>>(d, p);
-  count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  auto go = [&](auto kern) -> int {
+    if (smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return note_cuda_error();
+    }
+    const int epb = SB_THREADS / LPE;
+    const long long blocks = ((long long)d.N + epb - 1) / epb;
+    kern<<<(unsigned)blocks, SB_THREADS, smem, s>>>(d, p);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
+    return SB_OK;
+  };
+  if (p.staged) return go(step_kernel<LPE, RNG, NP1, true>);
+  if constexpr (LPE == 32) return go(step_kernel<LPE, RNG, NP1, false>);  // pick_lpe: unstaged => one warp per instance
+  return SB_EUNSUPPORTED;
 }
 
 template <int LPE>
@@ -798,6 +831,7 @@ static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t 
 }
 
 int pick_lpe(const SbDev& d) {
+  if (!stage_planes(d)) return 32;  // planes used in place in global memory: one warp per instance
   if (const char* e = getenv("SB_LPE")) {
     int v = atoi(e);
     if (v == 4 || v == 8 || v == 16 || v == 32) return v;
