@@ -220,6 +220,7 @@ SB_UNROLL(SB_COPY_UNROLL)
   // NOTE: the caller must __syncwarp() before the staging row is scattered into again.
 }
 
+#ifndef SB_ONLY_LPE  // the step-kernel instantiations of one LPE are compiled in their own translation unit
 // ----------------------------------------------------------------------------------------------
 // Standalone observation kernel (sb_observe): a pure function of grid + positions, so every
 // (instance, agent) pair is independent: one warp per pair, window cells read straight from global
@@ -320,6 +321,8 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
   if (lanes == 16) return np1 ? launch(observe_kernel<true, 16>) : launch(observe_kernel<false, 16>);
   return np1 ? launch(observe_kernel<true, 32>) : launch(observe_kernel<false, 32>);
 }
+
+#endif  // SB_ONLY_LPE
 
 // LPE  lanes per instance; RNG  SB_K_* sweep variant; NP1  one stored plane + one-hot fast path;
 // STAGED  planes live in shared memory for the whole launch (compile-time, so that every access to the
@@ -830,6 +833,20 @@ static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t 
   }
 }
 
+#define SB_CAT2(a, b) a##b
+#define SB_CAT(a, b) SB_CAT2(a, b)
+#ifdef SB_ONLY_LPE
+// translation unit of ONE group width: every step_kernel<SB_ONLY_LPE, ...> instantiation (make -j compiles the
+// four widths and the rest of the library in parallel)
+int SB_CAT(launch_rng_, SB_ONLY_LPE)(const SbDev& d, const StepParams& p, int kr, cudaStream_t s) {
+  return launch_rng<SB_ONLY_LPE>(d, p, kr, s);
+}
+#else
+int launch_rng_4(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
+int launch_rng_8(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
+int launch_rng_16(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
+int launch_rng_32(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
+
 int pick_lpe(const SbDev& d) {
   if (!stage_planes(d)) return 32;  // planes used in place in global memory: one warp per instance
   if (const char* e = getenv("SB_LPE")) {
@@ -855,11 +872,13 @@ int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s) {
   else if (p.a.rng == SB_RNG_SPARSE) kr = SB_K_SPARSE;
   else kr = d.simd_sweep ? SB_K_PHILOX_SIMD : SB_K_PHILOX_GENERIC;
   switch (pick_lpe(d)) {
-    case 4: return launch_rng<4>(d, p, kr, s);
-    case 8: return launch_rng<8>(d, p, kr, s);
-    case 16: return launch_rng<16>(d, p, kr, s);
-    default: return launch_rng<32>(d, p, kr, s);
+    case 4: return launch_rng_4(d, p, kr, s);
+    case 8: return launch_rng_8(d, p, kr, s);
+    case 16: return launch_rng_16(d, p, kr, s);
+    default: return launch_rng_32(d, p, kr, s);
   }
 }
+
+#endif  // SB_ONLY_LPE
 
 }  // namespace sb
