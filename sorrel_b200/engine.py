@@ -137,6 +137,75 @@ def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
 
+def build_desc(spec: WorldSpec, num_envs: int, env_id_base: int, dyn_layers: list[int], env_stride: int,
+               h_appearance: np.ndarray, d_appearance: int, d_template: int, static_layers_invisible: bool,
+               obs_extra_width: int = 0, d_obs_extra: int = 0) -> tuple[SbWorldDesc, bool]:
+    """Fill `SbWorldDesc` from a `WorldSpec` (pure host code: the pointers are passed as integers, so the
+    descriptor logic and `sb_validate` are testable without a GPU).  Returns (descriptor, sparse mode available)."""
+    H, W, L = spec.height, spec.width, spec.layers
+    d = SbWorldDesc()
+    d.abi_version = _abi.SB_ABI_VERSION
+    d.num_envs, d.num_agents = num_envs, int(spec.num_agents)
+    d.height, d.width, d.num_layers = H, W, L
+    d.num_dyn_layers = len(dyn_layers)
+    for i, z in enumerate(dyn_layers):
+        d.dyn_layers[i] = z
+    d.agent_layer = spec.agent_layer
+    d.num_kinds = len(spec.kind_names)
+    d.num_channels = spec.channels
+    d.vision = spec.vision
+    d.fill_kind, d.agent_kind, d.default_kind = spec.fill_kind, spec.agent_kind, spec.default_kind
+    d.num_actions = len(spec.action_deltas)
+    for i, (dy, dx) in enumerate(spec.action_deltas[: _abi.SB_MAX_ACTIONS]):
+        d.action_dy[i], d.action_dx[i] = dy, dx
+    d.num_spawn_choices = len(spec.spawn_choices)
+    for i, k in enumerate(spec.spawn_choices[: _abi.SB_MAX_CHOICES]):
+        d.spawn_choice_kinds[i] = k
+    d.spawn_prob = float(spec.spawn_prob)
+    d.env_id_base = int(env_id_base)
+    for k in range(min(len(spec.kind_names), _abi.SB_MAX_KINDS)):
+        d.kind_value[k] = float(spec.kind_value[k])
+        d.kind_passable[k] = 1 if spec.kind_passable[k] else 0
+        d.kind_rule[k] = int(spec.kind_rule[k])
+    d.d_appearance = int(d_appearance)
+    d.h_appearance = h_appearance.ctypes.data
+    d.d_template = int(d_template)
+    d.static_layers_invisible = 1 if static_layers_invisible else 0
+    d.obs_transform = int(spec.obs_transform)
+    K = min(len(spec.kind_names), _abi.SB_MAX_KINDS)
+    for k in range(K):
+        d.kind_rule_prob[k] = float(spec.kind_rule_prob[k]) if spec.kind_rule_prob else 0.0
+        d.kind_rule_to[k] = int(spec.kind_rule_to[k]) if spec.kind_rule_to else _abi.SB_NO_KIND
+        d.kind_rule_layer[k] = int(spec.kind_rule_layer[k]) if spec.kind_rule_layer else -1
+        d.kind_rule_mask[k] = int(spec.kind_rule_mask[k]) if spec.kind_rule_mask else 0
+    d.uses_facing = 1 if spec.uses_facing else 0
+    for i in range(_abi.SB_MAX_ACTIONS):
+        d.action_facing[i] = int(spec.action_facing[i]) if spec.action_facing and i < len(spec.action_facing) else -1
+        d.action_beam_kind[i] = int(spec.action_beam_kind[i]) \
+            if spec.action_beam_kind and i < len(spec.action_beam_kind) else _abi.SB_NO_KIND
+    d.beam_layer = int(spec.beam_layer)
+    if spec.beam_offsets is not None:
+        bo = np.asarray(spec.beam_offsets)
+        if bo.shape[0] != 4 or bo.shape[1] > _abi.SB_MAX_BEAM_CELLS:
+            raise ValueError("beam_offsets must be [4, n <= SB_MAX_BEAM_CELLS, 2]")
+        d.num_beam_cells = int(bo.shape[1])
+        for f in range(4):
+            for b in range(bo.shape[1]):
+                d.beam_dy[f][b], d.beam_dx[f][b] = int(bo[f, b, 0]), int(bo[f, b, 1])
+    d.beam_block_mask = int(spec.beam_block_mask)
+    d.reward_all_layers = 1 if spec.reward_all_layers else 0
+    d.reward_count = int(spec.reward_count)
+    if obs_extra_width:
+        d.obs_extra = int(obs_extra_width)
+        d.d_obs_extra = int(d_obs_extra)
+    cdf = binomial_cdf_u64(env_stride, spec.spawn_prob) if env_stride < 65536 else None
+    if cdf is not None:
+        d.spawn_cdf_len = len(cdf)
+        for i, v in enumerate(cdf):
+            d.spawn_cdf[i] = v
+    return d, cdf is not None
+
+
 class Engine:
     """N instances of one `WorldSpec` on one CUDA device (one rank's shard)."""
 
@@ -188,67 +257,12 @@ class Engine:
             flat = (cells[:, 0] * W + cells[:, 1]).astype(np.int32)
             self.item_groups.append((int(kind), int(layer), int(count), torch.from_numpy(flat).to(self.device)))
 
-        d = SbWorldDesc()
-        d.abi_version = _abi.SB_ABI_VERSION
-        d.num_envs, d.num_agents = self.N, self.A
-        d.height, d.width, d.num_layers = H, W, L
-        d.num_dyn_layers = self.n_planes
-        for i, z in enumerate(self.dyn_layers):
-            d.dyn_layers[i] = z
-        d.agent_layer = spec.agent_layer
-        d.num_kinds = len(spec.kind_names)
-        d.num_channels = spec.channels
-        d.vision = spec.vision
-        d.fill_kind, d.agent_kind, d.default_kind = spec.fill_kind, spec.agent_kind, spec.default_kind
-        d.num_actions = len(spec.action_deltas)
-        for i, (dy, dx) in enumerate(spec.action_deltas[: _abi.SB_MAX_ACTIONS]):
-            d.action_dy[i], d.action_dx[i] = dy, dx
-        d.num_spawn_choices = len(spec.spawn_choices)
-        for i, k in enumerate(spec.spawn_choices[: _abi.SB_MAX_CHOICES]):
-            d.spawn_choice_kinds[i] = k
-        d.spawn_prob = float(spec.spawn_prob)
-        d.env_id_base = int(env_id_base)
-        for k in range(min(len(spec.kind_names), _abi.SB_MAX_KINDS)):
-            d.kind_value[k] = float(spec.kind_value[k])
-            d.kind_passable[k] = 1 if spec.kind_passable[k] else 0
-            d.kind_rule[k] = int(spec.kind_rule[k])
-        d.d_appearance = self.d_appearance.data_ptr()
-        d.h_appearance = self.h_appearance.ctypes.data
-        d.d_template = self.d_template.data_ptr()
-        d.static_layers_invisible = 1 if invisible else 0
-        d.obs_transform = int(spec.obs_transform)
-        K = min(len(spec.kind_names), _abi.SB_MAX_KINDS)
-        for k in range(K):
-            d.kind_rule_prob[k] = float(spec.kind_rule_prob[k]) if spec.kind_rule_prob else 0.0
-            d.kind_rule_to[k] = int(spec.kind_rule_to[k]) if spec.kind_rule_to else _abi.SB_NO_KIND
-            d.kind_rule_layer[k] = int(spec.kind_rule_layer[k]) if spec.kind_rule_layer else -1
-            d.kind_rule_mask[k] = int(spec.kind_rule_mask[k]) if spec.kind_rule_mask else 0
-        d.uses_facing = 1 if spec.uses_facing else 0
-        for i in range(_abi.SB_MAX_ACTIONS):
-            d.action_facing[i] = int(spec.action_facing[i]) if spec.action_facing and i < len(spec.action_facing) else -1
-            d.action_beam_kind[i] = int(spec.action_beam_kind[i]) \
-                if spec.action_beam_kind and i < len(spec.action_beam_kind) else _abi.SB_NO_KIND
-        d.beam_layer = int(spec.beam_layer)
-        if spec.beam_offsets is not None:
-            bo = np.asarray(spec.beam_offsets)
-            if bo.shape[0] != 4 or bo.shape[1] > _abi.SB_MAX_BEAM_CELLS:
-                raise ValueError("beam_offsets must be [4, n <= SB_MAX_BEAM_CELLS, 2]")
-            d.num_beam_cells = int(bo.shape[1])
-            for f in range(4):
-                for b in range(bo.shape[1]):
-                    d.beam_dy[f][b], d.beam_dx[f][b] = int(bo[f, b, 0]), int(bo[f, b, 1])
-        d.beam_block_mask = int(spec.beam_block_mask)
-        d.reward_all_layers = 1 if spec.reward_all_layers else 0
-        d.reward_count = int(spec.reward_count)
-        if self.d_obs_extra is not None:
-            d.obs_extra = int(self.d_obs_extra.shape[1])
-            d.d_obs_extra = self.d_obs_extra.data_ptr()
-        cdf = binomial_cdf_u64(self.env_stride, spec.spawn_prob) if self.env_stride < 65536 else None
-        self.sparse_available = cdf is not None
-        if cdf is not None:
-            d.spawn_cdf_len = len(cdf)
-            for i, v in enumerate(cdf):
-                d.spawn_cdf[i] = v
+        self.desc, self.sparse_available = build_desc(
+            spec, self.N, env_id_base, self.dyn_layers, self.env_stride, self.h_appearance,
+            self.d_appearance.data_ptr(), self.d_template.data_ptr(), invisible,
+            0 if self.d_obs_extra is None else int(self.d_obs_extra.shape[1]),
+            0 if self.d_obs_extra is None else self.d_obs_extra.data_ptr())
+        d = self.desc
         self.desc = d
         check(self.lib.sb_validate(C.byref(d)), "world description")
 

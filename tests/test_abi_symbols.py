@@ -85,3 +85,70 @@ def test_no_cpu_fallback():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def _host_desc(spec):
+    """SbWorldDesc for an oracle spec without touching a GPU (device pointers are opaque non-NULL integers:
+    sb_validate only reads the HOST copy of the appearance table)."""
+    import numpy as np
+
+    import sb_testutil as util
+    from sorrel_b200 import _abi
+    from sorrel_b200.engine import build_desc
+
+    es = util.engine_spec(spec)
+    dyn = es.resolved_dynamic_layers()
+    stride = (es.height * es.width + 15) // 16 * 16
+    happ = np.ascontiguousarray(es.appearance, dtype=np.float64)
+    width = 0 if es.obs_extra is None else int(es.obs_extra.shape[2])
+    d, _ = build_desc(es, 8, 0, dyn, len(dyn) * stride, happ, 0x1000, 0x2000, True, width, 0x3000 if width else 0)
+    return d, happ, _abi
+
+
+def test_descriptor_validation_without_gpu(built_lib):
+    """sb_validate on real world descriptions and on every way of breaking them (status codes of SURVEY §8b)."""
+    from oracle import restatement as R
+
+    L = built_lib.lib()
+    ok, inval, unsup, evision = built_lib.SB_OK, built_lib.SB_EINVAL, built_lib.SB_EUNSUPPORTED, built_lib.SB_EVISION
+    for spec in (R.treasurehunt_spec(), R.treasurehunt_spec(9, 15, 4, 3, 0.03, obs="rgb"), R.cleanup_spec()):
+        d, keep, _ = _host_desc(spec)
+        assert L.sb_validate(ctypes.byref(d)) == ok
+
+    def broken(spec, mutate):
+        d, keep, _ = _host_desc(spec)
+        mutate(d)
+        return L.sb_validate(ctypes.byref(d))
+
+    th, cl = R.treasurehunt_spec(), R.cleanup_spec()
+    assert broken(th, lambda d: setattr(d, "abi_version", 1)) == inval
+    assert broken(th, lambda d: setattr(d, "vision", 11)) == evision  # > (H-1)//2: visual_field.py:78-87
+    assert broken(th, lambda d: setattr(d, "num_kinds", 33)) == unsup
+    assert broken(th, lambda d: setattr(d, "spawn_prob", 1.5)) == inval
+    assert broken(th, lambda d: setattr(d, "fill_kind", 9)) == inval
+    assert broken(th, lambda d: setattr(d, "d_template", None)) == inval
+    assert broken(th, lambda d: d.kind_rule.__setitem__(0, 9)) == unsup  # unknown rule id
+    assert broken(th, lambda d: setattr(d, "agent_layer", 0)) == inval  # agent layer must be dynamic
+    # column rules
+    assert broken(cl, lambda d: d.kind_rule_prob.__setitem__(2, 2.0)) == inval  # River: probability > 1
+    assert broken(cl, lambda d: d.kind_rule_to.__setitem__(4, 40)) == inval  # AppleTree -> unknown kind
+    assert broken(cl, lambda d: d.kind_rule_layer.__setitem__(3, 5)) == inval  # Pollution tests a missing layer
+    # beams / facings / positional code
+    assert broken(cl, lambda d: setattr(d, "beam_layer", 7)) == inval
+    assert broken(cl, lambda d: setattr(d, "num_beam_cells", 17)) == unsup
+    assert broken(cl, lambda d: d.action_facing.__setitem__(0, 4)) == inval
+    assert broken(cl, lambda d: d.action_beam_kind.__setitem__(4, 99)) == inval
+    assert broken(cl, lambda d: setattr(d, "d_obs_extra", None)) == inval
+
+
+def test_item_group_struct_matches_header(built_lib):
+    import subprocess
+    import tempfile
+
+    src = '#include <stdio.h>\n#include "sorrel_b200.h"\nint main(){printf("%zu\\n",sizeof(SbItemGroup));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        assert int(subprocess.check_output([exe]).split()[0]) == ctypes.sizeof(built_lib.SbItemGroup)
