@@ -139,3 +139,64 @@ def test_cleanup_observe_standalone(cuda_device):
         want = np.concatenate((R.observe(spec, oenv.grid, y, x).reshape(-1), spec.obs_extra[y, x])).astype(np.float32)
         np.testing.assert_array_equal(obs[2, a].cpu().numpy(), want)
     eng.check_errors()
+
+
+def test_cleanup_full_size_invariants(cuda_device):
+    """The example's own shape at 16 384 instances x 10 agents x 40 turns (sizes the oracle cannot replay in a test):
+    size-independent invariants of the rule set."""
+    spec = R.cleanup_spec()
+    H, W, A = spec.height, spec.width, spec.num_agents
+    N, T, cap = 1 << 14, 40, 4
+    eng = _engine(spec, N, cuda_device, seed=21)
+    buf = _buffer(spec, N, cap, cuda_device)
+    eng.reset()
+    rew = torch.zeros((T, N, A), dtype=torch.float32, device=cuda_device)
+    act = torch.zeros((T, N, A), dtype=torch.int32, device=cuda_device)
+    eng.step(T, buffer=buf, reward_out=rew, action_out=act)
+    eng.check_errors()
+    g = eng.grid[:, :, : H * W].view(N, 3, H, W)
+    tmpl = torch.from_numpy(np.moveaxis(spec.template, 2, 0).copy()).to(cuda_device)  # [3, H, W]
+    obj, agents, beams = g[:, 0], g[:, 1], g[:, 2]
+    # walls never move or appear, on any layer
+    assert ((g == 1) == (tmpl == 1)[None]).all()
+    # object layer: River <-> Pollution on river cells, AppleTree <-> Apple on orchard cells, Sand fixed
+    river, orchard, sand = (tmpl[0] == 2)[None], (tmpl[0] == 4)[None], (tmpl[0] == 9)[None]
+    assert (((obj == 2) | (obj == 3)) == river).all() and (((obj == 4) | (obj == 5)) == orchard).all()
+    assert ((obj == 9) == sand).all()
+    # agent layer: exactly A agents per instance, at their recorded positions; nothing else but walls / empty
+    assert ((agents == 8).sum(dim=(1, 2)) == A).all()
+    assert (agents.reshape(N, -1).gather(1, eng.agent_pos.long()) == 8).all()
+    assert ((agents == 0) | (agents == 1) | (agents == 8)).all()
+    # beam layer: empty, wall, or a beam of either age; a beam lives at most two sweeps
+    assert ((beams == 0) | (beams == 1) | (beams == 6) | (beams == 7) | (beams == 10) | (beams == 11)).all()
+    # an Apple never lies under an agent after the sweep... but it may right after a move: only check the rule's
+    # direction: pollution spawns at Bernoulli(0.009) per river cell and turn and is only removed by CleanBeams
+    n_river = int(river.sum())
+    frac = float((obj == 3).sum()) / (N * n_river)
+    assert 0.1 < frac < 1 - (1 - 0.009) ** T + 0.02
+    # rewards: +1 per Apple tile entered, -1 per ZapBeam over the target tile, integers in [-1, 1] here; cleanup
+    # adds every reward to world.total_reward twice
+    assert ((rew == -1) | (rew == 0) | (rew == 1)).all()
+    assert torch.equal(eng.total_reward, 2.0 * rew.double().sum(dim=(0, 2)))
+    assert ((act >= 0) & (act < 6)).all() and float((act >= 4).float().mean()) > 0.3  # both beams are used
+    # facings are what the last movement action left (or the initial 2)
+    moved = act < 4
+    last = torch.where(moved, torch.arange(T, device=cuda_device)[:, None, None], -1).max(dim=0).values
+    table = torch.tensor([0, 2, 3, 1], device=cuda_device)
+    want = torch.where(last >= 0, table[act.long().gather(0, last.clamp(min=0)[None])[0]], 2)
+    assert torch.equal(eng.agent_facing.long(), want)
+    # observation rows: crop entries are small non-negative integers (layers summed), own channel set at the centre,
+    # and the last 12 floats are the positional code of the cell the agent observed from
+    st = buf.states.view(N * A, cap, -1)
+    crop = st[:, :, : spec.onehot_size].view(N * A, cap, 9, 11, 11)
+    assert ((crop == 0) | (crop == 1) | (crop == 2) | (crop == 3)).all() and (crop[:, :, 0] == 0).all()
+    assert (crop[:, :, 8, 5, 5] == 1).all()
+    codes = torch.from_numpy(spec.obs_extra.reshape(H * W, -1).astype(np.float32)).to(cuda_device)
+    got = st[:, :, spec.onehot_size:]
+    # the row in slot (T-1) % cap was observed from the position BEFORE the last move; check membership instead:
+    # every code row equals some cell's code and that cell is within 1 step of the final position
+    final = eng.agent_pos.reshape(-1).long()
+    slot = (T - 1) % cap
+    cand = torch.stack([final, final - 1, final + 1, final - W, final + W], dim=1).clamp(0, H * W - 1)
+    match = (codes[cand] == got[:, slot][:, None, :]).all(dim=2).any(dim=1)
+    assert match.all()
