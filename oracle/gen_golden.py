@@ -318,9 +318,90 @@ def cleanup_cases():
                      pollution_p=0.05, n_frames=3)  # two episodes: facings persist across reset, ring add_empty
 
 
+IOWA_IDS = {"EmptyEntity": 0, "Wall": 1, "Sand": 2, "GamblingAgent": 7}
+IOWA_DECK_VALUES = {"a": (1.1, -1.4), "b": (1.1, -11.4), "c": (0.6, 0.1), "d": (0.6, -1.9)}
+
+
+def iowa_grid_ids(world) -> np.ndarray:
+    """Kind ids of a GamblingWorld; a Deck's mutable value selects one of its three rows (fresh / win / loss)."""
+    H, W, L = world.map.shape
+    g = np.zeros((H, W, L), dtype=np.uint8)
+    for idx, e in np.ndenumerate(world.map):
+        name = type(e).__name__
+        if name == "Deck":
+            i = "abcd".index(e.name)
+            win, lose = IOWA_DECK_VALUES[e.name]
+            if e.value == 0:
+                g[idx] = 3 + i
+            elif e.value == win:
+                g[idx] = 8 + 2 * i
+            else:
+                assert e.value == lose, (e.name, e.value)
+                g[idx] = 9 + 2 * i
+        else:
+            g[idx] = IOWA_IDS[name]
+    return g
+
+
+def run_iowa_case(name, seed, H, W, v, p, T, epochs=1):
+    """examples/iowa with the reference's RandomModel instead of IQN (2 agents, as iowa/env.py:41 hard-codes)."""
+    from sorrel.examples.iowa.entities import EmptyEntity as IEmpty
+    from sorrel.examples.iowa.env import GamblingEnv
+    from sorrel.examples.iowa.world import GamblingWorld
+
+    config = {"experiment": {"epochs": epochs, "max_turns": T, "record_period": 50},
+              "model": {"agent_vision_radius": v, "epsilon_decay": 0.0005,
+                        "parameters": {"layer_size": 16, "epsilon": 0.5, "device": "cpu", "n_frames": 1}},
+              "world": {"height": H, "width": W, "spawn_prob": p}}
+    world = GamblingWorld(config=config, default_entity=IEmpty())
+    env = GamblingEnv(world, config)
+    cap = T * epochs
+    for ag in env.agents:
+        m = RandomModel(ag.observation_spec.input_size, 4, cap)
+        m.memory = Buffer(capacity=cap, obs_shape=tuple(ag.observation_spec.input_size), n_frames=1)
+        m.memory.extra_data["positions"] = np.zeros((cap, 2), dtype=np.int64)
+        ag.model = m
+    log = DrawLog()
+    grids, starts, totals = [], [], []
+    with record(log):
+        set_seed(seed)
+        for ep in range(epochs):
+            env.reset()
+            starts.append([ag.location[:2] for ag in env.agents])
+            for t in range(T):
+                env.take_turn()
+                grids.append(iowa_grid_ids(world))
+            world.is_done = True
+            totals.append(world.total_reward)
+    mems = [ag.model.memory for ag in env.agents]
+    data = dict(
+        world="iowa", seed=seed, H=H, W=W, A=len(env.agents), v=v, p=p, T=T, epochs=epochs, capacity=cap, n_frames=1,
+        starts=np.array(starts, dtype=np.int64), grids=np.array(grids, dtype=np.uint8),
+        total_reward=np.array(totals, dtype=np.float64),
+        states=np.stack([b.states for b in mems]), actions=np.stack([b.actions for b in mems]),
+        rewards=np.stack([b.rewards for b in mems]), dones=np.stack([b.dones for b in mems]),
+        positions=np.stack([b.extra_data["positions"] for b in mems]),
+        buf_idx=np.array([b.idx for b in mems]), buf_size=np.array([b.size for b in mems]),
+        n_uniform=np.int64(sum(1 for c in log.calls if c[0] == "random")),
+    )
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **data)
+    r = np.stack([b.rewards for b in mems])
+    print(f"{name}: total_reward={totals} uniforms={int(data['n_uniform'])} distinct rewards={np.unique(r)} "
+          f"-> {os.path.getsize(path)} B")
+
+
+def iowa_cases():
+    run_iowa_case("iowa_s4_20", 4, 20, 20, 2, 0.01, 100)  # the example's own shape (iowa/main.py)
+    run_iowa_case("iowa_s6_9x12", 6, 9, 12, 2, 0.08, 60, epochs=2)  # dense decks: every value state is visited
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "transformer":
         transformer_case()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "iowa":
+        iowa_cases()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "cleanup":
         cleanup_cases()
@@ -349,6 +430,7 @@ def main():
     transformer_case()
     observe_cases()
     cleanup_cases()
+    iowa_cases()
 
 
 if __name__ == "__main__":

@@ -15,7 +15,7 @@ def golden_cases(max_cells: int = 64 * 64, with_large: bool = False):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name.startswith(("observe_", "transformer_", "cleanup_")):
+        if name.startswith(("observe_", "transformer_", "cleanup_", "iowa_")):
             continue
         if name.startswith("large") and not with_large:
             continue
@@ -34,6 +34,14 @@ def cleanup_cases():
 def cleanup_spec_from_golden(g) -> R.WorldSpec:
     return R.cleanup_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), int(g["initial_apples"]),
                           float(g["apple_p"]), float(g["pollution_p"]), int(g["beam_radius"]))
+
+
+def iowa_cases():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "iowa_*.npz")))
+
+
+def iowa_spec_from_golden(g) -> R.WorldSpec:
+    return R.iowa_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), float(g["p"]))
 
 
 def spec_from_golden(g) -> R.WorldSpec:
@@ -55,7 +63,8 @@ def engine_spec(o: R.WorldSpec):
         dynamic_layers=list(o.dynamic_layers) if o.dynamic_layers else None,
         obs_transform=int(getattr(o, "obs_transform", 0)),
         action_deltas=[tuple(d) for d in o.action_deltas],
-        kind_rule_prob=o.kind_rule_prob, kind_rule_to=o.kind_rule_to, kind_rule_layer=o.kind_rule_layer,
+        kind_rule_prob=o.kind_rule_prob, kind_rule_to=o.kind_rule_to, kind_rule_else=o.kind_rule_else,
+        kind_rule_layer=o.kind_rule_layer,
         kind_rule_mask=o.kind_rule_mask, action_facing=o.action_facing, action_beam_kind=o.action_beam_kind,
         beam_layer=o.beam_layer, beam_offsets=o.beam_offsets, beam_block_mask=o.beam_block_mask,
         reward_all_layers=o.reward_all_layers, reward_count=o.reward_count, initial_facing=o.initial_facing,

@@ -186,3 +186,28 @@ def test_restatement_reproduces_reference_cleanup(name):
             assert arr.dtype == g[key].dtype, key
             np.testing.assert_array_equal(arr, g[key][a], err_msg=key)
         assert b.idx == int(g["buf_idx"][a]) and b.size == int(g["buf_size"][a])
+
+
+@pytest.mark.parametrize("name", util.iowa_cases())
+def test_restatement_reproduces_reference_iowa(name):
+    """examples/iowa (per-entity mutable value): decks redraw their value at every sweep (three
+    kind rows per deck), a deck spawned this turn is worth 0 until its first sweep, Sand is visible, walls on both
+    layers; rewards are non-integer Python floats, so `total_reward` is checked in float64 and the buffer in float32."""
+    g = util.load_golden(name)
+    spec = util.iowa_spec_from_golden(g)
+    T, E = int(g["T"]), int(g["epochs"])
+    env = R.OracleEnv(spec, R.NumpyDraws(int(g["seed"])), capacity=int(g["capacity"]))
+    gi = 0
+    for ep in range(E):
+        env.reset()
+        np.testing.assert_array_equal(env.pos, g["starts"][ep])
+        for t in range(T):
+            env.take_turn()
+            np.testing.assert_array_equal(env.grid, g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+            gi += 1
+        assert env.total_reward == float(g["total_reward"][ep])
+    for a, b in enumerate(env.buffers):
+        for key, arr in (("states", b.states), ("actions", b.actions), ("rewards", b.rewards),
+                         ("dones", b.dones), ("positions", b.positions)):
+            assert arr.dtype == g[key].dtype, key
+            np.testing.assert_array_equal(arr, g[key][a], err_msg=key)
