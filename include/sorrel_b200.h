@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 2
+#define SB_ABI_VERSION 3
 
 #define SB_MAX_KINDS 32    /* entity classes per world (kind ids are uint8 < SB_MAX_KINDS) */
 #define SB_MAX_CHANNELS 32 /* observation channels C = len(entity_list) */
@@ -70,8 +70,10 @@ typedef enum SbStatus {
    reference's shipped rule sets do.  The sweep visits the planes in ascending layer order, so a rule
    sees lower layers after, higher layers before their own transition of the turn -- exactly the
    C-order np.ndenumerate sweep of Environment.take_turn (environment.py:88-91). */
-#define SB_RULE_SPAWN_TO 2  /* Bernoulli(kind_rule_prob[k]) -> kind_rule_to[k], no choice draw:
-                               River -> Pollution, AppleTree -> Apple (examples/cleanup/entities.py:43-54,74-90) */
+#define SB_RULE_SPAWN_TO 2  /* Bernoulli(kind_rule_prob[k]) -> kind_rule_to[k], else kind_rule_else[k] (SB_NO_KIND =
+                               unchanged), one uniform, no choice draw: River -> Pollution, AppleTree -> Apple
+                               (examples/cleanup/entities.py:43-54,74-90); Deck.transition / draw with the mutable
+                               value folded into the kind id (examples/iowa/entities.py:33-69) */
 #define SB_RULE_BECOME_IF 3 /* the cell of the same column on layer kind_rule_layer[k] holds a kind of
                                kind_rule_mask[k] -> kind_rule_to[k]: Pollution under a CleanBeam -> River,
                                Apple under an agent -> AppleTree (cleanup/entities.py:57-71,93-105) */
@@ -170,6 +172,12 @@ typedef struct SbWorldDesc {
   const float* d_obs_extra;  /* device [H*W][obs_extra], row of the agent's cell: positional code
                                 (CleanupObservation.observe cleanup/agents.py:52-62, observation/embedding.py:8-44),
                                 computed by the caller (numpy, f64 -> f32 like Buffer.states) */
+  /* ---- ABI v3: value states (examples/iowa) ---- */
+  uint8_t kind_rule_else[SB_MAX_KINDS]; /* SB_RULE_SPAWN_TO: kind when the draw fails; SB_NO_KIND = unchanged */
+  int32_t use_value64;                  /* 1: rewards are kind_value64 (Python floats such as 1.1 or -1.4): the ring
+                                           stores (float)value, world.total_reward accumulates the double */
+  int32_t reserved2;
+  double kind_value64[SB_MAX_KINDS];
 } SbWorldDesc;
 
 /* One group of items placed on distinct cells at reset, before the agents (cleanup/env.py:126-132:

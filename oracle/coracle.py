@@ -25,9 +25,10 @@ class OrWorld(C.Structure):
         ("n_choices", C.c_int32), ("choices", C.c_int32 * 8),
         ("n_spawnable", C.c_int32), ("obs_transform", C.c_int32),
         ("p", C.c_double),
-        ("value", C.c_float * 32), ("passable", C.c_uint8 * 32), ("rule", C.c_uint8 * 32),
+        ("value", C.c_double * 32), ("passable", C.c_uint8 * 32), ("rule", C.c_uint8 * 32),
         ("appearance", C.c_void_p), ("tmpl", C.c_void_p), ("spawnable", C.c_void_p),
-        ("rule_prob", C.c_double * 32), ("rule_to", C.c_uint8 * 32), ("rule_layer", C.c_int8 * 32),
+        ("rule_prob", C.c_double * 32), ("rule_to", C.c_uint8 * 32), ("rule_else", C.c_uint8 * 32),
+        ("rule_layer", C.c_int8 * 32),
         ("rule_mask", C.c_uint32 * 32),
         ("uses_facing", C.c_int32), ("initial_facing", C.c_int32),
         ("action_facing", C.c_int8 * 8), ("action_beam_kind", C.c_uint8 * 8),
@@ -118,6 +119,7 @@ class COracle:
         for k in range(w.K):
             w.rule_prob[k] = float(spec.kind_rule_prob[k]) if spec.kind_rule_prob else 0.0
             w.rule_to[k] = int(spec.kind_rule_to[k]) if spec.kind_rule_to else R.NO_KIND
+            w.rule_else[k] = int(spec.kind_rule_else[k]) if spec.kind_rule_else else R.NO_KIND
             w.rule_layer[k] = int(spec.kind_rule_layer[k]) if spec.kind_rule_layer else -1
             w.rule_mask[k] = int(spec.kind_rule_mask[k]) if spec.kind_rule_mask else 0
         w.uses_facing = 1 if (spec.action_facing is not None or spec.action_beam_kind is not None) else 0

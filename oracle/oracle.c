@@ -170,7 +170,7 @@ typedef struct {
   int32_t n_spawnable;
   int32_t obs_transform; /* 0 none, 1 RGB: clip(sum, 0, 255) / 255 (observation_spec.py:483) */
   double p;
-  float value[OR_MAX_KINDS];
+  double value[OR_MAX_KINDS]; /* Entity.value as the Python float it is (iowa: 1.1, -1.4, ...) */
   uint8_t passable[OR_MAX_KINDS], rule[OR_MAX_KINDS];
   const double* appearance; /* [K][C] */
   const uint8_t* tmpl;      /* [H][W][L] (reference index order y, x, z) */
@@ -178,6 +178,7 @@ typedef struct {
   /* ---- column rules, facings + beams, all-layer rewards, positional code, item groups (examples/cleanup) ---- */
   double rule_prob[OR_MAX_KINDS];
   uint8_t rule_to[OR_MAX_KINDS];
+  uint8_t rule_else[OR_MAX_KINDS]; /* SPAWN_TO: kind when the draw fails, OR_NO_KIND = unchanged */
   int8_t rule_layer[OR_MAX_KINDS];
   uint32_t rule_mask[OR_MAX_KINDS];
   int32_t uses_facing, initial_facing;
@@ -413,6 +414,8 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
               } else {
                 *cellp = w->rule_to[kind];
               }
+            } else if (rule == OR_RULE_SPAWN_TO && w->rule_else[kind] != OR_NO_KIND) {
+              *cellp = w->rule_else[kind]; /* iowa Deck.draw: the no-loss value state */
             }
           } else {
             uint32_t r[4];
@@ -421,11 +424,15 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
             const uint64_t lo45 = thr & ((1ull << 45) - 1);
             philox(env, tick, pcell >> 4, DOM_SWEEP, k0, k1, r);
             uint32_t b = pcell & 15, r8 = (r[b >> 2] >> (8 * (b & 3))) & 0xFF;
-            if (r8 > hi8) continue;
-            if (rule == OR_RULE_SPAWN || r8 == hi8) philox(env, tick, pcell, DOM_CELL, k0, k1, r);
-            if (r8 == hi8) {
+            int hit = r8 <= hi8;
+            if (hit && (rule == OR_RULE_SPAWN || r8 == hi8)) philox(env, tick, pcell, DOM_CELL, k0, k1, r);
+            if (hit && r8 == hi8) {
               uint64_t refine = (((uint64_t)r[0] << 13) | (r[1] >> 19)) & ((1ull << 45) - 1);
-              if (!(refine < lo45)) continue;
+              hit = refine < lo45;
+            }
+            if (!hit) {
+              if (rule == OR_RULE_SPAWN_TO && w->rule_else[kind] != OR_NO_KIND) *cellp = w->rule_else[kind];
+              continue;
             }
             if (rule == OR_RULE_SPAWN) *cellp = (uint8_t)w->choices[bounded64(r[2], r[3], (uint32_t)w->n_choices)];
             else *cellp = w->rule_to[kind];
@@ -459,7 +466,7 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
           }
       }
       int ny = y + w->dy[action], nx = x + w->dx[action];
-      float reward = 0.0f;
+      double reward = 0.0; /* the Python float the reference adds to world.total_reward; the ring stores float32 */
       if (ny >= 0 && ny < w->H && nx >= 0 && nx < w->W) {
         uint8_t* tp = g + ((size_t)ny * w->W + nx) * w->L + w->agent_layer;
         if (w->reward_all_layers) { /* observe_all_layers, cleanup/agents.py:160-170 */
@@ -475,11 +482,11 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
         }
       }
       /* agent.py:172 (cleanup adds the reward a second time in act(): cleanup/agents.py:172) */
-      e->total[n] += (double)reward * (double)(w->reward_count > 0 ? w->reward_count : 1);
+      e->total[n] += reward * (double)(w->reward_count > 0 ? w->reward_count : 1);
       if (e->capacity > 0) {          /* Buffer.add, buffers.py:46-63; position AFTER the move */
         size_t at = (size_t)slot * rows + row;
         e->actions[at] = action;
-        e->rewards[at] = reward;
+        e->rewards[at] = (float)reward;
         e->dones[at] = 0.0f; /* world.is_done is False during the episode */
         e->positions[2 * at] = y;
         e->positions[2 * at + 1] = x;

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-SB_ABI_VERSION = 2
+SB_ABI_VERSION = 3
 SB_MAX_KINDS = 32
 SB_MAX_CHANNELS = 32
 SB_MAX_LAYERS = 8
@@ -85,6 +85,11 @@ class SbWorldDesc(C.Structure):
         ("reward_count", C.c_int32),
         ("obs_extra", C.c_int32),
         ("d_obs_extra", C.c_void_p),
+        # ---- ABI v3 ----
+        ("kind_rule_else", C.c_uint8 * SB_MAX_KINDS),
+        ("use_value64", C.c_int32),
+        ("reserved2", C.c_int32),
+        ("kind_value64", C.c_double * SB_MAX_KINDS),
     ]
 
 

@@ -105,6 +105,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     const int rule = w->kind_rule[k];
     d.rule[k] = (uint8_t)rule;
     d.rule_to[k] = w->kind_rule_to[k];
+    d.rule_else[k] = w->kind_rule_else[k];
+    d.value64[k] = w->use_value64 ? w->kind_value64[k] : (double)w->kind_value[k];
     if (rule == SB_RULE_SPAWN) {
       d.spawn_mask |= 1u << k;
       d.draw_mask |= 1u << k;
@@ -114,6 +116,7 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
       ++n_spawn_kinds;
     } else if (rule == SB_RULE_SPAWN_TO) {
       if (!(w->kind_rule_prob[k] >= 0.0) || w->kind_rule_prob[k] > 1.0 || !kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
+      if (w->kind_rule_else[k] != SB_NO_KIND && !kind_ok(w->kind_rule_else[k])) return SB_EINVAL;
       d.draw_mask |= 1u << k;
       d.prob[k] = w->kind_rule_prob[k];
       d.thr53[k] = spawn_threshold(d.prob[k]);
@@ -163,7 +166,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
       d.beam_block_mask = w->beam_block_mask;
     }
   }
-  d.ext_act = (w->uses_facing || d.reward_all || d.reward_count != 1) ? 1 : 0;
+  d.use_value64 = w->use_value64 ? 1 : 0;
+  d.ext_act = (w->uses_facing || d.reward_all || d.reward_count != 1 || d.use_value64) ? 1 : 0;
   if (n_spawn_kinds > 0 && d.n_choices == 0 && d.p > 0.0) return SB_EINVAL;
   for (int i = 0; i < d.n_choices; ++i) {
     if (!kind_ok(w->spawn_choice_kinds[i])) return SB_EINVAL;

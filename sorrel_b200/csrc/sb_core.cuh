@@ -59,7 +59,9 @@ struct SbDev {
   int32_t ext_act;    // facings / beams / all-layer rewards / reward_count != 1
   uint32_t draw_mask; // kinds whose rule consumes a uniform (SPAWN, SPAWN_TO)
   uint32_t det_mask;  // kinds with a deterministic rule (BECOME_IF, BECOME)
-  uint8_t rule[SB_MAX_KINDS], rule_to[SB_MAX_KINDS];
+  uint8_t rule[SB_MAX_KINDS], rule_to[SB_MAX_KINDS], rule_else[SB_MAX_KINDS];
+  int32_t use_value64;           // rewards are value64 (Python floats that float32 cannot hold)
+  double value64[SB_MAX_KINDS];  // total_reward accumulates these; the ring stores (float)value64
   int32_t rule_plane_off[SB_MAX_KINDS];  // BECOME_IF: byte offset of the tested plane
   uint32_t rule_mask[SB_MAX_KINDS];
   uint64_t thr53[SB_MAX_KINDS];  // ceil(prob * 2^53) per drawing kind
@@ -249,8 +251,10 @@ SB_HD int sb_target_cell(const SbDev& d, uint32_t yx, int action) {
 }
 
 // `pre_tk` >= 0: kind of the target cell already loaded by the caller (same cell, same state).
+// `reward64` != nullptr (worlds with use_value64 / all-layer rewards): receives the reward as the double the
+// reference adds to world.total_reward; the returned float is its float32 rounding (Buffer.rewards).
 SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action, bool writer,
-                         uint32_t& err, bool all_layers = false, int pre_tk = -1) {
+                         uint32_t& err, bool all_layers = false, int pre_tk = -1, double* reward64 = nullptr) {
   int y = (int)(*yx >> 16), x = (int)(*yx & 0xFFFFu);
   int dy = 0, dx = 0;
   if ((unsigned)action < (unsigned)d.n_actions) {
@@ -271,14 +275,19 @@ SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action
     return 0.0f;
   }
   float reward = d.value[tk];  // reward = value of the entity at the target cell (agent.py:219-220)
+  if (reward64) *reward64 = d.value64[tk];
   if (all_layers) {  // sum over every layer of the target column (observe_all_layers, cleanup/agents.py:160-170)
-    reward = 0.0f;
+    double r64 = 0.0;
     for (int z = 0; z < d.L; ++z) {
       const int pl = d.plane_of_layer[z];
       const uint32_t k = pl >= 0 ? genv[pl * d.plane_stride + ny * d.W + nx] : d.tmpl[z * d.plane_stride + ny * d.W + nx];
-      if (k < (uint32_t)d.K) reward += d.value[k];
+      if (k < (uint32_t)d.K) r64 += d.value64[k];
       else err |= SB_ERR_BAD_KIND;
     }
+    reward = (float)r64;
+    if (reward64) *reward64 = r64;
+  } else if (reward64) {
+    reward = (float)*reward64;  // Buffer.rewards is float32 (buffers.py:33,58)
   }
   if ((d.passable_mask >> tk) & 1u) {
     if (writer) {

@@ -453,6 +453,8 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
                 } else {
                   genv[cell] = d.rule_to[kind];
                 }
+              } else if (rule == SB_RULE_SPAWN_TO && d.rule_else[kind] != SB_NO_KIND) {
+                genv[cell] = d.rule_else[kind];  // iowa Deck.draw: the no-loss value state
               }
             } else {
               if (u == u) err |= SB_ERR_TAPE_ALIGN;  // tape holds a draw for a cell that has no drawing rule
@@ -576,6 +578,8 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
                   if (nk >= 0) genv[cell] = (uint8_t)nk;
                 } else if (sb_bernoulli_hit(d.thr53[kind], r8, envid, tick, cell, rk)) {
                   genv[cell] = d.rule_to[kind];
+                } else if (d.rule_else[kind] != SB_NO_KIND) {
+                  genv[cell] = d.rule_else[kind];
                 }
               } else {
                 const int nk = sb_column_rule(d, genv, kind, rule, cc * 16 + b);
@@ -631,10 +635,10 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
     };
 
     // one agent's move by ONE lane: MovingAgent.act + Gridworld.move + the scalar part of Buffer.add
-    auto move_and_record = [&](int a, int pre_tk) -> float {
+    auto move_and_record = [&](int a, int pre_tk, double* reward64 = nullptr) -> float {
       uint32_t yx = spos[a];
       const int action = sact[a];
-      const float reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all, pre_tk);
+      const float reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all, pre_tk, reward64);
       spos[a] = yx;
       const size_t row = row0 + a;
       if (p.has_buf) {
@@ -680,8 +684,13 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       }
       if (lane == 0 && active) {
         // world.total_reward += reward (agent.py:172; cleanup adds it twice: cleanup/agents.py:172)
-        const float reward = move_and_record(a, pre_tk);
-        total += (double)(EXT ? reward * (float)d.reward_count : reward);
+        if (EXT && d.ext_act) {  // the double the reference adds (non-integer values, all-layer sums), x reward_count
+          double r64 = 0.0;
+          move_and_record(a, pre_tk, &r64);
+          total += r64 * (double)d.reward_count;
+        } else {
+          total += (double)move_and_record(a, pre_tk);
+        }
       }
       __syncwarp();
     };

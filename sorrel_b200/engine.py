@@ -54,6 +54,7 @@ class WorldSpec:
     # ---- column rules, facings + beams, all-layer rewards, positional code (examples/cleanup) ----
     kind_rule_prob: list[float] | None = None  # SB_RULE_SPAWN_TO probability per kind
     kind_rule_to: list[int] | None = None  # resulting kind of SPAWN_TO / BECOME_IF / BECOME
+    kind_rule_else: list[int] | None = None  # SPAWN_TO: kind when the draw fails (SB_NO_KIND = unchanged)
     kind_rule_layer: list[int] | None = None  # BECOME_IF: layer of the same column that is tested
     kind_rule_mask: list[int] | None = None  # BECOME_IF: bit j set <=> kind j satisfies the test
     action_facing: list[int] | None = None  # facing 0 N, 1 E, 2 S, 3 W an action sets; -1 unchanged
@@ -176,8 +177,12 @@ def build_desc(spec: WorldSpec, num_envs: int, env_id_base: int, dyn_layers: lis
     for k in range(K):
         d.kind_rule_prob[k] = float(spec.kind_rule_prob[k]) if spec.kind_rule_prob else 0.0
         d.kind_rule_to[k] = int(spec.kind_rule_to[k]) if spec.kind_rule_to else _abi.SB_NO_KIND
+        d.kind_rule_else[k] = int(spec.kind_rule_else[k]) if spec.kind_rule_else else _abi.SB_NO_KIND
+        d.kind_value64[k] = float(spec.kind_value[k])
         d.kind_rule_layer[k] = int(spec.kind_rule_layer[k]) if spec.kind_rule_layer else -1
         d.kind_rule_mask[k] = int(spec.kind_rule_mask[k]) if spec.kind_rule_mask else 0
+    # values that float32 cannot hold (iowa: 1.1, -1.4, ...): total_reward must accumulate the Python floats
+    d.use_value64 = 1 if any(float(np.float32(v)) != float(v) for v in spec.kind_value) else 0
     d.uses_facing = 1 if spec.uses_facing else 0
     for i in range(_abi.SB_MAX_ACTIONS):
         d.action_facing[i] = int(spec.action_facing[i]) if spec.action_facing and i < len(spec.action_facing) else -1

@@ -137,7 +137,7 @@ float hc_agent_act_all_layers(uint8_t* planes, int H, int W, int L, int K, const
     d.dy_packed |= (uint64_t)(uint8_t)dy[i] << (8 * i);
     d.dx_packed |= (uint64_t)(uint8_t)dx[i] << (8 * i);
   }
-  for (int k = 0; k < K; ++k) d.value[k] = value[k];
+  for (int k = 0; k < K; ++k) d.value[k] = value[k], d.value64[k] = (double)value[k];
   uint32_t e = 0;
   float r = sb_agent_act(d, planes, yx, action, true, e, true);
   *err = e;

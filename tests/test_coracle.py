@@ -165,3 +165,45 @@ def test_c_oracle_philox_equals_python_cleanup():
             np.testing.assert_array_equal(ring["states"][row], o.buffers[a].states)
             np.testing.assert_array_equal(ring["rewards"][:, row], o.buffers[a].rewards)
             np.testing.assert_array_equal(ring["actions"][:, row], o.buffers[a].actions)
+
+
+@pytest.mark.parametrize("name", util.iowa_cases())
+def test_c_oracle_reproduces_reference_iowa(name):
+    """The C restatement on the iowa rule set (value states, float rewards, float64 total) vs the reference fixtures."""
+    g = util.load_golden(name)
+    spec = util.iowa_spec_from_golden(g)
+    T, E, A = int(g["T"]), int(g["epochs"]), int(g["A"])
+    co = coracle.COracle(spec, 1, capacity=int(g["capacity"]), rng=coracle.RNG_NUMPY, seed=int(g["seed"]))
+    gi = 0
+    for ep in range(E):
+        co.reset()
+        for t in range(T):
+            co.step(1)
+            np.testing.assert_array_equal(co.grid[0], g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+            gi += 1
+        assert co.total_reward[0] == float(g["total_reward"][ep])
+    ring = co.ring()
+    for a in range(A):
+        np.testing.assert_array_equal(ring["states"][a], g["states"][a])
+        np.testing.assert_array_equal(ring["actions"][:, a], g["actions"][a])
+        np.testing.assert_array_equal(ring["rewards"][:, a], g["rewards"][a])
+        np.testing.assert_array_equal(ring["positions"][:, a], g["positions"][a])
+
+
+def test_c_oracle_philox_equals_python_iowa():
+    spec = R.iowa_spec(10, 13, 3, 2, 0.06)
+    N, T, seed = 7, 25, 31
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=40, threads=2)
+    co.reset()
+    co.step(T)
+    ring = co.ring()
+    for n in range(N):
+        o = R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=40 + n, capacity=T)
+        o.reset()
+        for _ in range(T):
+            o.take_turn()
+        np.testing.assert_array_equal(co.grid[n], o.grid)
+        assert co.total_reward[n] == o.total_reward
+        for a in range(3):
+            np.testing.assert_array_equal(ring["rewards"][:, n * 3 + a], o.buffers[a].rewards)
+            np.testing.assert_array_equal(ring["states"][n * 3 + a], o.buffers[a].states)

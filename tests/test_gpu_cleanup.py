@@ -200,3 +200,66 @@ def test_cleanup_full_size_invariants(cuda_device):
     cand = torch.stack([final, final - 1, final + 1, final - W, final + W], dim=1).clamp(0, H * W - 1)
     match = (codes[cand] == got[:, slot][:, None, :]).all(dim=2).any(dim=1)
     assert match.all()
+
+
+# ------------------------------------------------------------------------------------------------
+# examples/iowa: value states (SPAWN_TO with an else branch), float rewards, float64 total_reward
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", util.iowa_cases())
+@pytest.mark.parametrize("fused", [False, True])
+def test_iowa_golden_replay(name, fused, cuda_device):
+    g = util.load_golden(name)
+    spec = util.iowa_spec_from_golden(g)
+    T, E, A = int(g["T"]), int(g["epochs"]), int(g["A"])
+    oenv = R.OracleEnv(spec, R.NumpyDraws(int(g["seed"])), capacity=int(g["capacity"]), record_tapes=True)
+    eng = _engine(spec, 1, cuda_device)
+    buf = _buffer(spec, 1, int(g["capacity"]), cuda_device)
+    gi = 0
+    for ep in range(E):
+        oenv.tapes.update({"spawn_u": [], "spawn_c": [], "actions": []})
+        oenv.reset()
+        for _ in range(T):
+            oenv.take_turn()
+        spawn_u, spawn_c, actions, placement, _ = _episode_tapes(spec, oenv.dense_tapes(), cuda_device)
+        eng.reset(placement)
+        np.testing.assert_array_equal(eng.agent_yx()[0], g["starts"][ep])
+        if fused:
+            eng.step(T, buffer=buf, actions=actions, spawn_u=spawn_u, spawn_c=spawn_c)
+            gi += T
+            np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi - 1])
+        else:
+            for t in range(T):
+                eng.step(1, buffer=buf, actions=actions[t:t + 1].contiguous(), spawn_u=spawn_u[t:t + 1].contiguous(),
+                         spawn_c=spawn_c[t:t + 1].contiguous())
+                np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+                gi += 1
+        eng.check_errors()
+        assert float(eng.total_reward[0]) == float(g["total_reward"][ep])  # float64 sum of 1.1, -1.4, 0.6, ...
+    for a in range(A):
+        row = buf.row(a)
+        for key in ("states", "actions", "rewards", "dones", "positions"):
+            assert row[key].dtype == g[key].dtype
+            np.testing.assert_array_equal(row[key], g[key][a], err_msg=f"{key} agent {a}")
+
+
+def test_iowa_philox_batch(cuda_device):
+    from oracle import coracle
+
+    spec = R.iowa_spec(20, 20, 2, 2, 0.03)
+    N, T, seed, base = 300, 40, 5, 77
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    buf = _buffer(spec, N, T, cuda_device)
+    eng.reset()
+    eng.step(T // 2, buffer=buf)
+    eng.step(T - T // 2, buffer=buf)
+    eng.check_errors()
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
+    co.reset()
+    co.step(T)
+    np.testing.assert_array_equal(eng.grid_numpy(), co.grid)
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), co.total_reward)
+    ring = co.ring()
+    np.testing.assert_array_equal(buf.states.cpu().numpy(), ring["states"])
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
+    np.testing.assert_array_equal(buf.actions.cpu().numpy(), ring["actions"])
+    assert len(np.unique(ring["rewards"])) >= 7  # walls, fresh decks and the win / loss states of every deck
