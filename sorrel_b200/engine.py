@@ -98,6 +98,10 @@ class WorldSpec:
             kinds = np.unique(self.template[:, :, z])
             if any(self.kind_rule[k] != _abi.SB_RULE_NONE for k in kinds):
                 dyn.add(z)
+            # a static layer that is VISIBLE (iowa's Sand floor) is stored per instance as well: the one-hot fast
+            # path reads stored planes only; an invisible one (treasurehunt's Sand) stays in the shared template
+            elif any(np.any(self.appearance[k] != 0) for k in kinds):
+                dyn.add(z)
         return sorted(dyn)
 
 

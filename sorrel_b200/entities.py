@@ -54,7 +54,7 @@ class Entity:
 
     # identity of a kind-table row: class + the attributes the kernels read
     def kind_key(self):
-        return (self.__class__.__name__, float(self.value), bool(self.passable))
+        return (self.__class__.__name__, str(self.kind), float(self.value), bool(self.passable))
 
 
 class Wall(Entity):

@@ -53,6 +53,19 @@ class ExpireAfter:
 
 
 @dataclass
+class ValueRedraw:
+    """At every sweep the entity's `value` becomes `value_if` with probability `prob`, else `value_else` (one
+    uniform).  Deck.transition -> draw (examples/iowa/entities.py:44-69).  The mutable per-entity value becomes part
+    of the kind id: the kind table gets two more rows for the class (same appearance, the two values), all three
+    chained by SB_RULE_SPAWN_TO with an else branch; a freshly created entity keeps its constructor value until
+    its first sweep, like in the reference."""
+
+    prob: float
+    value_if: float
+    value_else: float
+
+
+@dataclass
 class SpawnBeam:
     """Effect of a non-movement action: place `entity` on every in-map cell of the beam pattern in front of
     the agent (relative to its facing), on the layer above the agent, unless the cell holds one of

@@ -16,7 +16,7 @@ from . import _abi
 from .engine import MOVE_DELTAS, Engine, WorldSpec
 from .entities import Entity
 from .rules import (MOVE_FACING, BecomeIfLayer, BernoulliBecome, BernoulliSpawn, ExpireAfter, SpawnBeam,
-                    beam_pattern)
+                    ValueRedraw, beam_pattern)
 
 
 class Gridworld:
@@ -144,20 +144,35 @@ class Gridworld:
                     note(c)
             elif isinstance(rule, (BernoulliBecome, BecomeIfLayer, ExpireAfter)):
                 note(rule.to)
+            elif isinstance(rule, ValueRedraw):
+                pass  # its value states are added below
             else:
                 raise ValueError(f"{e.kind}: unsupported transition rule {rule!r}")
         spawn_rules = {(r.prob, tuple(c.kind_key() for c in r.choices)) for r in rules.values()
                        if isinstance(r, BernoulliSpawn)}
         if len(spawn_rules) > 1:
             raise ValueError("only one distinct BernoulliSpawn rule per world is supported")
-        for key, r in list(rules.items()):  # aged copies of expiring entities
+        for key, r in list(rules.items()):  # aged copies of expiring entities, value states of redrawn ones
             if isinstance(r, ExpireAfter):
                 for age in range(1, r.sweeps + 1):
                     protos[key[:-1] + (age,)] = protos[key]
+            elif isinstance(r, ValueRedraw):
+                for state, val in ((1, r.value_else), (2, r.value_if)):
+                    twin = copy.copy(protos[key])
+                    twin.value = val
+                    protos[key[:-1] + (state,)] = twin
+
+        default_kind_str = self.default_entity.kind
 
         def order(item):
-            (name, _, _, age) = item[0]
-            return (age > 0, entity_list.index(name) if name in entity_list else len(entity_list), name, age)
+            (name, kind, _, _, age) = item[0]
+            if name in entity_list:
+                idx = entity_list.index(name)
+            elif kind in entity_list and kind != default_kind_str:  # iowa Deck("a") has kind "DeckA"
+                idx = entity_list.index(kind)
+            else:  # e.g. treasurehunt Sand: looks like the default entity, is its own class
+                idx = len(entity_list)
+            return (age > 0, idx, name, kind, age)
 
         keys = [k for k, _ in sorted(protos.items(), key=order)]
         if len(keys) > _abi.SB_MAX_KINDS:
@@ -186,6 +201,7 @@ class Gridworld:
         K = len(keys)
         kind_rule = [_abi.SB_RULE_NONE] * K
         prob, to, layer, mask = [0.0] * K, [_abi.SB_NO_KIND] * K, [-1] * K, [0] * K
+        els = [_abi.SB_NO_KIND] * K
         spawn_rule = None
         for key, r in rules.items():
             i = kid[key]
@@ -201,6 +217,11 @@ class Gridworld:
                     j = kid[key[:-1] + (age,)]
                     kind_rule[j] = _abi.SB_RULE_BECOME
                     to[j] = kid[key[:-1] + (age + 1,)] if age < r.sweeps else kind_of(r.to)
+            elif isinstance(r, ValueRedraw):  # every value state redraws the same way
+                for state in range(3):
+                    j = kid[key[:-1] + (state,)]
+                    kind_rule[j], prob[j] = _abi.SB_RULE_SPAWN_TO, float(r.prob)
+                    to[j], els[j] = kid[key[:-1] + (2,)], kid[key[:-1] + (1,)]
         extended = any(kr not in (_abi.SB_RULE_NONE, _abi.SB_RULE_SPAWN) for kr in kind_rule)
 
         # ---- actions: movement decode, facings, beams ----
@@ -233,7 +254,8 @@ class Gridworld:
             groups.append((kind_of(ent), int(locs[0, 2]), int(count), locs[:, :2].copy()))
         spec = WorldSpec(
             height=self.height, width=self.width, layers=self.layers,
-            kind_names=[protos[k].__class__.__name__ + (f"#{k[3]}" if k[3] else "") for k in keys],
+            kind_names=[(k[1] if k[1] in entity_list and k[0] not in entity_list and k[1] != default_kind_str
+                         else k[0]) + (f"#{k[4]}" if k[4] else "") for k in keys],
             kind_value=[float(protos[k].value) for k in keys],
             kind_passable=[bool(protos[k].passable) for k in keys],
             kind_rule=kind_rule,
@@ -245,6 +267,7 @@ class Gridworld:
             spawn_choices=[kind_of(c) for c in spawn_rule.choices] if spawn_rule else [],
             action_deltas=deltas, obs_transform=int(getattr(observation_spec, "obs_transform", 0)),
             kind_rule_prob=prob if extended else None, kind_rule_to=to if extended else None,
+            kind_rule_else=els if extended else None,
             kind_rule_layer=layer if extended else None, kind_rule_mask=mask if extended else None,
             action_facing=facing if beam is not None else None,
             action_beam_kind=beam_kind if beam is not None else None,

@@ -185,3 +185,34 @@ def test_cleanup_kind_table_from_entity_classes_equals_oracle_spec(shape):
     np.testing.assert_array_equal(got.item_groups[0][3], ref.item_groups[0][3])
     assert got.resolved_dynamic_layers() == [0, 1, 2] and got.obs_size == ref.obs_size
     assert a0.observation_spec.input_size == (1, ref.obs_size)
+
+
+def test_iowa_kind_table_from_entity_classes_equals_oracle_spec():
+    """examples/iowa declared through Entity.transition_rule (BernoulliSpawn + ValueRedraw) compiles to the tables
+    of the oracle's iowa spec (pinned to the reference's fixtures): three value states per deck, float values."""
+    from sorrel_b200 import config as _config
+    from sorrel_b200.examples.iowa.entities import EmptyEntity
+    from sorrel_b200.examples.iowa.env import GamblingEnv
+    from sorrel_b200.examples.iowa.world import GamblingWorld
+
+    cfg = {"experiment": {"epochs": 1, "max_turns": 10}, "model": {"agent_vision_radius": 2, "parameters": {}},
+           "world": {"height": 20, "width": 20, "spawn_prob": 0.01}}
+    world = GamblingWorld(cfg, EmptyEntity(), num_envs=2)
+    env = GamblingEnv.__new__(GamblingEnv)
+    env.config, env.world, env.model_factory = _config.wrap(cfg), world, None
+    env._spawnable, env._item_groups = None, []
+    env.setup_agents()
+    env.populate_environment()
+    a0 = env.agents[0]
+    got = world.build_spec(a0, a0.observation_spec, a0.action_spec, 2, env._spawnable, env._item_groups)
+    ref = util.engine_spec(R.iowa_spec())
+    assert got.kind_names == ref.kind_names
+    assert got.kind_value == [float(x) for x in ref.kind_value]  # 1.1, -1.4, -11.4, 0.6, 0.1, -1.9 as Python floats
+    assert got.kind_passable == ref.kind_passable and got.kind_rule == ref.kind_rule
+    for f in ("kind_rule_prob", "kind_rule_to", "kind_rule_else", "agent_kind", "agent_layer", "default_kind",
+              "fill_kind", "vision", "spawn_prob", "spawn_choices"):
+        assert getattr(got, f) == getattr(ref, f), f
+    for f in ("appearance", "template", "spawnable"):
+        np.testing.assert_array_equal(getattr(got, f), getattr(ref, f), err_msg=f)
+    # Sand is visible on layer 0: storing both layers per instance keeps the one-hot fast path
+    assert got.resolved_dynamic_layers() == [0, 1] == ref.resolved_dynamic_layers()
