@@ -396,9 +396,75 @@ def iowa_cases():
     run_iowa_case("iowa_s6_9x12", 6, 9, 12, 2, 0.08, 60, epochs=2)  # dense decks: every value state is visited
 
 
+def run_tag_case(name, seed, H, W, A, v, T, epochs=1):
+    """examples/tag (base Gridworld, 1 layer) with the reference's RandomModel instead of IQN."""
+    from sorrel.entities.basic_entities import EmptyEntity as BEmpty
+    from sorrel.examples.tag.env import TagEnv
+    from sorrel.worlds import Gridworld
+
+    config = {"experiment": {"epochs": epochs, "max_turns": T, "record_period": 50},
+              "model": {"epsilon_decay": 0.0001}, "agent": {"num_agents": A, "vision_radius": v},
+              "world": {"height": H, "width": W, "layers": 1}}
+    np.random.seed(seed + 1000)  # the It agent is drawn in the constructor (tag/env.py:91-94)
+    world = Gridworld(**config["world"], default_entity=BEmpty())
+    env = TagEnv(world, config)
+    cap = T * epochs
+    ids = {"EmptyEntity": 0, "Wall": 1, "It": 2, "NotIt": 3}
+    initial_flags = np.array([int(ag.it) for ag in env.agents], dtype=np.int64)
+    for ag in env.agents:
+        n_in = int(ag.observation_spec.input_size[0])
+        m = RandomModel((n_in,), 4, cap)
+        m.memory = Buffer(capacity=cap, obs_shape=(n_in,), n_frames=1)
+        m.memory.extra_data["positions"] = np.zeros((cap, 2), dtype=np.int64)
+        ag.model = m
+
+    def grid_ids(w):
+        g = np.zeros(w.map.shape, dtype=np.uint8)
+        for idx, e in np.ndenumerate(w.map):
+            g[idx] = ids[e.kind]
+        return g
+
+    log = DrawLog()
+    grids, starts, totals, flags = [], [], [], []
+    with record(log):
+        set_seed(seed)
+        for ep in range(epochs):
+            env.reset()
+            starts.append([ag.location[:2] for ag in env.agents])
+            grids.append(grid_ids(world))
+            for t in range(T):
+                env.take_turn()
+                grids.append(grid_ids(world))
+                flags.append([int(ag.it) for ag in env.agents])
+            world.is_done = True
+            totals.append(world.total_reward)
+    mems = [ag.model.memory for ag in env.agents]
+    data = dict(
+        world="tag", seed=seed, H=H, W=W, A=A, v=v, T=T, epochs=epochs, capacity=cap, n_frames=1,
+        initial_flags=initial_flags, starts=np.array(starts, dtype=np.int64), grids=np.array(grids, dtype=np.uint8),
+        flags=np.array(flags, dtype=np.int64), total_reward=np.array(totals, dtype=np.float64),
+        states=np.stack([b.states for b in mems]), actions=np.stack([b.actions for b in mems]),
+        rewards=np.stack([b.rewards for b in mems]), dones=np.stack([b.dones for b in mems]),
+        positions=np.stack([b.extra_data["positions"] for b in mems]),
+    )
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **data)
+    fl = np.array(flags)
+    print(f"{name}: total_reward={totals} it-agent changes={(np.diff(fl.argmax(axis=1)) != 0).sum()} "
+          f"-> {os.path.getsize(path)} B")
+
+
+def tag_cases():
+    run_tag_case("tag_s2_a5_11", 2, 11, 11, 5, 4, 60)  # the example's own shape (tag/main.py), 3 x its episode length
+    run_tag_case("tag_s3_a7_8x9", 3, 8, 9, 7, 3, 40, epochs=2)  # crowded: the role changes hands often
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "transformer":
         transformer_case()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "tag":
+        tag_cases()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "iowa":
         iowa_cases()
@@ -431,6 +497,7 @@ def main():
     observe_cases()
     cleanup_cases()
     iowa_cases()
+    tag_cases()
 
 
 if __name__ == "__main__":

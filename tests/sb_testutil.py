@@ -15,7 +15,7 @@ def golden_cases(max_cells: int = 64 * 64, with_large: bool = False):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name.startswith(("observe_", "transformer_", "cleanup_", "iowa_")):
+        if name.startswith(("observe_", "transformer_", "cleanup_", "iowa_", "tag_")):
             continue
         if name.startswith("large") and not with_large:
             continue
@@ -44,6 +44,14 @@ def iowa_spec_from_golden(g) -> R.WorldSpec:
     return R.iowa_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), float(g["p"]))
 
 
+def tag_cases():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "tag_*.npz")))
+
+
+def tag_spec_from_golden(g) -> R.WorldSpec:
+    return R.tag_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), 10, int(np.argmax(g["initial_flags"])))
+
+
 def spec_from_golden(g) -> R.WorldSpec:
     obs = str(g["obs_spec"]) if "obs_spec" in g else "onehot"
     return R.treasurehunt_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), float(g["p"]), obs=obs)
@@ -69,6 +77,8 @@ def engine_spec(o: R.WorldSpec):
         beam_layer=o.beam_layer, beam_offsets=o.beam_offsets, beam_block_mask=o.beam_block_mask,
         reward_all_layers=o.reward_all_layers, reward_count=o.reward_count, initial_facing=o.initial_facing,
         obs_extra=o.obs_extra, item_groups=list(o.item_groups),
+        agent_kind_alt=o.agent_kind_alt, initial_flags=o.initial_flags, touch_swap=o.touch_swap,
+        reward_own=o.reward_own, obs_flag=o.obs_flag,
     )
 
 

@@ -211,3 +211,31 @@ def test_restatement_reproduces_reference_iowa(name):
                          ("dones", b.dones), ("positions", b.positions)):
             assert arr.dtype == g[key].dtype, key
             np.testing.assert_array_equal(arr, g[key][a], err_msg=key)
+
+
+@pytest.mark.parametrize("name", util.tag_cases())
+def test_restatement_reproduces_reference_tag(name):
+    """examples/tag (agent kind flips): the It agent shows as another kind, hands the role to the
+    first adjacent NotIt agent after its move, rewards follow the agent's own state, the flag is appended to the
+    observation and survives reset."""
+    g = util.load_golden(name)
+    spec = util.tag_spec_from_golden(g)
+    T, E = int(g["T"]), int(g["epochs"])
+    env = R.OracleEnv(spec, R.NumpyDraws(int(g["seed"])), capacity=int(g["capacity"]))
+    gi = 0
+    for ep in range(E):
+        env.reset()
+        np.testing.assert_array_equal(env.pos, g["starts"][ep])
+        np.testing.assert_array_equal(env.grid, g["grids"][gi], err_msg="after reset")
+        gi += 1
+        for t in range(T):
+            env.take_turn()
+            np.testing.assert_array_equal(env.grid, g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+            np.testing.assert_array_equal(env.flags, g["flags"][ep * T + t])
+            gi += 1
+        assert env.total_reward == float(g["total_reward"][ep])
+    for a, b in enumerate(env.buffers):
+        for key, arr in (("states", b.states), ("actions", b.actions), ("rewards", b.rewards),
+                         ("dones", b.dones), ("positions", b.positions)):
+            assert arr.dtype == g[key].dtype, key
+            np.testing.assert_array_equal(arr, g[key][a], err_msg=key)
