@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 3
+#define SB_ABI_VERSION 4
 
 #define SB_MAX_KINDS 32    /* entity classes per world (kind ids are uint8 < SB_MAX_KINDS) */
 #define SB_MAX_CHANNELS 32 /* observation channels C = len(entity_list) */
@@ -178,6 +178,18 @@ typedef struct SbWorldDesc {
                                            stores (float)value, world.total_reward accumulates the double */
   int32_t reserved2;
   double kind_value64[SB_MAX_KINDS];
+  /* ---- ABI v4: agents with a binary state shown as a second kind (examples/tag: "It" / "NotIt") ---- */
+  int32_t agent_kind_alt; /* -1, or the kind an agent whose flag is set is drawn with (TagAgent.it setter,
+                             examples/tag/agents.py:44-52); agent_kind is the kind of the others */
+  int32_t touch_swap;     /* 1: after its move a flagged agent hands the flag to the first unflagged agent among the
+                             neighbours (y-1,x), (y,x+1), (y+1,x), (y,x-1) (TagAgent.act tag/agents.py:84-99,
+                             Location.adjacent location.py:144) */
+  int32_t reward_own;     /* 1: reward = kind_value[own kind after the exchange] instead of the target's value
+                             (tag/agents.py:101-105) */
+  int32_t obs_flag;       /* 1: the flag is appended to every observation as one more float (TagAgent.pov :55-65) */
+  int32_t* d_agent_flag;  /* device int32 [N][A]: the flags; read by sb_reset / sb_reset_ex (they survive
+                             Environment.reset like the agent attribute does), written back by sb_step; required iff
+                             agent_kind_alt >= 0 */
 } SbWorldDesc;
 
 /* One group of items placed on distinct cells at reset, before the agents (cleanup/env.py:126-132:
@@ -201,7 +213,7 @@ typedef struct SbItemGroup {
  */
 typedef struct SbBufferDesc {
   int32_t capacity;
-  int32_t obs_size; /* C*S*S + obs_extra floats */
+  int32_t obs_size; /* C*S*S + obs_extra (+ 1 with obs_flag) floats */
   int32_t n_frames;
   int32_t reserved;
   int64_t rows;

@@ -39,6 +39,8 @@ class OrWorld(C.Structure):
         ("obs_extra", C.c_int32), ("extra", C.c_void_p),
         ("n_groups", C.c_int32), ("group_kind", C.c_int32 * 4), ("group_layer", C.c_int32 * 4),
         ("group_count", C.c_int32 * 4), ("group_n_cells", C.c_int32 * 4), ("group_cells", C.c_void_p * 4),
+        ("agent_kind_alt", C.c_int32), ("touch_swap", C.c_int32), ("reward_own", C.c_int32), ("obs_flag", C.c_int32),
+        ("initial_flags", C.c_int32 * 64),
     ]
 
 
@@ -60,7 +62,7 @@ def lib():
         L.or_step.argtypes = [C.c_void_p, C.c_int]
         L.or_step.restype = None
         L.or_set_tick.argtypes = [C.c_void_p, C.c_uint32]
-        for name in ("or_grid", "or_pos", "or_facing", "or_total", "or_states", "or_actions", "or_rewards", "or_dones",
+        for name in ("or_grid", "or_pos", "or_facing", "or_flags", "or_total", "or_states", "or_actions", "or_rewards", "or_dones",
                      "or_positions", "or_tape_u", "or_tape_c", "or_tape_a", "or_tape_placement"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_void_p
@@ -148,6 +150,16 @@ class COracle:
             self._groups.append(flat)
             w.group_kind[gi], w.group_layer[gi], w.group_count[gi] = int(kind), int(layer), int(count)
             w.group_n_cells[gi], w.group_cells[gi] = len(flat), flat.ctypes.data
+        # ---- agents with a second kind (examples/tag) ----
+        w.agent_kind_alt = int(spec.agent_kind_alt)
+        w.touch_swap, w.obs_flag = int(bool(spec.touch_swap)), int(bool(spec.obs_flag))
+        w.reward_own = 1 if spec.reward_own is not None else 0
+        if spec.reward_own is not None:  # the target's value is never read in this mode
+            for k in range(w.K):
+                w.value[k] = float(spec.reward_own[k])
+        if spec.initial_flags is not None:
+            for a, f in enumerate(spec.initial_flags):
+                w.initial_flags[a] = int(f)
         self._w = w
         self.threads = threads
         self.h = self.L.or_create(C.byref(w), self.N, self.capacity, n_frames, rng, seed, env_id_base, threads,
@@ -186,6 +198,10 @@ class COracle:
     @property
     def facing(self):
         return _view(self.L.or_facing(self.h), (self.N, self.spec.num_agents), np.int32)
+
+    @property
+    def flags(self):
+        return _view(self.L.or_flags(self.h), (self.N, self.spec.num_agents), np.int32)
 
     @property
     def total_reward(self):

@@ -193,6 +193,9 @@ typedef struct {
   int32_t n_groups, group_kind[OR_MAX_GROUPS], group_layer[OR_MAX_GROUPS], group_count[OR_MAX_GROUPS],
       group_n_cells[OR_MAX_GROUPS];
   const int32_t* group_cells[OR_MAX_GROUPS]; /* y*W+x, reference order */
+  /* agents with a binary state shown as a second kind (examples/tag): TagAgent.it, tag/agents.py:40-52,76-106 */
+  int32_t agent_kind_alt, touch_swap, reward_own, obs_flag;
+  int32_t initial_flags[64];
 } or_world_t;
 
 typedef struct {
@@ -206,6 +209,7 @@ typedef struct {
   uint8_t* grid; /* [N][H][W][L] */
   int32_t* pos;  /* [N][A] cell index */
   int32_t* facing; /* [N][A] MovingAgent.direction: survives reset */
+  int32_t* flags;  /* [N][A] TagAgent.it: survives reset */
   double* total; /* [N] */
   mt_t* mt;      /* [N] numpy streams (seed = seed + n) */
   /* ring, engine layout */
@@ -243,13 +247,15 @@ or_env_t* or_create(const or_world_t* w, int64_t N, int capacity, int n_frames, 
   e->n_frames = n_frames;
   e->record = record;
   int S = 2 * w->v + 1;
-  e->obs_size = w->C * S * S + w->obs_extra;
+  e->obs_size = w->C * S * S + w->obs_extra + (w->obs_flag ? 1 : 0);
   e->plane_stride = (w->H * w->W + 15) / 16 * 16;
   size_t cells = (size_t)w->H * w->W * w->L, rows = (size_t)N * w->A;
   e->grid = (uint8_t*)malloc(N * cells);
   e->pos = (int32_t*)calloc(rows, sizeof(int32_t));
   e->facing = (int32_t*)calloc(rows, sizeof(int32_t));
   for (size_t r = 0; r < rows; ++r) e->facing[r] = w->initial_facing;
+  e->flags = (int32_t*)calloc(rows, sizeof(int32_t));
+  for (size_t r = 0; r < rows; ++r) e->flags[r] = w->initial_flags[r % (size_t)w->A];
   e->total = (double*)calloc(N, sizeof(double));
   if (rng_mode == OR_RNG_NUMPY) {
     e->mt = (mt_t*)malloc(N * sizeof(mt_t));
@@ -273,6 +279,7 @@ or_env_t* or_create(const or_world_t* w, int64_t N, int capacity, int n_frames, 
 void or_destroy(or_env_t* e) {
   if (!e) return;
   free(e->facing);
+  free(e->flags);
   free(e->grid), free(e->pos), free(e->total), free(e->mt), free(e->states), free(e->actions);
   free(e->rewards), free(e->dones), free(e->positions), free(e->tape_u), free(e->tape_c), free(e->tape_a);
   free(e->tape_pl);
@@ -335,7 +342,9 @@ static void reset_range(or_env_t* e, int64_t n0, int64_t n1) {
     }
     for (int a = 0; a < w->A; ++a) {
       int cell = w->spawnable[picks[a]];
-      g[(size_t)cell * w->L + w->agent_layer] = (uint8_t)w->agent_kind; /* world.add, gridworld.py:67-76 */
+      /* world.add, gridworld.py:67-76; a flagged agent is drawn with its other kind */
+      g[(size_t)cell * w->L + w->agent_layer] =
+          (uint8_t)((w->agent_kind_alt >= 0 && e->flags[n * w->A + a]) ? w->agent_kind_alt : w->agent_kind);
       e->pos[n * w->A + a] = cell;
       e->tape_pl[n * w->A + a] = picks[a];
     }
@@ -445,6 +454,7 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
       int slot = e->capacity > 0 ? (e->idx + t) % e->capacity : 0;
       float* obs = e->capacity > 0 ? e->states + (row * e->capacity + slot) * e->obs_size : obs_local;
       observe(w, g, y, x, obs); /* pov(): state BEFORE the move */
+      if (w->obs_flag) obs[e->obs_size - 1] = (float)e->flags[row]; /* TagAgent.pov, tag/agents.py:55-65 */
       int action;
       if (e->rng_mode == OR_RNG_NUMPY) {
         action = (int)np_randint(mt, (uint32_t)w->n_actions); /* RandomModel, base_model.py:111 */
@@ -474,13 +484,32 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
         } else {
           reward = w->value[*tp]; /* reward = target.value, agent.py:219-220 */
         }
-        if (w->passable[*tp]) { /* Gridworld.move, gridworld.py:95-122 */
-          *tp = (uint8_t)w->agent_kind;
+        if (w->passable[*tp]) { /* Gridworld.move, gridworld.py:95-122: the agent object itself moves */
+          *tp = g[((size_t)y * w->W + x) * w->L + w->agent_layer];
           g[((size_t)y * w->W + x) * w->L + w->agent_layer] = (uint8_t)w->default_kind;
           e->pos[row] = ny * w->W + nx;
           y = ny, x = nx;
         }
       }
+      if (w->touch_swap && e->flags[row]) { /* TagAgent.act, tag/agents.py:84-99; Location.adjacent order */
+        static const int oy[4] = {-1, 0, 1, 0}, ox[4] = {0, 1, 0, -1};
+        for (int k = 0; k < 4; ++k) {
+          int qy = y + oy[k], qx = x + ox[k];
+          if (qy < 0 || qy >= w->H || qx < 0 || qx >= w->W) continue;
+          int b = -1;
+          for (int i = 0; i < w->A; ++i)
+            if (e->pos[n * w->A + i] == qy * w->W + qx) b = i;
+          if (b >= 0 && !e->flags[n * w->A + b]) {
+            e->flags[row] = 0;
+            e->flags[n * w->A + b] = 1;
+            g[((size_t)y * w->W + x) * w->L + w->agent_layer] = (uint8_t)w->agent_kind;
+            g[((size_t)qy * w->W + qx) * w->L + w->agent_layer] = (uint8_t)w->agent_kind_alt;
+            break;
+          }
+        }
+      }
+      if (w->reward_own) /* tag/agents.py:101-105: by the agent's own state after the exchange */
+        reward = w->value[g[((size_t)y * w->W + x) * w->L + w->agent_layer]];
       /* agent.py:172 (cleanup adds the reward a second time in act(): cleanup/agents.py:172) */
       e->total[n] += reward * (double)(w->reward_count > 0 ? w->reward_count : 1);
       if (e->capacity > 0) {          /* Buffer.add, buffers.py:46-63; position AFTER the move */
@@ -565,6 +594,7 @@ void or_add_empty(or_env_t* e) { /* buffers.py:65-69 */
 uint8_t* or_grid(or_env_t* e) { return e->grid; }
 int32_t* or_pos(or_env_t* e) { return e->pos; }
 int32_t* or_facing(or_env_t* e) { return e->facing; }
+int32_t* or_flags(or_env_t* e) { return e->flags; }
 double* or_total(or_env_t* e) { return e->total; }
 float* or_states(or_env_t* e) { return e->states; }
 int64_t* or_actions(or_env_t* e) { return e->actions; }

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-SB_ABI_VERSION = 3
+SB_ABI_VERSION = 4
 SB_MAX_KINDS = 32
 SB_MAX_CHANNELS = 32
 SB_MAX_LAYERS = 8
@@ -90,6 +90,12 @@ class SbWorldDesc(C.Structure):
         ("use_value64", C.c_int32),
         ("reserved2", C.c_int32),
         ("kind_value64", C.c_double * SB_MAX_KINDS),
+        # ---- ABI v4 ----
+        ("agent_kind_alt", C.c_int32),
+        ("touch_swap", C.c_int32),
+        ("reward_own", C.c_int32),
+        ("obs_flag", C.c_int32),
+        ("d_agent_flag", C.c_void_p),
     ]
 
 

@@ -85,7 +85,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   if (w->obs_extra < 0 || w->obs_extra > 256 || (w->obs_extra > 0 && !w->d_obs_extra)) return SB_EINVAL;
   d.obs_extra = w->obs_extra;
   d.extra_tbl = w->d_obs_extra;
-  d.obs_size = d.oh_size + d.obs_extra;
+  d.obs_flag = w->obs_flag ? 1 : 0;
+  d.obs_size = d.oh_size + d.obs_extra + d.obs_flag;
   d.inv_S = (65536u + (uint32_t)d.S - 1u) / (uint32_t)d.S;
   d.fill_kind = w->fill_kind;
   d.agent_kind = w->agent_kind;
@@ -167,7 +168,18 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     }
   }
   d.use_value64 = w->use_value64 ? 1 : 0;
-  d.ext_act = (w->uses_facing || d.reward_all || d.reward_count != 1 || d.use_value64) ? 1 : 0;
+  d.agent_kind_alt = -1;
+  if (w->agent_kind_alt >= 0) {
+    if (!kind_ok(w->agent_kind_alt) || w->agent_kind_alt == w->agent_kind || !w->d_agent_flag) return SB_EINVAL;
+    d.agent_kind_alt = w->agent_kind_alt;
+    d.agent_flag = w->d_agent_flag;
+  } else if (w->touch_swap || w->obs_flag) {
+    return SB_EINVAL;
+  }
+  d.touch_swap = w->touch_swap ? 1 : 0;
+  d.reward_own = w->reward_own ? 1 : 0;
+  d.ext_act = (w->uses_facing || d.reward_all || d.reward_count != 1 || d.use_value64 || d.agent_kind_alt >= 0 ||
+               d.reward_own) ? 1 : 0;
   if (n_spawn_kinds > 0 && d.n_choices == 0 && d.p > 0.0) return SB_EINVAL;
   for (int i = 0; i < d.n_choices; ++i) {
     if (!kind_ok(w->spawn_choice_kinds[i])) return SB_EINVAL;
@@ -177,7 +189,7 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     d.dy_packed |= (uint64_t)(uint8_t)w->action_dy[i] << (8 * i);
     d.dx_packed |= (uint64_t)(uint8_t)w->action_dx[i] << (8 * i);
   }
-  const bool ext = d.ext_rules || d.ext_act || d.obs_extra > 0;  // only the generic / replay variants implement these
+  const bool ext = d.ext_rules || d.ext_act || d.obs_extra > 0 || d.obs_flag;  // only the generic / replay variants implement these
   d.simd_sweep = (d.single_spawn_kind >= 0 && d.hi8 + 1u <= 128u && !ext) ? 1 : 0;
   {
     uint32_t n2 = 1;
@@ -275,10 +287,13 @@ __global__ void __launch_bounds__(SB_THREADS)
         for (;;) {
           SbU4 w = sb_philox(envid, tick, j++, SB_DOM_RESET, (uint32_t)seed, (uint32_t)(seed >> 32));
           cell = spawnable[sb_bounded(w.x, w.y, (uint32_t)n_spawnable)];
-          if (plane[cell] != (uint8_t)d.agent_kind) break;
+          if (plane[cell] != (uint8_t)d.agent_kind && (d.agent_kind_alt < 0 || plane[cell] != (uint8_t)d.agent_kind_alt))
+            break;
         }
       }
-      plane[cell] = (uint8_t)d.agent_kind;  // world.add(loc, agent) overwrites, gridworld.py:67-76
+      // world.add(loc, agent) overwrites, gridworld.py:67-76; a flagged agent is drawn with its other kind
+      const bool flagged = d.agent_kind_alt >= 0 && d.agent_flag[(size_t)env * d.A + a] != 0;
+      plane[cell] = (uint8_t)(flagged ? d.agent_kind_alt : d.agent_kind);
       agent_pos[(size_t)env * d.A + a] = cell;
     }
     total_reward[env] = 0.0;  // create_world, gridworld.py:65

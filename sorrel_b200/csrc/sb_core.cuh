@@ -60,6 +60,8 @@ struct SbDev {
   uint32_t draw_mask; // kinds whose rule consumes a uniform (SPAWN, SPAWN_TO)
   uint32_t det_mask;  // kinds with a deterministic rule (BECOME_IF, BECOME)
   uint8_t rule[SB_MAX_KINDS], rule_to[SB_MAX_KINDS], rule_else[SB_MAX_KINDS];
+  int32_t agent_kind_alt, touch_swap, reward_own, obs_flag;  // agents with a second kind (tag)
+  int32_t* agent_flag;           // device [N][A]
   int32_t use_value64;           // rewards are value64 (Python floats that float32 cannot hold)
   double value64[SB_MAX_KINDS];  // total_reward accumulates these; the ring stores (float)value64
   int32_t rule_plane_off[SB_MAX_KINDS];  // BECOME_IF: byte offset of the tested plane
@@ -253,8 +255,10 @@ SB_HD int sb_target_cell(const SbDev& d, uint32_t yx, int action) {
 // `pre_tk` >= 0: kind of the target cell already loaded by the caller (same cell, same state).
 // `reward64` != nullptr (worlds with use_value64 / all-layer rewards): receives the reward as the double the
 // reference adds to world.total_reward; the returned float is its float32 rounding (Buffer.rewards).
+// `own_kind` >= 0: the byte the moving agent is drawn with (worlds where an agent has two kinds); else agent_kind.
 SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action, bool writer,
-                         uint32_t& err, bool all_layers = false, int pre_tk = -1, double* reward64 = nullptr) {
+                         uint32_t& err, bool all_layers = false, int pre_tk = -1, double* reward64 = nullptr,
+                         int own_kind = -1) {
   int y = (int)(*yx >> 16), x = (int)(*yx & 0xFFFFu);
   int dy = 0, dx = 0;
   if ((unsigned)action < (unsigned)d.n_actions) {
@@ -291,12 +295,34 @@ SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action
   }
   if ((d.passable_mask >> tk) & 1u) {
     if (writer) {
-      plane[ny * d.W + nx] = (uint8_t)d.agent_kind;  // target entity discarded, agent placed
+      plane[ny * d.W + nx] = (uint8_t)(own_kind >= 0 ? own_kind : d.agent_kind);  // target discarded, agent placed
       plane[y * d.W + x] = (uint8_t)d.default_kind;  // vacated cell <- default entity
     }
     *yx = ((uint32_t)ny << 16) | (uint32_t)nx;
   }
   return reward;
+}
+
+// TagAgent.act (examples/tag/agents.py:84-105) after the move: an agent drawn with agent_kind_alt ("It") hands the role
+// to the first neighbour drawn with agent_kind ("NotIt") in the order of Location.adjacent (location.py:144): up,
+// right, down, left.  The state lives in the grid byte of the agents.  Returns the agent's kind afterwards.
+SB_HD uint32_t sb_touch_swap(const SbDev& d, uint8_t* genv, uint32_t yx) {
+  uint8_t* plane = genv + d.agent_plane * d.plane_stride;
+  const int y = (int)(yx >> 16), x = (int)(yx & 0xFFFFu);
+  const int cur = y * d.W + x;
+  if (plane[cur] == (uint8_t)d.agent_kind_alt) {
+    const int oy[4] = {-1, 0, 1, 0}, ox[4] = {0, 1, 0, -1};
+    for (int k = 0; k < 4; ++k) {
+      const int qy = y + oy[k], qx = x + ox[k];
+      if ((unsigned)qy >= (unsigned)d.H || (unsigned)qx >= (unsigned)d.W) continue;
+      if (plane[qy * d.W + qx] == (uint8_t)d.agent_kind) {
+        plane[cur] = (uint8_t)d.agent_kind;
+        plane[qy * d.W + qx] = (uint8_t)d.agent_kind_alt;
+        break;
+      }
+    }
+  }
+  return plane[cur];
 }
 
 // ------------------------------------------------------------------------------------------------

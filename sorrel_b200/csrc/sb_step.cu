@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
       const float* src = d.extra_tbl + (size_t)(y * d.W + x) * d.obs_extra;
       for (int e = lane; e < d.obs_extra; e += LANES) dst[d.oh_size + e] = __ldg(src + e);
     }
+    if (d.obs_flag && valid && lane == 0)  // TagAgent.pov: [self.it]
+      dst[d.oh_size + d.obs_extra] = genv[d.agent_plane * d.plane_stride + y * d.W + x] == (uint8_t)d.agent_kind_alt
+                                         ? 1.0f : 0.0f;
     if (++a == d.A) {
       a = 0;
       ++env;
@@ -632,13 +635,31 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           if (dsts[1]) dsts[1][d.oh_size + e] = vf;
         }
       }
+      if (EXT && d.obs_flag && active && lane == 0) {  // TagAgent.pov: [self.it] appended (tag/agents.py:55-65)
+        const float vf = genv[d.agent_plane * d.plane_stride + y * d.W + x] == (uint8_t)d.agent_kind_alt ? 1.0f : 0.0f;
+        if (dsts[0]) dsts[0][d.oh_size + d.obs_extra] = vf;
+        if (dsts[1]) dsts[1][d.oh_size + d.obs_extra] = vf;
+      }
     };
 
     // one agent's move by ONE lane: MovingAgent.act + Gridworld.move + the scalar part of Buffer.add
     auto move_and_record = [&](int a, int pre_tk, double* reward64 = nullptr) -> float {
       uint32_t yx = spos[a];
       const int action = sact[a];
-      const float reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all, pre_tk, reward64);
+      float reward;
+      if (EXT && d.agent_kind_alt >= 0) {
+        // the agent moves as the kind it is drawn with; then the role hand-over and the own-state reward (tag)
+        const int own = genv[d.agent_plane * d.plane_stride + (int)(yx >> 16) * d.W + (int)(yx & 0xFFFFu)];
+        reward = sb_agent_act(d, genv, &yx, action, true, err, d.reward_all, pre_tk, reward64, own);
+        uint32_t mine = (uint32_t)own;
+        if (d.touch_swap) mine = sb_touch_swap(d, genv, yx);
+        if (d.reward_own) {
+          reward = (float)d.value64[mine];
+          if (reward64) *reward64 = d.value64[mine];
+        }
+      } else {
+        reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all, pre_tk, reward64);
+      }
       spos[a] = yx;
       const size_t row = row0 + a;
       if (p.has_buf) {
@@ -792,6 +813,12 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
     }
     if (EXT && p.a.d_agent_facing)
       for (int a = lane; a < d.A; a += LPE) p.a.d_agent_facing[(size_t)env * d.A + a] = sfacing[a];
+    if (EXT && d.agent_kind_alt >= 0)  // the flags live in the grid while stepping; persist them for the next reset
+      for (int a = lane; a < d.A; a += LPE) {
+        const uint32_t yx = spos[a];
+        d.agent_flag[(size_t)env * d.A + a] =
+            genv[d.agent_plane * d.plane_stride + (int)(yx >> 16) * d.W + (int)(yx & 0xFFFFu)] == (uint8_t)d.agent_kind_alt;
+      }
     if (lane == 0) p.total_reward[env] = total;
   }
   if (active && err && p.a.d_error) atomicOr(p.a.d_error, err);

@@ -67,6 +67,12 @@ class WorldSpec:
     initial_facing: int = 2  # MovingAgent.direction default (agents/agent.py:185)
     obs_extra: np.ndarray | None = None  # [H, W, E] appended to the flattened crop (positional code)
     item_groups: list = field(default_factory=list)  # (kind, layer, count, cells[n, 2]) placed at reset, in order
+    # ---- agents with a binary state shown as a second kind (examples/tag) ----
+    agent_kind_alt: int = -1
+    initial_flags: np.ndarray | None = None  # [A] 0/1 at construction (every instance starts with the same flags)
+    touch_swap: bool = False
+    reward_own: list[float] | None = None  # reward by the agent's own kind after the exchange
+    obs_flag: bool = False
 
     @property
     def channels(self) -> int:
@@ -82,7 +88,8 @@ class WorldSpec:
 
     @property
     def obs_size(self) -> int:
-        return self.onehot_size + (0 if self.obs_extra is None else int(self.obs_extra.shape[2]))
+        return self.onehot_size + (0 if self.obs_extra is None else int(self.obs_extra.shape[2])) + \
+            (1 if self.obs_flag else 0)
 
     @property
     def uses_facing(self) -> bool:
@@ -144,7 +151,7 @@ def _ptr(t: torch.Tensor | None) -> int | None:
 
 def build_desc(spec: WorldSpec, num_envs: int, env_id_base: int, dyn_layers: list[int], env_stride: int,
                h_appearance: np.ndarray, d_appearance: int, d_template: int, static_layers_invisible: bool,
-               obs_extra_width: int = 0, d_obs_extra: int = 0) -> tuple[SbWorldDesc, bool]:
+               obs_extra_width: int = 0, d_obs_extra: int = 0, d_agent_flag: int = 0) -> tuple[SbWorldDesc, bool]:
     """Fill `SbWorldDesc` from a `WorldSpec` (pure host code: the pointers are passed as integers, so the
     descriptor logic and `sb_validate` are testable without a GPU).  Returns (descriptor, sparse mode available)."""
     H, W, L = spec.height, spec.width, spec.layers
@@ -183,10 +190,17 @@ def build_desc(spec: WorldSpec, num_envs: int, env_id_base: int, dyn_layers: lis
         d.kind_rule_to[k] = int(spec.kind_rule_to[k]) if spec.kind_rule_to else _abi.SB_NO_KIND
         d.kind_rule_else[k] = int(spec.kind_rule_else[k]) if spec.kind_rule_else else _abi.SB_NO_KIND
         d.kind_value64[k] = float(spec.kind_value[k])
+        if spec.reward_own is not None:  # the target's value is never read in this mode: the table holds own rewards
+            d.kind_value[k] = d.kind_value64[k] = float(spec.reward_own[k])
         d.kind_rule_layer[k] = int(spec.kind_rule_layer[k]) if spec.kind_rule_layer else -1
         d.kind_rule_mask[k] = int(spec.kind_rule_mask[k]) if spec.kind_rule_mask else 0
     # values that float32 cannot hold (iowa: 1.1, -1.4, ...): total_reward must accumulate the Python floats
     d.use_value64 = 1 if any(float(np.float32(v)) != float(v) for v in spec.kind_value) else 0
+    d.agent_kind_alt = int(spec.agent_kind_alt)
+    d.touch_swap = 1 if spec.touch_swap else 0
+    d.reward_own = 1 if spec.reward_own is not None else 0
+    d.obs_flag = 1 if spec.obs_flag else 0
+    d.d_agent_flag = int(d_agent_flag) if d_agent_flag else None
     d.uses_facing = 1 if spec.uses_facing else 0
     for i in range(_abi.SB_MAX_ACTIONS):
         d.action_facing[i] = int(spec.action_facing[i]) if spec.action_facing and i < len(spec.action_facing) else -1
@@ -256,6 +270,11 @@ class Engine:
         # MovingAgent.direction of every agent: set at construction, NOT reset by Environment.reset
         self.agent_facing = torch.full((self.N, self.A), int(spec.initial_facing), dtype=torch.int32,
                                        device=self.device) if spec.uses_facing else None
+        # flags of agents with a second kind (tag's `it`): like the agent attribute they survive reset
+        self.agent_flag = None
+        if spec.agent_kind_alt >= 0:
+            f0 = np.zeros(self.A, dtype=np.int32) if spec.initial_flags is None else np.asarray(spec.initial_flags, dtype=np.int32)
+            self.agent_flag = torch.from_numpy(np.broadcast_to(f0, (self.N, self.A)).copy()).to(self.device)
         self.d_obs_extra = None
         if spec.obs_extra is not None:  # f64 -> f32 exactly like `Buffer.states[idx] = obs` (buffers.py:56)
             ex = np.ascontiguousarray(spec.obs_extra, dtype=np.float64).reshape(H * W, -1).astype(np.float32)
@@ -270,7 +289,8 @@ class Engine:
             spec, self.N, env_id_base, self.dyn_layers, self.env_stride, self.h_appearance,
             self.d_appearance.data_ptr(), self.d_template.data_ptr(), invisible,
             0 if self.d_obs_extra is None else int(self.d_obs_extra.shape[1]),
-            0 if self.d_obs_extra is None else self.d_obs_extra.data_ptr())
+            0 if self.d_obs_extra is None else self.d_obs_extra.data_ptr(),
+            0 if self.agent_flag is None else self.agent_flag.data_ptr())
         d = self.desc
         self.desc = d
         check(self.lib.sb_validate(C.byref(d)), "world description")
@@ -385,12 +405,18 @@ class Engine:
         a.d_agent_facing = _ptr(self.agent_facing)
 
     def observe(self, out: torch.Tensor | None = None) -> torch.Tensor:
-        """ObservationSpec.observe for every (instance, agent): float32 [N, A, C, S, S]."""
+        """ObservationSpec.observe for every (instance, agent): float32 [N, A, C, S, S], or [N, A, obs_size] when
+        rows carry more than the crop (positional code, state flag)."""
         s = self.spec
         if out is None:
-            shape = (self.N, self.A, s.channels, s.obs_side, s.obs_side) if s.obs_extra is None \
-                else (self.N, self.A, s.obs_size)  # crop flattened + positional code
+            shape = (self.N, self.A, s.channels, s.obs_side, s.obs_side) if s.obs_size == s.onehot_size \
+                else (self.N, self.A, s.obs_size)
             out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        if out.numel() != self.N * self.A * s.obs_size or out.dtype != torch.float32 or not out.is_contiguous() \
+                or out.device != self.grid.device:
+            raise ValueError(f"observe(out=...): expected a contiguous float32 tensor of "
+                             f"{self.N * self.A * s.obs_size} elements on {self.grid.device}, got "
+                             f"{tuple(out.shape)} {out.dtype} on {out.device}")
         check(self.lib.sb_observe(C.byref(self.desc), self.grid.data_ptr(), self.agent_pos.data_ptr(),
                                   out.data_ptr(), self._stream()), "sb_observe")
         return out

@@ -143,4 +143,13 @@ float hc_agent_act_all_layers(uint8_t* planes, int H, int W, int L, int K, const
   *err = e;
   return r;
 }
+
+// role hand-over of examples/tag on a 1-plane image; returns the acting agent's kind afterwards
+int hc_touch_swap(uint8_t* plane, int H, int W, int y, int x, int agent_kind, int agent_kind_alt) {
+  SbDev d;
+  memset(&d, 0, sizeof d);
+  d.H = H, d.W = W, d.plane_stride = (H * W + 15) / 16 * 16, d.agent_plane = 0;
+  d.agent_kind = agent_kind, d.agent_kind_alt = agent_kind_alt;
+  return (int)sb_touch_swap(d, plane, ((uint32_t)y << 16) | (uint32_t)x);
+}
 }

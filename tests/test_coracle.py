@@ -207,3 +207,28 @@ def test_c_oracle_philox_equals_python_iowa():
         for a in range(3):
             np.testing.assert_array_equal(ring["rewards"][:, n * 3 + a], o.buffers[a].rewards)
             np.testing.assert_array_equal(ring["states"][n * 3 + a], o.buffers[a].states)
+
+
+@pytest.mark.parametrize("name", util.tag_cases())
+def test_c_oracle_reproduces_reference_tag(name):
+    g = util.load_golden(name)
+    spec = util.tag_spec_from_golden(g)
+    T, E, A = int(g["T"]), int(g["epochs"]), int(g["A"])
+    co = coracle.COracle(spec, 1, capacity=int(g["capacity"]), rng=coracle.RNG_NUMPY, seed=int(g["seed"]))
+    gi = 0
+    for ep in range(E):
+        co.reset()
+        np.testing.assert_array_equal(co.grid[0], g["grids"][gi], err_msg="after reset")
+        gi += 1
+        for t in range(T):
+            co.step(1)
+            np.testing.assert_array_equal(co.grid[0], g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+            np.testing.assert_array_equal(co.flags[0], g["flags"][ep * T + t])
+            gi += 1
+        assert co.total_reward[0] == float(g["total_reward"][ep])
+    ring = co.ring()
+    for a in range(A):
+        np.testing.assert_array_equal(ring["states"][a], g["states"][a])
+        np.testing.assert_array_equal(ring["actions"][:, a], g["actions"][a])
+        np.testing.assert_array_equal(ring["rewards"][:, a], g["rewards"][a])
+        np.testing.assert_array_equal(ring["positions"][:, a], g["positions"][a])

@@ -263,3 +263,72 @@ def test_iowa_philox_batch(cuda_device):
     np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
     np.testing.assert_array_equal(buf.actions.cpu().numpy(), ring["actions"])
     assert len(np.unique(ring["rewards"])) >= 7  # walls, fresh decks and the win / loss states of every deck
+
+
+# ------------------------------------------------------------------------------------------------
+# examples/tag: agents with a second kind ("It"), role hand-over to a neighbour, own-state rewards, flag in the row
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", util.tag_cases())
+@pytest.mark.parametrize("fused", [False, True])
+def test_tag_golden_replay(name, fused, cuda_device):
+    g = util.load_golden(name)
+    spec = util.tag_spec_from_golden(g)
+    T, E, A = int(g["T"]), int(g["epochs"]), int(g["A"])
+    oenv = R.OracleEnv(spec, R.NumpyDraws(int(g["seed"])), capacity=int(g["capacity"]), record_tapes=True)
+    eng = _engine(spec, 1, cuda_device)
+    buf = _buffer(spec, 1, int(g["capacity"]), cuda_device)
+    gi = 0
+    for ep in range(E):
+        oenv.tapes.update({"spawn_u": [], "spawn_c": [], "actions": []})
+        oenv.reset()
+        for _ in range(T):
+            oenv.take_turn()
+        spawn_u, spawn_c, actions, placement, _ = _episode_tapes(spec, oenv.dense_tapes(), cuda_device)
+        eng.reset(placement)  # the flags of the previous episode decide who is drawn as "It"
+        np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi], err_msg="after reset")
+        gi += 1
+        if fused:
+            eng.step(T, buffer=buf, actions=actions, spawn_u=spawn_u, spawn_c=spawn_c)
+            gi += T
+            np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi - 1])
+        else:
+            for t in range(T):
+                eng.step(1, buffer=buf, actions=actions[t:t + 1].contiguous(), spawn_u=spawn_u[t:t + 1].contiguous(),
+                         spawn_c=spawn_c[t:t + 1].contiguous())
+                np.testing.assert_array_equal(eng.grid_numpy()[0], g["grids"][gi], err_msg=f"epoch {ep} turn {t}")
+                np.testing.assert_array_equal(eng.agent_flag.cpu().numpy()[0], g["flags"][ep * T + t])
+                gi += 1
+        eng.check_errors()
+        assert float(eng.total_reward[0]) == float(g["total_reward"][ep])
+        np.testing.assert_array_equal(eng.agent_flag.cpu().numpy()[0], g["flags"][(ep + 1) * T - 1])
+    for a in range(A):
+        row = buf.row(a)
+        for key in ("states", "actions", "rewards", "dones", "positions"):
+            assert row[key].dtype == g[key].dtype
+            np.testing.assert_array_equal(row[key], g[key][a], err_msg=f"{key} agent {a}")
+
+
+def test_tag_philox_batch(cuda_device):
+    from oracle import coracle
+
+    spec = R.tag_spec(9, 10, 6, 3, 10, it_agent=2)
+    N, T, seed, base = 200, 30, 13, 9
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    buf = _buffer(spec, N, 2 * T, cuda_device)
+    co = coracle.COracle(spec, N, capacity=2 * T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
+    for ep in range(2):  # the second episode starts from the flags the first one left
+        eng.reset()
+        eng.step(T, buffer=buf)
+        co.reset()
+        co.step(T)
+        eng.check_errors()
+        np.testing.assert_array_equal(eng.grid_numpy(), co.grid)
+        np.testing.assert_array_equal(eng.agent_flag.cpu().numpy(), co.flags)
+        np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), co.total_reward)
+    ring = co.ring()
+    np.testing.assert_array_equal(buf.states.cpu().numpy(), ring["states"])
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
+    assert (eng.agent_flag.sum(dim=1) == 1).all()  # exactly one "It" per instance, always
+    obs = eng.observe()
+    assert tuple(obs.shape) == (N, 6, spec.obs_size)
+    np.testing.assert_array_equal(obs[:, :, -1].cpu().numpy(), co.flags.astype(np.float32))

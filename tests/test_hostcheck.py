@@ -225,3 +225,28 @@ def test_agent_act_all_layer_reward(hc):
             assert after[ny, nx] == 5 and after[y, x] == 0
         else:
             assert after[y, x] == 5
+
+
+def test_touch_swap_order_and_conditions(hc):
+    """TagAgent.act (tag/agents.py:84-99): only an "It" agent hands over, to the FIRST "NotIt" neighbour in the order
+    up, right, down, left (Location.adjacent, location.py:144); nothing else changes."""
+    hc.hc_touch_swap.argtypes = [C.c_void_p] + [C.c_int] * 6
+    H, W, IT, NOT = 6, 7, 2, 3
+    rng = np.random.RandomState(4)
+    stride = (H * W + 15) // 16 * 16
+    for _ in range(600):
+        plane = np.full(stride, 0xFF, dtype=np.uint8)
+        cells = rng.choice([0, 1, NOT, IT], size=(H, W), p=[0.45, 0.1, 0.35, 0.1]).astype(np.uint8)
+        y, x = int(rng.randint(0, H)), int(rng.randint(0, W))
+        cells[y, x] = IT if rng.rand() < 0.7 else NOT
+        plane[: H * W] = cells.reshape(-1)
+        want = cells.copy()
+        if cells[y, x] == IT:
+            for oy, ox in ((-1, 0), (0, 1), (1, 0), (0, -1)):
+                qy, qx = y + oy, x + ox
+                if 0 <= qy < H and 0 <= qx < W and cells[qy, qx] == NOT:
+                    want[y, x], want[qy, qx] = NOT, IT
+                    break
+        got = hc.hc_touch_swap(plane.ctypes.data, H, W, y, x, NOT, IT)
+        np.testing.assert_array_equal(plane[: H * W].reshape(H, W), want)
+        assert got == want[y, x]
