@@ -77,3 +77,18 @@ class MovingAgent(Agent):
     def action_effects(self, world) -> dict:
         """Non-movement actions: action name -> effect from sorrel_b200.rules (e.g. SpawnBeam)."""
         return {}
+
+    # -- agents with a binary state that changes how they look (examples/tag: `it`) -------------------------
+    #: (kind string without the flag, kind string with it), e.g. ("NotIt", "It"); None = one kind
+    state_kinds = None
+    #: after its move a flagged agent hands the flag to the first unflagged neighbour (TagAgent.act)
+    touch_swap = False
+    #: {kind string: reward}: reward by the agent's own state after the exchange instead of the target's value
+    reward_by_state = None
+    #: the flag is appended to the observation (TagAgent.pov)
+    observe_flag = False
+
+    @property
+    def flag(self) -> bool:
+        """Initial value of the flag for this agent slot (every instance starts with the same flags)."""
+        return False

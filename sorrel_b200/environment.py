@@ -76,10 +76,11 @@ class Environment:
         a0 = self.agents[0]
         for k, ag in enumerate(self.agents):
             ag.index, ag.env = k, self
-            if type(ag) is not type(a0) or ag.kind_key() != a0.kind_key():
-                raise ValueError("all agent slots must be of one Agent class (one kind-table row)")
+            if type(ag) is not type(a0) or (ag.value, ag.passable) != (a0.value, a0.passable):
+                raise ValueError("all agent slots must be of one Agent class (one kind-table row per state)")
         A = len(self.agents)
-        eng = self.world.compile(a0, a0.observation_spec, a0.action_spec, A, self._spawnable, self._item_groups)
+        flags = [int(bool(ag.flag)) for ag in self.agents] if getattr(a0, "state_kinds", None) else None
+        eng = self.world.compile(a0, a0.observation_spec, a0.action_spec, A, self._spawnable, self._item_groups, flags)
         model = a0.model
         cap = int(getattr(model, "memory_size", 0) or self.config.get("engine", {}).get("buffer_capacity", 1024))
         n_frames = int(getattr(model, "n_frames", 1))

@@ -101,7 +101,7 @@ class Gridworld:
     # compilation: object template -> kind table + uint8 template -> device instances
     # ------------------------------------------------------------------------------------------
     def build_spec(self, agent_proto: Entity, observation_spec, action_spec, num_agents: int,
-                   spawnable, item_groups=()) -> WorldSpec:
+                   spawnable, item_groups=(), initial_flags=None) -> WorldSpec:
         """Pure host logic (no CUDA): derive the kind table from the entity prototypes.
 
         A kind-table row is (class, value, passable, age); `age` > 0 only for classes whose rule is
@@ -120,6 +120,12 @@ class Gridworld:
         note(self.default_entity)
         for _, e in np.ndenumerate(self.map):
             note(e)
+        agent_alt = None
+        if getattr(agent_proto, "state_kinds", None):  # two kinds for one agent class (tag: "NotIt" / "It")
+            plain, flagged = agent_proto.state_kinds
+            agent_proto, agent_alt = copy.copy(agent_proto), copy.copy(agent_proto)
+            agent_proto.kind, agent_alt.kind = plain, flagged
+            note(agent_alt)
         note(agent_proto)
         for ent, _, _ in item_groups:
             note(ent)
@@ -132,7 +138,7 @@ class Gridworld:
         rules: dict[tuple, object] = {}
         while pending:
             e = pending.pop()
-            if e is agent_proto:
+            if e is agent_proto or e is agent_alt:
                 continue  # `not isinstance(x, Agent)`: agents are not swept (environment.py:90)
             rule = e.transition_rule(self)
             if rule is None:
@@ -278,12 +284,20 @@ class Gridworld:
             reward_all_layers=reward_all, reward_count=reward_count,
             initial_facing=int(getattr(agent_proto, "direction", 2)),
             obs_extra=extra, item_groups=groups,
+            agent_kind_alt=kind_of(agent_alt) if agent_alt is not None else -1,
+            initial_flags=None if agent_alt is None else np.asarray(
+                initial_flags if initial_flags is not None else [0] * int(num_agents), dtype=np.int64),
+            touch_swap=bool(agent_alt is not None and getattr(agent_proto, "touch_swap", False)),
+            reward_own=None if not getattr(agent_proto, "reward_by_state", None) else
+            [float(agent_proto.reward_by_state.get(protos[k].kind, 0.0)) for k in keys],
+            obs_flag=bool(agent_alt is not None and getattr(agent_proto, "observe_flag", False)),
         )
         return spec
 
     def compile(self, agent_proto: Entity, observation_spec, action_spec, num_agents: int, spawnable,
-                item_groups=()) -> Engine:
-        self.spec = self.build_spec(agent_proto, observation_spec, action_spec, num_agents, spawnable, item_groups)
+                item_groups=(), initial_flags=None) -> Engine:
+        self.spec = self.build_spec(agent_proto, observation_spec, action_spec, num_agents, spawnable, item_groups,
+                                    initial_flags)
         self.engine = Engine(self.spec, self.num_envs, device=self.device, env_id_base=self.env_id_base,
                              seed=self.seed)
         return self.engine

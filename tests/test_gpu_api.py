@@ -307,3 +307,68 @@ def test_iowa_example_env_fused_matches_oracle(cuda_device):
             np.testing.assert_array_equal(mem.rewards[:, n].cpu().numpy(), o.buffers[a].rewards)
             seen.update(np.unique(o.buffers[a].rewards).tolist())
     assert len(seen) >= 5  # several deck value states were collected
+
+
+def test_tag_example_env_matches_oracle(cuda_device):
+    """TagEnv (examples/tag) on the base Gridworld through the reference-shaped API, fused and split-phase."""
+    from sorrel_b200.entities import EmptyEntity
+    from sorrel_b200.examples.tag.env import TagEnv
+    from sorrel_b200.models import BaseModel
+    from sorrel_b200.worlds import Gridworld
+
+    cfg = {"experiment": {"epochs": 1, "max_turns": 20}, "model": {"memory_size": 32, "n_frames": 1},
+           "agent": {"num_agents": 5, "vision_radius": 3, "it_agent": 1}, "world": {"height": 9, "width": 10, "layers": 1}}
+    N, seed, T = 16, 44, 20
+    spec = R.tag_spec(9, 10, 5, 3, 10, it_agent=1)
+
+    def oracle(n, draws):
+        o = R.OracleEnv(spec, draws, env_id=n, capacity=32)
+        if hasattr(draws, "env"):
+            draws.env = o
+        o.reset()
+        for _ in range(T):
+            o.take_turn()
+        return o
+
+    # fused: in-kernel uniform policy
+    env = TagEnv(Gridworld(**cfg["world"], default_entity=EmptyEntity(), num_envs=N, device="cuda:0", seed=seed), cfg)
+    env.take_turns(T)
+    env.engine.check_errors()
+    grids = env.engine.grid_numpy()
+    for n in range(0, N, 3):
+        o = oracle(n, R.PhiloxDraws(seed))
+        np.testing.assert_array_equal(grids[n], o.grid)
+        np.testing.assert_array_equal(env.engine.agent_flag.cpu().numpy()[n], o.flags)
+        assert float(env.world.total_reward[n]) == o.total_reward
+        for a in range(5):
+            np.testing.assert_array_equal(env.agents[a].model.memory.states[n].cpu().numpy(), o.buffers[a].states)
+
+    # split-phase: a host policy that looks at the observation (its last entry is the agent's own `it` flag)
+    class FlagPolicy(BaseModel):
+        def take_action(self, state):
+            return ((state != 0).sum(dim=1) + 2 * state[:, -1].to(torch.int64)).to(torch.int32) % 4
+
+    class Draws(R.PhiloxDraws):
+        env = None
+
+        def action(self, n_actions, env_id, tick, agent):
+            o = self.env
+            y, x = o.pos[agent]
+            obs = np.concatenate((R.observe(o.spec, o.grid, y, x).reshape(-1), [float(o.flags[agent])]))
+            return int(((obs != 0).sum() + 2 * int(o.flags[agent])) % 4)
+
+    env = TagEnv(Gridworld(**cfg["world"], default_entity=EmptyEntity(), num_envs=N, device="cuda:0", seed=seed), cfg,
+                 model_factory=lambda inp, na: FlagPolicy(inp, na, memory_size=32, n_frames=1))
+    assert not env._fusable
+    for _ in range(T):
+        env.take_turn()
+    env.engine.check_errors()
+    grids = env.engine.grid_numpy()
+    for n in range(0, N, 5):
+        o = oracle(n, Draws(seed))
+        np.testing.assert_array_equal(grids[n], o.grid, err_msg=f"instance {n}")
+        assert float(env.world.total_reward[n]) == o.total_reward
+        for a in range(5):
+            mem = env.agents[a].model.memory
+            np.testing.assert_array_equal(mem.actions[:, n].cpu().numpy(), o.buffers[a].actions)
+            np.testing.assert_array_equal(mem.rewards[:, n].cpu().numpy(), o.buffers[a].rewards)

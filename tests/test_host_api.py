@@ -216,3 +216,33 @@ def test_iowa_kind_table_from_entity_classes_equals_oracle_spec():
         np.testing.assert_array_equal(getattr(got, f), getattr(ref, f), err_msg=f)
     # Sand is visible on layer 0: storing both layers per instance keeps the one-hot fast path
     assert got.resolved_dynamic_layers() == [0, 1] == ref.resolved_dynamic_layers()
+
+
+def test_tag_kind_table_from_entity_classes_equals_oracle_spec():
+    """examples/tag declared through TagAgent's class attributes (state_kinds / touch_swap / reward_by_state /
+    observe_flag) on the base Gridworld compiles to the oracle's tag spec (pinned to the reference's fixtures)."""
+    from sorrel_b200 import config as _config
+    from sorrel_b200.entities import EmptyEntity
+    from sorrel_b200.examples.tag.env import TagEnv
+    from sorrel_b200.worlds import Gridworld
+
+    cfg = {"experiment": {"epochs": 1, "max_turns": 10}, "model": {},
+           "agent": {"num_agents": 5, "vision_radius": 4, "it_agent": 3}, "world": {"height": 11, "width": 11, "layers": 1}}
+    world = Gridworld(**cfg["world"], default_entity=EmptyEntity(), num_envs=2)
+    env = TagEnv.__new__(TagEnv)
+    env.config, env.world, env.model_factory = _config.wrap(cfg), world, None
+    env._spawnable, env._item_groups = None, []
+    env.setup_agents()
+    env.populate_environment()
+    a0 = env.agents[0]
+    flags = [int(ag.flag) for ag in env.agents]
+    got = world.build_spec(a0, a0.observation_spec, a0.action_spec, 5, env._spawnable, env._item_groups, flags)
+    ref = util.engine_spec(R.tag_spec(11, 11, 5, 4, 10, it_agent=3))
+    assert got.kind_names == ref.kind_names == ["EmptyEntity", "Wall", "It", "NotIt"]
+    assert got.kind_passable == ref.kind_passable and got.kind_rule == ref.kind_rule
+    assert (got.agent_kind, got.agent_kind_alt, got.agent_layer, got.default_kind, got.fill_kind) == (3, 2, 0, 0, 1)
+    assert got.touch_swap and got.obs_flag and got.reward_own == ref.reward_own == [0.0, 0.0, 0.0, 10.0]
+    np.testing.assert_array_equal(got.initial_flags, ref.initial_flags)
+    for f in ("appearance", "template", "spawnable"):
+        np.testing.assert_array_equal(getattr(got, f), getattr(ref, f), err_msg=f)
+    assert got.obs_size == ref.obs_size == 4 * 81 + 1 and a0.observation_spec.input_size == (325, 1)
