@@ -439,6 +439,16 @@ class Engine:
             out[:, :, :, z] = g[:, pl, : H * W].reshape(self.N, H, W)
         return out
 
+    def grid_instance(self, env: int) -> np.ndarray:
+        """One instance as uint8 [H, W, L] (rendering / debugging: reads back a single instance, not the batch)."""
+        s = self.spec
+        H, W = s.height, s.width
+        out = s.template.copy()
+        g = self.grid[env].cpu().numpy()
+        for pl, z in enumerate(self.dyn_layers):
+            out[:, :, z] = g[pl, : H * W].reshape(H, W)
+        return out
+
     def agent_yx(self) -> np.ndarray:
         """int64 [N, A, 2] agent locations (y, x)."""
         p = self.agent_pos.cpu().numpy().astype(np.int64)

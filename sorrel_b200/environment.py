@@ -225,25 +225,37 @@ class Environment:
 
     def run_experiment(self, animate: bool = False, logging: bool = True, logger=None,
                        output_dir: Path | None = None) -> list[dict]:
-        """environment.py:108-211 without the host-only extras (GIF rendering, checkpoints):
+        """environment.py:108-211 without checkpoints; `animate=True` renders device instance 0 of every
+        `record_period`-th epoch to `<output_dir>/gifs/` through `sorrel_b200.visualization.ImageRenderer`:
         epochs x (reset, start_epoch_action, max_turns turns, end_epoch_action, train_step, log,
         epsilon decay).  Returns the per-epoch reward summaries."""
         exp = self.config.experiment
         history = []
         fuse = int(self.config.get("engine", {}).get("turns_per_launch", 25))
+        renderer = None
+        if animate:  # environment.py:136-142: one device instance is read back per turn of a recorded epoch
+            from .visualization import ImageRenderer
+
+            renderer = ImageRenderer(self.__class__.__name__, int(exp.get("record_period", 50)), int(exp.max_turns))
+            output_dir = Path(output_dir) if output_dir is not None else Path("./data/")
         for epoch in range(exp.epochs + 1):
             self.reset()
             self.add_empty()
+            animate_this_epoch = renderer is not None and epoch % renderer.record_period == 0
             for agent in self.agents:
                 agent.model.start_epoch_action(epoch=epoch)
             while not self.turn >= exp.max_turns:
+                if animate_this_epoch:
+                    renderer.add_image(self.world)
                 if self._fusable:
-                    self.take_turns(min(fuse, exp.max_turns - self.turn))
+                    self.take_turns(1 if animate_this_epoch else min(fuse, exp.max_turns - self.turn))
                 else:
                     self.take_turn()
                 if self.world.is_done and self.stop_if_done:
                     break
             self.world.is_done = True
+            if animate_this_epoch:
+                renderer.save_gif(epoch, output_dir / "gifs")
             total_loss = 0
             for agent in self.agents:
                 agent.model.end_epoch_action(epoch=epoch)

@@ -372,3 +372,26 @@ def test_tag_example_env_matches_oracle(cuda_device):
             mem = env.agents[a].model.memory
             np.testing.assert_array_equal(mem.actions[:, n].cpu().numpy(), o.buffers[a].actions)
             np.testing.assert_array_equal(mem.rewards[:, n].cpu().numpy(), o.buffers[a].rewards)
+
+
+def test_run_experiment_animate_writes_gif(cuda_device, tmp_path):
+    """ImageRenderer readback hook (utils/visualization.py:227-273): one frame per turn of a recorded epoch, painted
+    from a single device instance."""
+    from PIL import Image
+
+    from sorrel_b200.visualization import render_instance
+
+    env, cfg = _make(8, 3)
+    cfg["experiment"]["record_period"] = 1
+    env.config.experiment.record_period = 1
+    env.run_experiment(animate=True, logging=False, output_dir=tmp_path)
+    gifs = sorted((tmp_path / "gifs").glob("*.gif"))
+    assert len(gifs) == cfg["experiment"]["epochs"] + 1
+    with Image.open(gifs[0]) as im:
+        assert im.n_frames == cfg["experiment"]["max_turns"] and im.size == (13 * 16, 11 * 16)
+    frame = render_instance(env.world, env=2)
+    y, x = env.engine.agent_yx()[2, 0]
+    spec = env.engine.spec
+    assert frame.shape == (11 * 16, 13 * 16, 3) and frame[y * 16 + 8, x * 16 + 8].any()  # the agent's tile is painted
+    assert not frame[5 * 16 + 8, 0 * 16 + 8].tolist() == [0, 0, 0]  # the wall border is visible
+    assert spec.kind_names[int(env.engine.grid_instance(2)[y, x, 1])] == "TreasurehuntAgent"
