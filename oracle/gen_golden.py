@@ -245,7 +245,7 @@ def cleanup_grid_ids(world) -> np.ndarray:
 
 
 def run_cleanup_case(name, seed, H, W, A, v, T, epochs=1, initial_apples=20, apple_p=0.002, pollution_p=0.009,
-                     beam_radius=3, n_frames=1):
+                     beam_radius=3, n_frames=1, mode="DEFAULT"):
     """examples/cleanup with the reference's RandomModel (6 actions) instead of IQN; everything else unmodified."""
     from omegaconf import OmegaConf
     from sorrel.examples.cleanup.entities import EmptyEntity as CEmpty
@@ -257,7 +257,7 @@ def run_cleanup_case(name, seed, H, W, A, v, T, epochs=1, initial_apples=20, app
                        "record_period": 50},
         "env": {"height": H, "width": W, "layers": 3, "default_object": "EmptyEntity", "full_mdp": False,
                 "pollution_threshold": 0.5, "initial_apples": initial_apples, "apple_spawn_chance": apple_p,
-                "pollution_spawn_chance": pollution_p, "mode": "DEFAULT"},
+                "pollution_spawn_chance": pollution_p, "mode": mode},
         "model": {"iqn": {"type": "iRainbowModel", "parameters": {
             "layer_size": 16, "n_step": 3, "batch_size": 8, "memory_size": 64, "LR": 0.00025, "TAU": .001,
             "GAMMA": 0.99, "n_quantiles": 4, "sync_freq": 200, "model_update_freq": 4, "epsilon": 0.8,
@@ -292,7 +292,7 @@ def run_cleanup_case(name, seed, H, W, A, v, T, epochs=1, initial_apples=20, app
             totals.append(world.total_reward)
     mems = [ag.model.memory for ag in env.agents]
     data = dict(
-        world="cleanup", seed=seed, H=H, W=W, A=A, v=v, T=T, epochs=epochs, capacity=cap, n_frames=n_frames,
+        world="cleanup", mode=mode, seed=seed, H=H, W=W, A=A, v=v, T=T, epochs=epochs, capacity=cap, n_frames=n_frames,
         initial_apples=initial_apples, apple_p=apple_p, pollution_p=pollution_p, beam_radius=beam_radius,
         starts=np.array(starts, dtype=np.int64), grids=np.array(grids, dtype=np.uint8),
         facings=np.array(facings, dtype=np.int64), total_reward=np.array(totals, dtype=np.float64),
@@ -316,6 +316,10 @@ def cleanup_cases():
                      beam_radius=2)  # dense dynamics: many spawns, cleaned pollution, eaten apples
     run_cleanup_case("cleanup_s8_a6_12x19", 8, 12, 19, 6, 2, 40, epochs=2, initial_apples=5, apple_p=0.02,
                      pollution_p=0.05, n_frames=3)  # two episodes: facings persist across reset, ring add_empty
+    if len(sys.argv) > 2 and sys.argv[2] != "apple":
+        return
+    run_cleanup_case("cleanup_apple_s9_a5_11x14", 9, 11, 14, 5, 3, 40, initial_apples=12, apple_p=0.03,
+                     beam_radius=2, mode="APPLE")  # env.mode == "APPLE": orchard everywhere, no river
 
 
 IOWA_IDS = {"EmptyEntity": 0, "Wall": 1, "Sand": 2, "GamblingAgent": 7}

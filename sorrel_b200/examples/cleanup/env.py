@@ -35,12 +35,16 @@ class CleanupEnv(Environment):
     def populate_environment(self):
         spawn_points, apple_spawn_points = [], []
         world = self.world
-        if world.mode == "APPLE":
-            raise NotImplementedError("mode APPLE is not offered; the example's config uses DEFAULT")
         for index in np.ndindex(world.map.shape):
             H, W, L = index
             if H in [0, world.height - 1] or W in [0, world.width - 1]:
                 world.add(index, Wall())
+            elif L == 0 and world.mode == "APPLE":  # env.py:117-123: an orchard everywhere
+                world.add(index, AppleTree())
+                if ((H % 2) == 0) and ((W % 2) == 0):
+                    spawn_points.append((index[0], index[1], world.agent_layer))
+                else:
+                    apple_spawn_points.append(index)
             elif L == 0:
                 if (H > 0 and H < (world.height // 3)) or (
                         H < ((world.height // 3) * 2 - 1) and W in [world.width // 3, 1 + world.width // 3]):

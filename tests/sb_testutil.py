@@ -33,7 +33,8 @@ def cleanup_cases():
 
 def cleanup_spec_from_golden(g) -> R.WorldSpec:
     return R.cleanup_spec(int(g["H"]), int(g["W"]), int(g["A"]), int(g["v"]), int(g["initial_apples"]),
-                          float(g["apple_p"]), float(g["pollution_p"]), int(g["beam_radius"]))
+                          float(g["apple_p"]), float(g["pollution_p"]), int(g["beam_radius"]),
+                          mode=str(g["mode"]) if "mode" in g else "DEFAULT")
 
 
 def iowa_cases():

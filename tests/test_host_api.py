@@ -138,19 +138,20 @@ def test_rgb_observation_spec_matches_reference_map():
     assert got.obs_transform == 1
 
 
-def _cleanup_config(H=21, W=31, A=10, v=5, apples=20, apple_p=0.002, poll_p=0.009, radius=3):
+def _cleanup_config(H=21, W=31, A=10, v=5, apples=20, apple_p=0.002, poll_p=0.009, radius=3, mode="DEFAULT"):
     return {
         "experiment": {"name": "cleanup", "epochs": 1, "max_turns": 50},
         "env": {"height": H, "width": W, "layers": 3, "default_object": "EmptyEntity", "full_mdp": False,
                 "pollution_threshold": 0.5, "initial_apples": apples, "apple_spawn_chance": apple_p,
-                "pollution_spawn_chance": poll_p, "mode": "DEFAULT"},
+                "pollution_spawn_chance": poll_p, "mode": mode},
         "model": {"iqn": {"parameters": {"memory_size": 16}}},
         "agent": {"agent": {"num": A, "beam_radius": radius,
                             "obs": {"channels": 8, "vision": v, "n_frames": 2, "embeddings": 3}}},
     }
 
 
-@pytest.mark.parametrize("shape", [(21, 31, 10, 5, 20, 3), (15, 16, 4, 3, 8, 2)])
+@pytest.mark.parametrize("shape", [(21, 31, 10, 5, 20, 3, "DEFAULT"), (15, 16, 4, 3, 8, 2, "DEFAULT"),
+                                   (11, 14, 5, 3, 12, 2, "APPLE")])
 def test_cleanup_kind_table_from_entity_classes_equals_oracle_spec(shape):
     """examples/cleanup declared through Entity.transition_rule / Agent.action_effects compiles to the very
     tables the oracle's hand-written cleanup spec holds (which is pinned to the reference's fixtures)."""
@@ -159,8 +160,8 @@ def test_cleanup_kind_table_from_entity_classes_equals_oracle_spec(shape):
     from sorrel_b200.examples.cleanup.env import CleanupEnv
     from sorrel_b200.examples.cleanup.world import CleanupWorld
 
-    H, W, A, v, apples, radius = shape
-    cfg = _cleanup_config(H, W, A, v, apples, radius=radius)
+    H, W, A, v, apples, radius, mode = shape
+    cfg = _cleanup_config(H, W, A, v, apples, radius=radius, mode=mode)
     world = CleanupWorld(cfg, EmptyEntity(), num_envs=2)
     env = CleanupEnv.__new__(CleanupEnv)  # host-only: run the subclass hooks without compiling / CUDA
     env.config, env.world, env.model_factory = _config.wrap(cfg), world, None
@@ -169,7 +170,22 @@ def test_cleanup_kind_table_from_entity_classes_equals_oracle_spec(shape):
     env.populate_environment()
     a0 = env.agents[0]
     got = world.build_spec(a0, a0.observation_spec, a0.action_spec, A, env._spawnable, env._item_groups)
-    ref = util.engine_spec(R.cleanup_spec(H, W, A, v, apples, 0.002, 0.009, radius))
+    ref = util.engine_spec(R.cleanup_spec(H, W, A, v, apples, 0.002, 0.009, radius, mode=mode))
+    if mode == "APPLE":
+        # no river in this layout: the compiled table simply lacks the kinds that never occur (River, Pollution,
+        # Sand), so ids differ from the oracle's fixed 12-row table; compare through the kind names
+        to_ref = [ref.kind_names.index(n) for n in got.kind_names]
+        np.testing.assert_array_equal(np.asarray(to_ref)[got.template], ref.template)
+        for k, r in enumerate(to_ref):
+            assert (got.kind_value[k], got.kind_passable[k], got.kind_rule[k], got.kind_rule_prob[k]) == \
+                   (float(ref.kind_value[r]), ref.kind_passable[r], ref.kind_rule[r], ref.kind_rule_prob[r])
+            if got.kind_rule[k]:
+                assert to_ref[got.kind_rule_to[k]] == ref.kind_rule_to[r]
+            np.testing.assert_array_equal(got.appearance[k], ref.appearance[r])
+        np.testing.assert_array_equal(got.spawnable, ref.spawnable)
+        np.testing.assert_array_equal(got.item_groups[0][3], ref.item_groups[0][3])
+        assert to_ref[got.item_groups[0][0]] == ref.item_groups[0][0] and got.item_groups[0][2] == apples
+        return
     assert got.kind_names == ref.kind_names
     assert got.kind_value == [float(x) for x in ref.kind_value]
     assert got.kind_passable == ref.kind_passable and got.kind_rule == ref.kind_rule
