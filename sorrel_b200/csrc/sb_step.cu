@@ -18,16 +18,6 @@
 #include "sb_core.cuh"
 #include "sb_internal.h"
 
-// tuning knobs (compile-time; the defaults are the measured best, see profiles/README.md)
-#ifndef SB_SCATTER_UNROLL
-#define SB_SCATTER_UNROLL 1
-#endif
-#ifndef SB_COPY_UNROLL
-#define SB_COPY_UNROLL 1
-#endif
-#define SB_PRAGMA_(x) _Pragma(#x)
-#define SB_UNROLL(n) SB_PRAGMA_(unroll n)
-
 namespace sb {
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -95,14 +85,8 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
     // loop is unrolled so the dependent shared-memory reads of several cells are in flight together
     const uint32_t inv_s = d.inv_S;
     uint16_t* const srow16 = stage16 + off;  // hoisted: the compiler recomputed `off` under the store's predicate
-SB_UNROLL(SB_SCATTER_UNROLL)
-    for (int ij = lane; ij < d.SS; ij += LANES) {
-#ifdef SB_IJ_LUT
-      const uint32_t l_ = lut_ij[ij];
-      const int i = (int)(l_ >> 8), j = (int)(l_ & 255u);
-#else
+    for (int ij = lane; ij < d.SS; ij += LANES) {  // rolled: unrolling did not pay (profiles/README.md)
       const int i = (int)(((uint32_t)ij * inv_s) >> 16), j = ij - i * d.S;
-#endif
       if (NP1 && NB > 1) {
         // planes in GLOBAL memory (standalone observation kernel, unstaged large maps): issue the NB window
         // loads of this lane back to back, then the dependent scatters (the compiler cannot hoist a generic
@@ -205,7 +189,6 @@ SB_UNROLL(SB_SCATTER_UNROLL)
         stage[off + lane] = 0.0f;
       }
       float4* s4 = reinterpret_cast<float4*>(stage + off + head);
-SB_UNROLL(SB_COPY_UNROLL)
       for (int qv = lane; qv < nvec; qv += LANES) {
         const float4 v = s4[qv];
         s4[qv] = zero4;
@@ -478,7 +461,11 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         const int iters = (d.n_chunks + LPE - 1) / LPE;
         // The loop stays rolled (one Philox body in the instruction cache); a lane that finds
         // candidates only appends their cell ids to the warp queue.
-#pragma unroll 1
+#ifndef SB_SWEEP_UNROLL
+#define SB_SWEEP_UNROLL 2  // measured: 7.71 -> 7.59 ms at the default shape; x8 overflowed the instruction cache
+#endif
+        constexpr int kSweepUnroll = SB_SWEEP_UNROLL;
+#pragma unroll kSweepUnroll
         for (int it = 0; it < iters; ++it) {
           const int c = it * LPE + lane;
           uint32_t m = 0;
@@ -782,9 +769,6 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           if (tc >= 0) pre_tk = genv[d.agent_plane * d.plane_stride + tc];
         }
         observe(a);
-#ifdef SB_SPLIT_SYNC
-        __syncwarp();
-#endif
         act(a, pre_tk);
       }
     } else {
