@@ -117,7 +117,10 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
       ++n_spawn_kinds;
     } else if (rule == SB_RULE_SPAWN_TO) {
       if (!(w->kind_rule_prob[k] >= 0.0) || w->kind_rule_prob[k] > 1.0 || !kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
-      if (w->kind_rule_else[k] != SB_NO_KIND && !kind_ok(w->kind_rule_else[k])) return SB_EINVAL;
+      if (w->kind_rule_else[k] != SB_NO_KIND) {
+        if (!kind_ok(w->kind_rule_else[k])) return SB_EINVAL;
+        d.else_mask |= 1u << k;
+      }
       d.draw_mask |= 1u << k;
       d.prob[k] = w->kind_rule_prob[k];
       d.thr53[k] = spawn_threshold(d.prob[k]);

@@ -59,6 +59,7 @@ struct SbDev {
   int32_t ext_act;    // facings / beams / all-layer rewards / reward_count != 1
   uint32_t draw_mask; // kinds whose rule consumes a uniform (SPAWN, SPAWN_TO)
   uint32_t det_mask;  // kinds with a deterministic rule (BECOME_IF, BECOME)
+  uint32_t else_mask; // SPAWN_TO kinds whose failed draw still changes the kind (rule_else != SB_NO_KIND)
   uint8_t rule[SB_MAX_KINDS], rule_to[SB_MAX_KINDS], rule_else[SB_MAX_KINDS];
   int32_t agent_kind_alt, touch_swap, reward_own, obs_flag;  // agents with a second kind (tag)
   int32_t* agent_flag;           // device [N][A]
@@ -281,15 +282,20 @@ SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action
   float reward = d.value[tk];  // reward = value of the entity at the target cell (agent.py:219-220)
   if (reward64) *reward64 = d.value64[tk];
   if (all_layers) {  // sum over every layer of the target column (observe_all_layers, cleanup/agents.py:160-170)
+    // float32-exact values (cleanup: 0, 1, -1) are summed in float; the double path is taken only when asked for
     double r64 = 0.0;
+    reward = 0.0f;
     for (int z = 0; z < d.L; ++z) {
       const int pl = d.plane_of_layer[z];
       const uint32_t k = pl >= 0 ? genv[pl * d.plane_stride + ny * d.W + nx] : d.tmpl[z * d.plane_stride + ny * d.W + nx];
-      if (k < (uint32_t)d.K) r64 += d.value64[k];
-      else err |= SB_ERR_BAD_KIND;
+      if (k >= (uint32_t)d.K) err |= SB_ERR_BAD_KIND;
+      else if (reward64) r64 += d.value64[k];
+      else reward += d.value[k];
     }
-    reward = (float)r64;
-    if (reward64) *reward64 = r64;
+    if (reward64) {
+      reward = (float)r64;
+      *reward64 = r64;
+    }
   } else if (reward64) {
     reward = (float)*reward64;  // Buffer.rewards is float32 (buffers.py:33,58)
   }

@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
                   if (nk >= 0) genv[cell] = (uint8_t)nk;
                 } else if (sb_bernoulli_hit(d.thr53[kind], r8, envid, tick, cell, rk)) {
                   genv[cell] = d.rule_to[kind];
-                } else if (d.rule_else[kind] != SB_NO_KIND) {
+                } else if ((d.else_mask >> kind) & 1u) {  // register-resident mask: most failed draws change nothing
                   genv[cell] = d.rule_else[kind];
                 }
               } else {
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         uint32_t mine = (uint32_t)own;
         if (d.touch_swap) mine = sb_touch_swap(d, genv, yx);
         if (d.reward_own) {
-          reward = (float)d.value64[mine];
+          reward = d.value[mine];
           if (reward64) *reward64 = d.value64[mine];
         }
       } else {
@@ -692,12 +692,13 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       }
       if (lane == 0 && active) {
         // world.total_reward += reward (agent.py:172; cleanup adds it twice: cleanup/agents.py:172)
-        if (EXT && d.ext_act) {  // the double the reference adds (non-integer values, all-layer sums), x reward_count
+        if (EXT && d.use_value64) {  // values float32 cannot hold (iowa): accumulate the double the reference adds
           double r64 = 0.0;
           move_and_record(a, pre_tk, &r64);
           total += r64 * (double)d.reward_count;
         } else {
-          total += (double)move_and_record(a, pre_tk);
+          const float reward = move_and_record(a, pre_tk);
+          total += (double)(EXT ? reward * (float)d.reward_count : reward);
         }
       }
       __syncwarp();
