@@ -877,9 +877,10 @@ int pick_lpe(const SbDev& d) {
   int lpe = 4;
   while (lpe < 32 && d.n_chunks / lpe > 8) lpe *= 2;
   if (d.A >= 4 && lpe < 8) lpe = 8;  // agent phases dominate: halve their latency (measured, profiles/README.md)
-  // small batches: widen the group until ~16 warps per SM are in flight (148 SMs), trading lane
-  // efficiency for latency (config 2: 4096 instances would otherwise occupy 128 blocks)
-  while (lpe < 32 && (long long)d.N * lpe < 148LL * 16 * 32) lpe *= 2;
+  // small batches: widen the group until ~8 warps per SM are in flight (148 SMs), trading lane efficiency for
+  // latency.  Config 2 (4096 instances x 100 turns): LPE 4 / 8 / 16 / 32 = 0.457 / 0.368 / 0.362 / 0.453 ms --
+  // beyond ~14 warps per SM the extra instruction streams cost more than the latency they hide.
+  while (lpe < 32 && (long long)d.N * lpe < 148LL * 8 * 32) lpe *= 2;
   // shared memory must fit, and should not cap the SM below 6 resident blocks (24 warps): big staging rows
   // (cleanup: 4.4 KB of f32 per instance) are better served by wider groups (measured: 16.9 -> 13.7 ms)
   const bool np1 = d.fast_obs && d.n_planes == 1;
