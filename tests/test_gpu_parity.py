@@ -183,9 +183,12 @@ def test_golden_ring(name, cuda_device):
 # ------------------------------------------------------------------------------------------------
 # 2. many instances at once, replayed numpy streams (seed = instance id)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("A,H,v,p,T,N", [(1, 21, 2, 0.005, 100, 96), (8, 21, 2, 0.005, 40, 40),
-                                         (3, 9, 3, 0.15, 30, 33)])
-def test_batched_replay(A, H, v, p, T, N, cuda_device):
+@pytest.mark.parametrize("A,H,v,p,T,N,lpe", [(1, 21, 2, 0.005, 100, 96, None), (8, 21, 2, 0.005, 40, 40, None),
+                                             (3, 9, 3, 0.15, 30, 33, None), (1, 21, 2, 0.005, 60, 31, 4),
+                                             (8, 21, 2, 0.005, 25, 18, 8), (2, 21, 2, 0.01, 25, 12, 16)])
+def test_batched_replay(A, H, v, p, T, N, lpe, cuda_device, monkeypatch):
+    if lpe:  # the replay variant at the group widths large batches use
+        monkeypatch.setenv("SB_LPE", str(lpe))
     spec = R.treasurehunt_spec(H, H, A, v, p)
     envs, tapes, finals = [], [], []
     for n in range(N):
@@ -216,7 +219,11 @@ def test_batched_replay(A, H, v, p, T, N, cuda_device):
 @pytest.mark.parametrize("A,H,W,v,p,T,N,lpe", [
     (1, 21, 21, 2, 0.005, 60, 70, None), (8, 21, 21, 2, 0.005, 25, 37, None), (2, 11, 14, 3, 0.3, 20, 19, None),
     (4, 12, 12, 1, 0.9, 6, 9, None), (1, 21, 21, 2, 0.005, 30, 20, 8), (1, 21, 21, 2, 0.005, 30, 20, 32),
-    (3, 40, 40, 4, 0.01, 10, 6, None)])
+    (3, 40, 40, 4, 0.01, 10, 6, None),
+    # the group widths large batches run with (small test batches are widened to 32 lanes by pick_lpe):
+    (1, 21, 21, 2, 0.005, 50, 41, 4),   # the headline variant step_kernel<4, SIMD, NP1, STAGED>
+    (8, 21, 21, 2, 0.01, 20, 19, 4), (8, 21, 21, 2, 0.01, 20, 19, 8), (2, 30, 30, 3, 0.01, 12, 9, 16),
+    (3, 11, 14, 3, 0.3, 15, 13, 4)])    # generic sweep (p too large for the byte filter) at 4 lanes
 def test_philox_mode(A, H, W, v, p, T, N, lpe, cuda_device, monkeypatch):
     if lpe:
         monkeypatch.setenv("SB_LPE", str(lpe))
@@ -238,7 +245,8 @@ def test_philox_mode(A, H, W, v, p, T, N, lpe, cuda_device, monkeypatch):
 
 @pytest.mark.parametrize("A,H,W,v,p,T,N,lpe", [
     (1, 21, 21, 2, 0.005, 60, 70, None), (8, 21, 21, 2, 0.005, 25, 37, None), (2, 11, 14, 3, 0.03, 30, 19, None),
-    (1, 21, 21, 2, 0.005, 30, 20, 8), (1, 21, 21, 2, 0.02, 30, 12, 32), (3, 40, 40, 4, 0.002, 10, 6, None)])
+    (1, 21, 21, 2, 0.005, 30, 20, 8), (1, 21, 21, 2, 0.02, 30, 12, 32), (3, 40, 40, 4, 0.002, 10, 6, None),
+    (1, 21, 21, 2, 0.005, 40, 33, 4), (2, 30, 30, 3, 0.004, 12, 9, 16)])
 def test_sparse_mode(A, H, W, v, p, T, N, lpe, cuda_device, monkeypatch):
     """SB_RNG_SPARSE (Binomial count + distinct uniform cells): kernels == oracle with the same stream."""
     if lpe:
