@@ -83,9 +83,12 @@ def test_cleanup_golden_replay(name, fused, cuda_device):
             np.testing.assert_array_equal(row[key], g[key][a], err_msg=f"{key} agent {a}")
 
 
-def test_cleanup_philox_batch(cuda_device):
+@pytest.mark.parametrize("lpe", [None, 16, 8])
+def test_cleanup_philox_batch(lpe, cuda_device, monkeypatch):
     """Counter-based mode (in-kernel item / agent placement, Bernoulli draws, uniform policy): many instances
     against the oracle restatement on the same stream, including a second episode (facings persist)."""
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
     spec = R.cleanup_spec(13, 17, 5, 3, initial_apples=6, apple_spawn_chance=0.03, pollution_spawn_chance=0.06,
                           beam_radius=2)
     N, T, seed, base = 40, 24, 99, 1000
@@ -242,8 +245,12 @@ def test_iowa_golden_replay(name, fused, cuda_device):
             np.testing.assert_array_equal(row[key], g[key][a], err_msg=f"{key} agent {a}")
 
 
-def test_iowa_philox_batch(cuda_device):
+@pytest.mark.parametrize("lpe", [None, 8])  # 8 lanes is what pick_lpe gives this world at large batch sizes
+def test_iowa_philox_batch(lpe, cuda_device, monkeypatch):
     from oracle import coracle
+
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
 
     spec = R.iowa_spec(20, 20, 2, 2, 0.03)
     N, T, seed, base = 300, 40, 5, 77
@@ -308,8 +315,12 @@ def test_tag_golden_replay(name, fused, cuda_device):
             np.testing.assert_array_equal(row[key], g[key][a], err_msg=f"{key} agent {a}")
 
 
-def test_tag_philox_batch(cuda_device):
+@pytest.mark.parametrize("lpe", [None, 8, 4])
+def test_tag_philox_batch(lpe, cuda_device, monkeypatch):
     from oracle import coracle
+
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
 
     spec = R.tag_spec(9, 10, 6, 3, 10, it_agent=2)
     N, T, seed, base = 200, 30, 13, 9
