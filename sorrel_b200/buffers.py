@@ -115,6 +115,25 @@ class Buffer:
         self.idx = (self.idx + self.n_frames - 1) % self.capacity
         self.size = min(self.size + 1, self.capacity)
 
+    def add_from_buffer(self, buffer: "Buffer") -> None:
+        """buffers.py:71-96 for every row at once: append the first `buffer.size` slots of `buffer` at this ring's
+        head (truncated at the end of the ring, the head is NOT wrapped -- like the reference), extra_data included."""
+        assert self.obs_shape == buffer.obs_shape, "Cannot add from a buffer with different state shapes."
+        if self.rows != buffer.rows:
+            raise ValueError(f"row count mismatch: {self.rows} vs {buffer.rows}")
+        n = min(self.capacity - self.idx, buffer.size)
+        lo, hi = self.idx, self.idx + n
+        self.states[:, lo:hi] = buffer.states[:, :n].to(self.device)
+        self.actions[lo:hi] = buffer.actions[:n].to(self.device)
+        self.rewards[lo:hi] = buffer.rewards[:n].to(self.device)
+        self.dones[lo:hi] = buffer.dones[:n].to(self.device)
+        for key, value in buffer.extra_data.items():
+            if key not in self.extra_data:
+                self.extra_data[key] = torch.zeros((self.capacity, *value.shape[1:]), dtype=value.dtype,
+                                                   device=self.device)
+            self.extra_data[key][lo:hi] = value[:n].to(self.device)
+        self.idx = self.idx + n
+
     def sample_indices(self, batch_size: int, rows: torch.Tensor | np.ndarray | None = None):
         """The index draw of Buffer.sample (buffers.py:109-111), batched.
 

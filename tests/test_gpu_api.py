@@ -395,3 +395,28 @@ def test_run_experiment_animate_writes_gif(cuda_device, tmp_path):
     assert frame.shape == (11 * 16, 13 * 16, 3) and frame[y * 16 + 8, x * 16 + 8].any()  # the agent's tile is painted
     assert not frame[5 * 16 + 8, 0 * 16 + 8].tolist() == [0, 0, 0]  # the wall border is visible
     assert spec.kind_names[int(env.engine.grid_instance(2)[y, x, 1])] == "TreasurehuntAgent"
+
+
+def test_buffer_add_from_buffer(cuda_device):
+    """Buffer.add_from_buffer (buffers.py:71-96) against the reference semantics restated on numpy: appended at the
+    head, truncated at the end of the ring, head not wrapped, extra_data copied."""
+    from sorrel_b200.buffers import Buffer
+
+    rows, obs = 3, 7
+    src = Buffer(6, (obs,), rows=rows, device=cuda_device, positions=(2,))
+    dst = Buffer(10, (obs,), rows=rows, device=cuda_device, positions=(2,))
+    rng = np.random.RandomState(0)
+    for t in range(4):
+        src.add(torch.from_numpy(rng.rand(rows, obs).astype(np.float32)), torch.from_numpy(rng.randint(0, 4, rows)),
+                torch.from_numpy(rng.rand(rows).astype(np.float32)), torch.zeros(rows),
+                positions=torch.from_numpy(rng.randint(0, 9, (rows, 2))))
+    dst.idx = 8  # only 2 of the 4 experiences fit
+    dst.add_from_buffer(src)
+    assert dst.idx == 10
+    np.testing.assert_array_equal(dst.states[:, 8:10].cpu().numpy(), src.states[:, :2].cpu().numpy())
+    np.testing.assert_array_equal(dst.actions[8:10].cpu().numpy(), src.actions[:2].cpu().numpy())
+    np.testing.assert_array_equal(dst.extra_data["positions"][8:10].cpu().numpy(),
+                                  src.extra_data["positions"][:2].cpu().numpy())
+    assert not dst.states[:, :8].any()
+    with pytest.raises(AssertionError):
+        dst.add_from_buffer(Buffer(4, (obs + 1,), rows=rows, device=cuda_device))
