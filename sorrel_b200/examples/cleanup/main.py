@@ -2,8 +2,7 @@
 
     python -m sorrel_b200.examples.cleanup.main [num_envs]
 """
-import sys
-
+from sorrel_b200.examples._common import run_cli
 from sorrel_b200.examples.cleanup.entities import EmptyEntity
 from sorrel_b200.examples.cleanup.env import CleanupEnv
 from sorrel_b200.examples.cleanup.world import CleanupWorld
@@ -19,7 +18,4 @@ CONFIG = {
 }
 
 if __name__ == "__main__":
-    num_envs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-    world = CleanupWorld(config=CONFIG, default_entity=EmptyEntity(), num_envs=num_envs)
-    env = CleanupEnv(world, CONFIG)
-    env.run_experiment()
+    run_cli(lambda cfg, n: CleanupWorld(cfg, EmptyEntity(), num_envs=n), CleanupEnv, CONFIG, 2048)

@@ -1,13 +1,14 @@
-"""Mirrors sorrel/examples/iowa/world.py:13-23."""
-from sorrel_b200 import config as _config
+"""`GamblingWorld` of sorrel/examples/iowa/world.py:13-23: two layers, spawn probability from `config.world`."""
+from sorrel_b200.examples._common import batch_args, section
 from sorrel_b200.worlds import Gridworld
 
 
 class GamblingWorld(Gridworld):
+    LAYERS = 2  # visible Sand floor + the layer walls, decks and agents live on
+
     def __init__(self, config, default_entity, num_envs: int = 1, device="cuda", seed: int = 0,
                  env_id_base: int = 0):
-        layers = 2
-        config = _config.wrap(config)
-        super().__init__(config.world.height, config.world.width, layers, default_entity, num_envs=num_envs,
-                         device=device, seed=seed, env_id_base=env_id_base)
-        self.spawn_prob = config.world.spawn_prob
+        w = section(config, "world")
+        Gridworld.__init__(self, w.height, w.width, self.LAYERS, default_entity,
+                           **batch_args(num_envs, device, seed, env_id_base))
+        self.spawn_prob = w.spawn_prob

@@ -1,4 +1,5 @@
-"""Mirrors sorrel/examples/tag/env.py:25-117 (base `Gridworld`, `Wall` / `EmptyEntity` of sorrel_b200.entities)."""
+"""`TagEnv` of sorrel/examples/tag/env.py:25-117 on the batched `Environment` (base `Gridworld`, the `Wall` /
+`EmptyEntity` of sorrel_b200.entities)."""
 import numpy as np
 
 from sorrel_b200.action import ActionSpec
@@ -8,39 +9,40 @@ from sorrel_b200.examples.tag.agents import TagAgent
 from sorrel_b200.models import RandomModel
 from sorrel_b200.observation import OneHotObservationSpec
 
+ENTITY_LIST = ["EmptyEntity", "Wall", "It", "NotIt"]  # env.py:44
+ACTIONS = ["up", "down", "left", "right"]
+
 
 class TagEnv(Environment):
     def __init__(self, world, config, model_factory=None) -> None:
         self.model_factory = model_factory
         super().__init__(world, config)
 
+    def _make_model(self, input_size, n_actions):
+        if self.model_factory is not None:
+            return self.model_factory(input_size, n_actions)
+        m = self.config.model  # the reference builds an IQN here; the policy network is outside the engine
+        return RandomModel(input_size, n_actions, memory_size=int(m.get("memory_size", 1024)),
+                           n_frames=int(m.get("n_frames", 5)))
+
     def setup_agents(self):
-        agents = []
-        for _ in range(self.config.agent.num_agents):
-            entity_list = ["EmptyEntity", "Wall", "It", "NotIt"]
-            observation_spec = OneHotObservationSpec(entity_list, full_view=False,
-                                                     vision_radius=self.config.agent.vision_radius)
-            input_size = (int(np.prod(observation_spec.input_size) + 1), 1)  # one more input for self.it
-            observation_spec.override_input_size(input_size)
-            action_spec = ActionSpec(["up", "down", "left", "right"])
-            if self.model_factory is not None:
-                model = self.model_factory(observation_spec.input_size, action_spec.n_actions)
-            else:  # the reference builds a PyTorchIQN here; the policy network is out of the engine's scope
-                model = RandomModel(observation_spec.input_size, action_spec.n_actions,
-                                    memory_size=int(self.config.model.get("memory_size", 1024)),
-                                    n_frames=int(self.config.model.get("n_frames", 5)))
-            agents.append(TagAgent(observation_spec, action_spec, model))
-        # randomly choose one agent to be "it" (env.py:91-94); every instance starts with this choice
-        it_agent_index = int(self.config.agent.get("it_agent", np.random.choice(len(agents))))
-        agents[it_agent_index].it = True
-        self.agents = agents
+        cfg = self.config.agent
+        self.agents = []
+        for _ in range(cfg.num_agents):
+            spec = OneHotObservationSpec(ENTITY_LIST, full_view=False, vision_radius=cfg.vision_radius)
+            spec.override_input_size((int(np.prod(spec.input_size) + 1), 1))  # + the agent's own `it` flag
+            actions = ActionSpec(ACTIONS)
+            self.agents.append(TagAgent(spec, actions, self._make_model(spec.input_size, actions.n_actions)))
+        # env.py:91-94 draws the It agent once, at construction; every device instance starts from that choice
+        chosen = cfg.get("it_agent")
+        self.agents[int(np.random.choice(len(self.agents)) if chosen is None else chosen)].it = True
 
     def populate_environment(self):
-        valid_spawn_locations = []
+        top, right = self.world.height - 1, self.world.width - 1
+        free = []
         for index in np.ndindex(self.world.map.shape):
-            y, x, z = index
-            if y in [0, self.world.height - 1] or x in [0, self.world.width - 1]:
+            if index[0] in (0, top) or index[1] in (0, right):
                 self.world.add(index, Wall())
             else:
-                valid_spawn_locations.append(index)
-        self.place_agents(valid_spawn_locations)
+                free.append(index)
+        self.place_agents(free)

@@ -1,4 +1,8 @@
-"""Mirrors sorrel/examples/treasurehunt/env.py:24-147."""
+"""`TreasurehuntEnv` of sorrel/examples/treasurehunt/env.py:24-147 on the batched `Environment`.
+
+Same two hooks as the reference -- `setup_agents()` builds one agent slot per `config.model.num_agents`,
+`populate_environment()` lays out walls / sand and names the cells agents may start on -- but the agent placement
+itself is drawn per instance on the device (`place_agents`), and the policy is pluggable (`model_factory`)."""
 import numpy as np
 
 from sorrel_b200.action import ActionSpec
@@ -8,46 +12,44 @@ from sorrel_b200.examples.treasurehunt.entities import Sand, Wall
 from sorrel_b200.models import RandomModel
 from sorrel_b200.observation import OneHotObservationSpec, RGBObservationSpec
 
+ENTITY_LIST = ["EmptyEntity", "Wall", "Gem", "Bone", "Food", "TreasurehuntAgent"]  # env.py:43-50: channel order
+ACTIONS = ["up", "down", "left", "right"]  # env.py:79
+SPEC_TYPES = {"onehot": OneHotObservationSpec, "rgb": RGBObservationSpec}  # config.model.observation_spec
+
 
 class TreasurehuntEnv(Environment):
     def __init__(self, world, config, model_factory=None) -> None:
-        self.model_factory = model_factory
+        self.model_factory = model_factory  # (input_size, n_actions) -> BaseModel; default: RandomModel
         super().__init__(world, config)
 
+    def _make_model(self, input_size, n_actions):
+        if self.model_factory is not None:
+            return self.model_factory(input_size, n_actions)
+        m = self.config.model  # the reference builds an IQN here; the policy network is outside the engine
+        return RandomModel(input_size, n_actions, memory_size=int(m.get("memory_size", 1024)),
+                           n_frames=int(m.get("n_frames", 5)))
+
     def setup_agents(self):
-        agent_num = int(self.config.model.get("num_agents", 2))
-        agents = []
-        for _ in range(agent_num):
-            entity_list = ["EmptyEntity", "Wall", "Gem", "Bone", "Food", "TreasurehuntAgent"]
-            obs_spec_type = self.config.model.get("observation_spec", "onehot")
-            if obs_spec_type == "onehot":
-                observation_spec = OneHotObservationSpec(
-                    entity_list, full_view=False, vision_radius=self.config.model.agent_vision_radius)
-            elif obs_spec_type == "rgb":
-                observation_spec = RGBObservationSpec(
-                    entity_list, full_view=False, vision_radius=self.config.model.agent_vision_radius)
-            else:
-                raise ValueError(f"Unknown observation spec type: {obs_spec_type}")
-            observation_spec.override_input_size((int(np.prod(observation_spec.input_size)),))
-            action_spec = ActionSpec(["up", "down", "left", "right"])
-            if self.model_factory is not None:
-                model = self.model_factory(observation_spec.input_size, action_spec.n_actions)
-            else:  # the reference builds an IQN here; the policy network is out of the engine's scope
-                model = RandomModel(observation_spec.input_size, action_spec.n_actions,
-                                    memory_size=int(self.config.model.get("memory_size", 1024)),
-                                    n_frames=int(self.config.model.get("n_frames", 5)))
-            agents.append(TreasurehuntAgent(observation_spec, action_spec, model))
-        self.agents = agents
+        m = self.config.model
+        kind = m.get("observation_spec", "onehot")
+        if kind not in SPEC_TYPES:
+            raise ValueError(f"Unknown observation spec type: {kind}")
+        self.agents = []
+        for _ in range(int(m.get("num_agents", 2))):
+            spec = SPEC_TYPES[kind](ENTITY_LIST, full_view=False, vision_radius=m.agent_vision_radius)
+            spec.override_input_size((int(np.prod(spec.input_size)),))  # the model sees the flattened view
+            actions = ActionSpec(ACTIONS)
+            self.agents.append(TreasurehuntAgent(spec, actions, self._make_model(spec.input_size, actions.n_actions)))
 
     def populate_environment(self):
-        valid_spawn_locations = []
-        for index in np.ndindex(self.world.map.shape):
-            y, x, z = index
-            if (y in [0, self.world.height - 1] or x in [0, self.world.width - 1]) and z == 1:
-                self.world.add(index, Wall())
-            elif z == 0:
-                self.world.add(index, Sand())
-            elif z == 1:
-                valid_spawn_locations.append(index)
-        # the reference draws ONE placement here; every device instance draws its own at reset
-        self.place_agents(valid_spawn_locations)
+        top, right = self.world.height - 1, self.world.width - 1
+        spawn_cells = []
+        for y, x, z in np.ndindex(self.world.map.shape):
+            on_border = y in (0, top) or x in (0, right)
+            if z == 0:
+                self.world.add((y, x, z), Sand())  # floor everywhere, also under the walls (env.py:126-132)
+            elif on_border:
+                self.world.add((y, x, z), Wall())
+            else:
+                spawn_cells.append((y, x, z))
+        self.place_agents(spawn_cells)  # env.py:141-147, drawn per instance at every reset

@@ -1,18 +1,18 @@
-"""Mirrors sorrel/examples/treasurehunt/world.py:13-29."""
-from sorrel_b200 import config as _config
+"""`TreasurehuntWorld` of sorrel/examples/treasurehunt/world.py:13-29: two layers, item values and the spawn
+probability read from `config.world`."""
+from sorrel_b200.examples._common import batch_args, section
 from sorrel_b200.worlds import Gridworld
+
+ITEM_KEYS = ("gem", "food", "bone")  # config.world.<key>_value
 
 
 class TreasurehuntWorld(Gridworld):
+    LAYERS = 2  # floor (Sand) + the layer walls, items and agents live on
+
     def __init__(self, config, default_entity, num_envs: int = 1, device="cuda", seed: int = 0,
                  env_id_base: int = 0):
-        layers = 2
-        config = _config.wrap(config)
-        super().__init__(config.world.height, config.world.width, layers, default_entity, num_envs=num_envs,
-                         device=device, seed=seed, env_id_base=env_id_base)
-        self.values = {
-            "gem": config.world.gem_value,
-            "food": config.world.food_value,
-            "bone": config.world.bone_value,
-        }
-        self.spawn_prob = config.world.spawn_prob
+        w = section(config, "world")
+        Gridworld.__init__(self, w.height, w.width, self.LAYERS, default_entity,
+                           **batch_args(num_envs, device, seed, env_id_base))
+        self.spawn_prob = w.spawn_prob
+        self.values = {key: w[f"{key}_value"] for key in ITEM_KEYS}
