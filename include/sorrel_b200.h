@@ -7,6 +7,10 @@
  * Python methods.  Each entry point below names the reference method(s) it replaces
  * (file:line relative to the reference root); INTEGRATION.md shows the ctypes binding.
  *
+ * ABI history: v1 treasurehunt (SB_RULE_SPAWN, one-hot / RGB crops, ring, stats); v2 column rules, facings and beams,
+ * all-layer rewards, positional code, item groups (examples/cleanup); v3 value states and float64 rewards
+ * (examples/iowa); v4 agents with a second kind (examples/tag).  Fields are only ever appended.
+ *
  * Conventions
  *  - plain C types, pointers and sizes only; no C++/torch types.
  *  - every pointer named `d_*` or living in a struct documented "device" is a DEVICE pointer on
