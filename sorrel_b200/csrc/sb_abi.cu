@@ -88,6 +88,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   d.obs_flag = w->obs_flag ? 1 : 0;
   d.obs_size = d.oh_size + d.obs_extra + d.obs_flag;
   d.inv_S = (65536u + (uint32_t)d.S - 1u) / (uint32_t)d.S;
+  d.inv_W = ((uint64_t)d.HW * (uint64_t)d.W < (1ull << 32) && d.W > 1)
+                ? (uint32_t)(((1ull << 32) + (uint64_t)d.W - 1) / (uint64_t)d.W) : 0u;
   d.fill_kind = w->fill_kind;
   d.agent_kind = w->agent_kind;
   d.default_kind = w->default_kind;

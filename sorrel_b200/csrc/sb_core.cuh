@@ -30,6 +30,7 @@ struct SbDev {
   int32_t plane_of_layer[SB_MAX_LAYERS];  // -1 for static layers
   int32_t K, C, v, S, SS, obs_size;
   uint32_t inv_S;  // ceil(65536 / S): ij / S == (ij * inv_S) >> 16 for ij < 512
+  uint32_t inv_W;  // ceil(2^32 / W) when cell / W == umulhi(cell, inv_W) for every cell < H*W (H*W*W < 2^32), else 0
   int32_t fill_kind, agent_kind, default_kind, n_actions, n_choices;
   int32_t fast_obs;           // appearance rows are zero / one-hot and static layers invisible
   int32_t fill_channel;       // fast path: channel of the fill kind (or 255 = none)

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
     int y = 0, x = 0;
     if (valid) {
       const int pos = agent_pos[pair];
-      y = pos / d.W;
+      y = d.inv_W ? (int)__umulhi((uint32_t)pos, d.inv_W) : pos / d.W;  // exact multiply-shift division (make_dev)
       x = pos - y * d.W;
     }
     const uint8_t* genv = grid + (size_t)(valid ? env : 0) * d.env_stride;
