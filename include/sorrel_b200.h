@@ -191,6 +191,10 @@ typedef struct SbWorldDesc {
   int32_t reward_own;     /* 1: reward = kind_value[own kind after the exchange] instead of the target's value
                              (tag/agents.py:101-105) */
   int32_t obs_flag;       /* 1: the flag is appended to every observation as one more float (TagAgent.pov :55-65) */
+  int32_t toroidal;       /* engine option, NOT a reference behaviour (the reference pads crops with the fill kind and
+                             has no toroidal worlds): 1 = observation windows and moves wrap around
+                             the map edges; observations then take the general (table-sum) path */
+  int32_t reserved3;
   int32_t* d_agent_flag;  /* device int32 [N][A]: the flags; read by sb_reset / sb_reset_ex (they survive
                              Environment.reset like the agent attribute does), written back by sb_step; required iff
                              agent_kind_alt >= 0 */

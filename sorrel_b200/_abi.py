@@ -95,6 +95,8 @@ class SbWorldDesc(C.Structure):
         ("touch_swap", C.c_int32),
         ("reward_own", C.c_int32),
         ("obs_flag", C.c_int32),
+        ("toroidal", C.c_int32),
+        ("reserved3", C.c_int32),
         ("d_agent_flag", C.c_void_p),
     ]
 

@@ -204,7 +204,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   // one-hot fast path: every appearance row is all-zero or exactly one 1.0
   if (w->obs_transform != SB_OBS_SUM && w->obs_transform != SB_OBS_RGB) return SB_EINVAL;
   d.obs_transform = w->obs_transform;
-  d.fast_obs = (w->static_layers_invisible || d.n_planes == d.L) && d.obs_transform == SB_OBS_SUM ? 1 : 0;
+  d.toroidal = w->toroidal ? 1 : 0;
+  d.fast_obs = (w->static_layers_invisible || d.n_planes == d.L) && d.obs_transform == SB_OBS_SUM && !d.toroidal ? 1 : 0;
   for (int k = 0; k < d.K; ++k) {
     int ch = 255, ones = 0;
     for (int c = 0; c < d.C; ++c) {

@@ -62,6 +62,7 @@ struct SbDev {
   uint32_t det_mask;  // kinds with a deterministic rule (BECOME_IF, BECOME)
   uint32_t else_mask; // SPAWN_TO kinds whose failed draw still changes the kind (rule_else != SB_NO_KIND)
   uint8_t rule[SB_MAX_KINDS], rule_to[SB_MAX_KINDS], rule_else[SB_MAX_KINDS];
+  int32_t toroidal;  // engine option: crops and moves wrap around the map edges (general observation path)
   int32_t agent_kind_alt, touch_swap, reward_own, obs_flag;  // agents with a second kind (tag)
   int32_t* agent_flag;           // device [N][A]
   int32_t use_value64;           // rewards are value64 (Python floats that float32 cannot hold)
@@ -250,7 +251,7 @@ SB_HD int sb_target_cell(const SbDev& d, uint32_t yx, int action) {
   if ((unsigned)action >= (unsigned)d.n_actions) return -1;
   const int ny = (int)(yx >> 16) + (int)(int8_t)((d.dy_packed >> (8 * action)) & 0xFF);
   const int nx = (int)(yx & 0xFFFFu) + (int)(int8_t)((d.dx_packed >> (8 * action)) & 0xFF);
-  if ((unsigned)ny >= (unsigned)d.H || (unsigned)nx >= (unsigned)d.W) return -1;
+  if ((unsigned)ny >= (unsigned)d.H || (unsigned)nx >= (unsigned)d.W) return -1;  // (no prefetch across the seam)
   return ny * d.W + nx;
 }
 
@@ -271,8 +272,13 @@ SB_HD float sb_agent_act(const SbDev& d, uint8_t* genv, uint32_t* yx, int action
   }
   int ny = y + dy, nx = x + dx;
   if ((unsigned)ny >= (unsigned)d.H || (unsigned)nx >= (unsigned)d.W) {
-    err |= SB_ERR_OFFGRID;
-    return 0.0f;
+    if (!d.toroidal) {  // numpy index wrap / IndexError in the reference: reported, not emulated
+      err |= SB_ERR_OFFGRID;
+      return 0.0f;
+    }
+    ny = ny < 0 ? ny + d.H : (ny >= d.H ? ny - d.H : ny);  // explicit toroidal mode: moves cross the seam
+    nx = nx < 0 ? nx + d.W : (nx >= d.W ? nx - d.W : nx);
+    pre_tk = -1;
   }
   uint8_t* plane = genv + d.agent_plane * d.plane_stride;
   uint32_t tk = pre_tk >= 0 ? (uint32_t)pre_tk : plane[ny * d.W + nx];
@@ -341,7 +347,12 @@ SB_HD double sb_obs_general(const SbDev& d, const uint8_t* genv, const uint8_t* 
                             int y, int x, int c, int i, int j) {
   int yy = y - d.v + i, xx = x - d.v + j;
   double s = 0.0;
-  if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) {
+  const bool outside = (unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W;
+  if (outside && d.toroidal) {  // |offset| <= v <= (H-1)/2, so one fold is enough
+    yy = yy < 0 ? yy + d.H : (yy >= d.H ? yy - d.H : yy);
+    xx = xx < 0 ? xx + d.W : (xx >= d.W ? xx - d.W : xx);
+  }
+  if (outside && !d.toroidal) {
     s = app[d.fill_kind * d.C + c];
   } else {
     int cell = yy * d.W + xx;

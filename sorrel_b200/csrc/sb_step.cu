@@ -614,6 +614,9 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           if (dsts[1]) dsts[1][e] = vf;
         }
       }
+      // every lane has read the grid and the agent's position before lane 0 moves the agent (the fast paths get
+      // this from the barrier inside emit_onehot_row)
+      if (!(NP1 || d.fast_obs)) __syncwarp();
       if (EXT && d.obs_extra && active) {  // positional code of the agent's cell (CleanupObservation.observe)
         const float* src = d.extra_tbl + (size_t)(y * d.W + x) * d.obs_extra;
         for (int e = lane; e < d.obs_extra; e += LPE) {

@@ -73,6 +73,7 @@ class WorldSpec:
     touch_swap: bool = False
     reward_own: list[float] | None = None  # reward by the agent's own kind after the exchange
     obs_flag: bool = False
+    toroidal: bool = False  # engine option (not a reference behaviour): crops and moves wrap around the map edges
 
     @property
     def channels(self) -> int:
@@ -200,6 +201,7 @@ def build_desc(spec: WorldSpec, num_envs: int, env_id_base: int, dyn_layers: lis
     d.touch_swap = 1 if spec.touch_swap else 0
     d.reward_own = 1 if spec.reward_own is not None else 0
     d.obs_flag = 1 if spec.obs_flag else 0
+    d.toroidal = 1 if spec.toroidal else 0
     d.d_agent_flag = int(d_agent_flag) if d_agent_flag else None
     d.uses_facing = 1 if spec.uses_facing else 0
     for i in range(_abi.SB_MAX_ACTIONS):

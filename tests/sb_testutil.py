@@ -79,7 +79,7 @@ def engine_spec(o: R.WorldSpec):
         reward_all_layers=o.reward_all_layers, reward_count=o.reward_count, initial_facing=o.initial_facing,
         obs_extra=o.obs_extra, item_groups=list(o.item_groups),
         agent_kind_alt=o.agent_kind_alt, initial_flags=o.initial_flags, touch_swap=o.touch_swap,
-        reward_own=o.reward_own, obs_flag=o.obs_flag,
+        reward_own=o.reward_own, obs_flag=o.obs_flag, toroidal=bool(getattr(o, "toroidal", False)),
     )
 
 

@@ -654,3 +654,40 @@ def test_agent_parallel_path_matches_oracle(A, H, W, v, p, T, N, staged, cuda_de
     np.testing.assert_array_equal(buf.extra_data["positions"].cpu().numpy(), ring["positions"])
     got = obs_out.cpu().numpy().reshape(T - T // 2, N * A, -1)
     np.testing.assert_array_equal(got, np.moveaxis(ring["states"][:, T // 2:], 0, 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# engine option: toroidal worlds (crops and moves wrap around the map edges)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lpe", [None, 4])
+def test_toroidal_option_matches_oracle(lpe, cuda_device, monkeypatch):
+    """NOT a reference behaviour (the reference pads crops with the fill kind and indexes the map with plain numpy
+    indices): an explicit toroidal mode.  Windows that reach over an edge show the opposite side, an
+    agent that steps over an edge re-enters on the opposite side; compared with the oracle restatement's own
+    definition of the same option, and the standalone observation kernel agrees with the fused step."""
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
+    spec = R.torus_spec(12, 15, 3, 3, 0.02)
+    N, T, seed = 23, 40, 8
+    eng = _engine(spec, N, cuda_device, seed=seed)
+    buf = _buffer(spec, N, T, cuda_device)
+    eng.reset()
+    eng.step(T, buffer=buf)
+    eng.check_errors()  # nothing is "off the grid" on a torus
+    crossed = 0
+    for n in range(0, N, 4):
+        o, _ = util.run_oracle_episode(spec, R.PhiloxDraws(seed), T, env_id=n)
+        np.testing.assert_array_equal(eng.grid_numpy()[n], o.grid)
+        np.testing.assert_array_equal(eng.agent_yx()[n], o.pos)
+        for a in range(3):
+            np.testing.assert_array_equal(buf.row(n * 3 + a)["states"], o.buffers[a].states)
+            np.testing.assert_array_equal(buf.row(n * 3 + a)["rewards"], o.buffers[a].rewards)
+            p = o.buffers[a].positions
+            crossed += int((np.abs(np.diff(p[:, 0])) > 1).sum() + (np.abs(np.diff(p[:, 1])) > 1).sum())
+    assert crossed > 0  # some agent did cross a seam
+    obs = eng.observe().reshape(N, 3, -1).cpu().numpy()
+    full = eng.grid_numpy()
+    for n in (0, 7):
+        for a in range(3):
+            y, x = eng.agent_yx()[n, a]
+            np.testing.assert_array_equal(obs[n, a], R.observe(spec, full[n], y, x).reshape(-1).astype(np.float32))
