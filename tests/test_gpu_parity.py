@@ -691,3 +691,24 @@ def test_toroidal_option_matches_oracle(lpe, cuda_device, monkeypatch):
         for a in range(3):
             y, x = eng.agent_yx()[n, a]
             np.testing.assert_array_equal(obs[n, a], R.observe(spec, full[n], y, x).reshape(-1).astype(np.float32))
+
+
+@pytest.mark.parametrize("lpe", [None, 4, 8])
+def test_general_observation_path_batch(lpe, cuda_device, monkeypatch):
+    """RGBObservationSpec (general path: table sums in f64, clip / 255) on many instances and several agents at the
+    group widths large batches use -- the path where every lane reads the grid itself right before lane 0 moves the
+    agent (a missing barrier there was found with the toroidal test)."""
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
+    spec = R.treasurehunt_spec(13, 16, 5, 3, 0.04, obs="rgb")
+    N, T, seed = 48, 25, 77
+    eng = _engine(spec, N, cuda_device, seed=seed)
+    buf = _buffer(spec, N, T, cuda_device)
+    eng.reset()
+    eng.step(T, buffer=buf)
+    eng.check_errors()
+    for n in range(0, N, 5):
+        o, _ = util.run_oracle_episode(spec, R.PhiloxDraws(seed), T, env_id=n)
+        np.testing.assert_array_equal(eng.grid_numpy()[n], o.grid)
+        for a in range(5):
+            np.testing.assert_array_equal(buf.row(n * 5 + a)["states"], o.buffers[a].states)
