@@ -343,3 +343,55 @@ def test_tag_philox_batch(lpe, cuda_device, monkeypatch):
     obs = eng.observe()
     assert tuple(obs.shape) == (N, 6, spec.obs_size)
     np.testing.assert_array_equal(obs[:, :, -1].cpu().numpy(), co.flags.astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# randomized differential test of the rule-set extensions against the C oracle
+# ------------------------------------------------------------------------------------------------
+def _fuzz_rule_cases(n=8, seed=77):
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        H, W = int(rng.randint(9, 26)), int(rng.randint(9, 34))
+        v = int(rng.randint(1, min(5, (min(H, W) - 1) // 2) + 1))
+        lpe = [None, 8, 16, 32][int(rng.randint(0, 4))]
+        out.append(("cleanup", i, H, W, int(rng.randint(1, 9)), v, lpe, int(rng.randint(1, 4))))
+        out.append(("iowa", i, H, W, int(rng.randint(1, 7)), min(v, 3), lpe, 0))
+        out.append(("tag", i, min(H, 16), min(W, 16), int(rng.randint(2, 9)), min(v, (min(H, W, 16) - 1) // 2), lpe, 0))
+    return out
+
+
+@pytest.mark.parametrize("case", _fuzz_rule_cases(), ids=lambda c: f"{c[0]}{c[1]}-{c[2]}x{c[3]}a{c[4]}v{c[5]}")
+def test_fuzz_rule_sets_against_c_oracle(case, cuda_device, monkeypatch):
+    from oracle import coracle
+
+    kind, i, H, W, A, v, lpe, radius = case
+    if lpe:
+        monkeypatch.setenv("SB_LPE", str(lpe))
+    if kind == "cleanup":
+        spec = R.cleanup_spec(H, W, A, v, initial_apples=3, apple_spawn_chance=0.02, pollution_spawn_chance=0.05,
+                              beam_radius=radius)
+    elif kind == "iowa":
+        spec = R.iowa_spec(H, W, A, v, 0.04)
+    else:
+        spec = R.tag_spec(H, W, A, v, 10, it_agent=i % A)
+    N, T, seed, base = 17, 18, 500 + i, 11 * i
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    buf = _buffer(spec, N, T, cuda_device)
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
+    eng.reset()
+    eng.step(T // 3, buffer=buf)
+    eng.step(T - T // 3, buffer=buf)
+    eng.check_errors()
+    co.reset()
+    co.step(T)
+    np.testing.assert_array_equal(eng.grid_numpy(), co.grid)
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), co.total_reward)
+    ring = co.ring()
+    np.testing.assert_array_equal(buf.states.cpu().numpy(), ring["states"])
+    np.testing.assert_array_equal(buf.actions.cpu().numpy(), ring["actions"])
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
+    if kind == "cleanup":
+        np.testing.assert_array_equal(eng.agent_facing.cpu().numpy(), co.facing)
+    if kind == "tag":
+        np.testing.assert_array_equal(eng.agent_flag.cpu().numpy(), co.flags)
