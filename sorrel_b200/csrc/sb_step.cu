@@ -7,12 +7,20 @@
 //             -> visual_field                  observation/visual_field.py:9-101
 //   act     : MovingAgent.act / Gridworld.move agents/agent.py:215-225, worlds/gridworld.py:95-122
 //   record  : Agent.add_memory -> Buffer.add   agents/agent.py:113-136, buffers.py:46-63
+// and, in the replay / generic variants only (`EXT`), the rule extensions of the other shipped examples:
+//   column rules, facings + beams, all-layer rewards, positional code   examples/cleanup/{entities,agents}.py
+//   value states, float64 rewards                                       examples/iowa/entities.py:33-73
+//   agents with a second kind, role hand-over                           examples/tag/agents.py:40-106
 //
 // Tiling: a *group* of LPE lanes (4..32, a power of two) owns one world instance whose dynamic
 // planes are staged in shared memory for the whole launch (all `num_turns` turns), so the grid is
 // read and written once per launch while every turn streams one observation row per agent straight
 // into its replay-ring slot with 128-bit stores.  Groups never talk to each other; the only
-// intra-warp cooperation is the per-warp spawn-candidate queue of the Philox sweep.
+// intra-warp cooperation is the per-warp spawn-candidate queue of the Philox sweep.  Large maps keep their
+// planes in global memory (STAGED = false, one warp per instance); there four mutually distant agents are
+// observed and moved at once by 8 lanes each (see the fused loop).  All synchronisation is __syncwarp():
+// every phase that lets ONE lane mutate the instance (a move, a beam, a hand-over) is fenced from the phases in
+// which all lanes read it.
 #include <cuda_runtime.h>
 
 #include "sb_core.cuh"
