@@ -1,18 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- agent-env-steps/s (including observations) of the batched gridworld engine.
 
-    python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU)
-    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on host cores
+    python bench.py --gpus N --steps K --warmup W             # this engine (one rank per GPU), BASELINE configs[4]
+    python bench.py --config 2|3|4|4obs|4obs19|5|cleanup ...   # the other BASELINE shapes, same line schema
+    python bench.py --impl reference --gpus N --steps K ...    # CPU arm: the oracle port on the host cores
 
-Workload (BASELINE.json configs[4], the one the metric "at 1/2/4/8 B200" is quoted on):
-2^20 treasurehunt worlds in total (21x21x2, 1 agent, 5x5 one-hot view, C=6, spawn_prob 0.005,
-episodes of 100 turns), sharded over the ranks with no collective on the step path.  One *step* =
-one launch of `--turns` fused turns for every instance of the rank (entity sweep, observation written
-straight into the replay ring, move, reward, Buffer.add) followed by one Buffer.sample gather of
-turns*N/64 transitions (5 stacked frames); every 100 turns the worlds are reset (and `add_empty`
-advances the ring) exactly like Environment.run_experiment, and the per-episode reward statistics are
-all-reduced (the only collective).  `value` times that with everything resident in HBM; `e2e` drives the
-same launch from pinned HOST action buffers and reads the rewards back to the host every step.
+Default workload (BASELINE.json configs[4], the one the metric "at 1/2/4/8 B200" is quoted on): 2^20 treasurehunt
+worlds in total (21x21x2, 1 agent, 5x5 one-hot view, C=6, spawn_prob 0.005, episodes of 100 turns), sharded over the
+ranks with no collective on the step path.  The GPU arm is driven through the product API only --
+`sorrel_b200.examples.treasurehunt.{TreasurehuntWorld, TreasurehuntEnv}` and `Environment.begin_epoch / take_turns /
+sample_device` -- exactly what `Environment.run_experiment` calls.  One *step* = `take_turns(T)` (one launch of T fused
+turns for every instance of the rank: entity sweep, observation written straight into the replay ring, move, reward,
+Buffer.add) followed by one Buffer.sample gather of T*N*A/64 transitions (5 stacked frames); every 100 turns
+`begin_epoch()` reduces the episode's reward statistics (the only collective), resets the worlds and `add_empty`s the
+ring.  `value` times that with everything resident in HBM; `e2e` drives the same step from pinned HOST action buffers
+and reads the rewards back to the host every step (`sorrel_b200.hostio.HostStepPipeline`); observations stay in the
+device ring by design (they are the learner's input), so they are not part of the host traffic.
+
+`oracle/` (the CPU restatement) is imported by the `cpu_baseline` leg and by `--impl reference` only.
 """
 from __future__ import annotations
 
@@ -24,12 +29,22 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 METRIC = "agent_env_steps_per_sec_incl_obs"
 UNIT = "agent-env-steps/s"
+
+# BASELINE.json configs[1..4] (+ the cleanup example): argument presets
+PRESETS = {
+    "2": dict(envs_total=4096, turns=100),
+    "3": dict(envs_total=16384, agents=8, turns=25),
+    "4": dict(envs_total=2048, agents=64, size=128, vision=4, turns=10, capacity=16),
+    "4obs": dict(obs_study=True, envs_total=4096, agents=64, size=128, vision=4),
+    "4obs19": dict(obs_study=True, envs_total=4096, agents=64, size=128, vision=9),
+    "5": dict(),
+    "cleanup": dict(world="cleanup", agents=10, vision=5, envs_total=32768, turns=25, capacity=8),
+}
 
 
 def parse_args():
@@ -38,6 +53,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(PRESETS),
+                    help="BASELINE.json shape preset (explicit flags given after it still override)")
     ap.add_argument("--envs-total", type=int, default=1 << 20, help="world instances over all ranks")
     ap.add_argument("--turns", type=int, default=25, help="fused turns per launch (one step)")
     ap.add_argument("--agents", type=int, default=1)
@@ -63,6 +80,11 @@ def parse_args():
                          "21x31x3, 10 agents, 11x11 one-hot view + positional code, beams, column rules)")
     ap.add_argument("--obs-study", action="store_true",
                     help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
+    ap.add_argument("--lpe", type=int, default=0, help="diagnostic: pin the lanes per instance (SbStepArgs.tune_lpe)")
+    # presets first, then the command line on top of them
+    pre = ap.parse_known_args()[0]
+    if pre.config:
+        ap.set_defaults(**PRESETS[pre.config])
     return ap.parse_args()
 
 
@@ -76,6 +98,11 @@ def workload_name(a):
             f"sample 1/{a.sample_div}")
 
 
+def shape_key(a, n_per_gpu: int, rng: str | None = None) -> str:
+    """Key of profiles/traffic.json: one ncu-measured DRAM byte count per (shape, sampler)."""
+    return f"{a.world}:{a.size}:{a.agents}:v{a.vision}:n{n_per_gpu}:t{a.turns}:c{a.capacity}:{rng or a.rng}"
+
+
 def alg_bytes_per_env_step(a) -> int:
     """2*H*W*L_dyn + A*(C*S^2*4 + 36) + 8."""
     S = 2 * a.vision + 1
@@ -84,6 +111,60 @@ def alg_bytes_per_env_step(a) -> int:
     return 2 * a.size * a.size * 1 + a.agents * (6 * S * S * 4 + 36) + 8
 
 
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(key: str):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("step_kernel_dram_bytes_per_launch", {}).get(key)
+
+
+# ----------------------------------------------------------------------------------------------------
+# product-API construction of the world family (no oracle / tests import on this path)
+# ----------------------------------------------------------------------------------------------------
+def make_env(a, num_envs: int, device, env_id_base: int = 0, tuning=None):
+    """The reference's example wiring with the world / env classes swapped."""
+    if a.world == "cleanup":
+        from sorrel_b200.examples.cleanup.entities import EmptyEntity
+        from sorrel_b200.examples.cleanup.env import CleanupEnv
+        from sorrel_b200.examples.cleanup.main import CONFIG
+        from sorrel_b200.examples.cleanup.world import CleanupWorld
+        import copy
+
+        cfg = copy.deepcopy(CONFIG)
+        cfg["experiment"]["max_turns"] = a.max_turns
+        cfg["model"]["iqn"]["parameters"]["memory_size"] = a.capacity
+        cfg["agent"]["agent"]["num"] = a.agents
+        cfg["agent"]["agent"]["obs"].update(vision=a.vision, n_frames=a.n_frames)
+        world = CleanupWorld(cfg, EmptyEntity(), num_envs=num_envs, device=device, seed=a.seed,
+                             env_id_base=env_id_base)
+        world.tuning = tuning
+        return CleanupEnv(world, cfg)
+    from sorrel_b200.examples.treasurehunt.entities import EmptyEntity
+    from sorrel_b200.examples.treasurehunt.env import TreasurehuntEnv
+    from sorrel_b200.examples.treasurehunt.world import TreasurehuntWorld
+
+    cfg = {"world": dict(height=a.size, width=a.size, spawn_prob=a.spawn_prob, gem_value=10, food_value=5,
+                         bone_value=-10),
+           "model": dict(agent_vision_radius=a.vision, observation_spec="onehot", num_agents=a.agents,
+                         memory_size=a.capacity, n_frames=a.n_frames),
+           "experiment": dict(epochs=1, max_turns=a.max_turns),
+           "engine": dict(turns_per_launch=a.turns)}
+    world = TreasurehuntWorld(cfg, EmptyEntity(), num_envs=num_envs, device=device, seed=a.seed,
+                              env_id_base=env_id_base)
+    world.tuning = tuning
+    return TreasurehuntEnv(world, cfg)
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C port (the reference is pure Python and cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------------
 def oracle_spec(a):
     from oracle import restatement as R
 
@@ -92,15 +173,12 @@ def oracle_spec(a):
     return R.treasurehunt_spec(a.size, a.size, a.agents, a.vision, a.spawn_prob)
 
 
-# ----------------------------------------------------------------------------------------------------
-# CPU arm: the oracle's C port (the reference is pure Python and cannot travel to the GPU box)
-# ----------------------------------------------------------------------------------------------------
 def cpu_port_throughput(a, seconds: float, threads: int | None = None):
     from oracle import coracle
 
     threads = threads or coracle.max_threads()
     spec = oracle_spec(a)
-    n = max(threads * 64, 1024)
+    n = max(threads * 64, 1024) if a.size <= 32 else max(threads * 2, 32)
     co = coracle.COracle(spec, n, capacity=a.capacity, n_frames=a.n_frames, rng=coracle.RNG_NUMPY, seed=a.seed,
                          threads=threads)
     co.reset()
@@ -135,6 +213,27 @@ def python_port_throughput(a, seconds: float = 3.0):
         env.take_turn()
         n += a.agents
     return n / (time.perf_counter() - t0)
+
+
+def reference_python_rate(a, seconds: float = 3.0):
+    """The UNMODIFIED reference's own take_turn() loop on one core, when /root/reference is present (build container
+    only: a Python reference cannot travel to the GPU box).  Elsewhere: the figures recorded by
+    oracle/time_reference.py in the build container (profiles/reference_cpu_timings.json)."""
+    recorded = None
+    rec_path = os.path.join(ROOT, "profiles", "reference_cpu_timings.json")
+    if os.path.exists(rec_path):
+        recorded = json.load(open(rec_path))
+    if a.world != "treasurehunt" or not os.path.isdir("/root/reference/sorrel"):
+        return {"live": None, "note": "reference not on box (pure-Python package, build container only)",
+                "recorded_in_build_container": recorded}
+    try:
+        from oracle import time_reference as TR
+
+        rate = TR.single_process_rate(a.size, a.size, a.agents, a.vision, a.spawn_prob, seconds)
+        return {"live": rate, "unit": UNIT, "cores": 1, "note": "sorrel TreasurehuntEnv.take_turn, RandomModel policy",
+                "recorded_in_build_container": recorded}
+    except Exception as exc:  # noqa: BLE001
+        return {"live": None, "note": f"reference import failed: {exc!r}", "recorded_in_build_container": recorded}
 
 
 def run_reference(a):
@@ -223,14 +322,8 @@ class ClockSampler:
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
 def run_ours(a):
-    import numpy as np
     import torch
     import torch.distributed as dist
-
-    from sorrel_b200.buffers import Buffer
-    from sorrel_b200.engine import Engine
-    from sorrel_b200.stats import RewardStats
-    import sb_testutil as util
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -242,17 +335,13 @@ def run_ours(a):
     assert a.envs_total % world == 0
     N = a.envs_total // world
     T, A = a.turns, a.agents
-    spec = util.engine_spec(oracle_spec(a))
-    eng = Engine(spec, N, device=dev, env_id_base=rank * N, seed=a.seed)
-    buf = Buffer(a.capacity, (spec.obs_size,), n_frames=a.n_frames, rows=N * A, device=dev, positions=(2,))
-    stats = RewardStats(dev)
+    env = make_env(a, N, dev, env_id_base=rank * N, tuning={"lpe": a.lpe} if a.lpe else None)
+    eng, buf = env.engine, env.buffer
     lib = eng.lib
     B = (T * N * A) // a.sample_div if a.sample_div else 0
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
 
-    graphs = {}  # rng mode -> StepGraph
-    turns_in_episode = [a.max_turns]  # forces a reset at the first step
     episode_stats = []
     seg = {"boundary": [], "step": [], "sample": []}  # (event, event) pairs per segment, timed steps only
 
@@ -264,34 +353,22 @@ def run_ours(a):
         e[0].record()
         return e
 
-    def one_step(record=False, actions=None, reward_out=None):
-        if turns_in_episode[0] >= a.max_turns:  # Environment.run_experiment epoch boundary
+    def one_step(record=False, rng=a.rng):
+        """Environment.run_experiment's inner loop: epoch boundary every max_turns turns, T fused turns, one
+        learner batch."""
+        if env.turn >= a.max_turns:  # environment.py:128-133,191-199
             e = mark("boundary", record)
-            episode_stats.append(stats.all_reduce(eng.total_reward))  # NCCL all_gather, 40 bytes per rank
-            eng.reset()
-            buf.add_empty()
-            turns_in_episode[0] = 0
+            episode_stats.append(env.begin_epoch())  # stats all_gather (40 B per rank), reset, add_empty
             if e:
                 e[1].record()
-        sg = graphs.get(a.rng)  # CUDA-graph replay (device-resident tick/slot) once captured
         e = mark("step", record)
-        if sg is not None and actions is None:
-            sg.replay_step()
-        else:
-            eng.step(T, buffer=buf, actions=actions, reward_out=reward_out, rng=a.rng)
+        env.take_turns(T, rng=rng)
         if e:
             e[1].record()
-        turns_in_episode[0] += T
         out = None
         if B:
             e = mark("sample", record)
-            if sg is not None and actions is None:
-                out = sg.replay_sample()
-            else:
-                hi = max(1, buf.size - buf.n_frames - 1)
-                rows = torch.randint(0, N * A, (B,), device=dev, generator=gen)
-                starts = torch.randint(0, hi, (B,), device=dev, generator=gen)
-                out = buf.gather(rows, starts)
+            out = env.sample_device(B, rng=rng, generator=gen)
             if e:
                 e[1].record()
         return out
@@ -301,48 +378,40 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(rng):
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(a.steps):
+            one_step(record=True, rng=rng)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        return float(ts.item())
+
     # ---------------- device-resident throughput ("value") ----------------
+    env.turn = a.max_turns  # the constructor already reset once: start the first step with a full boundary
     # warm-up: at least W steps AND one full episode boundary (stats + reset kernels get loaded)
-    warm = max(a.warmup, a.max_turns // T + 1)
-    for _ in range(warm):
+    for _ in range(max(a.warmup, a.max_turns // T + 1)):
         one_step()
     if not a.no_graphs:  # the ring is full and every kernel has run once: capture, then warm the replays
-        from sorrel_b200.graphs import StepGraph
-
-        graphs[a.rng] = StepGraph(eng, buf, T, rng=a.rng, sample_batch=B)
+        env.enable_graphs(T, sample_batch=B, rng=a.rng)
         for _ in range(3):
             one_step()
+    plan = eng.step_plan(T, rng=a.rng)
     # NVML is initialised BEFORE the barrier: doing it after would make rank 0 enter the timed region a few
     # milliseconds late and every other rank wait for it at the first all-gather (measured: +4.6 ms)
     clocks = ClockSampler(local) if (rank == 0 and not a.no_clocks) else None
-    barrier()
     l0 = lib.sb_launch_count()
     t_wall0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    host_s = []
-    for i in range(a.steps):
-        h0 = time.perf_counter()
-        one_step(record=True)
-        host_s.append(time.perf_counter() - h0)
-    g1.record()
-    t_enq = time.perf_counter()
-    barrier()
+    ms_total = timed(a.rng)
     t_wall1 = time.perf_counter()
-    if os.environ.get("SB_BENCH_DEBUG"):
-        print(f"[rank {rank}] gpu_ms={g0.elapsed_time(g1):.3f} host_enqueue_ms={1e3 * (t_enq - t_wall0):.3f} "
-              f"host_step_ms max={1e3 * max(host_s):.3f} median={1e3 * sorted(host_s)[len(host_s) // 2]:.3f} "
-              f"wall_ms={1e3 * (t_wall1 - t_wall0):.3f}", file=sys.stderr, flush=True)
     launches = lib.sb_launch_count() - l0
-    ms_total = g0.elapsed_time(g1)
     eng.check_errors()
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in seg["step"]]
-    seg_main = seg
     breakdown = {k: sum(e0.elapsed_time(e1) for e0, e1 in v) / a.steps for k, v in seg.items()}
-    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total = float(tt.item())
     clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
     steps_total = a.envs_total * A * T * a.steps
     value = steps_total / (ms_total * 1e-3)
@@ -350,29 +419,22 @@ def run_ours(a):
     # ---------------- the same workload with the sparse spawn sampler (reported beside `value`) ----------------
     alt = None
     if a.rng == "philox" and eng.sparse_available and not a.no_alt:
-        a.rng = "sparse"
         seg = {"boundary": [], "step": [], "sample": []}
         for _ in range(3):
-            one_step()
+            one_step(rng="sparse")
         if not a.no_graphs:
-            graphs["sparse"] = StepGraph(eng, buf, T, rng="sparse", sample_batch=B)
+            env.enable_graphs(T, sample_batch=B, rng="sparse")
             for _ in range(3):
-                one_step()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for i in range(a.steps):
-            one_step(record=True)
-        s1.record()
-        barrier()
-        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                one_step(rng="sparse")
+        ms_alt = timed("sparse")
         sk = [e0.elapsed_time(e1) for e0, e1 in seg["step"]]
+        k_alt = sum(sk) / len(sk)
+        peak, _ = hbm_peak()
+        tr = measured_traffic(shape_key(a, N, "sparse"))
         alt = {"rng": "sparse (Binomial count + distinct cells; same law as one draw per cell)",
-               "value": steps_total / (float(ts.item()) * 1e-3), "unit": UNIT,
-               "ms_per_step": float(ts.item()) / a.steps, "kernel_ms": sum(sk) / len(sk)}
-        a.rng = "philox"
+               "value": steps_total / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt / a.steps,
+               "kernel_ms": k_alt, "frac": alg_bytes_per_env_step(a) * N * T / (k_alt * 1e-3) / 1e9 / peak,
+               "traffic": tr, "frac_dram": None if tr is None else tr / (k_alt * 1e-3) / 1e9 / peak}
         eng.check_errors()
 
     # ---------------- end-to-end with host buffers ----------------
@@ -381,24 +443,25 @@ def run_ours(a):
         from sorrel_b200.hostio import HostStepPipeline
 
         pipe = HostStepPipeline(eng, buf, T, rng=a.rng, timing=True)
-        h_actions = [torch.randint(0, 4, (T, N, A), dtype=torch.int32).pin_memory() for _ in range(2)]
-        def e2e_step(i):
-            """The same step as `one_step` (boundary stats + reset, fused turns, Buffer.sample), with the
-            step's actions coming from pinned host memory and its rewards read back to the host."""
-            if turns_in_episode[0] >= a.max_turns:
-                episode_stats.append(stats.all_reduce(eng.total_reward))
-                eng.reset()
-                buf.add_empty()
-                turns_in_episode[0] = 0
-            pipe.submit(h_actions[i % 2])
-            turns_in_episode[0] += T
-            if B:
-                hi = max(1, buf.size - buf.n_frames - 1)
-                rows = torch.randint(0, N * A, (B,), device=dev, generator=gen)
-                starts = torch.randint(0, hi, (B,), device=dev, generator=gen)
-                buf.gather(rows, starts)
+        n_act = env.agents[0].action_spec.n_actions
+        h_actions = [torch.randint(0, n_act, (T, N, A), dtype=torch.int32).pin_memory() for _ in range(2)]
 
-        for i in range(max(3, a.warmup)):
+        def e2e_step(i):
+            """The same step as `one_step` (boundary statistics + reset, fused turns, Buffer.sample), with the
+            step's actions coming from pinned host memory and its rewards read back to the host."""
+            if env.turn >= a.max_turns:
+                episode_stats.append(env.begin_epoch())
+            pipe.submit(h_actions[i % 2])
+            env.turn += T
+
+        for i in range(max(3, a.warmup)):  # eager: loads the tape-policy path
+            e2e_step(i)
+        pipe.drain()
+        if not a.no_graphs:  # per-slot graphs of [step, clock advance, index draw, sample] over fixed buffers
+            pipe = HostStepPipeline(eng, buf, T, rng=a.rng, timing=True, graphs=True, sample_batch=B)
+        else:
+            pipe.B = B
+        for i in range(3):
             e2e_step(i)
         pipe.drain()
         barrier()
@@ -418,8 +481,13 @@ def run_ours(a):
         e2e = {"value": steps_total / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
                "ms_per_step": e2e_ms / a.steps, "reward_checksum": float(results),
-               "step_kernel_ms": sum(e0.elapsed_time(e1) for e0, e1 in pipe.kernel_events[-a.steps:]) / a.steps}
+               "step_kernel_ms": sum(e0.elapsed_time(e1) for e0, e1 in pipe.kernel_events[-a.steps:]) / a.steps,
+               "api": "sorrel_b200.hostio.HostStepPipeline.submit (pinned host actions in, host rewards out, "
+                      "3 streams, 2 buffers in flight" + ("" if a.no_graphs else ", compute stage = CUDA graph") + ")",
+               "note": "observations are written straight into the device replay ring (the learner's input) and "
+                       "stay in HBM by design; only actions and rewards cross PCIe"}
         eng.check_errors()
+        buf.check_errors()
 
     if rank != 0:
         if world > 1:
@@ -427,39 +495,42 @@ def run_ours(a):
         return
 
     # ---------------- roofline of the dominant kernel ----------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     bytes_per_launch = alg_bytes_per_env_step(a) * N * T
     k_ms = sum(kernel_ms) / len(kernel_ms)
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):  # ncu-measured DRAM bytes of one launch; only valid for the shape it was taken on
-        tj = json.load(open(tp))
-        if (tj.get("envs_per_gpu"), tj.get("turns"), tj.get("agents"), tj.get("size")) == (N, T, A, a.size):
-            traffic = tj.get("step_kernel_dram_bytes_per_launch")
+    traffic = measured_traffic(shape_key(a, N))  # ncu dram bytes of ONE launch of exactly this shape, else null
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "sb::step_kernel", "kernel_ms": k_ms,
+                "traffic": traffic,
+                "frac_dram": None if traffic is None else traffic / (k_ms * 1e-3) / 1e9 / peak,
+                "kernel": plan["kernel"], "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                "step_kernel_share_of_step": k_ms * a.steps / ms_total, "breakdown_ms_per_step": breakdown}
+                "step_kernel_share_of_step": k_ms * a.steps / ms_total, "breakdown_ms_per_step": breakdown,
+                "note": "frac = algorithmic bytes (SURVEY 8d: grid r/w every turn) / time / peak; frac_dram = the "
+                        "DRAM bytes ncu measured for one launch of this shape / time / peak (turn fusion keeps the "
+                        "grid in shared memory, so it moves fewer bytes than the algorithmic count)"}
 
     cpu = None
     if not a.no_cpu:
         cpu = cpu_port_throughput(a, a.cpu_seconds)
-        cpu["python_port_1core"] = python_port_throughput(a, 2.0)
+        if a.size <= 32:
+            cpu["python_port_1core"] = python_port_throughput(a, 2.0)
+        cpu["reference_python"] = reference_python_rate(a)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(a), "envs_per_gpu": N, "parallelism": f"env-shard x{world}",
-                   "l2": "inputs larger than L2 (grid + ring slots touched per step >> 126 MB)",
+                   "l2": "inputs larger than L2 (grid + ring slots touched per step >> 126 MB)"
+                         if N * A * T * eng.spec.obs_size * 4 > 256e6 else
+                         "working set of a step fits L2 at this batch size (small-batch config as named)",
                    "policy": "in-kernel uniform (RandomModel)",
+                   "api": "TreasurehuntWorld/TreasurehuntEnv -> Environment.begin_epoch / take_turns / sample_device"
+                          if a.world == "treasurehunt" else
+                          "CleanupWorld/CleanupEnv -> Environment.begin_epoch / take_turns / sample_device",
                    "launch": "eager" if a.no_graphs else "CUDA graph replay (device-resident tick/slot)",
-                   "world": a.world,
+                   "world": a.world, "variant": plan,
                    "rng": "philox4x32-10, " + ("one byte per cell per turn" if a.rng == "philox" else
                                                "sparse (Binomial count + distinct cells)")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
@@ -475,15 +546,11 @@ def run_obs_study(a):
     """BASELINE configs[3]: large map, many agents, one-hot crop written at HBM speed (sb_observe alone)."""
     import torch
 
-    from sorrel_b200.engine import Engine
-    import sb_testutil as util
-
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    spec = util.engine_spec(oracle_spec(a))
     N, A = a.envs_total, a.agents
-    eng = Engine(spec, N, device=dev, seed=a.seed)
-    eng.reset()
+    env = make_env(a, N, dev)
+    eng, spec = env.engine, env.engine.spec
     # ~35 % of the interior pre-seeded with items (steady-state density of the reference, SURVEY 8d)
     g = eng.grid[:, 0, : a.size * a.size]
     items = torch.randint(2, 5, g.shape, device=dev, dtype=torch.uint8)
@@ -494,39 +561,46 @@ def run_obs_study(a):
     # rotate over several output tensors so that consecutive launches do not hit lines still in L2
     n_out = max(2, int(200e6 // (N * A * obs * 4)) + 1)
     outs = [torch.empty((N, A, spec.channels, S, S), dtype=torch.float32, device=dev) for _ in range(n_out)]
-    for i in range(a.warmup):
+    for i in range(max(3, a.warmup)):
         eng.observe(outs[i % n_out])
     torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    for i in range(a.steps):
+    clocks = None if a.no_clocks else ClockSampler(dev.index or 0, period=0.002)
+    reps = max(a.steps, 200)  # long enough for the NVML thread to see the region (launches are 0.1-0.4 ms)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    t0 = time.perf_counter()
+    for i in range(reps):
         evs[i][0].record()
         eng.observe(outs[i % n_out])
         evs[i][1].record()
     torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    clock_info = clocks.stop(t0, t1) if clocks else None
     ms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
     k_ms = sum(ms) / len(ms)
     alg = N * A * obs * 4 + N * a.size * a.size + N * A * 4
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) \
-        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    peak, peak_src = hbm_peak()
     ach = alg / (k_ms * 1e-3) / 1e9
     print(json.dumps({
         "metric": "observations_per_sec", "value": N * A / (k_ms * 1e-3), "unit": "obs/s", "n_gpus": 1,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": k_ms, "higher_is_better": True, "dtype": "u8",
+        "steps": reps, "warmup": max(3, a.warmup), "ms_per_step": k_ms, "higher_is_better": True, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": f"obs-kernel study: {N} envs x {A} agents, {a.size}x{a.size} map, {S}x{S} one-hot "
-                               f"window, C={spec.channels}, {obs * 4} B per observation, {n_out} rotating outputs"},
+                               f"window, C={spec.channels}, {obs * 4} B per observation, {n_out} rotating outputs",
+                   "api": "TreasurehuntEnv -> Engine.observe (sb_observe)",
+                   "l2": f"{n_out} rotating output tensors, {N * A * obs * 4 / 1e6:.0f} MB each"},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "kernel": "sb::observe_kernel", "kernel_ms": k_ms, "kernel_ms_min": ms[0],
-                     "algorithmic_bytes_per_launch": alg},
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+        "gpu_launches": reps, "clocks": clock_info,
     }), flush=True)
 
 
 def main():
     a = parse_args()
-    if a.obs_study:
-        run_obs_study(a)
-    elif a.impl == "reference":
+    if a.impl == "reference":
         run_reference(a)
+    elif a.obs_study:
+        run_obs_study(a)
     else:
         run_ours(a)
 

@@ -9,7 +9,8 @@
  *
  * ABI history: v1 treasurehunt (SB_RULE_SPAWN, one-hot / RGB crops, ring, stats); v2 column rules, facings and beams,
  * all-layer rewards, positional code, item groups (examples/cleanup); v3 value states and float64 rewards
- * (examples/iowa); v4 agents with a second kind (examples/tag).  Fields are only ever appended.
+ * (examples/iowa); v4 agents with a second kind (examples/tag); v5 launch tuning in SbStepArgs (the library reads no
+ * environment variables), sb_step_plan, device error word for the ring gathers.  Fields are only ever appended.
  *
  * Conventions
  *  - plain C types, pointers and sizes only; no C++/torch types.
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 4
+#define SB_ABI_VERSION 5
 
 #define SB_MAX_KINDS 32    /* entity classes per world (kind ids are uint8 < SB_MAX_KINDS) */
 #define SB_MAX_CHANNELS 32 /* observation channels C = len(entity_list) */
@@ -61,6 +62,8 @@ typedef enum SbStatus {
 #define SB_ERR_TAPE_ALIGN 2u /* replay: a cell drew a uniform where the tape holds NaN */
 #define SB_ERR_BAD_ACTION 4u /* action outside [0, num_actions) */
 #define SB_ERR_BAD_KIND 8u   /* grid byte >= num_kinds */
+#define SB_ERR_BAD_INDEX 16u /* Buffer.sample gather: row outside [0, rows) or start outside [0, capacity - n_frames):
+                                numpy raises IndexError there (buffers.py:112-119) */
 
 /* observation transforms */
 #define SB_OBS_SUM 0 /* OneHotObservationSpec / raw table sums (observation_spec.py:175-205) */
@@ -230,6 +233,9 @@ typedef struct SbBufferDesc {
   float* d_rewards;
   float* d_dones;
   int64_t* d_positions; /* may be NULL */
+  /* ---- ABI v5 ---- */
+  uint32_t* d_error;    /* optional device error word: the gathers OR SB_ERR_BAD_INDEX into it instead of reading
+                           outside the ring */
 } SbBufferDesc;
 
 /* sb_step modes */
@@ -261,7 +267,25 @@ typedef struct SbStepArgs {
                                 two counters from device memory instead of the fields above, so that an
                                 identical launch can be replayed from a CUDA graph (sb_clock_advance) */
   int32_t* d_agent_facing;   /* [N][A] MovingAgent.direction, read and written; required iff desc.uses_facing */
+  /* ---- ABI v5: launch tuning, 0 = the library chooses (tests pin the variant they check; sb_step_plan reports it).
+     These replace the SB_LPE / SB_STAGED / SB_NO_PAR environment variables v4 read at every launch. ---- */
+  int32_t tune_lpe;    /* lanes that own one instance: 0 auto, or 2 / 4 / 8 / 16 / 32 */
+  int32_t tune_staged; /* instance planes staged in shared memory for the launch: 0 auto, 1 staged, -1 used in place
+                          in global memory (one warp per instance: tune_lpe must be 0 or 32) */
+  int32_t tune_par;    /* agent-parallel path of warp-per-instance worlds: 0 auto, -1 off */
+  int32_t reserved5;
 } SbStepArgs;
+
+/* What sb_step would launch for (desc, args): filled by sb_step_plan without touching the device. */
+typedef struct SbStepPlan {
+  int32_t lpe;          /* lanes per instance */
+  int32_t kernel_rng;   /* 0 replay, 1 byte-SIMD Philox sweep, 2 generic Philox sweep, 3 sparse sampler */
+  int32_t fast_onehot;  /* 1: one stored plane + one-hot fast path (bf16 staging row, 128-bit stores) */
+  int32_t staged;       /* planes staged in shared memory */
+  int32_t par;          /* agent-parallel path enabled */
+  int32_t threads, smem_bytes;
+  int64_t blocks;
+} SbStepPlan;
 
 /* -- library / geometry ------------------------------------------------------------------ */
 int sb_abi_version(void);
@@ -303,6 +327,9 @@ int sb_reset_ex(const SbWorldDesc* desc, uint8_t* d_grid, int32_t* d_agent_pos, 
  */
 int sb_step(const SbWorldDesc* desc, const SbStepArgs* args, uint8_t* d_grid, int32_t* d_agent_pos,
             double* d_total_reward, const SbBufferDesc* buf, void* stream);
+
+/* The launch sb_step(desc, args, ...) would make (variant, tiling, shared memory, grid); no device work. */
+int sb_step_plan(const SbWorldDesc* desc, const SbStepArgs* args, SbStepPlan* out);
 
 /* Advance a device-resident {tick, slot} pair (see SbStepArgs.d_clock): tick += add_tick,
  * slot = (slot + add_slot) % capacity.  Graph-capturable companion of sb_step. */

@@ -11,7 +11,7 @@ from . import restatement as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "liboracle.so")
-RNG_NUMPY, RNG_PHILOX = 0, 1
+RNG_NUMPY, RNG_PHILOX, RNG_SPARSE = 0, 1, 2
 
 
 class OrWorld(C.Structure):
@@ -62,6 +62,8 @@ def lib():
         L.or_step.argtypes = [C.c_void_p, C.c_int]
         L.or_step.restype = None
         L.or_set_tick.argtypes = [C.c_void_p, C.c_uint32]
+        L.or_set_sparse_cdf.argtypes = [C.c_void_p, C.c_void_p]
+        L.or_set_env_ids.argtypes = [C.c_void_p, C.c_void_p]
         for name in ("or_grid", "or_pos", "or_facing", "or_flags", "or_total", "or_states", "or_actions", "or_rewards", "or_dones",
                      "or_positions", "or_tape_u", "or_tape_c", "or_tape_a", "or_tape_placement"):
             getattr(L, name).argtypes = [C.c_void_p]
@@ -88,7 +90,9 @@ class COracle:
 
     def __init__(self, spec: R.WorldSpec, num_envs: int, *, capacity: int = 0, n_frames: int = 1,
                  rng: int = RNG_PHILOX, seed: int = 0, env_id_base: int = 0, threads: int = 1,
-                 record: bool = False):
+                 record: bool = False, env_ids=None):
+        """`env_ids` (optional, length num_envs): global instance id of every instance -- replays a SAMPLE of a larger
+        counter-based batch (numpy mode: instance n is seeded seed + n regardless)."""
         self.L = lib()
         self.spec, self.N, self.capacity = spec, int(num_envs), int(capacity)
         w = OrWorld()
@@ -166,6 +170,14 @@ class COracle:
                                   1 if record else 0)
         self.plane_stride = R.plane_stride(spec.height, spec.width)
         self._T = 0
+        if rng == RNG_SPARSE:
+            cdf = R.binomial_cdf_u64(len(spec.dynamic_layers) * self.plane_stride, float(spec.spawn_prob))
+            self._cdf = np.array(cdf, dtype=np.uint64)
+            self.L.or_set_sparse_cdf(self.h, self._cdf.ctypes.data)
+        if env_ids is not None:
+            ids = np.ascontiguousarray(env_ids, dtype=np.uint64)
+            assert ids.shape == (self.N,)
+            self.L.or_set_env_ids(self.h, ids.ctypes.data)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -26,6 +26,8 @@
  *                    32-bit outputs, permutation = Fisher-Yates from the top with masked rejection.
  *                    Validated against numpy itself in tests/test_coracle.py.
  *   OR_RNG_PHILOX -- the engine's counter-based stream (Philox4x32-10).
+ *   OR_RNG_SPARSE -- the same stream with the spawn field sampled sparsely (Binomial count by inverse CDF on a
+ *                    caller-supplied exact table, then distinct uniform cells); placement and actions as PHILOX.
  *   tapes         -- OR_RNG_NUMPY can record the dense replay tapes the CUDA kernels consume.
  *
  * Parity status: pinned against tests/golden/ (generated from the unmodified reference).
@@ -41,6 +43,8 @@
 #define OR_MAX_LAYERS 8
 #define OR_RNG_NUMPY 0
 #define OR_RNG_PHILOX 1
+#define OR_RNG_SPARSE 2 /* Philox stream, sparse sampling of the spawn field (DESIGN.md "Counter-based RNG") */
+#define OR_SPARSE_KMAX 64
 #define OR_RULE_SPAWN 1
 #define OR_RULE_SPAWN_TO 2  /* Bernoulli(rule_prob[k]) -> rule_to[k], one uniform, no choice draw */
 #define OR_RULE_BECOME_IF 3 /* same column on rule_layer[k] holds a kind of rule_mask[k] -> rule_to[k] */
@@ -53,6 +57,7 @@
 #define DOM_CELL 0x43450000u
 #define DOM_ACTION 0x41430000u
 #define DOM_RESET 0x52530000u
+#define DOM_SPARSE 0x53500000u
 
 /* ---------------------------------------------------------------------------------------------
  * MT19937 + numpy legacy draws
@@ -226,7 +231,13 @@ typedef struct {
   int tape_T;
   uint32_t hi8;
   uint64_t lo45;
+  uint64_t cdf[OR_SPARSE_KMAX]; /* OR_RNG_SPARSE: floor(2^64 P(X <= k)), X ~ Binomial(n_dyn*plane_stride, P/2^53) */
+  uint64_t* env_ids;            /* optional [N]: global id of every instance (else env_id_base + n) */
 } or_env_t;
+
+static inline uint32_t env_id_of(const or_env_t* e, int64_t n) {
+  return (uint32_t)(e->env_ids ? e->env_ids[n] : e->env_id_base + (uint64_t)n);
+}
 
 static int zd_of_layer(const or_world_t* w, int z) {
   for (int i = 0; i < w->n_dyn; ++i)
@@ -283,6 +294,7 @@ void or_destroy(or_env_t* e) {
   free(e->grid), free(e->pos), free(e->total), free(e->mt), free(e->states), free(e->actions);
   free(e->rewards), free(e->dones), free(e->positions), free(e->tape_u), free(e->tape_c), free(e->tape_a);
   free(e->tape_pl);
+  free(e->env_ids);
   free(e);
 }
 
@@ -305,7 +317,7 @@ static void reset_range(or_env_t* e, int64_t n0, int64_t n1) {
         np_permutation_head(&e->mt[n], nc, cnt, gp, sc);
         free(sc);
       } else {
-        uint32_t env = (uint32_t)(e->env_id_base + (uint64_t)n), j = (uint32_t)(gi + 1) << 24, r[4];
+        uint32_t env = env_id_of(e, n), j = (uint32_t)(gi + 1) << 24, r[4];
         for (int a = 0; a < cnt; ++a) {
           for (;;) {
             philox(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
@@ -326,7 +338,7 @@ static void reset_range(or_env_t* e, int64_t n0, int64_t n1) {
       /* np.random.choice(len(valid), size=A, replace=False) == permutation(len)[:A], env.py:141 */
       np_permutation_head(&e->mt[n], w->n_spawnable, w->A, picks, scratch);
     } else {
-      uint32_t env = (uint32_t)(e->env_id_base + (uint64_t)n), j = 0, r[4];
+      uint32_t env = env_id_of(e, n), j = 0, r[4];
       for (int a = 0; a < w->A; ++a) {
         for (;;) {
           philox(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
@@ -385,7 +397,7 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
   const size_t cells = (size_t)w->H * w->W * w->L, rows = (size_t)e->N * w->A;
   uint8_t* g = e->grid + n * cells;
   mt_t* mt = e->mt ? &e->mt[n] : 0;
-  const uint32_t env = (uint32_t)(e->env_id_base + (uint64_t)n);
+  const uint32_t env = env_id_of(e, n);
   const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
   const size_t tape_stride = (size_t)w->n_dyn * e->plane_stride;
   float obs_local[32 * 21 * 21 + 256];
@@ -393,6 +405,31 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
     const uint32_t tick = e->tick + 1 + (uint32_t)t;
     double* tu = e->record ? e->tape_u + ((size_t)(t_base + t) * e->N + n) * tape_stride : 0;
     uint8_t* tc = e->record ? e->tape_c + ((size_t)(t_base + t) * e->N + n) * tape_stride : 0;
+    if (e->rng_mode == OR_RNG_SPARSE) {
+      /* The iid Bernoulli(p) field of entities.py:72-75 sampled sparsely: K ~ Binomial(cells, P/2^53) by inverse
+         CDF, then K distinct uniform cells of the padded plane layout by sequential rejection over the draw stream
+         j = 1, 2, ...; a hit spawns iff the cell (still) carries the spawn rule. */
+      uint32_t r[4];
+      const uint32_t n_cells = (uint32_t)tape_stride;
+      philox(env, tick, 0u, DOM_SPARSE, k0, k1, r);
+      const uint64_t u = ((uint64_t)r[0] << 32) | r[1];
+      int K = 0;
+      while (K < OR_SPARSE_KMAX && u >= e->cdf[K]) ++K;
+      uint32_t hits[OR_SPARSE_KMAX], j = 1;
+      for (int got = 0; got < K;) {
+        philox(env, tick, j++, DOM_SPARSE, k0, k1, r);
+        const uint32_t pos = bounded64(r[0], r[1], n_cells);
+        int dup = 0;
+        for (int h = 0; h < got; ++h) dup |= hits[h] == pos;
+        if (dup) continue;
+        hits[got++] = pos;
+        const int zd = (int)(pos / (uint32_t)e->plane_stride), off = (int)(pos % (uint32_t)e->plane_stride);
+        if (off >= w->H * w->W) continue; /* padding byte */
+        uint8_t* cellp = g + (size_t)off * w->L + w->dyn_layers[zd];
+        if (w->rule[*cellp] == OR_RULE_SPAWN)
+          *cellp = (uint8_t)w->choices[bounded64(r[2], r[3], (uint32_t)w->n_choices)];
+      }
+    } else
     /* entity sweep in C order (y, x, z) over the live map, environment.py:88-91 */
     for (int y = 0; y < w->H; ++y)
       for (int x = 0; x < w->W; ++x)
@@ -608,6 +645,14 @@ int32_t* or_tape_placement(or_env_t* e) { return e->tape_pl; }
 int or_idx(or_env_t* e) { return e->idx; }
 int or_size(or_env_t* e) { return e->size; }
 void or_set_tick(or_env_t* e, uint32_t tick) { e->tick = tick; }
+void or_set_sparse_cdf(or_env_t* e, const uint64_t* cdf) { memcpy(e->cdf, cdf, sizeof(e->cdf)); }
+/* global instance ids (Philox counter word 0) of a SAMPLE of a larger batch: lets a test replay instances
+   {i0, i1, ...} of a 2^20-instance launch without stepping the rest */
+void or_set_env_ids(or_env_t* e, const uint64_t* ids) {
+  free(e->env_ids);
+  e->env_ids = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)e->N);
+  memcpy(e->env_ids, ids, sizeof(uint64_t) * (size_t)e->N);
+}
 int or_max_threads(void) {
   long n = sysconf(_SC_NPROCESSORS_ONLN);
   return n > 0 ? (int)n : 1;

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-SB_ABI_VERSION = 4
+SB_ABI_VERSION = 5
 SB_MAX_KINDS = 32
 SB_MAX_CHANNELS = 32
 SB_MAX_LAYERS = 8
@@ -21,7 +21,7 @@ SB_MAX_BEAM_CELLS = 16
 SB_MAX_ITEM_GROUPS = 4
 
 SB_OK, SB_EINVAL, SB_EUNSUPPORTED, SB_EALIGN, SB_ECUDA, SB_ENODEVICE, SB_EVISION = 0, -1, -2, -3, -4, -5, -6
-SB_ERR_OFFGRID, SB_ERR_TAPE_ALIGN, SB_ERR_BAD_ACTION, SB_ERR_BAD_KIND = 1, 2, 4, 8
+SB_ERR_OFFGRID, SB_ERR_TAPE_ALIGN, SB_ERR_BAD_ACTION, SB_ERR_BAD_KIND, SB_ERR_BAD_INDEX = 1, 2, 4, 8, 16
 SB_RULE_NONE, SB_RULE_SPAWN, SB_RULE_SPAWN_TO, SB_RULE_BECOME_IF, SB_RULE_BECOME = 0, 1, 2, 3, 4
 SB_RNG_TAPE, SB_RNG_PHILOX, SB_RNG_SPARSE = 0, 1, 2
 SB_SPARSE_KMAX = 64
@@ -124,6 +124,8 @@ class SbBufferDesc(C.Structure):
         ("d_rewards", C.c_void_p),
         ("d_dones", C.c_void_p),
         ("d_positions", C.c_void_p),
+        # ---- ABI v5 ----
+        ("d_error", C.c_void_p),
     ]
 
 
@@ -150,7 +152,34 @@ class SbStepArgs(C.Structure):
         ("d_error", C.c_void_p),
         ("d_clock", C.c_void_p),
         ("d_agent_facing", C.c_void_p),
+        # ---- ABI v5: launch tuning (0 = the library chooses) ----
+        ("tune_lpe", C.c_int32),
+        ("tune_staged", C.c_int32),
+        ("tune_par", C.c_int32),
+        ("reserved5", C.c_int32),
     ]
+
+
+class SbStepPlan(C.Structure):
+    _fields_ = [
+        ("lpe", C.c_int32),
+        ("kernel_rng", C.c_int32),
+        ("fast_onehot", C.c_int32),
+        ("staged", C.c_int32),
+        ("par", C.c_int32),
+        ("threads", C.c_int32),
+        ("smem_bytes", C.c_int32),
+        ("blocks", C.c_int64),
+    ]
+
+    KERNEL_RNG = {0: "replay", 1: "philox byte-SIMD", 2: "philox generic", 3: "sparse"}
+
+    def as_dict(self) -> dict:
+        return {"kernel": f"sb::step_kernel<{self.lpe},{self.kernel_rng},{self.fast_onehot},{self.staged}>",
+                "lanes_per_instance": self.lpe, "sweep": self.KERNEL_RNG.get(self.kernel_rng, "?"),
+                "fast_onehot": bool(self.fast_onehot), "planes_staged": bool(self.staged),
+                "agent_parallel": bool(self.par), "threads": self.threads, "smem_bytes": self.smem_bytes,
+                "blocks": int(self.blocks)}
 
 
 # name -> (restype, argtypes); every symbol include/sorrel_b200.h declares
@@ -168,6 +197,7 @@ SIGNATURES = {
                               C.c_void_p, C.POINTER(SbItemGroup), C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "sb_step": (C.c_int, [C.POINTER(SbWorldDesc), C.POINTER(SbStepArgs), C.c_void_p, C.c_void_p, C.c_void_p,
                           C.POINTER(SbBufferDesc), C.c_void_p]),
+    "sb_step_plan": (C.c_int, [C.POINTER(SbWorldDesc), C.POINTER(SbStepArgs), C.POINTER(SbStepPlan)]),
     "sb_clock_advance": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sb_observe": (C.c_int, [C.POINTER(SbWorldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_buffer_add": (C.c_int, [C.POINTER(SbBufferDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -237,8 +267,10 @@ def error_bits_to_exception(bits: int) -> Exception | None:
         names.append("action outside the ActionSpec (KeyError in the reference, action_spec.py:27-36)")
     if bits & SB_ERR_BAD_KIND:
         names.append("grid holds a kind id >= num_kinds")
+    if bits & SB_ERR_BAD_INDEX:
+        names.append("Buffer.sample index outside the ring (IndexError in the reference, buffers.py:112-119)")
     msg = "; ".join(names)
-    if bits & SB_ERR_OFFGRID:
+    if bits & (SB_ERR_OFFGRID | SB_ERR_BAD_INDEX):
         return IndexError(msg)
     if bits & SB_ERR_BAD_ACTION:
         return KeyError(msg)

@@ -42,6 +42,7 @@ class Buffer:
         if self.device.type != "cuda":
             raise _abi.SorrelB200Error("sorrel_b200.Buffer lives on a CUDA device (no CPU fallback)")
         self.extra_data: dict[str, torch.Tensor] = {}
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)  # device error word of the gathers
         self._alloc()
         for key, value in kwargs.items():  # buffers.py:38-44
             shape = (self.capacity, self.rows, *value) if isinstance(value, tuple) else (self.capacity, self.rows)
@@ -69,6 +70,7 @@ class Buffer:
             d.d_dones = self.dones.data_ptr()
             pos = self.extra_data.get("positions")
             d.d_positions = pos.data_ptr() if pos is not None else None
+            d.d_error = self.error.data_ptr()
             self._desc = d
         return self._desc
 
@@ -128,9 +130,12 @@ class Buffer:
         self.rewards[lo:hi] = buffer.rewards[:n].to(self.device)
         self.dones[lo:hi] = buffer.dones[:n].to(self.device)
         for key, value in buffer.extra_data.items():
+            if value.shape[1] != self.rows:
+                raise ValueError(f"extra_data[{key!r}]: {value.shape[1]} rows, this ring has {self.rows}")
             if key not in self.extra_data:
                 self.extra_data[key] = torch.zeros((self.capacity, *value.shape[1:]), dtype=value.dtype,
                                                    device=self.device)
+                self._desc = None  # the cached C view may not know this array yet (positions)
             self.extra_data[key][lo:hi] = value[:n].to(self.device)
         self.idx = self.idx + n
 
@@ -146,6 +151,29 @@ class Buffer:
             rows = np.zeros(batch_size, dtype=np.int64) if self.rows == 1 else \
                 np.random.randint(0, self.rows, size=batch_size)
         return np.asarray(rows, dtype=np.int64), starts.astype(np.int64)
+
+    def sample_indices_device(self, batch_size: int, generator: torch.Generator | None = None):
+        """Index draw for training loops: (rows, starts) drawn ON THE DEVICE, no host synchronisation (the host draw
+        above is kept for seed-for-seed agreement with the reference).  Pairs are drawn independently -- with `rows`
+        x `size` transitions to choose from, repeats are as rare as they are harmless; a single-row ring whose
+        population is smaller than the batch still raises like the reference's `replace=False` draw."""
+        hi = max(1, self.size - self.n_frames - 1)
+        if self.rows * hi < batch_size:
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        rows = torch.randint(0, self.rows, (batch_size,), device=self.device, generator=generator)
+        starts = torch.randint(0, hi, (batch_size,), device=self.device, generator=generator)
+        return rows, starts
+
+    def sample_device(self, batch_size: int, generator: torch.Generator | None = None):
+        """`sample` with the index draw on the device (see `sample_indices_device`)."""
+        return self.gather(*self.sample_indices_device(batch_size, generator))
+
+    def check_errors(self) -> None:
+        """Synchronising read of the gathers' device error word; IndexError like numpy's fancy indexing."""
+        bits = int(self.error.item())
+        if bits:
+            self.error.zero_()
+            raise _abi.error_bits_to_exception(bits)
 
     def gather(self, rows, starts):
         """Buffer.sample's gather (buffers.py:112-124) for (row, start) pairs; device tensors in

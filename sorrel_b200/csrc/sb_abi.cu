@@ -13,9 +13,7 @@ namespace sb {
 static thread_local char g_cuda_err[256] = "";
 static std::atomic<uint64_t> g_launches{0};
 
-int note_cuda_error() {
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaPeekAtLastError();
+int note_cuda_error(cudaError_t e) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", cudaGetErrorString(e));
   return SB_ECUDA;
 }
@@ -190,10 +188,15 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     if (!kind_ok(w->spawn_choice_kinds[i])) return SB_EINVAL;
     d.choices_packed |= (uint64_t)w->spawn_choice_kinds[i] << (8 * i);
   }
+  int max_delta = 0;
   for (int i = 0; i < d.n_actions; ++i) {
     d.dy_packed |= (uint64_t)(uint8_t)w->action_dy[i] << (8 * i);
     d.dx_packed |= (uint64_t)(uint8_t)w->action_dx[i] << (8 * i);
+    max_delta = max(max_delta, max(abs((int)w->action_dy[i]), abs((int)w->action_dx[i])));
   }
+  // two agents farther apart than this cannot read or write a cell the other's move touches this turn: a move
+  // changes cells within max_delta of the agent, a window reaches v, two targets are at most 2*max_delta apart
+  d.par_radius = max(d.v + max_delta, 2 * max_delta);
   const bool ext = d.ext_rules || d.ext_act || d.obs_extra > 0 || d.obs_flag;  // only the generic / replay variants implement these
   d.simd_sweep = (d.single_spawn_kind >= 0 && d.hi8 + 1u <= 128u && !ext) ? 1 : 0;
   {
@@ -344,6 +347,11 @@ __global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__
   if (sample >= batch) return;
   const int64_t row = rows_idx[sample], s0 = starts[sample];
   const int F = b.n_frames;
+  // numpy raises IndexError for these (buffers.py:112-119); report instead of reading a neighbouring row
+  if (row < 0 || row >= b.rows || s0 < 0 || s0 + F >= b.capacity) {
+    if (lane == 0 && b.d_error) atomicOr(b.d_error, SB_ERR_BAD_INDEX);
+    return;
+  }
   const size_t n = (size_t)F * b.obs_size;
   const float* src = b.d_states + ((size_t)row * b.capacity + s0) * b.obs_size;
   float* ds = states + (size_t)sample * n;
@@ -544,19 +552,18 @@ int sb_reset_ex(const SbWorldDesc* w, uint8_t* d_grid, int32_t* d_agent_pos, dou
                                                                 d_spawnable, n_spawnable, d_placement, groups,
                                                                 seed, tick);
   count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  return check_launch();
 }
 
-int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t* d_agent_pos,
-            double* d_total_reward, const SbBufferDesc* buf, void* stream) {
-  SbDev d;
+// validation shared by sb_step and sb_step_plan (`plan_only`: the state pointers are not required)
+static int prepare_step(const SbWorldDesc* w, const SbStepArgs* a, const SbBufferDesc* buf, bool plan_only, SbDev* dout,
+                        StepParams* pout) {
+  SbDev& d = *dout;
   int rc = make_dev(w, &d);
   if (rc) return rc;
-  if (!a || !d_grid || !d_agent_pos || !d_total_reward) return SB_EINVAL;
-  if (!aligned16(d_grid)) return SB_EALIGN;
+  if (!a) return SB_EINVAL;
   if (a->num_turns < 1) return SB_EINVAL;
-  StepParams p;
+  StepParams& p = *pout;
   memset(&p, 0, sizeof(p));
   p.a = *a;
   if (a->mode == SB_MODE_SPLIT) {
@@ -564,17 +571,17 @@ int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t*
     if (a->act_agent >= d.A || a->obs_agent >= d.A) return SB_EINVAL;
     if (a->act_agent < 0) p.a.act_agent = -1;
     if (a->obs_agent < 0 && a->obs_agent != SB_OBS_ALL) p.a.obs_agent = -1;
-    if (a->act_agent >= 0 && a->policy == SB_POLICY_TAPE && !a->d_actions) return SB_EINVAL;
+    if (!plan_only && a->act_agent >= 0 && a->policy == SB_POLICY_TAPE && !a->d_actions) return SB_EINVAL;
   } else if (a->mode == SB_MODE_FUSED) {
-    if (a->policy == SB_POLICY_TAPE && !a->d_actions) return SB_EINVAL;
+    if (!plan_only && a->policy == SB_POLICY_TAPE && !a->d_actions) return SB_EINVAL;
   } else {
     return SB_EINVAL;
   }
   const bool sweeps = a->mode == SB_MODE_FUSED || a->do_sweep;
-  if (sweeps && a->rng == SB_RNG_TAPE && (!a->d_spawn_u || !a->d_spawn_c)) return SB_EINVAL;
+  if (!plan_only && sweeps && a->rng == SB_RNG_TAPE && (!a->d_spawn_u || !a->d_spawn_c)) return SB_EINVAL;
   if (a->rng != SB_RNG_TAPE && a->rng != SB_RNG_PHILOX && a->rng != SB_RNG_SPARSE) return SB_EINVAL;
   if (a->rng == SB_RNG_SPARSE && !d.sparse_ok) return SB_EINVAL;
-  if (w->uses_facing && !a->d_agent_facing) return SB_EINVAL;
+  if (!plan_only && w->uses_facing && !a->d_agent_facing) return SB_EINVAL;
   if (a->policy != SB_POLICY_TAPE && a->policy != SB_POLICY_UNIFORM) return SB_EINVAL;
   if (buf) {
     rc = check_buf(buf);
@@ -585,18 +592,38 @@ int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t*
     p.has_buf = 1;
   }
   p.write_back = 1;
+  return SB_OK;
+}
+
+int sb_step(const SbWorldDesc* w, const SbStepArgs* a, uint8_t* d_grid, int32_t* d_agent_pos,
+            double* d_total_reward, const SbBufferDesc* buf, void* stream) {
+  SbDev d;
+  StepParams p;
+  if (!d_grid || !d_agent_pos || !d_total_reward) return SB_EINVAL;
+  if (!aligned16(d_grid)) return SB_EALIGN;
+  const int rc = prepare_step(w, a, buf, false, &d, &p);
+  if (rc) return rc;
   p.grid = d_grid;
   p.agent_pos = d_agent_pos;
   p.total_reward = d_total_reward;
   return launch_step(d, p, (cudaStream_t)stream);
 }
 
+int sb_step_plan(const SbWorldDesc* w, const SbStepArgs* a, SbStepPlan* out) {
+  SbDev d;
+  StepParams p;
+  if (!out) return SB_EINVAL;
+  memset(out, 0, sizeof(*out));
+  const int rc = prepare_step(w, a, nullptr, true, &d, &p);
+  if (rc) return rc;
+  return launch_step(d, p, nullptr, out);
+}
+
 int sb_clock_advance(uint32_t* d_clock, uint32_t add_tick, uint32_t add_slot, uint32_t capacity, void* stream) {
   if (!d_clock || capacity == 0) return SB_EINVAL;
   clock_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_clock, add_tick, add_slot, capacity);
   count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  return check_launch();
 }
 
 int sb_observe(const SbWorldDesc* w, const uint8_t* d_grid, const int32_t* d_agent_pos, float* d_obs_out,
@@ -618,8 +645,7 @@ int sb_buffer_add(const SbBufferDesc* buf, int32_t slot, const float* d_obs, con
   buffer_add_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *buf, slot, d_obs, d_actions, d_rewards, d_dones, d_positions);
   count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  return check_launch();
 }
 
 int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts, int32_t batch,
@@ -630,13 +656,13 @@ int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64
   if (batch <= 0 || !d_rows || !d_starts || !d_states || !d_actions || !d_rewards || !d_next_states ||
       !d_dones || !d_valid)
     return SB_EINVAL;
+  if (buf->capacity < buf->n_frames + 1) return SB_EINVAL;  // a transition spans n_frames + 1 consecutive slots
   const long long threads = (long long)batch * 32;
   buffer_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *buf, d_rows, d_starts, batch, d_states, d_actions, d_rewards, d_next_states, d_dones, d_valid, nullptr,
       nullptr);
   count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  return check_launch();
 }
 
 int sb_buffer_sample_transformer(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts,
@@ -648,13 +674,13 @@ int sb_buffer_sample_transformer(const SbBufferDesc* buf, const int64_t* d_rows,
       !d_dones || !d_valid)
     return SB_EINVAL;
   if (buf->n_frames > 32) return SB_EUNSUPPORTED;
+  if (buf->capacity < buf->n_frames + 1) return SB_EINVAL;
   const long long threads = (long long)batch * 32;
   buffer_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       *buf, d_rows, d_starts, batch, d_states, nullptr, nullptr, d_next_states, d_dones, d_valid, d_action_seq,
       d_next_action_seq);
   count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  return check_launch();
 }
 
 int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, void* stream) {
@@ -666,8 +692,7 @@ int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, 
   buffer_current_state_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*buf, idx,
                                                                                                    d_out);
   count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  return check_launch();
 }
 
 size_t sb_stats_scratch_bytes(void) { return sizeof(StatsScratch); }
@@ -679,8 +704,7 @@ int sb_reward_stats(const double* d_total_reward, int64_t n, double* d_out, void
   reward_stats_kernel<<<blocks, STATS_THREADS, 0, (cudaStream_t)stream>>>(d_total_reward, n, d_out,
                                                                          (StatsScratch*)d_scratch);
   count_launch();
-  if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-  return SB_OK;
+  return check_launch();
 }
 
 }  // extern "C"

@@ -77,6 +77,7 @@ struct SbDev {
   int8_t beam_dy[4][SB_MAX_BEAM_CELLS], beam_dx[4][SB_MAX_BEAM_CELLS];
   uint32_t beam_block_mask;
   int32_t reward_all, reward_count;
+  int32_t par_radius;  // agents farther apart than this (Chebyshev) cannot interact within one turn: max(v + m, 2m)
 };
 
 // ------------------------------------------------------------------------------------------------

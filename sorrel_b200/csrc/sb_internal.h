@@ -40,12 +40,17 @@ struct StepParams {
   uint32_t rk[20];                                // Philox round keys of a.seed (constant-bank operands)
 };
 
-int note_cuda_error();  // records cudaGetLastError() text for sb_last_cuda_error, returns SB_ECUDA
+int note_cuda_error(cudaError_t e);  // records the error text for sb_last_cuda_error, returns SB_ECUDA
+// after a launch / runtime call: SB_OK, or SB_ECUDA with the (single) cudaGetLastError() result recorded
+inline int check_launch() {
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SB_OK : note_cuda_error(e);
+}
 void count_launch();
 
 int make_dev(const SbWorldDesc* desc, SbDev* out);  // validates + derives the device view
-int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s);
-int pick_lpe(const SbDev& d);
+// plan != nullptr: fill it and do not launch
+int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s, SbStepPlan* plan = nullptr);
 int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos, float* out, cudaStream_t s);
 
 }  // namespace sb

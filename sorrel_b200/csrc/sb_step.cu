@@ -46,24 +46,24 @@ struct SmemLayout {
 
 // planes above this size stay in global memory (a 128x128 plane is 16 KB: staging it would leave room for
 // ~12 instances, i.e. 12 warps, per SM)
-__host__ inline bool stage_planes(const SbDev& d) {
-  if (const char* e = getenv("SB_STAGED")) return atoi(e) != 0;
+__host__ inline bool stage_planes(const SbDev& d, int tune_staged) {
+  if (tune_staged) return tune_staged > 0;  // SbStepArgs.tune_staged
   return d.env_stride <= 4096;
 }
 
-__host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, bool np1) {
+__host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, bool np1, bool staged, bool sparse) {
   SmemLayout L;
   const int epb = threads / lpe;
   L.q_off = round_up(2 * d.SS, 16);
   L.planes_off = L.q_off + round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
-  L.plane_env = stage_planes(d) ? pad64mod128(d.env_stride) : 0;
+  L.plane_env = staged ? pad64mod128(d.env_stride) : 0;
   L.pos_off = L.planes_off + epb * L.plane_env;
   L.stage_off = L.pos_off + round_up(epb * 12 * d.A, 16);  // packed yx, action, facing per agent
   L.stage_row = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
   // warp-per-instance worlds with several agents observe up to SB_PAR independent agents at once
   L.stage_env = (np1 && lpe == 32 && d.A >= SB_PAR) ? SB_PAR * L.stage_row : L.stage_row;
   L.hits_off = L.stage_off + epb * L.stage_env;  // SB_RNG_SPARSE: accepted cells of the turn, u16[KMAX]
-  L.total = L.hits_off + epb * SB_SPARSE_KMAX * 2;
+  L.total = L.hits_off + (sparse ? epb * SB_SPARSE_KMAX * 2 : 0);  // only the sparse sampler keeps a hit list
   return L;
 }
 
@@ -298,9 +298,10 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
   const unsigned long long pairs = (unsigned long long)d.N * d.A;
   auto launch = [&](auto kern) -> int {
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return note_cuda_error();
+    if (smem > 48 * 1024) {
+      const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return note_cuda_error(e);
+    }
     // persistent grid of exactly ONE wave: (SMs) x (blocks that are resident together, from the occupancy
     // calculator: registers cap it at 6, not 8); each group takes a contiguous run of pairs.  A fixed 148 x 8
     // grid ran 1.33 waves, i.e. a second, one-third-full wave (ncu: launch__waves_per_multiprocessor).
@@ -315,7 +316,7 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
     if (ppg > 0xFFFFFFFFull) return SB_EUNSUPPORTED;
     kern<<<(unsigned)blocks, OBS_THREADS, smem, s>>>(d, grid, agent_pos, out, stage_bytes, d.fast_obs, (unsigned)ppg);
     count_launch();
-    return cudaGetLastError() == cudaSuccess ? SB_OK : note_cuda_error();
+    return check_launch();
   };
   if (lanes == 16) return np1 ? launch(observe_kernel<true, 16>) : launch(observe_kernel<false, 16>);
   return np1 ? launch(observe_kernel<true, 32>) : launch(observe_kernel<false, 32>);
@@ -722,10 +723,11 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
 
     if (fused && LPE == 32 && NP1 && p.par) {
       // Warp-per-instance worlds (large maps, many agents): SB_PAR consecutive agents whose positions are
-      // pairwise more than v + 1 apart (Chebyshev) cannot see or touch each other's moves this turn -- an
-      // agent's move changes cells within 1 of its position, a window reaches v -- so their observations and
-      // moves commute with the list order of environment.py:92 and are done AT ONCE, 8 lanes per agent.  Groups
-      // that fail the test (or the tail) take the sequential path.  Rewards are added in list order.
+      // pairwise more than par_radius = max(v + m, 2m) apart (Chebyshev; m = longest action delta, 1 for
+      // MovingAgent) cannot see or touch each other's moves this turn -- an agent's move changes cells within m of
+      // its position, a window reaches v, two targets are 2m apart at most -- so their observations and moves
+      // commute with the list order of environment.py:92 and are done AT ONCE, 8 lanes per agent.  Groups that
+      // fail the test (or the tail) take the sequential path.  Rewards are added in list order.
       constexpr int SL = 32 / SB_PAR;
       for (int a0 = 0; a0 < d.A; a0 += SB_PAR) {
         bool par = a0 + SB_PAR <= d.A;
@@ -739,7 +741,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
             }
             const uint32_t pi = spos[a0 + i], pj = spos[a0 + j];
             const int dy = (int)(pi >> 16) - (int)(pj >> 16), dx = (int)(pi & 0xFFFFu) - (int)(pj & 0xFFFFu);
-            conflict = max(abs(dy), abs(dx)) <= d.v + 1;
+            conflict = max(abs(dy), abs(dx)) <= d.par_radius;
           }
           par = !__any_sync(0xFFFFFFFFu, conflict);
         }
@@ -829,44 +831,51 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
 // launch
 // ----------------------------------------------------------------------------------------------
 template <int LPE, int RNG, bool NP1>
-static int launch_one(const SbDev& d, StepParams p, cudaStream_t s) {
-  const SmemLayout L = smem_layout(d, SB_THREADS, LPE, NP1);
+static int launch_one(const SbDev& d, StepParams p, cudaStream_t s, SbStepPlan* plan) {
+  const bool staged = stage_planes(d, p.a.tune_staged);
+  const SmemLayout L = smem_layout(d, SB_THREADS, LPE, NP1, staged, RNG == SB_K_SPARSE);
   sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
   p.q_off = L.q_off, p.planes_off = L.planes_off, p.pos_off = L.pos_off, p.stage_off = L.stage_off;
   p.plane_env = L.plane_env, p.stage_env = L.stage_env, p.hits_off = L.hits_off;
   p.stage_row = L.stage_row;
-  p.par = (NP1 && LPE == 32 && d.A >= SB_PAR && !d.ext_act && !d.obs_extra && !getenv("SB_NO_PAR")) ? 1 : 0;
-  p.staged = stage_planes(d) ? 1 : 0;
+  p.par = (NP1 && LPE == 32 && d.A >= SB_PAR && !d.ext_act && !d.obs_extra && !d.toroidal && p.a.tune_par >= 0) ? 1 : 0;
+  p.staged = staged ? 1 : 0;
   const int smem = L.total;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
+  if (!staged && LPE != 32) return SB_EUNSUPPORTED;  // planes used in place: one warp per instance
+  const int epb = SB_THREADS / LPE;
+  const long long blocks = ((long long)d.N + epb - 1) / epb;
+  if (plan) {
+    plan->lpe = LPE, plan->kernel_rng = RNG, plan->fast_onehot = NP1 ? 1 : 0, plan->staged = p.staged, plan->par = p.par;
+    plan->threads = SB_THREADS, plan->smem_bytes = smem, plan->blocks = blocks;
+    return SB_OK;
+  }
   auto go = [&](auto kern) -> int {
     if (smem > 48 * 1024) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-        return note_cuda_error();
+      const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return note_cuda_error(e);
     }
-    const int epb = SB_THREADS / LPE;
-    const long long blocks = ((long long)d.N + epb - 1) / epb;
     kern<<<(unsigned)blocks, SB_THREADS, smem, s>>>(d, p);
     count_launch();
-    if (cudaGetLastError() != cudaSuccess) return note_cuda_error();
-    return SB_OK;
+    return check_launch();
   };
-  if (p.staged) return go(step_kernel<LPE, RNG, NP1, true>);
-  if constexpr (LPE == 32) return go(step_kernel<LPE, RNG, NP1, false>);  // pick_lpe: unstaged => one warp per instance
+  if (staged) return go(step_kernel<LPE, RNG, NP1, true>);
+  if constexpr (LPE == 32) return go(step_kernel<LPE, RNG, NP1, false>);
   return SB_EUNSUPPORTED;
 }
 
 template <int LPE>
-static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t s) {
+static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan) {
   const bool np1 = d.fast_obs && d.n_planes == 1;
   switch (kr) {
     case SB_K_TAPE:  // replay: speed is irrelevant, but it shares the observation / agent code under test
-      return np1 ? launch_one<LPE, SB_K_TAPE, true>(d, p, s) : launch_one<LPE, SB_K_TAPE, false>(d, p, s);
+      return np1 ? launch_one<LPE, SB_K_TAPE, true>(d, p, s, plan) : launch_one<LPE, SB_K_TAPE, false>(d, p, s, plan);
     case SB_K_PHILOX_SIMD:
-      return np1 ? launch_one<LPE, SB_K_PHILOX_SIMD, true>(d, p, s) : launch_one<LPE, SB_K_PHILOX_SIMD, false>(d, p, s);
+      return np1 ? launch_one<LPE, SB_K_PHILOX_SIMD, true>(d, p, s, plan)
+                 : launch_one<LPE, SB_K_PHILOX_SIMD, false>(d, p, s, plan);
     case SB_K_SPARSE:
-      return np1 ? launch_one<LPE, SB_K_SPARSE, true>(d, p, s) : launch_one<LPE, SB_K_SPARSE, false>(d, p, s);
-    default: return launch_one<LPE, SB_K_PHILOX_GENERIC, false>(d, p, s);
+      return np1 ? launch_one<LPE, SB_K_SPARSE, true>(d, p, s, plan) : launch_one<LPE, SB_K_SPARSE, false>(d, p, s, plan);
+    default: return launch_one<LPE, SB_K_PHILOX_GENERIC, false>(d, p, s, plan);
   }
 }
 
@@ -874,22 +883,20 @@ static int launch_rng(const SbDev& d, const StepParams& p, int kr, cudaStream_t 
 #define SB_CAT(a, b) SB_CAT2(a, b)
 #ifdef SB_ONLY_LPE
 // translation unit of ONE group width: every step_kernel<SB_ONLY_LPE, ...> instantiation (make -j compiles the
-// four widths and the rest of the library in parallel)
-int SB_CAT(launch_rng_, SB_ONLY_LPE)(const SbDev& d, const StepParams& p, int kr, cudaStream_t s) {
-  return launch_rng<SB_ONLY_LPE>(d, p, kr, s);
+// widths and the rest of the library in parallel)
+int SB_CAT(launch_rng_, SB_ONLY_LPE)(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan) {
+  return launch_rng<SB_ONLY_LPE>(d, p, kr, s, plan);
 }
 #else
-int launch_rng_4(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
-int launch_rng_8(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
-int launch_rng_16(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
-int launch_rng_32(const SbDev& d, const StepParams& p, int kr, cudaStream_t s);
+int launch_rng_4(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
+int launch_rng_8(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
+int launch_rng_16(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
+int launch_rng_32(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
 
-int pick_lpe(const SbDev& d) {
-  if (!stage_planes(d)) return 32;  // planes used in place in global memory: one warp per instance
-  if (const char* e = getenv("SB_LPE")) {
-    int v = atoi(e);
-    if (v == 4 || v == 8 || v == 16 || v == 32) return v;
-  }
+// Lanes per instance.  `hint` = SbStepArgs.tune_lpe (0: choose).
+static int pick_lpe(const SbDev& d, int hint, bool staged, bool sparse) {
+  if (!staged) return 32;  // planes used in place in global memory: one warp per instance
+  if (hint) return hint;
   int lpe = 4;
   while (lpe < 32 && d.n_chunks / lpe > 8) lpe *= 2;
   if (d.A >= 4 && lpe < 8) lpe = 8;  // agent phases dominate: halve their latency (measured, profiles/README.md)
@@ -900,20 +907,24 @@ int pick_lpe(const SbDev& d) {
   // shared memory must fit, and should not cap the SM below 6 resident blocks (24 warps): big staging rows
   // (cleanup: 4.4 KB of f32 per instance) are better served by wider groups (measured: 16.9 -> 13.7 ms)
   const bool np1 = d.fast_obs && d.n_planes == 1;
-  while (lpe < 32 && smem_layout(d, SB_THREADS, lpe, np1).total > 227 * 1024 / 6) lpe *= 2;
+  while (lpe < 32 && smem_layout(d, SB_THREADS, lpe, np1, staged, sparse).total > 227 * 1024 / 6) lpe *= 2;
   return lpe;
 }
 
-int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s) {
+int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s, SbStepPlan* plan) {
   int kr;
   if (p.a.rng == SB_RNG_TAPE) kr = SB_K_TAPE;
   else if (p.a.rng == SB_RNG_SPARSE) kr = SB_K_SPARSE;
   else kr = d.simd_sweep ? SB_K_PHILOX_SIMD : SB_K_PHILOX_GENERIC;
-  switch (pick_lpe(d)) {
-    case 4: return launch_rng_4(d, p, kr, s);
-    case 8: return launch_rng_8(d, p, kr, s);
-    case 16: return launch_rng_16(d, p, kr, s);
-    default: return launch_rng_32(d, p, kr, s);
+  const int hint = p.a.tune_lpe;
+  if (hint != 0 && hint != 4 && hint != 8 && hint != 16 && hint != 32) return SB_EINVAL;
+  if (p.a.tune_staged < -1 || p.a.tune_staged > 1 || p.a.tune_par < -1 || p.a.tune_par > 0) return SB_EINVAL;
+  if (p.a.tune_staged < 0 && hint != 0 && hint != 32) return SB_EINVAL;
+  switch (pick_lpe(d, hint, stage_planes(d, p.a.tune_staged), kr == SB_K_SPARSE)) {
+    case 4: return launch_rng_4(d, p, kr, s, plan);
+    case 8: return launch_rng_8(d, p, kr, s, plan);
+    case 16: return launch_rng_16(d, p, kr, s, plan);
+    default: return launch_rng_32(d, p, kr, s, plan);
   }
 }
 

@@ -235,8 +235,14 @@ class Engine:
     """N instances of one `WorldSpec` on one CUDA device (one rank's shard)."""
 
     def __init__(self, spec: WorldSpec, num_envs: int, device: torch.device | str = "cuda",
-                 env_id_base: int = 0, seed: int = 0):
+                 env_id_base: int = 0, seed: int = 0, tuning: dict | None = None):
+        """`tuning` pins the launch variant (SbStepArgs.tune_*): {"lpe": 4|8|16|32, "staged": 1|-1, "par": -1};
+        anything left out is chosen by the library.  Tests use it to check a specific kernel variant."""
         self.lib = lib()  # raises if the CUDA library is missing
+        self.tuning = dict(tuning or {})
+        unknown = set(self.tuning) - {"lpe", "staged", "par"}
+        if unknown:
+            raise ValueError(f"unknown tuning keys {sorted(unknown)}")
         self.spec = spec
         self.N = int(num_envs)
         self.A = int(spec.num_agents)
@@ -405,6 +411,24 @@ class Engine:
         a.d_drew_out = chk(drew_out, (T, N, ES), torch.uint8, "drew_out")
         a.d_error = self.error.data_ptr()
         a.d_agent_facing = _ptr(self.agent_facing)
+        self.apply_tuning(a)
+
+    def apply_tuning(self, a: SbStepArgs) -> None:
+        a.tune_lpe = int(self.tuning.get("lpe", 0) or 0)
+        a.tune_staged = int(self.tuning.get("staged", 0) or 0)
+        a.tune_par = int(self.tuning.get("par", 0) or 0)
+
+    def step_plan(self, num_turns: int = 1, rng: str = "philox", replay: bool = False) -> dict:
+        """The launch `step(...)` would make (kernel variant, lanes per instance, shared memory, grid)."""
+        a = SbStepArgs()
+        a.mode, a.num_turns, a.seed = _abi.SB_MODE_FUSED, int(num_turns), self.seed
+        a.rng = _abi.SB_RNG_TAPE if replay else (_abi.SB_RNG_SPARSE if rng == "sparse" else _abi.SB_RNG_PHILOX)
+        a.policy = _abi.SB_POLICY_UNIFORM
+        a.act_agent = a.obs_agent = -1
+        self.apply_tuning(a)
+        plan = _abi.SbStepPlan()
+        check(self.lib.sb_step_plan(C.byref(self.desc), C.byref(a), C.byref(plan)), "sb_step_plan")
+        return plan.as_dict()
 
     def observe(self, out: torch.Tensor | None = None) -> torch.Tensor:
         """ObservationSpec.observe for every (instance, agent): float32 [N, A, C, S, S], or [N, A, obs_size] when

@@ -93,6 +93,7 @@ class Environment:
         self._reward_slot = torch.zeros((1, eng.N, A), dtype=torch.float32, device=eng.device)
         self._action_slot = torch.zeros((1, eng.N, A), dtype=torch.int32, device=eng.device)
         self._turn_open = False
+        self._graphs = {}  # (turns, rng) -> StepGraph, see enable_graphs()
 
     @property
     def engine(self):
@@ -123,12 +124,45 @@ class Environment:
             agent.transition(self.world)
         self.buffer.advance(1)
 
-    def take_turns(self, num_turns: int) -> None:
-        """`num_turns` x take_turn() in ONE launch (in-kernel policies only)."""
+    def take_turns(self, num_turns: int, rng: str = "philox") -> None:
+        """`num_turns` x take_turn() in ONE launch (in-kernel policies only).  `rng`: "philox" draws one random byte
+        per cell per turn like the reference's draw-per-cell loop; "sparse" samples the same spawn field sparsely.
+        Replays the CUDA graph captured by `enable_graphs(num_turns, ...)` when there is one."""
         if not self._fusable:
             raise RuntimeError("take_turns() needs in-kernel policies; use take_turn() with a host policy")
-        self.engine.step(num_turns, buffer=self.buffer)
+        graph = self._graphs.get((int(num_turns), rng))
+        if graph is not None:
+            graph.replay_step()
+        else:
+            self.engine.step(num_turns, buffer=self.buffer, rng=rng)
         self.turn += num_turns
+
+    def enable_graphs(self, num_turns: int, sample_batch: int = 0, rng: str = "philox") -> None:
+        """Capture `take_turns(num_turns, rng)` (+ a `sample_batch`-transition `sample_device`) as CUDA graphs with
+        the tick / ring slot kept on the device, so that launch-bound regimes (small batches, one shard of many)
+        spend no host time per step.  Call after at least one eager `take_turns` / `sample_device` of the same
+        shape (module loading is not capturable) and once the ring is full (its population is baked in)."""
+        from .graphs import StepGraph
+
+        self._graphs[(int(num_turns), rng)] = StepGraph(self.engine, self.buffer, int(num_turns), rng=rng,
+                                                        sample_batch=int(sample_batch))
+
+    def sample_device(self, batch_size: int, rng: str = "philox", generator=None):
+        """Buffer.sample for the learner with the index draw on the device (buffers.py:98-124): replays the captured
+        graph when `enable_graphs` was given this batch size, else `Buffer.sample_device`."""
+        for (turns, g_rng), graph in self._graphs.items():
+            if g_rng == rng and graph.B == int(batch_size):
+                return graph.replay_sample()
+        return self.buffer.sample_device(int(batch_size), generator)
+
+    def begin_epoch(self) -> torch.Tensor:
+        """What `run_experiment` does between two epochs (environment.py:128-133,191-199) without a host sync: reduce
+        the finished episode's `world.total_reward` over every instance of every rank (device tensor {sum, sum_sq,
+        min, max, count}; the ONE collective, 40 bytes per rank), `reset()`, `add_empty()`."""
+        stats = self.stats.all_reduce(self.engine.total_reward)
+        self.reset()
+        self.add_empty()
+        return stats
 
     # -- split-phase plumbing used by Agent.pov / Agent.act ----------------------------------------
     def _observe_slot(self, k: int) -> torch.Tensor:

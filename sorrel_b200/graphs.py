@@ -16,25 +16,47 @@ from . import _abi
 from ._abi import SbStepArgs, check
 
 
+class DeviceClock:
+    """{tick0, slot0} of the next step launch in device memory + the host's record of what it holds.  Graphs that
+    step the same engine / ring share one clock."""
+
+    def __init__(self, device):
+        self.tensor = torch.zeros(2, dtype=torch.int32, device=device)
+        self.held = [0, 0]
+
+
 class StepGraph:
-    def __init__(self, engine, buffer, turns: int, rng: str = "philox", sample_batch: int = 0):
-        """Capture one step of `turns` fused turns with the in-kernel policy, recording into `buffer`.
+    def __init__(self, engine, buffer, turns: int, rng: str = "philox", sample_batch: int = 0,
+                 actions: torch.Tensor | None = None, reward_out: torch.Tensor | None = None,
+                 clock: DeviceClock | None = None):
+        """Capture one step of `turns` fused turns recording into `buffer`: with the in-kernel policy, or -- when
+        `actions` (int32 [turns, N, A], a FIXED device tensor the caller refills before every replay) is given -- with
+        caller-supplied actions; `reward_out` (float32 [turns, N, A], fixed) receives the step's rewards.
 
         Every kernel involved must have been launched once before (CUDA loads modules lazily and that
         is not capturable): run one eager `engine.step(...)` / `buffer.gather(...)` first."""
         self.eng, self.buf, self.T, self.rng, self.B = engine, buffer, int(turns), rng, int(sample_batch)
+        self._keep = (actions, reward_out)
         dev = engine.device
-        self.clock = torch.zeros(2, dtype=torch.int32, device=dev)
-        self._dev = [0, 0]  # host mirror of the device clock {tick0, slot0}
+        self._clock = clock or DeviceClock(dev)
+        self.clock = self._clock.tensor
         self._args = SbStepArgs()
         a = self._args
         a.mode, a.num_turns, a.seed = _abi.SB_MODE_FUSED, self.T, engine.seed
         a.rng = _abi.SB_RNG_SPARSE if rng == "sparse" else _abi.SB_RNG_PHILOX
-        a.policy = _abi.SB_POLICY_UNIFORM
+        a.policy = _abi.SB_POLICY_UNIFORM if actions is None else _abi.SB_POLICY_TAPE
+        shape = (self.T, engine.N, engine.A)
+        for t, dtype, name in ((actions, torch.int32, "actions"), (reward_out, torch.float32, "reward_out")):
+            if t is not None and (tuple(t.shape) != shape or t.dtype != dtype or not t.is_contiguous()
+                                  or t.device != engine.grid.device):
+                raise ValueError(f"{name}: expected contiguous {dtype} {shape} on {engine.grid.device}")
+        a.d_actions = None if actions is None else actions.data_ptr()
+        a.d_reward_out = None if reward_out is None else reward_out.data_ptr()
         a.act_agent = a.obs_agent = -1
         a.d_error = engine.error.data_ptr()
         a.d_clock = self.clock.data_ptr()
         a.d_agent_facing = None if engine.agent_facing is None else engine.agent_facing.data_ptr()
+        engine.apply_tuning(a)
         self.sample = None
         if self.B:
             F, obs = buffer.n_frames, buffer.obs_size
@@ -79,13 +101,14 @@ class StepGraph:
     def _sync_clock(self):
         """Bring the device clock in line with the host bookkeeping (after reset / add_empty / eager steps)."""
         want = [(self.eng.tick + 1) & 0xFFFFFFFF, self.buf.idx]
-        if want != self._dev:
+        held = self._clock.held
+        if want != held:
             cap = self.buf.capacity
-            check(self.eng.lib.sb_clock_advance(self.clock.data_ptr(), (want[0] - self._dev[0]) & 0xFFFFFFFF,
-                                                (want[1] - self._dev[1]) % cap, cap,
+            check(self.eng.lib.sb_clock_advance(self.clock.data_ptr(), (want[0] - held[0]) & 0xFFFFFFFF,
+                                                (want[1] - held[1]) % cap, cap,
                                                 torch.cuda.current_stream(self.eng.device).cuda_stream),
                   "sb_clock_advance")
-            self._dev = want
+            self._clock.held = want
 
     def replay_step(self):
         """`turns` fused turns for every instance."""
@@ -93,7 +116,8 @@ class StepGraph:
         self.graph.replay()
         self.eng.tick += self.T
         self.buf.advance(self.T)
-        self._dev = [(self._dev[0] + self.T) & 0xFFFFFFFF, (self._dev[1] + self.T) % self.buf.capacity]
+        held = self._clock.held
+        self._clock.held = [(held[0] + self.T) & 0xFFFFFFFF, (held[1] + self.T) % self.buf.capacity]
 
     def replay_sample(self):
         """Draw `sample_batch` (row, start) pairs and gather them; returns the (reused) batch tensors."""

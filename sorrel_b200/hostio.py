@@ -2,9 +2,14 @@
 
 `HostStepPipeline.submit(host_actions)` is the end-to-end form of `Environment.take_turn` for a
 caller whose policy lives on the host: H2D copy of the step's actions, the fused step launch
-(observations stay in HBM, written straight into the replay ring), D2H copy of the step's rewards.
-The three stages run on three CUDA streams with `depth` buffers in flight, so the copies of step
-i+1 / i-1 overlap the kernel of step i.
+(observations stay in HBM, written straight into the replay ring -- they are the learner's input and
+never cross PCIe), D2H copy of the step's rewards.  The three stages run on three CUDA streams with
+`depth` buffers in flight, so the copies of step i+1 / i-1 overlap the kernel of step i.
+
+With `graphs=True` the compute stage of every slot ([step kernel, device clock advance, index draw,
+Buffer.sample gather]) is a captured CUDA graph over that slot's fixed device buffers: per step the
+host then issues two copies, one graph launch and a handful of event calls -- no per-step argument
+marshalling or allocation -- which is what keeps a 1 ms step (one shard of eight) from being host-bound.
 """
 from __future__ import annotations
 
@@ -12,12 +17,14 @@ import torch
 
 
 class HostStepPipeline:
-    def __init__(self, engine, buffer, turns: int, depth: int = 2, rng: str = "philox", timing: bool = False):
+    def __init__(self, engine, buffer, turns: int, depth: int = 2, rng: str = "philox", timing: bool = False,
+                 graphs: bool = False, sample_batch: int = 0):
         self.eng, self.buf, self.T, self.depth, self.rng = engine, buffer, int(turns), depth, rng
         self.timing, self.kernel_events = timing, []  # (start, end) CUDA events around every step launch
+        self.B = int(sample_batch)
         dev, N, A = engine.device, engine.N, engine.A
         shape = (self.T, N, A)
-        self.d_actions = [torch.empty(shape, dtype=torch.int32, device=dev) for _ in range(depth)]
+        self.d_actions = [torch.zeros(shape, dtype=torch.int32, device=dev) for _ in range(depth)]
         self.d_rewards = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(depth)]
         self.h_rewards = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.s_h2d, self.s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -26,10 +33,18 @@ class HostStepPipeline:
         self.i = 0
         self.h2d_bytes = self.d_actions[0].numel() * 4
         self.d2h_bytes = self.d_rewards[0].numel() * 4
+        self.sampled = None  # the last step's Buffer.sample batch (device tensors), when sample_batch > 0
+        self.graphs = None
+        if graphs:
+            from .graphs import DeviceClock, StepGraph
+
+            clock = DeviceClock(dev)
+            self.graphs = [StepGraph(engine, buffer, self.T, rng=rng, sample_batch=self.B, actions=self.d_actions[k],
+                                     reward_out=self.d_rewards[k], clock=clock) for k in range(depth)]
 
     def submit(self, h_actions: torch.Tensor) -> torch.Tensor:
         """Enqueue one step driven by `h_actions` (pinned int32 [T, N, A]).  Returns the pinned host
-        reward buffer this step will fill (valid after `wait(slot)` / `drain()`)."""
+        reward buffer this step will fill (valid after `drain()` or once `ev_d2h[slot]` has completed)."""
         k = self.i % self.depth
         cur = torch.cuda.current_stream(self.eng.device)
         if self.i >= self.depth:
@@ -43,7 +58,11 @@ class HostStepPipeline:
         if self.timing:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(cur)
-        self.eng.step(self.T, buffer=self.buf, actions=self.d_actions[k], reward_out=self.d_rewards[k], rng=self.rng)
+        if self.graphs is not None:
+            self.graphs[k].replay_step()
+        else:
+            self.eng.step(self.T, buffer=self.buf, actions=self.d_actions[k], reward_out=self.d_rewards[k],
+                          rng=self.rng)
         if self.timing:
             e1.record(cur)
             self.kernel_events.append((e0, e1))
@@ -52,6 +71,9 @@ class HostStepPipeline:
             self.s_d2h.wait_event(self.ev_compute[k])
             self.h_rewards[k].copy_(self.d_rewards[k], non_blocking=True)
             self.ev_d2h[k].record(self.s_d2h)
+        if self.B:  # the learner's batch of this step (device-resident), after the rewards are on their way
+            self.sampled = self.graphs[k].replay_sample() if self.graphs is not None else \
+                self.buf.sample_device(self.B)
         self.i += 1
         return self.h_rewards[k]
 

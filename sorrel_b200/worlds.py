@@ -31,6 +31,7 @@ class Gridworld:
         self.seed = int(seed)
         self.env_id_base = int(env_id_base)
         self.engine: Engine | None = None
+        self.tuning: dict | None = None  # optional launch tuning handed to the Engine (see Engine.__init__)
         self.spec: WorldSpec | None = None
         self._kinds: list[Entity] = []
         self.create_world()
@@ -299,7 +300,7 @@ class Gridworld:
         self.spec = self.build_spec(agent_proto, observation_spec, action_spec, num_agents, spawnable, item_groups,
                                     initial_flags)
         self.engine = Engine(self.spec, self.num_envs, device=self.device, env_id_base=self.env_id_base,
-                             seed=self.seed)
+                             seed=self.seed, tuning=self.tuning)
         return self.engine
 
     # ------------------------------------------------------------------------------------------

@@ -152,3 +152,65 @@ def test_item_group_struct_matches_header(built_lib):
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         assert int(subprocess.check_output([exe]).split()[0]) == ctypes.sizeof(built_lib.SbItemGroup)
+
+
+def test_step_plan_without_gpu(built_lib):
+    """sb_step_plan is pure host code: the launch variant per BASELINE shape, the tuning fields of ABI v5 (which
+    replaced the v4 environment variables) and their validation."""
+    from oracle import restatement as R
+
+    L, abi = built_lib.lib(), built_lib
+
+    def plan(spec, n, **tune):
+        d, keep, _ = _host_desc(spec)
+        d.num_envs = n
+        a = abi.SbStepArgs()
+        a.mode, a.num_turns, a.rng, a.policy = abi.SB_MODE_FUSED, 25, tune.pop("rng", abi.SB_RNG_PHILOX), abi.SB_POLICY_UNIFORM
+        a.act_agent = a.obs_agent = -1
+        a.tune_lpe, a.tune_staged, a.tune_par = tune.get("lpe", 0), tune.get("staged", 0), tune.get("par", 0)
+        out = abi.SbStepPlan()
+        return L.sb_step_plan(ctypes.byref(d), ctypes.byref(a), ctypes.byref(out)), out
+
+    th1 = R.treasurehunt_spec(21, 21, 1, 2, 0.005)
+    rc, p = plan(th1, 1 << 20)  # config 5: the headline variant
+    assert rc == abi.SB_OK and (p.lpe, p.kernel_rng, p.fast_onehot, p.staged) == (4, 1, 1, 1)
+    assert p.blocks == (1 << 20) // 32 and p.threads == 128 and 0 < p.smem_bytes <= 227 * 1024 // 8
+    rc, p = plan(th1, 4096)  # config 2: small batches widen the groups
+    assert rc == abi.SB_OK and p.lpe > 4
+    rc, p = plan(R.treasurehunt_spec(21, 21, 8, 2, 0.005), 16384)  # config 3
+    assert rc == abi.SB_OK and p.lpe == 8 and p.staged == 1
+    rc, p = plan(R.treasurehunt_spec(128, 128, 64, 4, 0.005), 2048)  # config 4: warp per instance, planes in place
+    assert rc == abi.SB_OK and (p.lpe, p.staged, p.par) == (32, 0, 1)
+    rc, p = plan(R.treasurehunt_spec(128, 128, 64, 4, 0.005), 2048, par=-1)
+    assert rc == abi.SB_OK and p.par == 0
+    rc, p = plan(th1, 64, lpe=4)  # what the tests and smoke() pin
+    assert rc == abi.SB_OK and p.lpe == 4
+    rc, p = plan(th1, 64, staged=-1)
+    assert rc == abi.SB_OK and (p.lpe, p.staged) == (32, 0)
+    rc, p = plan(th1, 1 << 20, rng=abi.SB_RNG_SPARSE)
+    assert rc == abi.SB_OK and p.kernel_rng == 3
+    assert plan(th1, 64, lpe=5)[0] == abi.SB_EINVAL
+    assert plan(th1, 64, lpe=8, staged=-1)[0] == abi.SB_EINVAL  # planes in place need one warp per instance
+    assert plan(th1, 64, staged=2)[0] == abi.SB_EINVAL
+    assert plan(R.treasurehunt_spec(128, 128, 64, 4, 0.005), 64, lpe=4, staged=1)[0] == abi.SB_EUNSUPPORTED  # smem
+
+
+def test_library_reads_no_environment_variables():
+    """ABI v5: kernel variants are chosen from SbStepArgs, never from the process environment."""
+    src = os.path.join(ROOT, "sorrel_b200", "csrc")
+    for f in os.listdir(src):
+        if f.endswith((".cu", ".cuh", ".h")):
+            assert "getenv" not in open(os.path.join(src, f)).read(), f
+
+
+def test_step_plan_struct_matches_header(built_lib):
+    import subprocess
+    import tempfile
+
+    src = '#include <stdio.h>\n#include "sorrel_b200.h"\nint main(){printf("%zu\\n",sizeof(SbStepPlan));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        assert int(subprocess.check_output([exe]).split()[0]) == ctypes.sizeof(built_lib.SbStepPlan)

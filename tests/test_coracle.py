@@ -93,6 +93,50 @@ def test_c_oracle_philox_equals_python(A, H, W, v, p, T, N):
             np.testing.assert_array_equal(ring["positions"][:, n * A + a], env.buffers[a].positions)
 
 
+@pytest.mark.parametrize("A,H,W,v,p,T,N", [(1, 21, 21, 2, 0.005, 40, 10), (8, 21, 21, 2, 0.005, 20, 6),
+                                           (2, 11, 14, 3, 0.03, 30, 7), (3, 40, 40, 4, 0.002, 10, 4),
+                                           (1, 21, 21, 2, 0.02, 30, 5)])
+def test_c_oracle_sparse_equals_python(A, H, W, v, p, T, N):
+    """SB_RNG_SPARSE in both restatements: Binomial count by inverse CDF + distinct uniform cells (same stream)."""
+    spec = R.treasurehunt_spec(H, W, A, v, p)
+    seed, base = 0xFEEDC0DE77, 9
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_SPARSE, seed=seed, env_id_base=base, threads=3)
+    co.reset()
+    co.step(T // 3)
+    co.step(T - T // 3)
+    ring = co.ring()
+    spawned = 0
+    for n in range(N):
+        env, _ = util.run_oracle_episode(spec, R.SparseDraws(seed), T, env_id=base + n)
+        np.testing.assert_array_equal(co.grid[n], env.grid)
+        assert co.total_reward[n] == env.total_reward
+        spawned += int(np.isin(env.grid[:, :, 1], spec.spawn_choices).sum())
+        for a in range(A):
+            np.testing.assert_array_equal(ring["states"][n * A + a], env.buffers[a].states)
+            np.testing.assert_array_equal(ring["rewards"][:, n * A + a], env.buffers[a].rewards)
+    assert spawned > 0
+
+
+def test_c_oracle_env_id_list_replays_a_sample():
+    """`env_ids`: instance n of a sampled oracle == instance env_ids[n] of the full batch (counter-based modes)."""
+    spec = R.treasurehunt_spec(21, 21, 2, 2, 0.01)
+    T, N, seed = 12, 40, 77
+    for mode in (coracle.RNG_PHILOX, coracle.RNG_SPARSE):
+        full = coracle.COracle(spec, N, capacity=T, rng=mode, seed=seed, env_id_base=100, threads=2)
+        ids = np.array([100, 107, 139, 121], dtype=np.uint64)
+        part = coracle.COracle(spec, len(ids), capacity=T, rng=mode, seed=seed, env_ids=ids)
+        for co in (full, part):
+            co.reset()
+            co.step(T)
+        sel = (ids - 100).astype(int)
+        np.testing.assert_array_equal(part.grid, full.grid[sel])
+        np.testing.assert_array_equal(part.total_reward, full.total_reward[sel])
+        fr, pr = full.ring(), part.ring()
+        rows = (sel[:, None] * 2 + np.arange(2)[None]).reshape(-1)
+        np.testing.assert_array_equal(pr["states"], fr["states"][rows])
+        np.testing.assert_array_equal(pr["positions"], fr["positions"][:, rows])
+
+
 def test_c_oracle_tapes_equal_python_tapes():
     spec = R.treasurehunt_spec(11, 13, 3, 2, 0.05)
     T, N = 20, 5

@@ -84,15 +84,14 @@ def test_cleanup_golden_replay(name, fused, cuda_device):
 
 
 @pytest.mark.parametrize("lpe", [None, 16, 8])
-def test_cleanup_philox_batch(lpe, cuda_device, monkeypatch):
+def test_cleanup_philox_batch(lpe, cuda_device):
     """Counter-based mode (in-kernel item / agent placement, Bernoulli draws, uniform policy): many instances
     against the oracle restatement on the same stream, including a second episode (facings persist)."""
-    if lpe:
-        monkeypatch.setenv("SB_LPE", str(lpe))
+    tuning = {"lpe": lpe} if lpe else {}
     spec = R.cleanup_spec(13, 17, 5, 3, initial_apples=6, apple_spawn_chance=0.03, pollution_spawn_chance=0.06,
                           beam_radius=2)
     N, T, seed, base = 40, 24, 99, 1000
-    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed, tuning=tuning)
     buf = _buffer(spec, N, 2 * T, cuda_device)
     oenvs = [R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=base + n, capacity=2 * T) for n in range(0, N, 9)]
     for ep in range(2):
@@ -246,15 +245,14 @@ def test_iowa_golden_replay(name, fused, cuda_device):
 
 
 @pytest.mark.parametrize("lpe", [None, 8])  # 8 lanes is what pick_lpe gives this world at large batch sizes
-def test_iowa_philox_batch(lpe, cuda_device, monkeypatch):
+def test_iowa_philox_batch(lpe, cuda_device):
     from oracle import coracle
 
-    if lpe:
-        monkeypatch.setenv("SB_LPE", str(lpe))
+    tuning = {"lpe": lpe} if lpe else {}
 
     spec = R.iowa_spec(20, 20, 2, 2, 0.03)
     N, T, seed, base = 300, 40, 5, 77
-    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed, tuning=tuning)
     buf = _buffer(spec, N, T, cuda_device)
     eng.reset()
     eng.step(T // 2, buffer=buf)
@@ -316,15 +314,14 @@ def test_tag_golden_replay(name, fused, cuda_device):
 
 
 @pytest.mark.parametrize("lpe", [None, 8, 4])
-def test_tag_philox_batch(lpe, cuda_device, monkeypatch):
+def test_tag_philox_batch(lpe, cuda_device):
     from oracle import coracle
 
-    if lpe:
-        monkeypatch.setenv("SB_LPE", str(lpe))
+    tuning = {"lpe": lpe} if lpe else {}
 
     spec = R.tag_spec(9, 10, 6, 3, 10, it_agent=2)
     N, T, seed, base = 200, 30, 13, 9
-    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed, tuning=tuning)
     buf = _buffer(spec, N, 2 * T, cuda_device)
     co = coracle.COracle(spec, N, capacity=2 * T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
     for ep in range(2):  # the second episode starts from the flags the first one left
@@ -362,12 +359,11 @@ def _fuzz_rule_cases(n=8, seed=77):
 
 
 @pytest.mark.parametrize("case", _fuzz_rule_cases(), ids=lambda c: f"{c[0]}{c[1]}-{c[2]}x{c[3]}a{c[4]}v{c[5]}")
-def test_fuzz_rule_sets_against_c_oracle(case, cuda_device, monkeypatch):
+def test_fuzz_rule_sets_against_c_oracle(case, cuda_device):
     from oracle import coracle
 
     kind, i, H, W, A, v, lpe, radius = case
-    if lpe:
-        monkeypatch.setenv("SB_LPE", str(lpe))
+    tuning = {"lpe": lpe} if lpe else {}
     if kind == "cleanup":
         spec = R.cleanup_spec(H, W, A, v, initial_apples=3, apple_spawn_chance=0.02, pollution_spawn_chance=0.05,
                               beam_radius=radius)
@@ -376,7 +372,7 @@ def test_fuzz_rule_sets_against_c_oracle(case, cuda_device, monkeypatch):
     else:
         spec = R.tag_spec(H, W, A, v, 10, it_agent=i % A)
     N, T, seed, base = 17, 18, 500 + i, 11 * i
-    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed, tuning=tuning)
     buf = _buffer(spec, N, T, cuda_device)
     co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
     eng.reset()
