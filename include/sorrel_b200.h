@@ -216,7 +216,8 @@ typedef struct SbItemGroup {
  * Batched replay ring: one reference `Buffer` (sorrel/buffers.py:11-44) per agent row,
  * rows = num_envs * num_agents, row r = env * A + agent.  `idx`/`size` are host scalars shared
  * by all rows (every agent adds exactly one experience per turn).
- *   states    float  [rows][capacity][obs_size]  (row-major per agent: frame stacks contiguous)
+ *   states    float  [rows][capacity][obs_size]  (row-major per agent: frame stacks contiguous; or any other
+ *                                                 (row, slot) stride pair, see states_row_stride below)
  *   actions   int64  [capacity][rows]
  *   rewards   float  [capacity][rows]
  *   dones     float  [capacity][rows]
@@ -236,6 +237,13 @@ typedef struct SbBufferDesc {
   /* ---- ABI v5 ---- */
   uint32_t* d_error;    /* optional device error word: the gathers OR SB_ERR_BAD_INDEX into it instead of reading
                            outside the ring */
+  /* Layout of `states`, in floats: element (row, slot, e) lives at row * states_row_stride + slot * states_slot_stride
+     + e.  Both 0 = agent-major, the default documented above ([rows][capacity][obs]: row stride capacity * obs_size,
+     slot stride obs_size; the F stacked frames of a transition are contiguous).  Slot-major ([capacity][rows][obs]: row
+     stride obs_size, slot stride rows * obs_size) makes the rows ONE TURN writes contiguous in HBM -- whole DRAM pages
+     instead of one 600-byte piece per 19 KB -- which is what multi-agent worlds want (profiles/README.md). */
+  int64_t states_row_stride;
+  int64_t states_slot_stride;
 } SbBufferDesc;
 
 /* sb_step modes */

@@ -126,6 +126,8 @@ class SbBufferDesc(C.Structure):
         ("d_positions", C.c_void_p),
         # ---- ABI v5 ----
         ("d_error", C.c_void_p),
+        ("states_row_stride", C.c_int64),
+        ("states_slot_stride", C.c_int64),
     ]
 
 

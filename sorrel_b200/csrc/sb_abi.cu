@@ -226,6 +226,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   for (int k = d.K; k < SB_MAX_KINDS; ++k) d.channel[k] = 255;
   for (int k = 0; k < 8; ++k) d.channel8 |= (uint64_t)d.channel[k] << (8 * k);
   d.fill_channel = d.channel[d.fill_kind];
+  d.rowwise_ok = d.K <= 7 ? 1 : 0;
+  d.channel8_oob = (d.channel8 & 0x00FFFFFFFFFFFFFFull) | ((uint64_t)(uint8_t)d.fill_channel << 56);
   d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536 && !ext) ? 1 : 0;
   if (d.sparse_ok) memcpy(d.cdf, w->spawn_cdf, sizeof(d.cdf));
   d.app = w->d_appearance;
@@ -320,7 +322,7 @@ __global__ void buffer_add_kernel(SbBufferDesc b, int slot, const float* __restr
   const int lane = threadIdx.x & 31;
   if (row >= b.rows) return;
   const float* src = obs + (size_t)row * b.obs_size;
-  float* dst = b.d_states + ((size_t)row * b.capacity + slot) * b.obs_size;
+  float* dst = b.d_states + (size_t)row * b.states_row_stride + (size_t)slot * b.states_slot_stride;
   for (int e = lane; e < b.obs_size; e += 32) dst[e] = src[e];
   if (lane == 0) {
     const size_t at = (size_t)slot * b.rows + row;
@@ -353,26 +355,53 @@ __global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__
     return;
   }
   const size_t n = (size_t)F * b.obs_size;
-  const float* src = b.d_states + ((size_t)row * b.capacity + s0) * b.obs_size;
+  const float* src = b.d_states + (size_t)row * b.states_row_stride + (size_t)s0 * b.states_slot_stride;
   float* ds = states + (size_t)sample * n;
   float* dn = next_states + (size_t)sample * n;
-  // 8-byte path when everything is 8-byte aligned (obs_size even), else scalar
-  if ((b.obs_size & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ds) |
-                                 reinterpret_cast<uintptr_t>(dn)) & 7u) == 0) {
-    const float2* s2 = reinterpret_cast<const float2*>(src);
-    float2* ds2 = reinterpret_cast<float2*>(ds);
-    float2* dn2 = reinterpret_cast<float2*>(dn);
-    const size_t n2 = n / 2, o2 = b.obs_size / 2;
-    for (size_t e = lane; e < n2 + o2; e += 32) {
-      float2 v = s2[e];
-      if (e < n2) ds2[e] = v;
-      if (e >= o2) dn2[e - o2] = v;
+  if (b.states_slot_stride == b.obs_size) {
+    // frames of a row are contiguous (agent-major ring): states / next_states are two overlapping linear copies of
+    // (F + 1) * obs floats.  8-byte path when everything is 8-byte aligned (obs_size even), else scalar
+    if ((b.obs_size & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ds) |
+                                   reinterpret_cast<uintptr_t>(dn)) & 7u) == 0) {
+      const float2* s2 = reinterpret_cast<const float2*>(src);
+      float2* ds2 = reinterpret_cast<float2*>(ds);
+      float2* dn2 = reinterpret_cast<float2*>(dn);
+      const size_t n2 = n / 2, o2 = b.obs_size / 2;
+      for (size_t e = lane; e < n2 + o2; e += 32) {
+        float2 v = s2[e];
+        if (e < n2) ds2[e] = v;
+        if (e >= o2) dn2[e - o2] = v;
+      }
+    } else {
+      for (size_t e = lane; e < n + b.obs_size; e += 32) {
+        float v = src[e];
+        if (e < n) ds[e] = v;
+        if (e >= (size_t)b.obs_size) dn[e - b.obs_size] = v;
+      }
     }
   } else {
-    for (size_t e = lane; e < n + b.obs_size; e += 32) {
-      float v = src[e];
-      if (e < n) ds[e] = v;
-      if (e >= (size_t)b.obs_size) dn[e - b.obs_size] = v;
+    // any other layout (slot-major ring): frame f of the transition is its own run of obs floats
+    const bool wide = (b.obs_size & 1) == 0 && (b.states_slot_stride & 1) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ds) |
+                        reinterpret_cast<uintptr_t>(dn)) & 7u) == 0;
+    for (int f = 0; f <= F; ++f) {
+      const float* sf = src + (size_t)f * b.states_slot_stride;
+      float* to_s = f < F ? ds + (size_t)f * b.obs_size : nullptr;
+      float* to_n = f > 0 ? dn + (size_t)(f - 1) * b.obs_size : nullptr;
+      if (wide) {
+        const float2* s2 = reinterpret_cast<const float2*>(sf);
+        for (int e = lane; e < b.obs_size / 2; e += 32) {
+          const float2 v = s2[e];
+          if (to_s) reinterpret_cast<float2*>(to_s)[e] = v;
+          if (to_n) reinterpret_cast<float2*>(to_n)[e] = v;
+        }
+      } else {
+        for (int e = lane; e < b.obs_size; e += 32) {
+          const float v = sf[e];
+          if (to_s) to_s[e] = v;
+          if (to_n) to_n[e] = v;
+        }
+      }
     }
   }
   if (action_seq && lane < F) {  // sample_transformer: actions[indices], actions[indices + 1] as f32
@@ -399,7 +428,7 @@ __global__ void buffer_current_state_kernel(SbBufferDesc b, int idx, float* __re
   for (int f = 0; f < F1; ++f) {
     int slot = idx - F1 + f;
     if (slot < 0) slot += b.capacity;
-    const float* src = b.d_states + ((size_t)row * b.capacity + slot) * b.obs_size;
+    const float* src = b.d_states + (size_t)row * b.states_row_stride + (size_t)slot * b.states_slot_stride;
     float* dst = out + ((size_t)row * F1 + f) * b.obs_size;
     for (int e = lane; e < b.obs_size; e += 32) dst[e] = src[e];
   }
@@ -471,10 +500,17 @@ __global__ void clock_advance_kernel(uint32_t* clock, uint32_t add_tick, uint32_
   clock[1] = (clock[1] + add_slot) % capacity;
 }
 
-static int check_buf(const SbBufferDesc* b) {
-  if (!b) return SB_EINVAL;
+// validates the ring description and returns it with the default (agent-major) strides filled in
+static int check_buf(const SbBufferDesc* in, SbBufferDesc* b) {
+  if (!in) return SB_EINVAL;
+  *b = *in;
   if (b->capacity <= 0 || b->obs_size <= 0 || b->n_frames <= 0 || b->rows <= 0) return SB_EINVAL;
   if (!b->d_states || !b->d_actions || !b->d_rewards || !b->d_dones) return SB_EINVAL;
+  if (b->states_row_stride == 0 && b->states_slot_stride == 0) {
+    b->states_row_stride = (int64_t)b->capacity * b->obs_size;
+    b->states_slot_stride = b->obs_size;
+  }
+  if (b->states_row_stride < b->obs_size || b->states_slot_stride < b->obs_size) return SB_EINVAL;
   return SB_OK;
 }
 
@@ -584,11 +620,10 @@ static int prepare_step(const SbWorldDesc* w, const SbStepArgs* a, const SbBuffe
   if (!plan_only && w->uses_facing && !a->d_agent_facing) return SB_EINVAL;
   if (a->policy != SB_POLICY_TAPE && a->policy != SB_POLICY_UNIFORM) return SB_EINVAL;
   if (buf) {
-    rc = check_buf(buf);
+    rc = check_buf(buf, &p.buf);
     if (rc) return rc;
     if (buf->obs_size != d.obs_size || buf->rows != (int64_t)d.N * d.A) return SB_EINVAL;
     if (!a->d_clock && (a->slot0 < 0 || a->slot0 >= buf->capacity)) return SB_EINVAL;
-    p.buf = *buf;
     p.has_buf = 1;
   }
   p.write_back = 1;
@@ -638,12 +673,13 @@ int sb_observe(const SbWorldDesc* w, const uint8_t* d_grid, const int32_t* d_age
 
 int sb_buffer_add(const SbBufferDesc* buf, int32_t slot, const float* d_obs, const int64_t* d_actions,
                   const float* d_rewards, const float* d_dones, const int64_t* d_positions, void* stream) {
-  int rc = check_buf(buf);
+  SbBufferDesc nb;
+  int rc = check_buf(buf, &nb);
   if (rc) return rc;
   if (slot < 0 || slot >= buf->capacity || !d_obs || !d_actions || !d_rewards || !d_dones) return SB_EINVAL;
   const long long threads = buf->rows * 32;
   buffer_add_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *buf, slot, d_obs, d_actions, d_rewards, d_dones, d_positions);
+      nb, slot, d_obs, d_actions, d_rewards, d_dones, d_positions);
   count_launch();
   return check_launch();
 }
@@ -651,7 +687,8 @@ int sb_buffer_add(const SbBufferDesc* buf, int32_t slot, const float* d_obs, con
 int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts, int32_t batch,
                      float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states,
                      float* d_dones, double* d_valid, void* stream) {
-  int rc = check_buf(buf);
+  SbBufferDesc nb;
+  int rc = check_buf(buf, &nb);
   if (rc) return rc;
   if (batch <= 0 || !d_rows || !d_starts || !d_states || !d_actions || !d_rewards || !d_next_states ||
       !d_dones || !d_valid)
@@ -659,7 +696,7 @@ int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64
   if (buf->capacity < buf->n_frames + 1) return SB_EINVAL;  // a transition spans n_frames + 1 consecutive slots
   const long long threads = (long long)batch * 32;
   buffer_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *buf, d_rows, d_starts, batch, d_states, d_actions, d_rewards, d_next_states, d_dones, d_valid, nullptr,
+      nb, d_rows, d_starts, batch, d_states, d_actions, d_rewards, d_next_states, d_dones, d_valid, nullptr,
       nullptr);
   count_launch();
   return check_launch();
@@ -668,7 +705,8 @@ int sb_buffer_sample(const SbBufferDesc* buf, const int64_t* d_rows, const int64
 int sb_buffer_sample_transformer(const SbBufferDesc* buf, const int64_t* d_rows, const int64_t* d_starts,
                                  int32_t batch, float* d_states, int64_t* d_action_seq, float* d_next_action_seq,
                                  float* d_next_states, float* d_dones, double* d_valid, void* stream) {
-  int rc = check_buf(buf);
+  SbBufferDesc nb;
+  int rc = check_buf(buf, &nb);
   if (rc) return rc;
   if (batch <= 0 || !d_rows || !d_starts || !d_states || !d_action_seq || !d_next_action_seq || !d_next_states ||
       !d_dones || !d_valid)
@@ -677,19 +715,20 @@ int sb_buffer_sample_transformer(const SbBufferDesc* buf, const int64_t* d_rows,
   if (buf->capacity < buf->n_frames + 1) return SB_EINVAL;
   const long long threads = (long long)batch * 32;
   buffer_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *buf, d_rows, d_starts, batch, d_states, nullptr, nullptr, d_next_states, d_dones, d_valid, d_action_seq,
+      nb, d_rows, d_starts, batch, d_states, nullptr, nullptr, d_next_states, d_dones, d_valid, d_action_seq,
       d_next_action_seq);
   count_launch();
   return check_launch();
 }
 
 int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, void* stream) {
-  int rc = check_buf(buf);
+  SbBufferDesc nb;
+  int rc = check_buf(buf, &nb);
   if (rc) return rc;
   if (idx < 0 || idx >= buf->capacity || !d_out) return SB_EINVAL;
   if (buf->n_frames < 2) return SB_OK;  // zero rows, like states[idx:idx]
   const long long threads = buf->rows * 32;
-  buffer_current_state_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*buf, idx,
+  buffer_current_state_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nb, idx,
                                                                                                    d_out);
   count_launch();
   return check_launch();

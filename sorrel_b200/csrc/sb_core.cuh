@@ -78,6 +78,10 @@ struct SbDev {
   uint32_t beam_block_mask;
   int32_t reward_all, reward_count;
   int32_t par_radius;  // agents farther apart than this (Chebyshev) cannot interact within one turn: max(v + m, 2m)
+  // row-wise window gather (narrow groups): channel8 with slot 7 := the fill kind's channel, so that an out-of-bounds
+  // window cell becomes a lookup of "kind 7" by a byte mask instead of a branch.  Valid when K <= 7 (slot 7 unused).
+  uint64_t channel8_oob;
+  int32_t rowwise_ok;
 };
 
 // ------------------------------------------------------------------------------------------------

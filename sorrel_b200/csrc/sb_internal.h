@@ -12,6 +12,9 @@
 #ifndef SB_PAR
 #define SB_PAR 4  // agents of one instance observed / moved at once by a warp (when independent)
 #endif
+#ifndef SB_ROWWISE_MAX_LPE
+#define SB_ROWWISE_MAX_LPE 8  // groups up to this width gather observation windows row by row (0: never)
+#endif
 #define SB_OBS_ALL (-2)  // SbStepArgs.obs_agent: observe every agent (sb_observe)
 
 // kernel RNG variants (template parameter)
@@ -37,6 +40,9 @@ struct StepParams {
   int32_t staged;                                 // planes staged in shared memory (else used in place)
   int32_t plane_env, stage_env;                   // per-instance strides of planes / staging rows
   int32_t stage_row, par;                         // one staging row; agent-parallel path enabled
+  int32_t agent_words;                            // 32-bit words of per-instance agent state (yx, facing, reward, actions)
+  int32_t act_turns;                              // turns whose actions are prepared at once (action window rows)
+  uint32_t inv_A;                                 // ceil(65536 / A)
   uint32_t rk[20];                                // Philox round keys of a.seed (constant-bank operands)
 };
 

@@ -42,7 +42,13 @@ __host__ __device__ inline int pad64mod128(int b) {
 // f32 otherwise (entries are sums over planes).
 struct SmemLayout {
   int q_off, planes_off, pos_off, stage_off, hits_off, plane_env, stage_env, stage_row, total;
+  int agent_words, act_turns;
 };
+
+// Turns whose actions are drawn (or loaded from the tape) at once, by different lanes of the group: with fewer agents
+// than lanes, lane l prepares the action of (turn t + l / A, agent l % A).  One agent on four lanes: one Philox call
+// per lane every four turns instead of one call by lane 0 (three lanes idle) every turn.
+__host__ __device__ inline int act_turns_ahead(int lpe, int A) { return A < lpe ? lpe / A : 1; }
 
 // planes above this size stay in global memory (a 128x128 plane is 16 KB: staging it would leave room for
 // ~12 instances, i.e. 12 warps, per SM)
@@ -58,7 +64,10 @@ __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, boo
   L.planes_off = L.q_off + round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
   L.plane_env = staged ? pad64mod128(d.env_stride) : 0;
   L.pos_off = L.planes_off + epb * L.plane_env;
-  L.stage_off = L.pos_off + round_up(epb * 12 * d.A, 16);  // packed yx, action, facing per agent
+  // per instance: packed yx [A], actions [act_turns x A], facing [A], reward of the turn [A]
+  L.act_turns = act_turns_ahead(lpe, d.A);
+  L.agent_words = 3 * d.A + L.act_turns * d.A;
+  L.stage_off = L.pos_off + round_up(epb * 4 * L.agent_words, 16);
   L.stage_row = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
   // warp-per-instance worlds with several agents observe up to SB_PAR independent agents at once
   L.stage_env = (np1 && lpe == 32 && d.A >= SB_PAR) ? SB_PAR * L.stage_row : L.stage_row;
@@ -68,9 +77,68 @@ __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, boo
 }
 
 __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float e) {
+#ifdef SB_EXP_NOSTORE  // timing experiment only (wrong results): the row is produced but never leaves the SM
+  if (a == 123.0f)
+#endif
   // streaming 128-bit store: observation rows are written once and not re-read by this kernel
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(e)
                : "memory");
+}
+
+// Row-wise form of the window scatter for NARROW groups (LANES <= 8) on a staged single plane.  A lane takes whole
+// window ROWS (i = lane, lane + LANES, ...) instead of single cells: the bytes of a row are fetched with two aligned
+// 32-bit shared loads per 5 cells and funnel-shifted into place, out-of-bounds cells are turned into "kind 7" -- whose
+// slot of channel8_oob holds the fill kind's channel -- by a byte mask, and four kinds are looked up by ONE byte
+// permute.  Per cell that leaves: extract the code, test it, one multiply-add for the address, one 16-bit store
+// (the cell-wise loop spends ~35 instructions per cell on index arithmetic, bounds tests and a byte load).
+// Requires K <= 7 (d.rowwise_ok).  `genv` must be shared memory: loads may touch up to 12 bytes before / after the
+// instance image (masked out), which always lie inside the block's allocation (queue before, agent area after).
+template <int LANES>
+__device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_t* genv, uint16_t* srow16, int y, int x,
+                                                    int lane) {
+  const int x0 = x - d.v;                                 // map column of window column 0 (may be negative)
+  const int jlo = max(0, -x0), jhi = min(d.S, d.W - x0);  // window columns [jlo, jhi) lie inside the map
+  const uint32_t tlo = (uint32_t)d.channel8_oob, thi = (uint32_t)(d.channel8_oob >> 32);
+  const int full = d.S - d.S % 5;  // columns covered by 5-cell groups; the rest is done cell by cell
+  for (int i = lane; i < d.S; i += LANES) {
+    const int yy = y - d.v + i;
+    const bool row_in = (unsigned)yy < (unsigned)d.H;
+    const int off = yy * d.W + x0;  // plane offset of window cell (i, 0); out-of-bounds bytes are masked below
+    uint16_t* const srow = srow16 + i * d.S;
+    for (int j0 = 0; j0 < full; j0 += 5) {
+      // byte mask of the in-bounds cells among j0 .. j0+3, and whether cell j0+4 is in bounds
+      const int lc = min(max(jlo - j0, 0), 4), hc = min(max(jhi - j0, 0), 4);
+      uint32_t m4 = __funnelshift_lc(~0u, 0u, 8 * hc) & ~__funnelshift_lc(~0u, 0u, 8 * lc);
+      bool in5 = jlo <= j0 + 4 && j0 + 4 < jhi;
+      uint32_t w0 = 0u, w1 = 0u;
+      if (row_in) {
+        const int al = (off + j0) & ~3;
+        w0 = *reinterpret_cast<const uint32_t*>(genv + al);
+        w1 = *reinterpret_cast<const uint32_t*>(genv + al + 4);
+      } else {
+        m4 = 0u;
+        in5 = false;
+      }
+      const uint32_t sh = ((uint32_t)(off + j0) & 3u) * 8u;
+      uint32_t k4 = __funnelshift_r(w0, w1, sh);                // kinds of cells j0 .. j0+3
+      const uint32_t k5 = in5 ? ((w1 >> sh) & 7u) : 7u;          // kind of cell j0+4
+      k4 = (k4 & m4) | (0x07070707u & ~m4);                     // out of bounds -> slot 7 (the fill channel)
+      const uint32_t t = k4 & 0x07070707u;
+      const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);  // nibbles k0, k1, k2, k3
+      const uint32_t c4 = __byte_perm(tlo, thi, sel);              // four channel codes
+      const uint32_t c5 = __byte_perm(tlo, thi, k5) & 0xFFu;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t code = (c4 >> (8 * u)) & 0xFFu;
+        if (code != 255u) srow[code * d.SS + j0 + u] = 0x3F80;  // bf16(1.0)
+      }
+      if (c5 != 255u) srow[c5 * d.SS + j0 + 4] = 0x3F80;
+    }
+    for (int j = full; j < d.S; ++j) {
+      const uint32_t code = sb_window_code(d, genv, y, x, i, j, 0);
+      if (code != 255u) srow[code * d.SS + j] = 0x3F80;
+    }
+  }
 }
 
 // One observation row through the one-hot fast path, by the LANES lanes that own the instance (all
@@ -81,7 +149,7 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
 // way.  `off` shifts the row inside the staging buffer so that the first 16-byte aligned global
 // address lines up with an aligned shared address (ring rows are only 8-byte aligned: 600 B, 1944 B).
 // `genv` may point to shared or global memory.
-template <int LANES, bool NP1, int NB = 1>
+template <int LANES, bool NP1, int NB = 1, bool ROWWISE = false>
 __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint16_t* lut_ij,
                                                 uint8_t* stage_raw, int y, int x, float* dst, int lane) {
   float* stage = reinterpret_cast<float*>(stage_raw);          // !NP1: f32 sums over planes
@@ -97,8 +165,10 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
 #define SB_SCATTER_UNROLL 2  // measured: 7.60 -> 7.55 ms at the default shape
 #endif
     constexpr int kScatterUnroll = (NB > 1) ? 1 : SB_SCATTER_UNROLL;
+    const bool rowwise = ROWWISE && d.rowwise_ok;
+    if (rowwise) scatter_rows_onehot<LANES>(d, genv, srow16, y, x, lane);
 #pragma unroll kScatterUnroll
-    for (int ij = lane; ij < d.SS; ij += LANES) {
+    for (int ij = rowwise ? d.SS : lane; ij < d.SS; ij += LANES) {
       const int i = (int)(((uint32_t)ij * inv_s) >> 16), j = ij - i * d.S;
       if (NP1 && NB > 1) {
         // planes in GLOBAL memory (standalone observation kernel, unstaged large maps): issue the NB window
@@ -324,11 +394,33 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
 
 #endif  // SB_ONLY_LPE
 
+// Resolve the queued spawn candidates of a warp, all 32 lanes at once: entry = group << 20 | cell.
+__device__ __forceinline__ void drain_queue(const SbDev& d, const uint32_t* q, uint32_t n, uint8_t* envs, int esz,
+                                            long long env0, uint32_t tick, const uint32_t* __restrict__ rk) {
+  for (uint32_t i = threadIdx.x & 31u; i < n; i += 32) {
+    const uint32_t entry = q[i];
+    const uint32_t g = entry >> 20, cell = entry & 0xFFFFFu;
+    const uint32_t eid = (uint32_t)(d.env_id_base + (uint64_t)(env0 + g));
+    const int kind = sb_resolve_candidate(d, eid, tick, cell, rk);
+    if (kind >= 0) envs[(size_t)g * esz + cell] = (uint8_t)kind;
+  }
+}
+
+// The same, out of line: called from inside the sweep loop only when the queue is about to overflow (dense
+// spawning), so that the two Philox bodies of the resolution exist ONCE in the hot instruction stream.
+static __device__ __noinline__ void drain_queue_cold(const SbDev* d, const uint32_t* q, uint32_t n, uint8_t* envs, int esz,
+                                              long long env0, uint32_t tick, const uint32_t* rk) {
+  drain_queue(*d, q, n, envs, esz, env0, tick, rk);
+}
+
 // LPE  lanes per instance; RNG  SB_K_* sweep variant; NP1  one stored plane + one-hot fast path;
 // STAGED  planes live in shared memory for the whole launch (compile-time, so that every access to the
 // instance image is an LDS / STS with 32-bit addressing instead of a generic load); false only with LPE == 32
+#ifndef SB_MIN_BLOCKS
+#define SB_MIN_BLOCKS 8  // resident blocks per SM the register allocation is sized for (64 registers)
+#endif
 template <int LPE, int RNG, bool NP1, bool STAGED>
-__global__ void __launch_bounds__(SB_THREADS, 8)
+__global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
     step_kernel(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int EPB = SB_THREADS / LPE;
@@ -346,7 +438,6 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   uint16_t* lut_ij = reinterpret_cast<uint16_t*>(smem_raw);  // [SS] (i << 8) | j of window cell ij
   uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + p.q_off);
   uint32_t* q = qbase + warp * (SB_QCAP + 1);  // spawn candidates of this warp's instances
-  uint32_t* qn = q + SB_QCAP;
   // planes: staged in shared memory for the whole launch, or (large maps, p.staged == 0) used in
   // place in global memory so that shared memory does not cap the number of resident warps
   const long long env0 = (long long)blockIdx.x * EPB;
@@ -355,9 +446,10 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   if constexpr (STAGED) envs = smem_raw + p.planes_off;
   else envs = p.grid + (size_t)env0 * d.env_stride;
   uint8_t* genv = envs + (STAGED ? grp * esz : (size_t)grp * esz);
-  uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * 3 * d.A;
-  int32_t* sact = reinterpret_cast<int32_t*>(spos + d.A);
-  int32_t* sfacing = sact + d.A;  // MovingAgent.direction (only read when d.ext_act)
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + p.pos_off) + grp * p.agent_words;
+  int32_t* sfacing = reinterpret_cast<int32_t*>(spos + d.A);  // MovingAgent.direction (only read when d.ext_act)
+  float* srew = reinterpret_cast<float*>(sfacing + d.A);      // reward of every agent's move this turn
+  int32_t* sact_win = reinterpret_cast<int32_t*>(srew + d.A);  // actions of the next act_turns turns: [turn][agent]
   uint8_t* stage_raw = smem_raw + p.stage_off + grp * p.stage_env;
 
   for (int ij = tid; ij < d.SS; ij += SB_THREADS) {
@@ -365,7 +457,6 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
     lut_ij[ij] = (uint16_t)((i << 8) | (ij - i * d.S));
   }
   for (int e = lane; e < p.stage_env / 4; e += LPE) reinterpret_cast<uint32_t*>(stage_raw)[e] = 0u;
-  if (wlane == 0) *qn = 0;
   __syncthreads();
 
   if (env0 + (long long)warp * GPW >= d.N) return;  // whole warp idle (only warp-level syncs below)
@@ -401,30 +492,47 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
   const size_t tape_stride = (size_t)d.env_stride;  // tape entries per instance per turn
   const bool fused = p.a.mode == SB_MODE_FUSED;
   const size_t row0 = (size_t)(active ? env : 0) * d.A;  // first ring row of this instance
-  float* const ring0 = p.has_buf ? p.buf.d_states + row0 * p.buf.capacity * d.obs_size : nullptr;
+  // observation rows go straight into the ring: element (row, slot) at row * row_stride + slot * slot_stride
+  float* const ring0 = p.has_buf ? p.buf.d_states + row0 * (size_t)p.buf.states_row_stride : nullptr;
+  auto ring_row = [&](int a, int slot_) -> float* {
+    return ring0 + (size_t)a * (size_t)p.buf.states_row_stride + (size_t)slot_ * (size_t)p.buf.states_slot_stride;
+  };
   // {tick0, slot0} from the launch arguments, or from device memory for graph-replayed launches
   const uint32_t tick0 = p.a.d_clock ? p.a.d_clock[0] : p.a.tick0;
   int slot = p.has_buf ? (p.a.d_clock ? (int)p.a.d_clock[1] : p.a.slot0) : 0;
 
+  int tw = 0;  // row of the action window this turn reads
   for (int t = 0; t < T; ++t, slot = (p.has_buf && slot + 1 < p.buf.capacity) ? slot + 1 : 0) {
     const uint32_t tick = tick0 + (uint32_t)t;
 
-    // ---- actions of this turn (parallel over agents; hides the tape-load latency) ------------
-    if (fused || p.a.act_agent >= 0) {
-      for (int a = lane; a < d.A; a += LPE) {
+    // ---- actions (parallel over (turn, agent) pairs; hides the tape-load latency) -------------------
+    // sact points at this turn's row of the action window; the window is refilled every act_turns turns
+    if (tw == p.act_turns) tw = 0;
+    int32_t* const sact = sact_win + tw * d.A;
+    if ((fused || p.a.act_agent >= 0) && tw == 0) {
+      for (int e = lane; e < p.act_turns * d.A; e += LPE) {
+        const int dt = p.act_turns > 1 ? (int)(((uint32_t)e * p.inv_A) >> 16) : 0;
+        const int a = e - dt * d.A;
         int act = 0;
-        if (p.a.policy == SB_POLICY_UNIFORM) {
-          SbU4 w = sb_philox_rk(envid, tick, (uint32_t)a, SB_DOM_ACTION, rk);
-          act = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
-        } else if (active && p.a.d_actions) {
-          act = p.a.d_actions[((size_t)t * d.N + env) * d.A + a];
+        if (t + dt < T) {
+          if (p.a.policy == SB_POLICY_UNIFORM) {
+            SbU4 w = sb_philox_rk(envid, tick + (uint32_t)dt, (uint32_t)a, SB_DOM_ACTION, rk);
+            act = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
+          } else if (active && p.a.d_actions) {
+            act = p.a.d_actions[((size_t)(t + dt) * d.N + env) * d.A + a];
+          }
         }
-        sact[a] = act;
+        sact_win[e] = act;
       }
     }
+    ++tw;
 
     // ---- entity sweep ----------------------------------------------------------------------
+#ifdef SB_EXP_NOSWEEP  // timing experiment only (wrong results): what the turn costs without the sweep
+    if (false) {
+#else
     if (fused || p.a.do_sweep) {
+#endif
       if (RNG == SB_K_TAPE) {
         // Replay, all rule types.  Planes in ascending layer order with a warp barrier in between: a column
         // rule then sees lower layers after and higher layers before their own transition of this turn,
@@ -467,53 +575,51 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           __syncwarp();
         }
       } else if (RNG == SB_K_PHILOX_SIMD) {
-        // First level, byte-SIMD: one Philox call covers the 16 cells of a chunk; cells whose
-        // random byte is <= hi8 AND that carry the spawn rule are rare (about 2 per instance-turn
-        // at p = 0.005), so they are pushed to a per-warp queue and resolved by all 32 lanes at
-        // once instead of diverging inside the chunk loop.
+        // First level, byte-SIMD: one Philox call covers the 16 cells of a chunk; cells whose random byte is below
+        // the filter bound AND that carry the spawn rule are rare (about 2 per instance-turn at p = 0.005), so they
+        // are appended to a per-warp queue -- positions from a ballot + popcount, the count lives in a (warp-
+        // uniform) register, no shared-memory atomics -- and resolved by all 32 lanes at once after the loop
+        // instead of diverging inside it.  Two chunks per trip: two independent Philox chains in flight, and one
+        // compaction round usually serves both (x4 / x8 no longer fit the instruction cache, profiles/README.md).
         const uint32_t spawn4 = (uint32_t)d.single_spawn_kind * 0x01010101u;
-        const int iters = (d.n_chunks + LPE - 1) / LPE;
-        // The loop stays rolled (one Philox body in the instruction cache); a lane that finds
-        // candidates only appends their cell ids to the warp queue.
-#ifndef SB_SWEEP_UNROLL
-#define SB_SWEEP_UNROLL 2  // measured: 7.71 -> 7.59 ms at the default shape; x8 overflowed the instruction cache
-#endif
-        constexpr int kSweepUnroll = SB_SWEEP_UNROLL;
-#pragma unroll kSweepUnroll
-        for (int it = 0; it < iters; ++it) {
-          const int c = it * LPE + lane;
-          uint32_t m = 0;
-          if (c < d.n_chunks && active) {
-            const uint4 k = genv4[c];
-            const SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
-            m = sb_simd_cand_chunk(k.x, k.y, k.z, k.w, r.x, r.y, r.z, r.w, spawn4, d.hmask4);
-          }
-          if (__ballot_sync(0xFFFFFFFFu, m != 0)) {
-            while (m) {
-              const int pos = __ffs(m) - 1;  // bit 8*b + w: byte b of word w of the chunk
-              m &= m - 1;
-              const uint32_t cell = (uint32_t)(c * 16 + 4 * (pos & 7) + (pos >> 3));
-              const uint32_t at = atomicAdd(qn, 1u);
-              if (at < SB_QCAP) {
-                q[at] = ((uint32_t)grp << 20) | cell;
-              } else {  // queue full (dense spawning): resolve in place
-                const int kind = sb_resolve_candidate(d, envid, tick, cell, rk);
-                if (kind >= 0) genv[cell] = (uint8_t)kind;
-              }
+        uint32_t qcount = 0;
+        for (int base = 0; base < d.n_chunks; base += 2 * LPE) {  // uniform trip count: ballots inside
+          const int c0 = base + lane, c1 = c0 + LPE;
+          uint32_t m0 = 0, m1 = 0;
+          if (active && c0 < d.n_chunks) {
+            const uint4 k = genv4[c0];
+            const SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c0, SB_DOM_SWEEP, rk);
+            m0 = sb_simd_cand_chunk(k.x, k.y, k.z, k.w, r.x, r.y, r.z, r.w, spawn4, d.hmask4);
+            if (c1 < d.n_chunks) {
+              const uint4 k1 = genv4[c1];
+              const SbU4 r1 = sb_philox_rk(envid, tick, (uint32_t)c1, SB_DOM_SWEEP, rk);
+              m1 = sb_simd_cand_chunk(k1.x, k1.y, k1.z, k1.w, r1.x, r1.y, r1.z, r1.w, spawn4, d.hmask4);
             }
           }
+          uint32_t b = __ballot_sync(0xFFFFFFFFu, (m0 | m1) != 0);
+          while (b) {  // one candidate per lane per round (a second round is needed in < 40 % of the trips)
+            if (qcount + 32u > (uint32_t)SB_QCAP) {  // dense spawning: make room (warp-uniform branch, cold)
+              __syncwarp();
+              drain_queue_cold(&d, q, qcount, envs, esz, env0, tick, rk);
+              __syncwarp();
+              qcount = 0;
+            }
+            if (m0 | m1) {
+              const bool first = m0 != 0;
+              const uint32_t m = first ? m0 : m1;
+              const int pos = __ffs(m) - 1;  // bit 8*b + w: byte b of word w of the chunk
+              if (first) m0 &= m0 - 1;
+              else m1 &= m1 - 1;
+              const uint32_t cell = (uint32_t)((first ? c0 : c1) * 16 + 4 * (pos & 7) + (pos >> 3));
+              q[qcount + __popc(b & ((1u << wlane) - 1u))] = ((uint32_t)grp << 20) | cell;
+            }
+            qcount += __popc(b);
+            b = __ballot_sync(0xFFFFFFFFu, (m0 | m1) != 0);
+          }
         }
         __syncwarp();
-        const uint32_t nq = min(*qn, (uint32_t)SB_QCAP);
-        for (uint32_t i = wlane; i < nq; i += 32) {
-          const uint32_t entry = q[i];
-          const uint32_t g = entry >> 20, cell = entry & 0xFFFFFu;
-          const uint32_t eid = (uint32_t)(d.env_id_base + (uint64_t)(env0 + g));
-          const int kind = sb_resolve_candidate(d, eid, tick, cell, rk);
-          if (kind >= 0) envs[(STAGED ? g * esz : (size_t)g * esz) + cell] = (uint8_t)kind;
-        }
+        drain_queue(d, q, qcount, envs, esz, env0, tick, rk);
         __syncwarp();
-        if (wlane == 0) *qn = 0;
       } else if (RNG == SB_K_SPARSE) {
         // Sparse sampling of the same Bernoulli field: K ~ Binomial(cells, p) by inverse CDF, then K
         // distinct uniform cells (sequential rejection over the draw stream j = 1, 2, ...).  The lanes of
@@ -602,7 +708,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       const uint32_t yx = spos[a];
       const int y = (int)(yx >> 16), x = (int)(yx & 0xFFFFu);
       float* dsts[2];
-      dsts[0] = (p.has_buf && active) ? ring0 + ((size_t)a * p.buf.capacity + slot) * d.obs_size : nullptr;
+      dsts[0] = (p.has_buf && active) ? ring_row(a, slot) : nullptr;
       dsts[1] = (p.a.d_obs_out && active)
                     ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size
                     : nullptr;
@@ -614,10 +720,12 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
         }
       } else if (NP1 || d.fast_obs) {
-        emit_onehot_row<LPE, NP1>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
+        // narrow groups on a staged plane gather the window row by row (scatter_rows_onehot)
+        constexpr bool RW = NP1 && STAGED && LPE <= SB_ROWWISE_MAX_LPE;
+        emit_onehot_row<LPE, NP1, 1, RW>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
         if (p.a.d_obs_out) {
           __syncwarp();
-          emit_onehot_row<LPE, NP1>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
+          emit_onehot_row<LPE, NP1, 1, RW>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
         }
       } else if (active) {
         for (int e = lane; e < d.oh_size; e += LPE) {
@@ -646,7 +754,33 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
       }
     };
 
-    // one agent's move by ONE lane: MovingAgent.act + Gridworld.move + the scalar part of Buffer.add
+    // The scalar part of Buffer.add (buffers.py:57-62) and the optional per-turn outputs for agents [a_lo, a_hi):
+    // one agent per LANE, after the agents of the turn have moved -- with A >= LPE every lane stores, where lane 0
+    // used to issue five stores per agent while the others waited (neighbouring rows are contiguous in the slot-major
+    // ring arrays, so the stores of a warp coalesce).
+    auto record_turn = [&](int a_lo, int a_hi) {
+      __syncwarp();
+      for (int a = a_lo + lane; a < a_hi && active; a += LPE) {
+        const uint32_t yx = spos[a];
+        const int action = sact[a];
+        const float reward = srew[a];
+        if (p.has_buf) {
+          const size_t at = (size_t)slot * rows + row0 + a;
+          p.buf.d_actions[at] = (int64_t)action;
+          p.buf.d_rewards[at] = reward;
+          p.buf.d_dones[at] = 0.0f;  // world.is_done is False for the whole episode
+          if (p.buf.d_positions)     // location AFTER the move (agent.py:131-134); 16-byte aligned pair
+            *reinterpret_cast<longlong2*>(p.buf.d_positions + 2 * at) =
+                make_longlong2((long long)(yx >> 16), (long long)(yx & 0xFFFFu));
+        }
+        const size_t o = ((size_t)t * d.N + env) * d.A + a;
+        if (p.a.d_reward_out) p.a.d_reward_out[o] = reward;
+        if (p.a.d_action_out) p.a.d_action_out[o] = action;
+      }
+      __syncwarp();  // the action window may be refilled right after
+    };
+
+    // one agent's move by ONE lane: MovingAgent.act + Gridworld.move
     auto move_and_record = [&](int a, int pre_tk, double* reward64 = nullptr) -> float {
       uint32_t yx = spos[a];
       const int action = sact[a];
@@ -665,20 +799,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         reward = sb_agent_act(d, genv, &yx, action, true, err, EXT && d.reward_all, pre_tk, reward64);
       }
       spos[a] = yx;
-      const size_t row = row0 + a;
-      if (p.has_buf) {
-        const size_t at = (size_t)slot * rows + row;
-        p.buf.d_actions[at] = (int64_t)action;
-        p.buf.d_rewards[at] = reward;
-        p.buf.d_dones[at] = 0.0f;  // world.is_done is False for the whole episode
-        if (p.buf.d_positions) {   // location AFTER the move (agent.py:131-134)
-          p.buf.d_positions[2 * at] = (int64_t)(yx >> 16);
-          p.buf.d_positions[2 * at + 1] = (int64_t)(yx & 0xFFFFu);
-        }
-      }
-      const size_t o = ((size_t)t * d.N + env) * d.A + a;
-      if (p.a.d_reward_out) p.a.d_reward_out[o] = reward;
-      if (p.a.d_action_out) p.a.d_action_out[o] = action;
+      srew[a] = reward;  // written to the ring (with the action and the new position) by record_turn below
       return reward;
     };
 
@@ -755,7 +876,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
             if (tc >= 0) pre_tk = genv[d.agent_plane * d.plane_stride + tc];
           }
           uint8_t* srow = stage_raw + sub * p.stage_row;
-          float* dst0 = (p.has_buf && active) ? ring0 + ((size_t)a * p.buf.capacity + slot) * d.obs_size : nullptr;
+          float* dst0 = (p.has_buf && active) ? ring_row(a, slot) : nullptr;
           emit_onehot_row<SL, NP1, 4>(d, genv, lut_ij, srow, y, x, dst0, sl);
           if (p.a.d_obs_out) {
             float* dst1 = active ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size : nullptr;
@@ -778,6 +899,7 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
           }
         }
       }
+      record_turn(0, d.A);
     } else if (fused) {
       for (int a = 0; a < d.A; ++a) {
         // planes in global memory: start the load of the cell agent a will step on NOW (its position, its
@@ -790,8 +912,12 @@ __global__ void __launch_bounds__(SB_THREADS, 8)
         observe(a);
         act(a, pre_tk);
       }
+      record_turn(0, d.A);
     } else {
-      if (p.a.act_agent >= 0) act(p.a.act_agent, -1);
+      if (p.a.act_agent >= 0) {
+        act(p.a.act_agent, -1);
+        record_turn(p.a.act_agent, p.a.act_agent + 1);
+      }
       if (p.a.obs_agent >= 0) {
         observe(p.a.obs_agent);
       } else if (p.a.obs_agent == SB_OBS_ALL) {
@@ -838,6 +964,9 @@ static int launch_one(const SbDev& d, StepParams p, cudaStream_t s, SbStepPlan* 
   p.q_off = L.q_off, p.planes_off = L.planes_off, p.pos_off = L.pos_off, p.stage_off = L.stage_off;
   p.plane_env = L.plane_env, p.stage_env = L.stage_env, p.hits_off = L.hits_off;
   p.stage_row = L.stage_row;
+  p.agent_words = L.agent_words;
+  p.act_turns = p.a.mode == SB_MODE_FUSED ? L.act_turns : 1;
+  p.inv_A = (65536u + (uint32_t)d.A - 1u) / (uint32_t)d.A;  // e / A == (e * inv_A) >> 16 for e < 32, A <= 64
   p.par = (NP1 && LPE == 32 && d.A >= SB_PAR && !d.ext_act && !d.obs_extra && !d.toroidal && p.a.tune_par >= 0) ? 1 : 0;
   p.staged = staged ? 1 : 0;
   const int smem = L.total;
@@ -888,6 +1017,7 @@ int SB_CAT(launch_rng_, SB_ONLY_LPE)(const SbDev& d, const StepParams& p, int kr
   return launch_rng<SB_ONLY_LPE>(d, p, kr, s, plan);
 }
 #else
+int launch_rng_2(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
 int launch_rng_4(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
 int launch_rng_8(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
 int launch_rng_16(const SbDev& d, const StepParams& p, int kr, cudaStream_t s, SbStepPlan* plan);
@@ -917,10 +1047,11 @@ int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s, SbStepPlan*
   else if (p.a.rng == SB_RNG_SPARSE) kr = SB_K_SPARSE;
   else kr = d.simd_sweep ? SB_K_PHILOX_SIMD : SB_K_PHILOX_GENERIC;
   const int hint = p.a.tune_lpe;
-  if (hint != 0 && hint != 4 && hint != 8 && hint != 16 && hint != 32) return SB_EINVAL;
+  if (hint != 0 && hint != 2 && hint != 4 && hint != 8 && hint != 16 && hint != 32) return SB_EINVAL;
   if (p.a.tune_staged < -1 || p.a.tune_staged > 1 || p.a.tune_par < -1 || p.a.tune_par > 0) return SB_EINVAL;
   if (p.a.tune_staged < 0 && hint != 0 && hint != 32) return SB_EINVAL;
   switch (pick_lpe(d, hint, stage_planes(d, p.a.tune_staged), kr == SB_K_SPARSE)) {
+    case 2: return launch_rng_2(d, p, kr, s, plan);
     case 4: return launch_rng_4(d, p, kr, s, plan);
     case 8: return launch_rng_8(d, p, kr, s, plan);
     case 16: return launch_rng_16(d, p, kr, s, plan);

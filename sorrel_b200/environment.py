@@ -84,8 +84,11 @@ class Environment:
         model = a0.model
         cap = int(getattr(model, "memory_size", 0) or self.config.get("engine", {}).get("buffer_capacity", 1024))
         n_frames = int(getattr(model, "n_frames", 1))
+        # ring layout: several agents per world -> the rows of one turn contiguous in HBM ("slot"); one agent ->
+        # frame stacks contiguous ("agent"); `config.engine.ring_layout` overrides (see buffers.Buffer)
+        layout = self.config.get("engine", {}).get("ring_layout", "slot" if A > 1 else "agent")
         self.buffer = Buffer(cap, (eng.spec.obs_size,), n_frames=n_frames, rows=eng.N * A, device=eng.device,
-                             positions=(2,))
+                             layout=layout, positions=(2,))
         for k, ag in enumerate(self.agents):
             ag.model.memory = AgentMemory(self.buffer, k, A)
         self.stats = RewardStats(eng.device)

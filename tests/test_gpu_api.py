@@ -420,3 +420,64 @@ def test_buffer_add_from_buffer(cuda_device):
     assert not dst.states[:, :8].any()
     with pytest.raises(AssertionError):
         dst.add_from_buffer(Buffer(4, (obs + 1,), rows=rows, device=cuda_device))
+
+
+def test_ring_layouts_agree_across_the_buffer_api(cuda_device):
+    """`Buffer(layout="slot")` (a turn's rows contiguous in HBM: what Environment picks for multi-agent worlds) and the
+    default agent-major layout are the same buffer to every caller: fused step writes, Buffer.add, current_state (with
+    ring wrap), sample / sample_transformer gathers on the same indices, add_from_buffer, save / load."""
+    import tempfile
+
+    from sorrel_b200.buffers import Buffer
+    from sorrel_b200.engine import Engine
+
+    spec = R.treasurehunt_spec(21, 21, 3, 2, 0.02)
+    N, cap, F, seed = 37, 12, 4, 99
+    bufs = {}
+    for layout in ("agent", "slot"):
+        eng = Engine(util.engine_spec(spec), N, device=cuda_device, seed=seed)
+        buf = Buffer(cap, (spec.obs_size,), n_frames=F, rows=N * 3, device=cuda_device, layout=layout, positions=(2,))
+        assert tuple(buf.states.shape) == (N * 3, cap, spec.obs_size)
+        eng.reset()
+        buf.add_empty()
+        eng.step(7, buffer=buf)
+        eng.step(9, buffer=buf)  # wraps the 12-deep ring
+        obs = eng.observe().reshape(N * 3, -1)
+        buf.add(obs, torch.arange(N * 3, device=cuda_device), torch.ones(N * 3, device=cuda_device), 0.0,
+                positions=torch.zeros((N * 3, 2), dtype=torch.int64, device=cuda_device))
+        eng.check_errors()
+        bufs[layout] = buf
+    a, s = bufs["agent"], bufs["slot"]
+    assert s.states.stride(1) == N * 3 * spec.obs_size and a.states.stride(1) == spec.obs_size
+    assert (a.idx, a.size) == (s.idx, s.size)
+    assert torch.equal(a.states, s.states) and torch.equal(a.actions, s.actions) and torch.equal(a.rewards, s.rewards)
+    # and both equal the oracle's ring (reset, add_empty, 16 turns; the extra add() above only touched slot 7)
+    o = R.OracleEnv(spec, R.PhiloxDraws(seed), env_id=5, capacity=cap, n_frames=F)
+    o.reset()
+    for b in o.buffers:
+        b.add_empty()
+    for _ in range(16):
+        o.take_turn()
+    keep = [i for i in range(cap) if i != 7]
+    for k in range(3):
+        np.testing.assert_array_equal(s.row(5 * 3 + k)["states"][keep], o.buffers[k].states[keep])
+    for idx in (2, 7):  # current_state with and without wrap
+        a.idx = s.idx = idx
+        assert torch.equal(a.current_state(), s.current_state())
+    rows = torch.randint(0, N * 3, (64,), device=cuda_device)
+    starts = torch.randint(0, cap - F - 1, (64,), device=cuda_device)
+    for x, y in zip(a.gather(rows, starts), s.gather(rows, starts)):
+        assert torch.equal(x, y)
+    for x, y in zip(a.gather_transformer(rows, starts), s.gather_transformer(rows, starts)):
+        assert torch.equal(x, y)
+    a.check_errors()
+    s.check_errors()
+    big = Buffer(3 * cap, (spec.obs_size,), n_frames=F, rows=N * 3, device=cuda_device, layout="slot", positions=(2,))
+    big.add_from_buffer(a)
+    assert torch.equal(big.states[:, : a.size], a.states[:, : a.size])
+    with tempfile.TemporaryDirectory() as d:
+        s.save(f"{d}/b.npz", row=4)
+        back = Buffer.load(f"{d}/b.npz", device=cuda_device)
+        assert torch.equal(back.states[0], a.states[4])
+    with pytest.raises(ValueError):
+        Buffer(4, (6,), rows=2, device=cuda_device, layout="diagonal")

@@ -29,11 +29,11 @@ def _engine(spec, n, device, **kw):
     return Engine(util.engine_spec(spec), n, device=device, **kw)
 
 
-def _buffer(spec, n, capacity, device, n_frames=1):
+def _buffer(spec, n, capacity, device, n_frames=1, layout="agent"):
     from sorrel_b200.buffers import Buffer
 
     return Buffer(capacity, (spec.obs_size,), n_frames=n_frames, rows=n * spec.num_agents, device=device,
-                  positions=(2,))
+                  layout=layout, positions=(2,))
 
 
 def _compare_all(eng, buf, co):
@@ -83,14 +83,16 @@ def test_config2_4096_envs_numpy_replay(cuda_device):
     _compare_all(eng, buf, co)
 
 
-def test_config3_16384_envs_8_agents(cuda_device):
+@pytest.mark.parametrize("layout", ["slot", "agent"])
+def test_config3_16384_envs_8_agents(layout, cuda_device):
     """BASELINE configs[2]: 16384 instances x 8 agents (movement conflicts, list-order priority), counter-based
-    stream, 25 + 15 turns into a 16-deep ring (wraps), the tiling the library picks at this size."""
+    stream, 25 + 15 turns into a 16-deep ring (wraps), the tiling the library picks at this size; with the ring layout
+    `Environment` picks for multi-agent worlds (slot-major) and with the agent-major one."""
     spec = R.treasurehunt_spec(21, 21, 8, 2, 0.005)
     N, cap, seed, base = 16384, 16, 0xC3C3C3, 1 << 20
     eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
     assert eng.step_plan(25)["lanes_per_instance"] == 8
-    buf = _buffer(spec, N, cap, cuda_device, n_frames=5)
+    buf = _buffer(spec, N, cap, cuda_device, n_frames=5, layout=layout)
     co = coracle.COracle(spec, N, capacity=cap, n_frames=5, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base,
                          threads=coracle.max_threads())
     eng.reset()
@@ -173,7 +175,7 @@ def test_config4_large_map_64_agents(cuda_device):
     eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
     plan = eng.step_plan(6)
     assert plan["lanes_per_instance"] == 32
-    buf = _buffer(spec, N, cap, cuda_device)
+    buf = _buffer(spec, N, cap, cuda_device, layout="slot")
     co = coracle.COracle(spec, N, capacity=cap, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base,
                          threads=coracle.max_threads())
     eng.reset()

@@ -185,7 +185,8 @@ def test_golden_ring(name, cuda_device):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("A,H,v,p,T,N,lpe", [(1, 21, 2, 0.005, 100, 96, None), (8, 21, 2, 0.005, 40, 40, None),
                                              (3, 9, 3, 0.15, 30, 33, None), (1, 21, 2, 0.005, 60, 31, 4),
-                                             (8, 21, 2, 0.005, 25, 18, 8), (2, 21, 2, 0.01, 25, 12, 16)])
+                                             (8, 21, 2, 0.005, 25, 18, 8), (2, 21, 2, 0.01, 25, 12, 16),
+                                             (1, 21, 2, 0.005, 40, 35, 2)])
 def test_batched_replay(A, H, v, p, T, N, lpe, cuda_device):
     tuning = {"lpe": lpe} if lpe else {}
     spec = R.treasurehunt_spec(H, H, A, v, p)
@@ -222,7 +223,8 @@ def test_batched_replay(A, H, v, p, T, N, lpe, cuda_device):
     # the group widths large batches run with (small test batches are widened to 32 lanes by pick_lpe):
     (1, 21, 21, 2, 0.005, 50, 41, 4),   # the headline variant step_kernel<4, SIMD, NP1, STAGED>
     (8, 21, 21, 2, 0.01, 20, 19, 4), (8, 21, 21, 2, 0.01, 20, 19, 8), (2, 30, 30, 3, 0.01, 12, 9, 16),
-    (3, 11, 14, 3, 0.3, 15, 13, 4)])    # generic sweep (p too large for the byte filter) at 4 lanes
+    (3, 11, 14, 3, 0.3, 15, 13, 4),     # generic sweep (p too large for the byte filter) at 4 lanes
+    (1, 21, 21, 2, 0.005, 50, 70, 2), (3, 17, 19, 3, 0.02, 20, 37, 2)])  # two lanes per instance
 def test_philox_mode(A, H, W, v, p, T, N, lpe, cuda_device):
     tuning = {"lpe": lpe} if lpe else {}
     seed, base = 0x1234ABCD5678, 5
@@ -244,7 +246,7 @@ def test_philox_mode(A, H, W, v, p, T, N, lpe, cuda_device):
 @pytest.mark.parametrize("A,H,W,v,p,T,N,lpe", [
     (1, 21, 21, 2, 0.005, 60, 70, None), (8, 21, 21, 2, 0.005, 25, 37, None), (2, 11, 14, 3, 0.03, 30, 19, None),
     (1, 21, 21, 2, 0.005, 30, 20, 8), (1, 21, 21, 2, 0.02, 30, 12, 32), (3, 40, 40, 4, 0.002, 10, 6, None),
-    (1, 21, 21, 2, 0.005, 40, 33, 4), (2, 30, 30, 3, 0.004, 12, 9, 16)])
+    (1, 21, 21, 2, 0.005, 40, 33, 4), (2, 30, 30, 3, 0.004, 12, 9, 16), (1, 21, 21, 2, 0.005, 40, 67, 2)])
 def test_sparse_mode(A, H, W, v, p, T, N, lpe, cuda_device):
     """SB_RNG_SPARSE (Binomial count + distinct uniform cells): kernels == oracle with the same stream."""
     tuning = {"lpe": lpe} if lpe else {}
