@@ -277,7 +277,8 @@ typedef struct SbStepArgs {
   int32_t* d_agent_facing;   /* [N][A] MovingAgent.direction, read and written; required iff desc.uses_facing */
   /* ---- ABI v5: launch tuning, 0 = the library chooses (tests pin the variant they check; sb_step_plan reports it).
      These replace the SB_LPE / SB_STAGED / SB_NO_PAR environment variables v4 read at every launch. ---- */
-  int32_t tune_lpe;    /* lanes that own one instance: 0 auto, or 2 / 4 / 8 / 16 / 32 */
+  int32_t tune_lpe;    /* lanes that own one instance: 0 auto, or 2 / 4 / 8 / 16 / 32, or 128 = one block per instance
+                          (16..64 agents, one-hot rows, byte-SIMD sweep; SB_EUNSUPPORTED where it does not apply) */
   int32_t tune_staged; /* instance planes staged in shared memory for the launch: 0 auto, 1 staged, -1 used in place
                           in global memory (one warp per instance: tune_lpe must be 0 or 32) */
   int32_t tune_par;    /* agent-parallel path of warp-per-instance worlds: 0 auto, -1 off */
@@ -336,7 +337,8 @@ int sb_reset_ex(const SbWorldDesc* desc, uint8_t* d_grid, int32_t* d_agent_pos, 
 int sb_step(const SbWorldDesc* desc, const SbStepArgs* args, uint8_t* d_grid, int32_t* d_agent_pos,
             double* d_total_reward, const SbBufferDesc* buf, void* stream);
 
-/* The launch sb_step(desc, args, ...) would make (variant, tiling, shared memory, grid); no device work. */
+/* The launch sb_step(desc, args, ..., buf != NULL, ...) would make (variant, tiling, shared memory, grid); no device
+ * work.  lpe 128 = the block-per-instance kernel of large many-agent worlds. */
 int sb_step_plan(const SbWorldDesc* desc, const SbStepArgs* args, SbStepPlan* out);
 
 /* Advance a device-resident {tick, slot} pair (see SbStepArgs.d_clock): tick += add_tick,

@@ -336,6 +336,28 @@ __global__ void buffer_add_kernel(SbBufferDesc b, int slot, const float* __restr
   }
 }
 
+// dst_a[e] = src[e] for e < hi_a and dst_b[e - lo_b] = src[e] for e >= lo_b, e in [0, total): one pass over the source
+// run feeding two (overlapping) destinations.  Four loads per lane are issued before their stores, so a warp keeps
+// ~2 KB in flight (the plain load-store loop left the gather latency-bound at ~3.6 TB/s).
+template <typename V>
+__device__ __forceinline__ void copy_run2(const V* __restrict__ src, V* __restrict__ dst_a, V* __restrict__ dst_b,
+                                          int hi_a, int lo_b, int total, int lane) {
+  for (int e0 = lane; e0 < total; e0 += 128) {
+    V v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e0 + 32 * u < total) v[u] = __ldg(src + e0 + 32 * u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + 32 * u;
+      if (e < total) {
+        if (e < hi_a) dst_a[e] = v[u];
+        if (e >= lo_b) dst_b[e - lo_b] = v[u];
+      }
+    }
+  }
+}
+
 __global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__ rows_idx,
                                      const int64_t* __restrict__ starts, int batch, float* __restrict__ states,
                                      int64_t* __restrict__ actions, float* __restrict__ rewards,
@@ -358,50 +380,33 @@ __global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__
   const float* src = b.d_states + (size_t)row * b.states_row_stride + (size_t)s0 * b.states_slot_stride;
   float* ds = states + (size_t)sample * n;
   float* dn = next_states + (size_t)sample * n;
+  // 8-byte accesses when everything is 8-byte aligned (obs_size and the strides even), else scalar
+  const bool wide = (b.obs_size & 1) == 0 && (b.states_slot_stride & 1) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ds) |
+                      reinterpret_cast<uintptr_t>(dn)) & 7u) == 0;
   if (b.states_slot_stride == b.obs_size) {
     // frames of a row are contiguous (agent-major ring): states / next_states are two overlapping linear copies of
-    // (F + 1) * obs floats.  8-byte path when everything is 8-byte aligned (obs_size even), else scalar
-    if ((b.obs_size & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ds) |
-                                   reinterpret_cast<uintptr_t>(dn)) & 7u) == 0) {
-      const float2* s2 = reinterpret_cast<const float2*>(src);
-      float2* ds2 = reinterpret_cast<float2*>(ds);
-      float2* dn2 = reinterpret_cast<float2*>(dn);
-      const size_t n2 = n / 2, o2 = b.obs_size / 2;
-      for (size_t e = lane; e < n2 + o2; e += 32) {
-        float2 v = s2[e];
-        if (e < n2) ds2[e] = v;
-        if (e >= o2) dn2[e - o2] = v;
-      }
-    } else {
-      for (size_t e = lane; e < n + b.obs_size; e += 32) {
-        float v = src[e];
-        if (e < n) ds[e] = v;
-        if (e >= (size_t)b.obs_size) dn[e - b.obs_size] = v;
-      }
-    }
+    // (F + 1) * obs floats
+    if (wide)
+      copy_run2(reinterpret_cast<const float2*>(src), reinterpret_cast<float2*>(ds), reinterpret_cast<float2*>(dn),
+                (int)(n / 2), b.obs_size / 2, (int)(n / 2) + b.obs_size / 2, lane);
+    else
+      copy_run2(src, ds, dn, (int)n, b.obs_size, (int)n + b.obs_size, lane);
   } else {
-    // any other layout (slot-major ring): frame f of the transition is its own run of obs floats
-    const bool wide = (b.obs_size & 1) == 0 && (b.states_slot_stride & 1) == 0 &&
-                      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ds) |
-                        reinterpret_cast<uintptr_t>(dn)) & 7u) == 0;
+    // any other layout (slot-major ring): frame f of the transition is its own run of obs floats; frame f goes to
+    // states[f] (f < F) and next_states[f - 1] (f > 0)
     for (int f = 0; f <= F; ++f) {
       const float* sf = src + (size_t)f * b.states_slot_stride;
-      float* to_s = f < F ? ds + (size_t)f * b.obs_size : nullptr;
-      float* to_n = f > 0 ? dn + (size_t)(f - 1) * b.obs_size : nullptr;
-      if (wide) {
-        const float2* s2 = reinterpret_cast<const float2*>(sf);
-        for (int e = lane; e < b.obs_size / 2; e += 32) {
-          const float2 v = s2[e];
-          if (to_s) reinterpret_cast<float2*>(to_s)[e] = v;
-          if (to_n) reinterpret_cast<float2*>(to_n)[e] = v;
-        }
-      } else {
-        for (int e = lane; e < b.obs_size; e += 32) {
-          const float v = sf[e];
-          if (to_s) to_s[e] = v;
-          if (to_n) to_n[e] = v;
-        }
-      }
+      float* to_s = ds + (size_t)f * b.obs_size;
+      float* to_n = dn + (size_t)f * b.obs_size - b.obs_size;
+      // copy_run2 writes to_s[e] for e < hi_s and to_n'[e - o] for e >= o: one frame, both or one destination
+      const int len = wide ? b.obs_size / 2 : b.obs_size;
+      const int hi_s = f < F ? len : 0, lo_n = f > 0 ? 0 : len;
+      if (wide)
+        copy_run2(reinterpret_cast<const float2*>(sf), reinterpret_cast<float2*>(to_s),
+                  reinterpret_cast<float2*>(to_n), hi_s, lo_n, len, lane);
+      else
+        copy_run2(sf, to_s, to_n, hi_s, lo_n, len, lane);
     }
   }
   if (action_seq && lane < F) {  // sample_transformer: actions[indices], actions[indices + 1] as f32
@@ -651,6 +656,7 @@ int sb_step_plan(const SbWorldDesc* w, const SbStepArgs* a, SbStepPlan* out) {
   memset(out, 0, sizeof(*out));
   const int rc = prepare_step(w, a, nullptr, true, &d, &p);
   if (rc) return rc;
+  p.has_buf = 1;  // the plan is for the usual launch: a replay ring attached, no second observation output
   return launch_step(d, p, nullptr, out);
 }
 

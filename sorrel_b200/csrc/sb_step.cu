@@ -99,13 +99,12 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
   const int x0 = x - d.v;                                 // map column of window column 0 (may be negative)
   const int jlo = max(0, -x0), jhi = min(d.S, d.W - x0);  // window columns [jlo, jhi) lie inside the map
   const uint32_t tlo = (uint32_t)d.channel8_oob, thi = (uint32_t)(d.channel8_oob >> 32);
-  const int full = d.S - d.S % 5;  // columns covered by 5-cell groups; the rest is done cell by cell
   for (int i = lane; i < d.S; i += LANES) {
     const int yy = y - d.v + i;
     const bool row_in = (unsigned)yy < (unsigned)d.H;
     const int off = yy * d.W + x0;  // plane offset of window cell (i, 0); out-of-bounds bytes are masked below
     uint16_t* const srow = srow16 + i * d.S;
-    for (int j0 = 0; j0 < full; j0 += 5) {
+    for (int j0 = 0; j0 < d.S; j0 += 5) {  // 5 cells per pair of aligned words
       // byte mask of the in-bounds cells among j0 .. j0+3, and whether cell j0+4 is in bounds
       const int lc = min(max(jlo - j0, 0), 4), hc = min(max(jhi - j0, 0), 4);
       uint32_t m4 = __funnelshift_lc(~0u, 0u, 8 * hc) & ~__funnelshift_lc(~0u, 0u, 8 * lc);
@@ -125,18 +124,17 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
       k4 = (k4 & m4) | (0x07070707u & ~m4);                     // out of bounds -> slot 7 (the fill channel)
       const uint32_t t = k4 & 0x07070707u;
       const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);  // nibbles k0, k1, k2, k3
-      const uint32_t c4 = __byte_perm(tlo, thi, sel);              // four channel codes
-      const uint32_t c5 = __byte_perm(tlo, thi, k5) & 0xFFu;
+      // four channel codes; cells past the end of the window row (last group of a row whose length is not a
+      // multiple of 5) become 255 = "nothing to write"
+      const int cnt = d.S - j0;
+      const uint32_t c4 = __byte_perm(tlo, thi, sel) | ~__funnelshift_lc(~0u, 0u, 8 * min(cnt, 4));
+      const uint32_t c5 = cnt >= 5 ? (__byte_perm(tlo, thi, k5) & 0xFFu) : 255u;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t code = (c4 >> (8 * u)) & 0xFFu;
         if (code != 255u) srow[code * d.SS + j0 + u] = 0x3F80;  // bf16(1.0)
       }
       if (c5 != 255u) srow[c5 * d.SS + j0 + 4] = 0x3F80;
-    }
-    for (int j = full; j < d.S; ++j) {
-      const uint32_t code = sb_window_code(d, genv, y, x, i, j, 0);
-      if (code != 255u) srow[code * d.SS + j] = 0x3F80;
     }
   }
 }
@@ -953,6 +951,267 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
   if (active && err && p.a.d_error) atomicOr(p.a.d_error, err);
 }
 
+#ifndef SB_ONLY_LPE
+// ----------------------------------------------------------------------------------------------
+// Block-per-instance variant for LARGE worlds with MANY agents (BASELINE config 4: 128x128, 64 agents).
+//
+// One warp per instance (above) leaves the GPU underfilled at the sizes such worlds are run at (2048 instances = 14
+// warps per SM) and every window cell is an L2 round trip because a 16 KB plane per warp does not fit in shared
+// memory.  Here ONE BLOCK of 4 warps owns the instance: the plane is staged in shared memory for the whole launch (16
+// KB + 16 staging rows: six blocks per SM), the sweep runs on all 128 lanes, and up to SIXTEEN agents are observed and
+// moved at once -- 4 warps x 4 subgroups of 8 lanes -- without giving up the list-order semantics of
+// environment.py:92:
+//
+//   Two agents whose start-of-turn positions are more than par_radius apart (Chebyshev) cannot read or write a cell
+//   the other's move touches this turn, so their sub-steps commute.  Agent k therefore only has to wait for the
+//   CONFLICTING agents before it in the list: level(k) = 1 + max{level(j) : j < k, |p_j - p_k| <= par_radius}.  Agents
+//   of one level are pairwise independent and run concurrently; levels run in order with a block barrier in between.
+//   A 64-bit mask per agent (its conflicting predecessors) is built once per turn by 64 lanes; "ready" is then
+//   (mask & ~done) == 0, evaluated identically by every warp (no exchange needed).  Typical turn: ~4 levels.
+//
+// Only the treasurehunt-type fast path is compiled (one stored plane, one-hot rows, byte-SIMD Philox sweep, fused
+// mode, ring attached); everything else keeps using the warp-per-instance kernel.
+// ----------------------------------------------------------------------------------------------
+constexpr int BLK_THREADS = 128, BLK_SLOTS = 16, BLK_SL = 8;  // 16 agent slots of 8 lanes
+
+struct BlockLayout {
+  int q_off, plane_off, agent_off, mask_off, stage_off, stage_row, act_turns, total;
+};
+
+__host__ __device__ inline BlockLayout block_layout(const SbDev& d) {
+  BlockLayout L;
+  L.q_off = 0;
+  L.plane_off = round_up((BLK_THREADS / 32) * (SB_QCAP + 1) * 4, 16) + 16;  // 16 bytes of slack before the plane
+  L.act_turns = act_turns_ahead(BLK_THREADS, d.A);
+  L.agent_off = L.plane_off + round_up(d.env_stride, 16) + 16;                // ... and after it (row-wise gathers)
+  L.mask_off = L.agent_off + round_up(4 * (2 * d.A + L.act_turns * d.A), 16);  // yx, reward, action window
+  L.stage_off = L.mask_off + round_up(8 * d.A, 16);
+  L.stage_row = pad64mod128((d.obs_size + 4) * 2);
+  L.total = L.stage_off + BLK_SLOTS * L.stage_row;
+  return L;
+}
+
+__device__ __forceinline__ int nth_set_bit64(uint64_t m, int k) {  // position of the k-th (0-based) set bit
+  const uint32_t lo = (uint32_t)m;
+  const int c = __popc(lo);
+  return k < c ? (int)__fns(lo, 0u, k + 1) : 32 + (int)__fns((uint32_t)(m >> 32), 0u, k - c + 1);
+}
+
+__global__ void __launch_bounds__(BLK_THREADS, 6)
+    step_kernel_block(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const BlockLayout L = block_layout(d);
+  const int tid = threadIdx.x, warp = tid >> 5, wlane = tid & 31;
+  const int slot_id = warp * (32 / BLK_SL) + wlane / BLK_SL, sl = wlane % BLK_SL;
+  const long long env = blockIdx.x;
+  uint32_t* q = reinterpret_cast<uint32_t*>(smem_raw + L.q_off) + warp * (SB_QCAP + 1);
+  uint8_t* plane = smem_raw + L.plane_off;
+  uint4* plane4 = reinterpret_cast<uint4*>(plane);
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem_raw + L.agent_off);
+  float* srew = reinterpret_cast<float*>(spos + d.A);
+  int32_t* sact_win = reinterpret_cast<int32_t*>(srew + d.A);
+  unsigned long long* smask = reinterpret_cast<unsigned long long*>(smem_raw + L.mask_off);
+  uint8_t* srow = smem_raw + L.stage_off + slot_id * L.stage_row;
+  const uint32_t envid = (uint32_t)(d.env_id_base + (uint64_t)env);
+  const uint32_t* __restrict__ rk = p.rk;
+
+  // ---- stage the instance ------------------------------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.grid + (size_t)env * d.env_stride);
+    for (int c = tid; c < d.n_chunks; c += BLK_THREADS) plane4[c] = __ldg(src + c);
+    for (int a = tid; a < d.A; a += BLK_THREADS) {
+      const int pos = p.agent_pos[(size_t)env * d.A + a];
+      const int y = pos / d.W;
+      spos[a] = ((uint32_t)y << 16) | (uint32_t)(pos - y * d.W);
+    }
+    for (int e = tid; e < BLK_SLOTS * L.stage_row / 4; e += BLK_THREADS)
+      reinterpret_cast<uint32_t*>(smem_raw + L.stage_off)[e] = 0u;
+  }
+  double total = tid == 0 ? p.total_reward[env] : 0.0;
+  uint32_t err = 0;
+  __syncthreads();
+
+  const int T = p.a.num_turns;
+  const size_t rows = (size_t)d.N * d.A, row0 = (size_t)env * d.A;
+  float* const ring0 = p.buf.d_states + row0 * (size_t)p.buf.states_row_stride;
+  const uint32_t tick0 = p.a.d_clock ? p.a.d_clock[0] : p.a.tick0;
+  int slot = p.a.d_clock ? (int)p.a.d_clock[1] : p.a.slot0;
+  const uint64_t all = d.A >= 64 ? ~0ull : ((1ull << d.A) - 1ull);
+  const uint32_t spawn4 = (uint32_t)d.single_spawn_kind * 0x01010101u;
+  int tw = 0;
+
+  for (int t = 0; t < T; ++t, slot = slot + 1 < p.buf.capacity ? slot + 1 : 0) {
+    const uint32_t tick = tick0 + (uint32_t)t;
+
+    // ---- actions of the next act_turns turns (one (turn, agent) pair per lane) -------------------
+    if (tw == L.act_turns) tw = 0;
+    int32_t* const sact = sact_win + tw * d.A;
+    if (tw == 0) {
+      for (int e = tid; e < L.act_turns * d.A; e += BLK_THREADS) {
+        const int dt = L.act_turns > 1 ? (int)(((uint32_t)e * p.inv_A) >> 16) : 0;
+        const int a = e - dt * d.A;
+        int act = 0;
+        if (t + dt < T) {
+          if (p.a.policy == SB_POLICY_UNIFORM) {
+            const SbU4 w = sb_philox_rk(envid, tick + (uint32_t)dt, (uint32_t)a, SB_DOM_ACTION, rk);
+            act = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
+          } else {
+            act = p.a.d_actions[((size_t)(t + dt) * d.N + env) * d.A + a];
+          }
+        }
+        sact_win[e] = act;
+      }
+    }
+    ++tw;
+
+    // ---- entity sweep: all 128 lanes, per-warp candidate queues (see step_kernel) ----------------
+    {
+      uint32_t qcount = 0;
+      for (int base = 0; base < d.n_chunks; base += 2 * BLK_THREADS) {
+        const int c0 = base + tid, c1 = c0 + BLK_THREADS;
+        uint32_t m0 = 0, m1 = 0;
+        if (c0 < d.n_chunks) {
+          const uint4 k = plane4[c0];
+          const SbU4 r = sb_philox_rk(envid, tick, (uint32_t)c0, SB_DOM_SWEEP, rk);
+          m0 = sb_simd_cand_chunk(k.x, k.y, k.z, k.w, r.x, r.y, r.z, r.w, spawn4, d.hmask4);
+          if (c1 < d.n_chunks) {
+            const uint4 k1 = plane4[c1];
+            const SbU4 r1 = sb_philox_rk(envid, tick, (uint32_t)c1, SB_DOM_SWEEP, rk);
+            m1 = sb_simd_cand_chunk(k1.x, k1.y, k1.z, k1.w, r1.x, r1.y, r1.z, r1.w, spawn4, d.hmask4);
+          }
+        }
+        uint32_t b = __ballot_sync(0xFFFFFFFFu, (m0 | m1) != 0);
+        while (b) {
+          if (qcount + 32u > (uint32_t)SB_QCAP) {
+            __syncwarp();
+            drain_queue_cold(&d, q, qcount, plane, 0, env, tick, rk);
+            __syncwarp();
+            qcount = 0;
+          }
+          if (m0 | m1) {
+            const bool first = m0 != 0;
+            const uint32_t m = first ? m0 : m1;
+            const int pos = __ffs(m) - 1;
+            if (first) m0 &= m0 - 1;
+            else m1 &= m1 - 1;
+            q[qcount + __popc(b & ((1u << wlane) - 1u))] = (uint32_t)((first ? c0 : c1) * 16 + 4 * (pos & 7) + (pos >> 3));
+          }
+          qcount += __popc(b);
+          b = __ballot_sync(0xFFFFFFFFu, (m0 | m1) != 0);
+        }
+      }
+      __syncwarp();
+      drain_queue(d, q, qcount, plane, 0, env, tick, rk);  // entries: group 0, instance `env`
+    }
+
+    // ---- conflicting predecessors of every agent (start-of-turn positions) ------------------------
+    for (int a = tid; a < d.A; a += BLK_THREADS) {
+      const uint32_t pa = spos[a];
+      const int ya = (int)(pa >> 16), xa = (int)(pa & 0xFFFFu);
+      uint64_t m = 0;
+      for (int j = 0; j < a; ++j) {
+        const uint32_t pj = spos[j];
+        const int dy = ya - (int)(pj >> 16), dx = xa - (int)(pj & 0xFFFFu);
+        if (max(abs(dy), abs(dx)) <= d.par_radius) m |= 1ull << j;
+      }
+      smask[a] = m;
+    }
+    __syncthreads();  // sweep writes, masks and the action window are visible to every warp
+
+    // ---- agents, level by level ---------------------------------------------------------------
+    uint64_t done = 0;
+    while (done != all) {  // block-uniform: every warp derives the same ready set
+      const int a_lo = wlane, a_hi = wlane + 32;
+      const bool rd_lo = a_lo < d.A && !((done >> a_lo) & 1ull) && (smask[a_lo] & ~done) == 0ull;
+      const bool rd_hi = a_hi < d.A && !((done >> a_hi) & 1ull) && (smask[a_hi] & ~done) == 0ull;
+      const uint64_t ready = (uint64_t)__ballot_sync(0xFFFFFFFFu, rd_lo) |
+                             ((uint64_t)__ballot_sync(0xFFFFFFFFu, rd_hi) << 32);
+      const int n = __popcll(ready);
+      for (int r0 = 0; r0 < n; r0 += BLK_SLOTS) {  // uniform trip count; a slot without an agent only synchronises
+        const int k = r0 + slot_id;
+        const int a = k < n ? nth_set_bit64(ready, k) : -1;
+        uint32_t yx = a >= 0 ? spos[a] : 0u;
+        float* dst = a >= 0 ? ring0 + (size_t)a * (size_t)p.buf.states_row_stride +
+                                  (size_t)slot * (size_t)p.buf.states_slot_stride
+                            : nullptr;
+        emit_onehot_row<BLK_SL, true, 1, true>(d, plane, nullptr, srow, (int)(yx >> 16), (int)(yx & 0xFFFFu), dst, sl);
+        // every lane of the subgroup has read the window (barrier inside emit_onehot_row): move
+        if (a >= 0 && sl == 0) {
+          srew[a] = sb_agent_act(d, plane, &yx, sact[a], true, err);
+          spos[a] = yx;
+        }
+        __syncwarp();
+      }
+      __syncthreads();  // the level's moves are visible before the next level observes
+      done |= ready;
+    }
+
+    // ---- Buffer.add scalars (one agent per lane) and world.total_reward in list order -------------
+    for (int a = tid; a < d.A; a += BLK_THREADS) {
+      const uint32_t yx = spos[a];
+      const size_t at = (size_t)slot * rows + row0 + a;
+      p.buf.d_actions[at] = (int64_t)sact[a];
+      p.buf.d_rewards[at] = srew[a];
+      p.buf.d_dones[at] = 0.0f;
+      if (p.buf.d_positions)
+        *reinterpret_cast<longlong2*>(p.buf.d_positions + 2 * at) =
+            make_longlong2((long long)(yx >> 16), (long long)(yx & 0xFFFFu));
+      const size_t o = ((size_t)t * d.N + env) * d.A + a;
+      if (p.a.d_reward_out) p.a.d_reward_out[o] = srew[a];
+      if (p.a.d_action_out) p.a.d_action_out[o] = sact[a];
+    }
+    if (tid == 0)
+      for (int a = 0; a < d.A; ++a) total += (double)srew[a];  // agent.py:172, list order
+    __syncthreads();  // the action window / rewards may be overwritten by the next turn
+  }
+
+  // ---- write the instance back ---------------------------------------------------------------
+  {
+    uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * d.env_stride);
+    for (int c = tid; c < d.n_chunks; c += BLK_THREADS) dst[c] = plane4[c];
+    for (int a = tid; a < d.A; a += BLK_THREADS) {
+      const uint32_t yx = spos[a];
+      p.agent_pos[(size_t)env * d.A + a] = (int32_t)((yx >> 16) * d.W + (yx & 0xFFFFu));
+    }
+    if (tid == 0) p.total_reward[env] = total;
+  }
+  if (err && p.a.d_error) atomicOr(p.a.d_error, err);
+}
+
+// The block-per-instance kernel applies to: fused mode, ring attached and no second observation output, one stored
+// plane with the one-hot fast path and the row-wise gather table, the byte-SIMD Philox sweep, at most 64 agents
+// (64-bit predecessor masks) but enough of them to occupy the 16 slots, a plane too large for the per-warp tilings
+// yet small enough for several blocks per SM.
+static bool block_kernel_applies(const SbDev& d, const StepParams& p, int kr) {
+  if (p.a.mode != SB_MODE_FUSED || !p.has_buf || p.a.d_obs_out) return false;
+  if (kr != SB_K_PHILOX_SIMD || !(d.fast_obs && d.n_planes == 1) || !d.rowwise_ok || d.toroidal) return false;
+  if (d.A < 16 || d.A > 64) return false;
+  if (p.a.tune_lpe != 0 && p.a.tune_lpe != 128) return false;
+  if (p.a.tune_staged < 0 || p.a.tune_par < 0) return false;
+  if (p.a.tune_lpe == 0 && d.env_stride <= 4096) return false;  // small maps: the per-warp tilings stage them already
+  return block_layout(d).total <= 227 * 1024 / 2;
+}
+
+static int launch_block(const SbDev& d, StepParams p, cudaStream_t s, SbStepPlan* plan) {
+  const BlockLayout L = block_layout(d);
+  sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
+  p.inv_A = (65536u + (uint32_t)d.A - 1u) / (uint32_t)d.A;
+  p.staged = 1, p.par = 1;
+  if (plan) {
+    plan->lpe = BLK_THREADS, plan->kernel_rng = SB_K_PHILOX_SIMD, plan->fast_onehot = 1, plan->staged = 1, plan->par = 1;
+    plan->threads = BLK_THREADS, plan->smem_bytes = L.total, plan->blocks = d.N;
+    return SB_OK;
+  }
+  if (L.total > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(step_kernel_block, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return note_cuda_error(e);
+  }
+  step_kernel_block<<<(unsigned)d.N, BLK_THREADS, L.total, s>>>(d, p);
+  count_launch();
+  return check_launch();
+}
+#endif  // SB_ONLY_LPE
+
 // ----------------------------------------------------------------------------------------------
 // launch
 // ----------------------------------------------------------------------------------------------
@@ -1047,9 +1306,11 @@ int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s, SbStepPlan*
   else if (p.a.rng == SB_RNG_SPARSE) kr = SB_K_SPARSE;
   else kr = d.simd_sweep ? SB_K_PHILOX_SIMD : SB_K_PHILOX_GENERIC;
   const int hint = p.a.tune_lpe;
-  if (hint != 0 && hint != 2 && hint != 4 && hint != 8 && hint != 16 && hint != 32) return SB_EINVAL;
+  if (hint != 0 && hint != 2 && hint != 4 && hint != 8 && hint != 16 && hint != 32 && hint != 128) return SB_EINVAL;
   if (p.a.tune_staged < -1 || p.a.tune_staged > 1 || p.a.tune_par < -1 || p.a.tune_par > 0) return SB_EINVAL;
   if (p.a.tune_staged < 0 && hint != 0 && hint != 32) return SB_EINVAL;
+  if (block_kernel_applies(d, p, kr)) return launch_block(d, p, s, plan);
+  if (hint == 128) return SB_EUNSUPPORTED;  // the block-per-instance kernel was asked for but does not apply
   switch (pick_lpe(d, hint, stage_planes(d, p.a.tune_staged), kr == SB_K_SPARSE)) {
     case 2: return launch_rng_2(d, p, kr, s, plan);
     case 4: return launch_rng_4(d, p, kr, s, plan);

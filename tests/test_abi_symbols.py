@@ -179,10 +179,14 @@ def test_step_plan_without_gpu(built_lib):
     assert rc == abi.SB_OK and p.lpe > 4
     rc, p = plan(R.treasurehunt_spec(21, 21, 8, 2, 0.005), 16384)  # config 3
     assert rc == abi.SB_OK and p.lpe == 8 and p.staged == 1
-    rc, p = plan(R.treasurehunt_spec(128, 128, 64, 4, 0.005), 2048)  # config 4: warp per instance, planes in place
+    rc, p = plan(R.treasurehunt_spec(128, 128, 64, 4, 0.005), 2048)  # config 4: block per instance, plane staged
+    assert rc == abi.SB_OK and (p.lpe, p.staged, p.par, p.blocks) == (128, 1, 1, 2048)
+    assert p.smem_bytes <= 227 * 1024 // 6  # six blocks per SM
+    rc, p = plan(R.treasurehunt_spec(128, 128, 64, 4, 0.005), 2048, lpe=32)  # ... or, pinned, warp per instance
     assert rc == abi.SB_OK and (p.lpe, p.staged, p.par) == (32, 0, 1)
     rc, p = plan(R.treasurehunt_spec(128, 128, 64, 4, 0.005), 2048, par=-1)
-    assert rc == abi.SB_OK and p.par == 0
+    assert rc == abi.SB_OK and (p.lpe, p.par) == (32, 0)
+    assert plan(th1, 64, lpe=128)[0] == abi.SB_EUNSUPPORTED  # one agent: the block kernel does not apply
     rc, p = plan(th1, 64, lpe=4)  # what the tests and smoke() pin
     assert rc == abi.SB_OK and p.lpe == 4
     rc, p = plan(th1, 64, staged=-1)

@@ -169,12 +169,13 @@ def test_config5_one_million_envs_sampled(mode, cuda_device):
 
 def test_config4_large_map_64_agents(cuda_device):
     """BASELINE configs[3]: 128x128 maps, 64 agents, 9x9 one-hot windows, 1024 instances, every array.  The library's
-    choice at this shape (planes used in place, one warp per instance, agent-parallel path) is what is checked."""
+    choice at this shape (block per instance: plane staged in shared memory, up to 16 independent agents at once) is
+    what is checked."""
     spec = R.treasurehunt_spec(128, 128, 64, 4, 0.005)
     N, cap, seed, base = 1024, 4, 0x4C4C, 77
     eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed)
     plan = eng.step_plan(6)
-    assert plan["lanes_per_instance"] == 32
+    assert plan["lanes_per_instance"] == 128 and plan["planes_staged"]  # block per instance
     buf = _buffer(spec, N, cap, cuda_device, layout="slot")
     co = coracle.COracle(spec, N, capacity=cap, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base,
                          threads=coracle.max_threads())

@@ -24,11 +24,11 @@ def _engine(spec, n, device, **kw):
     return Engine(util.engine_spec(spec), n, device=device, **kw)
 
 
-def _buffer(spec, n, capacity, device, n_frames=1):
+def _buffer(spec, n, capacity, device, n_frames=1, layout="agent"):
     from sorrel_b200.buffers import Buffer
 
     return Buffer(capacity, (spec.obs_size,), n_frames=n_frames, rows=n * spec.num_agents, device=device,
-                  positions=(2,))
+                  layout=layout, positions=(2,))
 
 
 def _tapes_to_device(spec, env_tapes, device):
@@ -657,6 +657,53 @@ def test_agent_parallel_path_matches_oracle(A, H, W, v, p, T, N, staged, cuda_de
     np.testing.assert_array_equal(buf.extra_data["positions"].cpu().numpy(), ring["positions"])
     got = obs_out.cpu().numpy().reshape(T - T // 2, N * A, -1)
     np.testing.assert_array_equal(got, np.moveaxis(ring["states"][:, T // 2:], 0, 1))
+
+
+@pytest.mark.parametrize("A,H,W,v,p,T,N", [
+    (64, 128, 128, 4, 0.005, 10, 5),   # BASELINE config 4 shape
+    (16, 64, 64, 3, 0.01, 30, 7),      # exactly one slot per agent
+    (24, 40, 40, 2, 0.02, 25, 6),      # crowded: long dependency chains, many levels
+    (37, 30, 33, 1, 0.02, 20, 5),      # A neither a multiple of 16 nor of 32, 3x3 windows
+    (40, 16, 16, 0, 0.02, 25, 6),      # v = 0, very crowded
+    (64, 24, 24, 5, 0.01, 12, 4),      # 64 agents within sight of each other: nearly sequential
+])
+def test_block_per_instance_kernel_matches_oracle(A, H, W, v, p, T, N, cuda_device):
+    """The block-per-instance kernel (plane staged in shared memory, 16 eight-lane slots, agents released level by level
+    as their conflicting predecessors finish) must reproduce the strictly sequential oracle (environment.py:92) bit for
+    bit in every array: grids, positions, rewards, total reward, every ring array; tape-driven actions as well."""
+    from oracle import coracle
+
+    seed, base = 0xB10C + A, 23
+    spec = R.treasurehunt_spec(H, W, A, v, p)
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed, tuning={"lpe": 128})
+    assert eng.step_plan(T)["lanes_per_instance"] == 128
+    buf = _buffer(spec, N, T, cuda_device)
+    rew = torch.zeros((T - T // 2, N, A), dtype=torch.float32, device=cuda_device)
+    eng.reset()
+    eng.step(T // 2, buffer=buf)
+    eng.step(T - T // 2, buffer=buf, reward_out=rew)
+    eng.check_errors()
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4,
+                         record=True)
+    co.reset()
+    co.step(T)
+    np.testing.assert_array_equal(eng.grid_numpy(), co.grid)
+    np.testing.assert_array_equal(eng.agent_pos.cpu().numpy(), co.pos)
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), co.total_reward)
+    ring = co.ring()
+    np.testing.assert_array_equal(buf.states.cpu().numpy(), ring["states"])
+    np.testing.assert_array_equal(buf.actions.cpu().numpy(), ring["actions"])
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
+    np.testing.assert_array_equal(buf.extra_data["positions"].cpu().numpy(), ring["positions"])
+    np.testing.assert_array_equal(rew.cpu().numpy().reshape(T - T // 2, N * A), ring["rewards"][T // 2:])
+    # the same turns driven by an action tape (policy TAPE) from the same start state
+    eng2 = _engine(spec, N, cuda_device, env_id_base=base, seed=seed, tuning={"lpe": 128})
+    buf2 = _buffer(spec, N, T, cuda_device, layout="slot")
+    eng2.reset()
+    eng2.step(T, buffer=buf2, actions=torch.from_numpy(co.tapes()["actions"].copy()).to(cuda_device))
+    eng2.check_errors()
+    np.testing.assert_array_equal(eng2.grid_numpy(), co.grid)
+    np.testing.assert_array_equal(buf2.states.cpu().numpy(), ring["states"])
 
 
 # ------------------------------------------------------------------------------------------------
