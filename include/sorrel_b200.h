@@ -196,7 +196,8 @@ typedef struct SbWorldDesc {
   int32_t obs_flag;       /* 1: the flag is appended to every observation as one more float (TagAgent.pov :55-65) */
   int32_t toroidal;       /* engine option, NOT a reference behaviour (the reference pads crops with the fill kind and
                              has no toroidal worlds): 1 = observation windows and moves wrap around
-                             the map edges; observations then take the general (table-sum) path */
+                             the map edges.  One-hot worlds keep the fast observation path (bf16 staging row, 128-bit
+                             stores): window indices are folded where the cell is looked up */
   int32_t reserved3;
   int32_t* d_agent_flag;  /* device int32 [N][A]: the flags; read by sb_reset / sb_reset_ex (they survive
                              Environment.reset like the agent attribute does), written back by sb_step; required iff
@@ -387,6 +388,10 @@ int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, 
 size_t sb_stats_scratch_bytes(void);
 int sb_reward_stats(const double* d_total_reward, int64_t n, double* d_out, void* d_scratch,
                     void* stream);
+
+/* Combine the per-rank partials of sb_reward_stats after the all-gather: d_parts double [num_ranks][5] -> d_out
+ * double[5] (sums added in rank order, min / max folded, counts added).  One tiny launch, stream-ordered. */
+int sb_stats_combine(const double* d_parts, int32_t num_ranks, double* d_out, void* stream);
 
 #ifdef __cplusplus
 }

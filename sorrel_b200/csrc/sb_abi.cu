@@ -208,7 +208,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   if (w->obs_transform != SB_OBS_SUM && w->obs_transform != SB_OBS_RGB) return SB_EINVAL;
   d.obs_transform = w->obs_transform;
   d.toroidal = w->toroidal ? 1 : 0;
-  d.fast_obs = (w->static_layers_invisible || d.n_planes == d.L) && d.obs_transform == SB_OBS_SUM && !d.toroidal ? 1 : 0;
+  // (toroidal worlds keep the fast path: window indices are folded where the cell code is looked up)
+  d.fast_obs = (w->static_layers_invisible || d.n_planes == d.L) && d.obs_transform == SB_OBS_SUM ? 1 : 0;
   for (int k = 0; k < d.K; ++k) {
     int ch = 255, ones = 0;
     for (int c = 0; c < d.C; ++c) {
@@ -226,7 +227,7 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   for (int k = d.K; k < SB_MAX_KINDS; ++k) d.channel[k] = 255;
   for (int k = 0; k < 8; ++k) d.channel8 |= (uint64_t)d.channel[k] << (8 * k);
   d.fill_channel = d.channel[d.fill_kind];
-  d.rowwise_ok = d.K <= 7 ? 1 : 0;
+  d.rowwise_ok = d.K <= 7 && !d.toroidal ? 1 : 0;  // (a toroidal window row is not one run of bytes)
   d.channel8_oob = (d.channel8 & 0x00FFFFFFFFFFFFFFull) | ((uint64_t)(uint8_t)d.fill_channel << 56);
   d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536 && !ext) ? 1 : 0;
   if (d.sparse_ok) memcpy(d.cdf, w->spawn_cdf, sizeof(d.cdf));
@@ -500,6 +501,16 @@ __global__ void __launch_bounds__(STATS_THREADS)
   }
 }
 
+__global__ void stats_combine_kernel(const double* __restrict__ parts, int ranks, double* __restrict__ out) {
+  double s = 0, ss = 0, mn = INFINITY, mx = -INFINITY, n = 0;
+  for (int r = 0; r < ranks; ++r) {  // fixed rank order: every rank computes the identical result
+    const double* p = parts + 5 * r;
+    stats_merge(s, ss, mn, mx, p[0], p[1], p[2], p[3]);
+    n += p[4];
+  }
+  out[0] = s, out[1] = ss, out[2] = mn, out[3] = mx, out[4] = n;
+}
+
 __global__ void clock_advance_kernel(uint32_t* clock, uint32_t add_tick, uint32_t add_slot, uint32_t capacity) {
   clock[0] += add_tick;
   clock[1] = (clock[1] + add_slot) % capacity;
@@ -748,6 +759,13 @@ int sb_reward_stats(const double* d_total_reward, int64_t n, double* d_out, void
   unsigned blocks = (unsigned)(want < STATS_BLOCKS ? want : STATS_BLOCKS);
   reward_stats_kernel<<<blocks, STATS_THREADS, 0, (cudaStream_t)stream>>>(d_total_reward, n, d_out,
                                                                          (StatsScratch*)d_scratch);
+  count_launch();
+  return check_launch();
+}
+
+int sb_stats_combine(const double* d_parts, int32_t num_ranks, double* d_out, void* stream) {
+  if (!d_parts || !d_out || num_ranks <= 0) return SB_EINVAL;
+  stats_combine_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_parts, num_ranks, d_out);
   count_launch();
   return check_launch();
 }

@@ -386,7 +386,11 @@ SB_HD uint32_t sb_kind_channel(const SbDev& d, uint32_t kind) {
 // Fast path, phase A: channel code of window cell (i, j) on plane `pl` (255 = contributes nothing).
 SB_HD uint32_t sb_window_code(const SbDev& d, const uint8_t* genv, int y, int x, int i, int j, int pl) {
   int yy = y - d.v + i, xx = x - d.v + j;
-  if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W)
-    return pl == 0 ? (uint32_t)d.fill_channel : 255u;  // out of bounds: the fill kind, once
+  if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) {
+    if (!d.toroidal) return pl == 0 ? (uint32_t)d.fill_channel : 255u;  // out of bounds: the fill kind, once
+    // toroidal worlds: the window shows the opposite side (|offset| <= v <= (H-1)/2, so one fold is enough)
+    yy = yy < 0 ? yy + d.H : (yy >= d.H ? yy - d.H : yy);
+    xx = xx < 0 ? xx + d.W : (xx >= d.W ? xx - d.W : xx);
+  }
   return sb_kind_channel(d, genv[pl * d.plane_stride + yy * d.W + xx]);
 }

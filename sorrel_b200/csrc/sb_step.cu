@@ -177,7 +177,11 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
         for (int u = 0; u < NB; ++u) {
           const int q = ij + u * LANES;
           const int qi = (int)(((uint32_t)q * inv_s) >> 16), qj = q - qi * d.S;
-          const int yy = y - d.v + qi, xx = x - d.v + qj;
+          int yy = y - d.v + qi, xx = x - d.v + qj;
+          if (d.toroidal) {  // fold once: |offset| <= v <= (H-1)/2
+            yy = yy < 0 ? yy + d.H : (yy >= d.H ? yy - d.H : yy);
+            xx = xx < 0 ? xx + d.W : (xx >= d.W ? xx - d.W : xx);
+          }
           kinds[u] = 0x100u;  // beyond the window
           if (q < d.SS)
             kinds[u] = ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) ? 0x200u  // out of bounds
@@ -197,7 +201,11 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
         // several stored planes are SUMMED (visual_field.py:51).  Slot (channel, ij) of the zeroed row is only
         // ever touched by this lane in this loop iteration, so the first plane stores and only a later plane
         // that lands on the same channel (stacked walls) needs a read-modify-write.
-        const int yy = y - d.v + i, xx = x - d.v + j;
+        int yy = y - d.v + i, xx = x - d.v + j;
+        if (d.toroidal) {
+          yy = yy < 0 ? yy + d.H : (yy >= d.H ? yy - d.H : yy);
+          xx = xx < 0 ? xx + d.W : (xx >= d.W ? xx - d.W : xx);
+        }
         float* srow = stage + off + ij;
         if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) {
           if (d.fill_channel != 255) srow[d.fill_channel * d.SS] = 1.0f;  // out of bounds: the fill kind, once

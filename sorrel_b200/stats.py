@@ -23,15 +23,24 @@ def combine_partials(parts: torch.Tensor) -> torch.Tensor:
 
 
 def all_reduce_partial(partial: torch.Tensor, group=None) -> torch.Tensor:
-    """One all_gather of the 5-vector across the process group, combined identically on every rank."""
+    """One all_gather of the 5-vector across the process group, combined identically on every rank.  On CUDA the
+    gather lands in one [R, 5] tensor and ONE small kernel (`sb_stats_combine`) folds it -- two stream-ordered launches
+    per episode instead of a dozen elementwise ones; CPU tensors (gloo tests) are combined with torch."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return combine_partials(partial[None])
+        return partial.clone() if partial.is_cuda else combine_partials(partial[None])
     world = dist.get_world_size(group)
-    parts = [torch.empty(5, dtype=partial.dtype, device=partial.device) for _ in range(world)]
-    dist.all_gather(parts, partial.contiguous(), group=group)
-    return combine_partials(torch.stack(parts))
+    if not partial.is_cuda:
+        parts = [torch.empty(5, dtype=partial.dtype, device=partial.device) for _ in range(world)]
+        dist.all_gather(parts, partial.contiguous(), group=group)
+        return combine_partials(torch.stack(parts))
+    parts = torch.empty((world, 5), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(parts, partial.contiguous(), group=group)
+    out = torch.empty(5, dtype=partial.dtype, device=partial.device)
+    check(lib().sb_stats_combine(parts.data_ptr(), world, out.data_ptr(),
+                                 torch.cuda.current_stream(partial.device).cuda_stream), "sb_stats_combine")
+    return out
 
 
 class PendingStats:

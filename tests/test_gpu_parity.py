@@ -542,6 +542,14 @@ def test_reward_stats(cuda_device):
             xs = x.cpu().numpy()
             np.testing.assert_array_equal(out.cpu().numpy(),
                                           np.array([xs.sum(), (xs * xs).sum(), xs.min(), xs.max(), n]))
+    # the partials of several ranks (what the all-gather delivers) folded by sb_stats_combine
+    from sorrel_b200.stats import combine_partials
+
+    parts = torch.tensor([[10.0, 60.0, -3.0, 7.0, 4.0], [-2.5, 9.25, -2.5, 0.0, 2.0], [0.0, 0.0, 0.0, 0.0, 1.0]],
+                         dtype=torch.float64, device=cuda_device)
+    out = torch.zeros(5, dtype=torch.float64, device=cuda_device)
+    check(L.sb_stats_combine(parts.data_ptr(), 3, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(out, combine_partials(parts)) and out.tolist() == [7.5, 69.25, -3.0, 7.0, 7.0]
 
 
 def test_reset_philox_placement(cuda_device):
@@ -709,16 +717,25 @@ def test_block_per_instance_kernel_matches_oracle(A, H, W, v, p, T, N, cuda_devi
 # ------------------------------------------------------------------------------------------------
 # engine option: toroidal worlds (crops and moves wrap around the map edges)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("lpe", [None, 4])
-def test_toroidal_option_matches_oracle(lpe, cuda_device):
+@pytest.mark.parametrize("lpe,staged,obs,H,W,v", [
+    (None, None, "onehot", 12, 15, 3), (4, None, "onehot", 12, 15, 3), (8, None, "onehot", 12, 15, 3),
+    (32, None, "onehot", 12, 15, 3), (32, 0, "onehot", 12, 15, 3),   # planes used in place in global memory
+    (4, None, "onehot", 9, 11, 4),                                     # v = (H-1)/2: the window spans the whole column
+    (None, None, "rgb", 12, 15, 3), (4, None, "rgb", 12, 15, 3)])      # the general (table-sum) path
+def test_toroidal_option_matches_oracle(lpe, staged, obs, H, W, v, cuda_device):
     """NOT a reference behaviour (the reference pads crops with the fill kind and indexes the map with plain numpy
     indices): an explicit toroidal mode.  Windows that reach over an edge show the opposite side, an
     agent that steps over an edge re-enters on the opposite side; compared with the oracle restatement's own
-    definition of the same option, and the standalone observation kernel agrees with the fused step."""
+    definition of the same option.  One-hot worlds take the FAST observation path (bf16 staging row, 128-bit stores,
+    folded window indices) -- the library reports it -- RGB worlds the general one; the standalone observation kernel
+    agrees with the fused step."""
     tuning = {"lpe": lpe} if lpe else {}
-    spec = R.torus_spec(12, 15, 3, 3, 0.02)
+    if staged is not None:
+        tuning["staged"] = 1 if staged else -1
+    spec = R.torus_spec(H, W, 3, v, 0.02, obs=obs)
     N, T, seed = 23, 40, 8
     eng = _engine(spec, N, cuda_device, seed=seed, tuning=tuning)
+    assert eng.step_plan(T)["fast_onehot"] == (obs == "onehot")
     buf = _buffer(spec, N, T, cuda_device)
     eng.reset()
     eng.step(T, buffer=buf)
@@ -734,12 +751,13 @@ def test_toroidal_option_matches_oracle(lpe, cuda_device):
             p = o.buffers[a].positions
             crossed += int((np.abs(np.diff(p[:, 0])) > 1).sum() + (np.abs(np.diff(p[:, 1])) > 1).sum())
     assert crossed > 0  # some agent did cross a seam
-    obs = eng.observe().reshape(N, 3, -1).cpu().numpy()
+    obs_now = eng.observe().reshape(N, 3, -1).cpu().numpy()
     full = eng.grid_numpy()
     for n in (0, 7):
         for a in range(3):
             y, x = eng.agent_yx()[n, a]
-            np.testing.assert_array_equal(obs[n, a], R.observe(spec, full[n], y, x).reshape(-1).astype(np.float32))
+            np.testing.assert_array_equal(obs_now[n, a],
+                                          R.observe(spec, full[n], y, x).reshape(-1).astype(np.float32))
 
 
 @pytest.mark.parametrize("lpe", [None, 4, 8])
