@@ -227,6 +227,7 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   for (int k = d.K; k < SB_MAX_KINDS; ++k) d.channel[k] = 255;
   for (int k = 0; k < 8; ++k) d.channel8 |= (uint64_t)d.channel[k] << (8 * k);
   d.fill_channel = d.channel[d.fill_kind];
+  d.S5 = d.S - d.S % 5;
   d.rowwise_ok = d.K <= 7 && !d.toroidal ? 1 : 0;  // (a toroidal window row is not one run of bytes)
   d.channel8_oob = (d.channel8 & 0x00FFFFFFFFFFFFFFull) | ((uint64_t)(uint8_t)d.fill_channel << 56);
   d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536 && !ext) ? 1 : 0;

@@ -82,6 +82,7 @@ struct SbDev {
   // window cell becomes a lookup of "kind 7" by a byte mask instead of a branch.  Valid when K <= 7 (slot 7 unused).
   uint64_t channel8_oob;
   int32_t rowwise_ok;
+  int32_t S5;  // S - S % 5: window columns covered by whole 5-cell groups of the row-wise gather
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -212,13 +213,28 @@ SB_HD bool sb_bernoulli_hit(uint64_t thr53, uint32_t r8, uint32_t env, uint32_t 
 
 // Deterministic column rules (SB_RULE_BECOME_IF / SB_RULE_BECOME) for the cell at byte offset `cell` = plane
 // base + `off` of the instance image `genv`.  Returns the new kind, or -1 when the cell keeps its kind.
-SB_HD int sb_column_rule(const SbDev& d, const uint8_t* genv, uint32_t kind, uint32_t rule, int off) {
-  if (rule == SB_RULE_BECOME) return (int)d.rule_to[kind];
+// `ktab` (optional): the per-kind tables in SHARED memory, see sb_fill_kind_tables -- lanes look up DIFFERENT kinds, and
+// a constant-bank load with a divergent index is replayed once per distinct address, a shared load is not.
+SB_HD int sb_column_rule(const SbDev& d, const uint8_t* genv, uint32_t kind, uint32_t rule, int off,
+                         const uint32_t* ktab = nullptr) {
+  const uint32_t to = ktab ? (ktab[kind] >> 16) & 0xFFu : (uint32_t)d.rule_to[kind];
+  if (rule == SB_RULE_BECOME) return (int)to;
   if (rule == SB_RULE_BECOME_IF) {
-    const uint32_t other = genv[d.rule_plane_off[kind] + off];
-    if (other < (uint32_t)SB_MAX_KINDS && ((d.rule_mask[kind] >> other) & 1u)) return (int)d.rule_to[kind];
+    const uint32_t other = genv[(ktab ? (int32_t)ktab[64 + kind] : d.rule_plane_off[kind]) + off];
+    const uint32_t mask = ktab ? ktab[32 + kind] : d.rule_mask[kind];
+    if (other < (uint32_t)SB_MAX_KINDS && ((mask >> other) & 1u)) return (int)to;
   }
   return -1;
+}
+
+// Per-kind tables for shared memory, 3 x 32 words: [kind] = channel | rule << 8 | rule_to << 16 | rule_else << 24,
+// [32 + kind] = rule_mask, [64 + kind] = rule_plane_off.  32 consecutive words = 32 different banks: conflict-free.
+#define SB_KTAB_WORDS 96
+SB_HD void sb_fill_kind_tables(const SbDev& d, uint32_t* ktab, int k) {
+  ktab[k] = (uint32_t)d.channel[k] | ((uint32_t)d.rule[k] << 8) | ((uint32_t)d.rule_to[k] << 16) |
+            ((uint32_t)d.rule_else[k] << 24);
+  ktab[32 + k] = d.rule_mask[k];
+  ktab[64 + k] = (uint32_t)d.rule_plane_off[k];
 }
 
 // Sparse sampling of the spawn field (SB_RNG_SPARSE).  K = number of table entries <= u.

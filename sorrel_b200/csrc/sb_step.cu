@@ -60,7 +60,7 @@ __host__ inline bool stage_planes(const SbDev& d, int tune_staged) {
 __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, bool np1, bool staged, bool sparse) {
   SmemLayout L;
   const int epb = threads / lpe;
-  L.q_off = round_up(2 * d.SS, 16);
+  L.q_off = round_up(2 * d.SS, 16) + 4 * SB_KTAB_WORDS;  // window LUT, per-kind tables, then the queues
   L.planes_off = L.q_off + round_up((threads / 32) * (SB_QCAP + 1) * 4, 16);
   L.plane_env = staged ? pad64mod128(d.env_stride) : 0;
   L.pos_off = L.planes_off + epb * L.plane_env;
@@ -93,9 +93,12 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
 // (the cell-wise loop spends ~35 instructions per cell on index arithmetic, bounds tests and a byte load).
 // Requires K <= 7 (d.rowwise_ok).  `genv` must be shared memory: loads may touch up to 12 bytes before / after the
 // instance image (masked out), which always lie inside the block's allocation (queue before, agent area after).
-template <int LANES>
-__device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_t* genv, uint16_t* srow16, int y, int x,
-                                                    int lane) {
+// PARTIAL = false: S is a multiple of 5 (the common 5x5 window): every group is whole.  PARTIAL = true: the last
+// group of a row holds S % 5 cells; cells past the row end get code 255.  Two instantiations rather than one loop with
+// a count: the extra mask arithmetic in the whole-group path cost 3-9 % of the step (profiles/README.md).
+template <int LANES, bool PARTIAL>
+__device__ __forceinline__ void scatter_rows_onehot_impl(const SbDev& d, const uint8_t* genv, uint16_t* srow16, int y,
+                                                         int x, int lane) {
   const int x0 = x - d.v;                                 // map column of window column 0 (may be negative)
   const int jlo = max(0, -x0), jhi = min(d.S, d.W - x0);  // window columns [jlo, jhi) lie inside the map
   const uint32_t tlo = (uint32_t)d.channel8_oob, thi = (uint32_t)(d.channel8_oob >> 32);
@@ -104,7 +107,7 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
     const bool row_in = (unsigned)yy < (unsigned)d.H;
     const int off = yy * d.W + x0;  // plane offset of window cell (i, 0); out-of-bounds bytes are masked below
     uint16_t* const srow = srow16 + i * d.S;
-    for (int j0 = 0; j0 < d.S; j0 += 5) {  // 5 cells per pair of aligned words
+    for (int j0 = 0; j0 < (PARTIAL ? d.S : d.S5); j0 += 5) {
       // byte mask of the in-bounds cells among j0 .. j0+3, and whether cell j0+4 is in bounds
       const int lc = min(max(jlo - j0, 0), 4), hc = min(max(jhi - j0, 0), 4);
       uint32_t m4 = __funnelshift_lc(~0u, 0u, 8 * hc) & ~__funnelshift_lc(~0u, 0u, 8 * lc);
@@ -119,16 +122,18 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
         in5 = false;
       }
       const uint32_t sh = ((uint32_t)(off + j0) & 3u) * 8u;
-      uint32_t k4 = __funnelshift_r(w0, w1, sh);                // kinds of cells j0 .. j0+3
-      const uint32_t k5 = in5 ? ((w1 >> sh) & 7u) : 7u;          // kind of cell j0+4
-      k4 = (k4 & m4) | (0x07070707u & ~m4);                     // out of bounds -> slot 7 (the fill channel)
+      uint32_t k4 = __funnelshift_r(w0, w1, sh);                   // kinds of cells j0 .. j0+3
+      const uint32_t k5 = in5 ? ((w1 >> sh) & 7u) : 7u;             // kind of cell j0+4
+      k4 = (k4 & m4) | (0x07070707u & ~m4);                        // out of bounds -> slot 7 (the fill channel)
       const uint32_t t = k4 & 0x07070707u;
       const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);  // nibbles k0, k1, k2, k3
-      // four channel codes; cells past the end of the window row (last group of a row whose length is not a
-      // multiple of 5) become 255 = "nothing to write"
-      const int cnt = d.S - j0;
-      const uint32_t c4 = __byte_perm(tlo, thi, sel) | ~__funnelshift_lc(~0u, 0u, 8 * min(cnt, 4));
-      const uint32_t c5 = cnt >= 5 ? (__byte_perm(tlo, thi, k5) & 0xFFu) : 255u;
+      uint32_t c4 = __byte_perm(tlo, thi, sel);                    // four channel codes
+      uint32_t c5 = __byte_perm(tlo, thi, k5) & 0xFFu;
+      if (PARTIAL) {
+        const int cnt = d.S - j0;
+        c4 |= ~__funnelshift_lc(~0u, 0u, 8 * min(cnt, 4));
+        if (cnt < 5) c5 = 255u;
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t code = (c4 >> (8 * u)) & 0xFFu;
@@ -137,6 +142,13 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
       if (c5 != 255u) srow[c5 * d.SS + j0 + 4] = 0x3F80;
     }
   }
+}
+
+template <int LANES>
+__device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_t* genv, uint16_t* srow16, int y, int x,
+                                                    int lane) {
+  if (d.S5 == d.S) scatter_rows_onehot_impl<LANES, false>(d, genv, srow16, y, x, lane);
+  else scatter_rows_onehot_impl<LANES, true>(d, genv, srow16, y, x, lane);
 }
 
 // One observation row through the one-hot fast path, by the LANES lanes that own the instance (all
@@ -148,7 +160,7 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
 // address lines up with an aligned shared address (ring rows are only 8-byte aligned: 600 B, 1944 B).
 // `genv` may point to shared or global memory.
 template <int LANES, bool NP1, int NB = 1, bool ROWWISE = false>
-__device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint16_t* lut_ij,
+__device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint32_t* ktab,
                                                 uint8_t* stage_raw, int y, int x, float* dst, int lane) {
   float* stage = reinterpret_cast<float*>(stage_raw);          // !NP1: f32 sums over planes
   uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_raw);  // NP1: bf16 (0 or 1.0)
@@ -213,7 +225,8 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
           const uint8_t* pc = genv + yy * d.W + xx;
           uint32_t first = 255u;
           for (int pl = 0; pl < d.n_planes; ++pl, pc += d.plane_stride) {
-            const uint32_t code = sb_kind_channel(d, *pc);
+            // several planes mean more than 8 kinds in practice: channel from the shared-memory kind table
+            const uint32_t code = ktab ? (ktab[*pc & 31u] & 0xFFu) : sb_kind_channel(d, *pc);
             if (code == 255u) continue;
             if (first == 255u) {
               srow[code * d.SS] = 1.0f;
@@ -317,8 +330,10 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
   constexpr int GROUPS = OBS_THREADS / LANES;
   uint16_t* lut_ij = reinterpret_cast<uint16_t*>(smem_raw);
   const int lut_bytes = round_up(2 * d.SS, 16);
+  uint32_t* ktab = reinterpret_cast<uint32_t*>(smem_raw + lut_bytes);
+  if (threadIdx.x < 32) sb_fill_kind_tables(d, ktab, threadIdx.x);
   const int grp = threadIdx.x / LANES, lane = threadIdx.x & (LANES - 1);
-  uint8_t* stage_raw = smem_raw + lut_bytes + grp * stage_bytes;
+  uint8_t* stage_raw = smem_raw + lut_bytes + 4 * SB_KTAB_WORDS + grp * stage_bytes;
   for (int ij = threadIdx.x; ij < d.SS; ij += OBS_THREADS) {
     int i = ij / d.S;
     lut_ij[ij] = (uint16_t)((i << 8) | (ij - i * d.S));
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
     float* dst = valid ? out + (size_t)pair * d.obs_size : nullptr;
     if (fast) {
       // window loads batched: 2 per lane cover a 5x5 window with 16 lanes, 4 per lane a 9x9 / 11x11 one with 32
-      emit_onehot_row<LANES, NP1, (LANES == 16 ? 2 : 4)>(d, genv, lut_ij, stage_raw, y, x, dst, lane);
+      emit_onehot_row<LANES, NP1, (LANES == 16 ? 2 : 4)>(d, genv, ktab, stage_raw, y, x, dst, lane);
       __syncwarp();
     } else if (valid) {
       for (int e = lane; e < d.oh_size; e += LANES) {
@@ -370,7 +385,7 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
   const int lanes = d.obs_size <= 256 ? 16 : 32;  // small rows: two pairs per warp
   const int groups = OBS_THREADS / lanes;
   const int stage_bytes = round_up((d.obs_size + 4) * (np1 ? 2 : 4), 16);
-  const int smem = round_up(2 * d.SS, 16) + groups * stage_bytes;
+  const int smem = round_up(2 * d.SS, 16) + 4 * SB_KTAB_WORDS + groups * stage_bytes;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
   const unsigned long long pairs = (unsigned long long)d.N * d.A;
   auto launch = [&](auto kern) -> int {
@@ -442,6 +457,8 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
 
   // ---- carve shared memory --------------------------------------------------------------
   uint16_t* lut_ij = reinterpret_cast<uint16_t*>(smem_raw);  // [SS] (i << 8) | j of window cell ij
+  uint32_t* ktab = reinterpret_cast<uint32_t*>(smem_raw + p.q_off) - SB_KTAB_WORDS;  // per-kind tables (sb_core.cuh)
+  if ((!NP1 || EXT) && tid < 32) sb_fill_kind_tables(d, ktab, tid);  // (the one-plane fast variants never read it)
   uint32_t* qbase = reinterpret_cast<uint32_t*>(smem_raw + p.q_off);
   uint32_t* q = qbase + warp * (SB_QCAP + 1);  // spawn candidates of this warp's instances
   // planes: staged in shared memory for the whole launch, or (large maps, p.staged == 0) used in
@@ -681,7 +698,8 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
               m &= m - 1;
               const uint32_t cell = (uint32_t)(c * 16 + b);
               const uint32_t kind = genv[cell];
-              const uint32_t rule = d.rule[kind];
+              const uint32_t kt = ktab[kind];  // channel | rule << 8 | rule_to << 16 | rule_else << 24
+              const uint32_t rule = (kt >> 8) & 0xFFu;
               if ((d.draw_mask >> kind) & 1u) {
                 if (!have_r) {
                   r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
@@ -693,12 +711,12 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
                   const int nk = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, rk);
                   if (nk >= 0) genv[cell] = (uint8_t)nk;
                 } else if (sb_bernoulli_hit(d.thr53[kind], r8, envid, tick, cell, rk)) {
-                  genv[cell] = d.rule_to[kind];
+                  genv[cell] = (uint8_t)(kt >> 16);
                 } else if ((d.else_mask >> kind) & 1u) {  // register-resident mask: most failed draws change nothing
-                  genv[cell] = d.rule_else[kind];
+                  genv[cell] = (uint8_t)(kt >> 24);
                 }
               } else {
-                const int nk = sb_column_rule(d, genv, kind, rule, cc * 16 + b);
+                const int nk = sb_column_rule(d, genv, kind, rule, cc * 16 + b, ktab);
                 if (nk >= 0) genv[cell] = (uint8_t)nk;
               }
             }
@@ -720,18 +738,18 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
                     : nullptr;
       if (NP1 && LPE == 32 && !STAGED) {
         // large maps used in place in global memory: batch the window loads (one L2 round trip per row, not 3)
-        emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
+        emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, ktab, stage_raw, y, x, dsts[0], lane);
         if (p.a.d_obs_out) {
           __syncwarp();
-          emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
+          emit_onehot_row<LPE, NP1, (NP1 && LPE == 32) ? 4 : 1>(d, genv, ktab, stage_raw, y, x, dsts[1], lane);
         }
       } else if (NP1 || d.fast_obs) {
         // narrow groups on a staged plane gather the window row by row (scatter_rows_onehot)
         constexpr bool RW = NP1 && STAGED && LPE <= SB_ROWWISE_MAX_LPE;
-        emit_onehot_row<LPE, NP1, 1, RW>(d, genv, lut_ij, stage_raw, y, x, dsts[0], lane);
+        emit_onehot_row<LPE, NP1, 1, RW>(d, genv, ktab, stage_raw, y, x, dsts[0], lane);
         if (p.a.d_obs_out) {
           __syncwarp();
-          emit_onehot_row<LPE, NP1, 1, RW>(d, genv, lut_ij, stage_raw, y, x, dsts[1], lane);
+          emit_onehot_row<LPE, NP1, 1, RW>(d, genv, ktab, stage_raw, y, x, dsts[1], lane);
         }
       } else if (active) {
         for (int e = lane; e < d.oh_size; e += LPE) {
@@ -883,11 +901,11 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
           }
           uint8_t* srow = stage_raw + sub * p.stage_row;
           float* dst0 = (p.has_buf && active) ? ring_row(a, slot) : nullptr;
-          emit_onehot_row<SL, NP1, 4>(d, genv, lut_ij, srow, y, x, dst0, sl);
+          emit_onehot_row<SL, NP1, 4>(d, genv, ktab, srow, y, x, dst0, sl);
           if (p.a.d_obs_out) {
             float* dst1 = active ? p.a.d_obs_out + (((size_t)t * d.N + env) * d.A + a) * d.obs_size : nullptr;
             __syncwarp();
-            emit_onehot_row<SL, NP1, 4>(d, genv, lut_ij, srow, y, x, dst1, sl);
+            emit_onehot_row<SL, NP1, 4>(d, genv, ktab, srow, y, x, dst1, sl);
           }
           // every window has been read (the barrier inside emit_onehot_row follows the scatter): move
           float reward = 0.0f;
