@@ -80,6 +80,7 @@ def parse_args():
                          "21x31x3, 10 agents, 11x11 one-hot view + positional code, beams, column rules)")
     ap.add_argument("--obs-study", action="store_true",
                     help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
+    ap.add_argument("--no-numa", action="store_true", help="diagnostic: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--lpe", type=int, default=0, help="diagnostic: pin the lanes per instance (SbStepArgs.tune_lpe)")
     # presets first, then the command line on top of them
     pre = ap.parse_known_args()[0]
@@ -330,6 +331,11 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not a.no_numa:  # host staging buffers and the thread that fills them next to the rank's GPU
+        from sorrel_b200.hostio import bind_to_gpu_numa_node
+
+        numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert a.envs_total % world == 0
@@ -404,11 +410,11 @@ def run_ours(a):
     # NVML is initialised BEFORE the barrier: doing it after would make rank 0 enter the timed region a few
     # milliseconds late and every other rank wait for it at the first all-gather (measured: +4.6 ms)
     clocks = ClockSampler(local) if (rank == 0 and not a.no_clocks) else None
-    l0 = lib.sb_launch_count()
+    l0 = env.kernel_launches()  # direct launches + library kernels inside replayed graphs
     t_wall0 = time.perf_counter()
     ms_total = timed(a.rng)
     t_wall1 = time.perf_counter()
-    launches = lib.sb_launch_count() - l0
+    launches = env.kernel_launches() - l0
     eng.check_errors()
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in seg["step"]]
     breakdown = {k: sum(e0.elapsed_time(e1) for e0, e1 in v) / a.steps for k, v in seg.items()}
@@ -485,7 +491,8 @@ def run_ours(a):
                "api": "sorrel_b200.hostio.HostStepPipeline.submit (pinned host actions in, host rewards out, "
                       "3 streams, 2 buffers in flight" + ("" if a.no_graphs else ", compute stage = CUDA graph") + ")",
                "note": "observations are written straight into the device replay ring (the learner's input) and "
-                       "stay in HBM by design; only actions and rewards cross PCIe"}
+                       "stay in HBM by design; only actions and rewards cross PCIe",
+               "numa": numa}
         eng.check_errors()
         buf.check_errors()
 

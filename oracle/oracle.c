@@ -229,8 +229,6 @@ typedef struct {
   int32_t* tape_a;  /* [T][N][A] */
   int32_t* tape_pl; /* [N][A] placement of the last reset */
   int tape_T;
-  uint32_t hi8;
-  uint64_t lo45;
   uint64_t cdf[OR_SPARSE_KMAX]; /* OR_RNG_SPARSE: floor(2^64 P(X <= k)), X ~ Binomial(n_dyn*plane_stride, P/2^53) */
   uint64_t* env_ids;            /* optional [N]: global id of every instance (else env_id_base + n) */
 } or_env_t;
@@ -280,10 +278,6 @@ or_env_t* or_create(const or_world_t* w, int64_t N, int capacity, int n_frames, 
     e->positions = (int64_t*)calloc(rows * capacity * 2, sizeof(int64_t));
   }
   e->tape_pl = (int32_t*)calloc(rows, sizeof(int32_t));
-  double p = w->p;
-  uint64_t thr = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(p, 53)));
-  e->hi8 = (uint32_t)(thr >> 45);
-  e->lo45 = thr & ((1ull << 45) - 1);
   return e;
 }
 
@@ -466,15 +460,19 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
           } else {
             uint32_t r[4];
             const uint64_t thr = !(prob > 0.0) ? 0 : (prob >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(prob, 53)));
-            const uint32_t hi8 = (uint32_t)(thr >> 45);
-            const uint64_t lo45 = thr & ((1ull << 45) - 1);
+            /* exact Bernoulli(thr / 2^53) in two levels (sb_core.cuh "Counter-based Bernoulli draw") */
+            uint32_t n2 = 0;
+            int lg = 0;
+            if (thr) {
+              const uint32_t hi = (uint32_t)((thr - 1) >> 45);
+              for (n2 = 1; n2 < hi + 1u; n2 <<= 1) ++lg;
+            }
             philox(env, tick, pcell >> 4, DOM_SWEEP, k0, k1, r);
             uint32_t b = pcell & 15, r8 = (r[b >> 2] >> (8 * (b & 3))) & 0xFF;
-            int hit = r8 <= hi8;
-            if (hit && (rule == OR_RULE_SPAWN || r8 == hi8)) philox(env, tick, pcell, DOM_CELL, k0, k1, r);
-            if (hit && r8 == hi8) {
-              uint64_t refine = (((uint64_t)r[0] << 13) | (r[1] >> 19)) & ((1ull << 45) - 1);
-              hit = refine < lo45;
+            int hit = r8 < n2; /* level 1 */
+            if (hit) {         /* level 2: 64 fresh bits below thr << (19 - log2 n2) */
+              philox(env, tick, pcell, DOM_CELL, k0, k1, r);
+              hit = ((((uint64_t)r[0] << 32) | r[1]) <= (thr << (19 - lg)) - 1ull);
             }
             if (!hit) {
               if (rule == OR_RULE_SPAWN_TO && w->rule_else[kind] != OR_NO_KIND) *cellp = w->rule_else[kind];

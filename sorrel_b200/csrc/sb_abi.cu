@@ -96,8 +96,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   d.env_id_base = w->env_id_base;
   d.p = w->spawn_prob;
   const uint64_t thr = spawn_threshold(d.p);
-  d.hi8 = (uint32_t)(thr >> 45);
-  d.lo45 = thr & ((1ull << 45) - 1);
+  d.n2 = sb_level1_bound(thr);
+  d.thr64m1 = sb_level2_bound(thr, d.n2);
   int n_spawn_kinds = 0;
   d.single_spawn_kind = -1;
   for (int k = 0; k < d.K; ++k) {
@@ -113,7 +113,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
       d.draw_mask |= 1u << k;
       d.single_spawn_kind = k;
       d.prob[k] = w->spawn_prob;
-      d.thr53[k] = thr;
+      d.n2k[k] = (uint16_t)d.n2;
+      d.thr64m1k[k] = d.thr64m1;
       ++n_spawn_kinds;
     } else if (rule == SB_RULE_SPAWN_TO) {
       if (!(w->kind_rule_prob[k] >= 0.0) || w->kind_rule_prob[k] > 1.0 || !kind_ok(w->kind_rule_to[k])) return SB_EINVAL;
@@ -123,7 +124,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
       }
       d.draw_mask |= 1u << k;
       d.prob[k] = w->kind_rule_prob[k];
-      d.thr53[k] = spawn_threshold(d.prob[k]);
+      d.n2k[k] = (uint16_t)sb_level1_bound(spawn_threshold(d.prob[k]));
+      d.thr64m1k[k] = sb_level2_bound(spawn_threshold(d.prob[k]), d.n2k[k]);
       d.ext_rules = 1;
     } else if (rule == SB_RULE_BECOME_IF) {
       const int z = w->kind_rule_layer[k];
@@ -198,12 +200,8 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   // changes cells within max_delta of the agent, a window reaches v, two targets are at most 2*max_delta apart
   d.par_radius = max(d.v + max_delta, 2 * max_delta);
   const bool ext = d.ext_rules || d.ext_act || d.obs_extra > 0 || d.obs_flag;  // only the generic / replay variants implement these
-  d.simd_sweep = (d.single_spawn_kind >= 0 && d.hi8 + 1u <= 128u && !ext) ? 1 : 0;
-  {
-    uint32_t n2 = 1;
-    while (n2 < d.hi8 + 1u) n2 <<= 1;
-    d.hmask4 = ((~(n2 - 1u)) & 0xFFu) * 0x01010101u;
-  }
+  d.simd_sweep = (d.single_spawn_kind >= 0 && d.n2 >= 1u && d.n2 <= 128u && !ext) ? 1 : 0;
+  d.hmask4 = ((~(d.n2 - 1u)) & 0xFFu) * 0x01010101u;
   // one-hot fast path: every appearance row is all-zero or exactly one 1.0
   if (w->obs_transform != SB_OBS_SUM && w->obs_transform != SB_OBS_RGB) return SB_EINVAL;
   d.obs_transform = w->obs_transform;

@@ -35,11 +35,11 @@ struct SbDev {
   int32_t fast_obs;           // appearance rows are zero / one-hot and static layers invisible
   int32_t fill_channel;       // fast path: channel of the fill kind (or 255 = none)
   int32_t single_spawn_kind;  // >= 0 when exactly one kind carries SB_RULE_SPAWN
-  int32_t simd_sweep;         // byte-SIMD candidate filter usable (single spawn kind, hi8 < 128)
-  uint32_t hmask4;            // ~(n2 - 1) replicated in 4 bytes, n2 = smallest power of two > hi8
+  int32_t simd_sweep;         // byte-SIMD level-1 filter usable (single spawn kind, 1 <= n2 <= 128)
+  uint32_t hmask4;            // ~(n2 - 1) replicated in 4 bytes
   uint32_t passable_mask, spawn_mask;  // bit k: kind k passable / has SB_RULE_SPAWN
-  uint32_t hi8;                        // top 8 bits of the 53-bit spawn threshold
-  uint64_t lo45;                       // low 45 bits
+  uint32_t n2;                         // level-1 bound of the spawn rule (sb_level1_bound): pass iff r8 < n2
+  uint64_t thr64m1;                    // level-2 bound (sb_level2_bound): spawn iff the 64 fresh bits <= this
   uint64_t choices_packed;             // spawn_choice_kinds, one byte each
   uint64_t channel8;                   // channel[0..7] packed (used when K <= 8)
   uint64_t dy_packed, dx_packed;       // action deltas, one signed byte each
@@ -69,7 +69,8 @@ struct SbDev {
   double value64[SB_MAX_KINDS];  // total_reward accumulates these; the ring stores (float)value64
   int32_t rule_plane_off[SB_MAX_KINDS];  // BECOME_IF: byte offset of the tested plane
   uint32_t rule_mask[SB_MAX_KINDS];
-  uint64_t thr53[SB_MAX_KINDS];  // ceil(prob * 2^53) per drawing kind
+  uint64_t thr64m1k[SB_MAX_KINDS];  // level-2 bound per drawing kind (SPAWN / SPAWN_TO)
+  uint16_t n2k[SB_MAX_KINDS];       // level-1 bound per drawing kind
   double prob[SB_MAX_KINDS];     // replay compares the recorded f64 uniform with this
   int8_t act_facing[SB_MAX_ACTIONS];
   uint8_t act_beam[SB_MAX_ACTIONS];
@@ -171,44 +172,48 @@ SB_HD uint32_t sb_byte_of(const SbU4& r, int b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Counter-based spawn rule (DESIGN.md "Counter-based RNG").  Cell `cell` (= plane * plane_stride +
-// y*W + x) of instance `env` at tick `tick` spawns iff U < ceil(p * 2^53) where the 53-bit uniform
-// U = r8 : refine45 is evaluated lazily: r8 is byte (cell & 15) of Philox(env, tick, cell >> 4,
-// SWEEP); only when r8 == hi8 are the low 45 bits (from Philox(env, tick, cell, CELL)) needed.
+// Counter-based Bernoulli draw (DESIGN.md "Counter-based RNG"): cell `cell` (= plane * plane_stride + y*W + x)
+// of instance `env` at tick `tick` "hits" with probability EXACTLY P / 2^53, P = ceil(p * 2^53) -- the
+// probability of the reference's `np.random.random() < p` -- evaluated in two levels so that almost every cell
+// costs one random BYTE:
+//   level 1: r8 = byte (cell & 15) of Philox(env, tick, cell >> 4, SWEEP); the cell passes iff r8 < n2, n2 = the
+//            smallest power of two >= ((P - 1) >> 45) + 1 (the byte-SIMD filter of 16 cells per Philox call);
+//   level 2: only for passing cells, 64 FRESH bits v from Philox(env, tick, cell, CELL): hit iff v < T,
+//            T = P * 2^19 / n2 = P << (19 - log2 n2)   (<= 2^64 because P <= n2 * 2^45).
+// P(hit) = (n2 / 256) * (T / 2^64) = P / 2^53.  The other 64 bits of the level-2 call choose the kind.
+// (Round 1 refined the SAME 53-bit uniform lazily, which made the resolver recompute the level-1 call; two
+// independent levels need one Philox call per candidate and no state carried from the filter.)
 // ------------------------------------------------------------------------------------------------
+SB_HD uint32_t sb_level1_bound(uint64_t P) {  // n2; 0 = never passes (p == 0)
+  if (P == 0) return 0u;
+  const uint32_t hi = (uint32_t)((P - 1) >> 45);  // <= 255
+  uint32_t n2 = 1;
+  while (n2 < hi + 1u) n2 <<= 1;
+  return n2;
+}
 
-// Second level: called for cells whose r8 <= hi8.  Returns the kind to spawn, or -1.
-SB_HD int sb_resolve_spawn(const SbDev& d, uint32_t env, uint32_t tick, uint32_t cell, bool r8_equal,
-                           const uint32_t* __restrict__ rk) {
-  SbU4 w = sb_philox_rk(env, tick, cell, SB_DOM_CELL, rk);
-  if (r8_equal) {
-    uint64_t refine = (((uint64_t)w.x << 13) | (uint64_t)(w.y >> 19)) & ((1ull << 45) - 1);
-    if (!(refine < d.lo45)) return -1;
-  }
-  uint32_t ci = sb_bounded(w.z, w.w, (uint32_t)d.n_choices);
+SB_HD uint64_t sb_level2_bound(uint64_t P, uint32_t n2) {  // T - 1 (T = 2^64 wraps to 0, minus one = all ones)
+  int lg = 0;
+  while ((1u << lg) < n2) ++lg;
+  return (P << (19 - lg)) - 1ull;
+}
+
+SB_HD bool sb_level2_hit(uint64_t thr64m1, const SbU4& w) { return (((uint64_t)w.x << 32) | w.y) <= thr64m1; }
+
+// Level 2 of the spawn rule for a cell that passed level 1.  Returns the kind to spawn, or -1.
+SB_HD int sb_resolve_candidate(const SbDev& d, uint32_t env, uint32_t tick, uint32_t cell,
+                               const uint32_t* __restrict__ rk) {
+  const SbU4 w = sb_philox_rk(env, tick, cell, SB_DOM_CELL, rk);
+  if (!sb_level2_hit(d.thr64m1, w)) return -1;
+  const uint32_t ci = sb_bounded(w.z, w.w, (uint32_t)d.n_choices);
   return (int)((d.choices_packed >> (8 * ci)) & 0xFFu);
 }
 
-// Resolve a cell that passed the byte-SIMD filter: recompute its first-level byte (the filter keeps
-// no per-cell state), apply the exact comparison and, if it spawns, draw the kind.  -1 = no spawn.
-SB_HD int sb_resolve_candidate(const SbDev& d, uint32_t env, uint32_t tick, uint32_t cell,
-                               const uint32_t* __restrict__ rk) {
-  const SbU4 r = sb_philox_rk(env, tick, cell >> 4, SB_DOM_SWEEP, rk);
-  const uint32_t r8 = sb_byte_of(r, (int)(cell & 15u));
-  if (r8 > d.hi8) return -1;  // the filter bound is a power of two >= hi8 + 1
-  return sb_resolve_spawn(d, env, tick, cell, r8 == d.hi8, rk);
-}
-
-// SB_RULE_SPAWN_TO under the counter-based stream: the same lazily evaluated 53-bit uniform, no choice draw.
-// `r8` is the cell's first-level byte; true = the cell spawns.
-SB_HD bool sb_bernoulli_hit(uint64_t thr53, uint32_t r8, uint32_t env, uint32_t tick, uint32_t cell,
+// SB_RULE_SPAWN_TO: the same two levels, no choice draw.  `r8` is the cell's level-1 byte; true = hit.
+SB_HD bool sb_bernoulli_hit(uint32_t n2, uint64_t thr64m1, uint32_t r8, uint32_t env, uint32_t tick, uint32_t cell,
                             const uint32_t* __restrict__ rk) {
-  const uint32_t hi8 = (uint32_t)(thr53 >> 45);
-  if (r8 > hi8) return false;
-  if (r8 < hi8) return true;
-  const SbU4 w = sb_philox_rk(env, tick, cell, SB_DOM_CELL, rk);
-  const uint64_t refine = (((uint64_t)w.x << 13) | (uint64_t)(w.y >> 19)) & ((1ull << 45) - 1);
-  return refine < (thr53 & ((1ull << 45) - 1));
+  if (r8 >= n2) return false;
+  return sb_level2_hit(thr64m1, sb_philox_rk(env, tick, cell, SB_DOM_CELL, rk));
 }
 
 // Deterministic column rules (SB_RULE_BECOME_IF / SB_RULE_BECOME) for the cell at byte offset `cell` = plane
@@ -245,9 +250,8 @@ SB_HD int sb_sparse_count(const SbDev& d, uint64_t u) {
 }
 
 // Byte-SIMD first-level FILTER for 4 cells (one 32-bit word of kinds / random bytes): returns 0x80 in
-// every byte whose kind == single_spawn_kind and whose random byte r8 < n2, n2 = 2^k >= hi8 + 1
-// (`hmask4` = ~(n2-1) replicated).  A superset of {r8 <= hi8}: the exact comparison happens when the
-// candidate is resolved.  One zero-byte detection on (kinds ^ spawn4) | (rnd & hmask4).
+// every byte whose kind == single_spawn_kind and whose random byte r8 < n2 (`hmask4` = ~(n2-1) replicated): exactly
+// the cells that pass level 1 of the Bernoulli draw above.  One zero-byte detection on (kinds ^ spawn4) | (rnd & hmask4).
 SB_HD uint32_t sb_simd_cand_word(uint32_t kinds, uint32_t rnd, uint32_t spawn4, uint32_t hmask4) {
   uint32_t x = (kinds ^ spawn4) | (rnd & hmask4);
   uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;

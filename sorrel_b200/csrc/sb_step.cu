@@ -707,10 +707,10 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
                 }
                 const uint32_t r8 = sb_byte_of(r, b);
                 if (rule == SB_RULE_SPAWN) {
-                  if (r8 > d.hi8) continue;
-                  const int nk = sb_resolve_spawn(d, envid, tick, cell, r8 == d.hi8, rk);
+                  if (r8 >= d.n2) continue;  // level 1
+                  const int nk = sb_resolve_candidate(d, envid, tick, cell, rk);
                   if (nk >= 0) genv[cell] = (uint8_t)nk;
-                } else if (sb_bernoulli_hit(d.thr53[kind], r8, envid, tick, cell, rk)) {
+                } else if (sb_bernoulli_hit(d.n2k[kind], d.thr64m1k[kind], r8, envid, tick, cell, rk)) {
                   genv[cell] = (uint8_t)(kt >> 16);
                 } else if ((d.else_mask >> kind) & 1u) {  // register-resident mask: most failed draws change nothing
                   genv[cell] = (uint8_t)(kt >> 24);

@@ -150,6 +150,11 @@ class Environment:
         self._graphs[(int(num_turns), rng)] = StepGraph(self.engine, self.buffer, int(num_turns), rng=rng,
                                                         sample_batch=int(sample_batch))
 
+    def kernel_launches(self) -> int:
+        """Kernels of libsorrel_b200 launched so far by this process: direct launches (`sb_launch_count`) plus the
+        library kernels inside replayed CUDA graphs."""
+        return int(self.engine.lib.sb_launch_count()) + sum(g.kernels_replayed for g in self._graphs.values())
+
     def sample_device(self, batch_size: int, rng: str = "philox", generator=None):
         """Buffer.sample for the learner with the index draw on the device (buffers.py:98-124): replays the captured
         graph when `enable_graphs` was given this batch size, else `Buffer.sample_device`."""

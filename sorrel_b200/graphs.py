@@ -37,6 +37,8 @@ class StepGraph:
         is not capturable): run one eager `engine.step(...)` / `buffer.gather(...)` first."""
         self.eng, self.buf, self.T, self.rng, self.B = engine, buffer, int(turns), rng, int(sample_batch)
         self._keep = (actions, reward_out)
+        #: kernels of libsorrel_b200 launched through graph replays (sb_launch_count only sees direct launches)
+        self.kernels_replayed = 0
         dev = engine.device
         self._clock = clock or DeviceClock(dev)
         self.clock = self._clock.tensor
@@ -114,6 +116,7 @@ class StepGraph:
         """`turns` fused turns for every instance."""
         self._sync_clock()
         self.graph.replay()
+        self.kernels_replayed += 2  # step kernel + clock advance
         self.eng.tick += self.T
         self.buf.advance(self.T)
         held = self._clock.held
@@ -124,6 +127,7 @@ class StepGraph:
         if max(1, self.buf.size - self.buf.n_frames - 1) != self._hi:
             raise RuntimeError("the ring population changed since capture: capture the StepGraph again")
         self.sample_graph.replay()
+        self.kernels_replayed += 1  # buffer_sample_kernel
         return self.sample
 
     def replay(self):

@@ -22,13 +22,11 @@ void hc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, uint32_t
 static void set_prob(SbDev* d, double p, int n_choices) {
   uint64_t thr = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(p, 53)));
   d->p = p;
-  d->hi8 = (uint32_t)(thr >> 45);
-  d->lo45 = thr & ((1ull << 45) - 1);
+  d->n2 = sb_level1_bound(thr);
+  d->thr64m1 = sb_level2_bound(thr, d->n2);
   d->n_choices = n_choices;
   d->choices_packed = 0x0706050403020100ull;
-  uint32_t n2 = 1;
-  while (n2 < d->hi8 + 1u) n2 <<= 1;
-  d->hmask4 = ((~(n2 - 1u)) & 0xFFu) * 0x01010101u;
+  d->hmask4 = ((~(d->n2 - 1u)) & 0xFFu) * 0x01010101u;
 }
 
 // first-level filter of one chunk: returns the 16-bit mask (bit = byte index in the chunk) of candidates
@@ -60,6 +58,9 @@ int hc_resolve_candidate(double p, int n_choices, uint32_t env, uint32_t tick, u
   set_prob(&d, p, n_choices);
   uint32_t rk[20];
   sb_philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), rk);
+  // level 1 the way the sweep evaluates it (byte (cell & 15) of the chunk's call), then the resolver = level 2
+  const SbU4 r = sb_philox_rk(env, tick, cell >> 4, SB_DOM_SWEEP, rk);
+  if (sb_byte_of(r, (int)(cell & 15u)) >= d.n2) return -1;
   return sb_resolve_candidate(d, env, tick, cell, rk);
 }
 
@@ -106,7 +107,8 @@ int hc_bernoulli_hit(double p, uint32_t env, uint32_t tick, uint32_t cell, uint6
   uint32_t rk[20];
   sb_philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), rk);
   const SbU4 r = sb_philox_rk(env, tick, cell >> 4, SB_DOM_SWEEP, rk);
-  return sb_bernoulli_hit(thr, sb_byte_of(r, (int)(cell & 15u)), env, tick, cell, rk) ? 1 : 0;
+  const uint32_t n2 = sb_level1_bound(thr);
+  return sb_bernoulli_hit(n2, sb_level2_bound(thr, n2), sb_byte_of(r, (int)(cell & 15u)), env, tick, cell, rk) ? 1 : 0;
 }
 
 // deterministic column rules on a 2-plane image: planes[2][stride]; the rule of `kind` tests plane `other_plane`

@@ -53,12 +53,13 @@ def test_philox_known_answers_and_round_key_variant(hc):
 
 @pytest.mark.parametrize("p", [0.005, 0.05, 0.2, 0.49, 1e-4, 0.00390625])
 def test_byte_simd_filter_is_exact_superset(hc, p):
-    """Filter mask == {cell is the spawning kind and r8 < n2}, n2 = power of two >= hi8+1 (so it contains
-    every cell with r8 <= hi8 and nothing of another kind)."""
+    """Filter mask == {cell is the spawning kind and r8 < n2}: exactly the cells that pass level 1 of the two-level
+    Bernoulli draw, n2 = the power of two R.level1_bound gives (>= the largest accepted top byte + 1)."""
     rng = np.random.RandomState(int(p * 1e6))
-    hi8 = R.spawn_threshold(p) >> 45
+    P = R.spawn_threshold(p)
     n2 = hc.hc_filter_bound(p)
-    assert n2 >= hi8 + 1 and n2 & (n2 - 1) == 0 and n2 < 2 * (hi8 + 1) + 1
+    assert n2 == R.level1_bound(P) and n2 & (n2 - 1) == 0 and n2 >= ((P - 1) >> 45) + 1
+    assert (P << 19) // n2 <= 1 << 64  # the level-2 bound fits: P(hit) = (n2 / 256) * (T / 2^64) = P / 2^53
     for spawn_kind in (0, 3, 7):
         for _ in range(400):
             kinds = np.where(rng.rand(16) < 0.5, spawn_kind, rng.randint(0, 256, 16)).astype(np.uint8)
