@@ -80,6 +80,7 @@ def parse_args():
                          "21x31x3, 10 agents, 11x11 one-hot view + positional code, beams, column rules)")
     ap.add_argument("--obs-study", action="store_true",
                     help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
+    ap.add_argument("--actions-i32", action="store_true", help="e2e: ship int32 actions instead of uint8")
     ap.add_argument("--no-numa", action="store_true", help="diagnostic: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--lpe", type=int, default=0, help="diagnostic: pin the lanes per instance (SbStepArgs.tune_lpe)")
     # presets first, then the command line on top of them
@@ -448,9 +449,10 @@ def run_ours(a):
     if not a.no_e2e:
         from sorrel_b200.hostio import HostStepPipeline
 
-        pipe = HostStepPipeline(eng, buf, T, rng=a.rng, timing=True)
+        act_dtype = torch.int32 if a.actions_i32 else torch.uint8  # action indices fit a byte (<= 8 actions)
+        pipe = HostStepPipeline(eng, buf, T, rng=a.rng, timing=True, action_dtype=act_dtype)
         n_act = env.agents[0].action_spec.n_actions
-        h_actions = [torch.randint(0, n_act, (T, N, A), dtype=torch.int32).pin_memory() for _ in range(2)]
+        h_actions = [torch.randint(0, n_act, (T, N, A), dtype=act_dtype).pin_memory() for _ in range(2)]
 
         def e2e_step(i):
             """The same step as `one_step` (boundary statistics + reset, fused turns, Buffer.sample), with the
@@ -464,7 +466,8 @@ def run_ours(a):
             e2e_step(i)
         pipe.drain()
         if not a.no_graphs:  # per-slot graphs of [step, clock advance, index draw, sample] over fixed buffers
-            pipe = HostStepPipeline(eng, buf, T, rng=a.rng, timing=True, graphs=True, sample_batch=B)
+            pipe = HostStepPipeline(eng, buf, T, rng=a.rng, timing=True, graphs=True, sample_batch=B,
+                                    action_dtype=act_dtype)
         else:
             pipe.B = B
         for i in range(3):
@@ -488,7 +491,8 @@ def run_ours(a):
                "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
                "ms_per_step": e2e_ms / a.steps, "reward_checksum": float(results),
                "step_kernel_ms": sum(e0.elapsed_time(e1) for e0, e1 in pipe.kernel_events[-a.steps:]) / a.steps,
-               "api": "sorrel_b200.hostio.HostStepPipeline.submit (pinned host actions in, host rewards out, "
+               "api": "sorrel_b200.hostio.HostStepPipeline.submit (pinned host " + ("int32" if a.actions_i32 else "uint8") +
+                      " actions in, float32 host rewards out, "
                       "3 streams, 2 buffers in flight" + ("" if a.no_graphs else ", compute stage = CUDA graph") + ")",
                "note": "observations are written straight into the device replay ring (the learner's input) and "
                        "stay in HBM by design; only actions and rewards cross PCIe",

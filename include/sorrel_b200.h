@@ -283,7 +283,8 @@ typedef struct SbStepArgs {
   int32_t tune_staged; /* instance planes staged in shared memory for the launch: 0 auto, 1 staged, -1 used in place
                           in global memory (one warp per instance: tune_lpe must be 0 or 32) */
   int32_t tune_par;    /* agent-parallel path of warp-per-instance worlds: 0 auto, -1 off */
-  int32_t reserved5;
+  int32_t actions_u8;  /* 1: d_actions points to uint8 [T][N][A] instead of int32 (an ActionSpec has at most
+                          SB_MAX_ACTIONS = 8 actions): a quarter of the host-to-device bytes of a host policy */
 } SbStepArgs;
 
 /* What sb_step would launch for (desc, args): filled by sb_step_plan without touching the device. */

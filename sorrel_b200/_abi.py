@@ -158,7 +158,7 @@ class SbStepArgs(C.Structure):
         ("tune_lpe", C.c_int32),
         ("tune_staged", C.c_int32),
         ("tune_par", C.c_int32),
-        ("reserved5", C.c_int32),
+        ("actions_u8", C.c_int32),
     ]
 
 

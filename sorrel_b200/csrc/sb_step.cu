@@ -542,7 +542,10 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
             SbU4 w = sb_philox_rk(envid, tick + (uint32_t)dt, (uint32_t)a, SB_DOM_ACTION, rk);
             act = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
           } else if (active && p.a.d_actions) {
-            act = p.a.d_actions[((size_t)(t + dt) * d.N + env) * d.A + a];
+            {
+              const size_t at = ((size_t)(t + dt) * d.N + env) * d.A + a;
+              act = p.a.actions_u8 ? (int)reinterpret_cast<const uint8_t*>(p.a.d_actions)[at] : p.a.d_actions[at];
+            }
           }
         }
         sact_win[e] = act;
@@ -1082,7 +1085,10 @@ __global__ void __launch_bounds__(BLK_THREADS, 6)
             const SbU4 w = sb_philox_rk(envid, tick + (uint32_t)dt, (uint32_t)a, SB_DOM_ACTION, rk);
             act = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
           } else {
-            act = p.a.d_actions[((size_t)(t + dt) * d.N + env) * d.A + a];
+            {
+              const size_t at = ((size_t)(t + dt) * d.N + env) * d.A + a;
+              act = p.a.actions_u8 ? (int)reinterpret_cast<const uint8_t*>(p.a.d_actions)[at] : p.a.d_actions[at];
+            }
           }
         }
         sact_win[e] = act;

@@ -402,7 +402,9 @@ class Engine:
                                  f"got {t.dtype} {tuple(t.shape)} on {t.device}")
             return t.data_ptr()
 
-        a.d_actions = chk(actions, (T, N, A), torch.int32, "actions")
+        # action tapes: int32, or uint8 (an ActionSpec has at most 8 actions: a quarter of the bytes a host policy ships)
+        a.actions_u8 = 1 if actions is not None and actions.dtype == torch.uint8 else 0
+        a.d_actions = chk(actions, (T, N, A), torch.uint8 if a.actions_u8 else torch.int32, "actions")
         a.d_spawn_u = chk(spawn_u, (T, N, ES), torch.float64, "spawn_u")
         a.d_spawn_c = chk(spawn_c, (T, N, ES), torch.uint8, "spawn_c")
         a.d_obs_out = chk(obs_out, (T, N, A, self.spec.obs_size), torch.float32, "obs_out")

@@ -48,7 +48,9 @@ class StepGraph:
         a.rng = _abi.SB_RNG_SPARSE if rng == "sparse" else _abi.SB_RNG_PHILOX
         a.policy = _abi.SB_POLICY_UNIFORM if actions is None else _abi.SB_POLICY_TAPE
         shape = (self.T, engine.N, engine.A)
-        for t, dtype, name in ((actions, torch.int32, "actions"), (reward_out, torch.float32, "reward_out")):
+        a.actions_u8 = 1 if actions is not None and actions.dtype == torch.uint8 else 0
+        for t, dtype, name in ((actions, torch.uint8 if a.actions_u8 else torch.int32, "actions"),
+                               (reward_out, torch.float32, "reward_out")):
             if t is not None and (tuple(t.shape) != shape or t.dtype != dtype or not t.is_contiguous()
                                   or t.device != engine.grid.device):
                 raise ValueError(f"{name}: expected contiguous {dtype} {shape} on {engine.grid.device}")

@@ -55,20 +55,24 @@ def bind_to_gpu_numa_node(device_index: int) -> dict:
 
 class HostStepPipeline:
     def __init__(self, engine, buffer, turns: int, depth: int = 2, rng: str = "philox", timing: bool = False,
-                 graphs: bool = False, sample_batch: int = 0):
+                 graphs: bool = False, sample_batch: int = 0, action_dtype: torch.dtype = torch.int32):
+        """`action_dtype`: torch.int32, or torch.uint8 -- action indices fit a byte (ActionSpec sizes <= 8), which
+        quarters the host-to-device traffic of a host policy."""
+        if action_dtype not in (torch.int32, torch.uint8):
+            raise ValueError("action_dtype must be torch.int32 or torch.uint8")
         self.eng, self.buf, self.T, self.depth, self.rng = engine, buffer, int(turns), depth, rng
         self.timing, self.kernel_events = timing, []  # (start, end) CUDA events around every step launch
         self.B = int(sample_batch)
         dev, N, A = engine.device, engine.N, engine.A
         shape = (self.T, N, A)
-        self.d_actions = [torch.zeros(shape, dtype=torch.int32, device=dev) for _ in range(depth)]
+        self.d_actions = [torch.zeros(shape, dtype=action_dtype, device=dev) for _ in range(depth)]
         self.d_rewards = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(depth)]
         self.h_rewards = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.s_h2d, self.s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         mk = lambda: [torch.cuda.Event() for _ in range(depth)]  # noqa: E731
         self.ev_h2d, self.ev_compute, self.ev_d2h = mk(), mk(), mk()
         self.i = 0
-        self.h2d_bytes = self.d_actions[0].numel() * 4
+        self.h2d_bytes = self.d_actions[0].numel() * self.d_actions[0].element_size()
         self.d2h_bytes = self.d_rewards[0].numel() * 4
         self.sampled = None  # the last step's Buffer.sample batch (device tensors), when sample_batch > 0
         self.graphs = None

@@ -481,3 +481,43 @@ def test_ring_layouts_agree_across_the_buffer_api(cuda_device):
         assert torch.equal(back.states[0], a.states[4])
     with pytest.raises(ValueError):
         Buffer(4, (6,), rows=2, device=cuda_device, layout="diagonal")
+
+
+@pytest.mark.parametrize("A,H,lpe", [(1, 21, 4), (3, 21, None), (20, 40, 128)])
+def test_uint8_action_tapes_equal_int32(A, H, lpe, cuda_device):
+    """Action tapes may be uint8 (ActionSpec sizes <= 8): same step as the int32 tape, a quarter of the bytes; eager
+    launches, the host pipeline and its CUDA-graph form."""
+    from sorrel_b200.buffers import Buffer
+    from sorrel_b200.engine import Engine
+    from sorrel_b200.hostio import HostStepPipeline
+
+    spec = R.treasurehunt_spec(H, H, A, 2, 0.02)
+    N, T = 33, 6
+    acts = torch.randint(0, 4, (3, T, N, A), dtype=torch.int32)
+    outs = {}
+    for mode in ("i32", "u8", "pipe", "pipe_graph"):
+        eng = Engine(util.engine_spec(spec), N, device=cuda_device, seed=5, tuning={"lpe": lpe} if lpe else None)
+        buf = Buffer(3 * T, (spec.obs_size,), rows=N * A, device=cuda_device, positions=(2,))
+        eng.reset()
+        rew = []
+        if mode in ("i32", "u8"):
+            for k in range(3):
+                tape = acts[k].to(cuda_device) if mode == "i32" else acts[k].to(torch.uint8).to(cuda_device)
+                r = torch.zeros((T, N, A), dtype=torch.float32, device=cuda_device)
+                eng.step(T, buffer=buf, actions=tape, reward_out=r)
+                rew.append(r.cpu())
+        else:
+            eng.step(T, buffer=buf, actions=acts[0].to(cuda_device))  # (kernels loaded before any capture)
+            rew.append(None)
+            pipe = HostStepPipeline(eng, buf, T, action_dtype=torch.uint8, graphs=mode == "pipe_graph")
+            for k in (1, 2):
+                h = pipe.submit(acts[k].to(torch.uint8).pin_memory())
+                pipe.drain()
+                rew.append(h.clone())
+        eng.check_errors()
+        outs[mode] = (eng.grid_numpy(), buf.states.cpu(), buf.actions.cpu(), rew)
+    for mode in ("u8", "pipe", "pipe_graph"):
+        np.testing.assert_array_equal(outs[mode][0], outs["i32"][0])
+        assert torch.equal(outs[mode][1], outs["i32"][1]) and torch.equal(outs[mode][2], outs["i32"][2])
+        for k in (1, 2):
+            assert torch.equal(outs[mode][3][k], outs["i32"][3][k])
