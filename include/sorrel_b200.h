@@ -382,6 +382,10 @@ int sb_buffer_sample_transformer(const SbBufferDesc* buf, const int64_t* d_rows,
  */
 int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, void* stream);
 
+/* Same with the write head read from device memory: idx = d_clock[1] (see SbStepArgs.d_clock), so that a captured
+ * CUDA graph of a whole split-phase turn can stack frames for its policy without a host-side index. */
+int sb_buffer_current_state_dev(const SbBufferDesc* buf, const uint32_t* d_clock, float* d_out, void* stream);
+
 /* -- per-episode reward statistics (feeds Logger.record_turn, utils/logging.py:48-72) ------- *
  * d_out double[5] = {sum, sum of squares, min, max, count} over d_total_reward[0..n); the only
  * quantity that is all-reduced across ranks (NCCL, by the caller).  d_scratch: >= sb_stats_scratch_bytes().

@@ -210,6 +210,7 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p]),
     "sb_buffer_current_state": (C.c_int, [C.POINTER(SbBufferDesc), C.c_int32, C.c_void_p, C.c_void_p]),
+    "sb_buffer_current_state_dev": (C.c_int, [C.POINTER(SbBufferDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_stats_scratch_bytes": (C.c_size_t, []),
     "sb_reward_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_stats_combine": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

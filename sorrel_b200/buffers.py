@@ -61,6 +61,10 @@ class Buffer:
         self.idx = 0
         self.size = 0
         self._desc = None
+        #: graphs.DeviceClock or None.  When set (Environment.enable_turn_graph), `current_state` reads the write head
+        #: from device memory and always copies into one fixed tensor, so that it can live inside a captured graph.
+        self.device_clock = None
+        self._cs_fixed = None
 
     def _alloc(self):
         dev = self.device
@@ -274,6 +278,13 @@ class Buffer:
         """buffers.py:143-154: the last n_frames-1 observations before the write head, per row:
         float32 [rows, n_frames-1, *obs_shape].  A zero-copy view unless the window wraps."""
         F1 = self.n_frames - 1
+        if self.device_clock is not None:
+            if self._cs_fixed is None:
+                self._cs_fixed = torch.zeros((self.rows, F1, *self.obs_shape), dtype=torch.float32, device=self.device)
+            check(self.lib.sb_buffer_current_state_dev(C.byref(self.desc()), self.device_clock.tensor.data_ptr(),
+                                                       self._cs_fixed.data_ptr(), self._stream()),
+                  "sb_buffer_current_state_dev")
+            return self._cs_fixed
         if self.idx >= F1:
             return self.states[:, self.idx - F1: self.idx]
         out = torch.empty((self.rows, F1, *self.obs_shape), dtype=torch.float32, device=self.device)

@@ -424,8 +424,10 @@ __global__ void buffer_sample_kernel(SbBufferDesc b, const int64_t* __restrict__
   }
 }
 
-__global__ void buffer_current_state_kernel(SbBufferDesc b, int idx, float* __restrict__ out) {
+__global__ void buffer_current_state_kernel(SbBufferDesc b, int idx, const uint32_t* __restrict__ clock,
+                                            float* __restrict__ out) {
   // rows [idx-(F-1), idx) with ring wrap (Buffer.current_state, buffers.py:143-154)
+  if (clock) idx = (int)clock[1];  // write head kept on the device (graph-replayed turns)
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= b.rows) return;
@@ -744,7 +746,20 @@ int sb_buffer_current_state(const SbBufferDesc* buf, int32_t idx, float* d_out, 
   if (idx < 0 || idx >= buf->capacity || !d_out) return SB_EINVAL;
   if (buf->n_frames < 2) return SB_OK;  // zero rows, like states[idx:idx]
   const long long threads = buf->rows * 32;
-  buffer_current_state_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nb, idx,
+  buffer_current_state_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nb, idx, nullptr,
+                                                                                                   d_out);
+  count_launch();
+  return check_launch();
+}
+
+int sb_buffer_current_state_dev(const SbBufferDesc* buf, const uint32_t* d_clock, float* d_out, void* stream) {
+  SbBufferDesc nb;
+  int rc = check_buf(buf, &nb);
+  if (rc) return rc;
+  if (!d_clock || !d_out) return SB_EINVAL;
+  if (buf->n_frames < 2) return SB_OK;
+  const long long threads = buf->rows * 32;
+  buffer_current_state_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nb, 0, d_clock,
                                                                                                    d_out);
   count_launch();
   return check_launch();

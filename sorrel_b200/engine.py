@@ -366,7 +366,7 @@ class Engine:
 
     def phase(self, *, sweep: bool = False, act_agent: int = -1, obs_agent: int = -1, buffer=None,
               actions: torch.Tensor | None = None, spawn_u=None, spawn_c=None, obs_out=None, reward_out=None,
-              new_turn: bool = False, rng: str = "philox") -> None:
+              new_turn: bool = False, rng: str = "philox", clock=None) -> None:
         """One split-phase launch: [sweep] -> [act agent k] -> [observe agent j] (SB_MODE_SPLIT).
 
         Lets a live policy run between `pov()` and `act()` of each agent exactly like
@@ -384,6 +384,8 @@ class Engine:
         a.do_sweep = 1 if sweep else 0
         a.act_agent, a.obs_agent = act_agent, obs_agent
         self._fill_ptrs(a, 1, actions, spawn_u, spawn_c, obs_out, reward_out, None, None)
+        if clock is not None:
+            a.d_clock = clock.tensor.data_ptr()
         bdesc = None
         if buffer is not None:
             a.slot0 = buffer.idx

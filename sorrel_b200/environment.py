@@ -97,6 +97,9 @@ class Environment:
         self._action_slot = torch.zeros((1, eng.N, A), dtype=torch.int32, device=eng.device)
         self._turn_open = False
         self._graphs = {}  # (turns, rng) -> StepGraph, see enable_graphs()
+        self._turn_graph = None  # CUDA graph of one whole split-phase turn, see enable_turn_graph()
+        self._turn_clock = None
+        self._obs_fixed = None
 
     @property
     def engine(self):
@@ -121,11 +124,80 @@ class Environment:
         if self._fusable:
             self.take_turns(1)
             return
-        self.turn += 1
+        if self._turn_graph is not None:  # the whole turn (every agent's phases and policy) as one graph replay
+            self._sync_turn_clock()
+            self._turn_graph.replay()
+            self.engine.tick += 1  # (the eager path advances it in the first phase launch of the turn)
+            self._after_turn()
+            return
+        if self._turn_clock is not None:
+            self._sync_turn_clock()
+        self._take_turn_split()
+        self._after_turn()
+
+    def _take_turn_split(self) -> None:
+        """One turn through the split-phase launches: Agent.transition per agent slot, in list order."""
         self._turn_open = False
         for agent in self.agents:  # entity sweep happens in agent 0's pov launch
             agent.transition(self.world)
+        if self._turn_clock is not None:  # device-resident {tick, slot}: advance them in stream order
+            from ._abi import check
+
+            check(self.engine.lib.sb_clock_advance(self._turn_clock.tensor.data_ptr(), 1, 1, self.buffer.capacity,
+                                                   torch.cuda.current_stream(self.engine.device).cuda_stream),
+                  "sb_clock_advance")
+
+    def _after_turn(self) -> None:
+        """Host bookkeeping of one finished turn."""
+        self.turn += 1
         self.buffer.advance(1)
+        if self._turn_clock is not None:
+            held = self._turn_clock.held
+            self._turn_clock.held = [(held[0] + 1) & 0xFFFFFFFF, (held[1] + 1) % self.buffer.capacity]
+
+    def _sync_turn_clock(self) -> None:
+        """Bring the device clock in line with the host (after reset / add_empty / eager turns)."""
+        from ._abi import check
+
+        want = [(self.engine.tick + 1) & 0xFFFFFFFF, self.buffer.idx]
+        held = self._turn_clock.held
+        if want != held:
+            cap = self.buffer.capacity
+            check(self.engine.lib.sb_clock_advance(self._turn_clock.tensor.data_ptr(), (want[0] - held[0]) & 0xFFFFFFFF,
+                                                   (want[1] - held[1]) % cap, cap,
+                                                   torch.cuda.current_stream(self.engine.device).cuda_stream),
+                  "sb_clock_advance")
+            self._turn_clock.held = want
+
+    def enable_turn_graph(self) -> None:
+        """Live policies (anything but the in-kernel `RandomModel`): capture ONE WHOLE TURN -- for every agent slot in
+        list order [sweep +] observe, frame stacking, `model.take_action`, act -- as a CUDA graph, with the tick and
+        the ring slot kept in device memory.  `take_turn()` then is one graph replay: an on-GPU policy runs with no
+        host work between the phases, exactly in the order of Agent.transition (agents/agent.py:155-173).
+
+        Requirements: every model's `take_action` must be capturable (device tensors in, device tensor out, no host
+        synchronisation, static shapes).  Observations reach the policy through one fixed tensor (the kernel writes
+        each row to its ring slot AND there), frame stacks through `Buffer.current_state()`'s device-clock form."""
+        from .graphs import DeviceClock
+
+        if self._fusable:
+            raise RuntimeError("in-kernel policies are fused already: use enable_graphs() / take_turns()")
+        eng = self.engine
+        A = len(self.agents)
+        self._turn_clock = DeviceClock(eng.device)
+        self.buffer.device_clock = self._turn_clock
+        self._obs_fixed = torch.zeros((1, eng.N, A, eng.spec.obs_size), dtype=torch.float32, device=eng.device)
+        # one eager turn in this mode first: CUDA loads modules lazily and that cannot be captured
+        self._sync_turn_clock()
+        self._take_turn_split()
+        self._after_turn()
+        torch.cuda.synchronize(eng.device)
+        tick = eng.tick
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._take_turn_split()
+        eng.tick = tick  # capturing ran the host-side tick bookkeeping of a turn that was not executed
+        self._turn_graph = graph
 
     def take_turns(self, num_turns: int, rng: str = "philox") -> None:
         """`num_turns` x take_turn() in ONE launch (in-kernel policies only).  `rng`: "philox" draws one random byte
@@ -175,12 +247,15 @@ class Environment:
     # -- split-phase plumbing used by Agent.pov / Agent.act ----------------------------------------
     def _observe_slot(self, k: int) -> torch.Tensor:
         eng = self.engine
+        extra = {} if self._turn_clock is None else {"obs_out": self._obs_fixed, "clock": self._turn_clock}
         if k == 0 and not self._turn_open:
-            eng.phase(sweep=True, obs_agent=0, buffer=self.buffer, new_turn=True)
+            eng.phase(sweep=True, obs_agent=0, buffer=self.buffer, new_turn=True, **extra)
             self._turn_open = True
         elif k > 0 and self._pending_obs != k:
-            eng.phase(obs_agent=k, buffer=self.buffer)
+            eng.phase(obs_agent=k, buffer=self.buffer, **extra)
         self._pending_obs = None
+        if self._obs_fixed is not None:  # fixed address: usable inside a captured graph
+            return self._obs_fixed[0, :, k]
         A = len(self.agents)
         return self.buffer.states[k::A, self.buffer.idx].reshape(eng.N, -1)
 
@@ -194,9 +269,10 @@ class Environment:
             act = act.expand(eng.N)
         self._action_slot[0, :, k] = act
         nxt = k + 1 if k + 1 < A else -1
+        extra = {} if self._turn_clock is None else {"obs_out": self._obs_fixed, "clock": self._turn_clock}
         # act agent k and, in the same launch, observe agent k+1 (it must see k's move)
         eng.phase(act_agent=k, obs_agent=nxt, buffer=self.buffer, actions=self._action_slot,
-                  reward_out=self._reward_slot)
+                  reward_out=self._reward_slot, **extra)
         self._pending_obs = nxt if nxt >= 0 else None
         return self._reward_slot[0, :, k]
 

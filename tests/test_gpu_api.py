@@ -521,3 +521,45 @@ def test_uint8_action_tapes_equal_int32(A, H, lpe, cuda_device):
         assert torch.equal(outs[mode][1], outs["i32"][1]) and torch.equal(outs[mode][2], outs["i32"][2])
         for k in (1, 2):
             assert torch.equal(outs[mode][3][k], outs["i32"][3][k])
+
+
+def test_turn_graph_equals_eager_split_phase(cuda_device):
+    """`Environment.enable_turn_graph()`: one whole split-phase turn (per agent slot: observe, frame stacking, the
+    policy, act) captured as a CUDA graph with device-resident tick / ring slot.  Replays must equal the eager
+    split-phase path turn for turn, across episode boundaries (reset, add_empty) and a ring wrap."""
+    from sorrel_b200.models import BaseModel
+
+    class ObsPolicy(BaseModel):
+        """capturable: action = (number of non-zero entries in the stacked frames) mod 4"""
+
+        def take_action(self, state):
+            return (state != 0).sum(dim=1).to(torch.int32) % 4
+
+    N, seed = 24, 17
+    envs = []
+    for graph in (False, True):
+        env, _ = _make(N, seed, model_factory=lambda inp, na: ObsPolicy(inp, na, memory_size=16, n_frames=3))
+        env.add_empty()
+        for _ in range(3):
+            env.take_turn()  # eager turns first: the graph starts from a non-trivial clock
+        if graph:
+            env.enable_turn_graph()  # (runs one eager turn itself, then captures)
+        else:
+            env.take_turn()
+        for _ in range(9):
+            env.take_turn()
+        env.reset()
+        env.add_empty()
+        for _ in range(11):  # 3 + 1 + 9 + 2 (add_empty) + 11 > 16: the ring wraps
+            env.take_turn()
+        env.engine.check_errors()
+        envs.append(env)
+    e, g = envs
+    assert g._turn_graph is not None
+    assert (e.turn, e.engine.tick, e.buffer.idx, e.buffer.size) == (g.turn, g.engine.tick, g.buffer.idx, g.buffer.size)
+    assert torch.equal(e.engine.grid, g.engine.grid) and torch.equal(e.engine.agent_pos, g.engine.agent_pos)
+    assert torch.equal(e.engine.total_reward, g.engine.total_reward)
+    assert torch.equal(e.buffer.states, g.buffer.states) and torch.equal(e.buffer.actions, g.buffer.actions)
+    assert torch.equal(e.buffer.rewards, g.buffer.rewards)
+    assert torch.equal(e.buffer.extra_data["positions"], g.buffer.extra_data["positions"])
+    assert int((e.buffer.actions != 0).sum()) > 0  # the policy did act
