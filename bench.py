@@ -44,6 +44,8 @@ PRESETS = {
     "4obs19": dict(obs_study=True, envs_total=4096, agents=64, size=128, vision=9),
     "5": dict(),
     "cleanup": dict(world="cleanup", agents=10, vision=5, envs_total=32768, turns=25, capacity=8),
+    # live (on-GPU, not in-kernel) policy: one split-phase turn per take_turn(), eager launches vs the turn graph
+    "live": dict(live=True, turns=1, n_frames=1),
 }
 
 
@@ -80,6 +82,9 @@ def parse_args():
                          "21x31x3, 10 agents, 11x11 one-hot view + positional code, beams, column rules)")
     ap.add_argument("--obs-study", action="store_true",
                     help="config 4: time the standalone observation kernel (sb_observe) against the HBM roofline")
+    ap.add_argument("--live", action="store_true",
+                    help="live-policy cadence: Environment.take_turn() through the split-phase launches with a device "
+                         "policy between observe and act, eager and as one CUDA graph per turn")
     ap.add_argument("--actions-i32", action="store_true", help="e2e: ship int32 actions instead of uint8")
     ap.add_argument("--no-numa", action="store_true", help="diagnostic: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--lpe", type=int, default=0, help="diagnostic: pin the lanes per instance (SbStepArgs.tune_lpe)")
@@ -606,10 +611,81 @@ def run_obs_study(a):
     }), flush=True)
 
 
+def run_live(a):
+    """Item 9 of the round-1 review: a policy that is NOT evaluated in-kernel (any torch module on the GPU) forces one
+    turn per take_turn().  Times Environment.take_turn() with a trivial device policy, eagerly and through
+    Environment.enable_turn_graph()."""
+    import torch
+
+    from sorrel_b200.models import BaseModel
+
+    class DevicePolicy(BaseModel):
+        """uniform random actions drawn by torch on the device (stands in for a network)"""
+
+        def take_action(self, state):
+            return torch.randint(0, self.action_space, (state.shape[0],), dtype=torch.int32, device=state.device)
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    N, A = a.envs_total, a.agents
+    out = {}
+    for mode in ("eager", "graph"):
+        env = make_env(a, N, dev)
+        for ag in env.agents:  # swap the in-kernel RandomModel for the device policy
+            m = DevicePolicy(ag.model.input_size, ag.model.action_space, ag.model.memory_size, n_frames=a.n_frames)
+            m.memory = ag.model.memory
+            ag.model = m
+        env._fusable = False
+        env.add_empty()
+        for _ in range(3):
+            env.take_turn()
+        if mode == "graph":
+            env.enable_turn_graph()
+        clocks = None if (a.no_clocks or mode == "eager") else ClockSampler(dev.index or 0, period=0.01)
+        turns = max(a.steps, 100)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        done = 0
+        while done < turns:
+            if env.turn >= a.max_turns:
+                env.begin_epoch()
+            env.take_turn()
+            done += 1
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms = max(e0.elapsed_time(e1), 1e3 * (t1 - t0)) / turns
+        out[mode] = {"ms_per_turn": ms, "value": N * A / (ms * 1e-3), "clocks": clocks.stop(t0, t1) if clocks else None}
+        env.engine.check_errors()
+        del env
+        torch.cuda.empty_cache()
+    peak, peak_src = hbm_peak()
+    alg = alg_bytes_per_env_step(a) * N
+    g = out["graph"]
+    print(json.dumps({
+        "metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": 1, "steps": max(a.steps, 100), "warmup": 3,
+        "ms_per_step": g["ms_per_turn"], "higher_is_better": True, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a) + ", live device policy (torch.randint) between observe and act",
+                   "api": "Environment.take_turn() (split-phase: Agent.pov / get_action / act) as one CUDA graph per "
+                          "turn (Environment.enable_turn_graph)",
+                   "l2": "inputs larger than L2" if N * A * 600 > 256e6 else "working set fits L2 at this batch size"},
+        "roofline": {"bound": "hbm", "achieved": alg / (g["ms_per_turn"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (g["ms_per_turn"] * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel": "split-phase sb::step_kernel launches + policy", "peak_source": peak_src,
+                     "note": "whole turn incl. the policy's torch kernels and the second copy of every row the policy "
+                             "reads"},
+        "eager": out["eager"], "gpu_launches": None, "clocks": g["clocks"],
+    }), flush=True)
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.live:
+        run_live(a)
     elif a.obs_study:
         run_obs_study(a)
     else:

@@ -281,6 +281,8 @@ class Buffer:
         if self.device_clock is not None:
             if self._cs_fixed is None:
                 self._cs_fixed = torch.zeros((self.rows, F1, *self.obs_shape), dtype=torch.float32, device=self.device)
+            if F1 == 0:  # no stacking: zero rows, like states[idx:idx]
+                return self._cs_fixed
             check(self.lib.sb_buffer_current_state_dev(C.byref(self.desc()), self.device_clock.tensor.data_ptr(),
                                                        self._cs_fixed.data_ptr(), self._stream()),
                   "sb_buffer_current_state_dev")
