@@ -52,7 +52,12 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
 
 
 def raw(name):
@@ -112,16 +117,24 @@ tot, p2 = lines("step_kernel")
 print(p2, "warp instructions:", tot)
 ds, ps = raw("sample_kernel")
 print(ps)
-if d:
-    def num(key):
-        v, u = d[key]
-        v = float(v.replace(",", ""))
-        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}.get(u, 1)
-    traffic = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-    json.dump({"step_kernel_dram_bytes_per_launch": traffic, "tag": tag, "envs_per_gpu": 1048576, "turns": 25,
-               "agents": 1, "size": 21,
-               "note": "dram__bytes_read.sum + dram__bytes_write.sum of one sb::step_kernel launch, ncu --set "
-                       "full, default bench.py workload on 1 GPU",
-               "grid_size": d["launch__grid_size"][0], "duration": d["gpu__time_duration.sum"]},
-              open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
-    print("traffic bytes/launch", traffic)
+# per-shape DRAM traffic (bench.py `roofline.traffic` / `frac_dram`): profiles/traffic.json, keyed by bench.shape_key
+SHAPES = {"step_kernel": "treasurehunt:21:1:v2:n1048576:t25:c32:philox",
+          "sparse_kernel": "treasurehunt:21:1:v2:n1048576:t25:c32:sparse",
+          "c3_kernel": "treasurehunt:21:8:v2:n16384:t25:c32:philox",
+          "c4_kernel": "treasurehunt:128:64:v4:n2048:t10:c16:philox",
+          "cleanup_kernel": "cleanup:21:10:v5:n32768:t25:c8:philox"}
+tpath = os.path.join(out_dir, "traffic.json")
+t = json.load(open(tpath)) if os.path.exists(tpath) else {"step_kernel_dram_bytes_per_launch": {}, "source": {}}
+for name, key in SHAPES.items():
+    dd, dst = raw(name)
+    if not dd:
+        continue
+    lines(name)
+
+    def num(k):
+        v, u = dd[k]
+        return float(v.replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}.get(u, 1)
+    t["step_kernel_dram_bytes_per_launch"][key] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    t["source"][key] = os.path.relpath(dst, ROOT)
+    print(name, key, t["step_kernel_dram_bytes_per_launch"][key])
+json.dump(t, open(tpath, "w"), indent=1)
