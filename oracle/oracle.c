@@ -159,6 +159,14 @@ static inline void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
   out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
 }
 
+/* The engine's keyed stream (sb_core.cuh sb_philox_rk): FIXED key, the 64-bit seed folded into counter words 1, 3. */
+#define PHILOX_K0 0xA4093822u
+#define PHILOX_K1 0x299F31D0u
+static inline void draw(uint32_t env, uint32_t tick, uint32_t index, uint32_t domain, uint32_t s0, uint32_t s1,
+                        uint32_t out[4]) {
+  philox(env, tick ^ s0, index, domain ^ s1, PHILOX_K0, PHILOX_K1, out);
+}
+
 static inline uint32_t bounded64(uint32_t hi, uint32_t lo, uint32_t n) {
   return (uint32_t)(((unsigned __int128)(((uint64_t)hi << 32) | lo) * n) >> 64);
 }
@@ -314,7 +322,7 @@ static void reset_range(or_env_t* e, int64_t n0, int64_t n1) {
         uint32_t env = env_id_of(e, n), j = (uint32_t)(gi + 1) << 24, r[4];
         for (int a = 0; a < cnt; ++a) {
           for (;;) {
-            philox(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
+            draw(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
             int32_t cand = (int32_t)bounded64(r[0], r[1], (uint32_t)nc);
             int dup = 0;
             for (int b = 0; b < a; ++b) dup |= gp[b] == cand;
@@ -335,7 +343,7 @@ static void reset_range(or_env_t* e, int64_t n0, int64_t n1) {
       uint32_t env = env_id_of(e, n), j = 0, r[4];
       for (int a = 0; a < w->A; ++a) {
         for (;;) {
-          philox(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
+          draw(env, e->tick + 1, j++, DOM_RESET, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), r);
           int32_t cand = (int32_t)bounded64(r[0], r[1], (uint32_t)w->n_spawnable);
           int dup = 0;
           for (int b = 0; b < a; ++b) dup |= picks[b] == cand;
@@ -405,13 +413,13 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
          j = 1, 2, ...; a hit spawns iff the cell (still) carries the spawn rule. */
       uint32_t r[4];
       const uint32_t n_cells = (uint32_t)tape_stride;
-      philox(env, tick, 0u, DOM_SPARSE, k0, k1, r);
+      draw(env, tick, 0u, DOM_SPARSE, k0, k1, r);
       const uint64_t u = ((uint64_t)r[0] << 32) | r[1];
       int K = 0;
       while (K < OR_SPARSE_KMAX && u >= e->cdf[K]) ++K;
       uint32_t hits[OR_SPARSE_KMAX], j = 1;
       for (int got = 0; got < K;) {
-        philox(env, tick, j++, DOM_SPARSE, k0, k1, r);
+        draw(env, tick, j++, DOM_SPARSE, k0, k1, r);
         const uint32_t pos = bounded64(r[0], r[1], n_cells);
         int dup = 0;
         for (int h = 0; h < got; ++h) dup |= hits[h] == pos;
@@ -467,11 +475,11 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
               const uint32_t hi = (uint32_t)((thr - 1) >> 45);
               for (n2 = 1; n2 < hi + 1u; n2 <<= 1) ++lg;
             }
-            philox(env, tick, pcell >> 4, DOM_SWEEP, k0, k1, r);
+            draw(env, tick, pcell >> 4, DOM_SWEEP, k0, k1, r);
             uint32_t b = pcell & 15, r8 = (r[b >> 2] >> (8 * (b & 3))) & 0xFF;
             int hit = r8 < n2; /* level 1 */
             if (hit) {         /* level 2: 64 fresh bits below thr << (19 - log2 n2) */
-              philox(env, tick, pcell, DOM_CELL, k0, k1, r);
+              draw(env, tick, pcell, DOM_CELL, k0, k1, r);
               hit = ((((uint64_t)r[0] << 32) | r[1]) <= (thr << (19 - lg)) - 1ull);
             }
             if (!hit) {
@@ -495,7 +503,7 @@ static void step_env(or_env_t* e, int64_t n, int T, int t_base) {
         action = (int)np_randint(mt, (uint32_t)w->n_actions); /* RandomModel, base_model.py:111 */
       } else {
         uint32_t r[4];
-        philox(env, tick, (uint32_t)a, DOM_ACTION, k0, k1, r);
+        draw(env, tick, (uint32_t)a, DOM_ACTION, k0, k1, r);
         action = (int)bounded64(r[0], r[1], (uint32_t)w->n_actions);
       }
       if (e->record) e->tape_a[((size_t)(t_base + t) * e->N + n) * w->A + a] = action;

@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(SB_THREADS)
   if (active && lane == 0) {
     uint8_t* plane = grid + (size_t)env * d.env_stride + (size_t)d.agent_plane * d.plane_stride;
     const uint32_t envid = (uint32_t)(d.env_id_base + (uint64_t)env);
+    const uint32_t sk[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     // item groups first, in order (cleanup/env.py:126-132: apples before agents)
     for (int g = 0; g < groups.n; ++g) {
       uint8_t* gp = grid + (size_t)env * d.env_stride + (size_t)groups.plane[g] * d.plane_stride;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(SB_THREADS)
           cell = groups.cells[g][groups.placement[g][(size_t)env * groups.count[g] + i]];
         } else {
           for (;;) {
-            SbU4 w = sb_philox(envid, tick, jg++, SB_DOM_RESET, (uint32_t)seed, (uint32_t)(seed >> 32));
+            SbU4 w = sb_philox_rk(envid, tick, jg++, SB_DOM_RESET, sk);
             cell = groups.cells[g][sb_bounded(w.x, w.y, (uint32_t)groups.n_cells[g])];
             if (gp[cell] != (uint8_t)groups.kind[g]) break;
           }
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(SB_THREADS)
       } else {
         // sequential rejection: uniform over the spawnable cells not taken yet
         for (;;) {
-          SbU4 w = sb_philox(envid, tick, j++, SB_DOM_RESET, (uint32_t)seed, (uint32_t)(seed >> 32));
+          SbU4 w = sb_philox_rk(envid, tick, j++, SB_DOM_RESET, sk);
           cell = spawnable[sb_bounded(w.x, w.y, (uint32_t)n_spawnable)];
           if (plane[cell] != (uint8_t)d.agent_kind && (d.agent_kind_alt < 0 || plane[cell] != (uint8_t)d.agent_kind_alt))
             break;

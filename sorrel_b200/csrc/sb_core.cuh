@@ -93,6 +93,10 @@ struct SbU4 {
   uint32_t x, y, z, w;
 };
 
+#if !defined(__CUDA_ARCH__)
+static inline uint32_t sb_host_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+#define __umulhi sb_host_umulhi
+#endif
 SB_HD void sb_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
   const uint64_t p = (uint64_t)a * (uint64_t)b;  // mul.wide.u32 -> one IMAD.WIDE.U32
   lo = (uint32_t)p;
@@ -122,24 +126,25 @@ SB_HD SbU4 sb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_
   return o;
 }
 
-// Same function with the 10 round keys (k + r*W) precomputed: rk[2r], rk[2r+1].  The kernels pass a
-// pointer into their __grid_constant__ parameters, so every key is a constant-bank operand of the
-// XOR and the key schedule costs no instructions.
-SB_HD void sb_philox_round_keys(uint32_t k0, uint32_t k1, uint32_t rk[20]) {
-  for (int r = 0; r < 10; ++r) {
-    rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
-    rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
-  }
-}
-
-SB_HD SbU4 sb_philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* __restrict__ rk) {
+// The engine's keyed stream: Philox4x32-10 with a FIXED key (the first 64 fractional bits of pi, as in the Random123
+// examples) and the 64-bit SEED folded into counter words 1 and 3:
+//     draw(env, tick, index, domain) = Philox4x32-10((env, tick ^ seed_lo, index, domain ^ seed_hi), K)
+// Every (seed, env, tick, index, domain) still maps to its own counter -- Philox is a bijection of the 128-bit counter
+// for a fixed key, so distinct counters give distinct, statistically independent outputs -- but the ten round keys are
+// now COMPILE-TIME constants: immediates of the XORs instead of twenty `LDC` loads (or twenty registers) per pair of
+// calls in the sweep loop, which sits at the 64-register cap.  `sk` = {seed_lo, seed_hi}; the kernels pass a pointer
+// into their __grid_constant__ parameters, so both XORs are loop-invariant uniform operations.
+#define SB_PHILOX_K0 0xA4093822u
+#define SB_PHILOX_K1 0x299F31D0u
+SB_HD SbU4 sb_philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* __restrict__ sk) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  c1 ^= sk[0];
+  c3 ^= sk[1];
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    uint32_t hi0, lo0, hi1, lo1;
-    sb_mulhilo(M0, c0, hi0, lo0);
-    sb_mulhilo(M1, c2, hi1, lo1);
-    uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    const uint32_t k0 = SB_PHILOX_K0 + (uint32_t)r * 0x9E3779B9u, k1 = SB_PHILOX_K1 + (uint32_t)r * 0xBB67AE85u;
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0, hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
     c0 = n0;
     c1 = lo1;
     c2 = n2;

@@ -43,7 +43,7 @@ struct StepParams {
   int32_t agent_words;                            // 32-bit words of per-instance agent state (yx, facing, reward, actions)
   int32_t act_turns;                              // turns whose actions are prepared at once (action window rows)
   uint32_t inv_A;                                 // ceil(65536 / A)
-  uint32_t rk[20];                                // Philox round keys of a.seed (constant-bank operands)
+  uint32_t rk[2];                                 // {seed_lo, seed_hi}: the stream words of sb_philox_rk
 };
 
 int note_cuda_error(cudaError_t e);  // records the error text for sb_last_cuda_error, returns SB_ECUDA

@@ -313,6 +313,9 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
 // 128-bit stores.  Config 4 (128x128, 64 agents, 9x9 window): 1944 B written per pair.
 // ----------------------------------------------------------------------------------------------
 constexpr int OBS_THREADS = 256;
+#ifndef SB_OBS_ROWWISE
+#define SB_OBS_ROWWISE 1
+#endif
 #ifndef SB_OBS_MINB
 #define SB_OBS_MINB 6  // resident blocks per SM the register allocation is sized for (40 registers)
 #endif
@@ -321,7 +324,10 @@ constexpr int OBS_THREADS = 256;
 // pairs so that (env, agent) advance incrementally (no divisions in the loop), the agents of one
 // instance are served back to back (its planes stay in L1) and consecutive rows land in the same DRAM
 // pages.
-template <bool NP1, int LANES>
+// ROWS: gather the window row by row (scatter_rows_onehot) from the planes in global memory.  The row gather may touch
+// a few bytes before / after an instance's planes, so the first and the last instance of the batch (whose neighbours
+// are outside the allocation) take the cell-wise path; the choice is made per warp (both halves agree).
+template <bool NP1, int LANES, bool ROWS = false>
 __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
     observe_kernel(const __grid_constant__ SbDev d, const uint8_t* __restrict__ grid,
                    const int32_t* __restrict__ agent_pos, float* __restrict__ out, int stage_bytes, int fast,
@@ -356,8 +362,14 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
     const uint8_t* genv = grid + (size_t)(valid ? env : 0) * d.env_stride;
     float* dst = valid ? out + (size_t)pair * d.obs_size : nullptr;
     if (fast) {
-      // window loads batched: 2 per lane cover a 5x5 window with 16 lanes, 4 per lane a 9x9 / 11x11 one with 32
-      emit_onehot_row<LANES, NP1, (LANES == 16 ? 2 : 4)>(d, genv, ktab, stage_raw, y, x, dst, lane);
+      bool rows = false;
+      if constexpr (ROWS) rows = __all_sync(0xFFFFFFFFu, !valid || (env > 0 && env + 1 < (unsigned long long)d.N));
+      if (ROWS && rows) {
+        emit_onehot_row<LANES, NP1, 1, true>(d, genv, ktab, stage_raw, y, x, dst, lane);
+      } else {
+        // window loads batched: 2 per lane cover a 5x5 window with 16 lanes, 4 per lane a 9x9 / 11x11 one with 32
+        emit_onehot_row<LANES, NP1, (LANES == 16 ? 2 : 4)>(d, genv, ktab, stage_raw, y, x, dst, lane);
+      }
       __syncwarp();
     } else if (valid) {
       for (int e = lane; e < d.oh_size; e += LANES) {
@@ -382,7 +394,10 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
 
 int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos, float* out, cudaStream_t s) {
   const bool np1 = d.fast_obs && d.n_planes == 1;
-  const int lanes = d.obs_size <= 256 ? 16 : 32;  // small rows: two pairs per warp
+  // row-wise window gather (one lane per window row) when the rows fit the 16 lanes of a half warp
+  // (measured: 9x9 windows 0.589 -> 0.608 of the HBM peak, 5x5 windows 0.72 -> 0.70: only for the wider ones)
+  const bool rows = np1 && d.rowwise_ok && d.S >= 7 && d.S <= 16 && SB_OBS_ROWWISE;
+  const int lanes = (d.obs_size <= 256 || rows) ? 16 : 32;  // two pairs per warp / one
   const int groups = OBS_THREADS / lanes;
   const int stage_bytes = round_up((d.obs_size + 4) * (np1 ? 2 : 4), 16);
   const int smem = round_up(2 * d.SS, 16) + 4 * SB_KTAB_WORDS + groups * stage_bytes;
@@ -409,6 +424,7 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
     count_launch();
     return check_launch();
   };
+  if (rows) return launch(observe_kernel<true, 16, true>);
   if (lanes == 16) return np1 ? launch(observe_kernel<true, 16>) : launch(observe_kernel<false, 16>);
   return np1 ? launch(observe_kernel<true, 32>) : launch(observe_kernel<false, 32>);
 }
@@ -1226,7 +1242,7 @@ static bool block_kernel_applies(const SbDev& d, const StepParams& p, int kr) {
 
 static int launch_block(const SbDev& d, StepParams p, cudaStream_t s, SbStepPlan* plan) {
   const BlockLayout L = block_layout(d);
-  sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
+  p.rk[0] = (uint32_t)p.a.seed, p.rk[1] = (uint32_t)(p.a.seed >> 32);  // the stream words of sb_philox_rk
   p.inv_A = (65536u + (uint32_t)d.A - 1u) / (uint32_t)d.A;
   p.staged = 1, p.par = 1;
   if (plan) {
@@ -1251,7 +1267,7 @@ template <int LPE, int RNG, bool NP1>
 static int launch_one(const SbDev& d, StepParams p, cudaStream_t s, SbStepPlan* plan) {
   const bool staged = stage_planes(d, p.a.tune_staged);
   const SmemLayout L = smem_layout(d, SB_THREADS, LPE, NP1, staged, RNG == SB_K_SPARSE);
-  sb_philox_round_keys((uint32_t)p.a.seed, (uint32_t)(p.a.seed >> 32), p.rk);
+  p.rk[0] = (uint32_t)p.a.seed, p.rk[1] = (uint32_t)(p.a.seed >> 32);  // the stream words of sb_philox_rk
   p.q_off = L.q_off, p.planes_off = L.planes_off, p.pos_off = L.pos_off, p.stage_off = L.stage_off;
   p.plane_env = L.plane_env, p.stage_env = L.stage_env, p.hits_off = L.hits_off;
   p.stage_row = L.stage_row;

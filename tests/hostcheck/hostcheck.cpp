@@ -13,9 +13,8 @@ extern "C" {
 void hc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, uint32_t* out_rk) {
   SbU4 r = sb_philox(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
   out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
-  uint32_t rk[20];
-  sb_philox_round_keys(key[0], key[1], rk);
-  SbU4 q = sb_philox_rk(ctr[0], ctr[1], ctr[2], ctr[3], rk);
+  // the engine's keyed stream: fixed key, `key` folded into counter words 1 and 3
+  SbU4 q = sb_philox_rk(ctr[0], ctr[1], ctr[2], ctr[3], key);
   out_rk[0] = q.x, out_rk[1] = q.y, out_rk[2] = q.z, out_rk[3] = q.w;
 }
 
@@ -56,8 +55,7 @@ int hc_resolve_candidate(double p, int n_choices, uint32_t env, uint32_t tick, u
   SbDev d;
   memset(&d, 0, sizeof d);
   set_prob(&d, p, n_choices);
-  uint32_t rk[20];
-  sb_philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), rk);
+  const uint32_t rk[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   // level 1 the way the sweep evaluates it (byte (cell & 15) of the chunk's call), then the resolver = level 2
   const SbU4 r = sb_philox_rk(env, tick, cell >> 4, SB_DOM_SWEEP, rk);
   if (sb_byte_of(r, (int)(cell & 15u)) >= d.n2) return -1;
@@ -65,7 +63,8 @@ int hc_resolve_candidate(double p, int n_choices, uint32_t env, uint32_t tick, u
 }
 
 uint32_t hc_action(uint32_t env, uint32_t tick, uint32_t agent, uint32_t n_actions, uint64_t seed) {
-  SbU4 w = sb_philox(env, tick, agent, SB_DOM_ACTION, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t sk[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  SbU4 w = sb_philox_rk(env, tick, agent, SB_DOM_ACTION, sk);
   return sb_bounded(w.x, w.y, n_actions);
 }
 
@@ -104,8 +103,7 @@ double hc_obs_general(const uint8_t* planes, const uint8_t* tmpl, const double* 
 // way the generic sweep does: byte (cell & 15) of Philox(env, tick, cell >> 4, SWEEP))
 int hc_bernoulli_hit(double p, uint32_t env, uint32_t tick, uint32_t cell, uint64_t seed) {
   const uint64_t thr = !(p > 0.0) ? 0 : (p >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(p, 53)));
-  uint32_t rk[20];
-  sb_philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), rk);
+  const uint32_t rk[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   const SbU4 r = sb_philox_rk(env, tick, cell >> 4, SB_DOM_SWEEP, rk);
   const uint32_t n2 = sb_level1_bound(thr);
   return sb_bernoulli_hit(n2, sb_level2_bound(thr, n2), sb_byte_of(r, (int)(cell & 15u)), env, tick, cell, rk) ? 1 : 0;

@@ -48,7 +48,12 @@ def test_philox_known_answers_and_round_key_variant(hc):
         o1, o2 = np.zeros(4, dtype=np.uint32), np.zeros(4, dtype=np.uint32)
         hc.hc_philox(c.ctypes.data, k.ctypes.data, o1.ctypes.data, o2.ctypes.data)
         ref = R.philox4x32_10(ctr, key)
-        assert tuple(int(x) for x in o1) == ref and tuple(int(x) for x in o2) == ref
+        assert tuple(int(x) for x in o1) == ref  # plain Philox4x32-10 (Random123 known answers above)
+        # the engine's keyed stream: fixed key, the seed words folded into counter words 1 and 3
+        seeded = R.philox4x32_10((ctr[0], ctr[1] ^ key[0], ctr[2], ctr[3] ^ key[1]), R.PHILOX_FIXED_KEY)
+        assert tuple(int(x) for x in o2) == seeded
+        d = R.PhiloxDraws(key[0] | (key[1] << 32))
+        assert d.px(*ctr) == seeded
 
 
 @pytest.mark.parametrize("p", [0.005, 0.05, 0.2, 0.49, 1e-4, 0.00390625])

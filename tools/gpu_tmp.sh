@@ -1,12 +1,7 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --config live > gpurun_out/ab22_live_1m.json 2> gpurun_out/ab22_live_1m.err || tail -5 gpurun_out/ab22_live_1m.err
-python bench.py --config live --envs-total 4096 > gpurun_out/ab22_live_4k.json 2> gpurun_out/ab22_live_4k.err || tail -5 gpurun_out/ab22_live_4k.err
-python bench.py --config live --envs-total 16384 --agents 8 > gpurun_out/ab22_live_c3.json 2> gpurun_out/ab22_live_c3.err || tail -5 gpurun_out/ab22_live_c3.err
-python - <<'PY'
-import json
-for f in ['ab22_live_1m','ab22_live_4k','ab22_live_c3']:
-    try:
-        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
-        print(f, 'graph %.3e (%.3f ms/turn, frac %.3f)  eager %.3e (%.3f ms/turn)'%(d['value'],d['ms_per_step'],d['roofline']['frac'],d['eager']['value'],d['eager']['ms_per_turn']))
-    except Exception as e: print(f,'ERR',e)
-PY
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+for C in 5 3 2 4; do
+python bench.py --config $C --no-e2e --no-cpu --steps 12 --warmup 4 > gpurun_out/ab24_main_c$C.json 2> gpurun_out/ab24_main_c$C.err
+done
+python tools/show_bench.py "gpurun_out/ab24_*.json"
