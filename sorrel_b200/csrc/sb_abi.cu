@@ -338,18 +338,21 @@ __global__ void buffer_add_kernel(SbBufferDesc b, int slot, const float* __restr
 }
 
 // dst_a[e] = src[e] for e < hi_a and dst_b[e - lo_b] = src[e] for e >= lo_b, e in [0, total): one pass over the source
-// run feeding two (overlapping) destinations.  Four loads per lane are issued before their stores, so a warp keeps
-// ~2 KB in flight (the plain load-store loop left the gather latency-bound at ~3.6 TB/s).
+// run feeding two (overlapping) destinations.  SB_COPY_DEPTH loads per lane are issued before their stores, so a
+// warp keeps several KB in flight (the plain load-store loop left the gather latency-bound at ~3.6 TB/s).
+#ifndef SB_COPY_DEPTH
+#define SB_COPY_DEPTH 4  // measured at config 5: 4 -> 0.89 ms, 8 -> 0.92 ms, 16 -> 1.37 ms
+#endif
 template <typename V>
 __device__ __forceinline__ void copy_run2(const V* __restrict__ src, V* __restrict__ dst_a, V* __restrict__ dst_b,
                                           int hi_a, int lo_b, int total, int lane) {
-  for (int e0 = lane; e0 < total; e0 += 128) {
-    V v[4];
+  for (int e0 = lane; e0 < total; e0 += 32 * SB_COPY_DEPTH) {
+    V v[SB_COPY_DEPTH];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < SB_COPY_DEPTH; ++u)
       if (e0 + 32 * u < total) v[u] = __ldg(src + e0 + 32 * u);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < SB_COPY_DEPTH; ++u) {
       const int e = e0 + 32 * u;
       if (e < total) {
         if (e < hi_a) dst_a[e] = v[u];

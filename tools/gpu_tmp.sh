@@ -1,7 +1,11 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-for C in 5 3 2 4; do
-python bench.py --config $C --no-e2e --no-cpu --steps 12 --warmup 4 > gpurun_out/ab24_main_c$C.json 2> gpurun_out/ab24_main_c$C.err
+for V in main mb7 mb6 copy4 copy16; do
+  if [ "$V" = main ]; then unset SB_LIB_PATH; else export SB_LIB_PATH=$GRAFT_REPO_ROOT/sorrel_b200/lib/variants/libsb_$V.so; fi
+  python bench.py --config 5 --no-e2e --no-cpu --no-alt --steps 12 --warmup 4 > gpurun_out/ab25_${V}.json 2> gpurun_out/ab25_${V}.err
 done
-python tools/show_bench.py "gpurun_out/ab24_*.json"
+unset SB_LIB_PATH
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/ab25_*.json')):
+    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, '%.3e'%d['value'], {k:round(v,3) for k,v in d['roofline']['breakdown_ms_per_step'].items()})
+PY
