@@ -1153,16 +1153,20 @@ __global__ void __launch_bounds__(BLK_THREADS, 6)
     }
 
     // ---- conflicting predecessors of every agent (start-of-turn positions) ------------------------
-    for (int a = tid; a < d.A; a += BLK_THREADS) {
+    // lane -> (agent a, half h): bits [32h, 32h + 32) of a's mask, i.e. predecessors j in that range -- all four warps
+    // work, 32 tests per lane, and the two halves are separate words (no reduction)
+    for (int e = tid; e < 2 * d.A; e += BLK_THREADS) {
+      const int a = e >> 1, h = e & 1;
       const uint32_t pa = spos[a];
       const int ya = (int)(pa >> 16), xa = (int)(pa & 0xFFFFu);
-      uint64_t m = 0;
-      for (int j = 0; j < a; ++j) {
+      uint32_t m = 0;
+      const int j_hi = min(a, 32 * h + 32);
+      for (int j = 32 * h; j < j_hi; ++j) {
         const uint32_t pj = spos[j];
         const int dy = ya - (int)(pj >> 16), dx = xa - (int)(pj & 0xFFFFu);
-        if (max(abs(dy), abs(dx)) <= d.par_radius) m |= 1ull << j;
+        if (max(abs(dy), abs(dx)) <= d.par_radius) m |= 1u << (j & 31);
       }
-      smask[a] = m;
+      reinterpret_cast<uint32_t*>(smask)[e] = m;  // little-endian halves of the 64-bit mask
     }
     __syncthreads();  // sweep writes, masks and the action window are visible to every warp
 

@@ -1,11 +1,5 @@
 cd $GRAFT_REPO_ROOT
-for V in main mb7 mb6 copy4 copy16; do
-  if [ "$V" = main ]; then unset SB_LIB_PATH; else export SB_LIB_PATH=$GRAFT_REPO_ROOT/sorrel_b200/lib/variants/libsb_$V.so; fi
-  python bench.py --config 5 --no-e2e --no-cpu --no-alt --steps 12 --warmup 4 > gpurun_out/ab25_${V}.json 2> gpurun_out/ab25_${V}.err
-done
-unset SB_LIB_PATH
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/ab25_*.json')):
-    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, '%.3e'%d['value'], {k:round(v,3) for k,v in d['roofline']['breakdown_ms_per_step'].items()})
-PY
+timeout 900 python -m pytest tests -m gpu -x -q -k "block_per or config4" 2>&1 | tail -3
+python bench.py --config 4 --no-e2e --no-cpu --no-alt --steps 12 --warmup 4 > gpurun_out/ab26_c4.json 2> gpurun_out/ab26_c4.err
+python bench.py --config 4 --envs-total 8192 --capacity 8 --no-e2e --no-cpu --no-alt --steps 8 --warmup 4 > gpurun_out/ab26_c4big.json 2> gpurun_out/ab26_c4big.err
+python tools/show_bench.py "gpurun_out/ab26_*.json"
