@@ -19,10 +19,8 @@ from sorrel_b200.engine import Engine  # noqa: E402
 dev = torch.device("cuda:0")
 
 
-def run(name, spec, N, T, rng="philox", env=None):
-    for k, v in (env or {}).items():
-        os.environ[k] = v
-    eng = Engine(util.engine_spec(spec), N, device=dev, seed=3)
+def run(name, spec, N, T, rng="philox", tuning=None):
+    eng = Engine(util.engine_spec(spec), N, device=dev, seed=3, tuning=tuning)
     buf = Buffer(8, (spec.obs_size,), n_frames=2, rows=N * spec.num_agents, device=dev, positions=(2,))
     eng.reset()
     eng.step(T, buffer=buf, rng=rng)
@@ -34,18 +32,18 @@ def run(name, spec, N, T, rng="philox", env=None):
     buf.current_state()
     eng.check_errors()
     torch.cuda.synchronize()
-    for k in (env or {}):
-        os.environ.pop(k)
-    print("ok", name, flush=True)
+    print("ok", name, eng.step_plan(T, rng=rng)["kernel"], flush=True)
 
 
 run("treasurehunt lpe4", R.treasurehunt_spec(), 37, 5)
 run("treasurehunt sparse", R.treasurehunt_spec(), 37, 5, rng="sparse")
 run("treasurehunt 8 agents lpe8", R.treasurehunt_spec(21, 21, 8, 2, 0.01), 21, 4)
 run("treasurehunt rgb (general path)", R.treasurehunt_spec(11, 11, 2, 2, 0.05, obs="rgb"), 9, 4)
-run("64x64 lpe32 par", R.treasurehunt_spec(64, 64, 16, 3, 0.01), 5, 4, env={"SB_LPE": "32"})
-run("64x64 unstaged par", R.treasurehunt_spec(64, 64, 16, 3, 0.01), 5, 4, env={"SB_STAGED": "0"})
+run("64x64 lpe32 par", R.treasurehunt_spec(64, 64, 16, 3, 0.01), 5, 4, tuning={"lpe": 32})
+run("64x64 unstaged par", R.treasurehunt_spec(64, 64, 16, 3, 0.01), 5, 4, tuning={"lpe": 32, "staged": -1})
+run("64x64 block per instance", R.treasurehunt_spec(64, 64, 16, 3, 0.01), 5, 4, tuning={"lpe": 128})
 run("128x128 config 4", R.treasurehunt_spec(128, 128, 64, 4, 0.005), 3, 2)
+run("torus", R.torus_spec(), 9, 4)
 run("cleanup", R.cleanup_spec(), 7, 4)
 run("iowa", R.iowa_spec(), 9, 4)
 run("tag", R.tag_spec(), 11, 4)
