@@ -1017,7 +1017,13 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
 // Only the treasurehunt-type fast path is compiled (one stored plane, one-hot rows, byte-SIMD Philox sweep, fused
 // mode, ring attached); everything else keeps using the warp-per-instance kernel.
 // ----------------------------------------------------------------------------------------------
-constexpr int BLK_THREADS = 128, BLK_SLOTS = 16, BLK_SL = 8;  // 16 agent slots of 8 lanes
+#ifndef SB_BLK_SPW
+#define SB_BLK_SPW 4  // agent slots per warp (of 8 lanes each): 4 = all lanes; 3 = 12 slots, smaller blocks (7 / SM)
+#endif
+#ifndef SB_BLK_MINB
+#define SB_BLK_MINB 6
+#endif
+constexpr int BLK_THREADS = 128, BLK_SPW = SB_BLK_SPW, BLK_SLOTS = 4 * BLK_SPW, BLK_SL = 8;
 
 struct BlockLayout {
   int q_off, plane_off, agent_off, mask_off, stage_off, stage_row, act_turns, total;
@@ -1031,7 +1037,7 @@ __host__ __device__ inline BlockLayout block_layout(const SbDev& d) {
   L.agent_off = L.plane_off + round_up(d.env_stride, 16) + 16;                // ... and after it (row-wise gathers)
   L.mask_off = L.agent_off + round_up(4 * (2 * d.A + L.act_turns * d.A), 16);  // yx, reward, action window
   L.stage_off = L.mask_off + round_up(8 * d.A, 16);
-  L.stage_row = pad64mod128((d.obs_size + 4) * 2);
+  L.stage_row = BLK_SPW == 4 ? pad64mod128((d.obs_size + 4) * 2) : round_up((d.obs_size + 4) * 2, 32);
   L.total = L.stage_off + BLK_SLOTS * L.stage_row;
   return L;
 }
@@ -1042,12 +1048,13 @@ __device__ __forceinline__ int nth_set_bit64(uint64_t m, int k) {  // position o
   return k < c ? (int)__fns(lo, 0u, k + 1) : 32 + (int)__fns((uint32_t)(m >> 32), 0u, k - c + 1);
 }
 
-__global__ void __launch_bounds__(BLK_THREADS, 6)
+__global__ void __launch_bounds__(BLK_THREADS, SB_BLK_MINB)
     step_kernel_block(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const BlockLayout L = block_layout(d);
   const int tid = threadIdx.x, warp = tid >> 5, wlane = tid & 31;
-  const int slot_id = warp * (32 / BLK_SL) + wlane / BLK_SL, sl = wlane % BLK_SL;
+  const bool has_slot = wlane / BLK_SL < BLK_SPW;  // (with 3 slots per warp the last 8 lanes only synchronise)
+  const int slot_id = warp * BLK_SPW + (has_slot ? wlane / BLK_SL : 0), sl = wlane % BLK_SL;
   const long long env = blockIdx.x;
   uint32_t* q = reinterpret_cast<uint32_t*>(smem_raw + L.q_off) + warp * (SB_QCAP + 1);
   uint8_t* plane = smem_raw + L.plane_off;
@@ -1181,7 +1188,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 6)
       const int n = __popcll(ready);
       for (int r0 = 0; r0 < n; r0 += BLK_SLOTS) {  // uniform trip count; a slot without an agent only synchronises
         const int k = r0 + slot_id;
-        const int a = k < n ? nth_set_bit64(ready, k) : -1;
+        const int a = (has_slot && k < n) ? nth_set_bit64(ready, k) : -1;
         uint32_t yx = a >= 0 ? spos[a] : 0u;
         float* dst = a >= 0 ? ring0 + (size_t)a * (size_t)p.buf.states_row_stride +
                                   (size_t)slot * (size_t)p.buf.states_slot_stride
