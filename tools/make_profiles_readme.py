@@ -1,0 +1,148 @@
+"""Regenerate the round-2 part of profiles/README.md from profiles/r02_shapes.jsonl and profiles/r02_scale_g*.json
+(the round-1 record below "# Round 1 record" is kept verbatim).  python tools/make_profiles_readme.py"""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+rows = [json.loads(l) for l in open(os.path.join(P, "r02_shapes.jsonl"))]
+old = open(os.path.join(P, "README.md")).read()
+r1 = old[old.index("# Round 1 record"):]
+tbl = ""
+for d in rows:
+    if d.get("eager"):
+        continue
+    r, s = d["roofline"], d.get("sparse_rng") or {}
+    w = d["config"]["workload"].split(", ring")[0].split(", C=")[0][:100]
+    fd, sk = r.get("frac_dram"), s.get("kernel_ms")
+    tbl += (f"| {w} | {d['value']:.3e} | {r['kernel_ms']:.3f} | {r['frac']:.3f} | {'' if fd is None else '%.3f' % fd} | "
+            f"{'' if not sk else '%.3f' % sk} | {(d.get('clocks') or {}).get('sm_mhz')} |\n")
+
+
+def live(envs, ag):
+    for d in rows:
+        if d.get("eager") and f"{envs} envs total" in d["config"]["workload"] and f"{ag} agent(s)" in d["config"]["workload"]:
+            return d
+
+
+l1, l4, l3 = live(1048576, 1), live(4096, 1), live(16384, 8)
+g = {n: json.load(open(os.path.join(P, f"r02_scale_g{n}.json"))) for n in (2, 4, 8)}
+one = next(d["value"] for d in rows if "1048576 envs total, 25 turns" in d["config"]["workload"] and not d.get("eager"))
+k1 = next(d["roofline"]["kernel_ms"] for d in rows
+          if "1048576 envs total, 25 turns" in d["config"]["workload"] and not d.get("eager"))
+
+
+def b(d):
+    return d["roofline"]["breakdown_ms_per_step"]
+
+
+def scale_row(n):
+    d = g[n]
+    return (f"| {n} | {d['value']:.3e} | {d['ms_per_step']:.3f} = {b(d)['step']:.3f} + {b(d)['sample']:.3f} + "
+            f"{b(d)['boundary']:.3f} | {d['value'] / n / one:.3f} | {d['e2e']['value']:.3e} |\n")
+
+
+head = f"""# profiles/ — ncu evidence
+
+All captures were taken on a B200 (sm_100a, 148 SMs, 1965 MHz, no throttle reasons) under `gpurun`, each only after the
+identical command had exited 0 without ncu, with `--clock-control none`.  Numbers printed by a run under ncu are never
+used as bench values; `bench.py` times with CUDA events.  **Round 2 first; the round-1 record follows unchanged.**
+
+## Round 2 (final build of the round)
+
+| file | what |
+|---|---|
+| `r02_launches.csv` | every kernel launched by `python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --no-graphs` (`ncu --metrics gpu__time_duration.sum`), aggregated per kernel: `sb::step_kernel<4,1,1,1>` 52.6 % of device time (6.28 ms per launch), the sparse sampler the same command times beside it 31.1 % (4.78 ms), `sb::buffer_sample_kernel` 12.7 % (0.85 ms), reset 0.5 %, reward stats 0.2 %.  Within the per-cell half of the run the step kernel is 0.87 of the step = `roofline.step_kernel_share_of_step` from CUDA events (0.87). |
+| `r02_step_kernel_metrics.csv`, `_source_lines.csv` | `ncu --set full` of one steady-state launch of the headline kernel (2^20 instances × 25 fused turns): 6.26 ms, 5.35e9 warp-instructions (round 1: 7.60 ms, 6.50e9), DRAM 17.16 GB written + 0.69 GB read (35 % of peak busy), issue slots 74 %, 62 registers, 8 blocks / SM from both limits |
+| `r02_step_kernel_sweep_loop.sass` | SASS of the sweep loop of the headline kernel (two Philox chains, level-1 filter, ballot queue push) |
+| `r02_sparse_kernel_*` | the same shape with the sparse sampler (`step_kernel<4,3,1,1>`) |
+| `r02_c3_kernel_*` | BASELINE config 3 at its named size (16384 × 8 agents, slot-major ring, `step_kernel<8,1,1,1>`) |
+| `r02_c4_kernel_*` | BASELINE config 4 at its named size (2048 × 128×128 × 64 agents): `sb::step_kernel_block` |
+| `r02_cleanup_kernel_*` | the cleanup example (`step_kernel<32,2,0,1>`) |
+| `r02_sample_kernel_metrics.csv` | `buffer_sample_kernel` after the batched-load rewrite |
+| `r02_shapes.jsonl` | one `bench.py` line per BASELINE shape (`tools/gpu_shapes.sh`, presets `--config 2|3|4|5|cleanup|4obs|4obs19`) and the three `--config live` lines, all with clocks sampled during the timed region |
+| `r02_scale_g2/4/8.json` | builder runs of `torchrun ... bench.py --gpus N` on one 8-GPU box |
+| `traffic.json` | DRAM bytes of one step-kernel launch per shape (`dram__bytes_read.sum + dram__bytes_write.sum` of the captures above) = `roofline.traffic`; `frac_dram = traffic / kernel time / peak` |
+| `reference_cpu_timings.json` | the UNMODIFIED reference timed in the build container (`python -m oracle.time_reference`) |
+
+### All shapes, one GPU (`r02_shapes.jsonl`; frac = algorithmic roofline, SURVEY §8d; frac_dram = measured DRAM traffic)
+
+| workload | agent-env-steps/s (obs/s for the obs study) | kernel ms | frac | frac_dram | sparse-sampler kernel ms | SM MHz |
+|---|---|---|---|---|---|---|
+{tbl}
+Round 1, same shapes: config 2 0.21 (T = 100) / 0.07 (T = 1); config 3 0.47 at 16384, 0.59 at 262144; config 4 0.46 at
+2048, 0.55 at 8192, 0.41 for 19×19 windows; config 5 0.81, 0.47 at T = 1; cleanup 0.48; observation study 0.66 / 0.72
+(config 4), 0.78 / 0.55 (5×5 windows; those launches are 0.2–0.4 ms: ±10 % between boxes).
+
+### What changed in the step kernel and what each change gave (2^20 × 25, `step_kernel<4,1,1,1>`, same command)
+
+| change | kernel time | note |
+|---|---|---|
+| round 1 final | 7.55 ms | 6.50e9 warp-instructions, issue slots 74 %, 7 blocks / SM (shared memory) |
+| the sparse sampler's hit list no longer allocated in the other variants | 7.45 ms | 8 blocks / SM |
+| ballot + popcount queue (no shared atomics, cold overflow drain), two chunks per trip; action window drawn by all lanes; ring scalars written one agent per lane | 6.89 ms | 5.93e9 warp-instructions |
+| row-wise window gather for groups of ≤ 8 lanes | 6.84 ms | sparse sampler: 5.33 → 4.88 ms |
+| two-level Bernoulli draw (one Philox call per candidate instead of two) | 6.51 ms | stream redefined in kernels and both oracles |
+| fixed Philox key, seed folded into the counter (round keys become immediates: no `LDC` / key registers in the loop) | **{k1:.2f} ms** | 5.35e9 warp-instructions; a first attempt through the generic `sb_philox(…, k0, k1)` made ptxas add zero-valued uniform registers to every product (6.68 ms) |
+| (experiment) no row stores at all | 6.89 ms (at the 6.84 ms build) | the stores are completely hidden behind the sweep |
+| (experiment) no sweep | 5.05 ms | then the stores bound the kernel: 17.2 GB / 5.05 ms = 3.4 TB/s of 600-byte pieces at a 19 KB stride |
+| (experiment) neither | 2.46 ms | instruction floor of observe + act + record |
+| (rejected) 2 lanes per instance | 7.34 ms | 64 instances per block: 4 blocks / SM |
+| (rejected) `__launch_bounds__(128, 7 / 6 / 5)` = 66 / 74 / 88 registers | 6.75 / 6.78 / 6.87 ms (at 6.84); 6.31 / 6.31 (at 6.28) | fewer rematerialisations, fewer warps: a wash |
+| (rejected) one row-gather loop with a per-group cell count instead of two instantiations | +3 % dense, +9 % sparse, +6 % config 3 | |
+
+### Ring layout (config 3, 16384 × 8 agents × 25 turns, `step_kernel<8,1,1,1>`)
+
+| ring `states` layout | kernel | frac |
+|---|---|---|
+| agent-major `[rows][capacity][obs]` (round 1) | 0.744 ms | 0.50 |
+| slot-major `[capacity][rows][obs]` (a turn's rows contiguous) | 0.543 ms | 0.69 |
+| + the later kernel changes | **0.516 ms** | **0.73** (frac_dram 0.60) |
+
+Same experiment at config 4: 1.041 → 0.985 ms; at config 5 (one agent per world): 6.84 → 6.77 ms dense, 4.88 → 4.83 ms
+sparse, while the sample gather prefers agent-major there — `Environment` picks slot-major only for multi-agent worlds.
+
+### Config 4: block per instance (`r02_c4_kernel_*`)
+
+`sb::step_kernel_block`, 2048 instances × 10 turns: 0.989 ms (one warp per instance, planes in L2, round-1 kernel on the
+same box) → **0.762 ms**; 8192 instances: 3.66 → 2.63 ms.  ncu: 78 registers, 36.9 KB shared memory per block, 6 blocks
+per SM, issue slots 59 %, `barrier` 2.2 stall cycles per issue (the level barriers), 2.6 GB written.  Rejected: 12 agent
+slots per block in 31 KB (7 blocks per SM: 2 waves instead of 2.3 at 2048 instances): 0.799 / 1.495 / 2.871 ms at 2048 /
+4096 / 8192 instances against 0.767 / 1.370 / 2.629.
+
+### Cleanup example (`r02_cleanup_kernel_*`, generic variant)
+
+12.7 ms per 25-turn launch (0.48 algorithmic, 0.44 of the peak in measured DRAM traffic: 36 GB of rows).  ncu before the
+shared-memory kind tables: 10.8e9 warp-instructions, lane efficiency 17 / 32, ADU pipe 45 % and 20 % of the stall
+samples on `d.channel[kind]` (twelve kinds: a constant-bank load with a divergent index is replayed once per distinct
+address); with the tables in shared memory (`sb_fill_kind_tables`) 13.8 → 13.1 ms, with the later kernel changes 12.7 ms.
+Still below the 0.60 bar: 363 window lookups per agent-turn (121 cells × 3 planes), agents strictly sequential (beams
+make every pair of the ten agents interact), `no_instruction` 2.0 stall cycles per issue (the EXT variants are large).
+
+### Sample gather (`buffer_sample_kernel`, config 5: 409 600 transitions of 5 stacked frames per step)
+
+round-1 loop (one load, two stores per trip): 1.08–1.20 ms → four loads in flight per lane: **0.88 ms** (4.5 TB/s);
+eight: 0.92 ms; sixteen: 1.37 ms (registers).
+
+### Live policies (`bench.py --config live`: `Environment.take_turn()` with a device policy between observe and act)
+
+| shape | eager split-phase launches | `enable_turn_graph()` |
+|---|---|---|
+| 4096 × 1 agent | {l4['eager']['ms_per_turn']:.3f} ms per turn | **{l4['ms_per_step']:.3f} ms** |
+| 16384 × 8 agents | {l3['eager']['ms_per_turn']:.3f} ms | **{l3['ms_per_step']:.3f} ms** |
+| 2^20 × 1 agent | {l1['eager']['ms_per_turn']:.3f} ms | {l1['ms_per_step']:.3f} ms (two grid round trips and two copies of every row per turn: kernel-bound) |
+
+### Multi-GPU (builder runs on one 8-GPU box, `r02_scale_g*.json`; the driver's SCALE file is the record)
+
+| GPUs | agent-env-steps/s | ms per step = step + sample + boundary | of N × one GPU ({one:.3e}) | e2e (uint8 actions in, f32 rewards out) |
+|---|---|---|---|---|
+{scale_row(2)}{scale_row(4)}{scale_row(8)}
+Round 1 at 8 GPUs: 2.22e10, 1.008 + 0.123 + 0.055 ms, e2e 1.50e10.  What is left at 8 GPUs is the tail of the step kernel at
+one eighth of the batch (3.46 waves: {b(g[8])['step']:.3f} ms against {k1:.2f} / 8 = {k1 / 8:.3f} ms) and the sample gather at a
+small batch; the box is one 24-core VM with a single NUMA node, where the end-to-end path moves 8 × (3.3 + 13.1) MB per ms.
+
+---
+
+"""
+open(os.path.join(P, "README.md"), "w").write(head + r1)
+print("profiles/README.md regenerated")
