@@ -89,7 +89,7 @@ typedef enum SbStatus {
 
 /* sources of randomness / actions for sb_step */
 #define SB_RNG_TAPE 0   /* replay recorded numpy draws: bit-exact to the reference */
-#define SB_RNG_PHILOX 1 /* counter-based Philox4x32-10 keyed by (seed, global env id, tick): one random
+#define SB_RNG_PHILOX 1 /* counter-based Philox4x32-10 over (seed, global env id, tick, index, domain): one random
                            byte per cell per turn (dense; mirrors the reference's draw-per-cell loop) */
 #define SB_RNG_SPARSE 2 /* same generator, sparse sampling of the same Bernoulli field: the number of
                            spawning cells K ~ Binomial(cells, p) is drawn first (inverse CDF on
@@ -98,9 +98,11 @@ typedef enum SbStatus {
 #define SB_POLICY_TAPE 0    /* actions supplied by the caller */
 #define SB_POLICY_UNIFORM 1 /* in-kernel uniform policy == RandomModel, models/base_model.py:107 */
 
-/* Philox counter word 3 ("domain"); word0 = global env id, word1 = tick, word2 = index */
+/* The keyed stream: draw(env, tick, index, domain) = Philox4x32-10((env, tick ^ seed_lo, index, domain ^ seed_hi), K)
+   with a FIXED key K (sb_core.cuh: SB_PHILOX_K0 / K1): word0 = global env id, word1 = tick, word2 = index, word3 =
+   "domain"; the 64-bit seed is folded into words 1 and 3, so the round keys are compile-time constants. */
 #define SB_DOM_SWEEP 0x53570000u  /* index = cell >> 4 : 16 cells per call, one byte each */
-#define SB_DOM_CELL 0x43450000u   /* index = cell      : 45 refinement bits + 64 choice bits */
+#define SB_DOM_CELL 0x43450000u   /* index = cell      : 64 level-2 bits + 64 choice bits (cells that passed level 1) */
 #define SB_DOM_ACTION 0x41430000u /* index = agent     : 64 action bits */
 #define SB_DOM_RESET 0x52530000u  /* index = try       : 64 placement bits */
 #define SB_DOM_SPARSE 0x53500000u /* index 0: 64 bits -> K;  index j >= 1: 64 position bits + 64 choice bits */

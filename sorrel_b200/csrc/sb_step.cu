@@ -16,11 +16,15 @@
 // planes are staged in shared memory for the whole launch (all `num_turns` turns), so the grid is
 // read and written once per launch while every turn streams one observation row per agent straight
 // into its replay-ring slot with 128-bit stores.  Groups never talk to each other; the only
-// intra-warp cooperation is the per-warp spawn-candidate queue of the Philox sweep.  Large maps keep their
-// planes in global memory (STAGED = false, one warp per instance); there four mutually distant agents are
-// observed and moved at once by 8 lanes each (see the fused loop).  All synchronisation is __syncwarp():
-// every phase that lets ONE lane mutate the instance (a move, a beam, a hand-over) is fenced from the phases in
-// which all lanes read it.
+// intra-warp cooperation is the per-warp spawn-candidate queue of the Philox sweep.  All synchronisation is
+// __syncwarp(): every phase that lets ONE lane mutate the instance (a move, a beam, a hand-over) is fenced from the
+// phases in which all lanes read it.
+//
+// Large maps with many agents (16..64 agents, planes of more than 4 KB) take `step_kernel_block` further down: one
+// BLOCK per instance, the plane staged in shared memory, up to sixteen mutually independent agents observed and moved
+// at once (dependency levels keep the list order of environment.py:92).  The older form of that idea -- planes used
+// in place in global memory (STAGED = false, one warp per instance), four mutually distant agents at once by 8 lanes
+// each -- remains for shapes the block kernel does not cover.
 #include <cuda_runtime.h>
 
 #include "sb_core.cuh"
