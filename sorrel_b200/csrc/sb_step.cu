@@ -320,6 +320,9 @@ constexpr int OBS_THREADS = 256;
 #ifndef SB_OBS_ROWWISE
 #define SB_OBS_ROWWISE 1
 #endif
+#ifndef SB_OBS_PIPELINED
+#define SB_OBS_PIPELINED 1
+#endif
 #ifndef SB_OBS_MINB
 #define SB_OBS_MINB 6  // resident blocks per SM the register allocation is sized for (40 registers)
 #endif
@@ -396,6 +399,146 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Standalone observation, row-wise gather, SOFTWARE-PIPELINED over the pairs a group walks (one-hot worlds with one
+// stored plane, 7..16-wide windows, no appended floats).  The plain kernel above was latency-bound: 47 % of its stall
+// samples sat on the two dependent global loads of a pair (its position, then the window words that position
+// addresses).  Here a lane (= one window row) issues the window loads of pair k+1 and the position load of pair k+2
+// BEFORE it scatters and streams out pair k, so both round trips are hidden behind a whole pair's work.
+// Loads are guarded against the ends of the grid allocation (a row gather may touch up to 12 bytes outside an
+// instance's planes), so no instance needs a special path.
+// ----------------------------------------------------------------------------------------------
+constexpr int OBS_ROW_LANES = 16, OBS_ROW_MAXG = 4;  // 16 lanes per pair; up to 4 groups of 5 cells per window row
+
+#ifndef SB_OBSROW_MINB
+#define SB_OBSROW_MINB 4  // the pipeline holds two pairs' window words in registers; latency is hidden by it, not by warps
+#endif
+template <bool PARTIAL>
+__global__ void __launch_bounds__(OBS_THREADS, SB_OBSROW_MINB)
+    observe_rows_kernel(const __grid_constant__ SbDev d, const uint8_t* __restrict__ grid,
+                        const int32_t* __restrict__ agent_pos, float* __restrict__ out, int stage_bytes,
+                        unsigned pairs_per_group, long long grid_bytes) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int LANES = OBS_ROW_LANES, GROUPS = OBS_THREADS / LANES;
+  const int grp = threadIdx.x / LANES, lane = threadIdx.x & (LANES - 1);
+  uint16_t* stage16 = reinterpret_cast<uint16_t*>(smem_raw + grp * stage_bytes);
+  for (int e = lane; e < stage_bytes / 4; e += LANES) reinterpret_cast<uint32_t*>(stage16)[e] = 0u;
+  __syncwarp();
+  const unsigned long long pairs = (unsigned long long)d.N * d.A;
+  const unsigned long long first = ((unsigned long long)blockIdx.x * GROUPS + grp) * pairs_per_group;
+  const int ng = (d.S + 4) / 5;
+  const uint32_t tlo = (uint32_t)d.channel8_oob, thi = (uint32_t)(d.channel8_oob >> 32);
+
+  auto load_pos = [&](unsigned long long pair) -> int { return pair < pairs ? __ldg(agent_pos + pair) : -1; };
+  // window words of row `lane` of the pair at `pair` (instance env) whose agent stands on cell `pos`
+  auto issue = [&](unsigned long long env, int pos, uint32_t (&w0)[OBS_ROW_MAXG], uint32_t (&w1)[OBS_ROW_MAXG]) {
+    const int y = pos < 0 ? 0 : (d.inv_W ? (int)__umulhi((uint32_t)pos, d.inv_W) : pos / d.W);
+    const int x = pos < 0 ? 0 : pos - y * d.W;
+    const int yy = y - d.v + lane;
+    const bool row_in = pos >= 0 && lane < d.S && (unsigned)yy < (unsigned)d.H;
+    const long long base = (long long)env * d.env_stride + (long long)yy * d.W + (x - d.v);
+#pragma unroll
+    for (int g = 0; g < OBS_ROW_MAXG; ++g) {
+      w0[g] = 0u, w1[g] = 0u;
+      if (g < ng && row_in) {
+        const long long al = (base + 5 * g) & ~3ll;
+        if (al >= 0) w0[g] = __ldg(reinterpret_cast<const uint32_t*>(grid + al));
+        if (al + 8 <= grid_bytes) w1[g] = __ldg(reinterpret_cast<const uint32_t*>(grid + al + 4));
+      }
+    }
+  };
+
+  unsigned long long env_c = first / (unsigned)d.A;
+  int a_c = (int)(first - env_c * (unsigned)d.A);
+  unsigned long long env_n = env_c;
+  int a_n = a_c;
+  auto advance = [&](unsigned long long& env, int& a) {
+    if (++a == d.A) {
+      a = 0;
+      ++env;
+    }
+  };
+  advance(env_n, a_n);
+  int pos_c = load_pos(first), pos_n = load_pos(first + 1);
+  uint32_t cw0[OBS_ROW_MAXG], cw1[OBS_ROW_MAXG], nw0[OBS_ROW_MAXG], nw1[OBS_ROW_MAXG];
+  issue(env_c, pos_c, cw0, cw1);
+
+  for (unsigned k = 0; k < pairs_per_group; ++k) {  // uniform trip count: both halves of a warp stay in step
+    const unsigned long long pair = first + k;
+    issue(env_n, pos_n, nw0, nw1);                 // pair k+1: in flight during the work below
+    const int pos_nn = load_pos(pair + 2);         // pair k+2
+    float* dst = pos_c >= 0 ? out + (size_t)pair * d.obs_size : nullptr;
+    const int head = dst ? (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3 : 0;
+    const int off = (4 - head) & 3;
+    if (dst && lane < d.S) {
+      // ---- scatter row `lane` of the window from the words loaded one iteration ago (scatter_rows_onehot_impl) ----
+      const int y = d.inv_W ? (int)__umulhi((uint32_t)pos_c, d.inv_W) : pos_c / d.W, x = pos_c - y * d.W;
+      const int x0 = x - d.v, yy = y - d.v + lane;
+      const int jlo = max(0, -x0), jhi = min(d.S, d.W - x0);
+      const bool row_in = (unsigned)yy < (unsigned)d.H;
+      const int boff = yy * d.W + x0;
+      uint16_t* const srow = stage16 + off + lane * d.S;
+#pragma unroll
+      for (int g = 0; g < OBS_ROW_MAXG; ++g) {
+        if (g < ng) {
+          const int j0 = 5 * g;
+          const int lc = min(max(jlo - j0, 0), 4), hc = min(max(jhi - j0, 0), 4);
+          uint32_t m4 = __funnelshift_lc(~0u, 0u, 8 * hc) & ~__funnelshift_lc(~0u, 0u, 8 * lc);
+          bool in5 = jlo <= j0 + 4 && j0 + 4 < jhi;
+          if (!row_in) m4 = 0u, in5 = false;
+          const uint32_t sh = ((uint32_t)(boff + j0) & 3u) * 8u;
+          uint32_t k4 = __funnelshift_r(cw0[g], cw1[g], sh);
+          const uint32_t k5 = in5 ? ((cw1[g] >> sh) & 7u) : 7u;
+          k4 = (k4 & m4) | (0x07070707u & ~m4);
+          const uint32_t t = k4 & 0x07070707u;
+          const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);
+          uint32_t c4 = __byte_perm(tlo, thi, sel);
+          uint32_t c5 = __byte_perm(tlo, thi, k5) & 0xFFu;
+          if (PARTIAL) {
+            const int cnt = d.S - j0;
+            c4 |= ~__funnelshift_lc(~0u, 0u, 8 * min(cnt, 4));
+            if (cnt < 5) c5 = 255u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t code = (c4 >> (8 * u)) & 0xFFu;
+            if (code != 255u) srow[code * d.SS + j0 + u] = 0x3F80;
+          }
+          if (c5 != 255u) srow[c5 * d.SS + j0 + 4] = 0x3F80;
+        }
+      }
+    }
+    __syncwarp();
+    if (dst) {  // ---- stream the row out (bf16 -> f32, 128-bit streaming stores), zeroing the staging row ----
+      const int nvec = d.oh_size > head ? (d.oh_size - head) >> 2 : 0;
+      const int etail = head + 4 * nvec + lane;
+      if (lane < head && lane < d.oh_size) {
+        dst[lane] = __uint_as_float((uint32_t)stage16[off + lane] << 16);
+        stage16[off + lane] = 0;
+      }
+      uint2* s2 = reinterpret_cast<uint2*>(stage16 + off + head);
+      for (int qv = lane; qv < nvec; qv += LANES) {
+        const uint2 w = s2[qv];
+        s2[qv] = make_uint2(0u, 0u);
+        st_f4(dst + head + 4 * qv, __uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
+              __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+      }
+      if (etail < d.oh_size) {
+        dst[etail] = __uint_as_float((uint32_t)stage16[off + etail] << 16);
+        stage16[off + etail] = 0;
+      }
+    }
+    __syncwarp();
+    // rotate the pipeline
+#pragma unroll
+    for (int g = 0; g < OBS_ROW_MAXG; ++g) cw0[g] = nw0[g], cw1[g] = nw1[g];
+    pos_c = pos_n;
+    pos_n = pos_nn;
+    env_c = env_n, a_c = a_n;
+    advance(env_n, a_n);
+  }
+}
+
 int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos, float* out, cudaStream_t s) {
   const bool np1 = d.fast_obs && d.n_planes == 1;
   // row-wise window gather (one lane per window row) when the rows fit the 16 lanes of a half warp
@@ -428,6 +571,30 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
     count_launch();
     return check_launch();
   };
+  if (rows && !d.obs_extra && !d.obs_flag && SB_OBS_PIPELINED) {  // software-pipelined row gather
+    const int sb = round_up((d.obs_size + 4) * 2, 16);
+    const int sm = groups * sb;
+    auto launch_rows = [&](auto kern) -> int {
+      if (sm > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        if (e != cudaSuccess) return note_cuda_error(e);
+      }
+      int dev = 0, sms = 148, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OBS_THREADS, sm) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+      unsigned long long blocks = (pairs + groups - 1) / groups;
+      if (blocks > (unsigned long long)sms * per_sm) blocks = (unsigned long long)sms * per_sm;
+      const unsigned long long ppg = (pairs + blocks * groups - 1) / (blocks * groups);
+      if (ppg > 0xFFFFFFFFull) return SB_EUNSUPPORTED;
+      kern<<<(unsigned)blocks, OBS_THREADS, sm, s>>>(d, grid, agent_pos, out, sb, (unsigned)ppg,
+                                                     (long long)d.N * d.env_stride);
+      count_launch();
+      return check_launch();
+    };
+    return d.S5 == d.S ? launch_rows(observe_rows_kernel<false>) : launch_rows(observe_rows_kernel<true>);
+  }
   if (rows) return launch(observe_kernel<true, 16, true>);
   if (lanes == 16) return np1 ? launch(observe_kernel<true, 16>) : launch(observe_kernel<false, 16>);
   return np1 ? launch(observe_kernel<true, 32>) : launch(observe_kernel<false, 32>);

@@ -448,6 +448,39 @@ def test_observe_random(general, cuda_device):
             np.testing.assert_array_equal(obs[n, a], ref)
 
 
+@pytest.mark.parametrize("H,W,v,A,N", [(9, 9, 4, 3, 5), (16, 23, 3, 6, 9), (21, 21, 5, 4, 37), (33, 18, 6, 7, 11),
+                                       (40, 40, 7, 9, 6), (21, 21, 2, 8, 40), (128, 128, 4, 64, 3)])
+def test_standalone_observe_all_window_widths(H, W, v, A, N, cuda_device):
+    """`sb_observe` (the software-pipelined row-wise kernel for 7..16-wide windows, the plain one otherwise) on worlds
+    without walls, with agents parked on corners, edges and the interior of the FIRST and LAST instance as well (the
+    row gather may touch bytes outside an instance's planes: guarded at the ends of the allocation), several launches
+    back to back (the staging rows must come back zeroed)."""
+    rng = np.random.RandomState(H * 100 + W)
+    spec = R.treasurehunt_spec(H, W, A, v, 0.0)
+    eng = _engine(spec, N, cuda_device)
+    eng.reset()
+    g = eng.grid.cpu().numpy()
+    g[:, 0, : H * W] = rng.choice([0, 0, 1, 2, 3, 4], size=(N, H * W)).astype(np.uint8)  # no border walls
+    cells = np.stack([rng.permutation(H * W)[:A] for _ in range(N)]).astype(np.int32)
+    corners = [0, W - 1, (H - 1) * W, H * W - 1, W // 2, (H // 2) * W, (H // 2) * W + W - 1, (H - 1) * W + W // 2]
+    for n in (0, N - 1):
+        for a in range(A):
+            cells[n, a] = corners[(a + n) % len(corners)] if a < len(corners) else cells[n, a]
+        cells[n] = np.where(np.bincount(cells[n], minlength=H * W)[cells[n]] > 1, rng.permutation(H * W)[:A], cells[n])
+    for n in range(N):
+        g[n, 0, cells[n]] = 5
+    eng.grid.copy_(torch.from_numpy(g))
+    eng.agent_pos.copy_(torch.from_numpy(cells))
+    full = eng.grid_numpy()
+    for _ in range(3):
+        obs = eng.observe().cpu().numpy()
+        for n in list(range(min(N, 3))) + [N - 1]:
+            for a in range(A):
+                y, x = divmod(int(cells[n, a]), W)
+                np.testing.assert_array_equal(obs[n, a], R.observe(spec, full[n], y, x).astype(np.float32),
+                                              err_msg=f"instance {n} agent {a} at ({y}, {x})")
+
+
 # ------------------------------------------------------------------------------------------------
 # 5. replay ring primitives, reward statistics, reset
 # ------------------------------------------------------------------------------------------------
