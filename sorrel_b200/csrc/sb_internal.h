@@ -44,6 +44,7 @@ struct StepParams {
   int32_t act_turns;                              // turns whose actions are prepared at once (action window rows)
   uint32_t inv_A;                                 // ceil(65536 / A)
   uint32_t rk[2];                                 // {seed_lo, seed_hi}: the stream words of sb_philox_rk
+  int32_t prefetch_blocks;                        // resident blocks of the launch (L2 prefetch distance), 0 = none
 };
 
 int note_cuda_error(cudaError_t e);  // records the error text for sb_last_cuda_error, returns SB_ECUDA
