@@ -228,6 +228,28 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   d.S5 = d.S - d.S % 5;
   d.rowwise_ok = d.K <= 7 && !d.toroidal ? 1 : 0;  // (a toroidal window row is not one run of bytes)
   d.channel8_oob = (d.channel8 & 0x00FFFFFFFFFFFFFFull) | ((uint64_t)(uint8_t)d.fill_channel << 56);
+  // class bytes of the generic sweep: A = ~(n2 - 1) of a drawing kind (level 1 passes iff (r8 & A) == 0); O bit 0 =
+  // the kind does not draw (or never passes: p == 0), bit 7 = visit always (deterministic rule; a draw whose failure
+  // still changes the kind)
+  d.cls_ok = d.K <= 15 ? 1 : 0;
+  for (int k = 0; k < 16; ++k) {
+    uint32_t a = 0xFFu, o = 0x01u;
+    if (k < d.K) {
+      if (((d.draw_mask >> k) & 1u) && d.n2k[k] >= 1) a = (~((uint32_t)d.n2k[k] - 1u)) & 0xFFu, o = 0u;
+      if (((d.det_mask >> k) & 1u) || ((d.else_mask >> k) & 1u)) o |= 0x80u;
+    }
+    d.cls_and[k >> 3] |= (uint64_t)a << (8 * (k & 7));
+    d.cls_or[k >> 3] |= (uint64_t)o << (8 * (k & 7));
+  }
+  for (int k = 8; k < 16; ++k) d.channel8_hi |= (uint64_t)d.channel[k] << (8 * (k - 8));
+  d.colgather_ok = (d.fast_obs && d.n_planes >= 2 && d.n_planes <= 3 && d.K <= 16 && !d.toroidal) ? 1 : 0;
+  for (int lg = 0; lg < 6; ++lg) {  // segments per window row: fill the 2^lg lanes, at most 8 cells per segment
+    int nseg = (1 << lg) / d.S;
+    nseg = nseg < (d.S + 7) / 8 ? (d.S + 7) / 8 : nseg;
+    nseg = nseg > d.S ? d.S : nseg;
+    d.cg_nseg[lg] = (int8_t)nseg;
+    d.cg_len[lg] = (int8_t)((d.S + nseg - 1) / nseg);
+  }
   d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536 && !ext) ? 1 : 0;
   if (d.sparse_ok) memcpy(d.cdf, w->spawn_cdf, sizeof(d.cdf));
   d.app = w->d_appearance;

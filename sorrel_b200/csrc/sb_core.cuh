@@ -84,6 +84,14 @@ struct SbDev {
   uint64_t channel8_oob;
   int32_t rowwise_ok;
   int32_t S5;  // S - S % 5: window columns covered by whole 5-cell groups of the row-wise gather
+  // column gather of several staged planes (sb_step.cu: scatter_cols_multi): channel[8..15] packed like channel8, and
+  // per group width 2^w the row segmentation -- cg_nseg[w] segments of cg_len[w] cells per window row
+  // byte-SIMD classification of the generic sweep (sb_step.cu): per-kind class bytes for kinds 0..7 / 8..15
+  uint64_t cls_and[2], cls_or[2];
+  int32_t cls_ok;  // K <= 15 (slot 15 = the 0xFF padding byte: never visited)
+  uint64_t channel8_hi;
+  int32_t colgather_ok;  // fast_obs, 2 or 3 stored planes, K <= 16, not toroidal
+  int8_t cg_nseg[6], cg_len[6];
 };
 
 // ------------------------------------------------------------------------------------------------

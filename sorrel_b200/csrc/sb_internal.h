@@ -15,6 +15,9 @@
 #ifndef SB_ROWWISE_MAX_LPE
 #define SB_ROWWISE_MAX_LPE 8  // groups up to this width gather observation windows row by row (0: never)
 #endif
+#ifndef SB_COLGATHER
+#define SB_COLGATHER 1  // several staged planes: gather observation windows by row segments (scatter_cols_multi)
+#endif
 #define SB_OBS_ALL (-2)  // SbStepArgs.obs_agent: observe every agent (sb_observe)
 
 // kernel RNG variants (template parameter)

@@ -41,9 +41,9 @@ __host__ __device__ inline int pad64mod128(int b) {
 }
 
 // Shared-memory layout of a block (see StepParams).  The staging row of an instance holds ONE
-// observation (+4 elements of alignment slack) and is all-zero between observations; it is bf16 when a
-// single stored plane is observed (entries are 0 or 1: the float is the bf16 shifted left by 16) and
-// f32 otherwise (entries are sums over planes).
+// observation (+4 elements of alignment slack) and is all-zero between observations; it is bf16: entries
+// are 0 / 1 (one stored plane) or the number of stored planes showing that channel in that cell (several planes
+// are summed: small integers, exact in bf16), and the float is the bf16 shifted left by 16.
 struct SmemLayout {
   int q_off, planes_off, pos_off, stage_off, hits_off, plane_env, stage_env, stage_row, total;
   int agent_words, act_turns;
@@ -72,7 +72,7 @@ __host__ inline SmemLayout smem_layout(const SbDev& d, int threads, int lpe, boo
   L.act_turns = act_turns_ahead(lpe, d.A);
   L.agent_words = 3 * d.A + L.act_turns * d.A;
   L.stage_off = L.pos_off + round_up(epb * 4 * L.agent_words, 16);
-  L.stage_row = pad64mod128((d.obs_size + 4) * (np1 ? 2 : 4));
+  L.stage_row = pad64mod128((d.obs_size + 4) * 2);  // bf16 on every fast path (entries are small integer counts)
   // warp-per-instance worlds with several agents observe up to SB_PAR independent agents at once
   L.stage_env = (np1 && lpe == 32 && d.A >= SB_PAR) ? SB_PAR * L.stage_row : L.stage_row;
   L.hits_off = L.stage_off + epb * L.stage_env;  // SB_RNG_SPARSE: accepted cells of the turn, u16[KMAX]
@@ -167,6 +167,96 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
   else scatter_rows_onehot_impl<LANES, true>(d, genv, srow16, y, x, lane);
 }
 
+// bf16 of a small plane count (1, 2, 3): what the staging row holds for a (channel, cell) shown by that many planes
+__device__ __forceinline__ uint16_t bf16_count(int n) { return n == 1 ? 0x3F80 : (n == 2 ? 0x4000 : 0x4040); }
+
+// Window gather for SEVERAL stored planes (2 or 3) staged in shared memory, any group width: the multi-plane
+// counterpart of scatter_rows_onehot.  A lane takes a SEGMENT of a window row (d.cg_len cells; d.cg_nseg segments per
+// row, chosen per group width so that S x nseg units fill the lanes: 11x11 windows on 32 lanes = 22 units of 6 / 5
+// cells) and walks it four cells at a time: per plane two aligned 32-bit shared loads and a funnel shift fetch the four
+// kinds, two byte permutes (kinds 0..7 / 8..15) turn them into channel codes, out-of-bounds cells become the fill
+// channel on the first plane and "nothing" on the others by a byte mask.  The codes of a cell's column are then in
+// registers together, so each (channel, cell) entry is STORED once with its final count -- 1, or 2 / 3 where several
+// planes show the same channel (cleanup: walls on every layer) -- instead of a shared-memory read-modify-write per
+// plane.  Per cell-plane that is ~8 instructions against ~35 for the cell-wise loop (a byte load, a dependent table
+// load, bounds tests and index arithmetic per plane).  Requires K <= 16, not toroidal (d.colgather_ok); `genv` must
+// be shared memory (loads may touch a few bytes before / after the instance image, masked out, inside the block's
+// allocation).
+template <int LANES>
+__device__ __forceinline__ void scatter_cols_multi(const SbDev& d, const uint8_t* genv, uint16_t* srow16, int y, int x,
+                                                   int lane) {
+  constexpr int LG = LANES == 32 ? 5 : LANES == 16 ? 4 : LANES == 8 ? 3 : LANES == 4 ? 2 : 1;
+  const int S = d.S, g = d.cg_len[LG], units = S * d.cg_nseg[LG];
+  const int x0 = x - d.v;                               // map column of window column 0 (may be negative)
+  const int jlo = max(0, -x0), jhi = min(S, d.W - x0);  // window columns [jlo, jhi) lie inside the map
+  const uint32_t clo0 = (uint32_t)d.channel8, clo1 = (uint32_t)(d.channel8 >> 32);
+  const uint32_t chi0 = (uint32_t)d.channel8_hi, chi1 = (uint32_t)(d.channel8_hi >> 32);
+  const uint32_t fill4 = (uint32_t)(d.fill_channel & 0xFF) * 0x01010101u;
+  for (int u = lane; u < units; u += LANES) {
+    const int sg = (int)(((uint32_t)u * d.inv_S) >> 16), i = u - sg * S;  // segment-major: (segment, window row)
+    const int yy = y - d.v + i;
+    const bool row_in = (unsigned)yy < (unsigned)d.H;
+    const int off = yy * d.W + x0;  // plane offset of window cell (i, 0); out-of-bounds bytes are masked below
+    uint16_t* const srow = srow16 + i * S;
+    const int j_end = min(S, (sg + 1) * g);
+    for (int j0 = sg * g; j0 < j_end; j0 += 4) {
+      const int cnt = min(4, j_end - j0);
+      const int lc = min(max(jlo - j0, 0), 4), hc = min(max(jhi - j0, 0), 4);
+      const uint32_t m4 = row_in ? (__funnelshift_lc(~0u, 0u, 8 * hc) & ~__funnelshift_lc(~0u, 0u, 8 * lc)) : 0u;
+      const uint32_t past = ~__funnelshift_lc(~0u, 0u, 8 * cnt);  // bytes of cells beyond the segment: show nothing
+      uint32_t c[3];
+      int n_vis = 0;  // planes that show anything in these four columns
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        c[pl] = 0xFFFFFFFFu;
+        if (pl < d.n_planes) {
+          uint32_t k4 = 0u;
+          if (row_in) {
+            const int o = pl * d.plane_stride + off + j0;
+            const int al = o & ~3;
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(genv + al);
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(genv + al + 4);
+            k4 = __funnelshift_r(w0, w1, ((uint32_t)o & 3u) * 8u);  // kinds of cells j0 .. j0+3
+          }
+          const uint32_t t = k4 & 0x07070707u;
+          const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);  // nibbles k0, k1, k2, k3 (low three bits)
+          uint32_t c4 = __byte_perm(clo0, clo1, sel);
+          if (d.K > 8) {  // kinds 8..15: the second table, chosen per byte by bit 3 of the kind
+            const uint32_t h4 = __byte_perm(chi0, chi1, sel);
+            const uint32_t m8 = ((k4 >> 3) & 0x01010101u) * 0xFFu;
+            c4 = (c4 & ~m8) | (h4 & m8);
+          }
+          c[pl] = (c4 & m4) | ((pl == 0 ? fill4 : 0xFFFFFFFFu) & ~m4) | past;  // out of bounds: the fill kind, once
+          n_vis += c[pl] != 0xFFFFFFFFu;
+        }
+      }
+      uint16_t* const cell0 = srow + j0;
+      if (n_vis <= 1) {
+        // the common case -- at most one plane shows anything here (open terrain; out-of-bounds columns): no entry
+        // can be shown twice, so every visible cell is one store of 1.0
+        const uint32_t c1 = c[0] & c[1] & c[2];
+        if (c1 != 0xFFFFFFFFu) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t a = (c1 >> (8 * e)) & 0xFFu;
+            if (a != 255u) cell0[a * d.SS + e] = 0x3F80;
+          }
+        }
+      } else {  // several planes visible (agents on terrain, beams, the walls of every layer): count equal channels
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t a = (c[0] >> (8 * e)) & 0xFFu, b = (c[1] >> (8 * e)) & 0xFFu, cc = (c[2] >> (8 * e)) & 0xFFu;
+          if ((a & b & cc) == 255u) continue;
+          uint16_t* const cell = cell0 + e;
+          if (a != 255u) cell[a * d.SS] = bf16_count(1 + (b == a) + (cc == a));
+          if (b != 255u && b != a) cell[b * d.SS] = bf16_count(1 + (cc == b));
+          if (cc != 255u && cc != a && cc != b) cell[cc * d.SS] = 0x3F80;
+        }
+      }
+    }
+  }
+}
+
 // One observation row through the one-hot fast path, by the LANES lanes that own the instance (all
 // of them must call; `dst == nullptr` only takes part in the synchronisation; the caller issues the
 // trailing __syncwarp, which lets it overlap the agent's move with the stream-out).  The row is all zeros
@@ -178,8 +268,7 @@ __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_
 template <int LANES, bool NP1, int NB = 1, bool ROWWISE = false>
 __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint32_t* ktab,
                                                 uint8_t* stage_raw, int y, int x, float* dst, int lane) {
-  float* stage = reinterpret_cast<float*>(stage_raw);          // !NP1: f32 sums over planes
-  uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_raw);  // NP1: bf16 (0 or 1.0)
+  uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_raw);  // bf16: 0 / 1.0 (NP1) or a small plane count
   const int head = dst ? (4 - (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3 : 0;
   const int off = (4 - head) & 3;
   if (dst) {
@@ -191,8 +280,13 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
 #define SB_SCATTER_UNROLL 2  // measured: 7.60 -> 7.55 ms at the default shape
 #endif
     constexpr int kScatterUnroll = (NB > 1) ? 1 : SB_SCATTER_UNROLL;
-    const bool rowwise = ROWWISE && d.rowwise_ok;
-    if (rowwise) scatter_rows_onehot<LANES>(d, genv, srow16, y, x, lane);
+    // ROWWISE (planes staged in shared memory): one stored plane -> row-wise gather of narrow groups; several
+    // stored planes -> column gather (scatter_cols_multi), any group width
+    const bool rowwise = ROWWISE && (NP1 ? d.rowwise_ok : d.colgather_ok);
+    if (rowwise) {
+      if constexpr (NP1) scatter_rows_onehot<LANES>(d, genv, srow16, y, x, lane);
+      else scatter_cols_multi<LANES>(d, genv, srow16, y, x, lane);
+    }
 #pragma unroll kScatterUnroll
     for (int ij = rowwise ? d.SS : lane; ij < d.SS; ij += LANES) {
       const int i = (int)(((uint32_t)ij * inv_s) >> 16), j = ij - i * d.S;
@@ -234,9 +328,9 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
           yy = yy < 0 ? yy + d.H : (yy >= d.H ? yy - d.H : yy);
           xx = xx < 0 ? xx + d.W : (xx >= d.W ? xx - d.W : xx);
         }
-        float* srow = stage + off + ij;
+        uint16_t* srow = srow16 + ij;
         if ((unsigned)yy >= (unsigned)d.H || (unsigned)xx >= (unsigned)d.W) {
-          if (d.fill_channel != 255) srow[d.fill_channel * d.SS] = 1.0f;  // out of bounds: the fill kind, once
+          if (d.fill_channel != 255) srow[d.fill_channel * d.SS] = 0x3F80;  // out of bounds: the fill kind, once
         } else {
           const uint8_t* pc = genv + yy * d.W + xx;
           uint32_t first = 255u;
@@ -245,10 +339,11 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
             const uint32_t code = ktab ? (ktab[*pc & 31u] & 0xFFu) : sb_kind_channel(d, *pc);
             if (code == 255u) continue;
             if (first == 255u) {
-              srow[code * d.SS] = 1.0f;
+              srow[code * d.SS] = 0x3F80;  // bf16(1.0)
               first = code;
-            } else {
-              srow[code * d.SS] += 1.0f;
+            } else {  // bf16 count + 1 (exact: counts are at most the number of planes)
+              const float f = __uint_as_float((uint32_t)srow[code * d.SS] << 16) + 1.0f;
+              srow[code * d.SS] = (uint16_t)(__float_as_uint(f) >> 16);
             }
           }
         }
@@ -259,7 +354,7 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
   if (dst) {
     const int nvec = d.oh_size > head ? (d.oh_size - head) >> 2 : 0;
     const int etail = head + 4 * nvec + lane;
-    if (NP1) {
+    {
       if (lane < head && lane < d.oh_size) {
         dst[lane] = __uint_as_float((uint32_t)stage16[off + lane] << 16);
         stage16[off + lane] = 0;
@@ -299,22 +394,6 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
       if (etail < d.oh_size) {
         dst[etail] = __uint_as_float((uint32_t)stage16[off + etail] << 16);
         stage16[off + etail] = 0;
-      }
-    } else {
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane < head && lane < d.oh_size) {
-        dst[lane] = stage[off + lane];
-        stage[off + lane] = 0.0f;
-      }
-      float4* s4 = reinterpret_cast<float4*>(stage + off + head);
-      for (int qv = lane; qv < nvec; qv += LANES) {
-        const float4 v = s4[qv];
-        s4[qv] = zero4;
-        st_f4(dst + head + 4 * qv, v.x, v.y, v.z, v.w);
-      }
-      if (etail < d.oh_size) {
-        dst[etail] = stage[off + etail];
-        stage[off + etail] = 0.0f;
       }
     }
   }
@@ -558,7 +637,7 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
   const bool rows = np1 && d.rowwise_ok && d.S >= 7 && d.S <= 16 && SB_OBS_ROWWISE;
   const int lanes = (d.obs_size <= 256 || rows) ? 16 : 32;  // two pairs per warp / one
   const int groups = OBS_THREADS / lanes;
-  const int stage_bytes = round_up((d.obs_size + 4) * (np1 ? 2 : 4), 16);
+  const int stage_bytes = round_up((d.obs_size + 4) * 2, 16);
   const int smem = round_up(2 * d.SS, 16) + 4 * SB_KTAB_WORDS + groups * stage_bytes;
   if (smem > 227 * 1024) return SB_EUNSUPPORTED;
   const unsigned long long pairs = (unsigned long long)d.N * d.A;
@@ -903,20 +982,55 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
             const int c = pl * cpp + cc;
             const uint4 k4 = genv4[c];
             const uint32_t kw[4] = {k4.x, k4.y, k4.z, k4.w};
-            // classify the 16 cells from registers (common case: no rule), then visit only the ruled ones in a
-            // ROLLED loop: the slow path (two Philox bodies) exists once in the instruction stream
+            // classify the 16 cells from registers (common case: nothing to do), then visit only the cells where
+            // something can happen in a ROLLED loop: the slow path (two Philox bodies) exists once in the
+            // instruction stream
             uint32_t m = 0;
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-              const uint32_t kind = (kw[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-              if (kind < (uint32_t)SB_MAX_KINDS && ((ruled >> kind) & 1u)) m |= 1u << b;
-            }
             bool have_r = false;
             SbU4 r;
+            if (d.cls_ok) {
+              // Byte-SIMD, four cells per word: two per-kind class bytes (A = level-1 mask of a drawing kind; O = bit 0
+              // "does not draw", bit 7 "always visit": deterministic rules, draws with an else branch) are looked up
+              // by byte permutes; a cell is visited iff it must always be, or it draws and its random byte passes
+              // level 1 of its kind -- (r8 & A) | (O & 1) == 0.  A River / AppleTree cell (a third of the cleanup map
+              // each) used to cost a trip of the loop below every turn; now 1 in 64 / 1 in 256 of them does.
+              uint32_t ca[4], co[4], nd = 0xFFFFFFFFu;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const uint32_t t = kw[w] & 0x07070707u;
+                const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);
+                const uint32_t m8 = ((kw[w] >> 3) & 0x01010101u) * 0xFFu;  // kinds 8..15 (and the 0xFF padding)
+                ca[w] = (__byte_perm((uint32_t)d.cls_and[0], (uint32_t)(d.cls_and[0] >> 32), sel) & ~m8) |
+                        (__byte_perm((uint32_t)d.cls_and[1], (uint32_t)(d.cls_and[1] >> 32), sel) & m8);
+                co[w] = (__byte_perm((uint32_t)d.cls_or[0], (uint32_t)(d.cls_or[0] >> 32), sel) & ~m8) |
+                        (__byte_perm((uint32_t)d.cls_or[1], (uint32_t)(d.cls_or[1] >> 32), sel) & m8);
+                nd &= co[w];
+              }
+              r.x = r.y = r.z = r.w = 0u;
+              if ((~nd & 0x01010101u) != 0u) {  // some cell of the chunk draws
+                r = sb_philox_rk(envid, tick, (uint32_t)c, SB_DOM_SWEEP, rk);
+                have_r = true;
+              }
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const uint32_t x = (rw[w] & ca[w]) | (co[w] & 0x01010101u);
+                const uint32_t tz = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                const uint32_t vis = (~(tz | x | 0x7F7F7F7Fu)) | (co[w] & 0x80808080u);  // 0x80 per cell to visit
+                m |= vis >> (7 - w);  // bit 8*b + w: byte b of word w
+              }
+            } else {
+#pragma unroll
+              for (int b = 0; b < 16; ++b) {
+                const uint32_t kind = (kw[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+                if (kind < (uint32_t)SB_MAX_KINDS && ((ruled >> kind) & 1u)) m |= 1u << b;
+              }
+            }
 #pragma unroll 1
             while (m) {
-              const int b = __ffs(m) - 1;
+              const int pos = __ffs(m) - 1;
               m &= m - 1;
+              const int b = d.cls_ok ? 4 * (pos & 7) + (pos >> 3) : pos;  // cell of the chunk
               const uint32_t cell = (uint32_t)(c * 16 + b);
               const uint32_t kind = genv[cell];
               const uint32_t kt = ktab[kind];  // channel | rule << 8 | rule_to << 16 | rule_else << 24
@@ -966,7 +1080,8 @@ __global__ void __launch_bounds__(SB_THREADS, SB_MIN_BLOCKS)
         }
       } else if (NP1 || d.fast_obs) {
         // narrow groups on a staged plane gather the window row by row (scatter_rows_onehot)
-        constexpr bool RW = NP1 && STAGED && LPE <= SB_ROWWISE_MAX_LPE;
+        // (several staged planes: the column gather of scatter_cols_multi, any group width)
+        constexpr bool RW = STAGED && (NP1 ? LPE <= SB_ROWWISE_MAX_LPE : SB_COLGATHER != 0);
         emit_onehot_row<LPE, NP1, 1, RW>(d, genv, ktab, stage_raw, y, x, dsts[0], lane);
         if (p.a.d_obs_out) {
           __syncwarp();
