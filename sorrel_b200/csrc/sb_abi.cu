@@ -243,12 +243,20 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
   }
   for (int k = 8; k < 16; ++k) d.channel8_hi |= (uint64_t)d.channel[k] << (8 * (k - 8));
   d.colgather_ok = (d.fast_obs && d.n_planes >= 2 && d.n_planes <= 3 && d.K <= 16 && !d.toroidal) ? 1 : 0;
-  for (int lg = 0; lg < 6; ++lg) {  // segments per window row: fill the 2^lg lanes, at most 8 cells per segment
-    int nseg = (1 << lg) / d.S;
-    nseg = nseg < (d.S + 7) / 8 ? (d.S + 7) / 8 : nseg;
-    nseg = nseg > d.S ? d.S : nseg;
-    d.cg_nseg[lg] = (int8_t)nseg;
-    d.cg_len[lg] = (int8_t)((d.S + nseg - 1) / nseg);
+  for (int lg = 0; lg < 6; ++lg) {
+    // segments per window row for groups of 2^lg lanes: a lane walks its segment four cells at a time, so a window
+    // costs ceil(S * nseg / lanes) trips x ceil(len / 4) chunk steps; take the cheapest split (at most 8 cells per
+    // segment; ties: fewer segments).  11x11 windows: 3 segments (4, 4, 3 cells) on 16 lanes = 3 steps, not 4.
+    const int lanes = 1 << lg;
+    int best = 0, best_cost = 1 << 30;
+    for (int nseg = (d.S + 7) / 8; nseg <= d.S; ++nseg) {
+      const int len = (d.S + nseg - 1) / nseg;
+      if ((nseg - 1) * len >= d.S) continue;  // the last segment would be empty
+      const int cost = ((d.S * nseg + lanes - 1) / lanes) * ((len + 3) / 4);
+      if (cost < best_cost) best = nseg, best_cost = cost;
+    }
+    d.cg_nseg[lg] = (int8_t)best;
+    d.cg_len[lg] = (int8_t)((d.S + best - 1) / best);
   }
   d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536 && !ext) ? 1 : 0;
   if (d.sparse_ok) memcpy(d.cdf, w->spawn_cdf, sizeof(d.cdf));

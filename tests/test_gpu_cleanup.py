@@ -391,3 +391,67 @@ def test_fuzz_rule_sets_against_c_oracle(case, cuda_device):
         np.testing.assert_array_equal(eng.agent_facing.cpu().numpy(), co.facing)
     if kind == "tag":
         np.testing.assert_array_equal(eng.agent_flag.cpu().numpy(), co.flags)
+
+
+# ------------------------------------------------------------------------------------------------
+# column gather of several staged planes (sb_step.cu: scatter_cols_multi): every window width, every group width
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lpe", [4, 8, 16, 32])
+@pytest.mark.parametrize("v", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+def test_multi_plane_window_gather_all_widths(v, lpe, cuda_device):
+    """Cleanup worlds (three stored planes, 12 kinds: both channel tables; walls on every layer: entries counted
+    three times; beams and agents on top of terrain) at every window width a descriptor accepts and every group
+    width: all rows of the ring against the C oracle.  Agents start anywhere, so windows hang over every edge."""
+    from oracle import coracle
+
+    H, W = 23, 27
+    spec = R.cleanup_spec(H, W, 4, v, initial_apples=5, apple_spawn_chance=0.03, pollution_spawn_chance=0.05,
+                          beam_radius=2)
+    N, T, seed, base = 9, 6, 40 + v, 3 * v
+    eng = _engine(spec, N, cuda_device, env_id_base=base, seed=seed, tuning={"lpe": lpe})
+    buf = _buffer(spec, N, T, cuda_device)
+    try:
+        eng.step_plan(T)
+    except ValueError:  # 32 instances of this size per block do not fit in shared memory
+        assert lpe == 4 and v >= 8
+        pytest.skip("tiling pinned by the test does not fit this shape")
+    co = coracle.COracle(spec, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, env_id_base=base, threads=4)
+    eng.reset()
+    eng.step(T, buffer=buf)
+    eng.check_errors()
+    co.reset()
+    co.step(T)
+    np.testing.assert_array_equal(eng.grid_numpy(), co.grid)
+    ring = co.ring()
+    np.testing.assert_array_equal(buf.states.cpu().numpy(), ring["states"])
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
+
+
+@pytest.mark.parametrize("lpe", [None, 4, 8, 32])
+@pytest.mark.parametrize("v", [2, 4])
+def test_two_plane_world_with_few_kinds(v, lpe, cuda_device):
+    """A treasurehunt world whose floor layer is stored per instance as well: two planes, 7 kinds (one channel
+    table), byte-SIMD sweep + column gather, against the C oracle of the same two-plane description (the draw
+    stream is keyed by the stored-plane cell index, so it differs from the one-plane layout's)."""
+    import dataclasses
+    from oracle import coracle
+
+    spec1 = R.treasurehunt_spec(15, 18, 3, v, 0.02)
+    spec2 = dataclasses.replace(spec1, dynamic_layers=[0, 1])
+    N, T, seed = 21, 12, 7
+    eng = _engine(spec2, N, cuda_device, seed=seed, tuning={"lpe": lpe} if lpe else {})
+    plan = eng.step_plan(T)
+    assert not plan["fast_onehot"] and plan["planes_staged"], plan
+    buf = _buffer(spec2, N, T, cuda_device)
+    co = coracle.COracle(spec2, N, capacity=T, rng=coracle.RNG_PHILOX, seed=seed, threads=4)
+    eng.reset()
+    eng.step(T, buffer=buf)
+    eng.check_errors()
+    co.reset()
+    co.step(T)
+    np.testing.assert_array_equal(eng.grid_numpy(), co.grid)
+    ring = co.ring()
+    np.testing.assert_array_equal(buf.states.cpu().numpy(), ring["states"])
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), ring["rewards"])
+    np.testing.assert_array_equal(eng.total_reward.cpu().numpy(), co.total_reward)
+    assert buf.states.sum() > 0
