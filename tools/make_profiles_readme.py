@@ -52,14 +52,14 @@ used as bench values; `bench.py` times with CUDA events.  **Round 2 first; the r
 
 | file | what |
 |---|---|
-| `r02_launches.csv` | every kernel launched by `python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --no-graphs` (`ncu --metrics gpu__time_duration.sum`), aggregated per kernel: `sb::step_kernel<4,1,1,1>` 52.6 % of device time (6.28 ms per launch), the sparse sampler the same command times beside it 31.1 % (4.78 ms), `sb::buffer_sample_kernel` 12.7 % (0.85 ms), reset 0.5 %, reward stats 0.2 %.  Within the per-cell half of the run the step kernel is 0.87 of the step = `roofline.step_kernel_share_of_step` from CUDA events (0.87). |
+| `r02_launches.csv` | every kernel launched by `python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --no-graphs` (`ncu --metrics gpu__time_duration.sum`), aggregated per kernel: `sb::step_kernel<4,1,1,1>` 53.9 % of device time (6.30 ms per launch), the sparse sampler the same command times beside it 31.9 % (4.79 ms), `sb::buffer_sample_staged_kernel` 10.6 % (0.70 ms), the ring fill of `add_empty` 2.6 %, reset 0.5 %, reward stats 0.2 %.  Within the per-cell half of the run the step kernel is 0.89 of the step = `roofline.step_kernel_share_of_step` from CUDA events (0.89). |
 | `r02_step_kernel_metrics.csv`, `_source_lines.csv` | `ncu --set full` of one steady-state launch of the headline kernel (2^20 instances × 25 fused turns): 6.26 ms, 5.35e9 warp-instructions (round 1: 7.60 ms, 6.50e9), DRAM 17.16 GB written + 0.69 GB read (35 % of peak busy), issue slots 74 %, 62 registers, 8 blocks / SM from both limits |
 | `r02_step_kernel_sweep_loop.sass` | SASS of the sweep loop of the headline kernel (two Philox chains, level-1 filter, ballot queue push) |
 | `r02_sparse_kernel_*` | the same shape with the sparse sampler (`step_kernel<4,3,1,1>`) |
 | `r02_c3_kernel_*` | BASELINE config 3 at its named size (16384 × 8 agents, slot-major ring, `step_kernel<8,1,1,1>`) |
 | `r02_c4_kernel_*` | BASELINE config 4 at its named size (2048 × 128×128 × 64 agents): `sb::step_kernel_block` |
-| `r02_cleanup_kernel_*` | the cleanup example (`step_kernel<32,2,0,1>`) |
-| `r02_sample_kernel_metrics.csv` | `buffer_sample_kernel` after the batched-load rewrite |
+| `r02_cleanup_kernel_*` | the cleanup example (`step_kernel<16,2,0,1>`, generic variant: column gather, byte-SIMD rule classification, 79 registers) |
+| `r02_sample_kernel_metrics.csv` | `buffer_sample_staged_kernel` (frames staged through shared memory with `cp.async`) |
 | `r02_shapes.jsonl` | one `bench.py` line per BASELINE shape (`tools/gpu_shapes.sh`, presets `--config 2|3|4|5|cleanup|4obs|4obs19`) and the three `--config live` lines, all with clocks sampled during the timed region |
 | `r02_scale_g2/4/8.json` | builder runs of `torchrun ... bench.py --gpus N` on one 8-GPU box |
 | `traffic.json` | DRAM bytes of one step-kernel launch per shape (`dram__bytes_read.sum + dram__bytes_write.sum` of the captures above) = `roofline.traffic`; `frac_dram = traffic / kernel time / peak` |
@@ -90,6 +90,8 @@ Round 1, same shapes: config 2 0.21 (T = 100) / 0.07 (T = 1); config 3 0.47 at 1
 | (rejected) 2 lanes per instance | 7.34 ms | 64 instances per block: 4 blocks / SM |
 | (rejected) `__launch_bounds__(128, 7 / 6 / 5)` = 66 / 74 / 88 registers | 6.75 / 6.78 / 6.87 ms (at 6.84); 6.31 / 6.31 (at 6.28) | fewer rematerialisations, fewer warps: a wash |
 | (rejected) one row-gather loop with a per-group cell count instead of two instantiations | +3 % dense, +9 % sparse, +6 % config 3 | |
+| (rejected) two-pass sweep: pass 1 tests the random bytes only (a chunk whose 16 bytes all fail level 1 cannot spawn: 88 % of them) and queues the other chunks; pass 2 redoes their Philox call and applies the exact filter | 6.38 ms against 6.29 (config 3: 0.526 / 0.514, config 2: 0.328 / 0.297) | ncu: 5.27e9 warp-instructions instead of 5.35e9 — the exact filter saved (33 → 15 instructions per chunk) is spent again on the second Philox call of the queued chunks and on the pushes; results identical (parity suite green), not kept |
+| (rejected) wave shaping: cap the resident blocks per SM (extra dynamic shared memory) when that makes the wave count integral, e.g. one eighth of the batch = 4096 blocks: 3.46 waves at 8 per SM, 3.95 at 7 | 131072 instances: 0.846 ms against 0.838; 196608: 1.244 against 1.232 | the partial last wave already runs faster (fewer warps per scheduler); lower residency costs more than the tail |
 
 ### Ring layout (config 3, 16384 × 8 agents × 25 turns, `step_kernel<8,1,1,1>`)
 
@@ -112,17 +114,34 @@ slots per block in 31 KB (7 blocks per SM: 2 waves instead of 2.3 at 2048 instan
 
 ### Cleanup example (`r02_cleanup_kernel_*`, generic variant)
 
-12.7 ms per 25-turn launch (0.48 algorithmic, 0.44 of the peak in measured DRAM traffic: 36 GB of rows).  ncu before the
-shared-memory kind tables: 10.8e9 warp-instructions, lane efficiency 17 / 32, ADU pipe 45 % and 20 % of the stall
-samples on `d.channel[kind]` (twelve kinds: a constant-bank load with a divergent index is replayed once per distinct
-address); with the tables in shared memory (`sb_fill_kind_tables`) 13.8 → 13.1 ms, with the later kernel changes 12.7 ms.
-Still below the 0.60 bar: 363 window lookups per agent-turn (121 cells × 3 planes), agents strictly sequential (beams
-make every pair of the ten agents interact), `no_instruction` 2.0 stall cycles per issue (the EXT variants are large).
+32768 instances × 10 agents × 25 turns per launch, rows of 1101 floats (36 GB written per launch).  Round 1 / first
+half of round 2: 12.7–13.1 ms (0.46–0.48 of the algorithmic roofline), 10.3e9 warp-instructions, a third of them in the
+cell-wise window gather (363 lookups per agent-turn: a byte load, a dependent table load, bounds tests and a
+read-modify-write of an f32 staging row per cell-plane).  Final build: **8.13 ms = 0.75 algorithmic, 0.68 of the measured
+HBM peak in DRAM traffic** (6.8e9 warp-instructions, 79 registers, 6 blocks per SM), step by step on the same command:
 
-### Sample gather (`buffer_sample_kernel`, config 5: 409 600 transitions of 5 stacked frames per step)
+| change | kernel |
+|---|---|
+| start of the session (`step_kernel<32,2,0,1>`, f32 staging rows, 7 blocks per SM) | 13.09 ms |
+| bf16 staging rows for multi-plane worlds (entries are small plane counts): 37 KB per block at 16 lanes per instance instead of 29 KB at 32 → `pick_lpe` takes 16 lanes | 12.27 ms |
+| column gather (`scatter_cols_multi`): a lane walks a row segment four cells at a time, two aligned 32-bit shared loads + funnel shift per plane, channel codes by two byte permutes (kinds 0–7 / 8–15), out-of-bounds by byte mask | 11.47 ms |
+| byte-SIMD classification + level-1 filter in the generic sweep (River / AppleTree cells no longer cost a loop trip each per turn: 1 in 64 / 256 of them does) | 10.68 ms |
+| branch-free ordered stores (plane q writes 1 + number of earlier planes with the same code; equalities found four cells at a time) instead of "one plane visible" / "several" paths that diverged in almost every warp | 9.64 ms |
+| stream-out of long rows four vectors per trip | 9.55 ms |
+| row segmentation from a cost model (11×11 windows on 16 lanes: segments of 4, 4, 3 cells = 3 chunk steps instead of 4) | 8.60 ms |
+| `__launch_bounds__(128, 6)` for the replay / generic variants: 79 registers instead of 64 (shared memory caps residency at 6 blocks anyway); 5 blocks / 87 registers: 8.59 ms | **8.13 ms** |
 
-round-1 loop (one load, two stores per trip): 1.08–1.20 ms → four loads in flight per lane: **0.88 ms** (4.5 TB/s);
-eight: 0.92 ms; sixteen: 1.37 ms (registers).
+Other group widths with the final code: 8 lanes 9.99 ms, 32 lanes 11.48 ms.  What is left (ncu): the per-plane emits 13 %
+of the instructions, the per-plane lookups 12 %, stream-out 10 %, sweep 10 %; agents stay strictly sequential (beams make
+every pair of the ten agents interact).
+
+### Sample gather (`buffer_sample_staged_kernel`, config 5: 409 600 transitions of 5 stacked frames per step)
+
+round-1 loop (one load, two stores per trip): 1.08–1.20 ms → four loads in flight per lane: 0.88 ms (ncu: latency-bound,
+0.21 eligible warps per cycle, DRAM 61 % busy; eight loads: 0.92 ms, sixteen: 1.37 ms: registers) → frames pulled into
+shared memory with 8-byte `cp.async` (no registers held while a warp's whole 3.6 KB run is in flight, 60 warps per SM),
+then written out twice from shared memory with streaming stores: **0.72 ms** in the bench (ncu 0.70 ms, 4.29 GB of DRAM
+traffic = 6.1 TB/s, DRAM 75 % busy); config 3 (slot-major ring, six separate runs per sample): 0.142 → 0.110 ms.
 
 ### Live policies (`bench.py --config live`: `Environment.take_turn()` with a device policy between observe and act)
 
@@ -140,6 +159,9 @@ eight: 0.92 ms; sixteen: 1.37 ms (registers).
 Round 1 at 8 GPUs: 2.22e10, 1.008 + 0.123 + 0.055 ms, e2e 1.50e10.  What is left at 8 GPUs is the tail of the step kernel at
 one eighth of the batch (3.46 waves: {b(g[8])['step']:.3f} ms against {k1:.2f} / 8 = {k1 / 8:.3f} ms) and the sample gather at a
 small batch; the box is one 24-core VM with a single NUMA node, where the end-to-end path moves 8 × (3.3 + 13.1) MB per ms.
+One GPU alone at one eighth of the batch (`bench.py --envs-total 131072`) runs the same end-to-end step in 1.019 ms against
+0.972 ms device-resident (step kernel 0.849 against 0.836 ms), so what the eight-rank end-to-end figure loses beyond that is
+contention between the ranks' host threads and DMA streams on that VM, not the pipeline.
 
 ---
 
