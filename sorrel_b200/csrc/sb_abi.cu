@@ -257,6 +257,16 @@ int make_dev(const SbWorldDesc* w, SbDev* out) {
     }
     d.cg_nseg[lg] = (int8_t)best;
     d.cg_len[lg] = (int8_t)((d.S + best - 1) / best);
+    // one stored plane (scatter_rows_onehot_seg): five cells per step, any segment length
+    best = 1, best_cost = 1 << 30;
+    for (int nseg = 1; nseg <= d.S; ++nseg) {
+      const int len = (d.S + nseg - 1) / nseg;
+      if ((nseg - 1) * len >= d.S) continue;
+      const int cost = ((d.S * nseg + lanes - 1) / lanes) * ((len + 4) / 5);
+      if (cost < best_cost) best = nseg, best_cost = cost;
+    }
+    d.rw_nseg[lg] = (int8_t)best;
+    d.rw_len[lg] = (int8_t)((d.S + best - 1) / best);
   }
   d.sparse_ok = (w->spawn_cdf_len == SB_SPARSE_KMAX && d.env_stride < 65536 && !ext) ? 1 : 0;
   if (d.sparse_ok) memcpy(d.cdf, w->spawn_cdf, sizeof(d.cdf));

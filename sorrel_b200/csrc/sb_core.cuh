@@ -92,6 +92,7 @@ struct SbDev {
   uint64_t channel8_hi;
   int32_t colgather_ok;  // fast_obs, 2 or 3 stored planes, K <= 16, not toroidal
   int8_t cg_nseg[6], cg_len[6];
+  int8_t rw_nseg[6], rw_len[6];  // the same for the segmented row-wise gather of one stored plane (five cells per step)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -160,6 +160,62 @@ __device__ __forceinline__ void scatter_rows_onehot_impl(const SbDev& d, const u
   }
 }
 
+// SEGMENTED form of the same gather: a lane takes a SEGMENT of a window row (d.rw_len cells; d.rw_nseg segments per row,
+// from the cost model in make_dev: trips x five-cell steps), so that a window whose rows outnumber the lanes by one --
+// 9x9 windows on the 8-lane agent slots of step_kernel_block: rows 0..7, then row 8 by one lane -- is not walked
+// twice at full cost (segments of 5 and 4 cells: 18 units = 3 trips of ONE step each instead of 2 trips of two).
+#ifndef SB_ROWSEG
+#define SB_ROWSEG 1
+#endif
+template <int LANES>
+__device__ __forceinline__ void scatter_rows_onehot_seg(const SbDev& d, const uint8_t* genv, uint16_t* srow16, int y,
+                                                        int x, int lane) {
+  constexpr int LG = LANES == 32 ? 5 : LANES == 16 ? 4 : LANES == 8 ? 3 : LANES == 4 ? 2 : 1;
+  const int S = d.S, g = d.rw_len[LG], units = S * d.rw_nseg[LG];
+  const int x0 = x - d.v;
+  const int jlo = max(0, -x0), jhi = min(S, d.W - x0);
+  const uint32_t tlo = (uint32_t)d.channel8_oob, thi = (uint32_t)(d.channel8_oob >> 32);
+  for (int un = lane; un < units; un += LANES) {
+    const int sg = (int)(((uint32_t)un * d.inv_S) >> 16), i = un - sg * S;  // segment-major: (segment, window row)
+    const int yy = y - d.v + i;
+    const bool row_in = (unsigned)yy < (unsigned)d.H;
+    const int off = yy * d.W + x0;
+    uint16_t* const srow = srow16 + i * S;
+    const int j_end = min(S, (sg + 1) * g);
+    for (int j0 = sg * g; j0 < j_end; j0 += 5) {
+      const int lc = min(max(jlo - j0, 0), 4), hc = min(max(jhi - j0, 0), 4);
+      uint32_t m4 = __funnelshift_lc(~0u, 0u, 8 * hc) & ~__funnelshift_lc(~0u, 0u, 8 * lc);
+      bool in5 = jlo <= j0 + 4 && j0 + 4 < jhi;
+      uint32_t w0 = 0u, w1 = 0u;
+      if (row_in) {
+        const int al = (off + j0) & ~3;
+        w0 = *reinterpret_cast<const uint32_t*>(genv + al);
+        w1 = *reinterpret_cast<const uint32_t*>(genv + al + 4);
+      } else {
+        m4 = 0u;
+        in5 = false;
+      }
+      const uint32_t sh = ((uint32_t)(off + j0) & 3u) * 8u;
+      uint32_t k4 = __funnelshift_r(w0, w1, sh);
+      const uint32_t k5 = in5 ? ((w1 >> sh) & 7u) : 7u;
+      k4 = (k4 & m4) | (0x07070707u & ~m4);
+      const uint32_t t = k4 & 0x07070707u;
+      const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);
+      uint32_t c4 = __byte_perm(tlo, thi, sel);
+      uint32_t c5 = __byte_perm(tlo, thi, k5) & 0xFFu;
+      const int cnt = j_end - j0;  // cells of the segment from j0 on
+      c4 |= ~__funnelshift_lc(~0u, 0u, 8 * min(cnt, 4));
+      if (cnt < 5) c5 = 255u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t code = (c4 >> (8 * e)) & 0xFFu;
+        if (code != 255u) srow[code * d.SS + j0 + e] = 0x3F80;
+      }
+      if (c5 != 255u) srow[c5 * d.SS + j0 + 4] = 0x3F80;
+    }
+  }
+}
+
 template <int LANES>
 __device__ __forceinline__ void scatter_rows_onehot(const SbDev& d, const uint8_t* genv, uint16_t* srow16, int y, int x,
                                                     int lane) {
@@ -273,9 +329,12 @@ __device__ __forceinline__ void scatter_cols_multi(const SbDev& d, const uint8_t
 // address lines up with an aligned shared address (ring rows are only 8-byte aligned: 600 B, 1944 B).
 // `genv` may point to shared or global memory.
 #ifndef SB_STREAM_UNROLL
-#define SB_STREAM_UNROLL 4  // vectors per trip of the stream-out loop of multi-plane worlds (long rows)
+#define SB_STREAM_UNROLL 4  // vectors per trip of the stream-out loop of long rows
 #endif
-template <int LANES, bool NP1, int NB = 1, bool ROWWISE = false>
+#ifndef SB_STREAM_LONG
+#define SB_STREAM_LONG 64  // one-plane worlds: rows of at least this many 16-byte vectors (9x9 windows: 121) take it too
+#endif
+template <int LANES, bool NP1, int NB = 1, int ROWWISE = 0>
 __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint32_t* ktab,
                                                 uint8_t* stage_raw, int y, int x, float* dst, int lane) {
   uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_raw);  // bf16: 0 / 1.0 (NP1) or a small plane count
@@ -292,9 +351,10 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
     constexpr int kScatterUnroll = (NB > 1) ? 1 : SB_SCATTER_UNROLL;
     // ROWWISE (planes staged in shared memory): one stored plane -> row-wise gather of narrow groups; several
     // stored planes -> column gather (scatter_cols_multi), any group width
-    const bool rowwise = ROWWISE && (NP1 ? d.rowwise_ok : d.colgather_ok);
+    const bool rowwise = ROWWISE != 0 && (NP1 ? d.rowwise_ok : d.colgather_ok);
     if (rowwise) {
-      if constexpr (NP1) scatter_rows_onehot<LANES>(d, genv, srow16, y, x, lane);
+      if constexpr (NP1 && ROWWISE == 2) scatter_rows_onehot_seg<LANES>(d, genv, srow16, y, x, lane);
+      else if constexpr (NP1) scatter_rows_onehot<LANES>(d, genv, srow16, y, x, lane);
       else scatter_cols_multi<LANES>(d, genv, srow16, y, x, lane);
     }
 #pragma unroll kScatterUnroll
@@ -376,7 +436,8 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
 #if SB_STREAM_UNROLL > 1
       // long rows (cleanup: 275 vectors): several vectors per trip, loads first (measured: cleanup 9.64 -> 9.55 ms;
       // the short rows of one-plane worlds gain nothing or lose, so they keep the simple loop)
-      for (; !NP1 && qv + (SB_STREAM_UNROLL - 1) * LANES < nvec; qv += SB_STREAM_UNROLL * LANES) {
+      for (; (!NP1 || nvec >= SB_STREAM_LONG) && qv + (SB_STREAM_UNROLL - 1) * LANES < nvec;
+           qv += SB_STREAM_UNROLL * LANES) {
         uint2 w[SB_STREAM_UNROLL];
 #pragma unroll
         for (int u = 0; u < SB_STREAM_UNROLL; ++u) w[u] = s2[qv + u * LANES];
@@ -490,7 +551,7 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
       bool rows = false;
       if constexpr (ROWS) rows = __all_sync(0xFFFFFFFFu, !valid || (env > 0 && env + 1 < (unsigned long long)d.N));
       if (ROWS && rows) {
-        emit_onehot_row<LANES, NP1, 1, true>(d, genv, ktab, stage_raw, y, x, dst, lane);
+        emit_onehot_row<LANES, NP1, 1, 1>(d, genv, ktab, stage_raw, y, x, dst, lane);
       } else {
         // window loads batched: 2 per lane cover a 5x5 window with 16 lanes, 4 per lane a 9x9 / 11x11 one with 32
         emit_onehot_row<LANES, NP1, (LANES == 16 ? 2 : 4)>(d, genv, ktab, stage_raw, y, x, dst, lane);
@@ -1113,7 +1174,7 @@ __global__ void __launch_bounds__(SB_THREADS, (RNG == SB_K_TAPE || RNG == SB_K_P
       } else if (NP1 || d.fast_obs) {
         // narrow groups on a staged plane gather the window row by row (scatter_rows_onehot)
         // (several staged planes: the column gather of scatter_cols_multi, any group width)
-        constexpr bool RW = STAGED && (NP1 ? LPE <= SB_ROWWISE_MAX_LPE : SB_COLGATHER != 0);
+        constexpr int RW = (STAGED && (NP1 ? LPE <= SB_ROWWISE_MAX_LPE : SB_COLGATHER != 0)) ? 1 : 0;
         emit_onehot_row<LPE, NP1, 1, RW>(d, genv, ktab, stage_raw, y, x, dsts[0], lane);
         if (p.a.d_obs_out) {
           __syncwarp();
@@ -1372,10 +1433,13 @@ __global__ void __launch_bounds__(SB_THREADS, (RNG == SB_K_TAPE || RNG == SB_K_P
 #ifndef SB_BLK_MINB
 #define SB_BLK_MINB 6
 #endif
+#ifndef SB_BLK_ORDER_TABLE
+#define SB_BLK_ORDER_TABLE 1
+#endif
 constexpr int BLK_THREADS = 128, BLK_SPW = SB_BLK_SPW, BLK_SLOTS = 4 * BLK_SPW, BLK_SL = 8;
 
 struct BlockLayout {
-  int q_off, plane_off, agent_off, mask_off, stage_off, stage_row, act_turns, total;
+  int q_off, plane_off, agent_off, mask_off, order_off, stage_off, stage_row, act_turns, total;
 };
 
 __host__ __device__ inline BlockLayout block_layout(const SbDev& d) {
@@ -1385,7 +1449,8 @@ __host__ __device__ inline BlockLayout block_layout(const SbDev& d) {
   L.act_turns = act_turns_ahead(BLK_THREADS, d.A);
   L.agent_off = L.plane_off + round_up(d.env_stride, 16) + 16;                // ... and after it (row-wise gathers)
   L.mask_off = L.agent_off + round_up(4 * (2 * d.A + L.act_turns * d.A), 16);  // yx, reward, action window
-  L.stage_off = L.mask_off + round_up(8 * d.A, 16);
+  L.order_off = L.mask_off + round_up(8 * d.A, 16);  // per warp: the ready agents of the level in list order, u8[64]
+  L.stage_off = L.order_off + (BLK_THREADS / 32) * 64;
   L.stage_row = BLK_SPW == 4 ? pad64mod128((d.obs_size + 4) * 2) : round_up((d.obs_size + 4) * 2, 32);
   L.total = L.stage_off + BLK_SLOTS * L.stage_row;
   return L;
@@ -1413,6 +1478,7 @@ __global__ void __launch_bounds__(BLK_THREADS, SB_BLK_MINB)
   int32_t* sact_win = reinterpret_cast<int32_t*>(srew + d.A);
   unsigned long long* smask = reinterpret_cast<unsigned long long*>(smem_raw + L.mask_off);
   uint8_t* srow = smem_raw + L.stage_off + slot_id * L.stage_row;
+  uint8_t* sorder = smem_raw + L.order_off + warp * 64;
   const uint32_t envid = (uint32_t)(d.env_id_base + (uint64_t)env);
   const uint32_t* __restrict__ rk = p.rk;
 
@@ -1535,14 +1601,26 @@ __global__ void __launch_bounds__(BLK_THREADS, SB_BLK_MINB)
       const uint64_t ready = (uint64_t)__ballot_sync(0xFFFFFFFFu, rd_lo) |
                              ((uint64_t)__ballot_sync(0xFFFFFFFFu, rd_hi) << 32);
       const int n = __popcll(ready);
+#if SB_BLK_ORDER_TABLE
+      // the k-th ready agent: every warp writes its own copy of the rank -> agent table (a lane knows the rank of its
+      // two agents from a popcount; finding the k-th set bit of a 64-bit mask is a ~40-instruction routine)
+      if (rd_lo) sorder[__popcll(ready & ((1ull << a_lo) - 1ull))] = (uint8_t)a_lo;
+      if (rd_hi) sorder[__popcll(ready & ((1ull << a_hi) - 1ull))] = (uint8_t)a_hi;
+      __syncwarp();
+#endif
       for (int r0 = 0; r0 < n; r0 += BLK_SLOTS) {  // uniform trip count; a slot without an agent only synchronises
         const int k = r0 + slot_id;
+#if SB_BLK_ORDER_TABLE
+        const int a = (has_slot && k < n) ? (int)sorder[k] : -1;
+#else
         const int a = (has_slot && k < n) ? nth_set_bit64(ready, k) : -1;
+#endif
         uint32_t yx = a >= 0 ? spos[a] : 0u;
         float* dst = a >= 0 ? ring0 + (size_t)a * (size_t)p.buf.states_row_stride +
                                   (size_t)slot * (size_t)p.buf.states_slot_stride
                             : nullptr;
-        emit_onehot_row<BLK_SL, true, 1, true>(d, plane, nullptr, srow, (int)(yx >> 16), (int)(yx & 0xFFFFu), dst, sl);
+        emit_onehot_row<BLK_SL, true, 1, SB_ROWSEG ? 2 : 1>(d, plane, nullptr, srow, (int)(yx >> 16), (int)(yx & 0xFFFFu),
+                                                            dst, sl);
         // every lane of the subgroup has read the window (barrier inside emit_onehot_row): move
         if (a >= 0 && sl == 0) {
           srew[a] = sb_agent_act(d, plane, &yx, sact[a], true, err);
