@@ -718,6 +718,170 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBSROW_MINB)
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Standalone observation with BULK-ASYNC stores (one-hot worlds with one stored plane, windows up to 16 wide, no
+// appended floats).  The row-wise kernel above moves every row through LDS -> convert -> STG.128 and zeroes its bf16
+// staging row on the way: ~8 shared-memory and 8 global-store instructions per lane per row, and ncu shows it bound
+// by exactly that (mio_throttle, 18 % issue-slot use, 58 % of the HBM peak).  Here a group of 16 lanes scatters the
+// ones of M consecutive rows (M = 1, 2 or 4: the smallest count whose bytes are a multiple of 16; 9x9 windows: two rows
+// = 3888 B) as f32 into one of two shared-memory tiles and ONE lane hands the finished tile to the bulk-copy engine
+// (`cp.async.bulk.global.shared::cta`, tracked by bulk groups): the rows leave the SM as one contiguous 16-byte-aligned
+// burst with no per-element instruction, while the group already gathers the next tile into the other buffer.  A tile
+// is zeroed (128-bit shared stores) only when it comes up for reuse, after `cp.async.bulk.wait_group.read` says the
+// engine has finished reading it.  The window loads stay software-pipelined (pair k+1 / position k+2 in flight).
+// ----------------------------------------------------------------------------------------------
+#ifndef SB_OBS_BULK
+#define SB_OBS_BULK 1
+#endif
+constexpr int OBS_BULK_THREADS = 128;
+__device__ __forceinline__ void bulk_store_tile(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+template <bool PARTIAL>
+__global__ void __launch_bounds__(OBS_BULK_THREADS)
+    observe_bulk_kernel(const __grid_constant__ SbDev d, const uint8_t* __restrict__ grid,
+                        const int32_t* __restrict__ agent_pos, float* __restrict__ out, int rows_per_tile,
+                        unsigned pairs_per_stream, long long grid_bytes) {
+  // every 16-lane group walks its own STREAM of consecutive tiles.  (A form in which the two halves of a warp fill the
+  // even / odd rows of one tile -- half the shared memory per warp -- was measured: 9x9 windows 0.142 -> 0.137 ms, 5x5
+  // windows 0.182 -> 0.202 ms; not kept.)
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int LANES = OBS_ROW_LANES;
+  const int lane = threadIdx.x & (LANES - 1);
+  constexpr int P = 1;
+  const int M = rows_per_tile, tile_floats = M * d.obs_size;  // tile_floats * 4 is a multiple of 16
+  const int stream_in_block = (int)(threadIdx.x / LANES);
+  constexpr int streams_per_block = OBS_BULK_THREADS / LANES;
+  const int zl = lane;
+  constexpr int zn = LANES;  // lanes that zero / copy a tile together
+  const bool elected = zl == 0;
+  float* const tiles = reinterpret_cast<float*>(smem_raw) + (size_t)stream_in_block * 2 * tile_floats;
+  for (int e = zl; e < 2 * tile_floats / 4; e += zn) reinterpret_cast<float4*>(tiles)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  const unsigned long long pairs = (unsigned long long)d.N * d.A;
+  const unsigned long long stream_first =
+      ((unsigned long long)blockIdx.x * streams_per_block + stream_in_block) * pairs_per_stream;
+  const unsigned long long first = stream_first;
+  const int ng = (d.S + 4) / 5;
+  const uint32_t tlo = (uint32_t)d.channel8_oob, thi = (uint32_t)(d.channel8_oob >> 32);
+
+  auto load_pos = [&](unsigned long long pair) -> int { return pair < pairs ? __ldg(agent_pos + pair) : -1; };
+  auto issue = [&](unsigned long long env, int pos, uint32_t (&w0)[OBS_ROW_MAXG], uint32_t (&w1)[OBS_ROW_MAXG]) {
+    const int y = pos < 0 ? 0 : (d.inv_W ? (int)__umulhi((uint32_t)pos, d.inv_W) : pos / d.W);
+    const int x = pos < 0 ? 0 : pos - y * d.W;
+    const int yy = y - d.v + lane;
+    const bool row_in = pos >= 0 && lane < d.S && (unsigned)yy < (unsigned)d.H;
+    const long long base = (long long)env * d.env_stride + (long long)yy * d.W + (x - d.v);
+#pragma unroll
+    for (int g = 0; g < OBS_ROW_MAXG; ++g) {
+      w0[g] = 0u, w1[g] = 0u;
+      if (g < ng && row_in) {
+        const long long al = (base + 5 * g) & ~3ll;
+        if (al >= 0) w0[g] = __ldg(reinterpret_cast<const uint32_t*>(grid + al));
+        if (al + 8 <= grid_bytes) w1[g] = __ldg(reinterpret_cast<const uint32_t*>(grid + al + 4));
+      }
+    }
+  };
+  auto advance = [&](unsigned long long& env, int& a) {  // P pairs further
+    a += P;
+    while (a >= d.A) {
+      a -= d.A;
+      ++env;
+    }
+  };
+
+  unsigned long long env_c = first / (unsigned)d.A;
+  int a_c = (int)(first - env_c * (unsigned)d.A);
+  unsigned long long env_n = env_c;
+  int a_n = a_c;
+  advance(env_n, a_n);
+  int pos_c = load_pos(first), pos_n = load_pos(first + P);
+  uint32_t cw0[OBS_ROW_MAXG], cw1[OBS_ROW_MAXG], nw0[OBS_ROW_MAXG], nw1[OBS_ROW_MAXG];
+  issue(env_c, pos_c, cw0, cw1);
+
+  const int steps_per_tile = M / P;            // rows of a tile this half fills
+  const unsigned steps = pairs_per_stream / P;  // pairs this half walks
+  int rs = 0;          // step within the current tile
+  unsigned tile = 0;   // tiles this stream has started
+  for (unsigned k = 0; k < steps; ++k) {  // uniform trip count: both halves of a warp stay in step
+    const unsigned long long pair = first + (unsigned long long)k * P;
+    float* const buf = tiles + (tile & 1u) * tile_floats;
+    if (rs == 0 && tile >= 2) {
+      // this buffer held tile - 2: the engine must have finished READING it before it is zeroed and refilled
+      if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      for (int e = zl; e < tile_floats / 4; e += zn) reinterpret_cast<float4*>(buf)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+    }
+    issue(env_n, pos_n, nw0, nw1);                                   // the half's next pair: in flight during the work below
+    const int pos_nn = load_pos(pair + 2ull * (unsigned)P);  // ... and the one after
+    if (pos_c >= 0 && lane < d.S) {
+      // ---- scatter row `lane` of the window (scatter_rows_onehot_impl on the words loaded one iteration ago) ----
+      const int y = d.inv_W ? (int)__umulhi((uint32_t)pos_c, d.inv_W) : pos_c / d.W, x = pos_c - y * d.W;
+      const int x0 = x - d.v, yy = y - d.v + lane;
+      const int jlo = max(0, -x0), jhi = min(d.S, d.W - x0);
+      const bool row_in = (unsigned)yy < (unsigned)d.H;
+      const int boff = yy * d.W + x0;
+      float* const srow = buf + rs * d.obs_size + lane * d.S;
+#pragma unroll
+      for (int g = 0; g < OBS_ROW_MAXG; ++g) {
+        if (g < ng) {
+          const int j0 = 5 * g;
+          const int lc = min(max(jlo - j0, 0), 4), hc = min(max(jhi - j0, 0), 4);
+          uint32_t m4 = __funnelshift_lc(~0u, 0u, 8 * hc) & ~__funnelshift_lc(~0u, 0u, 8 * lc);
+          bool in5 = jlo <= j0 + 4 && j0 + 4 < jhi;
+          if (!row_in) m4 = 0u, in5 = false;
+          const uint32_t sh = ((uint32_t)(boff + j0) & 3u) * 8u;
+          uint32_t k4 = __funnelshift_r(cw0[g], cw1[g], sh);
+          const uint32_t k5 = in5 ? ((cw1[g] >> sh) & 7u) : 7u;
+          k4 = (k4 & m4) | (0x07070707u & ~m4);
+          const uint32_t t = k4 & 0x07070707u;
+          const uint32_t sel = __byte_perm(t | (t >> 4), 0u, 0x4420);
+          uint32_t c4 = __byte_perm(tlo, thi, sel);
+          uint32_t c5 = __byte_perm(tlo, thi, k5) & 0xFFu;
+          if (PARTIAL) {
+            const int cnt = d.S - j0;
+            c4 |= ~__funnelshift_lc(~0u, 0u, 8 * min(cnt, 4));
+            if (cnt < 5) c5 = 255u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t code = (c4 >> (8 * u)) & 0xFFu;
+            if (code != 255u) srow[code * d.SS + j0 + u] = 1.0f;
+          }
+          if (c5 != 255u) srow[c5 * d.SS + j0 + 4] = 1.0f;
+        }
+      }
+    }
+    if (++rs == steps_per_tile) {  // the tile is complete
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the scattered ones, seen by the copy engine
+      __syncwarp();
+      const unsigned long long t0 = stream_first + (unsigned long long)tile * (unsigned)M;  // first pair of the tile
+      if (t0 + (unsigned)M <= pairs) {
+        if (elected) bulk_store_tile(out + (size_t)t0 * d.obs_size, buf, (uint32_t)tile_floats * 4u);
+      } else if (t0 < pairs) {  // the last tile of the batch is short: plain stores of its valid rows
+        const int n_valid = (int)(pairs - t0) * d.obs_size;
+        for (int e = zl; e < n_valid; e += zn) out[(size_t)t0 * d.obs_size + e] = buf[e];
+      }
+      if (elected) asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // (an empty group keeps the count)
+      rs = 0;
+      ++tile;
+    }
+    // rotate the pipeline
+#pragma unroll
+    for (int g = 0; g < OBS_ROW_MAXG; ++g) cw0[g] = nw0[g], cw1[g] = nw1[g];
+    pos_c = pos_n;
+    pos_n = pos_nn;
+    env_c = env_n, a_c = a_n;
+    advance(env_n, a_n);
+  }
+  // shared memory must outlive the reads of the copy engine
+  if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
 int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos, float* out, cudaStream_t s) {
   const bool np1 = d.fast_obs && d.n_planes == 1;
   // row-wise window gather (one lane per window row) when the rows fit the 16 lanes of a half warp
@@ -750,6 +914,39 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
     count_launch();
     return check_launch();
   };
+  if (SB_OBS_BULK && np1 && d.rowwise_ok && d.S <= 16 && !d.obs_extra && !d.obs_flag &&
+      (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {  // bulk-async stores of whole tiles of rows
+    const int M = (d.obs_size & 3) == 0 ? 1 : ((d.obs_size & 1) == 0 ? 2 : 4);  // rows per 16-byte-multiple tile
+    const int streams = OBS_BULK_THREADS / OBS_ROW_LANES;  // tile streams per block
+    const int sm = streams * 2 * M * d.obs_size * 4;
+    // f32 tiles cost shared memory: the bulk form wins while ~9 blocks stay resident (5x5 windows, 1200-byte tiles:
+    // 0.224 -> 0.182 ms = 0.75 -> 0.92 of the HBM peak at 2^20 x 1; 0.407 -> 0.332 ms at 262144 x 8); with 3888-byte tiles
+    // (9x9 windows) three blocks fit and it loses to the bf16 row kernel (0.142 against 0.137 ms)
+    if (sm <= 24 * 1024) {
+      auto launch_bulk = [&](auto kern) -> int {
+        if (sm > 48 * 1024) {
+          const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+          if (e != cudaSuccess) return note_cuda_error(e);
+        }
+        int dev = 0, sms = 148, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OBS_BULK_THREADS, sm) != cudaSuccess || per_sm < 1)
+          per_sm = 2;
+        unsigned long long blocks = (pairs + streams - 1) / streams;
+        if (blocks > (unsigned long long)sms * per_sm) blocks = (unsigned long long)sms * per_sm;
+        unsigned long long pps = (pairs + blocks * streams - 1) / (blocks * streams);
+        pps = (pps + M - 1) / M * M;  // whole tiles per stream: tiles never straddle two streams
+        if (pps > 0xFFFFFFFFull) return SB_EUNSUPPORTED;
+        blocks = (pairs + pps * streams - 1) / (pps * streams);
+        kern<<<(unsigned)blocks, OBS_BULK_THREADS, sm, s>>>(d, grid, agent_pos, out, M, (unsigned)pps,
+                                                            (long long)d.N * d.env_stride);
+        count_launch();
+        return check_launch();
+      };
+      return d.S5 == d.S ? launch_bulk(observe_bulk_kernel<false>) : launch_bulk(observe_bulk_kernel<true>);
+    }
+  }
   if (rows && !d.obs_extra && !d.obs_flag && SB_OBS_PIPELINED) {  // software-pipelined row gather
     const int sb = round_up((d.obs_size + 4) * 2, 16);
     const int sm = groups * sb;

@@ -449,9 +449,11 @@ def test_observe_random(general, cuda_device):
 
 
 @pytest.mark.parametrize("H,W,v,A,N", [(9, 9, 4, 3, 5), (16, 23, 3, 6, 9), (21, 21, 5, 4, 37), (33, 18, 6, 7, 11),
-                                       (40, 40, 7, 9, 6), (21, 21, 2, 8, 40), (128, 128, 4, 64, 3)])
+                                       (40, 40, 7, 9, 6), (21, 21, 2, 8, 40), (128, 128, 4, 64, 3),
+                                       (21, 21, 2, 3, 5), (12, 12, 1, 3, 7), (15, 14, 2, 1, 9)])
 def test_standalone_observe_all_window_widths(H, W, v, A, N, cuda_device):
-    """`sb_observe` (the software-pipelined row-wise kernel for 7..16-wide windows, the plain one otherwise) on worlds
+    """`sb_observe` (the bulk-async kernel for small rows -- whole and short last tiles: odd pair counts --, the
+    software-pipelined row-wise kernel for 7..16-wide windows, the plain one otherwise) on worlds
     without walls, with agents parked on corners, edges and the interior of the FIRST and LAST instance as well (the
     row gather may touch bytes outside an instance's planes: guarded at the ends of the allocation), several launches
     back to back (the staging rows must come back zeroed)."""
@@ -475,6 +477,39 @@ def test_standalone_observe_all_window_widths(H, W, v, A, N, cuda_device):
     for _ in range(3):
         obs = eng.observe().cpu().numpy()
         for n in list(range(min(N, 3))) + [N - 1]:
+            for a in range(A):
+                y, x = divmod(int(cells[n, a]), W)
+                np.testing.assert_array_equal(obs[n, a], R.observe(spec, full[n], y, x).astype(np.float32),
+                                              err_msg=f"instance {n} agent {a} at ({y}, {x})")
+
+
+@pytest.mark.parametrize("v,A,N", [(1, 3, 5), (2, 5, 3), (1, 1, 2), (2, 2, 34)])
+def test_standalone_observe_odd_row_size(v, A, N, cuda_device):
+    """Seven observation channels: rows of 7 * S * S floats (odd), so the bulk-async kernel ships FOUR rows per tile
+    (the smallest multiple of 16 bytes); pair counts that leave a short last tile of one, two or three rows."""
+    import dataclasses
+
+    rng = np.random.RandomState(17 * v + A)
+    H, W = 11, 13
+    base = R.treasurehunt_spec(H, W, A, v, 0.0)
+    app = np.zeros((7, 7), dtype=np.float64)
+    for k in range(1, 6):
+        app[k, k + 1] = 1.0  # channel 0 and 1 stay empty, kind k shows on channel k + 1
+    spec = dataclasses.replace(base, appearance=app)
+    assert spec.obs_size % 2 == 1
+    eng = _engine(spec, N, cuda_device)
+    eng.reset()
+    g = eng.grid.cpu().numpy()
+    g[:, 0, : H * W] = rng.choice([0, 0, 1, 2, 3, 4], size=(N, H * W)).astype(np.uint8)
+    cells = np.stack([rng.permutation(H * W)[:A] for _ in range(N)]).astype(np.int32)
+    for n in range(N):
+        g[n, 0, cells[n]] = 5
+    eng.grid.copy_(torch.from_numpy(g))
+    eng.agent_pos.copy_(torch.from_numpy(cells))
+    full = eng.grid_numpy()
+    for _ in range(3):  # several launches: the tiles must come back zeroed
+        obs = eng.observe().cpu().numpy()
+        for n in range(N):
             for a in range(A):
                 y, x = divmod(int(cells[n, a]), W)
                 np.testing.assert_array_equal(obs[n, a], R.observe(spec, full[n], y, x).astype(np.float32),
