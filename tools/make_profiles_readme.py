@@ -107,10 +107,30 @@ sparse, while the sample gather prefers agent-major there — `Environment` pick
 ### Config 4: block per instance (`r02_c4_kernel_*`)
 
 `sb::step_kernel_block`, 2048 instances × 10 turns: 0.989 ms (one warp per instance, planes in L2, round-1 kernel on the
-same box) → **0.762 ms**; 8192 instances: 3.66 → 2.63 ms.  ncu: 78 registers, 36.9 KB shared memory per block, 6 blocks
-per SM, issue slots 59 %, `barrier` 2.2 stall cycles per issue (the level barriers), 2.6 GB written.  Rejected: 12 agent
-slots per block in 31 KB (7 blocks per SM: 2 waves instead of 2.3 at 2048 instances): 0.799 / 1.495 / 2.871 ms at 2048 /
-4096 / 8192 instances against 0.767 / 1.370 / 2.629.
+same box) → 0.762 ms (first block kernel) → **0.704 ms** (0.71 algorithmic); 8192 instances: 3.66 → 2.63 → **2.44 ms**
+(0.82); 19×19 windows at 1024 instances: 0.931 → 0.864 ms (0.53).  The second step, one A/B of three changes on the same box
+(0.773 → 0.707 ms): the SEGMENTED row-wise gather (9×9 windows on the 8-lane agent slots: 9 rows were 2 trips of two
+five-cell steps each, the second trip with one lane working; segments of 5 and 4 cells = 18 units = 3 trips of one step),
+a per-warp rank → agent table instead of the k-th-set-bit routine (`__fns`, 7 % of the instructions), and the stream-out
+of long rows four vectors per trip.  ncu (final): 74 registers, 37.2 KB shared memory per block, 6 blocks per SM, issue
+slots 59 %, `barrier` 1.9 stall cycles per issue (the level barriers), 2.6 GB written, 4.45e8 warp-instructions (4.89e8
+before).  Rejected: 12 agent slots per block in 31 KB (7 blocks per SM: 2 waves instead of 2.3 at 2048 instances): 0.799 /
+1.495 / 2.871 ms at 2048 / 4096 / 8192 instances against 0.767 / 1.370 / 2.629.
+
+### Standalone observation (`sb_observe`, the "obs-kernel HBM roofline study" of config 4 and the small-row shapes)
+
+| shape | row-wise bf16 kernel (LDS → convert → `STG.128`) | bulk-async kernel |
+|---|---|---|
+| 2^20 × 1 agent, 5×5 windows (600-byte rows, tiles of 2 rows) | 0.224 ms (0.75 of the HBM peak) | **0.182 ms (0.92)** |
+| 262144 × 8 agents, 5×5 windows | 0.407 ms (0.52) | **0.333 ms (0.63)** |
+| 65536 × 4 agents, 32×32 maps, 7×7 windows (1176-byte rows, tiles of 2) | **0.080 ms (0.72)** | 0.085 ms (two halves of a warp per tile) |
+| 4096 × 64 agents, 128×128 maps, 9×9 windows (1944-byte rows, tiles of 2) | **0.136 ms (0.65)** | 0.142 ms (three blocks per SM); 0.137 ms with the two halves of a warp filling one tile |
+
+The bulk-async kernel (`observe_bulk_kernel`: M rows = a multiple of 16 bytes scattered as f32 into a double-buffered
+shared-memory tile, ONE `cp.async.bulk.global.shared::cta` per tile — `UBLKCP.G.S` in the SASS —, tiles zeroed on reuse
+after `cp.async.bulk.wait_group.read`) removes every per-element instruction of the stream-out, but its f32 tiles cost
+shared memory: it is used while ~9 blocks stay resident (tiles up to 1536 bytes); 9×9 windows stay on the bf16 row kernel
+(for which 4 / 6 / 8 resident blocks were measured: 0.136 / 0.144 / 0.155 ms — registers, not warps, are what it needs).
 
 ### Cleanup example (`r02_cleanup_kernel_*`, generic variant)
 
