@@ -91,6 +91,7 @@ Round 1, same shapes: config 2 0.21 (T = 100) / 0.07 (T = 1); config 3 0.47 at 1
 | (rejected) `__launch_bounds__(128, 7 / 6 / 5)` = 66 / 74 / 88 registers | 6.75 / 6.78 / 6.87 ms (at 6.84); 6.31 / 6.31 (at 6.28) | fewer rematerialisations, fewer warps: a wash |
 | (rejected) one row-gather loop with a per-group cell count instead of two instantiations | +3 % dense, +9 % sparse, +6 % config 3 | |
 | (rejected) two-pass sweep: pass 1 tests the random bytes only (a chunk whose 16 bytes all fail level 1 cannot spawn: 88 % of them) and queues the other chunks; pass 2 redoes their Philox call and applies the exact filter | 6.38 ms against 6.29 (config 3: 0.526 / 0.514, config 2: 0.328 / 0.297) | ncu: 5.27e9 warp-instructions instead of 5.35e9 — the exact filter saved (33 → 15 instructions per chunk) is spent again on the second Philox call of the queued chunks and on the pushes; results identical (parity suite green), not kept |
+| (rejected) one shared-memory RECORD per instance (planes, agent words, staging row behind a single base register) instead of one array per kind of data — the per-line profile charges ~7 % of the instructions to re-deriving the three bases under the 64-register cap | 6.31 ms against 6.28 (sparse sampler 5.04 / 4.79, cleanup 8.33 / 8.12) | the compiler rematerialises as before and the staging rows lose their 64-mod-128 stride |
 | (rejected) wave shaping: cap the resident blocks per SM (extra dynamic shared memory) when that makes the wave count integral, e.g. one eighth of the batch = 4096 blocks: 3.46 waves at 8 per SM, 3.95 at 7 | 131072 instances: 0.846 ms against 0.838; 196608: 1.244 against 1.232 | the partial last wave already runs faster (fewer warps per scheduler); lower residency costs more than the tail |
 
 ### Ring layout (config 3, 16384 × 8 agents × 25 turns, `step_kernel<8,1,1,1>`)
