@@ -1895,6 +1895,75 @@ static int launch_block(const SbDev& d, StepParams p, cudaStream_t s, SbStepPlan
 }
 #endif  // SB_ONLY_LPE
 
+#ifndef SB_ONLY_LPE
+// ----------------------------------------------------------------------------------------------
+// Split-phase launch that ONLY moves one agent (`act_agent` set, nothing to observe afterwards, no sweep): the last
+// launch of every live-policy turn (Agent.act of the last agent slot, agents/agent.py:166-173).  MovingAgent.act
+// touches two cells, one position and the ring scalars, so one THREAD per instance works on the planes in place in
+// global memory -- ~5 sectors per instance instead of staging the whole instance into shared memory and writing it
+// back (896 bytes at 21x21).  Worlds with facings / beams / all-layer rewards / agent states keep the general kernel.
+// ----------------------------------------------------------------------------------------------
+#ifndef SB_ACT_ONLY
+#define SB_ACT_ONLY 1
+#endif
+constexpr int ACT_THREADS = 256;
+__global__ void __launch_bounds__(ACT_THREADS)
+    act_only_kernel(const __grid_constant__ SbDev d, const __grid_constant__ StepParams p) {
+  const long long env = (long long)blockIdx.x * ACT_THREADS + threadIdx.x;
+  if (env >= d.N) return;
+  const int a = p.a.act_agent;
+  const size_t ia = (size_t)env * d.A + a;
+  uint8_t* genv = p.grid + (size_t)env * d.env_stride;
+  const uint32_t tick = p.a.d_clock ? p.a.d_clock[0] : p.a.tick0;
+  int action = 0;
+  if (p.a.policy == SB_POLICY_UNIFORM) {
+    const SbU4 w = sb_philox_rk((uint32_t)(d.env_id_base + (uint64_t)env), tick, (uint32_t)a, SB_DOM_ACTION, p.rk);
+    action = (int)sb_bounded(w.x, w.y, (uint32_t)d.n_actions);
+  } else if (p.a.d_actions) {
+    action = p.a.actions_u8 ? (int)reinterpret_cast<const uint8_t*>(p.a.d_actions)[ia] : p.a.d_actions[ia];
+  }
+  const int pos = p.agent_pos[ia];
+  const int y = pos / d.W;
+  uint32_t yx = ((uint32_t)y << 16) | (uint32_t)(pos - y * d.W);
+  uint32_t err = 0;
+  const float reward = sb_agent_act(d, genv, &yx, action, true, err);
+  p.agent_pos[ia] = (int32_t)((yx >> 16) * d.W + (yx & 0xFFFFu));
+  p.total_reward[env] += (double)reward;  // world.total_reward += reward (agent.py:172)
+  if (p.has_buf) {  // the scalar part of Buffer.add (buffers.py:57-62)
+    const int slot = p.a.d_clock ? (int)p.a.d_clock[1] : p.a.slot0;
+    const size_t at = (size_t)slot * ((size_t)d.N * d.A) + ia;
+    p.buf.d_actions[at] = (int64_t)action;
+    p.buf.d_rewards[at] = reward;
+    p.buf.d_dones[at] = 0.0f;
+    if (p.buf.d_positions)
+      *reinterpret_cast<longlong2*>(p.buf.d_positions + 2 * at) =
+          make_longlong2((long long)(yx >> 16), (long long)(yx & 0xFFFFu));
+  }
+  if (p.a.d_reward_out) p.a.d_reward_out[ia] = reward;
+  if (p.a.d_action_out) p.a.d_action_out[ia] = action;
+  if (err && p.a.d_error) atomicOr(p.a.d_error, err);
+}
+
+static bool act_only_applies(const SbDev& d, const StepParams& p) {
+  if (!SB_ACT_ONLY || p.a.mode != SB_MODE_SPLIT || p.a.do_sweep || p.a.act_agent < 0 || p.a.obs_agent != -1) return false;
+  if (d.ext_act || d.agent_kind_alt >= 0 || d.obs_flag) return false;
+  return p.a.tune_lpe == 0 && p.a.tune_staged == 0;
+}
+
+static int launch_act_only(const SbDev& d, StepParams p, cudaStream_t s, SbStepPlan* plan) {
+  p.rk[0] = (uint32_t)p.a.seed, p.rk[1] = (uint32_t)(p.a.seed >> 32);  // the stream words of sb_philox_rk
+  const long long blocks = ((long long)d.N + ACT_THREADS - 1) / ACT_THREADS;
+  if (plan) {
+    plan->lpe = 1, plan->kernel_rng = SB_K_TAPE, plan->fast_onehot = 0, plan->staged = 0, plan->par = 0;
+    plan->threads = ACT_THREADS, plan->smem_bytes = 0, plan->blocks = blocks;
+    return SB_OK;
+  }
+  act_only_kernel<<<(unsigned)blocks, ACT_THREADS, 0, s>>>(d, p);
+  count_launch();
+  return check_launch();
+}
+#endif  // SB_ONLY_LPE
+
 // ----------------------------------------------------------------------------------------------
 // launch
 // ----------------------------------------------------------------------------------------------
@@ -2004,6 +2073,7 @@ int launch_step(const SbDev& d, const StepParams& p, cudaStream_t s, SbStepPlan*
   if (hint != 0 && hint != 2 && hint != 4 && hint != 8 && hint != 16 && hint != 32 && hint != 128) return SB_EINVAL;
   if (p.a.tune_staged < -1 || p.a.tune_staged > 1 || p.a.tune_par < -1 || p.a.tune_par > 0) return SB_EINVAL;
   if (p.a.tune_staged < 0 && hint != 0 && hint != 32) return SB_EINVAL;
+  if (act_only_applies(d, p)) return launch_act_only(d, p, s, plan);
   if (block_kernel_applies(d, p, kr)) return launch_block(d, p, s, plan);
   if (hint == 128) return SB_EUNSUPPORTED;  // the block-per-instance kernel was asked for but does not apply
   switch (pick_lpe(d, hint, stage_planes(d, p.a.tune_staged), kr == SB_K_SPARSE)) {
