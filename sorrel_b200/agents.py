@@ -39,6 +39,8 @@ class Agent(Entity):
     def get_action(self, state: torch.Tensor) -> torch.Tensor:
         """treasurehunt/agents.py:34-41: stack the previous n_frames-1 observations with `state`."""
         prev = self.model.memory.current_state()  # [N, F-1, obs]
+        if prev.shape[1] == 0:  # n_frames == 1: nothing to stack (a cat would still copy every row: 630 MB at 2^20)
+            return self.model.take_action(state)
         stacked = torch.cat((prev.reshape(prev.shape[0], -1), state), dim=1)
         return self.model.take_action(stacked)
 
