@@ -640,7 +640,8 @@ def run_live(a):
         for _ in range(3):
             env.take_turn()
         if mode == "graph":
-            env.enable_turn_graph()
+            # large batches: one graph per ring slot (the policy reads the ring row itself; no second copy of the rows)
+            env.enable_turn_graph(per_slot=N * A * env.engine.spec.obs_size * 4 > 64e6)
         clocks = None if (a.no_clocks or mode == "eager") else ClockSampler(dev.index or 0, period=0.01)
         turns = max(a.steps, 100)
         torch.cuda.synchronize()

@@ -38,6 +38,9 @@ class Agent(Entity):
 
     def get_action(self, state: torch.Tensor) -> torch.Tensor:
         """treasurehunt/agents.py:34-41: stack the previous n_frames-1 observations with `state`."""
+        stacked = self.env._stacked_view(self.index) if self.env is not None else None
+        if stacked is not None:  # the frames already sit next to each other in the ring: no copy
+            return self.model.take_action(stacked)
         prev = self.model.memory.current_state()  # [N, F-1, obs]
         if prev.shape[1] == 0:  # n_frames == 1: nothing to stack (a cat would still copy every row: 630 MB at 2^20)
             return self.model.take_action(state)

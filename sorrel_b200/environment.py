@@ -126,7 +126,8 @@ class Environment:
             return
         if self._turn_graph is not None:  # the whole turn (every agent's phases and policy) as one graph replay
             self._sync_turn_clock()
-            self._turn_graph.replay()
+            graph = self._turn_graph[self.buffer.idx] if isinstance(self._turn_graph, list) else self._turn_graph
+            graph.replay()
             self.engine.tick += 1  # (the eager path advances it in the first phase launch of the turn)
             self._after_turn()
             return
@@ -169,15 +170,21 @@ class Environment:
                   "sb_clock_advance")
             self._turn_clock.held = want
 
-    def enable_turn_graph(self) -> None:
+    def enable_turn_graph(self, per_slot: bool = False) -> None:
         """Live policies (anything but the in-kernel `RandomModel`): capture ONE WHOLE TURN -- for every agent slot in
         list order [sweep +] observe, frame stacking, `model.take_action`, act -- as a CUDA graph, with the tick and
         the ring slot kept in device memory.  `take_turn()` then is one graph replay: an on-GPU policy runs with no
         host work between the phases, exactly in the order of Agent.transition (agents/agent.py:155-173).
 
         Requirements: every model's `take_action` must be capturable (device tensors in, device tensor out, no host
-        synchronisation, static shapes).  Observations reach the policy through one fixed tensor (the kernel writes
-        each row to its ring slot AND there), frame stacks through `Buffer.current_state()`'s device-clock form."""
+        synchronisation, static shapes).
+
+        `per_slot=False`: ONE graph.  Observations reach the policy through one fixed tensor (the kernel writes each row
+        to its ring slot AND there), frame stacks through `Buffer.current_state()`'s device-clock form (a copy).
+        `per_slot=True`: one graph PER RING SLOT (`capacity` captures sharing one memory pool), each with the addresses
+        of its slot baked in: the policy reads the observation straight from the ring slot the kernel wrote and the
+        frame stack is the usual zero-copy view, so a turn writes every row once.  Worth it for large batches, where the
+        second copy of the rows costs more than anything else the graph saves."""
         from .graphs import DeviceClock
 
         if self._fusable:
@@ -185,19 +192,33 @@ class Environment:
         eng = self.engine
         A = len(self.agents)
         self._turn_clock = DeviceClock(eng.device)
-        self.buffer.device_clock = self._turn_clock
-        self._obs_fixed = torch.zeros((1, eng.N, A, eng.spec.obs_size), dtype=torch.float32, device=eng.device)
+        if not per_slot:
+            self.buffer.device_clock = self._turn_clock
+            self._obs_fixed = torch.zeros((1, eng.N, A, eng.spec.obs_size), dtype=torch.float32, device=eng.device)
         # one eager turn in this mode first: CUDA loads modules lazily and that cannot be captured
         self._sync_turn_clock()
         self._take_turn_split()
         self._after_turn()
         torch.cuda.synchronize(eng.device)
         tick = eng.tick
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self._take_turn_split()
-        eng.tick = tick  # capturing ran the host-side tick bookkeeping of a turn that was not executed
-        self._turn_graph = graph
+        if not per_slot:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._take_turn_split()
+            eng.tick = tick  # capturing ran the host-side tick bookkeeping of a turn that was not executed
+            self._turn_graph = graph
+            return
+        idx, graphs, pool = self.buffer.idx, [], None
+        for slot in range(self.buffer.capacity):  # the kernels read tick / slot from the device clock; the HOST-side
+            self.buffer.idx = slot                # views (observation row, frame stack) are what gets baked in per slot
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=pool):
+                self._take_turn_split()
+            pool = graph.pool() if pool is None else pool
+            eng.tick = tick
+            graphs.append(graph)
+        self.buffer.idx = idx
+        self._turn_graph = graphs
 
     def take_turns(self, num_turns: int, rng: str = "philox") -> None:
         """`num_turns` x take_turn() in ONE launch (in-kernel policies only).  `rng`: "philox" draws one random byte
@@ -260,6 +281,20 @@ class Environment:
         return self.buffer.states[k::A, self.buffer.idx].reshape(eng.N, -1)
 
     _pending_obs = None
+
+    def _stacked_view(self, k: int):
+        """The policy input of agent slot k -- the previous n_frames-1 observations followed by the one `pov()` just
+        produced (treasurehunt/agents.py:34-41) -- as a ZERO-COPY view of the ring, or None when the frames are not
+        adjacent in memory.  In the agent-major ring the slots of a row are contiguous, and the kernel has just written
+        the observation into the slot at the write head, so frames [idx-(F-1), idx] of a row are one run of F*obs floats
+        (`torch.cat` of the same frames copies N*F*obs floats per turn: 0.3 ms at 262144 x 3 frames).  The view is
+        row-strided; the caller must not write to it."""
+        buf = self.buffer
+        F1 = buf.n_frames - 1
+        if F1 == 0 or self._obs_fixed is not None or buf.layout != "agent" or buf.idx < F1:
+            return None
+        A = len(self.agents)
+        return buf.states[k::A, buf.idx - F1: buf.idx + 1].reshape(self.engine.N, -1)
 
     def _act_slot(self, k: int, action) -> torch.Tensor:
         eng = self.engine

@@ -523,10 +523,12 @@ def test_uint8_action_tapes_equal_int32(A, H, lpe, cuda_device):
             assert torch.equal(outs[mode][3][k], outs["i32"][3][k])
 
 
-def test_turn_graph_equals_eager_split_phase(cuda_device):
+@pytest.mark.parametrize("per_slot", [False, True])
+def test_turn_graph_equals_eager_split_phase(per_slot, cuda_device):
     """`Environment.enable_turn_graph()`: one whole split-phase turn (per agent slot: observe, frame stacking, the
-    policy, act) captured as a CUDA graph with device-resident tick / ring slot.  Replays must equal the eager
-    split-phase path turn for turn, across episode boundaries (reset, add_empty) and a ring wrap."""
+    policy, act) captured as a CUDA graph with device-resident tick / ring slot -- one graph, or one per ring slot
+    reading the observation straight from the ring.  Replays must equal the eager split-phase path turn for turn,
+    across episode boundaries (reset, add_empty) and a ring wrap."""
     from sorrel_b200.models import BaseModel
 
     class ObsPolicy(BaseModel):
@@ -543,7 +545,7 @@ def test_turn_graph_equals_eager_split_phase(cuda_device):
         for _ in range(3):
             env.take_turn()  # eager turns first: the graph starts from a non-trivial clock
         if graph:
-            env.enable_turn_graph()  # (runs one eager turn itself, then captures)
+            env.enable_turn_graph(per_slot=per_slot)  # (runs one eager turn itself, then captures)
         else:
             env.take_turn()
         for _ in range(9):
@@ -563,3 +565,33 @@ def test_turn_graph_equals_eager_split_phase(cuda_device):
     assert torch.equal(e.buffer.rewards, g.buffer.rewards)
     assert torch.equal(e.buffer.extra_data["positions"], g.buffer.extra_data["positions"])
     assert int((e.buffer.actions != 0).sum()) > 0  # the policy did act
+
+
+def test_stacked_view_equals_concatenated_frames(cuda_device):
+    """Agent.get_action's zero-copy frame stack (a row-strided view of the agent-major ring) holds exactly what the
+    reference builds with np.vstack((prev_states, state)) (treasurehunt/agents.py:34-41); where the frames are not
+    adjacent (ring wrap) the concatenating path is taken."""
+    from sorrel_b200.models import BaseModel
+
+    seen = []
+
+    class Recorder(BaseModel):
+        def take_action(self, state):
+            seen.append(state)
+            return torch.zeros(state.shape[0], dtype=torch.int32, device=state.device)
+
+    N = 9
+    env, _ = _make(N, 5, model_factory=lambda inp, na: Recorder(inp, na, memory_size=8, n_frames=3), num_agents=1)
+    assert env.buffer.layout == "agent" and len(env.agents) == 1
+    env.add_empty()
+    views = 0
+    for t in range(13):  # crosses the ring wrap (capacity 8)
+        idx = env.buffer.idx
+        seen.clear()
+        env.take_turn()
+        (state,) = seen
+        prev = [env.buffer.states[:, (idx - 2 + f) % 8] for f in range(2)]
+        want = torch.cat(prev + [env.buffer.states[:, idx]], dim=1)
+        assert torch.equal(state, want), f"turn {t}, head {idx}"
+        views += int(not state.is_contiguous())
+    assert views >= 6  # most turns took the zero-copy path

@@ -170,13 +170,18 @@ traffic = 6.1 TB/s, DRAM 75 % busy); config 3 (slot-major ring, six separate run
 |---|---|---|
 | 4096 × 1 agent | {l4['eager']['ms_per_turn']:.3f} ms per turn | **{l4['ms_per_step']:.3f} ms** |
 | 16384 × 8 agents | {l3['eager']['ms_per_turn']:.3f} ms | **{l3['ms_per_step']:.3f} ms** |
-| 2^20 × 1 agent | **{l1['eager']['ms_per_turn']:.3f} ms** | {l1['ms_per_step']:.3f} ms (the captured turn writes every row twice — ring slot and the fixed tensor the policy reads —, which costs more than the launch gaps it removes at this size) |
+| 2^20 × 1 agent | {l1['eager']['ms_per_turn']:.3f} ms | **{l1['ms_per_step']:.3f} ms** (one graph per ring slot; kernel-bound: sweep + observe launch 0.37 ms, act-only launch 0.06 ms) |
 
-Second half of round 2, same command: 1.082 / 0.986 ms (eager / graph) at 2^20 × 1 → 0.954 / 0.859 with the act-only
-launch (the last launch of a turn only moves one agent: one thread per instance on the planes in place, 57 µs instead of
-a full staging round trip) → **0.468 / 0.642** once `Agent.get_action` no longer concatenates an EMPTY frame stack with
-the observation when `n_frames == 1` (`torch.cat` still copied every row: sixteen 26-µs copy kernels = 630 MB per turn,
-found with an ncu launch list of the turn); 16384 × 8: 0.216 → 0.127 ms per turn in graph mode.
+Second half of round 2, same command, 2^20 × 1 (eager / graph): 1.082 / 0.986 ms → 0.954 / 0.859 with the act-only launch
+(the last launch of a turn only moves one agent: one thread per instance on the planes in place, 57 µs instead of a full
+staging round trip) → 0.468 / 0.642 once `Agent.get_action` no longer concatenates an EMPTY frame stack with the
+observation when `n_frames == 1` (`torch.cat` still copied every row: sixteen 26-µs copy kernels = 630 MB per turn, found
+with an ncu launch list of the turn) → **0.467 / 0.471** with `enable_turn_graph(per_slot=True)`: one captured graph per
+ring slot with that slot's addresses baked in, so the policy reads the observation from the ring row the kernel wrote
+and the captured turn stops writing every row twice.  16384 × 8: 0.216 → 0.117 ms per turn (graph).  With stacked frames
+(262144 × 1, `n_frames = 3`): 0.529 / 0.532 → **0.215 / 0.166 ms** — in the agent-major ring the frames of a row are
+adjacent, so the policy input is a zero-copy row-strided view of the ring instead of a `torch.cat` of N × F × obs floats
+per turn (`Environment._stacked_view`, `test_stacked_view_equals_concatenated_frames`).
 
 ### Multi-GPU (builder runs on one 8-GPU box, `r02_scale_g*.json`; the driver's SCALE file is the record)
 
