@@ -502,6 +502,9 @@ constexpr int OBS_THREADS = 256;
 #ifndef SB_OBS_PIPELINED
 #define SB_OBS_PIPELINED 1
 #endif
+#ifndef SB_OBS_SEG
+#define SB_OBS_SEG 1
+#endif
 #ifndef SB_OBS_MINB
 #define SB_OBS_MINB 6  // resident blocks per SM the register allocation is sized for (40 registers)
 #endif
@@ -513,7 +516,7 @@ constexpr int OBS_THREADS = 256;
 // ROWS: gather the window row by row (scatter_rows_onehot) from the planes in global memory.  The row gather may touch
 // a few bytes before / after an instance's planes, so the first and the last instance of the batch (whose neighbours
 // are outside the allocation) take the cell-wise path; the choice is made per warp (both halves agree).
-template <bool NP1, int LANES, bool ROWS = false>
+template <bool NP1, int LANES, int ROWS = 0>  // ROWS: 0 cell-wise, 1 one lane per window row, 2 row segments
 __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
     observe_kernel(const __grid_constant__ SbDev d, const uint8_t* __restrict__ grid,
                    const int32_t* __restrict__ agent_pos, float* __restrict__ out, int stage_bytes, int fast,
@@ -549,9 +552,10 @@ __global__ void __launch_bounds__(OBS_THREADS, SB_OBS_MINB)
     float* dst = valid ? out + (size_t)pair * d.obs_size : nullptr;
     if (fast) {
       bool rows = false;
-      if constexpr (ROWS) rows = __all_sync(0xFFFFFFFFu, !valid || (env > 0 && env + 1 < (unsigned long long)d.N));
-      if (ROWS && rows) {
-        emit_onehot_row<LANES, NP1, 1, 1>(d, genv, ktab, stage_raw, y, x, dst, lane);
+      if constexpr (ROWS != 0)
+        rows = __all_sync(0xFFFFFFFFu, !valid || (env > 0 && env + 1 < (unsigned long long)d.N));
+      if (ROWS != 0 && rows) {
+        emit_onehot_row<LANES, NP1, 1, ROWS>(d, genv, ktab, stage_raw, y, x, dst, lane);
       } else {
         // window loads batched: 2 per lane cover a 5x5 window with 16 lanes, 4 per lane a 9x9 / 11x11 one with 32
         emit_onehot_row<LANES, NP1, (LANES == 16 ? 2 : 4)>(d, genv, ktab, stage_raw, y, x, dst, lane);
@@ -971,7 +975,11 @@ int launch_observe(const SbDev& d, const uint8_t* grid, const int32_t* agent_pos
     };
     return d.S5 == d.S ? launch_rows(observe_rows_kernel<false>) : launch_rows(observe_rows_kernel<true>);
   }
-  if (rows) return launch(observe_kernel<true, 16, true>);
+  if (rows) return launch(observe_kernel<true, 16, 1>);
+  // windows wider than 16 (19x19: the other reading of config 4's "9x9 vision radius"): 32 lanes per pair, each taking
+  // row SEGMENTS (scatter_rows_onehot_seg: 19x19 = 76 units of 5 / 4 cells, three single-step trips) instead of 361
+  // cell-wise visits
+  if (SB_OBS_SEG && np1 && d.rowwise_ok && d.S > 16 && lanes == 32) return launch(observe_kernel<true, 32, 2>);
   if (lanes == 16) return np1 ? launch(observe_kernel<true, 16>) : launch(observe_kernel<false, 16>);
   return np1 ? launch(observe_kernel<true, 32>) : launch(observe_kernel<false, 32>);
 }

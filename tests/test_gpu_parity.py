@@ -450,10 +450,11 @@ def test_observe_random(general, cuda_device):
 
 @pytest.mark.parametrize("H,W,v,A,N", [(9, 9, 4, 3, 5), (16, 23, 3, 6, 9), (21, 21, 5, 4, 37), (33, 18, 6, 7, 11),
                                        (40, 40, 7, 9, 6), (21, 21, 2, 8, 40), (128, 128, 4, 64, 3),
-                                       (21, 21, 2, 3, 5), (12, 12, 1, 3, 7), (15, 14, 2, 1, 9)])
+                                       (21, 21, 2, 3, 5), (12, 12, 1, 3, 7), (15, 14, 2, 1, 9),
+                                       (40, 44, 9, 5, 7), (45, 41, 10, 3, 4), (36, 36, 8, 8, 5)])
 def test_standalone_observe_all_window_widths(H, W, v, A, N, cuda_device):
     """`sb_observe` (the bulk-async kernel for small rows -- whole and short last tiles: odd pair counts --, the
-    software-pipelined row-wise kernel for 7..16-wide windows, the plain one otherwise) on worlds
+    software-pipelined row-wise kernel for 7..16-wide windows, row segments on 32 lanes for wider ones) on worlds
     without walls, with agents parked on corners, edges and the interior of the FIRST and LAST instance as well (the
     row gather may touch bytes outside an instance's planes: guarded at the ends of the allocation), several launches
     back to back (the staging rows must come back zeroed)."""

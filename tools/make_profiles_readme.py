@@ -126,6 +126,7 @@ before).  Rejected: 12 agent slots per block in 31 KB (7 blocks per SM: 2 waves 
 | 262144 × 8 agents, 5×5 windows | 0.407 ms (0.52) | **0.333 ms (0.63)** |
 | 65536 × 4 agents, 32×32 maps, 7×7 windows (1176-byte rows, tiles of 2) | **0.080 ms (0.72)** | 0.085 ms (two halves of a warp per tile) |
 | 4096 × 64 agents, 128×128 maps, 9×9 windows (1944-byte rows, tiles of 2) | **0.136 ms (0.65)** | 0.142 ms (three blocks per SM); 0.137 ms with the two halves of a warp filling one tile |
+| 4096 × 64 agents, 128×128 maps, 19×19 windows (8664-byte rows) | cell-wise 0.505 ms (0.71) → **row segments on 32 lanes 0.476 ms (0.75)** | — |
 
 The bulk-async kernel (`observe_bulk_kernel`: M rows = a multiple of 16 bytes scattered as f32 into a double-buffered
 shared-memory tile, ONE `cp.async.bulk.global.shared::cta` per tile — `UBLKCP.G.S` in the SASS —, tiles zeroed on reuse
