@@ -332,7 +332,7 @@ __device__ __forceinline__ void scatter_cols_multi(const SbDev& d, const uint8_t
 #define SB_STREAM_UNROLL 4  // vectors per trip of the stream-out loop of long rows
 #endif
 #ifndef SB_STREAM_LONG
-#define SB_STREAM_LONG 64  // one-plane worlds: rows of at least this many 16-byte vectors (9x9 windows: 121) take it too
+#define SB_STREAM_LONG 64  // rows of at least this many 16-byte vectors (9x9 windows: 121; cleanup: 275) take it
 #endif
 template <int LANES, bool NP1, int NB = 1, int ROWWISE = 0>
 __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* genv, const uint32_t* ktab,
@@ -436,7 +436,10 @@ __device__ __forceinline__ void emit_onehot_row(const SbDev& d, const uint8_t* g
 #if SB_STREAM_UNROLL > 1
       // long rows (cleanup: 275 vectors): several vectors per trip, loads first (measured: cleanup 9.64 -> 9.55 ms;
       // the short rows of one-plane worlds gain nothing or lose, so they keep the simple loop)
-      for (; (!NP1 || nvec >= SB_STREAM_LONG) && qv + (SB_STREAM_UNROLL - 1) * LANES < nvec;
+      // (compile-time choice: the extra loop in the one-plane step_kernel variants cost the sparse sampler 8 % at
+      // config 3 -- registers / instruction cache -- even when it was skipped at run time)
+      constexpr bool kLongRows = !NP1 || ROWWISE == 2;
+      for (; kLongRows && nvec >= SB_STREAM_LONG && qv + (SB_STREAM_UNROLL - 1) * LANES < nvec;
            qv += SB_STREAM_UNROLL * LANES) {
         uint2 w[SB_STREAM_UNROLL];
 #pragma unroll
