@@ -20,6 +20,12 @@
 // __syncwarp(): every phase that lets ONE lane mutate the instance (a move, a beam, a hand-over) is fenced from the
 // phases in which all lanes read it.
 //
+// Worlds with several stored planes (cleanup, iowa) gather their windows by row segments with byte-permute channel
+// lookups and ordered stores of plane counts (`scatter_cols_multi`); their sweep classifies cells four at a time.
+// A split-phase launch that only moves one agent takes `act_only_kernel` (one thread per instance, planes in place).
+// The standalone observation (`sb_observe`) has three forms: bulk-async stores of whole tiles of small rows
+// (`observe_bulk_kernel`), a software-pipelined row-wise kernel for 7..16-wide windows, and `observe_kernel`.
+//
 // Large maps with many agents (16..64 agents, planes of more than 4 KB) take `step_kernel_block` further down: one
 // BLOCK per instance, the plane staged in shared memory, up to sixteen mutually independent agents observed and moved
 // at once (dependency levels keep the list order of environment.py:92).  The older form of that idea -- planes used
