@@ -55,6 +55,7 @@ used as bench values; `bench.py` times with CUDA events.  **Round 2 first; the r
 | `r02_launches.csv` | every kernel launched by `python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --no-graphs` (`ncu --metrics gpu__time_duration.sum`), aggregated per kernel: `sb::step_kernel<4,1,1,1>` 53.9 % of device time (6.30 ms per launch), the sparse sampler the same command times beside it 31.9 % (4.79 ms), `sb::buffer_sample_staged_kernel` 10.6 % (0.70 ms), the ring fill of `add_empty` 2.6 %, reset 0.5 %, reward stats 0.2 %.  Within the per-cell half of the run the step kernel is 0.89 of the step = `roofline.step_kernel_share_of_step` from CUDA events (0.89). |
 | `r02_step_kernel_metrics.csv`, `_source_lines.csv` | `ncu --set full` of one steady-state launch of the headline kernel (2^20 instances × 25 fused turns): 6.26 ms, 5.35e9 warp-instructions (round 1: 7.60 ms, 6.50e9), DRAM 17.16 GB written + 0.69 GB read (35 % of peak busy), issue slots 74 %, 62 registers, 8 blocks / SM from both limits |
 | `r02_step_kernel_sweep_loop.sass` | SASS of the sweep loop of the headline kernel (two Philox chains, level-1 filter, ballot queue push) |
+| `r02_observe_bulk_kernel.sass` | SASS of the tile hand-over of `sb::observe_bulk_kernel` (`DEPBAR.LE SB0` = bulk wait_group.read, `FENCE.VIEW.ASYNC.S`, `UBLKCP.G.S` = one bulk-async store per tile of rows) |
 | `r02_sparse_kernel_*` | the same shape with the sparse sampler (`step_kernel<4,3,1,1>`) |
 | `r02_c3_kernel_*` | BASELINE config 3 at its named size (16384 × 8 agents, slot-major ring, `step_kernel<8,1,1,1>`) |
 | `r02_c4_kernel_*` | BASELINE config 4 at its named size (2048 × 128×128 × 64 agents): `sb::step_kernel_block` |
