@@ -763,7 +763,6 @@ __global__ void __launch_bounds__(OBS_BULK_THREADS)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int LANES = OBS_ROW_LANES;
   const int lane = threadIdx.x & (LANES - 1);
-  constexpr int P = 1;
   const int M = rows_per_tile, tile_floats = M * d.obs_size;  // tile_floats * 4 is a multiple of 16
   const int stream_in_block = (int)(threadIdx.x / LANES);
   constexpr int streams_per_block = OBS_BULK_THREADS / LANES;
@@ -797,10 +796,9 @@ __global__ void __launch_bounds__(OBS_BULK_THREADS)
       }
     }
   };
-  auto advance = [&](unsigned long long& env, int& a) {  // P pairs further
-    a += P;
-    while (a >= d.A) {
-      a -= d.A;
+  auto advance = [&](unsigned long long& env, int& a) {
+    if (++a == d.A) {
+      a = 0;
       ++env;
     }
   };
@@ -810,16 +808,16 @@ __global__ void __launch_bounds__(OBS_BULK_THREADS)
   unsigned long long env_n = env_c;
   int a_n = a_c;
   advance(env_n, a_n);
-  int pos_c = load_pos(first), pos_n = load_pos(first + P);
+  int pos_c = load_pos(first), pos_n = load_pos(first + 1);
   uint32_t cw0[OBS_ROW_MAXG], cw1[OBS_ROW_MAXG], nw0[OBS_ROW_MAXG], nw1[OBS_ROW_MAXG];
   issue(env_c, pos_c, cw0, cw1);
 
-  const int steps_per_tile = M / P;            // rows of a tile this half fills
-  const unsigned steps = pairs_per_stream / P;  // pairs this half walks
+  const int steps_per_tile = M;            // rows of a tile
+  const unsigned steps = pairs_per_stream;  // pairs this group walks
   int rs = 0;          // step within the current tile
   unsigned tile = 0;   // tiles this stream has started
   for (unsigned k = 0; k < steps; ++k) {  // uniform trip count: both halves of a warp stay in step
-    const unsigned long long pair = first + (unsigned long long)k * P;
+    const unsigned long long pair = first + k;
     float* const buf = tiles + (tile & 1u) * tile_floats;
     if (rs == 0 && tile >= 2) {
       // this buffer held tile - 2: the engine must have finished READING it before it is zeroed and refilled
@@ -828,8 +826,8 @@ __global__ void __launch_bounds__(OBS_BULK_THREADS)
       for (int e = zl; e < tile_floats / 4; e += zn) reinterpret_cast<float4*>(buf)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
     }
-    issue(env_n, pos_n, nw0, nw1);                                   // the half's next pair: in flight during the work below
-    const int pos_nn = load_pos(pair + 2ull * (unsigned)P);  // ... and the one after
+    issue(env_n, pos_n, nw0, nw1);  // the next pair: in flight during the work below
+    const int pos_nn = load_pos(pair + 2);  // ... and the one after
     if (pos_c >= 0 && lane < d.S) {
       // ---- scatter row `lane` of the window (scatter_rows_onehot_impl on the words loaded one iteration ago) ----
       const int y = d.inv_W ? (int)__umulhi((uint32_t)pos_c, d.inv_W) : pos_c / d.W, x = pos_c - y * d.W;
