@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 # 2. full captures of the dominant kernels (steady-state launches)
 bash tools/gpu_ncu.sh ${TAG}_step_kernel
 bash tools/gpu_ncu.sh ${TAG}_sparse_kernel --rng sparse
-bash tools/gpu_ncu.sh ${TAG}_c2_kernel --config 2
+SKIP=3 bash tools/gpu_ncu.sh ${TAG}_c2_kernel --config 2   # (few launches: skip fewer)
 bash tools/gpu_ncu.sh ${TAG}_c3_kernel --config 3
 bash tools/gpu_ncu.sh ${TAG}_c4_kernel --config 4
 CMD2="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-alt --no-graphs --no-clocks"

@@ -57,6 +57,7 @@ used as bench values; `bench.py` times with CUDA events.  **Round 2 first; the r
 | `r02_step_kernel_sweep_loop.sass` | SASS of the sweep loop of the headline kernel (two Philox chains, level-1 filter, ballot queue push) |
 | `r02_observe_bulk_kernel.sass` | SASS of the tile hand-over of `sb::observe_bulk_kernel` (`DEPBAR.LE SB0` = bulk wait_group.read, `FENCE.VIEW.ASYNC.S`, `UBLKCP.G.S` = one bulk-async store per tile of rows) |
 | `r02_sparse_kernel_*` | the same shape with the sparse sampler (`step_kernel<4,3,1,1>`) |
+| `r02_c2_kernel_*` | BASELINE config 2 at its named size (4096 × 1 agent, 100 fused turns, `step_kernel<16,1,1,1>`): 0.29 ms, 0.43 waves, 13 warps per SM, issue slots 55 %, 410 warp-instructions per env-turn (16 lanes per instance: twice the 4-lane count) — a batch this small is latency- and issue-bound, not HBM-bound (180 MB written) |
 | `r02_c3_kernel_*` | BASELINE config 3 at its named size (16384 × 8 agents, slot-major ring, `step_kernel<8,1,1,1>`) |
 | `r02_c4_kernel_*` | BASELINE config 4 at its named size (2048 × 128×128 × 64 agents): `sb::step_kernel_block` |
 | `r02_cleanup_kernel_*` | the cleanup example (`step_kernel<16,2,0,1>`, generic variant: column gather, byte-SIMD rule classification, 79 registers) |

@@ -120,6 +120,7 @@ print(ps)
 # per-shape DRAM traffic (bench.py `roofline.traffic` / `frac_dram`): profiles/traffic.json, keyed by bench.shape_key
 SHAPES = {"step_kernel": "treasurehunt:21:1:v2:n1048576:t25:c32:philox",
           "sparse_kernel": "treasurehunt:21:1:v2:n1048576:t25:c32:sparse",
+          "c2_kernel": "treasurehunt:21:1:v2:n4096:t100:c32:philox",
           "c3_kernel": "treasurehunt:21:8:v2:n16384:t25:c32:philox",
           "c4_kernel": "treasurehunt:128:64:v4:n2048:t10:c16:philox",
           "cleanup_kernel": "cleanup:21:10:v5:n32768:t25:c8:philox"}
